@@ -1,0 +1,271 @@
+/*
+ * fm3d.h -- C-ABI of libfm3d: the B200 (sm_100a) implementation of the
+ * match -> triangulate -> normal-optimise -> patch-extract hot path of
+ * caomw/3DFeatureMatcher.
+ *
+ * The reference has no FFI of its own: its boundary is the public surface of four
+ * C++ classes.  Every entry point below names the reference method(s) it replaces
+ * (file:line under the reference tree).  The class adapters in
+ * 3dfeaturematcher_b200/host/ (same class names and signatures as the reference) and
+ * the ctypes binding in 3dfeaturematcher_b200/api.py are thin wrappers over exactly
+ * these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays row-major and caller-allocated;
+ *   - functions without a _dev suffix take HOST pointers, copy in/out on the context's
+ *     stream and return after the result is in the caller's buffers;
+ *   - functions with a _dev suffix take DEVICE pointers (memory of the context's GPU),
+ *     enqueue work on the context's stream and return without synchronising
+ *     (fm3d_sync waits);
+ *   - every function returns FM3D_OK (0) or a negative fm3d_status; fm3d_last_error
+ *     gives the text.  Nothing calls exit(), nothing throws across the boundary;
+ *   - there is no CPU implementation behind any of these calls: without a usable
+ *     sm_100 device fm3d_ctx_create fails with FM3D_ERR_NO_DEVICE.
+ *   - one fm3d_ctx per host thread / per GPU; a context is not re-entrant.
+ */
+#ifndef FM3D_H_
+#define FM3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM3D_VERSION 100 /* 0.1.0 */
+
+typedef struct fm3d_ctx fm3d_ctx;
+
+typedef enum fm3d_status {
+    FM3D_OK = 0,
+    FM3D_ERR_INVALID_ARG = -1,
+    FM3D_ERR_CUDA = -2,
+    FM3D_ERR_NO_DEVICE = -3,
+    FM3D_ERR_STATE = -4,       /* camera / images / pose not set yet */
+    FM3D_ERR_UNSUPPORTED = -5,
+    FM3D_ERR_NOMEM = -6
+} fm3d_status;
+
+/* Per-feature outcome of the normal optimiser.  The reference silently erases a failed
+ * feature from points3D ("Bad point!" / "Not enough pixels!",
+ * Triangulator/normaloptimizer.cpp:364-382); here every feature keeps its index and
+ * gets a status instead. */
+typedef enum fm3d_feature_status {
+    FM3D_FEAT_OK = 0,
+    FM3D_FEAT_NO_PIXELS = 1,  /* m_dat == 0,                     normaloptimizer.cpp:364-369 */
+    FM3D_FEAT_ABORT_BBOX = 2, /* isInBoundingBox failed,         singlecameratriangulator.cpp:557-560 */
+    FM3D_FEAT_ABORT_PIXEL = 3,/* isPixelGood failed (img 1 or 2), singlecameratriangulator.cpp:580-584,623-626 */
+    FM3D_FEAT_ABORT_NAN = 4   /* NaN normal / NaN plane point,   normaloptimizer.cpp:81-85, singlecameratriangulator.cpp:465-469 */
+} fm3d_feature_status;
+
+/* Semantics of the unqualified abs() in the angle-penalty wall of evaluateNormal
+ * (Triangulator/normaloptimizer.cpp:133-138). */
+typedef enum fm3d_penalty_mode {
+    FM3D_PENALTY_FABS = 0,    /* abs() == fabs(): the source as compiled by g++ >= 6 */
+    FM3D_PENALTY_INT_ABS = 1, /* abs() == int abs(int): pre-C++11 toolchains */
+    FM3D_PENALTY_OFF = 2
+} fm3d_penalty_mode;
+
+/* ------------------------------------------------------------------ context ---- */
+
+int fm3d_version(void);
+
+/* Creates a context bound to CUDA device `device` (one stream, scratch buffers). */
+int fm3d_ctx_create(int device, fm3d_ctx** out);
+void fm3d_ctx_destroy(fm3d_ctx* ctx);
+const char* fm3d_last_error(const fm3d_ctx* ctx);
+int fm3d_sync(fm3d_ctx* ctx);
+/* cudaStream_t of the context, as an opaque pointer (for event timing by the caller). */
+void* fm3d_stream(fm3d_ctx* ctx);
+int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                     char* name, int name_len);
+
+/* Tuning / mode knobs that are not part of the reference's settings.yml:
+ *   "geometry_f32"      0 (default): fp64 ray/plane/projection arithmetic as the reference;
+ *                       1: fp32 geometry (faster, normals agree to <<0.5 deg)
+ *   "matcher_tensor"    1 (default): use the tcgen05 contraction when descriptors are
+ *                       integer-valued in [0,255] and dim == 128;  0: always the exact
+ *                       CUDA-core fp32 path
+ *   "lm_patience"       lm_control.patience / maxcall (default 100 -> 300 evaluations/level)
+ *   "normals_threads"   threads per CTA of the normal optimiser (default 512)
+ * Returns FM3D_ERR_INVALID_ARG for an unknown key. */
+int fm3d_set_option(fm3d_ctx* ctx, const char* key, double value);
+int fm3d_get_option(fm3d_ctx* ctx, const char* key, double* value);
+
+/* Counters of the last call that launched kernels on this context (for benchmarking):
+ * number of kernel launches and of bulk-copy (memcpy/memset) operations. */
+int fm3d_get_launch_counters(fm3d_ctx* ctx, int64_t* kernel_launches, int64_t* copies);
+
+/* ------------------------------------------------------------------- camera ---- */
+
+/* Replaces the camera part of SingleCameraTriangulator::SingleCameraTriangulator
+ * (Triangulator/singlecameratriangulator.cpp:67-112): K row-major 3x3,
+ * dist = (k1,k2,p1,p2,k3) in OpenCV order (settings.yml names them k0,k1,p1,p2,k2),
+ * and the depth gate zThresholdMin/zThresholdMax. */
+int fm3d_set_camera(fm3d_ctx* ctx, const double K[9], const double dist[5],
+                    double z_min, double z_max);
+
+/* Replaces the result of SingleCameraTriangulator::setg12
+ * (Triangulator/singlecameratriangulator.cpp:123-143): g12 row-major 4x4,
+ * X_cam2 = R * X_cam1 + t.  Composing g12 from (T1,T2,rodrigues1,rodrigues2,g_IC) is
+ * host arithmetic done by the class adapter (fm3d_compose_g12 below). */
+int fm3d_set_g12(fm3d_ctx* ctx, const double g12[16]);
+
+/* Host helper (no GPU work): g12 = g_IC^-1 * g2^-1 * g1 * g_IC with g_i = [Rodrigues(r_i) | T_i]
+ * (singlecameratriangulator.cpp:123-143, tools.cpp:87-99). */
+int fm3d_compose_g12(const double T1[3], const double T2[3], const double rod1[3],
+                     const double rod2[3], const double rodIC[3], const double tIC[3],
+                     double g12_out[16]);
+
+/* ----------------------------------------------------------------- matching ---- */
+
+/* Exact brute-force 2-nearest-neighbour search, query = frame A, train = frame B.
+ * Replaces matcher_->knnMatch(desc_a, desc_b, matches, 2)
+ * (DescriptorsMatcher/descriptorsmatcher.cpp:84-85,101,117) with the exact search the
+ * north star asks for (the reference's FLANN index is approximate and randomised).
+ *   q: nq x dim float32, t: nt x dim float32.
+ *   idx[2*i+k]  train index of the k-th neighbour of query i (-1 if nt <= k)
+ *   dist[2*i+k] L2 distance (square-rooted, float32) as cv::DMatch::distance
+ * Ties are broken by the lower train index. */
+int fm3d_match_knn2_f32(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt,
+                        int dim, int32_t* idx, float* dist);
+
+/* Same for binary descriptors (ORB 32 B, BRISK/FREAK 64 B): Hamming distance as float. */
+int fm3d_match_knn2_hamming(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t,
+                            int nt, int nbytes, int32_t* idx, float* dist);
+
+/* Replaces the matching part of DescriptorsMatcher::compareWithNNDR
+ * (descriptorsmatcher.cpp:117-129): keep the best match of query i iff it has two
+ * neighbours and (double)d0 <= eps * (double)d1.  Output is ordered by ascending query
+ * index; *nmatch entries are written to qidx/tidx/dist (capacity nq each).
+ * If mutual != NULL the role-swapped search is also run and mutual[j] = 1 iff the best
+ * train of qidx[j] has qidx[j] as its own best query (the fused cross-check; the
+ * reference's crosscompare, :74-87, only returns both raw lists). */
+int fm3d_match_nndr_f32(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt,
+                        int dim, double eps, int32_t* qidx, int32_t* tidx, float* dist,
+                        uint8_t* mutual, int* nmatch);
+int fm3d_match_nndr_hamming(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t,
+                            int nt, int nbytes, double eps, int32_t* qidx, int32_t* tidx,
+                            float* dist, uint8_t* mutual, int* nmatch);
+
+/* Device-pointer variants (asynchronous).  nmatch_dev is a device int. */
+int fm3d_match_knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt,
+                            int dim, int32_t* idx, float* dist);
+int fm3d_match_knn2_hamming_dev(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t,
+                                int nt, int nbytes, int32_t* idx, float* dist);
+int fm3d_nndr_filter_dev(fm3d_ctx* ctx, const int32_t* idx, const float* dist, int nq,
+                         double eps, int32_t* qidx, int32_t* tidx, float* dist_out,
+                         int* nmatch_dev);
+
+/* ------------------------------------------------------------ triangulation ---- */
+
+/* Replaces SingleCameraTriangulator::setKeypoints + ::triangulate
+ * (singlecameratriangulator.cpp:145-230): for match i take kp1[qidx[i]], kp2[tidx[i]]
+ * (float x,y pairs, as cv::KeyPoint::pt), undistort both (5 fixed-point iterations, as
+ * cv::undistortPoints), 4x4 DLT with P1=[I|0], P2=g12[0:3,:], dehomogenise, and keep the
+ * point iff z_min <= Z < z_max.
+ *   xyz_all  n x 3 : dehomogenised point of every match (also the gated-out ones)
+ *   mask     n     : 1 = inlier (the reference's outliersMask)
+ *   xyz      n x 3 : order-preserving compaction of the inliers (first *ninl rows valid)
+ *   src_idx  n     : match index of every compacted row (nullable)
+ * Pass qidx == tidx == NULL to use kp1[i], kp2[i] directly. */
+int fm3d_triangulate(fm3d_ctx* ctx, const float* kp1, int n1, const float* kp2, int n2,
+                     const int32_t* qidx, const int32_t* tidx, int n, double* xyz_all,
+                     uint8_t* mask, double* xyz, int32_t* src_idx, int* ninl);
+int fm3d_triangulate_dev(fm3d_ctx* ctx, const float* kp1, int n1, const float* kp2, int n2,
+                         const int32_t* qidx, const int32_t* tidx, int n, double* xyz_all,
+                         uint8_t* mask, double* xyz, int32_t* src_idx, int* ninl_dev);
+
+/* cv::undistortPoints as called at singlecameratriangulator.cpp:169-170,542 (no R, no P:
+ * normalised ideal coordinates), exposed for parity tests of the primitive. */
+int fm3d_undistort_points(fm3d_ctx* ctx, const double* pts, int n, double* out);
+
+/* ------------------------------------------------------------------- images ---- */
+
+/* Replaces NormalOptimizer::setImages / compute_pyramids
+ * (Triangulator/normaloptimizer.cpp:191-221) and SingleCameraTriangulator::setImages
+ * (:116-120): uploads both 8-bit images (row stride `stride` bytes) and builds
+ * `pyramids` cv::pyrDown levels of each on the GPU (pyramids+1 images per view). */
+int fm3d_set_images(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int w, int h,
+                    int stride, int pyramids);
+int fm3d_set_images_dev(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int w,
+                        int h, int stride, int pyramids);
+/* Copies pyramid level `level` of image `image` (1 or 2) to the host (tightly packed). */
+int fm3d_get_pyramid_level(fm3d_ctx* ctx, int image, int level, uint8_t* out, int* w,
+                           int* h);
+
+/* ------------------------------------------------------- normal optimisation ---- */
+
+/* Replaces NormalOptimizer::computeOptimizedNormals (normaloptimizer.cpp:321-452) with
+ * everything below it: extractPixelsContour (singlecameratriangulator.cpp:341-397),
+ * optimize_pyramid/optimize (normaloptimizer.cpp:223-292), lmmin (lmfit), evaluateNormal
+ * (normaloptimizer.cpp:65-149) and the three per-evaluation helpers
+ * (singlecameratriangulator.cpp:530-665).
+ *   xyz        n x 3  feature points in camera-1 coordinates
+ *   pixels_ray        Neighborhoods.pixelsRay   (disc radius in image-1 pixels)
+ *   epsilon_lmmin     Neighborhoods.epsilonLMMIN (lm_control.epsilon)
+ *   penalty_mode      fm3d_penalty_mode
+ *   normals    n x 3  refined unit normals (initial guess P/|P| if the feature failed)
+ *   status     n      fm3d_feature_status
+ *   nfev       n x (pyramids+1), column l = evaluations spent at pyramid level l (nullable)
+ *   npenalty   n      evaluations that entered the penalty branch (nullable)
+ *   cost       n      final sum of squared residuals at level 0 (nullable)
+ * The number of pyramid levels is the one given to fm3d_set_images. */
+int fm3d_optimize_normals(fm3d_ctx* ctx, const double* xyz, int n, int pixels_ray,
+                          double epsilon_lmmin, int penalty_mode, double* normals,
+                          int32_t* status, int32_t* nfev, int32_t* npenalty, double* cost);
+int fm3d_optimize_normals_dev(fm3d_ctx* ctx, const double* xyz, int n, int pixels_ray,
+                              double epsilon_lmmin, int penalty_mode, double* normals,
+                              int32_t* status, int32_t* nfev, int32_t* npenalty,
+                              double* cost);
+
+/* One evaluation of the cost the optimiser minimises (evaluateNormal,
+ * normaloptimizer.cpp:65-149) for given normals at pyramid level `level`:
+ * cost[i] = sum of squared weighted residuals, m[i] = number of disc pixels,
+ * status[i] as above.  Used by parity tests and by the dense candidate-normal sweep. */
+int fm3d_evaluate_normals(fm3d_ctx* ctx, const double* xyz, const double* normals_phi_theta,
+                          int n, int pixels_ray, int level, int penalty_mode, double* cost,
+                          int32_t* m, int32_t* status);
+
+/* Replaces NormalOptimizer::computeFeaturesFrames (normaloptimizer.cpp:454-505):
+ * frame = [x y z P; 0 0 0 1], z = n, x = normalize(g x z), y = normalize(z x x),
+ * row-major 4x4 per feature.  gravity as NormalOptimizer::getGravity (:185-188). */
+int fm3d_feature_frames(fm3d_ctx* ctx, const double* xyz, const double* normals, int n,
+                        const double gravity[3], double* frames);
+int fm3d_feature_frames_dev(fm3d_ctx* ctx, const double* xyz, const double* normals, int n,
+                            const double gravity[3], double* frames);
+
+/* ---------------------------------------------------------- patch extraction ---- */
+
+/* Patch edge S = 2*floor(epsilon / (0.01*cmPerPixel))
+ * (Triangulator/neighborhoodsgenerator.cpp:136-137). */
+int fm3d_patch_size(double epsilon_m, double cm_per_pixel);
+
+/* Replaces NeighborhoodsGenerator::getReferenceSquaredNeighborhood
+ * (neighborhoodsgenerator.cpp:134-158) + SingleCameraTriangulator::
+ * projectReferencePointsToImageWithFrames (singlecameratriangulator.cpp:769-849): for
+ * every frame project the S x S metric grid on the feature plane into image 1 (with lens
+ * distortion), sample bilinearly and truncate to u8; 0 where the pixel is outside.
+ *   patches       n x S x S u8, patch(row=j, col=i) <- grid point (i,j)   (as the reference
+ *                 writes patch.at<uchar>(col,row))
+ *   image_points  n x S*S x 2 f64 in grid order idx = i*S + j (nullable: 16 B per pixel) */
+int fm3d_extract_patches(fm3d_ctx* ctx, const double* frames, int n, double epsilon_m,
+                         double cm_per_pixel, uint8_t* patches, double* image_points);
+int fm3d_extract_patches_dev(fm3d_ctx* ctx, const double* frames, int n, double epsilon_m,
+                             double cm_per_pixel, uint8_t* patches, double* image_points);
+
+/* Replaces SingleCameraTriangulator::projectPointsToImage
+ * (singlecameratriangulator.cpp:667-767) for explicit 3-D groups (n groups of S*S points,
+ * camera-1 coordinates) and either image (image = 1 or 2). */
+int fm3d_project_groups(fm3d_ctx* ctx, int image, const double* groups, int n, int S,
+                        uint8_t* patches, double* image_points);
+
+/* Replaces NeighborhoodsGenerator::computeSquareNeighborhoodsByNormals
+ * (neighborhoodsgenerator.cpp:76-132): out n x S*S x 3 = frame * (grid point, 1). */
+int fm3d_square_neighborhoods(fm3d_ctx* ctx, const double* frames, int n, double epsilon_m,
+                              double cm_per_pixel, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FM3D_H_ */
