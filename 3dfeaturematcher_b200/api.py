@@ -1,0 +1,312 @@
+"""ctypes binding of libfm3d.so (include/fm3d.h) -- the only way Python reaches the GPU path.
+
+There is no CPU implementation here: if libfm3d.so is missing or no sm_100 device is
+usable, construction of `Context` raises.  numpy arrays are used for the host-pointer entry
+points; the `*_dev` methods take raw device addresses (e.g. `torch.Tensor.data_ptr()`), enqueue
+on the context's stream and do not synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfm3d.so")
+
+FEAT_OK, FEAT_NO_PIXELS, FEAT_ABORT_BBOX, FEAT_ABORT_PIXEL, FEAT_ABORT_NAN = 0, 1, 2, 3, 4
+PENALTY_FABS, PENALTY_INT_ABS, PENALTY_OFF = 0, 1, 2
+
+_dp, _fp, _ip, _bp = (C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                      C.POINTER(C.c_uint8))
+
+# every symbol include/fm3d.h declares (tests/test_abi.py checks the library exports them all)
+SYMBOLS = [
+    "fm3d_version", "fm3d_ctx_create", "fm3d_ctx_destroy", "fm3d_last_error", "fm3d_sync",
+    "fm3d_stream", "fm3d_device_info", "fm3d_set_option", "fm3d_get_option",
+    "fm3d_get_launch_counters", "fm3d_set_camera", "fm3d_set_g12", "fm3d_compose_g12",
+    "fm3d_match_knn2_f32", "fm3d_match_knn2_hamming", "fm3d_match_nndr_f32",
+    "fm3d_match_nndr_hamming", "fm3d_match_knn2_f32_dev", "fm3d_match_knn2_hamming_dev",
+    "fm3d_nndr_filter_dev", "fm3d_triangulate", "fm3d_triangulate_dev", "fm3d_undistort_points",
+    "fm3d_set_images", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
+    "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_feature_frames",
+    "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
+    "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
+]
+
+
+class Fm3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfm3d error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libfm3d.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m 3dfeaturematcher_b200.build` "
+                               "(__graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.fm3d_last_error.restype = C.c_char_p
+        lib.fm3d_stream.restype = C.c_void_p
+        lib.fm3d_patch_size.argtypes = [C.c_double, C.c_double]
+        _lib = lib
+    return _lib
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def compose_g12(T1, T2, rod1, rod2, rodIC, tIC):
+    """SingleCameraTriangulator::setg12 host arithmetic (no GPU needed)."""
+    out = np.empty(16)
+    args = [_arr(x, np.float64) for x in (T1, T2, rod1, rod2, rodIC, tIC)]
+    rc = load_library().fm3d_compose_g12(*[_ptr(a, _dp) for a in args], _ptr(out, _dp))
+    if rc:
+        raise Fm3dError(rc, "fm3d_compose_g12")
+    return out.reshape(4, 4)
+
+
+def patch_size(epsilon_m, cm_per_pixel):
+    return load_library().fm3d_patch_size(float(epsilon_m), float(cm_per_pixel))
+
+
+class Context:
+    """One fm3d_ctx: one GPU, one stream."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.fm3d_ctx_create(int(device), C.byref(self._h))
+        if rc:
+            raise Fm3dError(rc, f"fm3d_ctx_create(device={device}) failed: no usable sm_100 GPU "
+                                "(libfm3d has no CPU path)")
+        self.device = device
+        self.levels = None
+        self.shape = None
+
+    def close(self):
+        if self._h:
+            self.lib.fm3d_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise Fm3dError(rc, self.lib.fm3d_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ context
+    def sync(self):
+        self._ck(self.lib.fm3d_sync(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.fm3d_stream(self._h)
+
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        name = C.create_string_buffer(256)
+        self._ck(self.lib.fm3d_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), name, 256))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+    def set_option(self, key, value):
+        self._ck(self.lib.fm3d_set_option(self._h, key.encode(), C.c_double(value)))
+
+    def get_option(self, key):
+        v = C.c_double()
+        self._ck(self.lib.fm3d_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def launch_counters(self):
+        k, c = C.c_int64(), C.c_int64()
+        self._ck(self.lib.fm3d_get_launch_counters(self._h, C.byref(k), C.byref(c)))
+        return k.value, c.value
+
+    # ------------------------------------------------------------------ camera
+    def set_camera(self, K, dist, z_min, z_max):
+        K, dist = _arr(K, np.float64).reshape(9), _arr(dist, np.float64).reshape(5)
+        self._ck(self.lib.fm3d_set_camera(self._h, _ptr(K, _dp), _ptr(dist, _dp), C.c_double(z_min), C.c_double(z_max)))
+
+    def set_g12(self, g12):
+        g = _arr(g12, np.float64).reshape(16)
+        self._ck(self.lib.fm3d_set_g12(self._h, _ptr(g, _dp)))
+
+    # ------------------------------------------------------------------ matching
+    def match_knn2_f32(self, q, t):
+        q, t = _arr(q, np.float32), _arr(t, np.float32)
+        nq, nt = q.shape[0], t.shape[0]
+        dim = q.shape[1] if q.ndim == 2 and q.shape[1] else (t.shape[1] if t.ndim == 2 else 1)
+        idx, dist = np.full((nq, 2), -1, np.int32), np.full((nq, 2), np.inf, np.float32)
+        self._ck(self.lib.fm3d_match_knn2_f32(self._h, _ptr(q, _fp), nq, _ptr(t, _fp), nt, max(dim, 1), _ptr(idx, _ip), _ptr(dist, _fp)))
+        return idx, dist
+
+    def match_knn2_hamming(self, q, t):
+        q, t = _arr(q, np.uint8), _arr(t, np.uint8)
+        nq, nt = q.shape[0], t.shape[0]
+        nb = q.shape[1] if q.ndim == 2 and q.shape[1] else (t.shape[1] if t.ndim == 2 else 32)
+        idx, dist = np.full((nq, 2), -1, np.int32), np.full((nq, 2), np.inf, np.float32)
+        self._ck(self.lib.fm3d_match_knn2_hamming(self._h, _ptr(q, _bp), nq, _ptr(t, _bp), nt, nb, _ptr(idx, _ip), _ptr(dist, _fp)))
+        return idx, dist
+
+    def match_nndr(self, q, t, eps, hamming=False, with_mutual=False):
+        dt = np.uint8 if hamming else np.float32
+        q, t = _arr(q, dt), _arr(t, dt)
+        nq, nt = q.shape[0], t.shape[0]
+        dim = q.shape[1] if q.ndim == 2 and q.shape[1] else (t.shape[1] if t.ndim == 2 else 1)
+        qi, ti = np.empty(nq, np.int32), np.empty(nq, np.int32)
+        d = np.empty(nq, np.float32)
+        mu = np.zeros(nq, np.uint8) if with_mutual else None
+        n = C.c_int(0)
+        if hamming:
+            rc = self.lib.fm3d_match_nndr_hamming(self._h, _ptr(q, _bp), nq, _ptr(t, _bp), nt, dim, C.c_double(eps),
+                                                  _ptr(qi, _ip), _ptr(ti, _ip), _ptr(d, _fp), _ptr(mu, _bp), C.byref(n))
+        else:
+            rc = self.lib.fm3d_match_nndr_f32(self._h, _ptr(q, _fp), nq, _ptr(t, _fp), nt, max(dim, 1), C.c_double(eps),
+                                              _ptr(qi, _ip), _ptr(ti, _ip), _ptr(d, _fp), _ptr(mu, _bp), C.byref(n))
+        self._ck(rc)
+        k = n.value
+        out = (qi[:k].copy(), ti[:k].copy(), d[:k].copy())
+        return out + (mu[:k].copy(),) if with_mutual else out
+
+    # ------------------------------------------------------------------ triangulation
+    def triangulate(self, kp1, kp2, qidx=None, tidx=None):
+        kp1, kp2 = _arr(kp1, np.float32).reshape(-1, 2), _arr(kp2, np.float32).reshape(-1, 2)
+        if qidx is not None:
+            qidx, tidx = _arr(qidx, np.int32), _arr(tidx, np.int32)
+            n = qidx.shape[0]
+        else:
+            n = kp1.shape[0]
+        xyz_all, xyz = np.empty((n, 3)), np.empty((n, 3))
+        mask, src = np.empty(n, np.uint8), np.empty(n, np.int32)
+        ninl = C.c_int(0)
+        self._ck(self.lib.fm3d_triangulate(self._h, _ptr(kp1, _fp), kp1.shape[0], _ptr(kp2, _fp), kp2.shape[0],
+                                           _ptr(qidx, _ip), _ptr(tidx, _ip), n, _ptr(xyz_all, _dp), _ptr(mask, _bp),
+                                           _ptr(xyz, _dp), _ptr(src, _ip), C.byref(ninl)))
+        k = ninl.value
+        return xyz_all, mask, xyz[:k].copy(), src[:k].copy()
+
+    def undistort_points(self, pts):
+        pts = _arr(pts, np.float64).reshape(-1, 2)
+        out = np.empty_like(pts)
+        self._ck(self.lib.fm3d_undistort_points(self._h, _ptr(pts, _dp), pts.shape[0], _ptr(out, _dp)))
+        return out
+
+    # ------------------------------------------------------------------ images
+    def set_images(self, img1, img2, pyramids):
+        img1, img2 = _arr(img1, np.uint8), _arr(img2, np.uint8)
+        assert img1.shape == img2.shape and img1.ndim == 2
+        h, w = img1.shape
+        self._ck(self.lib.fm3d_set_images(self._h, _ptr(img1, _bp), _ptr(img2, _bp), w, h, w, int(pyramids)))
+        self.levels, self.shape = int(pyramids), (h, w)
+
+    def set_images_dev(self, img1_ptr, img2_ptr, w, h, stride, pyramids):
+        self._ck(self.lib.fm3d_set_images_dev(self._h, C.c_void_p(img1_ptr), C.c_void_p(img2_ptr), w, h, stride, int(pyramids)))
+        self.levels, self.shape = int(pyramids), (h, w)
+
+    def get_pyramid_level(self, image, level):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.fm3d_get_pyramid_level(self._h, image, level, None, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        self._ck(self.lib.fm3d_get_pyramid_level(self._h, image, level, _ptr(out, _bp), C.byref(w), C.byref(h)))
+        return out
+
+    # ------------------------------------------------------------------ normals
+    def optimize_normals(self, xyz, pixels_ray, epsilon_lmmin=1e-10, penalty_mode=PENALTY_FABS):
+        xyz = _arr(xyz, np.float64).reshape(-1, 3)
+        n = xyz.shape[0]
+        L1 = (self.levels or 0) + 1
+        normals, status = np.empty((n, 3)), np.empty(n, np.int32)
+        nfev, npen, cost = np.zeros((n, L1), np.int32), np.zeros(n, np.int32), np.empty(n)
+        self._ck(self.lib.fm3d_optimize_normals(self._h, _ptr(xyz, _dp), n, int(pixels_ray), C.c_double(epsilon_lmmin),
+                                                int(penalty_mode), _ptr(normals, _dp), _ptr(status, _ip), _ptr(nfev, _ip),
+                                                _ptr(npen, _ip), _ptr(cost, _dp)))
+        return {"normals": normals, "status": status, "nfev": nfev, "npenalty": npen, "cost": cost}
+
+    def evaluate_normals(self, xyz, phi_theta, pixels_ray, level, penalty_mode=PENALTY_FABS):
+        xyz = _arr(xyz, np.float64).reshape(-1, 3)
+        pt = _arr(phi_theta, np.float64).reshape(-1, 2)
+        n = xyz.shape[0]
+        cost, m, status = np.empty(n), np.empty(n, np.int32), np.empty(n, np.int32)
+        self._ck(self.lib.fm3d_evaluate_normals(self._h, _ptr(xyz, _dp), _ptr(pt, _dp), n, int(pixels_ray), int(level),
+                                                int(penalty_mode), _ptr(cost, _dp), _ptr(m, _ip), _ptr(status, _ip)))
+        return cost, m, status
+
+    def feature_frames(self, xyz, normals, gravity):
+        xyz = _arr(xyz, np.float64).reshape(-1, 3)
+        normals = _arr(normals, np.float64).reshape(-1, 3)
+        g = _arr(gravity, np.float64).reshape(3)
+        n = xyz.shape[0]
+        frames = np.empty((n, 4, 4))
+        self._ck(self.lib.fm3d_feature_frames(self._h, _ptr(xyz, _dp), _ptr(normals, _dp), n, _ptr(g, _dp), _ptr(frames, _dp)))
+        return frames
+
+    # ------------------------------------------------------------------ patches
+    def extract_patches(self, frames, epsilon_m, cm_per_pixel, want_points=True):
+        frames = _arr(frames, np.float64).reshape(-1, 16)
+        n = frames.shape[0]
+        S = patch_size(epsilon_m, cm_per_pixel)
+        patches = np.empty((n, S, S), np.uint8)
+        ip = np.empty((n, S * S, 2)) if want_points else None
+        self._ck(self.lib.fm3d_extract_patches(self._h, _ptr(frames, _dp), n, C.c_double(epsilon_m), C.c_double(cm_per_pixel),
+                                               _ptr(patches, _bp), _ptr(ip, _dp)))
+        return patches, ip
+
+    def project_groups(self, image, groups, want_points=True):
+        groups = _arr(groups, np.float64)
+        n, ss = groups.shape[0], groups.shape[1]
+        S = int(round(np.sqrt(ss)))
+        patches = np.empty((n, S, S), np.uint8)
+        ip = np.empty((n, S * S, 2)) if want_points else None
+        self._ck(self.lib.fm3d_project_groups(self._h, int(image), _ptr(groups, _dp), n, S, _ptr(patches, _bp), _ptr(ip, _dp)))
+        return patches, ip
+
+    def square_neighborhoods(self, frames, epsilon_m, cm_per_pixel):
+        frames = _arr(frames, np.float64).reshape(-1, 16)
+        n = frames.shape[0]
+        S = patch_size(epsilon_m, cm_per_pixel)
+        out = np.empty((n, S * S, 3))
+        self._ck(self.lib.fm3d_square_neighborhoods(self._h, _ptr(frames, _dp), n, C.c_double(epsilon_m), C.c_double(cm_per_pixel), _ptr(out, _dp)))
+        return out
+
+    # ------------------------------------------------------------------ device-pointer entry points
+    def match_knn2_f32_dev(self, q, nq, t, nt, dim, idx, dist):
+        self._ck(self.lib.fm3d_match_knn2_f32_dev(self._h, C.c_void_p(q), nq, C.c_void_p(t), nt, dim, C.c_void_p(idx), C.c_void_p(dist)))
+
+    def match_knn2_hamming_dev(self, q, nq, t, nt, nbytes, idx, dist):
+        self._ck(self.lib.fm3d_match_knn2_hamming_dev(self._h, C.c_void_p(q), nq, C.c_void_p(t), nt, nbytes, C.c_void_p(idx), C.c_void_p(dist)))
+
+    def nndr_filter_dev(self, idx, dist, nq, eps, qidx, tidx, dist_out, nmatch):
+        self._ck(self.lib.fm3d_nndr_filter_dev(self._h, C.c_void_p(idx), C.c_void_p(dist), nq, C.c_double(eps), C.c_void_p(qidx),
+                                               C.c_void_p(tidx), C.c_void_p(dist_out), C.c_void_p(nmatch)))
+
+    def triangulate_dev(self, kp1, n1, kp2, n2, qidx, tidx, n, xyz_all, mask, xyz, src_idx, ninl):
+        self._ck(self.lib.fm3d_triangulate_dev(self._h, C.c_void_p(kp1), n1, C.c_void_p(kp2), n2, C.c_void_p(qidx), C.c_void_p(tidx), n,
+                                               C.c_void_p(xyz_all), C.c_void_p(mask), C.c_void_p(xyz), C.c_void_p(src_idx), C.c_void_p(ninl)))
+
+    def optimize_normals_dev(self, xyz, n, pixels_ray, epsilon_lmmin, penalty_mode, normals, status, nfev=None, npenalty=None, cost=None):
+        self._ck(self.lib.fm3d_optimize_normals_dev(self._h, C.c_void_p(xyz), n, int(pixels_ray), C.c_double(epsilon_lmmin), int(penalty_mode),
+                                                    C.c_void_p(normals), C.c_void_p(status), C.c_void_p(nfev), C.c_void_p(npenalty), C.c_void_p(cost)))
+
+    def feature_frames_dev(self, xyz, normals, n, gravity, frames):
+        g = _arr(gravity, np.float64).reshape(3)
+        self._ck(self.lib.fm3d_feature_frames_dev(self._h, C.c_void_p(xyz), C.c_void_p(normals), n, _ptr(g, _dp), C.c_void_p(frames)))
+
+    def extract_patches_dev(self, frames, n, epsilon_m, cm_per_pixel, patches, image_points=None):
+        self._ck(self.lib.fm3d_extract_patches_dev(self._h, C.c_void_p(frames), n, C.c_double(epsilon_m), C.c_double(cm_per_pixel),
+                                                   C.c_void_p(patches), C.c_void_p(image_points)))

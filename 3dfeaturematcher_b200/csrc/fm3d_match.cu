@@ -1,0 +1,718 @@
+// fm3d_match.cu -- K1/K2: exact brute-force 2-nearest-neighbour descriptor matching with a
+// fused top-2 epilogue, Lowe ratio test and mutual-best flag.
+//
+// Replaces matcher_->knnMatch(a, b, matches, 2) + the NNDR loop of
+// DescriptorsMatcher::compareWithNNDR / ::compare / ::crosscompare
+// (DescriptorsMatcher/descriptorsmatcher.cpp:74-131).  The reference searches with FLANN
+// (approximate, randomised); the north star asks for the exact search with cv::BFMatcher
+// semantics: L2 distances square-rooted in float, Hamming counts as float, ties broken by the
+// lower train index, ratio test in double on the float distances.
+//
+// Three kernels produce per-(query, train-split) partial top-2 lists that one finalise kernel
+// merges lexicographically by (distance, index):
+//
+//  match_tc_kernel   float descriptors that are integer-valued in [0,255] with dim 128 (SIFT):
+//                    distance contraction on the 5th-gen tensor cores.  The operands are
+//                    re-tiled once into the UMMA K-major core-matrix layout as bf16 with K
+//                    extended from 128 to 144: A = [-2q | qq2 qq1 qq0 65536 256 1 0..],
+//                    B = [t | 65536 256 1 tt2 tt1 tt0 0..] (|q|^2, |t|^2 split in base 256), so
+//                    the fp32 accumulator in TMEM holds |q|^2 + |t|^2 - 2 q.t = d^2 exactly (all
+//                    partial sums are integers below 2^24).  Warp-specialised: one thread
+//                    streams 72 KB train tiles with cp.async.bulk (UBLKCP) into a 2-stage smem
+//                    ring, one thread issues tcgen05.mma (M128 N256 K16 x 9) into a double-
+//                    buffered 2 x 256-column TMEM accumulator, four warps drain it with
+//                    tcgen05.ld (one query row per thread) keeping a running top-2 in registers.
+//  match_f32_kernel  any other float descriptors: exact CUDA-core path, sum of squared
+//                    differences accumulated in ascending dimension order with separately
+//                    rounded multiply and add (bit-identical to the scalar oracle).
+//  match_ham_kernel  binary descriptors: xor + popc on 32-bit words, train tile staged in smem
+//                    with 128-bit loads and read back with 128-bit broadcast loads; packed
+//                    (distance << 22 | index) keys make the top-2 update three integer min/max.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "fm3d_internal.cuh"
+
+namespace {
+
+struct Cand {
+    float d;   // squared L2 / Hamming count
+    int idx;
+};
+
+__device__ __forceinline__ bool cand_less(float d, int i, float d2, int i2) {
+    return d < d2 || (d == d2 && i < i2);
+}
+
+__device__ __forceinline__ void top2_insert(float d, int i, float& b0, int& i0, float& b1, int& i1) {
+    if (cand_less(d, i, b0, i0)) { b1 = b0; i1 = i0; b0 = d; i0 = i; }
+    else if (cand_less(d, i, b1, i1)) { b1 = d; i1 = i; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic exact fp32 path.  CTA tile: 64 queries x 64 train, 256 threads, 4x4 per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int FT = 64, FK = 16;
+
+__global__ void __launch_bounds__(256)
+match_f32_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim,
+                 int tiles_per_split, Cand* __restrict__ partial) {
+    __shared__ float sq[FK][FT + 1];
+    __shared__ float st[FK][FT + 1];
+    __shared__ float s_d[FT][16][2];
+    __shared__ int s_i[FT][16][2];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // tx: train quad, ty: query quad
+    const int q0 = blockIdx.x * FT;
+    const int split = blockIdx.y;
+    const int nt_tiles = (nt + FT - 1) / FT;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(nt_tiles, tile_lo + tiles_per_split);
+    float b0[4], b1[4];
+    int i0[4], i1[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { b0[a] = INFINITY; b1[a] = INFINITY; i0[a] = 0x7fffffff; i1[a] = 0x7fffffff; }
+    for (int tile = tile_lo; tile < tile_hi; tile++) {
+        const int t0 = tile * FT;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+        for (int k0 = 0; k0 < dim; k0 += FK) {
+            __syncthreads();
+            for (int i = tid; i < FT * FK; i += 256) {
+                const int r = i / FK, k = i - r * FK;
+                sq[k][r] = (q0 + r < nq && k0 + k < dim) ? q[(size_t)(q0 + r) * dim + k0 + k] : 0.f;
+                st[k][r] = (t0 + r < nt && k0 + k < dim) ? t[(size_t)(t0 + r) * dim + k0 + k] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < FK; k++) {
+                float qa[4], tb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { qa[a] = sq[k][ty * 4 + a]; tb[a] = st[k][tx * 4 + a]; }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const float d = __fsub_rn(qa[a], tb[b]);
+                        acc[a][b] = __fadd_rn(acc[a][b], __fmul_rn(d, d));
+                    }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int j = t0 + tx * 4 + b;
+                if (j < nt) top2_insert(acc[a][b], j, b0[a], i0[a], b1[a], i1[a]);
+            }
+    }
+    // merge the 16 column-owners of every query row
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        s_d[ty * 4 + a][tx][0] = b0[a]; s_d[ty * 4 + a][tx][1] = b1[a];
+        s_i[ty * 4 + a][tx][0] = i0[a]; s_i[ty * 4 + a][tx][1] = i1[a];
+    }
+    __syncthreads();
+    if (tid < FT && q0 + tid < nq) {
+        float m0 = INFINITY, m1 = INFINITY;
+        int j0 = 0x7fffffff, j1 = 0x7fffffff;
+        for (int c = 0; c < 16; c++) {
+            top2_insert(s_d[tid][c][0], s_i[tid][c][0], m0, j0, m1, j1);
+            top2_insert(s_d[tid][c][1], s_i[tid][c][1], m0, j0, m1, j1);
+        }
+        Cand* o = partial + ((size_t)split * nq + q0 + tid) * 2;
+        o[0].d = m0; o[0].idx = j0;
+        o[1].d = m1; o[1].idx = j1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Hamming path.  128 threads, 2 queries per thread, train tile of 128 descriptors in smem.
+// ------------------------------------------------------------------------------------------
+template <int WORDS>  // 32-bit words per descriptor (8 = ORB, 16 = BRISK/FREAK)
+__global__ void __launch_bounds__(128)
+match_ham_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t, int nt,
+                 int tiles_per_split, uint32_t* __restrict__ partial) {
+    constexpr int TT = 128;
+    __shared__ __align__(16) uint32_t s_t[TT * WORDS];
+    const int tid = threadIdx.x;
+    const int qa = blockIdx.x * 256 + tid, qb = qa + 128;
+    const int split = blockIdx.y;
+    const int nt_tiles = (nt + TT - 1) / TT;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(nt_tiles, tile_lo + tiles_per_split);
+    uint32_t A[WORDS], B[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; w += 4) {
+        const uint4 va = qa < nq ? *reinterpret_cast<const uint4*>(q + (size_t)qa * WORDS + w) : make_uint4(0, 0, 0, 0);
+        const uint4 vb = qb < nq ? *reinterpret_cast<const uint4*>(q + (size_t)qb * WORDS + w) : make_uint4(0, 0, 0, 0);
+        A[w] = va.x; A[w + 1] = va.y; A[w + 2] = va.z; A[w + 3] = va.w;
+        B[w] = vb.x; B[w + 1] = vb.y; B[w + 2] = vb.z; B[w + 3] = vb.w;
+    }
+    uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, c0 = 0xffffffffu, c1 = 0xffffffffu;
+    for (int tile = tile_lo; tile < tile_hi; tile++) {
+        const int t0 = tile * TT;
+        __syncthreads();
+        for (int i = tid; i < TT * WORDS / 4; i += 128) {
+            const int r = (i * 4) / WORDS;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (t0 + r < nt) v = *reinterpret_cast<const uint4*>(t + (size_t)t0 * WORDS + (size_t)i * 4);
+            *reinterpret_cast<uint4*>(&s_t[i * 4]) = v;
+        }
+        __syncthreads();
+        const int cnt = min(TT, nt - t0);
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            int da = 0, db = 0;
+#pragma unroll
+            for (int w = 0; w < WORDS; w += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&s_t[j * WORDS + w]);  // broadcast
+                da += __popc(A[w] ^ v.x) + __popc(A[w + 1] ^ v.y) + __popc(A[w + 2] ^ v.z) + __popc(A[w + 3] ^ v.w);
+                db += __popc(B[w] ^ v.x) + __popc(B[w + 1] ^ v.y) + __popc(B[w + 2] ^ v.z) + __popc(B[w + 3] ^ v.w);
+            }
+            const uint32_t ka = ((uint32_t)da << 22) | (uint32_t)(t0 + j);
+            const uint32_t kb = ((uint32_t)db << 22) | (uint32_t)(t0 + j);
+            uint32_t m = min(ka, a0); a1 = min(a1, max(ka, a0)); a0 = m;
+            m = min(kb, c0); c1 = min(c1, max(kb, c0)); c0 = m;
+        }
+    }
+    if (qa < nq) { uint32_t* o = partial + ((size_t)split * nq + qa) * 2; o[0] = a0; o[1] = a1; }
+    if (qb < nq) { uint32_t* o = partial + ((size_t)split * nq + qb) * 2; o[0] = c0; o[1] = c1; }
+}
+
+__global__ void finalize_f32_kernel(const Cand* __restrict__ partial, int nsplit, int nq, int nt,
+                                    int32_t* __restrict__ idx, float* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float m0 = INFINITY, m1 = INFINITY;
+    int j0 = 0x7fffffff, j1 = 0x7fffffff;
+    for (int s = 0; s < nsplit; s++) {
+        const Cand* p = partial + ((size_t)s * nq + i) * 2;
+        if (p[0].idx >= 0 && p[0].idx < nt) top2_insert(p[0].d, p[0].idx, m0, j0, m1, j1);
+        if (p[1].idx >= 0 && p[1].idx < nt) top2_insert(p[1].d, p[1].idx, m0, j0, m1, j1);
+    }
+    const bool v0 = j0 < nt, v1 = j1 < nt;
+    idx[2 * i] = v0 ? j0 : -1;
+    idx[2 * i + 1] = v1 ? j1 : -1;
+    dist[2 * i] = v0 ? sqrtf(m0) : INFINITY;       // DMatch::distance for NORM_L2
+    dist[2 * i + 1] = v1 ? sqrtf(m1) : INFINITY;
+}
+
+__global__ void finalize_ham_kernel(const uint32_t* __restrict__ partial, int nsplit, int nq, int nt,
+                                    int32_t* __restrict__ idx, float* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu;
+    for (int s = 0; s < nsplit; s++) {
+        const uint32_t* p = partial + ((size_t)s * nq + i) * 2;
+        for (int k = 0; k < 2; k++) {
+            const uint32_t key = p[k];
+            const uint32_t m = min(key, a0); a1 = min(a1, max(key, a0)); a0 = m;
+        }
+    }
+    const bool v0 = a0 != 0xffffffffu, v1 = a1 != 0xffffffffu;
+    idx[2 * i] = v0 ? (int)(a0 & 0x3fffffu) : -1;
+    idx[2 * i + 1] = v1 ? (int)(a1 & 0x3fffffu) : -1;
+    dist[2 * i] = v0 ? (float)(a0 >> 22) : INFINITY;
+    dist[2 * i + 1] = v1 ? (float)(a1 >> 22) : INFINITY;
+}
+
+// NNDR filter (descriptorsmatcher.cpp:119-129) with order-preserving compaction by one CTA.
+__global__ void __launch_bounds__(1024)
+nndr_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dist, int nq, double eps,
+            int32_t* __restrict__ qidx, int32_t* __restrict__ tidx, float* __restrict__ dout,
+            int* __restrict__ nmatch) {
+    __shared__ int warp_cnt[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int start = 0; start < nq; start += blockDim.x) {
+        const int i = start + tid;
+        bool keep = false;
+        if (i < nq && idx[2 * i] >= 0 && idx[2 * i + 1] >= 0)
+            keep = (double)dist[2 * i] <= eps * (double)dist[2 * i + 1];
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < wid; w++) off += warp_cnt[w];
+        off += __popc(bal & ((1u << lane) - 1u));
+        if (keep) { qidx[off] = i; tidx[off] = idx[2 * i]; dout[off] = dist[2 * i]; }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += warp_cnt[w];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *nmatch = base_s;
+}
+
+__global__ void mutual_kernel(const int32_t* __restrict__ qidx, const int32_t* __restrict__ tidx,
+                              const int* __restrict__ nmatch, const int32_t* __restrict__ idx_ba,
+                              uint8_t* __restrict__ mutual) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nmatch) return;
+    mutual[i] = idx_ba[2 * tidx[i]] == qidx[i] ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core path (tcgen05 + TMEM + bulk-copy pipeline)
+// ------------------------------------------------------------------------------------------
+constexpr int TC_DIM = 128;
+constexpr int TC_KCHUNKS = 18;                      // 16-byte K chunks per row: 16 data + 2 extras
+constexpr int TC_GROUP_BYTES = TC_KCHUNKS * 128;    // 8 rows x 18 chunks x 16 B = 2304
+constexpr int TC_M = 128, TC_N = 256;
+constexpr int TC_A_BYTES = (TC_M / 8) * TC_GROUP_BYTES;   // 36864
+constexpr int TC_B_BYTES = (TC_N / 8) * TC_GROUP_BYTES;   // 73728
+constexpr int TC_STAGES = 2;
+constexpr int TC_SMEM = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 256;
+constexpr int TC_THREADS = 192;
+
+// Re-tile n x 128 float descriptors into the UMMA K-major no-swizzle core-matrix layout
+// (8 rows x 16 B core matrices; 18 K-chunks of a row group contiguous) as bf16, rows padded
+// to `n_pad`.  is_query: values are -2*q and the extras carry |q|^2; else values are t and the
+// extras carry |t|^2.  not_integer is set if any value is not an integer in [0,255].
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float* __restrict__ src, int n, int n_pad, int is_query,
+               uint8_t* __restrict__ dst, int* __restrict__ not_integer) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // one warp per row
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    bool bad = false;
+    if (row < n) {
+        const float4 x = *reinterpret_cast<const float4*>(src + (size_t)row * TC_DIM + lane * 4);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+#pragma unroll
+        for (int k = 0; k < 4; k++) bad |= !(v[k] >= 0.f && v[k] <= 255.f && v[k] == floorf(v[k]));
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(not_integer, 1);
+    float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    uint8_t* g = dst + (size_t)(row >> 3) * TC_GROUP_BYTES + (row & 7) * 16;
+    const float sc = is_query ? -2.f : 1.f;
+    // lane holds dims 4*lane..4*lane+3 -> chunk lane/2, half lane&1
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(sc * v[0], sc * v[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(sc * v[2], sc * v[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(g + (lane >> 1) * 128 + (lane & 1) * 8) = pk;
+    if (lane == 0) {
+        // extras: 16 bf16 = chunks 16 and 17
+        const unsigned s = row < n ? (unsigned)ss : 0xffffffu;   // padded rows: |.|^2 = 2^24-1 -> never win
+        const float e2 = (float)((s >> 16) & 255u), e1 = (float)((s >> 8) & 255u), e0 = (float)(s & 255u);
+        float ex[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ex[k] = 0.f;
+        if (is_query) { ex[0] = e2; ex[1] = e1; ex[2] = e0; ex[3] = 65536.f; ex[4] = 256.f; ex[5] = 1.f; }
+        else { ex[0] = 65536.f; ex[1] = 256.f; ex[2] = 1.f; ex[3] = e2; ex[4] = e1; ex[5] = e0; }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(ex[c * 8 + 2 * k], ex[c * 8 + 2 * k + 1]);
+                w[k] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            *reinterpret_cast<uint4*>(g + (16 + c) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (long long spin = 0; spin < (1ll << 28); spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();  // a pipeline bug must fail the launch, not hang the GPU
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: LBO = stride between the two 16-byte K chunks of one MMA (128 B),
+// SBO = stride between 8-row groups (2304 B), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((128u >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)(((uint32_t)TC_GROUP_BYTES >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// grid = (query tiles of 128, train splits).  qa / tb: re-tiled operands (tc_prep_kernel).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int nt_tiles,
+                int tiles_per_split, Cand* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);
+    uint64_t* a_full = bars + 0;
+    uint64_t* b_full = bars + 1;            // [TC_STAGES]
+    uint64_t* b_empty = bars + 1 + TC_STAGES;
+    uint64_t* acc_full = bars + 1 + 2 * TC_STAGES;   // [2]
+    uint64_t* acc_empty = bars + 3 + 2 * TC_STAGES;  // [2]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x, split = blockIdx.y;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(nt_tiles, tile_lo + tiles_per_split);
+    const int ntiles = tile_hi - tile_lo;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        const uint32_t ncols = 512;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ===== producer: one thread streams the query tile once and the train tiles through the ring
+        if (lane == 0) {
+            mbar_expect_tx(a_full, TC_A_BYTES);
+            bulk_g2s(sA, qa + (size_t)qtile * TC_A_BYTES, TC_A_BYTES, a_full);
+            for (int it = 0; it < ntiles; it++) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(&b_empty[s], ph ^ 1u);
+                mbar_expect_tx(&b_full[s], TC_B_BYTES);
+                bulk_g2s(sB + (size_t)s * TC_B_BYTES, tb + (size_t)(tile_lo + it) * TC_B_BYTES, TC_B_BYTES, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread, D[tmem] (+)= A[smem] * B[smem]^T, 9 K-steps of 16
+        if (lane == 0) {
+            // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            mbar_wait(a_full, 0);
+            const uint32_t a_addr = s32(sA);
+            for (int it = 0; it < ntiles; it++) {
+                const int s = it % TC_STAGES, acc = it & 1;
+                mbar_wait(&b_full[s], (uint32_t)(it / TC_STAGES) & 1u);
+                mbar_wait(&acc_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t b_addr = s32(sB + (size_t)s * TC_B_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+#pragma unroll
+                for (int k = 0; k < TC_KCHUNKS / 2; k++)
+                    umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 256), umma_smem_desc(b_addr + k * 256), idesc, k > 0);
+                umma_commit(&b_empty[s]);     // smem stage reusable once these MMAs have read it
+                umma_commit(&acc_full[acc]);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, thread <-> TMEM lane <-> query row; running top-2 in registers
+        const int lane_grp = warp & 3;                  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const int row = lane_grp * 32 + lane;
+        float m0 = INFINITY, m1 = INFINITY;
+        int i0 = 0x7fffffff, i1 = 0x7fffffff;
+        for (int it = 0; it < ntiles; it++) {
+            const int acc = it & 1;
+            mbar_wait(&acc_full[acc], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const int col_base = (tile_lo + it) * TC_N;
+#pragma unroll 1
+            for (int c = 0; c < TC_N / 32; c++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * TC_N + c * 32), v);
+                float gmin = __uint_as_float(v[0]);
+#pragma unroll
+                for (int k = 1; k < 32; k++) gmin = fminf(gmin, __uint_as_float(v[k]));
+                if (gmin < m1) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        const float d = __uint_as_float(v[k]);
+                        if (d < m1) {   // ascending index scan: strict < keeps the lower index on ties
+                            const int j = col_base + c * 32 + k;
+                            if (d < m0) { m1 = m0; i1 = i0; m0 = d; i0 = j; }
+                            else { m1 = d; i1 = j; }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+        }
+        const int qrow = qtile * TC_M + row;
+        if (qrow < nq) {
+            Cand* o = partial + ((size_t)split * nq + qrow) * 2;
+            o[0].d = m0; o[0].idx = i0;
+            o[1].d = m1; o[1].idx = i1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        const uint32_t ncols = 512;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+int pick_splits(int work_tiles, int nt_tiles, int sms, int* tiles_per_split) {
+    int splits = 1;
+    if (work_tiles < 2 * sms) splits = (2 * sms + work_tiles - 1) / work_tiles;
+    if (splits > nt_tiles) splits = nt_tiles;
+    if (splits < 1) splits = 1;
+    *tiles_per_split = (nt_tiles + splits - 1) / splits;
+    if (*tiles_per_split < 1) *tiles_per_split = 1;
+    const int eff = (nt_tiles + *tiles_per_split - 1) / *tiles_per_split;
+    return eff > 0 ? eff : 1;
+}
+
+int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, int32_t* idx,
+                 float* dist) {
+    const int sms = ctx->prop.multiProcessorCount;
+    bool use_tc = ctx->opt_matcher_tensor && dim == TC_DIM && nt >= 1 &&
+                  (((uintptr_t)q | (uintptr_t)t) & 15) == 0;
+    if (use_tc) {
+        const int nq_pad = (nq + TC_M - 1) / TC_M * TC_M, nt_pad = (nt + TC_N - 1) / TC_N * TC_N;
+        const size_t ba = (size_t)(nq_pad / 8) * TC_GROUP_BYTES, bb = (size_t)(nt_pad / 8) * TC_GROUP_BYTES;
+        uint8_t* ops = nullptr;
+        if (int rc = fm3d_scratch(ctx, 3, ba + bb + 256, (void**)&ops)) return rc;
+        int* flag = reinterpret_cast<int*>(ops + ba + bb);
+        ctx->n_copy++;
+        FM3D_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+        tc_prep_kernel<<<nq_pad / 8, 256, 0, ctx->stream>>>(q, nq, nq_pad, 1, ops, flag);
+        FM3D_LAUNCH_CHECK(ctx);
+        tc_prep_kernel<<<nt_pad / 8, 256, 0, ctx->stream>>>(t, nt, nt_pad, 0, ops + ba, flag);
+        FM3D_LAUNCH_CHECK(ctx);
+        int h_flag = 0;
+        if (int rc = fm3d_d2h(ctx, &h_flag, flag, sizeof(int))) return rc;
+        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_flag == 0) {
+            const int q_tiles = nq_pad / TC_M, nt_tiles = nt_pad / TC_N;
+            int tps = 1;
+            const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
+            Cand* partial = nullptr;
+            if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * nq, (void**)&partial)) return rc;
+            FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+            dim3 grid(q_tiles, splits);
+            match_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, partial);
+            FM3D_LAUNCH_CHECK(ctx);
+            finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits, nq, nt, idx, dist);
+            FM3D_LAUNCH_CHECK(ctx);
+            return FM3D_OK;
+        }
+    }
+    const int q_tiles = (nq + FT - 1) / FT, nt_tiles = (nt + FT - 1) / FT;
+    int tps = 1;
+    const int splits = nt_tiles > 0 ? pick_splits(q_tiles, nt_tiles, sms, &tps) : 1;
+    Cand* partial = nullptr;
+    if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * nq, (void**)&partial)) return rc;
+    dim3 grid(q_tiles, splits);
+    match_f32_kernel<<<grid, 256, 0, ctx->stream>>>(q, nq, t, nt, dim, tps, partial);
+    FM3D_LAUNCH_CHECK(ctx);
+    finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits, nq, nt, idx, dist);
+    FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
+}
+
+int knn2_ham_dev(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int nbytes,
+                 int32_t* idx, float* dist) {
+    if (nbytes != 32 && nbytes != 64)
+        return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "binary descriptors of %d bytes (supported: 32, 64)", nbytes);
+    if (nt >= (1 << 22)) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "more than 4M train descriptors");
+    if ((((uintptr_t)q | (uintptr_t)t) & 15) != 0) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "descriptors must be 16-byte aligned");
+    const int sms = ctx->prop.multiProcessorCount;
+    const int q_tiles = (nq + 255) / 256, nt_tiles = (nt + 127) / 128;
+    int tps = 1;
+    const int splits = nt_tiles > 0 ? pick_splits(q_tiles, nt_tiles, 4 * sms, &tps) : 1;
+    uint32_t* partial = nullptr;
+    if (int rc = fm3d_scratch(ctx, 4, sizeof(uint32_t) * 2 * (size_t)splits * nq, (void**)&partial)) return rc;
+    dim3 grid(q_tiles, splits);
+    if (nbytes == 32)
+        match_ham_kernel<8><<<grid, 128, 0, ctx->stream>>>((const uint32_t*)q, nq, (const uint32_t*)t, nt, tps, partial);
+    else
+        match_ham_kernel<16><<<grid, 128, 0, ctx->stream>>>((const uint32_t*)q, nq, (const uint32_t*)t, nt, tps, partial);
+    FM3D_LAUNCH_CHECK(ctx);
+    finalize_ham_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits, nq, nt, idx, dist);
+    FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
+}
+
+// host-pointer front end shared by the four host entry points
+int match_host(fm3d_ctx* ctx, const void* q, int nq, const void* t, int nt, int row_bytes, int dim_or_bytes,
+               bool hamming, bool nndr, double eps, int32_t* idx_or_qidx, int32_t* tidx, float* dist,
+               uint8_t* mutual, int* nmatch) {
+    if (int rc = fm3d_bind(ctx)) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t bq = (size_t)nq * row_bytes, bt = (size_t)nt * row_bytes;
+    const size_t bi = sizeof(int32_t) * 2 * (size_t)nq, bi_t = sizeof(int32_t) * 2 * (size_t)nt;
+    size_t o_q = 0, o_t = o_q + al(bq), o_idx = o_t + al(bt), o_d = o_idx + al(bi);
+    size_t o_qi = o_d + al(bi), o_ti = o_qi + al(bi / 2), o_do = o_ti + al(bi / 2), o_n = o_do + al(bi / 2);
+    size_t o_iba = o_n + 256, o_dba = o_iba + al(bi_t), o_mu = o_dba + al(bi_t), o_end = o_mu + al((size_t)nq);
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, o_end, (void**)&d)) return rc;
+    if (int rc = fm3d_h2d(ctx, d + o_q, q, bq)) return rc;
+    if (int rc = fm3d_h2d(ctx, d + o_t, t, bt)) return rc;
+    int32_t* d_idx = (int32_t*)(d + o_idx);
+    float* d_dist = (float*)(d + o_d);
+    int rc;
+    if (nq > 0) {
+        rc = hamming ? knn2_ham_dev(ctx, (const uint8_t*)(d + o_q), nq, (const uint8_t*)(d + o_t), nt, dim_or_bytes, d_idx, d_dist)
+                     : knn2_f32_dev(ctx, (const float*)(d + o_q), nq, (const float*)(d + o_t), nt, dim_or_bytes, d_idx, d_dist);
+        if (rc) return rc;
+    }
+    if (!nndr) {
+        if (int r2 = fm3d_d2h(ctx, idx_or_qidx, d_idx, bi)) return r2;
+        if (int r2 = fm3d_d2h(ctx, dist, d_dist, bi)) return r2;
+        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return FM3D_OK;
+    }
+    nndr_kernel<<<1, 1024, 0, ctx->stream>>>(d_idx, d_dist, nq, eps, (int32_t*)(d + o_qi), (int32_t*)(d + o_ti),
+                                             (float*)(d + o_do), (int*)(d + o_n));
+    FM3D_LAUNCH_CHECK(ctx);
+    if (mutual && nq > 0 && nt > 0) {
+        rc = hamming ? knn2_ham_dev(ctx, (const uint8_t*)(d + o_t), nt, (const uint8_t*)(d + o_q), nq, dim_or_bytes,
+                                    (int32_t*)(d + o_iba), (float*)(d + o_dba))
+                     : knn2_f32_dev(ctx, (const float*)(d + o_t), nt, (const float*)(d + o_q), nq, dim_or_bytes,
+                                    (int32_t*)(d + o_iba), (float*)(d + o_dba));
+        if (rc) return rc;
+        mutual_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>((const int32_t*)(d + o_qi), (const int32_t*)(d + o_ti),
+                                                                 (const int*)(d + o_n), (const int32_t*)(d + o_iba),
+                                                                 (uint8_t*)(d + o_mu));
+        FM3D_LAUNCH_CHECK(ctx);
+    }
+    int h_n = 0;
+    if (int r2 = fm3d_d2h(ctx, &h_n, d + o_n, sizeof(int))) return r2;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int r2 = fm3d_d2h(ctx, idx_or_qidx, d + o_qi, sizeof(int32_t) * (size_t)h_n)) return r2;
+    if (int r2 = fm3d_d2h(ctx, tidx, d + o_ti, sizeof(int32_t) * (size_t)h_n)) return r2;
+    if (int r2 = fm3d_d2h(ctx, dist, d + o_do, sizeof(float) * (size_t)h_n)) return r2;
+    if (mutual && nq > 0 && nt > 0) if (int r2 = fm3d_d2h(ctx, mutual, d + o_mu, (size_t)h_n)) return r2;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *nmatch = h_n;
+    return FM3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fm3d_match_knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                            int32_t* idx, float* dist) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nt >= 0 && dim > 0 && (nq == 0 || (q && idx && dist)) && (nt == 0 || t));
+    if (nq == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    return knn2_f32_dev(ctx, q, nq, t, nt, dim, idx, dist);
+}
+
+int fm3d_match_knn2_hamming_dev(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                                int nbytes, int32_t* idx, float* dist) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nt >= 0 && nbytes > 0 && (nq == 0 || (q && idx && dist)) && (nt == 0 || t));
+    if (nq == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    return knn2_ham_dev(ctx, q, nq, t, nt, nbytes, idx, dist);
+}
+
+int fm3d_nndr_filter_dev(fm3d_ctx* ctx, const int32_t* idx, const float* dist, int nq, double eps,
+                         int32_t* qidx, int32_t* tidx, float* dist_out, int* nmatch_dev) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nmatch_dev && (nq == 0 || (idx && dist && qidx && tidx && dist_out)));
+    if (int rc = fm3d_bind(ctx)) return rc;
+    nndr_kernel<<<1, 1024, 0, ctx->stream>>>(idx, dist, nq, eps, qidx, tidx, dist_out, nmatch_dev);
+    FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
+}
+
+int fm3d_match_knn2_f32(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                        int32_t* idx, float* dist) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nt >= 0 && dim > 0 && (nq == 0 || (q && idx && dist)) && (nt == 0 || t));
+    if (nq == 0) return FM3D_OK;
+    return match_host(ctx, q, nq, t, nt, dim * (int)sizeof(float), dim, false, false, 0.0, idx, nullptr, dist, nullptr, nullptr);
+}
+
+int fm3d_match_knn2_hamming(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                            int nbytes, int32_t* idx, float* dist) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nt >= 0 && nbytes > 0 && (nq == 0 || (q && idx && dist)) && (nt == 0 || t));
+    if (nq == 0) return FM3D_OK;
+    return match_host(ctx, q, nq, t, nt, nbytes, nbytes, true, false, 0.0, idx, nullptr, dist, nullptr, nullptr);
+}
+
+int fm3d_match_nndr_f32(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                        double eps, int32_t* qidx, int32_t* tidx, float* dist, uint8_t* mutual,
+                        int* nmatch) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nt >= 0 && dim > 0 && nmatch && (nq == 0 || (q && qidx && tidx && dist)) && (nt == 0 || t));
+    *nmatch = 0;
+    if (nq == 0) return FM3D_OK;
+    return match_host(ctx, q, nq, t, nt, dim * (int)sizeof(float), dim, false, true, eps, qidx, tidx, dist, mutual, nmatch);
+}
+
+int fm3d_match_nndr_hamming(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                            int nbytes, double eps, int32_t* qidx, int32_t* tidx, float* dist,
+                            uint8_t* mutual, int* nmatch) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, nq >= 0 && nt >= 0 && nbytes > 0 && nmatch && (nq == 0 || (q && qidx && tidx && dist)) && (nt == 0 || t));
+    *nmatch = 0;
+    if (nq == 0) return FM3D_OK;
+    return match_host(ctx, q, nq, t, nt, nbytes, nbytes, true, true, eps, qidx, tidx, dist, mutual, nmatch);
+}
+
+}  // extern "C"

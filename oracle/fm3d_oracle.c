@@ -716,6 +716,25 @@ int orc_lmmin_expsin(const double* t, const double* y, int m, double* x, double 
     return 0;
 }
 
+/* Two-parameter problem f_i = x0*exp(x1*t_i) - y_i: lets tests compare the product's n=2 LM
+ * state machine (csrc/fm3d_lm2.h, driven by tests/cpp/lm2_harness.cpp) with this generic one. */
+static int exp2_eval(const double* p, int m, void* data, double* f) {
+    orc_expsin* d = (orc_expsin*)data;
+    for (int i = 0; i < m; i++) f[i] = p[0] * exp(p[1] * d->t[i]) - d->y[i];
+    return 0;
+}
+int orc_lmmin_exp2(const double* t, const double* y, int m, double* x, double epsilon,
+                   int patience, int minpack_mode, int* nfev, int* info) {
+    orc_expsin d = {t, y};
+    orc_lm_control c = {30 * ORC_EPS, 30 * ORC_EPS, 30 * ORC_EPS, epsilon, 100.0, patience, 1, minpack_mode};
+    orc_lm_status st;
+    double* work = (double*)malloc(sizeof(double) * (size_t)m * 4);
+    orc_lmmin_impl(2, x, m, &d, exp2_eval, &c, &st, work);
+    free(work);
+    *nfev = st.nfev; *info = st.info;
+    return 0;
+}
+
 /* ------------------------------------------------------- normal optimisation ---- */
 
 typedef struct {

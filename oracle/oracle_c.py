@@ -216,3 +216,12 @@ def lmmin_expsin(t, y, x0, epsilon=1e-10, patience=100, minpack_mode=0):
     lib().orc_lmmin_expsin(_p(t, c_dp), _p(y, c_dp), t.size, _p(x, c_dp), C.c_double(epsilon), patience, minpack_mode,
                            C.byref(nfev), C.byref(info))
     return x, nfev.value, info.value
+
+
+def lmmin_exp2(t, y, x0, epsilon=1e-10, patience=100, minpack_mode=0):
+    t, y = _d(t), _d(y)
+    x = _d(x0).copy()
+    nfev, info = C.c_int(0), C.c_int(0)
+    lib().orc_lmmin_exp2(_p(t, c_dp), _p(y, c_dp), t.size, _p(x, c_dp), C.c_double(epsilon), patience, minpack_mode,
+                         C.byref(nfev), C.byref(info))
+    return x, nfev.value, info.value

@@ -1,0 +1,311 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on seeded inputs.
+
+Bars: bit-exact for indices / bytes / integer work; 1e-9 relative for fp64 geometry (the
+north star allows 1e-4 on 3-D points); 0.5 degrees on refined normals (north star), with the
+tighter expectation written next to each check.
+"""
+import numpy as np
+import pytest
+
+from common import angle_deg, cam_tuple, car2sph, orc, setup_ctx, stereo_case, synth
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ triangulation (K3)
+def test_undistort_points(ctx):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(0, 640, (5000, 2))
+    pts[:, 1] *= 0.75
+    np.testing.assert_allclose(ctx.undistort_points(pts), orc.undistort_points(cam.K, cam.dist, pts), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.7])
+def test_triangulate(ctx, noise):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
+    ctx.set_g12(cam.g12)
+    rng = np.random.default_rng(5)
+    n = 3000
+    # matches into shuffled keypoint tables, some far off so that the depth gate drops them
+    kp1 = np.repeat(case["kp1"], n // 40, axis=0).astype(np.float32)
+    kp2 = np.repeat(case["kp2_true"], n // 40, axis=0).astype(np.float32)
+    kp2 += rng.normal(0, noise, kp2.shape).astype(np.float32)
+    kp2[::7, 0] += rng.uniform(-40, 40, kp2[::7, 0].shape).astype(np.float32)
+    perm1, perm2 = rng.permutation(n), rng.permutation(n)
+    t1, t2 = np.empty_like(kp1), np.empty_like(kp2)
+    t1[perm1], t2[perm2] = kp1, kp2
+    qidx, tidx = perm1.astype(np.int32), perm2.astype(np.int32)
+    xyz_all, mask, xyz, src = ctx.triangulate(t1, t2, qidx, tidx)
+    o_all, o_mask, o_xyz = orc.triangulate(*cam_tuple(cam)[:2], cam.g12, cam.z_min, cam.z_max, t1, t2, qidx, tidx)
+    assert 0 < o_mask.sum() < n
+    np.testing.assert_array_equal(mask, o_mask)
+    np.testing.assert_allclose(xyz_all, o_all, rtol=1e-9, atol=1e-12)     # bar 1e-4 relative
+    np.testing.assert_allclose(xyz, o_xyz, rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(src, np.nonzero(o_mask)[0])            # order-preserving compaction
+
+
+def test_triangulate_empty_and_direct(ctx):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
+    ctx.set_g12(cam.g12)
+    xyz_all, mask, xyz, src = ctx.triangulate(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert xyz_all.shape == (0, 3) and xyz.shape == (0, 3)
+    xyz_all, mask, xyz, src = ctx.triangulate(case["kp1"], case["kp2_true"])
+    np.testing.assert_allclose(xyz_all, case["X"], rtol=0, atol=2e-3)     # ground truth of the scene
+    assert mask.all()
+
+
+# ------------------------------------------------------------------ pyramids (K4)
+@pytest.mark.parametrize("shape", [(480, 640), (477, 635), (67, 131), (5, 9), (1080, 1920)])
+def test_pyramid_bit_exact(ctx, shape):
+    rng = np.random.default_rng(shape[0])
+    img1 = rng.integers(0, 256, shape, dtype=np.uint8)
+    img2 = rng.integers(0, 256, shape, dtype=np.uint8)
+    levels = 3 if min(shape) > 16 else 1
+    ctx.set_images(img1, img2, levels)
+    for k, img in ((1, img1), (2, img2)):
+        ref = orc.pyramid_levels(orc.build_pyramid(img, levels), shape[1], shape[0], levels)
+        for l in range(levels + 1):
+            got = ctx.get_pyramid_level(k, l)
+            assert got.shape == ref[l].shape
+            np.testing.assert_array_equal(got, ref[l])
+
+
+# ------------------------------------------------------------------ matcher (K1/K2)
+def _check_knn(idx, dist, o_idx, o_dist):
+    np.testing.assert_array_equal(idx, o_idx)
+    np.testing.assert_array_equal(dist, o_dist)
+
+
+@pytest.mark.parametrize("nq,nt", [(300, 360), (1, 1), (5, 2), (1000, 1300), (129, 257), (2048, 4096)])
+def test_match_f32_integer_descriptors_tensor_path(ctx, nq, nt):
+    q, t, _ = synth.make_float_descriptors(nq, max(nt - nq, 0), 7 + nq)
+    t = t[:nt]
+    ctx.set_option("matcher_tensor", 1)
+    idx, dist = ctx.match_knn2_f32(q, t)
+    o_idx, o_dist = orc.knn2_f32(q, t, threads=8)
+    _check_knn(idx, dist, o_idx, o_dist)
+
+
+def test_match_f32_tensor_path_extremes_and_ties(ctx):
+    rng = np.random.default_rng(11)
+    t = rng.integers(0, 256, (700, 128)).astype(np.float32)
+    t[100] = 255.0
+    t[101] = 0.0
+    t[3] = t[7] = t[20] = t[650]           # duplicates: ties must resolve to the lower index
+    q = t[rng.integers(0, 700, 260)].copy()
+    q[0] = 0.0
+    q[1] = 255.0                            # |q|^2 = |t|^2 = 128*255^2: largest exact accumulations
+    q[2] = t[650]
+    idx, dist = ctx.match_knn2_f32(q, t)
+    o_idx, o_dist = orc.knn2_f32(q, t, threads=8)
+    _check_knn(idx, dist, o_idx, o_dist)
+    assert tuple(idx[2]) == (3, 7)
+
+
+def test_match_f32_generic_path(ctx):
+    rng = np.random.default_rng(13)
+    for dim in (128, 64, 37):
+        q = rng.standard_normal((333, dim)).astype(np.float32)
+        t = rng.standard_normal((517, dim)).astype(np.float32)
+        idx, dist = ctx.match_knn2_f32(q, t)
+        o_idx, o_dist = orc.knn2_f32(q, t, threads=8)
+        _check_knn(idx, dist, o_idx, o_dist)
+    # integer-valued data through the CUDA-core path must agree with the tensor path
+    q, t, _ = synth.make_float_descriptors(500, 100, 3)
+    ctx.set_option("matcher_tensor", 0)
+    a = ctx.match_knn2_f32(q, t)
+    ctx.set_option("matcher_tensor", 1)
+    b = ctx.match_knn2_f32(q, t)
+    _check_knn(a[0], a[1], b[0], b[1])
+
+
+@pytest.mark.parametrize("nbytes", [32, 64])
+@pytest.mark.parametrize("nq,nt", [(300, 360), (3, 1), (1500, 2100)])
+def test_match_hamming(ctx, nbytes, nq, nt):
+    q, t, _ = synth.make_binary_descriptors(nq, max(nt - nq, 0), 5 + nq, nbytes=nbytes)
+    t = t[:nt]
+    if nt > 30:
+        t[5] = t[9] = t[21]
+        q[0] = t[21]
+    idx, dist = ctx.match_knn2_hamming(q, t)
+    o_idx, o_dist = orc.knn2_hamming(q, t, threads=8)
+    _check_knn(idx, dist, o_idx, o_dist)
+
+
+def test_match_empty_train_and_query(ctx):
+    q = np.zeros((4, 128), np.float32)
+    idx, dist = ctx.match_knn2_f32(q, np.zeros((0, 128), np.float32))
+    assert (idx == -1).all() and np.isinf(dist).all()
+    idx, dist = ctx.match_knn2_f32(np.zeros((0, 128), np.float32), q)
+    assert idx.shape == (0, 2)
+
+
+@pytest.mark.parametrize("hamming", [False, True])
+def test_match_nndr_and_mutual(ctx, hamming):
+    if hamming:
+        q, t, gt = synth.make_binary_descriptors(800, 160, 21)
+        eps = 0.8
+    else:
+        q, t, gt = synth.make_float_descriptors(800, 160, 21)
+        eps = 0.55
+    qi, ti, d, mu = ctx.match_nndr(q, t, eps, hamming=hamming, with_mutual=True)
+    o_idx, o_dist = (orc.knn2_hamming if hamming else orc.knn2_f32)(q, t, threads=8)
+    oq, ot, od = orc.nndr_filter(o_idx, o_dist, eps)
+    np.testing.assert_array_equal(qi, oq)
+    np.testing.assert_array_equal(ti, ot)
+    np.testing.assert_array_equal(d, od)
+    ba_idx, _ = (orc.knn2_hamming if hamming else orc.knn2_f32)(t, q, threads=8)
+    np.testing.assert_array_equal(mu, (ba_idx[ot, 0] == oq).astype(np.uint8))
+    # the synthetic inliers are recovered
+    inl = gt[qi] >= 0
+    assert inl.mean() > 0.95 and (ti[inl] == gt[qi][inl]).all()
+
+
+# ------------------------------------------------------------------ normals (K5-K7)
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_cost_evaluation_matches_oracle(ctx, level):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    xyz = case["X"][:24]
+    rng = np.random.default_rng(level)
+    n0 = xyz / np.linalg.norm(xyz, axis=1, keepdims=True)
+    pt = car2sph(n0) + rng.normal(0, 0.15, (xyz.shape[0], 2))
+    cost, m, status = ctx.evaluate_normals(xyz, pt, 32, level, 2)
+    o_cost, o_m, o_status = orc.evaluate_cost(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, pt, 32, level, 2)
+    np.testing.assert_array_equal(m, o_m)
+    np.testing.assert_array_equal(status, o_status)
+    ok = o_status == 0
+    assert ok.sum() >= 20
+    # identical float samples wherever the fp32 cast of the coordinates agrees; allow a few pixels to differ
+    np.testing.assert_allclose(cost[ok], o_cost[ok], rtol=2e-5)
+
+
+@pytest.mark.parametrize("penalty_mode", [2, 0, 1])
+def test_optimize_normals_small_disc(ctx, penalty_mode):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    xyz = case["X"]
+    res = ctx.optimize_normals(xyz, 32, 1e-10, penalty_mode)
+    o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, 32, 1e-10,
+                             penalty_mode=penalty_mode, threads=8)
+    np.testing.assert_array_equal(res["status"], o["status"])
+    ok = o["status"] == 0
+    assert ok.sum() >= 30
+    # interior features: the oracle never entered the penalty branch (SURVEY 8c stratification)
+    interior = ok & (o["npenalty"] == 0)
+    ang = angle_deg(res["normals"], o["normals"])
+    assert interior.sum() >= 1 or penalty_mode != 2
+    assert (ang[interior] <= 0.5).all(), ang[interior].max()          # north-star bar
+    assert np.median(ang[interior]) <= 0.01 if interior.any() else True
+    if penalty_mode == 2:
+        assert interior.sum() == ok.sum()
+        gt = angle_deg(res["normals"], case["normal"])
+        o_gt = angle_deg(o["normals"], case["normal"])
+        assert (gt[ok] <= o_gt[ok] + 0.1).all()
+        np.testing.assert_allclose(res["cost"][ok], o["cost"][ok], rtol=0.01)
+    else:
+        # wall features are reported, not gated
+        wall = ok & ~interior
+        print("wall features:", int(wall.sum()), "agree<=0.5deg:", int((ang[wall] <= 0.5).sum()))
+
+
+def test_optimize_normals_default_settings_r64(ctx):
+    """build/settings.yml defaults: pixelsRay 64, pyramids 3 (4 LM stages)."""
+    case = stereo_case(640, 480, 24, 1000, 64)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 3)
+    xyz = case["X"]
+    res = ctx.optimize_normals(xyz, 64, 1e-10, 2)
+    o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 3, xyz, 64, 1e-10,
+                             penalty_mode=2, threads=8)
+    np.testing.assert_array_equal(res["status"], o["status"])
+    ok = o["status"] == 0
+    ang = angle_deg(res["normals"], o["normals"])
+    assert (ang[ok] <= 0.5).all(), ang[ok].max()
+    assert (angle_deg(res["normals"], case["normal"])[ok] <= angle_deg(o["normals"], case["normal"])[ok] + 0.1).all()
+    print("nfev gpu", res["nfev"].sum(0), "oracle", o["nfev"].sum(0), "max angle", ang[ok].max())
+
+
+def test_optimize_normals_fp32_geometry(ctx):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    xyz = case["X"]
+    ctx.set_option("geometry_f32", 1)
+    try:
+        res = ctx.optimize_normals(xyz, 32, 1e-10, 2)
+    finally:
+        ctx.set_option("geometry_f32", 0)
+    o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, 32, 1e-10,
+                             penalty_mode=2, threads=8)
+    ok = (o["status"] == 0) & (res["status"] == 0)
+    assert ok.sum() >= 30
+    assert (angle_deg(res["normals"], o["normals"])[ok] <= 0.5).all()
+
+
+def test_optimize_normals_aborts_and_clipped_discs(ctx):
+    """Features whose disc is clipped by the border (D1), projects outside image 2 (abort, D8)
+    or has no pixels at all."""
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    Z = 1.9
+    # 3-D points on the rays of chosen image-1 pixels: left border, outside, top border, corner
+    pix = np.array([[8.0, 240.0], [300.0, 6.0], [320.0, 472.0], [632.0, 470.0], [600.0, 30.0]])
+    rays = orc.undistort_points(cam.K, cam.dist, pix)
+    pts = np.concatenate([rays * Z, np.full((pix.shape[0], 1), Z)], axis=1)
+    far = np.array([[9.0, 0.3, Z]])                       # projects far outside image 1: no pixels
+    xyz = np.concatenate([case["X"][:1], pts, far, case["X"][1:2]])
+    res = ctx.optimize_normals(xyz, 32, 1e-10, 2)
+    o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, 32, 1e-10,
+                             penalty_mode=2, threads=4)
+    np.testing.assert_array_equal(res["status"], o["status"])
+    assert (o["status"] == 1).any() and ((o["m"] > 0) & (o["m"] < 3209)).sum() >= 3
+    print("statuses", o["status"], "m", o["m"])
+    ok = o["status"] == 0
+    assert (angle_deg(res["normals"], o["normals"])[ok] <= 0.5).all()
+    cost, m, st = ctx.evaluate_normals(xyz, car2sph(xyz / np.linalg.norm(xyz, axis=1, keepdims=True)), 32, 0, 2)
+    np.testing.assert_array_equal(m, o["m"])
+
+
+# ------------------------------------------------------------------ frames + patches (K7/K8)
+def test_frames_and_patches(ctx):
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    xyz, normals = case["X"][:12], case["normal"][:12]
+    g = np.array([0.006, 0.99992, -0.011])
+    frames = ctx.feature_frames(xyz, normals, g)
+    o_frames = orc.feature_frames(xyz, normals, g)
+    np.testing.assert_allclose(frames, o_frames, rtol=0, atol=1e-14)
+    for eps_m, cmpp in ((0.16, 0.25), (0.05, 0.25), (0.0825, 0.5)):
+        patches, ip = ctx.extract_patches(frames, eps_m, cmpp, want_points=True)
+        o_patches, o_ip = orc.extract_patches(cam.K, cam.dist, case["scene"].img1, o_frames, eps_m, cmpp)
+        assert patches.shape == o_patches.shape
+        np.testing.assert_allclose(ip, o_ip, rtol=0, atol=1e-9)
+        diff = patches.astype(int) - o_patches.astype(int)
+        assert (np.abs(diff) <= 1).all() and (diff != 0).mean() < 1e-3    # float-cast boundaries only
+        p2, _ = ctx.extract_patches(frames, eps_m, cmpp, want_points=False)
+        np.testing.assert_array_equal(p2, patches)
+    nb = ctx.square_neighborhoods(frames, 0.05, 0.25)
+    S = orc.patch_size(0.05, 0.25)
+    i, j = np.meshgrid(np.arange(S), np.arange(S), indexing="ij")
+    ref = np.stack([-0.05 + 0.0025 * i.ravel(), -0.05 + 0.0025 * j.ravel(), np.zeros(S * S), np.ones(S * S)], 1)
+    np.testing.assert_allclose(nb, np.einsum("nij,pj->npi", o_frames, ref)[:, :, :3], rtol=0, atol=1e-12)
+    # explicit groups into either image (projectPointsToImage)
+    for image in (1, 2):
+        gp, gip = ctx.project_groups(image, nb)
+        o_ip2 = np.stack([orc.project_points(cam.K, cam.dist, cam.g12, image, grp) for grp in nb])
+        np.testing.assert_allclose(gip, o_ip2, rtol=0, atol=1e-9)
+    gp1, _ = ctx.project_groups(1, nb)
+    p1, _ = ctx.extract_patches(frames, 0.05, 0.25, want_points=False)
+    assert (np.abs(gp1.astype(int) - p1.astype(int)) <= 1).all()
