@@ -173,6 +173,29 @@ __device__ __forceinline__ float sample_img2(const LevelView& L, float x, float 
     return fm3d_lerp4(b00, b01, b10, b11, __fsub_rn(x, fx0), __fsub_rn(y, fy0));
 }
 
+// Ray offsets from the centre ray, 8 bytes per pixel.  fp64 geometry stores them as 32-bit fixed
+// point (resolution <= 2^-31 of the disc's angular extent, ~1e-10: two orders finer than float),
+// fp32 geometry stores floats.
+template <typename G> struct RayStore;
+template <> struct RayStore<double> {
+    typedef int2 type;
+    static __device__ __forceinline__ int2 pack(double dx, double dy, double scale) {
+        return make_int2(__double2int_rn(dx * scale), __double2int_rn(dy * scale));
+    }
+    static __device__ __forceinline__ void unpack(int2 v, double inv_scale, double cx, double cy, double& x, double& y) {
+        x = fma((double)v.x, inv_scale, cx);
+        y = fma((double)v.y, inv_scale, cy);
+    }
+};
+template <> struct RayStore<float> {
+    typedef float2 type;
+    static __device__ __forceinline__ float2 pack(double dx, double dy, double) { return make_float2((float)dx, (float)dy); }
+    static __device__ __forceinline__ void unpack(float2 v, float, float cx, float cy, float& x, float& y) {
+        x = cx + v.x;
+        y = cy + v.y;
+    }
+};
+
 template <typename G>
 struct CamG {
     G fx, fy, cx, cy, k1, k2, p1, p2, k3;
@@ -217,16 +240,17 @@ template <typename G, bool RAYS_SMEM>
 __global__ void __launch_bounds__(NT_MAX, 1)
 normals_kernel(const __grid_constant__ NormalsArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
+    typedef typename RayStore<G>::type ray_t;
     uint8_t* win = smem;
-    float2* rays;
+    ray_t* rays;
     float* i1;
     uint8_t* tail;
     if (RAYS_SMEM) {
-        rays = reinterpret_cast<float2*>(smem + WIN_BYTES);
+        rays = reinterpret_cast<ray_t*>(smem + WIN_BYTES);
         i1 = reinterpret_cast<float*>(rays + A.mcap);
         tail = reinterpret_cast<uint8_t*>(i1 + A.mcap);
     } else {
-        rays = A.rays_g + (size_t)blockIdx.x * A.mcap;
+        rays = reinterpret_cast<ray_t*>(A.rays_g) + (size_t)blockIdx.x * A.mcap;
         i1 = A.i1_g + (size_t)blockIdx.x * A.mcap;
         tail = smem + WIN_BYTES;
     }
@@ -235,6 +259,8 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
     tail += (sizeof(RowTable) + 15) & ~(size_t)15;
     double* red = reinterpret_cast<double*>(tail);        // [16 warps][6]
     tail += sizeof(double) * 16 * 6;
+    unsigned* wflags = reinterpret_cast<unsigned*>(tail);  // [16 warps]
+    tail += sizeof(unsigned) * 16;
     FeatureShared* S = reinterpret_cast<FeatureShared*>(tail);
     tail += (sizeof(FeatureShared) + 15) & ~(size_t)15;
     PassParams<G>* PP = reinterpret_cast<PassParams<G>*>(tail);
@@ -321,6 +347,10 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
         // centre ray and ideal rays of all disc pixels (normal-independent)
         double vcx, vcy;
         fm3d_undistort(cam, cu, cv, vcx, vcy);
+        // fixed-point scale: offsets are bounded by ~(r+2)/f (x2 for lens distortion)
+        const double ray_bound = 2.0 * (double)(r + 2) / fmin(fabs(cam.fx), fabs(cam.fy));
+        const double ray_scale = ldexp(1.0, 30 - ilogb(ray_bound));
+        const G ray_inv_scale = (G)(1.0 / ray_scale);
         if (m > 0) {
             int row = 0;
             for (int idx = tid; idx < m; idx += NT) {
@@ -329,7 +359,7 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
                 const double py = cv + (double)rows->jrow[row];
                 double vx, vy;
                 fm3d_undistort(cam, px, py, vx, vy);
-                rays[idx] = make_float2((float)(vx - vcx), (float)(vy - vcy));
+                rays[idx] = RayStore<G>::pack(vx - vcx, vy - vcy, ray_scale);
             }
         }
         const G gvcx = (G)vcx, gvcy = (G)vcy;
@@ -362,7 +392,8 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
                 double wxc = floor(scale * u2), wyc = floor(scale * v2);
                 if (!(wxc > -1e6 && wxc < 1e6)) wxc = 0;
                 if (!(wyc > -1e6 && wyc < 1e6)) wyc = 0;
-                S->wx0 = (int)wxc - L.ww / 2;
+                // TMA needs the box start address 16-byte aligned: x origin is a multiple of 16 pixels
+                S->wx0 = (((int)wxc - L.ww / 2 + 8) >> 4) << 4;
                 S->wy0 = (int)wyc - wh / 2;
                 S->level = lvl;
             }
@@ -481,15 +512,18 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
                     const G n1x = PP->nx[1], n1y = PP->ny[1], n1z = PP->nz[1], m1 = PP->mnum[1];
                     const G n2x = PP->nx[2], n2y = PP->ny[2], n2z = PP->nz[2], m2 = PP->mnum[2];
                     for (int idx = tid; idx < m; idx += NT) {
-                        const float2 dr = rays[idx];
+                        const ray_t dr = rays[idx];
                         const float I1 = i1[idx];
-                        const G vx = gvcx + (G)dr.x, vy = gvcy + (G)dr.y;
+                        G vx, vy;
+                        RayStore<G>::unpack(dr, ray_inv_scale, gvcx, gvcy, vx, vy);
                         const G a = C.R[0] * vx + C.R[1] * vy + C.R[2];
                         const G b = C.R[3] * vx + C.R[4] * vy + C.R[5];
                         const G c = C.R[6] * vx + C.R[7] * vy + C.R[8];
+                        unsigned f1 = 0, f2 = 0;
                         const float d0 = eval_pixel<G>(C, L, vx, vy, a, b, c, n0x, n0y, n0z, m0, I1, flags);
-                        const float d1 = eval_pixel<G>(C, L, vx, vy, a, b, c, n1x, n1y, n1z, m1, I1, flags);
-                        const float d2 = eval_pixel<G>(C, L, vx, vy, a, b, c, n2x, n2y, n2z, m2, I1, flags);
+                        const float d1 = eval_pixel<G>(C, L, vx, vy, a, b, c, n1x, n1y, n1z, m1, I1, f1);
+                        const float d2 = eval_pixel<G>(C, L, vx, vy, a, b, c, n2x, n2y, n2z, m2, I1, f2);
+                        flags |= (f1 << 3) | (f2 << 6);
                         const double D0 = (double)d0;
                         const double e1 = (double)__fsub_rn(d1, d0), e2 = (double)__fsub_rn(d2, d0);
                         acc0 = fma(D0, D0, acc0);
@@ -502,9 +536,10 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
                 } else {
                     const G n0x = PP->nx[0], n0y = PP->ny[0], n0z = PP->nz[0], m0 = PP->mnum[0];
                     for (int idx = tid; idx < m; idx += NT) {
-                        const float2 dr = rays[idx];
+                        const ray_t dr = rays[idx];
                         const float I1 = i1[idx];
-                        const G vx = gvcx + (G)dr.x, vy = gvcy + (G)dr.y;
+                        G vx, vy;
+                        RayStore<G>::unpack(dr, ray_inv_scale, gvcx, gvcy, vx, vy);
                         const G a = C.R[0] * vx + C.R[1] * vy + C.R[2];
                         const G b = C.R[3] * vx + C.R[4] * vy + C.R[5];
                         const G c = C.R[6] * vx + C.R[7] * vy + C.R[8];
@@ -518,16 +553,26 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
                     acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
                     acc4 = warp_sum(acc4); acc5 = warp_sum(acc5);
                 }
+                flags = __reduce_or_sync(0xffffffffu, flags);
                 if (lane == 0) {
                     double* rw = red + wid * 6;
                     rw[0] = acc0; rw[1] = acc1; rw[2] = acc2; rw[3] = acc3; rw[4] = acc4; rw[5] = acc5;
+                    wflags[wid] = flags;
                 }
-                const int any_flags = __syncthreads_or((int)flags);
+                __syncthreads();
 
                 if (tid == 0) {
+                    unsigned any_flags = 0;
+                    for (int w = 0; w < NW; w++) any_flags |= wflags[w];
                     if (any_flags) {
-                        S->status = (any_flags & FLAG_NAN) ? FM3D_FEAT_ABORT_NAN
-                                  : (any_flags & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
+                        // flag groups of f(x), f(x+h0 e0), f(x+h1 e1): the reference evaluates them in this
+                        // order and stops at the first failing one; inside one evaluation all bounding-box /
+                        // NaN tests precede the pixel tests
+                        int g = any_flags & 7;
+                        if (!g) g = (any_flags >> 3) & 7;
+                        if (!g) g = (any_flags >> 6) & 7;
+                        S->status = (g & FLAG_NAN) ? FM3D_FEAT_ABORT_NAN
+                                  : (g & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
                         PP->cmd = 0;
                     } else {
                         double s[6] = {0, 0, 0, 0, 0, 0};
@@ -596,7 +641,7 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
 }
 
 size_t tail_bytes(bool f32) {
-    size_t t = 16 + ((sizeof(RowTable) + 15) & ~(size_t)15) + sizeof(double) * 16 * 6 +
+    size_t t = 16 + ((sizeof(RowTable) + 15) & ~(size_t)15) + sizeof(double) * 16 * 6 + sizeof(unsigned) * 16 +
                ((sizeof(FeatureShared) + 15) & ~(size_t)15);
     t += f32 ? ((sizeof(PassParams<float>) + 15) & ~(size_t)15) : ((sizeof(PassParams<double>) + 15) & ~(size_t)15);
     return t + 16;
@@ -645,7 +690,7 @@ int run_normals(fm3d_ctx* ctx, NormalsArgs& A) {
     for (int l = 0; l <= A.pyr.levels; l++) {
         const double rs = (double)A.r / (double)(1 << l);
         int half = (int)ceil(1.3 * rs) + 8;
-        int ww = (2 * half + 15) & ~15, wh = 2 * half;
+        int ww = (2 * half + 16 + 15) & ~15, wh = 2 * half;   // +16: slack for the 16-pixel origin alignment
         if (ww > WIN_MAX_W) ww = WIN_MAX_W;
         if (wh > WIN_MAX_H) wh = WIN_MAX_H;
         A.win_w[l] = ww; A.win_h[l] = wh;

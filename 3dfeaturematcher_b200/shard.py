@@ -1,0 +1,61 @@
+"""One-process-per-GPU sharding of the hot path over torch.distributed (NCCL on the GPU box,
+gloo in the CPU tests).
+
+Every stage of the path is independent per query keypoint / per feature, so the
+only exchanges are the ones the north star names: broadcast the train-descriptor set and the
+two images from rank 0, gather the per-shard matches and normals.  No collective sits inside a
+kernel.  Shards are contiguous blocks of queries, so concatenating the gathered shards in rank
+order reproduces the single-GPU output order (ascending query index).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of `n` items owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n: int, world: int):
+    return [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
+
+
+def broadcast_(tensors, src: int = 0):
+    """In-place broadcast of the replicated inputs (train descriptors, images)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    for t in tensors:
+        dist.broadcast(t, src=src)
+
+
+def gather_rows(local: torch.Tensor, count: int, max_count: int):
+    """All-gather of a variable number of rows per rank.
+
+    local: (>=count, ...) tensor whose first `count` rows are valid.  Every rank contributes a
+    block padded to `max_count` rows; returns (rows of all ranks in rank order, counts per rank).
+    """
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local[:count].clone(), [count]
+    world = dist.get_world_size()
+    cnt = torch.tensor([count], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    pad = torch.zeros((max_count,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:count] = local[:count]
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0), counts
+
+
+def gather_matches(qidx_local: torch.Tensor, tidx: torch.Tensor, dist_: torch.Tensor, count: int,
+                   query_offset: int, max_count: int):
+    """Gathers NNDR matches of all shards; local query indices become global ones."""
+    q, counts = gather_rows(qidx_local + query_offset, count, max_count)
+    t, _ = gather_rows(tidx, count, max_count)
+    d, _ = gather_rows(dist_, count, max_count)
+    return q, t, d, counts

@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- features/sec of the match + triangulate + normal-optimise hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fm3d|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one synthetic stereo pair of BASELINE.json configs[1]:
+1280x720, 5 000 SIFT-128 float keypoints per GPU, pixelsRay 64, pyramids 3 (4 LM stages),
+NNDR 0.55, penalty as compiled today (fabs).  Inputs are resident in HBM for `value`; `e2e` is
+the same step through the host-buffer C-ABI calls (pinned host inputs, copies inside the
+timed region).  With N ranks every rank owns a contiguous shard of N*5000 query keypoints
+(weak scaling), rank 0's train descriptors and images are broadcast with NCCL and the
+per-shard matches and normals are all-gathered inside the timed region.
+
+`--impl reference` times the reference's CPU path (the plain-C oracle port: the reference
+itself cannot be built in this image) with all host threads on a bounded sample of the same
+workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, N_KP, N_DISTRACT = 1280, 720, 5000, 1000
+PIXELS_RAY, PYRAMIDS, NNDR_EPS, EPS_LMMIN = 64, 3, 0.55, 1e-10
+PENALTY = 0  # FM3D_PENALTY_FABS: the source as compiled by today's g++
+FLOP_PER_PIXEL_EVAL = 64.0  # algorithmic fp32 work of one pixel evaluation
+SEED = 1001
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_workload(n_ranks, rank):
+    """Global problem: one stereo pair with n_ranks*N_KP query keypoints; returns the global
+    arrays (every rank generates the same ones; rank 0's copy is the one that gets broadcast)."""
+    synth = importlib.import_module("3dfeaturematcher_b200.synth")
+    t0 = time.time()
+    case = synth.make_stereo_case(WIDTH, HEIGHT, N_KP * n_ranks, SEED, pixels_ray=PIXELS_RAY,
+                                  n_distractors=N_DISTRACT * n_ranks)
+    log(f"[rank {rank}] workload generated in {time.time() - t0:.1f}s")
+    return case
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_reference(case, n_features_sample, threads):
+    """Times the CPU port of the reference path (oracle/fm3d_oracle.c) on a bounded sample."""
+    from oracle import oracle_c as orc
+    cam = case["scene"].cam
+    nq = min(N_KP, case["desc1"].shape[0])
+    nt = nq + N_DISTRACT
+    q, t = case["desc1"][:nq], case["desc2"][:nt]
+    t0 = time.perf_counter()
+    idx, dist = orc.knn2_f32(q, t, threads=threads)
+    qi, ti, d = orc.nndr_filter(idx, dist, NNDR_EPS)
+    t_match = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    xyz_all, mask, xyz = orc.triangulate(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["kp1"], case["kp2"], qi, ti)
+    t_tri = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pyr1 = orc.build_pyramid(case["scene"].img1, PYRAMIDS)
+    pyr2 = orc.build_pyramid(case["scene"].img2, PYRAMIDS)
+    t_pyr = time.perf_counter() - t0
+    rng = np.random.default_rng(7)
+    sel = np.sort(rng.choice(xyz.shape[0], min(n_features_sample, xyz.shape[0]), replace=False))
+    t0 = time.perf_counter()
+    res = orc.optimize_normals(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                               PYRAMIDS, xyz[sel], PIXELS_RAY, EPS_LMMIN, penalty_mode=PENALTY, threads=threads,
+                               pyr1=pyr1, pyr2=pyr2)
+    t_norm = time.perf_counter() - t0
+    n_match = len(qi)
+    per_feature = (t_match + t_tri + t_pyr) / max(n_match, 1) + t_norm / max(len(sel), 1)
+    return {
+        "features_per_s": 1.0 / per_feature, "n_match": n_match, "n_sample": int(len(sel)),
+        "t_match_s": t_match, "t_triangulate_s": t_tri, "t_pyramid_s": t_pyr, "t_normals_sample_s": t_norm,
+        "pixel_evals_sample": res["pixel_evals"],
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    case = make_workload(1, 0)
+    n_sample = max(2 * threads, 32)
+    vals, t_all = [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = cpu_reference(case, n_sample, threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            vals.append(r["features_per_s"])
+            t_all.append(dt)
+    v = float(np.mean(vals))
+    sample = (f"matching {N_KP}x{N_KP + N_DISTRACT} in full, normal optimisation on a seeded sample of {r['n_sample']} "
+              f"of {r['n_match']} features, per-feature times summed")
+    out = {
+        "impl": "reference", "metric": "features/sec (match+triangulate+normal-opt)", "value": v, "unit": "features/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(t_all)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": v, "unit": "features/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(n_ranks):
+    return {"workload": f"BASELINE configs[1]: {WIDTH}x{HEIGHT} synthetic stereo pair, {N_KP} SIFT-128 float keypoints per GPU "
+                        f"(+{N_DISTRACT} distractors), pixelsRay {PIXELS_RAY}, pyramids {PYRAMIDS} (4 LM stages), NNDR {NNDR_EPS}",
+            "penalty_mode": "fabs", "geometry": "f64", "per_gpu_query_keypoints": N_KP, "global_query_keypoints": N_KP * n_ranks,
+            "parallelism": f"keypoint shards x{n_ranks}", "l2_flush_between_steps": True}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    api = importlib.import_module("3dfeaturematcher_b200.api")
+    shard = importlib.import_module("3dfeaturematcher_b200.shard")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the fm3d path has no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = api.Context(local_rank)
+    info = ctx.device_info()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    case = make_workload(world, rank)
+    cam = case["scene"].cam
+    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
+    ctx.set_g12(cam.g12)
+    H, W = case["scene"].img1.shape
+    nq_glob, nt = case["desc1"].shape[0], case["desc2"].shape[0]
+    lo, hi = shard.shard_bounds(nq_glob, world, rank)
+    nq = hi - lo
+    L1 = PYRAMIDS + 1
+
+    # ---- pinned host copies (e2e arm) and resident device copies (value arm)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+    h_q, h_t = pin(case["desc1"][lo:hi]), pin(case["desc2"])
+    h_kp1, h_kp2 = pin(case["kp1"][lo:hi]), pin(case["kp2"])
+    h_img1, h_img2 = pin(case["scene"].img1), pin(case["scene"].img2)
+    with torch.cuda.stream(stream):
+        d_q, d_kp1 = h_q.to(dev), h_kp1.to(dev)
+        # replicated inputs: only rank 0's copy is meaningful before the broadcast
+        d_t, d_kp2, d_img1, d_img2 = h_t.to(dev), h_kp2.to(dev), h_img1.to(dev), h_img2.to(dev)
+        if rank != 0 and world > 1:
+            for x in (d_t, d_kp2, d_img1, d_img2):
+                x.zero_()
+        d_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        d_dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+        d_qi = torch.empty(nq, dtype=torch.int32, device=dev)
+        d_ti = torch.empty(nq, dtype=torch.int32, device=dev)
+        d_do = torch.empty(nq, dtype=torch.float32, device=dev)
+        d_nm = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_xyz_all = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+        d_xyz = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+        d_mask = torch.empty(nq, dtype=torch.uint8, device=dev)
+        d_src = torch.empty(nq, dtype=torch.int32, device=dev)
+        d_ninl = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_normals = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+        d_status = torch.empty(nq, dtype=torch.int32, device=dev)
+        d_nfev = torch.zeros((nq, L1), dtype=torch.int32, device=dev)
+        d_npen = torch.zeros(nq, dtype=torch.int32, device=dev)
+        d_cost = torch.empty(nq, dtype=torch.float64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream.synchronize()
+
+    n_stage = 5
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_stage + 1)] for _ in range(args.steps)]
+
+    def device_step(events=None):
+        """One pass of the hot path on resident inputs (all work on the context's stream)."""
+        with torch.cuda.stream(stream):
+            if events: events[0].record(stream)
+            if world > 1:
+                shard.broadcast_([d_t, d_kp2, d_img1, d_img2], src=0)
+            ctx.match_knn2_f32_dev(d_q.data_ptr(), nq, d_t.data_ptr(), nt, 128, d_idx.data_ptr(), d_dist.data_ptr())
+            ctx.nndr_filter_dev(d_idx.data_ptr(), d_dist.data_ptr(), nq, NNDR_EPS, d_qi.data_ptr(), d_ti.data_ptr(),
+                                d_do.data_ptr(), d_nm.data_ptr())
+            if events: events[1].record(stream)
+            n_match = int(d_nm.item())          # sizes the following launches (4-byte D2H, as a host caller needs)
+            ctx.triangulate_dev(d_kp1.data_ptr(), nq, d_kp2.data_ptr(), nt, d_qi.data_ptr(), d_ti.data_ptr(), n_match,
+                                d_xyz_all.data_ptr(), d_mask.data_ptr(), d_xyz.data_ptr(), d_src.data_ptr(), d_ninl.data_ptr())
+            if events: events[2].record(stream)
+            ctx.set_images_dev(d_img1.data_ptr(), d_img2.data_ptr(), W, H, W, PYRAMIDS)
+            if events: events[3].record(stream)
+            n_inl = int(d_ninl.item())
+            ctx.optimize_normals_dev(d_xyz.data_ptr(), n_inl, PIXELS_RAY, EPS_LMMIN, PENALTY, d_normals.data_ptr(),
+                                     d_status.data_ptr(), d_nfev.data_ptr(), d_npen.data_ptr(), d_cost.data_ptr())
+            if events: events[4].record(stream)
+            if world > 1:
+                g_q, g_t, g_d, counts = shard.gather_matches(d_qi, d_ti, d_do, n_match, lo, nq)
+                g_n, _ = shard.gather_rows(d_normals, n_inl, nq)
+                g_s, _ = shard.gather_rows(d_status, n_inl, nq)
+            if events: events[5].record(stream)
+        return n_match, n_inl
+
+    def host_step():
+        """The same pass through the host-buffer C-ABI entry points (copies inside)."""
+        if world > 1:
+            with torch.cuda.stream(stream):
+                shard.broadcast_([d_t, d_kp2, d_img1, d_img2], src=0)
+            stream.synchronize()
+        qi, ti, d = ctx.match_nndr(h_q.numpy(), h_t.numpy(), NNDR_EPS)
+        xyz_all, mask, xyz, src = ctx.triangulate(h_kp1.numpy(), h_kp2.numpy(), qi, ti)
+        ctx.set_images(h_img1.numpy(), h_img2.numpy(), PYRAMIDS)
+        res = ctx.optimize_normals(xyz, PIXELS_RAY, EPS_LMMIN, PENALTY)
+        h2d = (h_q.numel() + h_t.numel()) * 4 + (h_kp1.numel() + h_kp2.numel()) * 4 + qi.nbytes + ti.nbytes + \
+            h_img1.numel() + h_img2.numel() + xyz.nbytes
+        d2h = qi.nbytes + ti.nbytes + d.nbytes + xyz_all.nbytes + mask.nbytes + xyz.nbytes + src.nbytes + \
+            res["normals"].nbytes + res["status"].nbytes + res["nfev"].nbytes + res["npenalty"].nbytes + res["cost"].nbytes
+        return len(qi), xyz.shape[0], h2d, d2h
+
+    def barrier():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        n_match, n_inl = device_step()
+        flush_l2()
+    barrier()
+
+    # ---- timed region: device-resident arm
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    k0, c0 = ctx.launch_counters()
+    t_dev_ms = 0.0
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        n_match, n_inl = device_step(ev[s])
+        flush_l2()                      # not between events 0..5 of a step: excluded from the step time
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    k1, c1 = ctx.launch_counters()
+    stage_ms = np.zeros(n_stage)
+    for s in range(args.steps):
+        for j in range(n_stage):
+            stage_ms[j] += ev[s][j].elapsed_time(ev[s][j + 1])
+    t_dev_ms = float(stage_ms.sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region: end-to-end arm (host buffers)
+    for _ in range(2):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        hm, hi_, h2d, d2h = host_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # ---- reduce over ranks: max time, summed features
+    tm = torch.tensor([t_dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    feats = torch.tensor([float(n_match), float(hm)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(feats, op=dist.ReduceOp.SUM)
+    t_dev_ms, t_e2e_ms = float(tm[0]), float(tm[1])
+    tot_feat, tot_feat_e2e = float(feats[0]), float(feats[1])
+
+    if rank == 0:
+        nfev = d_nfev[:n_inl].cpu().numpy().astype(np.int64)
+        status = d_status[:n_inl].cpu().numpy()
+        npen = d_npen[:n_inl].cpu().numpy()
+        # algorithmic work of the normal optimiser: sum over features and levels of nfev * m;
+        # every bench feature has the full disc (m = 12853 at r = 64)
+        m_disc = sum(2 * int(np.floor(np.sqrt(PIXELS_RAY ** 2 - j * j))) + 1 for j in range(-PIXELS_RAY, PIXELS_RAY + 1))
+        pixel_evals = float(nfev.sum()) * m_disc
+        t_norm_s = stage_ms[3] / args.steps * 1e-3
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+        fp32_peak = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
+        achieved = pixel_evals * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        bf16_peak = peaks.get("bf16_tflops", 1590.0)
+        pyr_bytes = sum(2 * 1.25 * (W >> l) * (H >> l) for l in range(PYRAMIDS))
+        match_pairs = float(nq) * nt
+        roofline = {
+            "kernel": "normals_kernel<double> (K6: LM normal search, one CTA per feature)",
+            "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+            "traffic": None,
+            "note": "compute-bound kernel (SURVEY 8d): algorithmic 64 flop x sum(nfev*m) pixel evaluations / CUDA-event time; "
+                    "peak = SMs*128*2*f_max (nominal fp32; MEASURED_PEAKS.json has no fp32 figure); geometry runs in fp64",
+            "pixel_evals_per_launch": pixel_evals, "ms_per_launch": t_norm_s * 1e3,
+            "hbm_compulsory_gbs": (n_inl * 44e3 / t_norm_s) / 1e9, "hbm_peak_gbs": hbm_peak,
+        }
+        roofline_other = {
+            "matcher_tc": {"bound": "tensor", "achieved": match_pairs * 256 / (stage_ms[0] / args.steps * 1e-3) / 1e12,
+                           "peak": bf16_peak, "unit": "TFLOP/s", "ms": stage_ms[0] / args.steps,
+                           "note": "includes operand re-tiling, NNDR filter and (N>1) the NCCL broadcast"},
+            "pyrdown": {"bound": "hbm", "achieved": pyr_bytes / (stage_ms[2] / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "ms": stage_ms[2] / args.steps, "note": "3 launches + 2 device copies of 0.9 MB images: launch-bound"},
+        }
+        cpu = cpu_reference(case, max(2 * (os.cpu_count() or 1), 32), os.cpu_count() or 1)
+        value = tot_feat * args.steps / (t_dev_ms * 1e-3)
+        out = {
+            "metric": "features/sec (match+triangulate+normal-opt)", "value": value, "unit": "features/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": tot_feat_e2e * args.steps / (t_e2e_ms * 1e-3), "unit": "features/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e_ms / args.steps},
+            "gpu_launches": int(k1 - k0),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_other": roofline_other,
+            "cpu_baseline": {"value": cpu["features_per_s"], "unit": "features/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": f"full {N_KP}x{N_KP + N_DISTRACT} matching + normal optimisation of {cpu['n_sample']} seeded features "
+                                       f"of {cpu['n_match']}, per-feature times summed", "detail": cpu},
+            "stage_ms_per_step": {"match+nndr": stage_ms[0] / args.steps, "triangulate": stage_ms[1] / args.steps,
+                                  "pyramids": stage_ms[2] / args.steps, "normals": stage_ms[3] / args.steps,
+                                  "gather": stage_ms[4] / args.steps},
+            "features_per_step": {"matches": tot_feat, "inliers_rank0": int(n_inl), "ok_rank0": int((status == 0).sum()),
+                                  "wall_touching_rank0": int((npen > 0).sum()), "nfev_mean_per_level": nfev.mean(0).tolist()},
+            "wall_s_device_arm": wall_dev, "gpu": info["name"],
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fm3d", choices=["fm3d", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

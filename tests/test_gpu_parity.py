@@ -260,9 +260,11 @@ def test_optimize_normals_aborts_and_clipped_discs(ctx):
     setup_ctx(ctx, case, 2)
     Z = 1.9
     # 3-D points on the rays of chosen image-1 pixels: left border, outside, top border, corner
-    pix = np.array([[8.0, 240.0], [300.0, 6.0], [320.0, 472.0], [632.0, 470.0], [600.0, 30.0]])
-    rays = orc.undistort_points(cam.K, cam.dist, pix)
-    pts = np.concatenate([rays * Z, np.full((pix.shape[0], 1), Z)], axis=1)
+    pix = np.array([[8.0, 240.0], [300.0, 6.0], [320.0, 472.0], [250.0, 470.0], [400.0, 473.0]])
+    # true surface points under those pixels (ray-cast into the scene), so the photometric problem is well posed
+    x, y, _ = synth.undistort_exact((pix[:, 0] - cam.K[0, 2]) / cam.K[0, 0], (pix[:, 1] - cam.K[1, 2]) / cam.K[1, 1], cam.dist)
+    pts, _, hit = synth._raycast(case["scene"].planes, np.zeros(3), np.stack([x, y, np.ones_like(x)], axis=1))
+    assert hit.all()
     far = np.array([[9.0, 0.3, Z]])                       # projects far outside image 1: no pixels
     xyz = np.concatenate([case["X"][:1], pts, far, case["X"][1:2]])
     res = ctx.optimize_normals(xyz, 32, 1e-10, 2)
