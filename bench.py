@@ -377,7 +377,7 @@ def run_gpu_arm(args):
             "pyrdown": {"bound": "hbm", "achieved": pyr_bytes / (stage_ms[2] / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
                         "unit": "GB/s", "ms": stage_ms[2] / args.steps, "note": "3 launches + 2 device copies of 0.9 MB images: launch-bound"},
         }
-        cpu = cpu_reference(case, max(2 * (os.cpu_count() or 1), 32), os.cpu_count() or 1)
+        cpu = cpu_reference(case, max(2 * (os.cpu_count() or 1), 32), os.cpu_count() or 1) if world == 1 else None
         value = tot_feat * args.steps / (t_dev_ms * 1e-3)
         out = {
             "metric": "features/sec (match+triangulate+normal-opt)", "value": value, "unit": "features/s",
@@ -390,9 +390,10 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": roofline,
             "roofline_other": roofline_other,
-            "cpu_baseline": {"value": cpu["features_per_s"], "unit": "features/s", "cores": os.cpu_count() or 1, "kind": "port",
-                             "sample": f"full {N_KP}x{N_KP + N_DISTRACT} matching + normal optimisation of {cpu['n_sample']} seeded features "
-                                       f"of {cpu['n_match']}, per-feature times summed", "detail": cpu},
+            "cpu_baseline": None if cpu is None else {
+                "value": cpu["features_per_s"], "unit": "features/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": f"full {N_KP}x{N_KP + N_DISTRACT} matching + normal optimisation of {cpu['n_sample']} seeded features "
+                          f"of {cpu['n_match']}, per-feature times summed", "detail": cpu},
             "stage_ms_per_step": {"match+nndr": stage_ms[0] / args.steps, "triangulate": stage_ms[1] / args.steps,
                                   "pyramids": stage_ms[2] / args.steps, "normals": stage_ms[3] / args.steps,
                                   "gather": stage_ms[4] / args.steps},

@@ -1,0 +1,81 @@
+"""The plain-C oracle against the committed golden vectors (tests/golden/*.npz, written by
+tools/make_golden.py from cv2.undistortPoints / projectPoints / triangulatePoints / pyrDown /
+BFMatcher and the cv2-based restatement of the reference).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from common import angle_deg, orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def prim():
+    return np.load(os.path.join(GOLD, "primitives.npz"))
+
+
+@pytest.fixture(scope="module")
+def nrm():
+    return np.load(os.path.join(GOLD, "normals.npz"))
+
+
+def test_undistort_and_project(prim):
+    np.testing.assert_allclose(orc.undistort_points(prim["K"], prim["dist"], prim["pts"]), prim["undistorted"], rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(orc.project_points(prim["K"], prim["dist"], prim["g12"], 1, prim["X"]), prim["proj1"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(orc.project_points(prim["K"], prim["dist"], prim["g12"], 2, prim["X"]), prim["proj2"], rtol=0, atol=1e-10)
+
+
+def test_triangulate(prim):
+    xyz_all, mask, xyz = orc.triangulate(prim["K"], prim["dist"], prim["g12"], 1.5, 2.4, prim["kp1"], prim["kp2"])
+    np.testing.assert_array_equal(mask, prim["mask"])
+    assert 0 < mask.sum() < mask.size
+    np.testing.assert_allclose(xyz_all, prim["xyz_all"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(xyz, prim["xyz"], rtol=1e-10, atol=1e-12)
+
+
+def test_pyrdown_bit_exact(prim):
+    lv = orc.pyramid_levels(orc.build_pyramid(prim["img"], 3), prim["img"].shape[1], prim["img"].shape[0], 3)
+    for k in (1, 2, 3):
+        np.testing.assert_array_equal(lv[k], prim[f"pyr{k}"])
+
+
+def test_matchers(prim):
+    idx, dist = orc.knn2_f32(prim["q"], prim["t"])
+    np.testing.assert_array_equal(idx, prim["idx_f"])
+    np.testing.assert_array_equal(dist, prim["dist_f"])
+    assert tuple(idx[0]) == (5, 11)                      # duplicates: lower train index first
+    idx, dist = orc.knn2_hamming(prim["qb"], prim["tb"])
+    np.testing.assert_array_equal(idx, prim["idx_b"])
+    np.testing.assert_array_equal(dist, prim["dist_b"])
+    q, t, d = orc.nndr_filter(prim["idx_f"], prim["dist_f"], 0.55)
+    np.testing.assert_array_equal(q, prim["nndr_q"])
+    np.testing.assert_array_equal(t, prim["nndr_t"])
+    np.testing.assert_array_equal(d, prim["nndr_d"])
+
+
+@pytest.mark.parametrize("mode,name", [(0, "fabs"), (1, "intabs"), (2, "off")])
+def test_normal_optimiser(nrm, mode, name):
+    r = orc.optimize_normals(nrm["K"], nrm["dist"], nrm["g12"], float(nrm["zmin"]), float(nrm["zmax"]), nrm["img1"], nrm["img2"],
+                             2, nrm["xyz"], 16, 1e-10, penalty_mode=mode, threads=2)
+    np.testing.assert_array_equal(r["status"], nrm[f"{name}_status"])
+    np.testing.assert_array_equal(r["m"], nrm[f"{name}_m"])
+    np.testing.assert_array_equal(r["nfev"], nrm[f"{name}_nfev"])          # same LM trajectory as the cv2 restatement
+    np.testing.assert_array_equal(r["npenalty"], nrm[f"{name}_npenalty"])
+    assert (angle_deg(r["normals"], nrm[f"{name}_normals"]) < 1e-5).all()
+    np.testing.assert_allclose(r["cost"], nrm[f"{name}_cost"], rtol=1e-9)
+    if name == "off":
+        assert (angle_deg(r["normals"], nrm["gt_normal"]) < 0.5).all()    # and it finds the true facet normals
+
+
+def test_cost_frames_patches(nrm):
+    for lvl in range(3):
+        c, m, st = orc.evaluate_cost(nrm["K"], nrm["dist"], nrm["g12"], float(nrm["zmin"]), float(nrm["zmax"]), nrm["img1"],
+                                     nrm["img2"], 2, nrm["xyz"], nrm["cost_pt"], 16, lvl, 2)
+        np.testing.assert_allclose(c, nrm[f"cost_l{lvl}"], rtol=1e-10)
+    fr = orc.feature_frames(nrm["xyz"], nrm["off_normals"], nrm["gravity"])
+    np.testing.assert_allclose(fr, nrm["frames"], rtol=0, atol=1e-15)
+    p, ip = orc.extract_patches(nrm["K"], nrm["dist"], nrm["img1"], nrm["frames"], 0.05, 0.25)
+    np.testing.assert_array_equal(p, nrm["patches"])
+    np.testing.assert_allclose(ip, nrm["image_points"], rtol=0, atol=1e-10)

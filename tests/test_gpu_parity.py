@@ -311,3 +311,49 @@ def test_frames_and_patches(ctx):
     gp1, _ = ctx.project_groups(1, nb)
     p1, _ = ctx.extract_patches(frames, 0.05, 0.25, want_points=False)
     assert (np.abs(gp1.astype(int) - p1.astype(int)) <= 1).all()
+
+
+# ------------------------------------------------------------------ committed golden vectors (cv2)
+def test_gpu_against_golden_vectors(ctx):
+    """The CUDA path against tests/golden/*.npz: outputs of cv2.undistortPoints / triangulatePoints /
+    pyrDown / BFMatcher and of the cv2-based restatement of the reference (tools/make_golden.py)."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    p = np.load(os.path.join(gold, "primitives.npz"))
+    ctx.set_camera(p["K"], p["dist"], 1.5, 2.4)
+    ctx.set_g12(p["g12"])
+    np.testing.assert_allclose(ctx.undistort_points(p["pts"]), p["undistorted"], rtol=1e-12, atol=1e-13)
+    xyz_all, mask, xyz, _ = ctx.triangulate(p["kp1"], p["kp2"])
+    np.testing.assert_array_equal(mask, p["mask"])
+    np.testing.assert_allclose(xyz_all, p["xyz_all"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(xyz, p["xyz"], rtol=1e-9, atol=1e-12)
+    ctx.set_images(p["img"], p["img"], 3)
+    for k in (1, 2, 3):
+        np.testing.assert_array_equal(ctx.get_pyramid_level(1, k), p[f"pyr{k}"])
+    idx, dist = ctx.match_knn2_f32(p["q"], p["t"])
+    np.testing.assert_array_equal(idx, p["idx_f"])
+    np.testing.assert_array_equal(dist, p["dist_f"])
+    idx, dist = ctx.match_knn2_hamming(p["qb"], p["tb"])
+    np.testing.assert_array_equal(idx, p["idx_b"])
+    np.testing.assert_array_equal(dist, p["dist_b"])
+    qi, ti, d = ctx.match_nndr(p["q"], p["t"], 0.55)
+    np.testing.assert_array_equal(qi, p["nndr_q"])
+    np.testing.assert_array_equal(ti, p["nndr_t"])
+
+    g = np.load(os.path.join(gold, "normals.npz"))
+    ctx.set_camera(g["K"], g["dist"], float(g["zmin"]), float(g["zmax"]))
+    ctx.set_g12(g["g12"])
+    ctx.set_images(g["img1"], g["img2"], 2)
+    for lvl in range(3):
+        cost, m, st = ctx.evaluate_normals(g["xyz"], g["cost_pt"], 16, lvl, 2)
+        np.testing.assert_allclose(cost, g[f"cost_l{lvl}"], rtol=1e-5)
+    res = ctx.optimize_normals(g["xyz"], 16, 1e-10, 2)
+    np.testing.assert_array_equal(res["status"], g["off_status"])
+    assert (angle_deg(res["normals"], g["off_normals"]) <= 0.5).all()
+    assert (angle_deg(res["normals"], g["gt_normal"]) <= 0.5).all()
+    frames = ctx.feature_frames(g["xyz"], g["off_normals"], g["gravity"])
+    np.testing.assert_allclose(frames, g["frames"], rtol=0, atol=1e-14)
+    patches, ip = ctx.extract_patches(g["frames"], 0.05, 0.25)
+    np.testing.assert_allclose(ip, g["image_points"], rtol=0, atol=1e-9)
+    diff = patches.astype(int) - g["patches"].astype(int)
+    assert (np.abs(diff) <= 1).all() and (diff != 0).mean() < 1e-3

@@ -1,0 +1,55 @@
+"""world_size-2 gloo test of the sharding helpers used by the N>1 path (CPU)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = importlib.import_module("3dfeaturematcher_b200.shard")
+    from oracle import oracle_c as orc      # the compute stand-in of this CPU test
+    synth = importlib.import_module("3dfeaturematcher_b200.synth")
+    q, t, _ = synth.make_float_descriptors(301, 60, 9)
+    # replicated inputs: only rank 0 holds the real train set before the broadcast
+    tt = torch.from_numpy(t.copy()) if rank == 0 else torch.zeros(t.shape, dtype=torch.float32)
+    shard.broadcast_([tt], src=0)
+    lo, hi = shard.shard_bounds(q.shape[0], world, rank)
+    idx, dd = orc.knn2_f32(q[lo:hi], tt.numpy())
+    qi, ti, d = orc.nndr_filter(idx, dd, 0.55)
+    n = len(qi)
+    cap = max(shard.shard_sizes(q.shape[0], world))
+    pad = lambda a, dt: torch.from_numpy(np.concatenate([a, np.zeros(cap - n, a.dtype)]).astype(dt))  # noqa: E731
+    gq, gt, gd, counts = shard.gather_matches(pad(qi, np.int32), pad(ti, np.int32), pad(d, np.float32), n, lo, cap)
+    if rank == 0:
+        ret["q"], ret["t"], ret["d"], ret["counts"] = gq.numpy(), gt.numpy(), gd.numpy(), counts
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_matching_equals_single_process():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    shard = importlib.import_module("3dfeaturematcher_b200.shard")
+    assert shard.shard_sizes(10, 3) == [4, 3, 3] and shard.shard_bounds(10, 3, 2) == (7, 10)
+    assert sum(shard.shard_sizes(5, 8)) == 5
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, 29533 + os.getpid() % 500, ret), nprocs=2, join=True)
+        from oracle import oracle_c as orc
+        synth = importlib.import_module("3dfeaturematcher_b200.synth")
+        q, t, _ = synth.make_float_descriptors(301, 60, 9)
+        idx, dd = orc.knn2_f32(q, t)
+        qi, ti, d = orc.nndr_filter(idx, dd, 0.55)
+        np.testing.assert_array_equal(ret["q"], qi)       # rank-order concatenation == ascending query order
+        np.testing.assert_array_equal(ret["t"], ti)
+        np.testing.assert_array_equal(ret["d"], d)
+        assert sum(ret["counts"]) == len(qi)

@@ -1,0 +1,90 @@
+"""Writes tests/golden/*.npz: inputs and outputs of the reference's arithmetic as computed by the
+OpenCV routines the reference calls (cv2 4.13 through oracle/oracle_cv.py).  Run in the build
+container (cv2 is needed); the fixtures are committed so that tests never depend on cv2 or on
+/root/reference at run time.
+
+    python tools/make_golden.py
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle_cv as oc  # noqa: E402
+
+synth = importlib.import_module("3dfeaturematcher_b200.synth")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def primitives():
+    rng = np.random.default_rng(20261018)
+    # the reference's own camera (build/settings.yml) and the pose of its two frames
+    K = np.array([[572.4765, 0, 549.75189], [0, 572.69354, 411.68039], [0, 0, 1.0]])
+    dist = synth.SETTINGS_DIST
+    cam = oc.Camera(K, dist, 1.5, 2.4)
+    pos1 = [5.301099, 8.031408, 1.977258, 0.153433, 0.149941, -2.658648]
+    pos2 = [4.735536, 7.691893, 1.913166, 0.252828, 0.048977, -2.676886]
+    g12 = cam.setg12(pos1[:3], pos2[:3], pos1[3:], pos2[3:], synth.SETTINGS_RODRIGUES_IC, synth.SETTINGS_TRANSLATION_IC)
+    pts = np.stack([rng.uniform(0, 1024, 400), rng.uniform(0, 768, 400)], 1)
+    und = oc.undistort_points(cam, pts)
+    X = np.stack([rng.uniform(-1.2, 1.2, 300), rng.uniform(-0.9, 0.9, 300), rng.uniform(1.5, 2.4, 300)], 1)
+    r2, t2 = oc.decompose_transformation(g12)
+    proj1 = oc.project_points(cam, X, np.zeros(3), np.zeros(3))
+    proj2 = oc.project_points(cam, X, r2, t2)
+    # matched keypoints = projections of X (+ noise, + gross outliers for the depth gate)
+    kp1 = proj1.astype(np.float32)
+    kp2 = (proj2 + rng.normal(0, 0.4, proj2.shape)).astype(np.float32)
+    kp2[::9, 0] += 35
+    xyz_all, mask, xyz = oc.triangulate(cam, kp1, kp2)
+    img = rng.integers(0, 256, (53, 71), dtype=np.uint8)
+    pyr = oc.compute_pyramids(img, 3)
+    q, t, _ = synth.make_float_descriptors(60, 30, 3)
+    t[5] = t[11] = t[40]
+    q[0] = t[40]
+    idx_f, dist_f = oc.knn2(q, t, False)
+    qb, tb, _ = synth.make_binary_descriptors(60, 30, 4)
+    tb[2] = tb[8] = tb[33]
+    qb[0] = tb[33]
+    idx_b, dist_b = oc.knn2(qb, tb, True)
+    qi, ti, d = oc.nndr_filter(idx_f, dist_f, 0.55)
+    np.savez_compressed(os.path.join(OUT, "primitives.npz"), K=K, dist=dist, g12=g12, pos1=pos1, pos2=pos2,
+                        pts=pts, undistorted=und, X=X, proj1=proj1, proj2=proj2, kp1=kp1, kp2=kp2, xyz_all=xyz_all,
+                        mask=mask, xyz=xyz, img=img, pyr1=pyr[1], pyr2=pyr[2], pyr3=pyr[3], q=q, t=t, idx_f=idx_f,
+                        dist_f=dist_f, qb=qb, tb=tb, idx_b=idx_b, dist_b=dist_b, nndr_q=qi, nndr_t=ti, nndr_d=d)
+
+
+def normals():
+    case = synth.make_stereo_case(320, 240, 6, 77, pixels_ray=16, n_distractors=4)
+    sc = case["scene"]
+    cam = oc.Camera(sc.cam.K, sc.cam.dist, sc.cam.z_min, sc.cam.z_max, sc.cam.g12)
+    pyr1, pyr2 = oc.compute_pyramids(sc.img1, 2), oc.compute_pyramids(sc.img2, 2)
+    xyz_all, mask, xyz = oc.triangulate(cam, case["kp1"], case["kp2_true"])
+    out = {"img1": sc.img1, "img2": sc.img2, "K": sc.cam.K, "dist": sc.cam.dist, "g12": sc.cam.g12,
+           "zmin": sc.cam.z_min, "zmax": sc.cam.z_max, "kp1": case["kp1"], "kp2": case["kp2_true"], "xyz": xyz_all,
+           "gt_normal": case["normal"]}
+    for mode, name in ((oc.PENALTY_FABS, "fabs"), (oc.PENALTY_INT_ABS, "intabs"), (oc.PENALTY_OFF, "off")):
+        r = oc.optimize_normals(cam, xyz_all, pyr1, pyr2, 16, 1e-10, mode)
+        for k in ("normals", "status", "nfev", "npenalty", "cost", "m"):
+            out[f"{name}_{k}"] = r[k]
+    pt = np.array([oc.car2sph(x / np.linalg.norm(x)) for x in xyz_all]) + 0.1
+    for lvl in range(3):
+        out[f"cost_l{lvl}"] = np.array([oc.evaluate_cost(cam, x, p, pyr1, pyr2, 16, lvl, oc.PENALTY_OFF)[0]
+                                        for x, p in zip(xyz_all, pt)])
+    out["cost_pt"] = pt
+    g = oc.gravity_from_settings(synth.SETTINGS_RODRIGUES_IC)
+    frames = oc.feature_frames(xyz_all, out["off_normals"], g)
+    ref = oc.reference_squared_neighborhood(0.05, 0.25)
+    patches, ips = zip(*[oc.project_reference_points(cam, sc.img1, ref, F) for F in frames])
+    out.update(gravity=g, frames=frames, patches=np.array(patches), image_points=np.array(ips))
+    np.savez_compressed(os.path.join(OUT, "normals.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    primitives()
+    normals()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
