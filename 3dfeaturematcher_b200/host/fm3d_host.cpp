@@ -1,0 +1,404 @@
+// fm3d_host.cpp -- the reference's four classes as thin adapters over the C-ABI of libfm3d.
+//
+// Same class names, method names, argument meaning and output conventions as the reference
+// (DescriptorsMatcher/descriptorsmatcher.cpp, Triangulator/{singlecameratriangulator,
+// normaloptimizer,neighborhoodsgenerator}.cpp): outputs that the reference appends to are
+// appended to, outputs it clears are cleared, failed features are erased from points3D in
+// place.  What differs is documented in the headers (injected features, no visualiser thread,
+// errors as std::runtime_error instead of exit()).  No arithmetic of the hot path lives here.
+#include <cmath>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/fm3d.h"
+#include "include/DescriptorsMatcher/descriptorsmatcher.h"
+#include "include/Triangulator/neighborhoodsgenerator.h"
+#include "include/Triangulator/normaloptimizer.h"
+#include "include/Triangulator/singlecameratriangulator.h"
+#include "include/tools.h"
+
+namespace {
+
+fm3d_ctx* host_ctx() {
+    static fm3d_ctx* ctx = nullptr;
+    if (!ctx) {
+        int dev = 0;
+        if (const char* e = getenv("FM3D_DEVICE")) dev = atoi(e);
+        int rc = fm3d_ctx_create(dev, &ctx);
+        if (rc != FM3D_OK) throw std::runtime_error("fm3d: no usable sm_100 GPU (libfm3d has no CPU path), code " + std::to_string(rc));
+    }
+    return ctx;
+}
+
+void check(fm3d_ctx* ctx, int rc, const char* what) {
+    if (rc != FM3D_OK) throw std::runtime_error(std::string("fm3d: ") + what + ": " + fm3d_last_error(ctx));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ tools
+void rodriguesToMatrix(const cv::Vec3d& r, cv::Matx33d& R) {
+    const double th = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R(i, j) = i == j ? 1.0 : 0.0;
+    if (th < 2.220446049250313e-16) return;
+    const double c = std::cos(th), s = std::sin(th), c1 = 1 - c;
+    const double k[3] = {r[0] / th, r[1] / th, r[2] / th};
+    const double kx[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R(i, j) = c * (i == j ? 1.0 : 0.0) + c1 * k[i] * k[j] + s * kx[i * 3 + j];
+}
+
+void matrixToRodrigues(const cv::Matx33d& R, cv::Vec3d& r) {
+    const double rx = R(2, 1) - R(1, 2), ry = R(0, 2) - R(2, 0), rz = R(1, 0) - R(0, 1);
+    const double s = std::sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R(0, 0) + R(1, 1) + R(2, 2) - 1) * 0.5;
+    c = c > 1 ? 1 : (c < -1 ? -1 : c);
+    const double th = std::acos(c);
+    if (s < 1e-5) {
+        if (c > 0) { r = cv::Vec3d(0, 0, 0); return; }
+        double t = (R(0, 0) + 1) * 0.5; double x = std::sqrt(t > 0 ? t : 0);
+        t = (R(1, 1) + 1) * 0.5; double y = std::sqrt(t > 0 ? t : 0) * (R(0, 1) < 0 ? -1.0 : 1.0);
+        t = (R(2, 2) + 1) * 0.5; double z = std::sqrt(t > 0 ? t : 0) * (R(0, 2) < 0 ? -1.0 : 1.0);
+        if (std::fabs(x) < std::fabs(y) && std::fabs(x) < std::fabs(z) && (R(1, 2) > 0) != (y * z > 0)) z = -z;
+        const double n = th / std::sqrt(x * x + y * y + z * z);
+        r = cv::Vec3d(x * n, y * n, z * n);
+        return;
+    }
+    const double vth = 1 / (2 * s) * th;
+    r = cv::Vec3d(rx * vth, ry * vth, rz * vth);
+}
+
+void composeTransformation(const cv::Matx33d& R, const cv::Vec3d& T, cv::Matx44d& G) {
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) G(i, j) = R(i, j); G(i, 3) = T(i); }
+    G(3, 0) = 0; G(3, 1) = 0; G(3, 2) = 0; G(3, 3) = 1;
+}
+
+void decomposeTransformation(const cv::Matx44d& G, cv::Vec3d& r, cv::Vec3d& t) {
+    cv::Matx33d R;
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R(i, j) = G(i, j); t(i) = G(i, 3); }
+    matrixToRodrigues(R, r);
+}
+
+void getSkewMatrix(const cv::Vec3d& v, cv::Matx33d& k) {
+    k(0, 0) = 0; k(0, 1) = -v[2]; k(0, 2) = v[1];
+    k(1, 0) = v[2]; k(1, 1) = 0; k(1, 2) = -v[0];
+    k(2, 0) = -v[1]; k(2, 1) = v[0]; k(2, 2) = 0;
+}
+
+void car2sph(const cv::Vec3d& v, double& phi, double& theta) {
+    theta = std::atan2(v[2], std::sqrt(v[0] * v[0] + v[1] * v[1]));
+    phi = std::atan2(v[1], v[0]);
+}
+
+void sph2car(const double phi, const double theta, cv::Vec3d& v) {
+    v[0] = std::cos(theta) * std::cos(phi);
+    v[1] = std::cos(theta) * std::sin(phi);
+    v[2] = std::sin(theta);
+}
+
+// ------------------------------------------------------------------------- DescriptorsMatcher
+DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv::Mat& frame_b)
+    : image_a_(frame_a), image_b_(frame_b), binary_(false), have_features_(false) {
+    std::string extractorType = (std::string)fs["FeatureOptions"]["ExtractorType"];
+    // the reference picks the LSH (binary) matcher for these (descriptorsmatcher.cpp:64-67)
+    binary_ = extractorType == "ORB" || extractorType == "BRISK" || extractorType == "FREAK";
+    host_ctx();
+}
+
+DescriptorsMatcher::~DescriptorsMatcher() {}
+
+void DescriptorsMatcher::setFeatures(const std::vector<cv::KeyPoint>& ka, const cv::Mat& da,
+                                     const std::vector<cv::KeyPoint>& kb, const cv::Mat& db) {
+    kpts_a_ = ka; kpts_b_ = kb; desc_a_ = da; desc_b_ = db;
+    have_features_ = true;
+}
+
+void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv::KeyPoint>& kb, cv::Mat& da, cv::Mat& db) {
+    if (have_features_) { ka = kpts_a_; kb = kpts_b_; da = desc_a_; db = desc_b_; return; }
+    if (!da.empty() && !db.empty()) return;  // pre-filled by the caller
+    throw std::runtime_error("fm3d: DescriptorsMatcher needs injected features (setFeatures): detection and "
+                             "description are upstream of the GPU hot path");
+}
+
+void DescriptorsMatcher::knn(const cv::Mat& q, const cv::Mat& t, std::vector<std::vector<cv::DMatch> >& out) {
+    fm3d_ctx* ctx = host_ctx();
+    const int nq = q.rows, nt = t.rows;
+    std::vector<int32_t> idx((size_t)nq * 2, -1);
+    std::vector<float> dist((size_t)nq * 2, 0.f);
+    if (binary_) {
+        if (q.depth() != CV_8U) throw std::runtime_error("fm3d: binary extractor needs CV_8U descriptors");
+        check(ctx, fm3d_match_knn2_hamming(ctx, q.ptr<uint8_t>(), nq, t.ptr<uint8_t>(), nt, q.cols, idx.data(), dist.data()), "knn (hamming)");
+    } else {
+        if (q.depth() != CV_32F) throw std::runtime_error("fm3d: float extractor needs CV_32F descriptors");
+        check(ctx, fm3d_match_knn2_f32(ctx, q.ptr<float>(), nq, t.ptr<float>(), nt, q.cols, idx.data(), dist.data()), "knn (L2)");
+    }
+    out.clear();
+    out.resize(nq);
+    for (int i = 0; i < nq; i++)
+        for (int k = 0; k < 2; k++)
+            if (idx[2 * i + k] >= 0) out[i].push_back(cv::DMatch(i, idx[2 * i + k], dist[2 * i + k]));
+}
+
+void DescriptorsMatcher::crosscompare(std::vector<std::vector<cv::DMatch> >& matchesAB, std::vector<std::vector<cv::DMatch> >& matchesBA,
+                                      std::vector<cv::KeyPoint>& kpts_a, std::vector<cv::KeyPoint>& kpts_b,
+                                      cv::Mat& da, cv::Mat& db) {
+    features(kpts_a, kpts_b, da, db);
+    knn(da, db, matchesAB);
+    knn(db, da, matchesBA);
+}
+
+void DescriptorsMatcher::compare(std::vector<std::vector<cv::DMatch> >& matches, std::vector<cv::KeyPoint>& kpts_a,
+                                 std::vector<cv::KeyPoint>& kpts_b, cv::Mat& da, cv::Mat& db) {
+    features(kpts_a, kpts_b, da, db);
+    knn(da, db, matches_);
+    matches = matches_;
+}
+
+void DescriptorsMatcher::compareWithNNDR(double epsilon, std::vector<cv::DMatch>& matches, std::vector<cv::KeyPoint>& kpts_a,
+                                         std::vector<cv::KeyPoint>& kpts_b, cv::Mat& da, cv::Mat& db) {
+    features(kpts_a, kpts_b, da, db);
+    fm3d_ctx* ctx = host_ctx();
+    const int nq = da.rows, nt = db.rows;
+    std::vector<int32_t> qi(nq), ti(nq);
+    std::vector<float> d(nq);
+    mutual_.assign(nq, 0);
+    int n = 0;
+    if (binary_)
+        check(ctx, fm3d_match_nndr_hamming(ctx, da.ptr<uint8_t>(), nq, db.ptr<uint8_t>(), nt, da.cols, epsilon, qi.data(), ti.data(),
+                                           d.data(), mutual_.data(), &n), "compareWithNNDR");
+    else
+        check(ctx, fm3d_match_nndr_f32(ctx, da.ptr<float>(), nq, db.ptr<float>(), nt, da.cols, epsilon, qi.data(), ti.data(), d.data(),
+                                       mutual_.data(), &n), "compareWithNNDR");
+    mutual_.resize(n);
+    for (int i = 0; i < n; i++) matches.push_back(cv::DMatch(qi[i], ti[i], d[i]));  // appended, not cleared (:126)
+}
+
+void DescriptorsMatcher::extractDescriptorsFromPatches(const std::vector<cv::Mat>&, cv::Mat&) {
+    throw std::runtime_error("fm3d: extractDescriptorsFromPatches needs the upstream OpenCV extractor (SURVEY 8f, next)");
+}
+
+// -------------------------------------------------------------------- SingleCameraTriangulator
+SingleCameraTriangulator::SingleCameraTriangulator(cv::FileStorage& settings)
+    : ctx_(host_ctx()), patch_eps_(0), patch_cmpp_(0), pyramids_(0), write_patch_files_(true) {
+    std::vector<double> tIC, rIC;
+    settings["CameraSettings"]["translationIC"] >> tIC;
+    settings["CameraSettings"]["rodriguesIC"] >> rIC;
+    if (tIC.size() != 3 || rIC.size() != 3) throw std::runtime_error("fm3d: CameraSettings.translationIC / rodriguesIC missing");
+    translation_IC_ = cv::Vec3d(tIC[0], tIC[1], tIC[2]);
+    rodrigues_IC_ = cv::Vec3d(rIC[0], rIC[1], rIC[2]);
+    cv::Matx33d R;
+    rodriguesToMatrix(rodrigues_IC_, R);
+    composeTransformation(R, translation_IC_, g_IC_);
+    double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 1}, dist[5];
+    K[0] = (double)settings["CameraSettings"]["Fx"]; K[4] = (double)settings["CameraSettings"]["Fy"];
+    K[2] = (double)settings["CameraSettings"]["Cx"]; K[5] = (double)settings["CameraSettings"]["Cy"];
+    // (k0,k1,p1,p2,k2) of settings.yml -> OpenCV (k1,k2,p1,p2,k3) (singlecameratriangulator.cpp:101-105)
+    dist[0] = (double)settings["CameraSettings"]["k0"]; dist[1] = (double)settings["CameraSettings"]["k1"];
+    dist[2] = (double)settings["CameraSettings"]["p1"]; dist[3] = (double)settings["CameraSettings"]["p2"];
+    dist[4] = (double)settings["CameraSettings"]["k2"];
+    settings["CameraSettings"]["zThresholdMin"] >> z_threshold_min_;
+    settings["CameraSettings"]["zThresholdMax"] >> z_threshold_max_;
+    settings["Neighborhoods"]["pixelsRay"] >> pixels_ray_;
+    settings["Neighborhoods"]["pyramids"] >> pyramids_;
+    settings["Neighborhoods"]["epsilon"] >> patch_eps_;
+    settings["Neighborhoods"]["cmPerPixel"] >> patch_cmpp_;
+    check(ctx_, fm3d_set_camera(ctx_, K, dist, z_threshold_min_, z_threshold_max_), "set_camera");
+}
+
+void SingleCameraTriangulator::setImages(const cv::Mat& img1, const cv::Mat& img2) {
+    img_1_ = img1; img_2_ = img2;  // shallow, like new cv::Mat(img) in the reference (:118-119)
+    check(ctx_, fm3d_set_images(ctx_, img1.data, img2.data, img1.cols, img1.rows, (int)img1.step(), pyramids_), "set_images");
+}
+
+void SingleCameraTriangulator::setg12(const cv::Vec3d& T1, const cv::Vec3d& T2, const cv::Vec3d& rod1, const cv::Vec3d& rod2,
+                                      cv::Matx44d& g12) {
+    double out[16];
+    if (fm3d_compose_g12(T1.val, T2.val, rod1.val, rod2.val, rodrigues_IC_.val, translation_IC_.val, out) != FM3D_OK)
+        throw std::runtime_error("fm3d: setg12 failed");
+    for (int i = 0; i < 16; i++) g_12_.val[i] = out[i];
+    g12 = g_12_;
+    check(ctx_, fm3d_set_g12(ctx_, out), "set_g12");
+}
+
+void SingleCameraTriangulator::setKeypoints(const std::vector<cv::KeyPoint>& kpts1, const std::vector<cv::KeyPoint>& kpts2,
+                                            const std::vector<cv::DMatch>& matches) {
+    kp1_.resize(kpts1.size() * 2); kp2_.resize(kpts2.size() * 2);
+    for (size_t i = 0; i < kpts1.size(); i++) { kp1_[2 * i] = kpts1[i].pt.x; kp1_[2 * i + 1] = kpts1[i].pt.y; }
+    for (size_t i = 0; i < kpts2.size(); i++) { kp2_[2 * i] = kpts2[i].pt.x; kp2_[2 * i + 1] = kpts2[i].pt.y; }
+    qidx_.resize(matches.size()); tidx_.resize(matches.size());
+    for (size_t i = 0; i < matches.size(); i++) { qidx_[i] = matches[i].queryIdx; tidx_[i] = matches[i].trainIdx; }
+}
+
+void SingleCameraTriangulator::triangulate(std::vector<cv::Vec3d>& triangulatedPoints, std::vector<bool>& outliersMask) {
+    const int n = (int)qidx_.size();
+    std::vector<double> xyz_all((size_t)n * 3), xyz((size_t)n * 3);
+    std::vector<uint8_t> mask(n);
+    int ninl = 0;
+    check(ctx_, fm3d_triangulate(ctx_, kp1_.data(), (int)kp1_.size() / 2, kp2_.data(), (int)kp2_.size() / 2, qidx_.data(), tidx_.data(), n,
+                                 xyz_all.data(), mask.data(), xyz.data(), nullptr, &ninl), "triangulate");
+    triangulatedPoints.clear();                      // cleared (:189)
+    for (int i = 0; i < n; i++) {                    // appended, never cleared (:202-209)
+        outliersMask.push_back(mask[i] != 0);
+        outliers_mask_.push_back(mask[i] != 0);
+    }
+    for (int i = 0; i < ninl; i++) triangulatedPoints.push_back(cv::Vec3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+}
+
+static void unpack_patches(int n, int S, const std::vector<uint8_t>& p, const std::vector<double>& ip,
+                           std::vector<cv::Mat>& patchesVector, std::vector<cv::Mat>& imagePointsVector, bool write_files) {
+    patchesVector.clear();
+    imagePointsVector.clear();
+    for (int f = 0; f < n; f++) {
+        cv::Mat patch(cv::Size(S, S), CV_8UC1);
+        memcpy(patch.data, p.data() + (size_t)f * S * S, (size_t)S * S);
+        cv::Mat pts(cv::Size(1, S * S), CV_64FC2);
+        memcpy(pts.data, ip.data() + (size_t)f * S * S * 2, sizeof(double) * 2 * S * S);
+        patchesVector.push_back(patch);
+        imagePointsVector.push_back(pts);
+    }
+    if (write_files)
+        for (int f = 0; f < n; f++) cv::imwrite("patch_" + NumberToString<int>(f) + ".pgm", patchesVector[f]);  // (:799-802)
+}
+
+void SingleCameraTriangulator::projectReferencePointsToImageWithFrames(const std::vector<cv::Vec3d>& ref,
+                                                                       const std::vector<cv::Matx44d>& featureFrames,
+                                                                       std::vector<cv::Mat>& patchesVector,
+                                                                       std::vector<cv::Mat>& imagePointsVector) {
+    const int S = (int)std::sqrt((double)ref.size());
+    // the GPU generates the S x S grid analytically; make sure the caller's reference neighbourhood is that grid
+    const int Sg = fm3d_patch_size(patch_eps_, patch_cmpp_);
+    const double inc = patch_cmpp_ * 0.01;
+    bool same = S == Sg && S > 0;
+    for (int k = 0; same && k < 3; k++) {
+        const int idx = k == 0 ? 0 : (k == 1 ? S * S - 1 : S + 1), i = idx / S, j = idx % S;
+        same = ref[idx][0] == -patch_eps_ + inc * i && ref[idx][1] == -patch_eps_ + inc * j && ref[idx][2] == 0;
+    }
+    if (!same) throw std::runtime_error("fm3d: reference neighbourhood is not the square grid of settings.yml (epsilon, cmPerPixel)");
+    const int n = (int)featureFrames.size();
+    std::vector<double> frames((size_t)n * 16);
+    for (int f = 0; f < n; f++) memcpy(&frames[(size_t)f * 16], featureFrames[f].val, sizeof(double) * 16);
+    std::vector<uint8_t> p((size_t)n * S * S);
+    std::vector<double> ip((size_t)n * S * S * 2);
+    check(ctx_, fm3d_extract_patches(ctx_, frames.data(), n, patch_eps_, patch_cmpp_, p.data(), ip.data()), "extract_patches");
+    unpack_patches(n, S, p, ip, patchesVector, imagePointsVector, write_patch_files_);
+}
+
+void SingleCameraTriangulator::projectPointsToImage(const IMAGE_ID id, const std::vector<std::vector<cv::Vec3d> >& groups,
+                                                    std::vector<cv::Mat>& patchesVector, std::vector<cv::Mat>& imagePointsVector) {
+    const int n = (int)groups.size();
+    if (n == 0) { patchesVector.clear(); imagePointsVector.clear(); return; }
+    const int S = (int)std::sqrt((double)groups[0].size());
+    std::vector<double> g((size_t)n * S * S * 3);
+    for (int f = 0; f < n; f++)
+        for (int k = 0; k < S * S; k++)
+            for (int c = 0; c < 3; c++) g[((size_t)f * S * S + k) * 3 + c] = groups[f][k][c];
+    std::vector<uint8_t> p((size_t)n * S * S);
+    std::vector<double> ip((size_t)n * S * S * 2);
+    check(ctx_, fm3d_project_groups(ctx_, id == image1 ? 1 : 2, g.data(), n, S, p.data(), ip.data()), "project_groups");
+    unpack_patches(n, S, p, ip, patchesVector, imagePointsVector, write_patch_files_);
+}
+
+// ------------------------------------------------------------------------------ NormalOptimizer
+NormalOptimizer::NormalOptimizer(const cv::FileStorage settings, SingleCameraTriangulator* sct)
+    : sct_(sct), penalty_mode_(FM3D_PENALTY_FABS) {
+    settings["Neighborhoods"]["pyramids"] >> pyr_levels_;
+    settings["Neighborhoods"]["epsilonLMMIN"] >> epsilon_lmmin_;
+    std::vector<double> rIC;
+    settings["CameraSettings"]["rodriguesIC"] >> rIC;
+    cv::Matx33d R;
+    rodriguesToMatrix(cv::Vec3d(rIC[0], rIC[1], rIC[2]), R);
+    // gravity = R_IC^-1 (0,0,-1) = -third row of R_IC (normaloptimizer.cpp:171-176)
+    gravity_ = cv::Vec3d(-R(2, 0), -R(2, 1), -R(2, 2));
+}
+
+cv::Vec3d NormalOptimizer::getGravity() { return gravity_; }
+
+void NormalOptimizer::setImages(const cv::Mat& img1, const cv::Mat& img2) {
+    if (sct_ == 0) throw std::runtime_error("fm3d: NormalOptimizer without a SingleCameraTriangulator");  // exit(-1) (:194-197)
+    sct_->pyramids_ = pyr_levels_;
+    sct_->setImages(img1, img2);  // uploads and builds the pyramids (compute_pyramids, :206-221)
+}
+
+void NormalOptimizer::computeOptimizedNormals(std::vector<cv::Vec3d>& points3D, std::vector<cv::Vec3d>& normalsVector) {
+    std::vector<cv::Scalar> colors(points3D.size(), cv::Scalar(150, 150, 255));
+    computeOptimizedNormals(points3D, normalsVector, colors);
+}
+
+void NormalOptimizer::computeOptimizedNormals(std::vector<cv::Vec3d>& points3D, std::vector<cv::Vec3d>& normalsVector,
+                                              std::vector<cv::Scalar>&) {
+    fm3d_ctx* ctx = sct_->context();
+    const int n = (int)points3D.size(), L1 = pyr_levels_ + 1;
+    std::vector<double> xyz((size_t)n * 3), normals((size_t)n * 3), cost(n);
+    std::vector<int32_t> status(n), nfev((size_t)n * L1), npen(n);
+    for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) xyz[3 * i + c] = points3D[i][c];
+    check(ctx, fm3d_optimize_normals(ctx, xyz.data(), n, sct_->pixelsRay(), epsilon_lmmin_, penalty_mode_, normals.data(),
+                                     status.data(), nfev.data(), npen.data(), cost.data()), "optimize_normals");
+    status_.assign(status.begin(), status.end());
+    nfev_.assign(n, 0);
+    for (int i = 0; i < n; i++) for (int l = 0; l < L1; l++) nfev_[i] += nfev[(size_t)i * L1 + l];
+    // failed features are erased from points3D in place; normals are appended (:364-382,447)
+    std::vector<cv::Vec3d> kept;
+    for (int i = 0; i < n; i++) {
+        if (status[i] != FM3D_FEAT_OK) continue;
+        kept.push_back(points3D[i]);
+        normalsVector.push_back(cv::Vec3d(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
+    }
+    points3D.swap(kept);
+}
+
+void NormalOptimizer::computeFeaturesFrames(std::vector<cv::Vec3d>& points3D, std::vector<cv::Vec3d>& normalsVector,
+                                            std::vector<cv::Matx44d>& featuresFrames) {
+    fm3d_ctx* ctx = sct_->context();
+    const int n = (int)std::min(points3D.size(), normalsVector.size());
+    std::vector<double> xyz((size_t)n * 3), nrm((size_t)n * 3), fr((size_t)n * 16);
+    for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) { xyz[3 * i + c] = points3D[i][c]; nrm[3 * i + c] = normalsVector[i][c]; }
+    check(ctx, fm3d_feature_frames(ctx, xyz.data(), nrm.data(), n, gravity_.val, fr.data()), "feature_frames");
+    for (int i = 0; i < n; i++) {
+        cv::Matx44d F;
+        memcpy(F.val, &fr[(size_t)i * 16], sizeof(double) * 16);
+        featuresFrames.push_back(F);  // appended (:490)
+    }
+}
+
+// ----------------------------------------------------------------------- NeighborhoodsGenerator
+NeighborhoodsGenerator::NeighborhoodsGenerator(cv::FileStorage settings) : epsilon_(0), cm_per_pixel_(0) {
+    std::string method = (std::string)settings["Neighborhoods"]["method"];
+    if (method != "square")
+        throw std::runtime_error("fm3d: Neighborhoods.method '" + method + "' is not supported (square only)");  // exit(-10) (:69-73)
+    settings["Neighborhoods"]["epsilon"] >> epsilon_;
+    settings["Neighborhoods"]["cmPerPixel"] >> cm_per_pixel_;
+}
+
+void NeighborhoodsGenerator::getReferenceSquaredNeighborhood(std::vector<cv::Vec3d>& neighborhood) {
+    const int S = fm3d_patch_size(epsilon_, cm_per_pixel_);
+    const double inc = cm_per_pixel_ * 0.01;
+    neighborhood.clear();
+    for (int i = 0; i < S; i++)
+        for (int j = 0; j < S; j++) neighborhood.push_back(cv::Vec3d(-epsilon_ + inc * i, -epsilon_ + inc * j, 0));
+}
+
+void NeighborhoodsGenerator::computeSquareNeighborhoodsByNormals(const std::vector<cv::Matx44d>& featuresFrames,
+                                                                 std::vector<std::vector<cv::Vec3d> >& neighborhoodsVector) {
+    fm3d_ctx* ctx = host_ctx();
+    const int n = (int)featuresFrames.size(), S = fm3d_patch_size(epsilon_, cm_per_pixel_);
+    neighborhoodsVector.clear();
+    if (n == 0) return;
+    std::vector<double> frames((size_t)n * 16), out((size_t)n * S * S * 3);
+    for (int f = 0; f < n; f++) memcpy(&frames[(size_t)f * 16], featuresFrames[f].val, sizeof(double) * 16);
+    check(ctx, fm3d_square_neighborhoods(ctx, frames.data(), n, epsilon_, cm_per_pixel_, out.data()), "square_neighborhoods");
+    neighborhoodsVector.resize(n);
+    for (int f = 0; f < n; f++) {
+        neighborhoodsVector[f].resize((size_t)S * S);
+        for (int k = 0; k < S * S; k++) {
+            const double* p = &out[((size_t)f * S * S + k) * 3];
+            neighborhoodsVector[f][k] = cv::Vec3d(p[0], p[1], p[2]);
+        }
+    }
+}
+
+void NeighborhoodsGenerator::computeSquareNeighborhoodByNormal(const cv::Matx44d& featureFrame, std::vector<cv::Vec3d>& neighborhood) {
+    std::vector<cv::Matx44d> one(1, featureFrame);
+    std::vector<std::vector<cv::Vec3d> > out;
+    computeSquareNeighborhoodsByNormals(one, out);
+    neighborhood = out.empty() ? std::vector<cv::Vec3d>() : out[0];
+}

@@ -1,0 +1,103 @@
+// Test driver: the call sequence of the reference's main.cpp (main.cpp:91-187) on top of the
+// fm3d class adapters.  Features come from a file because keypoint detection/description is
+// upstream of the hot path.  Usage: pipeline_main -s settings.yml features.bin result.bin
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "DescriptorsMatcher/descriptorsmatcher.h"
+#include "Triangulator/neighborhoodsgenerator.h"
+#include "Triangulator/normaloptimizer.h"
+#include "Triangulator/singlecameratriangulator.h"
+
+static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
+
+int main(int argc, char** argv) {
+    if (argc < 5 || strcmp(argv[1], "-s") != 0) { std::cerr << "usage: -s <settings.yml> <features.bin> <result.bin>\n"; return 1; }
+    cv::FileStorage fs;
+    fs.open(argv[2], cv::FileStorage::READ);
+    if (!fs.isOpened()) { std::cerr << "Could not open settings file: " << argv[2] << std::endl; return 1; }
+    std::string IMG_1, IMG_2;
+    fs["IMAGES"]["img1"] >> IMG_1;
+    fs["IMAGES"]["img2"] >> IMG_2;
+    cv::Mat img1 = cv::imread(IMG_1, CV_LOAD_IMAGE_GRAYSCALE), img2 = cv::imread(IMG_2, CV_LOAD_IMAGE_GRAYSCALE);
+    if (img1.empty() || img2.empty()) { std::cerr << "could not read images\n"; return 1; }
+
+    // upstream features
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) { std::cerr << "no features file\n"; return 1; }
+    int n1, n2, dim;
+    rd(f, &n1, 4); rd(f, &n2, 4); rd(f, &dim, 4);
+    std::vector<float> k1(2 * n1), k2(2 * n2);
+    cv::Mat d1(n1, dim, CV_32FC1), d2(n2, dim, CV_32FC1);
+    rd(f, k1.data(), 8 * n1); rd(f, k2.data(), 8 * n2);
+    rd(f, d1.data, (size_t)4 * n1 * dim); rd(f, d2.data, (size_t)4 * n2 * dim);
+    fclose(f);
+    std::vector<cv::KeyPoint> in1(n1), in2(n2);
+    for (int i = 0; i < n1; i++) in1[i] = cv::KeyPoint(k1[2 * i], k1[2 * i + 1], 1.f);
+    for (int i = 0; i < n2; i++) in2[i] = cv::KeyPoint(k2[2 * i], k2[2 * i + 1], 1.f);
+
+    std::vector<cv::KeyPoint> kpts1, kpts2;
+    cv::Mat desc1, desc2;
+    std::vector<cv::DMatch> matches;
+    DescriptorsMatcher dm(fs, img1, img2);
+    dm.setFeatures(in1, d1, in2, d2);
+    dm.compareWithNNDR(fs["NNDR"]["epsilon"], matches, kpts1, kpts2, desc1, desc2);
+
+    std::vector<double> pos1, pos2;
+    fs["IMAGES"]["pos1"] >> pos1;
+    fs["IMAGES"]["pos2"] >> pos2;
+    cv::Vec3d translation1(pos1[0], pos1[1], pos1[2]), translation2(pos2[0], pos2[1], pos2[2]);
+    cv::Vec3d rodrigues1(pos1[3], pos1[4], pos1[5]), rodrigues2(pos2[3], pos2[4], pos2[5]);
+    cv::Matx44d g12;
+    std::vector<cv::Vec3d> triagulated;
+    std::vector<bool> outliersMask;
+    SingleCameraTriangulator sct(fs);
+    sct.setKeypoints(kpts1, kpts2, matches);
+    sct.setg12(translation1, translation2, rodrigues1, rodrigues2, g12);
+    sct.triangulate(triagulated, outliersMask);
+    std::vector<cv::Vec3d> all_points = triagulated;
+
+    NormalOptimizer no(fs, &sct);
+    if (const char* e = getenv("FM3D_PENALTY")) no.setPenaltyMode(atoi(e));
+    std::vector<cv::Vec3d> normalsVector;
+    std::vector<cv::Scalar> colors(triagulated.size(), cv::Scalar(150, 150, 255));
+    no.setImages(img1, img2);
+    no.startVisualizerThread();
+    no.computeOptimizedNormals(triagulated, normalsVector, colors);
+    std::vector<cv::Matx44d> featuresFrames;
+    no.computeFeaturesFrames(triagulated, normalsVector, featuresFrames);
+
+    NeighborhoodsGenerator ng(fs);
+    std::vector<cv::Vec3d> referenceNeighborhood;
+    ng.getReferenceSquaredNeighborhood(referenceNeighborhood);
+    std::vector<cv::Mat> patchesVector, imagePointsVector;
+    sct.setImages(img1, img2);
+    sct.projectReferencePointsToImageWithFrames(referenceNeighborhood, featuresFrames, patchesVector, imagePointsVector);
+    std::vector<std::vector<cv::Vec3d> > neighborhoodsVector;
+    ng.computeSquareNeighborhoodsByNormals(featuresFrames, neighborhoodsVector);
+    no.stopVisualizerThread();
+
+    // results
+    FILE* o = fopen(argv[4], "wb");
+    int nm = (int)matches.size(), np = (int)all_points.size(), nn = (int)normalsVector.size();
+    int S = patchesVector.empty() ? 0 : patchesVector[0].rows;
+    fwrite(&nm, 4, 1, o); fwrite(&np, 4, 1, o); fwrite(&nn, 4, 1, o); fwrite(&S, 4, 1, o);
+    for (int i = 0; i < nm; i++) { fwrite(&matches[i].queryIdx, 4, 1, o); fwrite(&matches[i].trainIdx, 4, 1, o); fwrite(&matches[i].distance, 4, 1, o); }
+    for (int i = 0; i < nm; i++) { unsigned char b = outliersMask[i]; fwrite(&b, 1, 1, o); }
+    fwrite(g12.val, 8, 16, o);
+    for (int i = 0; i < np; i++) fwrite(all_points[i].val, 8, 3, o);
+    for (int i = 0; i < np; i++) fwrite(&no.lastStatus()[i], 4, 1, o);
+    for (int i = 0; i < nn; i++) fwrite(triagulated[i].val, 8, 3, o);
+    for (int i = 0; i < nn; i++) fwrite(normalsVector[i].val, 8, 3, o);
+    for (int i = 0; i < nn; i++) fwrite(featuresFrames[i].val, 8, 16, o);
+    for (int i = 0; i < nn; i++) fwrite(patchesVector[i].data, 1, (size_t)S * S, o);
+    for (int i = 0; i < nn; i++) fwrite(neighborhoodsVector[i][S * S - 1].val, 8, 3, o);
+    cv::Vec3d g = no.getGravity();
+    fwrite(g.val, 8, 3, o);
+    fclose(o);
+    std::cout << nm << " matches, " << np << " inliers, " << nn << " normals, patches " << S << "x" << S << std::endl;
+    return 0;
+}
