@@ -30,7 +30,7 @@ SYMBOLS = [
     "fm3d_match_nndr_hamming", "fm3d_match_knn2_f32_dev", "fm3d_match_knn2_hamming_dev",
     "fm3d_nndr_filter_dev", "fm3d_triangulate", "fm3d_triangulate_dev", "fm3d_undistort_points",
     "fm3d_set_images", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
-    "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_feature_frames",
+    "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_get_normals_stats", "fm3d_feature_frames",
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
 ]
@@ -237,6 +237,14 @@ class Context:
                                                 int(penalty_mode), _ptr(normals, _dp), _ptr(status, _ip), _ptr(nfev, _ip),
                                                 _ptr(npen, _ip), _ptr(cost, _dp)))
         return {"normals": normals, "status": status, "nfev": nfev, "npenalty": npen, "cost": cost}
+
+    def normals_stats(self):
+        out = (C.c_int64 * 16)()
+        self._ck(self.lib.fm3d_get_normals_stats(self._h, out))
+        keys = ("passes_value", "passes_jacobian", "passes_fused", "fused_accepted", "passes_slow",
+                "pixel_evals_value", "pixel_evals_jacobian", "features", "cycles_pixels", "cycles_barrier",
+                "cycles_serial", "cycles_lm", "cycles_publish")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def evaluate_normals(self, xyz, phi_theta, pixels_ray, level, penalty_mode=PENALTY_FABS):
         xyz = _arr(xyz, np.float64).reshape(-1, 3)

@@ -170,6 +170,8 @@ static int* fm3d_option_slot(fm3d_ctx* ctx, const char* key) {
     if (!strcmp(key, "lm_patience")) return &ctx->opt_lm_patience;
     if (!strcmp(key, "normals_threads")) return &ctx->opt_normals_threads;
     if (!strcmp(key, "normals_tma")) return &ctx->opt_normals_tma;
+    if (!strcmp(key, "normals_fast")) return &ctx->opt_normals_fast;
+    if (!strcmp(key, "normals_fuse")) return &ctx->opt_normals_fuse;
     return nullptr;
 }
 

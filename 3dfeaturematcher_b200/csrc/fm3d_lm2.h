@@ -9,8 +9,8 @@
 // Everything lmdif needs from the m x 2 Jacobian J and the residual f is contained in
 //   ff = f.f,  S00 = J0.J0,  S01 = J0.J1,  S11 = J1.J1,  g0 = J0.f,  g1 = J1.f
 // (R of the pivoted QR is the Cholesky factor of J^T J, Q^T f restricted to its first two
-// components is R^-T J^T f).  The trust-region logic, lmpar and qrsolv below are MINPACK's,
-// with lmfit's deltas (step rule max(eps^2, eps|x|), 0.55 in the shrink rule, first-call
+// components is R^-T J^T f).  The trust-region logic and lmpar below are MINPACK's, written
+// for two unknowns on the normal equations, with lmfit's deltas (step rule max(eps^2, eps|x|), 0.55 in the shrink rule, first-call
 // delta clip, user break -> info 11).  Host+device code; no allocation; n fixed to 2.
 #ifndef FM3D_LM2_H_
 #define FM3D_LM2_H_
@@ -39,141 +39,202 @@ struct fm3d_lm2 {
     // state
     double x[2], xt[2], h[2];
     double diag[2], delta, par, xnorm, fnorm, gnorm;
-    double r[4], qtf[2], acnorm[2], step[2], pnorm;
-    int ipvt[2];
+    double S00, S01, S11, g0, g1;   // J^T J and J^T f at x
+    double acnorm[2], step[2], pnorm;
     int iter, nfev, info;
     int first; // 1 until the first Jacobian pass has been consumed
 };
 
 FM3D_HD double fm3d_enorm2(double a, double b) { return sqrt(a * a + b * b); }
 
-// MINPACK qrsolv, n = 2.  r: row-major 2x2 (upper = R, strict lower overwritten).
-FM3D_HD void fm3d_qrsolv2(double* r, const int* ipvt, const double* diag, const double* qtb,
-                          double* x, double* sdiag) {
-    double wa[2];
-    for (int j = 0; j < 2; j++) {
-        for (int i = j; i < 2; i++) r[i * 2 + j] = r[j * 2 + i];
-        x[j] = r[j * 2 + j];
-        wa[j] = qtb[j];
-    }
-    for (int j = 0; j < 2; j++) {
-        int l = ipvt[j];
-        if (diag[l] != 0.0) {
-            for (int k = j; k < 2; k++) sdiag[k] = 0.0;
-            sdiag[j] = diag[l];
-            double qtbpj = 0.0;
-            for (int k = j; k < 2; k++) {
-                if (sdiag[k] == 0.0) continue;
-                double sn, cs;
-                if (fabs(r[k * 2 + k]) < fabs(sdiag[k])) {
-                    double cotan = r[k * 2 + k] / sdiag[k];
-                    sn = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
-                    cs = sn * cotan;
-                } else {
-                    double tn = sdiag[k] / r[k * 2 + k];
-                    cs = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
-                    sn = cs * tn;
-                }
-                r[k * 2 + k] = cs * r[k * 2 + k] + sn * sdiag[k];
-                double temp = cs * wa[k] + sn * qtbpj;
-                qtbpj = -sn * wa[k] + cs * qtbpj;
-                wa[k] = temp;
-                for (int i = k + 1; i < 2; i++) {
-                    temp = cs * r[i * 2 + k] + sn * sdiag[i];
-                    sdiag[i] = -sn * r[i * 2 + k] + cs * sdiag[i];
-                    r[i * 2 + k] = temp;
-                }
-            }
-        }
-        sdiag[j] = r[j * 2 + j];
-        r[j * 2 + j] = x[j];
-    }
-    int nsing = 2;
-    for (int j = 0; j < 2; j++) {
-        if (sdiag[j] == 0.0 && nsing == 2) nsing = j;
-        if (nsing < 2) wa[j] = 0.0;
-    }
-    for (int k = 1; k <= nsing; k++) {
-        int j = nsing - k;
-        double sum = 0.0;
-        for (int i = j + 1; i < nsing; i++) sum += r[i * 2 + j] * wa[i];
-        wa[j] = (wa[j] - sum) / sdiag[j];
-    }
-    for (int j = 0; j < 2; j++) x[ipvt[j]] = wa[j];
+// Cheap arithmetic for the serial LM update on the GPU (one thread, dependent chains: what counts
+// is the number of instructions in a row).  Host builds use the plain operators.
+//   fm3d_rcp    1/a in fp64: MUFU.RCP64H seed + two Newton steps (full precision up to the last
+//               ulp, no special-case branch: the operands here are positive and normal)
+//   fm3d_fdiv, fm3d_frcp, fm3d_fsqrt   fp32 MUFU forms (lmpar's search for par: 10 % tolerance)
+#if defined(__CUDA_ARCH__)
+FM3D_HD double fm3d_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = fma(r, fma(-a, r, 1.0), r);
+    r = fma(r, fma(-a, r, 1.0), r);
+    return r;
+}
+FM3D_HD float fm3d_frcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+FM3D_HD float fm3d_fdiv(float a, float b) { return a * fm3d_frcp(b); }
+FM3D_HD float fm3d_fsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+#else
+FM3D_HD double fm3d_rcp(double a) { return 1.0 / a; }
+FM3D_HD float fm3d_frcp(float a) { return 1.0f / a; }
+FM3D_HD float fm3d_fdiv(float a, float b) { return a / b; }
+FM3D_HD float fm3d_fsqrt(float a) { return sqrtf(a); }
+#endif
+
+// a*d - b*c with one rounding of the products compensated (Kahan)
+FM3D_HD double fm3d_det2(double a, double b, double c, double d) {
+    const double w = b * c;
+    const double e = fma(-b, c, w);
+    const double f = fma(a, d, -w);
+    return f + e;
 }
 
-// MINPACK lmpar, n = 2.  Returns the new par; x = step.
-FM3D_HD double fm3d_lmpar2(double* r, const int* ipvt, const double* diag, const double* qtb,
-                           double delta, double par, double* x) {
-    double wa1[2], wa2[2], sdiag[2];
-    int nsing = 2;
-    for (int j = 0; j < 2; j++) {
-        wa1[j] = qtb[j];
-        if (r[j * 2 + j] == 0.0 && nsing == 2) nsing = j;
-        if (nsing < 2) wa1[j] = 0.0;
-    }
-    for (int k = 1; k <= nsing; k++) {
-        int j = nsing - k;
-        wa1[j] /= r[j * 2 + j];
-        double temp = wa1[j];
-        for (int i = 0; i < j; i++) wa1[i] -= r[i * 2 + j] * temp;
-    }
-    for (int j = 0; j < 2; j++) x[ipvt[j]] = wa1[j];
-    int iter = 0;
-    for (int j = 0; j < 2; j++) wa2[j] = diag[j] * x[j];
-    double dxnorm = fm3d_enorm2(wa2[0], wa2[1]);
-    double fp = dxnorm - delta;
-    if (fp <= 0.1 * delta) return 0.0;
-    double parl = 0.0;
-    if (nsing >= 2) {
-        for (int j = 0; j < 2; j++) { int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
-        for (int j = 0; j < 2; j++) {
-            double sum = 0.0;
-            for (int i = 0; i < j; i++) sum += r[i * 2 + j] * wa1[i];
-            wa1[j] = (wa1[j] - sum) / r[j * 2 + j];
+// MINPACK lmpar for n = 2, on the normal equations.  lmpar works on the pivoted QR factor R of J
+// and calls qrsolv for every candidate parameter; with two unknowns R^T R = J^T J is already at
+// hand (it is what the CTA reduces), every solve (J^T J + par D^2) p = J^T f is a 2x2 Cramer
+// formula and the Newton correction ||R_par^-T D^2 p / |D p| ||^2 is the quadratic form of the same
+// inverse.  The iteration (bounds parl/paru, 0.1 delta tolerance, at most 10 steps, rank handling
+// of the Gauss-Newton step) is MINPACK's; the arithmetic is scalar: no arrays, no data-dependent
+// indexing.  Returns the new par; (*p0, *p1) = step.  This fp64 version is the fall-back of the
+// mixed-precision one below and what the host tests compare it with.
+FM3D_HD double fm3d_lmpar2_f64(const fm3d_lm2* s, double delta, double par, double* p0, double* p1) {
+    const double S00 = s->S00, S01 = s->S01, S11 = s->S11, g0 = s->g0, g1 = s->g1;
+    const double d0 = s->diag[0], d1 = s->diag[1];
+    // Gauss-Newton step; pivot = column of larger norm (first maximum wins), a zero diagonal of
+    // R zeroes the remaining components
+    const bool piv1 = S11 > S00;
+    const double Spp = piv1 ? S11 : S00, Sqq = piv1 ? S00 : S11;
+    const double gp = piv1 ? g1 : g0, gq = piv1 ? g0 : g1;
+    double xp = 0.0, xq = 0.0, t = 0.0;
+    bool full_rank = false;
+    if (Spp != 0.0) {
+        const double iS = 1.0 / Spp;
+        t = Sqq - S01 * S01 * iS;               // r11^2
+        if (t > 0.0) {
+            full_rank = true;
+            xq = (gq - S01 * gp * iS) / t;
         }
-        double temp = fm3d_enorm2(wa1[0], wa1[1]);
-        parl = fp / delta / temp / temp;
+        xp = (gp - S01 * xq) * iS;
     }
-    for (int j = 0; j < 2; j++) {
-        double sum = 0.0;
-        for (int i = 0; i <= j; i++) sum += r[i * 2 + j] * qtb[i];
-        wa1[j] = sum / diag[ipvt[j]];
+    double x0 = piv1 ? xq : xp, x1 = piv1 ? xp : xq;
+    double dx0 = d0 * x0, dx1 = d1 * x1;
+    double dxnorm = fm3d_enorm2(dx0, dx1);
+    double fp = dxnorm - delta;
+    if (fp <= 0.1 * delta) { *p0 = x0; *p1 = x1; return 0.0; }
+    double parl = 0.0;
+    if (full_rank) {
+        const double y0 = d0 * (dx0 / dxnorm), y1 = d1 * (dx1 / dxnorm);
+        const double w2 = (S11 * y0 * y0 - 2.0 * S01 * y0 * y1 + S00 * y1 * y1) / (Spp * t);
+        parl = fp / delta / w2;
     }
-    double gnorm = fm3d_enorm2(wa1[0], wa1[1]);
+    const double gnorm = fm3d_enorm2(g0 / d0, g1 / d1);
     double paru = gnorm / delta;
     if (paru == 0.0) paru = FM3D_DBL_MIN / fmin(delta, 0.1);
     par = fmax(par, parl);
     par = fmin(par, paru);
     if (par == 0.0) par = gnorm / dxnorm;
-    for (;;) {
-        iter++;
+    for (int iter = 1;; iter++) {
         if (par == 0.0) par = fmax(FM3D_DBL_MIN, 0.001 * paru);
-        double temp = sqrt(par);
-        for (int j = 0; j < 2; j++) wa1[j] = temp * diag[j];
-        fm3d_qrsolv2(r, ipvt, wa1, qtb, x, sdiag);
-        for (int j = 0; j < 2; j++) wa2[j] = diag[j] * x[j];
-        dxnorm = fm3d_enorm2(wa2[0], wa2[1]);
-        temp = fp;
+        const double m00 = fma(par * d0, d0, S00), m11 = fma(par * d1, d1, S11);
+        const double idet = 1.0 / fm3d_det2(m00, S01, S01, m11);
+        x0 = fm3d_det2(m11, S01, g1, g0) * idet;    // m11 g0 - S01 g1
+        x1 = fm3d_det2(m00, S01, g0, g1) * idet;    // m00 g1 - S01 g0
+        dx0 = d0 * x0; dx1 = d1 * x1;
+        dxnorm = fm3d_enorm2(dx0, dx1);
+        const double temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-        for (int j = 0; j < 2; j++) { int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
-        for (int j = 0; j < 2; j++) {
-            wa1[j] /= sdiag[j];
-            double t2 = wa1[j];
-            for (int i = j + 1; i < 2; i++) wa1[i] -= r[i * 2 + j] * t2;
-        }
-        temp = fm3d_enorm2(wa1[0], wa1[1]);
-        double parc = fp / delta / temp / temp;
+        const double y0 = d0 * (dx0 / dxnorm), y1 = d1 * (dx1 / dxnorm);
+        const double w2 = (m11 * y0 * y0 - 2.0 * S01 * y0 * y1 + m00 * y1 * y1) * idet;
+        const double parc = fp / delta / w2;
         if (fp > 0.0) parl = fmax(parl, par);
         if (fp < 0.0) paru = fmin(paru, par);
         par = fmax(parl, par + parc);
     }
+    *p0 = x0; *p1 = x1;
     return par;
 }
 
+FM3D_HD float fm3d_det2f(float a, float b, float c, float d) {
+    const float w = b * c;
+    const float e = fmaf(-b, c, w);
+    const float f = fmaf(a, d, -w);
+    return f + e;
+}
+
+// The same iteration with the search for par in fp32.  lmpar only asks for |D p| within 10 % of
+// delta, so the Newton iteration on par does not need fp64: it runs in the scaled variables
+// z = D p (A = D^-1 J^T J D^-1 has |a_ij| <= 1 because diag_j >= |J_j|, b = D^-1 J^T f has
+// |b_j| <= |f|), where fp32 neither overflows nor loses the 10 % decision.  The step that is
+// returned solves (J^T J + par D^2) p = J^T f in fp64 for the par found, and the Gauss-Newton
+// step and its acceptance test are fp64 too.  On the GPU this takes the serial LM update between
+// two passes from ~30 dependent fp64 divisions / square roots to 3.
+FM3D_HD double fm3d_lmpar2(const fm3d_lm2* s, double delta, double par, double* p0, double* p1) {
+    const double S00 = s->S00, S01 = s->S01, S11 = s->S11, g0 = s->g0, g1 = s->g1;
+    const double d0 = s->diag[0], d1 = s->diag[1];
+    // Gauss-Newton step (fp64): rank test as in the QR (r11^2 = Sqq - S01^2 / Spp > 0)
+    const bool piv1 = S11 > S00;
+    const double Spp = piv1 ? S11 : S00, Sqq = piv1 ? S00 : S11;
+    const double gp = piv1 ? g1 : g0, gq = piv1 ? g0 : g1;
+    double xp = 0.0, xq = 0.0;
+    bool full_rank = false;
+    if (Spp != 0.0) {
+        const double det = fm3d_det2(Spp, S01, S01, Sqq);       // Spp * r11^2
+        if (det > 0.0) {
+            full_rank = true;
+            const double idet = fm3d_rcp(det);
+            xq = fm3d_det2(Spp, S01, gp, gq) * idet;            // Spp gq - S01 gp
+            xp = fm3d_det2(Sqq, S01, gq, gp) * idet;            // Sqq gp - S01 gq
+        } else {
+            xp = gp * fm3d_rcp(Spp);
+        }
+    }
+    const double x0 = piv1 ? xq : xp, x1 = piv1 ? xp : xq;
+    const double dx0 = d0 * x0, dx1 = d1 * x1;
+    const double dx2 = dx0 * dx0 + dx1 * dx1;
+    // fp = |D p| - delta <= 0.1 delta
+    if (dx2 <= 1.21 * delta * delta) { *p0 = x0; *p1 = x1; return 0.0; }
+
+    // Newton iteration on par in fp32, scaled variables
+    const double id0 = fm3d_rcp(d0), id1 = fm3d_rcp(d1);
+    const float a00 = (float)(S00 * id0 * id0), a01 = (float)(S01 * id0 * id1), a11 = (float)(S11 * id1 * id1);
+    const float b0 = (float)(g0 * id0), b1 = (float)(g1 * id1);
+    const float df = (float)delta, idf = fm3d_frcp(df);
+    float dxn = fm3d_fsqrt((float)dx2);
+    float fp = dxn - df;
+    float parl = 0.0f;
+    if (full_rank) {
+        const float z0 = (float)dx0, z1 = (float)dx1;
+        const float det0 = fm3d_det2f(a00, a01, a01, a11);
+        const float w2 = fm3d_fdiv(a11 * z0 * z0 - 2.0f * a01 * z0 * z1 + a00 * z1 * z1, det0 * dxn * dxn);
+        if (det0 > 0.0f && w2 > 0.0f) parl = fm3d_fdiv(fp * idf, w2);
+    }
+    const float gnorm = fm3d_fsqrt(b0 * b0 + b1 * b1);
+    float paru = gnorm * idf;
+    if (paru == 0.0f) paru = 1.1754944e-38f / fminf(df, 0.1f);
+    float parf = (float)par;
+    parf = fmaxf(parf, parl);
+    parf = fminf(parf, paru);
+    if (parf == 0.0f) parf = fm3d_fdiv(gnorm, dxn);
+    for (int iter = 1;; iter++) {
+        if (parf == 0.0f) parf = fmaxf(1.1754944e-38f, 0.001f * paru);
+        const float m00 = a00 + parf, m11 = a11 + parf;
+        const float idet = fm3d_frcp(fm3d_det2f(m00, a01, a01, m11));
+        const float z0 = fm3d_det2f(m11, a01, b1, b0) * idet;
+        const float z1 = fm3d_det2f(m00, a01, b0, b1) * idet;
+        const float zn2 = z0 * z0 + z1 * z1;
+        dxn = fm3d_fsqrt(zn2);
+        const float temp = fp;
+        fp = dxn - df;
+        if (fabsf(fp) <= 0.1f * df || (parl == 0.0f && fp <= temp && temp < 0.0f) || iter == 10) break;
+        const float w2 = fm3d_fdiv((m11 * z0 * z0 - 2.0f * a01 * z0 * z1 + m00 * z1 * z1) * idet, zn2);
+        const float parc = fm3d_fdiv(fp * idf, w2);
+        if (fp > 0.0f) parl = fmaxf(parl, parf);
+        if (fp < 0.0f) paru = fminf(paru, parf);
+        parf = fmaxf(parl, parf + parc);
+    }
+    if (!(parf >= 0.0f && parf <= 3.0e38f)) return fm3d_lmpar2_f64(s, delta, par, p0, p1);
+    // the step for this par, fp64
+    const double pd = (double)parf;
+    const double m00 = fma(pd * d0, d0, S00), m11 = fma(pd * d1, d1, S11);
+    const double idet = fm3d_rcp(fm3d_det2(m00, S01, S01, m11));
+    *p0 = fm3d_det2(m11, S01, g1, g0) * idet;
+    *p1 = fm3d_det2(m00, S01, g0, g1) * idet;
+    return pd;
+}
+
 FM3D_HD void fm3d_lm2_fd_steps(fm3d_lm2* s) {
-    for (int j = 0; j < 2; j++) s->h[j] = fmax(s->eps * s->eps, s->eps * fabs(s->x[j]));
+    s->h[0] = fmax(s->eps * s->eps, s->eps * fabs(s->x[0]));
+    s->h[1] = fmax(s->eps * s->eps, s->eps * fabs(s->x[1]));
 }
 
 // lm_control_double with the reference's epsilon override (normaloptimizer.cpp:272-274).
@@ -195,53 +256,40 @@ FM3D_HD int fm3d_lm2_init(fm3d_lm2* s, double phi, double theta, double epsilon,
 
 // Inner loop head: solve for the step and publish the trial point.
 FM3D_HD int fm3d_lm2_propose(fm3d_lm2* s) {
-    s->par = fm3d_lmpar2(s->r, s->ipvt, s->diag, s->qtf, s->delta, s->par, s->step);
-    for (int j = 0; j < 2; j++) s->xt[j] = s->x[j] - s->step[j];
-    s->pnorm = fm3d_enorm2(s->diag[0] * s->step[0], s->diag[1] * s->step[1]);
+    double p0, p1;
+    s->par = fm3d_lmpar2(s, s->delta, s->par, &p0, &p1);
+    s->step[0] = p0; s->step[1] = p1;
+    s->xt[0] = s->x[0] - p0;
+    s->xt[1] = s->x[1] - p1;
+    s->pnorm = fm3d_enorm2(s->diag[0] * p0, s->diag[1] * p1);
     if (s->nfev <= 1 + 2) s->delta = fmin(s->delta, s->pnorm);
     return FM3D_LM_CMD_TRIAL;
 }
 
-// Consume the sums of a Jacobian pass: ff = |f(x)|^2 and the Gram entries of the
-// forward-difference Jacobian (already divided by the steps).
+// Consume the sums of a Jacobian pass: ff = |f(x)|^2, the Gram entries of the Jacobian and
+// J^T f.
 FM3D_HD int fm3d_lm2_after_jacobian(fm3d_lm2* s, double ff, double S00, double S01, double S11,
                                     double g0, double g1) {
     if (s->first) { s->nfev = 3; s->first = 0; } else { s->nfev += 2; }
     s->fnorm = sqrt(ff);
-    const double S[2] = {S00, S11};
-    const double g[2] = {g0, g1};
-    s->acnorm[0] = sqrt(S00); s->acnorm[1] = sqrt(S11);
-    // qrfac with column pivoting (first maximum wins, as MINPACK's kmax scan)
-    int p = (s->acnorm[1] > s->acnorm[0]) ? 1 : 0;
-    int q = 1 - p;
-    s->ipvt[0] = p; s->ipvt[1] = q;
-    double r00 = s->acnorm[p], r01 = 0.0, r11 = 0.0, qt0 = 0.0, qt1 = 0.0;
-    if (r00 != 0.0) {
-        r01 = S01 / r00;
-        double t = S[q] - r01 * r01;
-        r11 = t > 0.0 ? sqrt(t) : 0.0;
-        qt0 = g[p] / r00;
-        if (r11 != 0.0) qt1 = (g[q] - r01 * qt0) / r11;
-    }
-    s->r[0] = r00; s->r[1] = r01; s->r[2] = 0.0; s->r[3] = r11;
-    s->qtf[0] = qt0; s->qtf[1] = qt1;
+    s->S00 = S00; s->S01 = S01; s->S11 = S11; s->g0 = g0; s->g1 = g1;
+    const double an0 = sqrt(S00), an1 = sqrt(S11);
+    s->acnorm[0] = an0; s->acnorm[1] = an1;
     if (s->iter == 0) {
-        for (int j = 0; j < 2; j++) s->diag[j] = s->acnorm[j] != 0.0 ? s->acnorm[j] : 1.0;
+        s->diag[0] = an0 != 0.0 ? an0 : 1.0;
+        s->diag[1] = an1 != 0.0 ? an1 : 1.0;
         s->xnorm = fm3d_enorm2(s->diag[0] * s->x[0], s->diag[1] * s->x[1]);
         s->delta = s->stepbound * s->xnorm;
         if (s->delta == 0.0) s->delta = s->stepbound;
     } else {
-        for (int j = 0; j < 2; j++) s->diag[j] = fmax(s->diag[j], s->acnorm[j]);
+        s->diag[0] = fmax(s->diag[0], an0);
+        s->diag[1] = fmax(s->diag[1], an1);
     }
+    // norm of the scaled gradient: max_j |(J^T f)_j| / (|J_j| |f|)
     double gnorm = 0.0;
     if (s->fnorm != 0.0) {
-        for (int j = 0; j < 2; j++) {
-            double an = s->acnorm[s->ipvt[j]];
-            if (an == 0.0) continue;
-            double sum = 0.0;
-            for (int i = 0; i <= j; i++) sum += s->r[i * 2 + j] * s->qtf[i] / s->fnorm;
-            gnorm = fmax(gnorm, fabs(sum / an));
-        }
+        if (an0 != 0.0) gnorm = fmax(gnorm, fabs(g0 * fm3d_rcp(s->fnorm * an0)));
+        if (an1 != 0.0) gnorm = fmax(gnorm, fabs(g1 * fm3d_rcp(s->fnorm * an1)));
     }
     s->gnorm = gnorm;
     if (gnorm <= s->gtol) { s->info = 4; return FM3D_LM_CMD_DONE; }
@@ -252,30 +300,30 @@ FM3D_HD int fm3d_lm2_after_jacobian(fm3d_lm2* s, double ff, double S00, double S
 FM3D_HD int fm3d_lm2_after_trial(fm3d_lm2* s, double ff_trial) {
     const double p1 = 0.1, p0001 = 1.0e-4;
     s->nfev += 1;
-    double fnorm = s->fnorm, fnorm1 = sqrt(ff_trial);
-    double actred = (p1 * fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
-    double wa3[2] = {0.0, 0.0};
-    for (int j = 0; j < 2; j++) {
-        wa3[j] = 0.0;
-        for (int i = 0; i <= j; i++) wa3[i] -= s->r[i * 2 + j] * s->step[s->ipvt[j]];
-    }
-    double temp1 = fm3d_enorm2(wa3[0], wa3[1]) / fnorm;
-    double temp2 = sqrt(s->par) * s->pnorm / fnorm;
-    double prered = temp1 * temp1 + 2.0 * temp2 * temp2;
-    double dirder = -(temp1 * temp1 + temp2 * temp2);
-    double ratio = prered != 0.0 ? actred / prered : 0.0;
+    const double fnorm = s->fnorm, fnorm1 = sqrt(ff_trial);
+    const double iff = fm3d_rcp(fnorm * fnorm);
+    // (fnorm1 / fnorm)^2 without the square root in the chain
+    const double actred = (p1 * fnorm1 < fnorm) ? 1.0 - ff_trial * iff : -1.0;
+    // |J p|^2 = p^T (J^T J) p
+    const double s0 = s->step[0], s1 = s->step[1];
+    const double jp2 = fmax(0.0, s->S00 * s0 * s0 + 2.0 * s->S01 * s0 * s1 + s->S11 * s1 * s1);
+    const double t1sq = jp2 * iff;
+    const double t2sq = s->par * s->pnorm * s->pnorm * iff;      // (sqrt(par) pnorm / fnorm)^2
+    const double prered = t1sq + 2.0 * t2sq;
+    const double dirder = -(t1sq + t2sq);
+    const double ratio = prered != 0.0 ? actred * fm3d_rcp(prered) : 0.0;
     if (ratio <= 0.25) {
         double temp;
         if (actred >= 0.0) temp = 0.5;
-        else temp = 0.5 * dirder / (dirder + 0.55 * actred);
+        else temp = 0.5 * dirder * fm3d_rcp(dirder + 0.55 * actred);
         if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
-        s->delta = temp * fmin(s->delta, s->pnorm / p1);
-        s->par /= temp;
+        s->delta = temp * fmin(s->delta, s->pnorm * 10.0);
+        s->par *= fm3d_rcp(temp);
     } else if (s->par == 0.0 || ratio >= 0.75) {
         s->delta = s->pnorm / 0.5;
         s->par *= 0.5;
     }
-    int accepted = ratio >= p0001;
+    const int accepted = ratio >= p0001;
     if (accepted) {
         s->x[0] = s->xt[0]; s->x[1] = s->xt[1];
         s->xnorm = fm3d_enorm2(s->diag[0] * s->x[0], s->diag[1] * s->x[1]);

@@ -26,123 +26,11 @@
 //              (fm3d_lm2.h) and publishes the next pass.
 // The reference aborts a feature on the first bad pixel of any evaluation (D8); here the
 // pass finishes and the OR of the per-pixel flags aborts it, which selects the same features.
-#include <math.h>
+#include "fm3d_normals_common.cuh"
 
-#include "fm3d_internal.cuh"
-#include "fm3d_lm2.h"
+using namespace fm3d_normals;
 
 namespace {
-
-constexpr int NT_MAX = 512;
-constexpr int WIN_MAX_W = 192, WIN_MAX_H = 192;
-constexpr int WIN_BYTES = WIN_MAX_W * WIN_MAX_H;
-constexpr int MAX_RAY = 255;
-constexpr int MAX_ROWS = 2 * MAX_RAY + 1;
-
-enum { FLAG_NAN = 1, FLAG_BBOX = 2, FLAG_PIX = 4 };
-
-struct NormalsArgs {
-    fm3d_cam cam;
-    fm3d_pyramid_desc pyr;
-    const double* xyz;
-    int n;
-    int r;
-    double eps_lmmin;
-    int penalty_mode;
-    int patience;
-    int mode;               // 0 optimise, 1 evaluate the cost at phi_theta / level only
-    int eval_level;
-    const double* phi_theta;
-    double* normals;
-    int32_t* status;
-    int32_t* nfev;
-    int32_t* npenalty;
-    double* cost;
-    int32_t* m_out;
-    int* work_counter;
-    int* error_flag;        // set to 1 if a TMA wait timed out (the kernel then falls back)
-    int mcap;
-    int win_w[FM3D_MAX_LEVELS], win_h[FM3D_MAX_LEVELS];
-    int use_tma;
-    float2* rays_g;
-    float* i1_g;
-    CUtensorMap tmap[FM3D_MAX_LEVELS];
-};
-
-// Parameters of one pass, written by thread 0 and read by everybody.
-template <typename G>
-struct PassParams {
-    G nx[3], ny[3], nz[3], mnum[3];
-    int ne;        // 1 (trial) or 3 (Jacobian)
-    int cmd;       // fm3d_lm_cmd, or 0 = feature finished
-};
-
-struct FeatureShared {
-    fm3d_lm2 lm;
-    double w[3];       // penalty weights of the evaluations of the current pass
-    double P[3];
-    double normal[3];
-    int feature;
-    int status;
-    int npenalty;
-    int level;
-    int m;
-    int wx0, wy0;      // window origin (level pixels)
-    int tma_phase;
-};
-
-// ---------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
-
-// ---------------------------------------------------------------------------- small helpers
-__device__ __forceinline__ double penalty_weight(double phi, double theta, int mode, int& entered) {
-    entered = 0;
-    if (mode == FM3D_PENALTY_OFF) return 1.0;
-    double at, ap;
-    if (mode == FM3D_PENALTY_INT_ABS) { at = (double)abs((int)theta); ap = (double)abs((int)phi); }
-    else { at = fabs(theta); ap = fabs(phi); }
-    const double pi = 3.14159265358979323846;
-    if (at - pi / 2 > 0 || ap - pi > 0) {
-        const double wt = exp(at - pi / 2) + 1;
-        const double wp = exp(ap - pi + 1) + 1;
-        entered = 1;
-        return wp * wt;
-    }
-    return 1.0;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 struct LevelView {
     const uint8_t* img2;   // global, pitched
@@ -227,15 +115,6 @@ __device__ __forceinline__ float eval_pixel(const CamG<G>& C, const LevelView& L
     const float I2 = sample_img2(L, su, sv);
     return __fsub_rn(I1, I2);
 }
-
-// Row-major walk over the clipped disc: pixel idx lives in row `row` at x offset i.
-struct RowTable {
-    int start[MAX_ROWS + 1];
-    short ilo[MAX_ROWS];
-    short jrow[MAX_ROWS];
-    int nrows;
-};
-
 template <typename G, bool RAYS_SMEM>
 __global__ void __launch_bounds__(NT_MAX, 1)
 normals_kernel(const __grid_constant__ NormalsArgs A) {
@@ -646,13 +525,6 @@ size_t tail_bytes(bool f32) {
     t += f32 ? ((sizeof(PassParams<float>) + 15) & ~(size_t)15) : ((sizeof(PassParams<double>) + 15) & ~(size_t)15);
     return t + 16;
 }
-
-int disc_capacity(int r) {
-    int m = 0;
-    for (int j = -r; j <= r; j++) m += 2 * (int)floor(sqrt((double)(r * r - j * j))) + 1;
-    return m;
-}
-
 __global__ void frames_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int n,
                               double gx, double gy, double gz, double* __restrict__ frames) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -677,6 +549,9 @@ int run_normals(fm3d_ctx* ctx, NormalsArgs& A) {
     if (A.r < 0 || A.r > MAX_RAY) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "pixels_ray must be in [0,%d]", MAX_RAY);
     if (A.n == 0) return FM3D_OK;
     if (int rc = fm3d_bind(ctx)) return rc;
+    // default: the fast kernel for the optimisation; cost evaluations (parity probes) stay on the
+    // evaluation-by-evaluation kernel unless normals_fast >= 2
+    if (ctx->opt_normals_fast && (A.mode == 0 || ctx->opt_normals_fast >= 2)) return run_normals_fast(ctx, A);
     A.cam = ctx->cam;
     A.pyr = ctx->pyr;
     A.patience = ctx->opt_lm_patience;
@@ -737,6 +612,16 @@ int run_normals(fm3d_ctx* ctx, NormalsArgs& A) {
 }  // namespace
 
 extern "C" {
+
+int fm3d_get_normals_stats(fm3d_ctx* ctx, int64_t out[16]) {
+    if (!ctx || !out) return FM3D_ERR_INVALID_ARG;
+    for (int k = 0; k < 16; k++) out[k] = 0;
+    if (!ctx->scratch[1]) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    FM3D_CUDA(ctx, cudaMemcpyAsync(out, (const char*)ctx->scratch[1] + 64, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
 
 int fm3d_optimize_normals_dev(fm3d_ctx* ctx, const double* xyz, int n, int pixels_ray,
                               double epsilon_lmmin, int penalty_mode, double* normals,

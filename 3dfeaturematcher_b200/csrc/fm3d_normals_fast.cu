@@ -1,0 +1,821 @@
+// fm3d_normals_fast.cu -- K5/K6/K7, the default implementation of the per-feature plane-normal
+// search (fm3d_set_option "normals_fast" = 1; fm3d_normals.cu is the evaluation-by-evaluation
+// restatement of the reference and stays available with "normals_fast" = 0).
+//
+// Same optimisation problem, same optimiser as the reference: coarse-to-fine over the pyramid
+// (Triangulator/normaloptimizer.cpp:223-245), lmfit's lmmin per level over (phi, theta)
+// (:247-292, state machine in fm3d_lm2.h), residual I1 - I2 of evaluateNormal (:65-149) with the
+// bounding-box / pixel gates and the penalty wall, disc lattice of extractPixelsContour
+// (Triangulator/singlecameratriangulator.cpp:341-397).  What changes is how the m x 2 problem is
+// evaluated on an SM:
+//
+//   geometry   fp32, written as offsets from the centre ray.  The centre ray meets every candidate
+//              plane in the feature point P itself, so its image-2 projection (xc, yc) does not
+//              depend on the normal; with the plane-induced homography H = (n.P) R + t n^T and the
+//              ray v = vc + dv,
+//                  x - xc = ((H0 - xc H2) . dv) / (H2 . v),   y - yc = ((H1 - yc H2) . dv) / (H2 . v)
+//              has no constant term: the quantities rounded to fp32 are small offsets, and nothing
+//              that is shared by all pixels of a pass is rounded (no common-mode jitter of the
+//              cost surface).  Distortion, K and the bilinear taps follow in fp32 as in
+//              getBilinearInterpPix32f (tools.cpp:129-142), taps from the TMA-staged window.
+//   Jacobian   analytic instead of lmfit's forward differences (step 1e-5 rad ~ 6e-4 px at the disc
+//              edge): the four taps of a sample also give the image gradient, the chain rule goes
+//              through K, the distortion polynomial, the perspective division and dH/dphi,
+//              dH/dtheta.  The penalty weights are still differenced exactly as lmfit would see
+//              them (w(x + h e_j) - w(x)), so the wall keeps its reference behaviour.
+//   schedule   a trial point is evaluated together with its Jacobian when it is the first trial of
+//              an LM iteration: if lmfit accepts it, the next iteration starts without another
+//              pass.  nfev counts the evaluations lmfit would have made (1 per trial, 2 per
+//              Jacobian), so it stays comparable with the reference.
+//   gates      isInBoundingBox / isPixelGood are tested on the boundary lattice of the disc only:
+//              the warp is a homeomorphism of the disc, so the interior cannot leave a rectangle
+//              its boundary stays in.  The same test proves that every tap of the pass lies in the
+//              staged window; if not, the pass is repeated with taps from global memory.
+#include "fm3d_normals_common.cuh"
+
+using namespace fm3d_normals;
+
+namespace fm3d_normals {
+namespace {
+
+constexpr int FAST_NT = 512;
+constexpr float FLOOR_MAGIC = 12582912.0f;          // 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x)
+constexpr unsigned FLOOR_MAGIC_BITS = 0x4B400000u;
+enum { FLAG_WINDOW = 8 };
+enum { PASS_STOP = 0, PASS_VALUE = 1, PASS_JAC = 2 };
+enum { AT_X_JAC = 0, AT_XT_PLAIN = 1, AT_XT_FUSED = 2 };
+
+// Everything a pass needs, written by thread 0.
+struct FastPass {
+    // e = 0: value, 1: d/dphi, 2: d/dtheta.  A_e = h[e][0] dx + h[e][1] dy + h[e][2] (x numerator, offset form),
+    // B_e = h[e][3] dx + h[e][4] dy + h[e][5], C_e = h[e][6] dx + h[e][7] dy + h[e][8] (common denominator)
+    float h[3][9];
+    float nd[3];        // sign(n.P) * n.v = nd[0] dx + nd[1] dy + nd[2]
+    float mabs;         // |n.P|
+    int kind;           // PASS_*
+    int slow;           // taps from global memory (a boundary tap left the staged window)
+};
+
+struct FastShared {
+    fm3d_lm2 lm;
+    double w[3];
+    double ht[2];       // forward-difference steps the penalty weights of this pass were taken at
+    double P[3];
+    double normal[3];
+    double vc[2];       // centre ray
+    double xc, yc;      // projection of P into camera 2 (normalised): independent of the normal
+    int feature;
+    int status;
+    int npenalty;
+    int m;
+    int wx0, wy0;
+    int tma_phase;
+    int where;          // AT_*
+    int alive;
+    int first_row, last_row;
+    unsigned long long stats[16];
+};
+
+struct LevelConst {
+    float xc, yc;
+    float k1, k2, k3, p1, p2;
+    float sfx, sfy, scx, scy;    // scale * K
+    float cols, rows;            // isPixelGood bounds on the scaled pixel
+    const uint8_t* win;
+    unsigned ww, coff, amax;
+    int wx0, wy0, lx_min, lx_cnt, ly_min, ly_cnt;
+    const uint8_t* img2;
+    int w, h, pitch;
+};
+
+__device__ __forceinline__ float rcp_nr(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return fmaf(r, fmaf(-a, r, 1.0f), r);
+}
+__device__ __forceinline__ float u2f(unsigned b) {  // I2FP (the compiler would pick the slow I2F.U16)
+    float f;
+    asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(b));
+    return f;
+}
+
+struct Acc {
+    double s0;
+    float s1, s2, s3, s4, s5;
+};
+
+// Warp of one disc pixel into image 2 and its residual; with JAC also the derivatives of the
+// sampled intensity with respect to (phi, theta).
+template <bool JAC, bool SLOW>
+__device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelConst& L, float2 dv, float I1, Acc& acc) {
+    const float A0 = fmaf(P.h[0][0], dv.x, fmaf(P.h[0][1], dv.y, P.h[0][2]));
+    const float B0 = fmaf(P.h[0][3], dv.x, fmaf(P.h[0][4], dv.y, P.h[0][5]));
+    const float C0 = fmaf(P.h[0][6], dv.x, fmaf(P.h[0][7], dv.y, P.h[0][8]));
+    const float iz = rcp_nr(C0);
+    const float dx = A0 * iz, dy = B0 * iz;
+    const float x = L.xc + dx, y = L.yc + dy;
+    // cv::projectPoints: distortion polynomial and K (x scale), singlecameratriangulator.cpp:602,627
+    const float r2 = fmaf(x, x, y * y);
+    const float cd = fmaf(r2, fmaf(r2, fmaf(r2, L.k3, L.k2), L.k1), 1.0f);
+    const float x2 = x + x, y2 = y + y;
+    const float xy2 = x2 * y;
+    const float a2 = fmaf(x2, x, r2), a3 = fmaf(y2, y, r2);
+    const float xd = fmaf(x, cd, fmaf(L.p1, xy2, L.p2 * a2));
+    const float yd = fmaf(y, cd, fmaf(L.p1, a3, L.p2 * xy2));
+    const float su = fmaf(xd, L.sfx, L.scx), sv = fmaf(yd, L.sfy, L.scy);
+    // floor and fraction without FRND/F2I
+    const float tx = __fadd_rd(su, FLOOR_MAGIC), ty = __fadd_rd(sv, FLOOR_MAGIC);
+    const float ax = su - (tx - FLOOR_MAGIC), ay = sv - (ty - FLOOR_MAGIC);
+    float b00, b01, b10, b11;
+    if (!SLOW) {
+        unsigned a = __float_as_uint(ty) * L.ww + __float_as_uint(tx) - L.coff;
+        a = min(a, L.amax);   // memory safety only: the boundary test proves a is in range
+        const uint8_t* p = L.win + a;
+        b00 = u2f(p[0]); b10 = u2f(p[1]);
+        b01 = u2f(p[L.ww]); b11 = u2f(p[L.ww + 1]);
+    } else {
+        const int x0 = (int)(__float_as_uint(tx) - FLOOR_MAGIC_BITS), y0 = (int)(__float_as_uint(ty) - FLOOR_MAGIC_BITS);
+        b00 = u2f(fm3d_at_flat(L.img2, L.w, L.h, L.pitch, x0, y0));
+        b01 = u2f(fm3d_at_flat(L.img2, L.w, L.h, L.pitch, x0, y0 + 1));
+        b10 = u2f(fm3d_at_flat(L.img2, L.w, L.h, L.pitch, x0 + 1, y0));
+        b11 = u2f(fm3d_at_flat(L.img2, L.w, L.h, L.pitch, x0 + 1, y0 + 1));
+    }
+    const float d0 = b01 - b00, d1 = b11 - b10;
+    const float c0 = fmaf(ay, d0, b00), c1 = fmaf(ay, d1, b10);
+    const float gx = c1 - c0;
+    const float I2 = fmaf(ax, gx, c0);
+    const float d = I1 - I2;
+    acc.s0 = fma((double)d, (double)d, acc.s0);
+    if (JAC) {
+        const float gy = fmaf(ax, d1 - d0, d0);
+        const float cdp = fmaf(r2, fmaf(r2, 3.0f * L.k3, 2.0f * L.k2), L.k1);   // d cd / d r2
+        const float Jxx = fmaf(x2 * x, cdp, fmaf(2.0f * L.p1, y, fmaf(6.0f * L.p2, x, cd)));
+        const float Jxy = fmaf(xy2, cdp, fmaf(2.0f * L.p1, x, 2.0f * L.p2 * y));
+        const float Jyy = fmaf(y2 * y, cdp, fmaf(6.0f * L.p1, y, fmaf(2.0f * L.p2, x, cd)));
+        const float Gx = gx * L.sfx, Gy = gy * L.sfy;
+        const float Ix = fmaf(Gx, Jxx, Gy * Jxy), Iy = fmaf(Gx, Jxy, Gy * Jyy);   // dI2/d(x,y)
+        const float q0 = Ix * iz, q1 = Iy * iz;
+        const float q2 = -fmaf(q0, dx, q1 * dy);
+        const float A1 = fmaf(P.h[1][0], dv.x, fmaf(P.h[1][1], dv.y, P.h[1][2]));
+        const float B1 = fmaf(P.h[1][3], dv.x, fmaf(P.h[1][4], dv.y, P.h[1][5]));
+        const float C1 = fmaf(P.h[1][6], dv.x, fmaf(P.h[1][7], dv.y, P.h[1][8]));
+        const float A2 = fmaf(P.h[2][0], dv.x, fmaf(P.h[2][1], dv.y, P.h[2][2]));
+        const float B2 = fmaf(P.h[2][3], dv.x, fmaf(P.h[2][4], dv.y, P.h[2][5]));
+        const float C2 = fmaf(P.h[2][6], dv.x, fmaf(P.h[2][7], dv.y, P.h[2][8]));
+        const float Ip = fmaf(q0, A1, fmaf(q1, B1, q2 * C1));   // dI2/dphi   (residual derivative = -Ip)
+        const float It = fmaf(q0, A2, fmaf(q1, B2, q2 * C2));   // dI2/dtheta
+        acc.s1 = fmaf(Ip, Ip, acc.s1);
+        acc.s2 = fmaf(Ip, It, acc.s2);
+        acc.s3 = fmaf(It, It, acc.s3);
+        acc.s4 = fmaf(Ip, d, acc.s4);
+        acc.s5 = fmaf(It, d, acc.s5);
+    }
+}
+
+// Gates of one boundary pixel (isInBoundingBox :646-655, isPixelGood :657-665) and the proof that its
+// taps are inside the staged window.
+__device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const LevelConst& L, float vcx, float vcy,
+                                                   float cmax, float2 dv) {
+    unsigned flags = 0;
+    const float den = fmaf(P.nd[0], dv.x, fmaf(P.nd[1], dv.y, P.nd[2]));
+    const float vx = vcx + dv.x, vy = vcy + dv.y;
+    const float t = fmaxf(1.0f, fmaxf(fabsf(vx), fabsf(vy)));
+    if (den != den || P.mabs != P.mabs) flags |= FLAG_NAN;
+    if (!(P.mabs * t < cmax * den)) flags |= FLAG_BBOX;
+    const float A0 = fmaf(P.h[0][0], dv.x, fmaf(P.h[0][1], dv.y, P.h[0][2]));
+    const float B0 = fmaf(P.h[0][3], dv.x, fmaf(P.h[0][4], dv.y, P.h[0][5]));
+    const float C0 = fmaf(P.h[0][6], dv.x, fmaf(P.h[0][7], dv.y, P.h[0][8]));
+    const float iz = rcp_nr(C0);
+    const float x = L.xc + A0 * iz, y = L.yc + B0 * iz;
+    const float r2 = fmaf(x, x, y * y);
+    const float cd = fmaf(r2, fmaf(r2, fmaf(r2, L.k3, L.k2), L.k1), 1.0f);
+    const float xy2 = 2.0f * x * y;
+    const float xd = fmaf(x, cd, fmaf(L.p1, xy2, L.p2 * fmaf(2.0f * x, x, r2)));
+    const float yd = fmaf(y, cd, fmaf(L.p1, fmaf(2.0f * y, y, r2), L.p2 * xy2));
+    const float su = fmaf(xd, L.sfx, L.scx), sv = fmaf(yd, L.sfy, L.scy);
+    if (!(su >= 0.0f && su <= L.cols && sv >= 0.0f && sv <= L.rows)) flags |= FLAG_PIX;
+    // one pixel of margin: the lattice boundary is a polygon, its warp slightly curved
+    const float fx0 = floorf(su), fy0 = floorf(sv);
+    const float lx = fx0 - (float)L.wx0, ly = fy0 - (float)L.wy0;
+    if (!(lx >= (float)(L.lx_min + 1) && lx < (float)(L.lx_min + L.lx_cnt - 1) &&
+          ly >= (float)(L.ly_min + 1) && ly < (float)(L.ly_min + L.ly_cnt - 1))) flags |= FLAG_WINDOW;
+    return flags;
+}
+
+template <bool JAC, bool SLOW, typename RayPtr>
+__device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& L, RayPtr rays, const float* i1, int m,
+                                           int tid, int NT, Acc& acc) {
+    int idx = tid;
+    for (; idx + NT < m; idx += 2 * NT) {
+        const float2 dva = rays[idx], dvb = rays[idx + NT];
+        const float Ia = i1[idx], Ib = i1[idx + NT];
+        eval_pixel_fast<JAC, SLOW>(P, L, dva, Ia, acc);
+        eval_pixel_fast<JAC, SLOW>(P, L, dvb, Ib, acc);
+    }
+    if (idx < m) eval_pixel_fast<JAC, SLOW>(P, L, rays[idx], i1[idx], acc);
+}
+
+// Warp 0, all lanes, uniform arguments: evaluation point (phi, theta) -> homography coefficients
+// of the pass.  The work is spread over the lanes (two sincos, nine coefficient rows, three penalty
+// weights) because it sits between two passes with the other fifteen warps waiting.
+__device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, double phi, double theta, int kind,
+                             int penalty_mode, double eps, int lane) {
+    // sincos(phi) on lane 0, sincos(theta) on lane 1
+    double sv, cv;
+    sincos(lane == 0 ? phi : theta, &sv, &cv);
+    const double sp = __shfl_sync(0xffffffffu, sv, 0), cp = __shfl_sync(0xffffffffu, cv, 0);
+    const double st = __shfl_sync(0xffffffffu, sv, 1), ct = __shfl_sync(0xffffffffu, cv, 1);
+    // sph2car (tools.cpp:772-777) and its derivatives
+    const double n0x = ct * cp, n0y = ct * sp, n0z = st;
+    if (n0x != n0x || n0y != n0y || n0z != n0z) {  // normaloptimizer.cpp:81-85
+        if (lane == 0) {
+            S->status = FM3D_FEAT_ABORT_NAN;
+            S->alive = 0;
+            PP->kind = PASS_STOP;
+        }
+        return;
+    }
+    const double vcx = S->vc[0], vcy = S->vc[1];
+    if (lane < 9) {
+        // lane = 3 e + row: e = 0 value, 1 d/dphi, 2 d/dtheta
+        const int e = lane / 3, row = lane - 3 * e;
+        const double nx = e == 0 ? n0x : (e == 1 ? -ct * sp : -st * cp);
+        const double ny = e == 0 ? n0y : (e == 1 ? ct * cp : -st * sp);
+        const double nz = e == 0 ? n0z : (e == 1 ? 0.0 : ct);
+        const double me = nx * S->P[0] + ny * S->P[1] + nz * S->P[2];
+        // third row of H_e = (n_e.P) R + t n_e^T, and row `row`
+        const double H20 = me * cam.R[6] + cam.t[2] * nx, H21 = me * cam.R[7] + cam.t[2] * ny, H22 = me * cam.R[8] + cam.t[2] * nz;
+        double c0, c1, c2;
+        if (row == 2) {
+            c0 = H20; c1 = H21; c2 = H22;
+        } else {
+            // numerators in offset form: (H0 - xc H2) . v and (H1 - yc H2) . v with v = vc + dv.  Their
+            // constant terms vanish when the centre ray passes exactly through P; what is left is
+            // the residual of the 5-iteration undistort of the centre pixel
+            const double ref = row == 0 ? S->xc : S->yc;
+            const double tr = cam.t[row];
+            c0 = me * cam.R[3 * row] + tr * nx - ref * H20;
+            c1 = me * cam.R[3 * row + 1] + tr * ny - ref * H21;
+            c2 = me * cam.R[3 * row + 2] + tr * nz - ref * H22;
+        }
+        PP->h[e][3 * row] = (float)c0;
+        PP->h[e][3 * row + 1] = (float)c1;
+        PP->h[e][3 * row + 2] = (float)(c0 * vcx + c1 * vcy + c2);
+    } else if (lane == 9) {
+        const double me = n0x * S->P[0] + n0y * S->P[1] + n0z * S->P[2];
+        const double sg = me < 0 ? -1.0 : 1.0;
+        if (me == 0.0) {        // k == 0 fails 0 < k for every pixel
+            PP->nd[0] = PP->nd[1] = PP->nd[2] = 0.0f;
+        } else {
+            PP->nd[0] = (float)(sg * n0x);
+            PP->nd[1] = (float)(sg * n0y);
+            PP->nd[2] = (float)(sg * (n0x * vcx + n0y * vcy + n0z));
+        }
+        PP->mabs = (float)fabs(me);
+        PP->kind = kind;
+    } else if (lane < 13) {
+        // penalty weights of f(x), f(x + h0 e0), f(x + h1 e1) as lmfit's forward differences see them
+        const int j = lane - 10;
+        const double h0 = fmax(eps * eps, eps * fabs(phi)), h1 = fmax(eps * eps, eps * fabs(theta));
+        int entered;
+        if (j == 0 || kind == PASS_JAC)
+            S->w[j] = penalty_weight(phi + (j == 1 ? h0 : 0.0), theta + (j == 2 ? h1 : 0.0), penalty_mode, entered);
+        if (j == 0) { S->ht[0] = h0; S->ht[1] = h1; }
+    }
+}
+
+// Consume the sums of a Jacobian evaluation at the point lm.x (analytic derivatives, differenced weights).
+__device__ __forceinline__ int consume_jacobian(FastShared* S, fm3d_lm2& lm, const double* s, int penalty_mode) {
+    // f_0 = w0 d,  (f_j - f_0)/h_j = w_j dd/dx_j + (w_j - w0) d / h_j,  dd/dx_j = -dI2/dx_j
+    const double w0 = S->w[0], w1 = S->w[1], w2 = S->w[2];
+    const double a1 = (w1 - w0) / S->ht[0], a2 = (w2 - w0) / S->ht[1];
+    const double A00 = s[0], E11 = s[1], E12 = s[2], E22 = s[3], E1d = -s[4], E2d = -s[5];
+    const double ff = w0 * w0 * A00;
+    const double S00 = w1 * w1 * E11 + 2 * w1 * a1 * E1d + a1 * a1 * A00;
+    const double S11 = w2 * w2 * E22 + 2 * w2 * a2 * E2d + a2 * a2 * A00;
+    const double S01 = w1 * w2 * E12 + w1 * a2 * E1d + w2 * a1 * E2d + a1 * a2 * A00;
+    const double g0 = w0 * (w1 * E1d + a1 * A00);
+    const double g1 = w0 * (w2 * E2d + a2 * A00);
+    if (penalty_mode != FM3D_PENALTY_OFF) {
+        // evaluations at x + h e_j that entered the penalty branch (counted like the reference's)
+        if (w1 != 1.0) S->npenalty++;
+        if (w2 != 1.0) S->npenalty++;
+    }
+    return fm3d_lm2_after_jacobian(&lm, ff, S00, S01, S11, g0, g1);
+}
+
+template <bool RAYS_SMEM>
+__global__ void __launch_bounds__(FAST_NT, 1)
+normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* win = smem;
+    float2* rays;
+    float* i1;
+    uint8_t* tail;
+    if (RAYS_SMEM) {
+        rays = reinterpret_cast<float2*>(smem + A.win_bytes);
+        i1 = reinterpret_cast<float*>(rays + A.mcap);
+        tail = reinterpret_cast<uint8_t*>(i1 + A.mcap);
+    } else {
+        rays = A.rays_g + (size_t)blockIdx.x * A.mcap;
+        i1 = A.i1_g + (size_t)blockIdx.x * A.mcap;
+        tail = smem + A.win_bytes;
+    }
+    tail = reinterpret_cast<uint8_t*>(((uintptr_t)tail + 15) & ~(uintptr_t)15);
+    RowTable* rows = reinterpret_cast<RowTable*>(tail);
+    tail += (sizeof(RowTable) + 15) & ~(size_t)15;
+    double* red = reinterpret_cast<double*>(tail);        // [16 warps][6]
+    tail += sizeof(double) * 16 * 6;
+    unsigned* wflags = reinterpret_cast<unsigned*>(tail);  // [16 warps]
+    tail += sizeof(unsigned) * 16;
+    FastShared* S = reinterpret_cast<FastShared*>(tail);
+    tail += (sizeof(FastShared) + 15) & ~(size_t)15;
+    FastPass* PP = reinterpret_cast<FastPass*>(tail);
+    tail += (sizeof(FastPass) + 15) & ~(size_t)15;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
+    const fm3d_cam& cam = A.cam;
+    const int r = A.r, W = A.pyr.lv[0].w, H = A.pyr.lv[0].h, levels = A.pyr.levels;
+    const float cmax = (float)(int)(2 * cam.zmax);  // int cMax = 2*z_threshold_max_ (:648)
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        S->tma_phase = 0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        // ------------------------------------------------------------ fetch a feature
+        if (tid == 0) S->feature = atomicAdd(A.work_counter, 1);
+        __syncthreads();
+        const int f = S->feature;
+        if (f >= A.n) break;
+        const double Px = A.xyz[3 * f], Py = A.xyz[3 * f + 1], Pz = A.xyz[3 * f + 2];
+
+        // ------------------------------------------------------------ prologue: disc lattice
+        double cu, cv;
+        fm3d_project(cam, Px, Py, Pz, cu, cv);  // extractPixelsContour(Vec3d) (:376-397)
+        for (int jr = tid; jr < 2 * r + 1; jr += NT) {
+            const int j = jr - r;
+            const double py = cv + (double)j;
+            int cnt = 0, lo = 0;
+            if (!(py < 0 || py >= (double)H) && cu == cu && cv == cv) {
+                const int hw = (int)floor(sqrt((double)(r * r - j * j)));
+                int ilo = -hw, ihi = hw;
+                // keep iff !(px < 0 || px >= W) with px = cu + i evaluated exactly as the reference does
+                if (cu + (double)ilo < 0) {
+                    int g = (int)ceil(-cu);
+                    ilo = g < -hw ? -hw : (g > hw + 1 ? hw + 1 : g);
+                    while (ilo <= hw && (cu + (double)ilo) < 0) ilo++;
+                    while (ilo - 1 >= -hw && !((cu + (double)(ilo - 1)) < 0)) ilo--;
+                }
+                if (cu + (double)ihi >= (double)W) {
+                    int g = (int)ceil((double)W - cu) - 1;
+                    ihi = g > hw ? hw : (g < -hw - 1 ? -hw - 1 : g);
+                    while (ihi >= -hw && (cu + (double)ihi) >= (double)W) ihi--;
+                    while (ihi + 1 <= hw && !((cu + (double)(ihi + 1)) >= (double)W)) ihi++;
+                }
+                cnt = ihi - ilo + 1;
+                if (cnt < 0) cnt = 0;
+                lo = ilo;
+            }
+            rows->start[jr + 1] = cnt;  // counts, prefix-summed below
+            rows->ilo[jr] = (short)lo;
+            rows->jrow[jr] = (short)j;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0, first = -1, last = -1;
+            rows->start[0] = 0;
+            for (int jr = 0; jr < 2 * r + 1; jr++) {
+                const int c = rows->start[jr + 1];
+                if (c > 0) { if (first < 0) first = jr; last = jr; }
+                acc += c;
+                rows->start[jr + 1] = acc;
+            }
+            rows->nrows = 2 * r + 1;
+            S->first_row = first; S->last_row = last;
+            S->m = acc;
+            S->status = acc > 0 ? FM3D_FEAT_OK : FM3D_FEAT_NO_PIXELS;
+            S->alive = acc > 0;
+            S->npenalty = 0;
+            for (int k = 0; k < 16; k++) S->stats[k] = 0;
+            S->P[0] = Px; S->P[1] = Py; S->P[2] = Pz;
+            const double nrm = sqrt(Px * Px + Py * Py + Pz * Pz);
+            S->normal[0] = Px / nrm; S->normal[1] = Py / nrm; S->normal[2] = Pz / nrm;  // (:343)
+            if (A.nfev && A.mode == 0) for (int l = 0; l <= levels; l++) A.nfev[(size_t)f * (levels + 1) + l] = 0;
+            // centre ray, and the camera-2 projection of P: P lies on every candidate plane, so this
+            // is where the centre of the disc lands whatever the normal (reference point of the
+            // offset form)
+            double vcx, vcy;
+            fm3d_undistort(cam, cu, cv, vcx, vcy);
+            S->vc[0] = vcx; S->vc[1] = vcy;
+            const double X2 = cam.R[0] * Px + cam.R[1] * Py + cam.R[2] * Pz + cam.t[0];
+            const double Y2 = cam.R[3] * Px + cam.R[4] * Py + cam.R[5] * Pz + cam.t[1];
+            const double Z2 = cam.R[6] * Px + cam.R[7] * Py + cam.R[8] * Pz + cam.t[2];
+            const double iz = Z2 != 0.0 ? 1.0 / Z2 : 1.0;
+            S->xc = X2 * iz; S->yc = Y2 * iz;
+        }
+        __syncthreads();
+        const int m = S->m;
+        if (A.m_out && tid == 0) A.m_out[f] = m;
+        const double vcx = S->vc[0], vcy = S->vc[1];
+        const float vcxf = (float)vcx, vcyf = (float)vcy;
+
+        // ideal rays of all disc pixels (normal-independent), as offsets from the centre ray
+        if (m > 0) {
+            int row = 0;
+            for (int idx = tid; idx < m; idx += NT) {
+                while (idx >= rows->start[row + 1]) row++;
+                const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
+                const double py = cv + (double)rows->jrow[row];
+                double vx, vy;
+                fm3d_undistort(cam, px, py, vx, vy);
+                rays[idx] = make_float2((float)(vx - vcx), (float)(vy - vcy));
+            }
+        }
+        // boundary lattice: both ends of every row, and the whole first and last row
+        const int nrows = 2 * r + 1;
+        const int first_row = S->first_row, last_row = S->last_row;
+        const int n_first = m > 0 ? rows->start[first_row + 1] - rows->start[first_row] : 0;
+        const int n_last = m > 0 ? rows->start[last_row + 1] - rows->start[last_row] : 0;
+        const int n_boundary = m > 0 ? 2 * nrows + n_first + n_last : 0;
+
+        // ------------------------------------------------------------ coarse-to-fine LM
+        const int lvl_hi = A.mode == 0 ? levels : A.eval_level;
+        const int lvl_lo = A.mode == 0 ? 0 : A.eval_level;
+        bool alive = m > 0;
+        for (int lvl = lvl_hi; lvl >= lvl_lo && alive; lvl--) {
+            const fm3d_level lv = A.pyr.lv[lvl];
+            const double scale = 1.0 / (double)(1 << lvl);      // actual_scale_ (:226-241)
+            const double inv_scale = 1.0 / scale;
+            const uint8_t* img1 = A.pyr.base[0] + lv.off;
+            LevelConst L;
+            L.img2 = A.pyr.base[1] + lv.off;
+            L.w = lv.w; L.h = lv.h; L.pitch = lv.pitch;
+            L.win = win; L.ww = (unsigned)A.win_w[lvl];
+            const int wh = A.win_h[lvl];
+            L.k1 = (float)cam.k1; L.k2 = (float)cam.k2; L.k3 = (float)cam.k3; L.p1 = (float)cam.p1; L.p2 = (float)cam.p2;
+            L.sfx = (float)(scale * cam.fx); L.sfy = (float)(scale * cam.fy);
+            L.scx = (float)(scale * cam.cx); L.scy = (float)(scale * cam.cy);
+            L.cols = (float)lv.w; L.rows = (float)lv.h;     // scale * (cols_l / scale)
+            L.xc = (float)S->xc; L.yc = (float)S->yc;
+
+            // window origin: centred on the projection of P into image 2
+            if (tid == 0) {
+                double u2, v2;
+                fm3d_distort_K<double>(S->xc, S->yc, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, cam.fx, cam.fy, cam.cx, cam.cy, u2, v2);
+                double wxc = floor(scale * u2), wyc = floor(scale * v2);
+                if (!(wxc > -1e6 && wxc < 1e6)) wxc = 0;
+                if (!(wyc > -1e6 && wyc < 1e6)) wyc = 0;
+                // TMA needs the box start address 16-byte aligned: x origin is a multiple of 16 pixels
+                S->wx0 = (((int)wxc - (int)L.ww / 2 + 8) >> 4) << 4;
+                S->wy0 = (int)wyc - wh / 2;
+            }
+            __syncthreads();  // also: everybody is done with the previous level's window
+            L.wx0 = S->wx0; L.wy0 = S->wy0;
+            bool staged = false;
+            if (L.ww > 0 && wh > 0) {
+                if (A.use_tma && A.win_tma[lvl]) {
+                    const uint32_t parity = (uint32_t)S->tma_phase;
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar, (uint32_t)(L.ww * wh));
+                        tma_load_2d(win, &A.tmap[lvl], L.wx0, L.wy0, bar);
+                    }
+                    bool ok = false;
+                    for (int spin = 0; spin < (1 << 22); spin++) {
+                        if (mbar_try_wait(bar, parity)) { ok = true; break; }
+                    }
+                    staged = __syncthreads_and(ok ? 1 : 0) != 0;
+                    if (tid == 0) {
+                        S->tma_phase ^= 1;
+                        if (!staged) atomicExch(A.error_flag, 1);
+                    }
+                } else {
+                    // boxes wider than a TMA tile (or TMA switched off): cooperative 16-byte loads
+                    const int ww = (int)L.ww, wq = ww >> 4;
+                    for (int i = tid; i < wq * wh; i += NT) {
+                        const int yy = i / wq, xq = i - yy * wq;
+                        const int gx = L.wx0 + 16 * xq, gy = L.wy0 + yy;
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (gy >= 0 && gy < lv.h && gx >= 0 && gx + 16 <= lv.pitch) {
+                            v = *reinterpret_cast<const uint4*>(L.img2 + (size_t)gy * lv.pitch + gx);
+                        } else if (gy >= 0 && gy < lv.h) {
+                            __align__(16) uint8_t b[16];
+                            for (int k = 0; k < 16; k++) b[k] = (gx + k >= 0 && gx + k < lv.w) ? L.img2[(size_t)gy * lv.pitch + gx + k] : 0;
+                            v = *reinterpret_cast<uint4*>(b);
+                        }
+                        *reinterpret_cast<uint4*>(win + (size_t)yy * ww + 16 * xq) = v;
+                    }
+                    staged = true;
+                }
+            }
+            // taps (x0,y0),(x0+1,y0+1) must lie inside the window and inside the image
+            {
+                int x_lo = max(L.wx0, 0), x_hi = min(L.wx0 + (int)L.ww, lv.w) - 1;  // x0 in [x_lo, x_hi)
+                int y_lo = max(L.wy0, 0), y_hi = min(L.wy0 + wh, lv.h) - 1;
+                L.lx_min = x_lo - L.wx0; L.lx_cnt = staged ? max(x_hi - x_lo, 0) : 0;
+                L.ly_min = y_lo - L.wy0; L.ly_cnt = staged ? max(y_hi - y_lo, 0) : 0;
+            }
+            L.coff = (FLOOR_MAGIC_BITS + (unsigned)L.wy0) * L.ww + FLOOR_MAGIC_BITS + (unsigned)L.wx0;
+            L.amax = L.ww * (unsigned)wh - L.ww - 2u;
+
+            // image-1 intensities of the level (updateImage1PixelsIntensity, :576-589)
+            unsigned lvl_flags = 0;
+            {
+                int row = 0;
+                for (int idx = tid; idx < m; idx += NT) {
+                    while (idx >= rows->start[row + 1]) row++;
+                    const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
+                    const double py = cv + (double)rows->jrow[row];
+                    if (!fm3d_pixel_good(px, py, inv_scale, lv.w, lv.h)) lvl_flags |= FLAG_PIX;
+                    i1[idx] = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, (float)(scale * px), (float)(scale * py));
+                }
+            }
+
+            // warp 0: start the LM of this level (optimize(), :247-292)
+            if (wid == 0) {
+                double phi, theta;
+                if (A.mode == 0) {
+                    const double* nv = S->normal;
+                    theta = atan2(nv[2], sqrt(nv[0] * nv[0] + nv[1] * nv[1]));  // car2sph (tools.cpp:767-771)
+                    phi = atan2(nv[1], nv[0]);
+                    if (lane == 0) {
+                        PP->slow = 0;
+                        fm3d_lm2_init(&S->lm, phi, theta, A.eps_lmmin, A.patience);
+                        S->where = AT_X_JAC;
+                    }
+                    publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
+                } else {
+                    phi = A.phi_theta[2 * f]; theta = A.phi_theta[2 * f + 1];
+                    if (lane == 0) {
+                        PP->slow = 0;
+                        S->lm.nfev = 0;
+                        S->lm.eps = 1e-5;
+                        S->where = AT_XT_PLAIN;
+                    }
+                    publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
+                }
+            }
+            __syncthreads();
+
+            // -------------------------------------------------------- pass loop (two barriers per pass)
+            for (;;) {
+                const FastPass P = *PP;
+                if (P.kind == PASS_STOP) break;
+                const long long t_a = clock64();
+
+                unsigned flags = lvl_flags;
+                lvl_flags = 0;
+                for (int k = tid; k < n_boundary; k += NT) {
+                    int idx;
+                    if (k < 2 * nrows) {
+                        const int row = k >> 1;
+                        const int s0 = rows->start[row], s1 = rows->start[row + 1];
+                        if (s1 <= s0) continue;
+                        idx = (k & 1) ? s1 - 1 : s0;
+                    } else if (k < 2 * nrows + n_first) {
+                        idx = rows->start[first_row] + (k - 2 * nrows);
+                    } else {
+                        idx = rows->start[last_row] + (k - 2 * nrows - n_first);
+                    }
+                    flags |= boundary_flags(P, L, vcxf, vcyf, cmax, rays[idx]);
+                }
+
+                Acc acc;
+                acc.s0 = 0.0; acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.0f;
+                if (P.kind == PASS_JAC) {
+                    if (!P.slow) run_pixels<true, false>(P, L, rays, i1, m, tid, NT, acc);
+                    else run_pixels<true, true>(P, L, rays, i1, m, tid, NT, acc);
+                } else {
+                    if (!P.slow) run_pixels<false, false>(P, L, rays, i1, m, tid, NT, acc);
+                    else run_pixels<false, true>(P, L, rays, i1, m, tid, NT, acc);
+                }
+                double a0 = warp_sum(acc.s0), a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+                if (P.kind == PASS_JAC) {
+                    a1 = warp_sum((double)acc.s1); a2 = warp_sum((double)acc.s2); a3 = warp_sum((double)acc.s3);
+                    a4 = warp_sum((double)acc.s4); a5 = warp_sum((double)acc.s5);
+                }
+                flags = __reduce_or_sync(0xffffffffu, flags);
+                if (lane == 0) {
+                    double* rw = red + wid * 6;
+                    rw[0] = a0; rw[1] = a1; rw[2] = a2; rw[3] = a3; rw[4] = a4; rw[5] = a5;
+                    wflags[wid] = flags;
+                }
+                const long long t_b0 = clock64();
+                __syncthreads();
+                const long long t_b = clock64();
+
+                if (wid == 0) {
+                    double s[6];
+                    unsigned any_flags = lane < NW ? wflags[lane] : 0u;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        double v = lane < NW ? red[lane * 6 + k] : 0.0;
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        s[k] = v;
+                    }
+                    any_flags = __reduce_or_sync(0xffffffffu, any_flags);
+                    int next_kind = PASS_STOP;          // what lane 0 asks the warp to publish
+                    double next_phi = 0.0, next_theta = 0.0;
+                    const long long t_r = clock64();
+                    long long t_p = t_r;
+                    if (lane == 0) {
+                        // the LM state works in registers: every access through the shared-memory
+                        // struct would be a 30-cycle load on a single thread's dependent chain
+                        fm3d_lm2 lm = S->lm;
+                        int cmd = -1;   // -1: repeat the pass
+                        {   // executed work (fm3d_get_normals_stats)
+                            const int wh_ = S->where;
+                            const int slot = P.kind == PASS_VALUE ? 0 : (wh_ == AT_X_JAC ? 1 : 2);
+                            S->stats[slot]++;
+                            if (P.slow) S->stats[4]++;
+                            S->stats[P.kind == PASS_VALUE ? 5 : 6] += (unsigned long long)m;
+                        }
+                        if ((any_flags & FLAG_WINDOW) && !(any_flags & 7) && !P.slow) {
+                            PP->slow = 1;               // same pass again, taps from global memory
+                        } else if ((any_flags & 7) || s[0] != s[0]) {
+                            // all bounding-box / NaN tests of an evaluation precede its pixel tests
+                            S->status = ((any_flags & FLAG_NAN) || !(any_flags & 7)) ? FM3D_FEAT_ABORT_NAN
+                                      : (any_flags & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
+                            S->alive = 0;
+                            PP->kind = PASS_STOP;
+                            cmd = 0;
+                        } else if (A.mode != 0) {
+                            A.cost[f] = S->w[0] * S->w[0] * s[0];
+                            PP->kind = PASS_STOP;
+                            cmd = 0;
+                        } else {
+                            const int where = S->where;
+                            bool first_trial = false;   // the next trial opens an LM iteration
+                            if (where == AT_X_JAC) {
+                                if (lm.first && S->w[0] != 1.0) S->npenalty++;
+                                cmd = consume_jacobian(S, lm, s, A.penalty_mode);
+                                first_trial = true;
+                            } else {
+                                if (S->w[0] != 1.0) S->npenalty++;
+                                cmd = fm3d_lm2_after_trial(&lm, S->w[0] * S->w[0] * s[0]);
+                                // accepted (x == xt now) and the Jacobian came with the trial
+                                if (cmd == FM3D_LM_CMD_JAC && where == AT_XT_FUSED) {
+                                    S->stats[3]++;
+                                    cmd = consume_jacobian(S, lm, s, A.penalty_mode);
+                                    first_trial = true;
+                                }
+                            }
+                            t_p = clock64();
+                            if (cmd == FM3D_LM_CMD_JAC) {
+                                S->where = AT_X_JAC;
+                                next_kind = PASS_JAC; next_phi = lm.x[0]; next_theta = lm.x[1];
+                            } else if (cmd == FM3D_LM_CMD_TRIAL) {
+                                // first trial of an iteration: evaluate its Jacobian along with it;
+                                // re-trials after a rejection are value-only
+                                const bool fuse = first_trial && A.fuse_trials;
+                                S->where = fuse ? AT_XT_FUSED : AT_XT_PLAIN;
+                                next_kind = fuse ? PASS_JAC : PASS_VALUE; next_phi = lm.xt[0]; next_theta = lm.xt[1];
+                            } else {
+                                PP->kind = PASS_STOP;   // FM3D_LM_CMD_DONE
+                            }
+                            S->lm = lm;
+                        }
+                    }
+                    next_kind = __shfl_sync(0xffffffffu, next_kind, 0);
+                    if (next_kind != PASS_STOP) {
+                        next_phi = __shfl_sync(0xffffffffu, next_phi, 0);
+                        next_theta = __shfl_sync(0xffffffffu, next_theta, 0);
+                        publish_pass(PP, S, cam, next_phi, next_theta, next_kind, A.penalty_mode, S->lm.eps, lane);
+                    }
+                    if (lane == 0) {
+                        const long long t_c = clock64();
+                        S->stats[8] += (unsigned long long)(t_b0 - t_a);   // thread 0: pixel work of the pass
+                        S->stats[9] += (unsigned long long)(t_b - t_b0);   // thread 0: wait at the barrier
+                        S->stats[10] += (unsigned long long)(t_c - t_b);   // reduction + LM + publish
+                        S->stats[11] += (unsigned long long)(t_p - t_r);   //   of which LM algebra
+                        S->stats[12] += (unsigned long long)(t_c - t_p);   //   of which sincos + homographies
+                    }
+                }
+                __syncthreads();
+            }
+            alive = S->alive != 0;
+
+            if (tid == 0 && A.mode == 0) {
+                const fm3d_lm2& lm = S->lm;
+                if (alive) {
+                    // sph2car of the solution (:289)
+                    S->normal[0] = cos(lm.x[1]) * cos(lm.x[0]);
+                    S->normal[1] = cos(lm.x[1]) * sin(lm.x[0]);
+                    S->normal[2] = sin(lm.x[1]);
+                    if (A.cost) A.cost[f] = lm.fnorm * lm.fnorm;
+                }
+                if (A.nfev) A.nfev[(size_t)f * (levels + 1) + lvl] = lm.nfev;
+            }
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------ epilogue
+        if (tid < 16 && A.stats) {
+            const unsigned long long v = tid == 7 ? 1ull : S->stats[tid];
+            if (v) atomicAdd(A.stats + tid, v);
+        }
+        if (tid == 0) {
+            const int st = S->status;
+            A.status[f] = st;
+            if (A.mode == 0) {
+                if (st == FM3D_FEAT_OK) {
+                    A.normals[3 * f] = S->normal[0]; A.normals[3 * f + 1] = S->normal[1]; A.normals[3 * f + 2] = S->normal[2];
+                } else {
+                    const double nrm = sqrt(Px * Px + Py * Py + Pz * Pz);
+                    A.normals[3 * f] = Px / nrm; A.normals[3 * f + 1] = Py / nrm; A.normals[3 * f + 2] = Pz / nrm;
+                    if (A.cost) A.cost[f] = __longlong_as_double(0x7ff8000000000000LL);
+                }
+                if (A.npenalty) A.npenalty[f] = S->npenalty;
+            } else if (st != FM3D_FEAT_OK) {
+                A.cost[f] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t fast_tail_bytes() {
+    return 16 + ((sizeof(RowTable) + 15) & ~(size_t)15) + sizeof(double) * 16 * 6 + sizeof(unsigned) * 16 +
+           ((sizeof(FastShared) + 15) & ~(size_t)15) + ((sizeof(FastPass) + 15) & ~(size_t)15) + 16;
+}
+
+}  // namespace
+
+int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
+    A.cam = ctx->cam;
+    A.pyr = ctx->pyr;
+    A.patience = ctx->opt_lm_patience;
+    A.use_tma = ctx->opt_normals_tma;
+    A.fuse_trials = ctx->opt_normals_fuse;
+    A.mcap = (disc_capacity(A.r) + 31) & ~31;
+    int nt = ctx->opt_normals_threads;
+    nt = nt < 64 ? 64 : (nt > FAST_NT ? FAST_NT : (nt & ~31));
+    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
+    const size_t per_px = sizeof(float2) + sizeof(float);
+    const size_t tail = fast_tail_bytes() + 128;
+
+    // window per level: the warp of the disc is close to a similarity, 1.3x the scaled radius
+    // plus margins; if the rays do not fit beside it they live in global memory and the window
+    // may take (almost) all of shared memory
+    auto plan_windows = [&](size_t budget) -> size_t {
+        size_t win_bytes = 0;
+        for (int l = 0; l <= A.pyr.levels; l++) {
+            const double rs = (double)A.r / (double)(1 << l);
+            int half = (int)ceil(1.3 * rs) + 8;
+            int ww = (2 * half + 16 + 15) & ~15, wh = 2 * half;   // +16: slack for the 16-pixel origin alignment
+            while ((size_t)ww * wh > budget && ww > 32 && wh > 16) { ww = (ww * 7 / 8) & ~15; wh = wh * 7 / 8; }
+            A.win_w[l] = ww; A.win_h[l] = wh;
+            A.win_tma[l] = (ww <= 256 && wh <= 256) ? 1 : 0;
+            if ((size_t)ww * wh > win_bytes) win_bytes = (size_t)ww * wh;
+        }
+        return (win_bytes + 127) & ~(size_t)127;
+    };
+    size_t win_bytes = plan_windows(64 << 10);
+    bool rays_smem = win_bytes + per_px * (size_t)A.mcap + tail <= smem_max;
+    if (!rays_smem) win_bytes = plan_windows(smem_max - tail - 1024);
+    A.win_bytes = (int)win_bytes;
+    for (int l = 0; l <= A.pyr.levels; l++) {
+        if (A.use_tma && A.win_tma[l]) {
+            const fm3d_level& lv = A.pyr.lv[l];
+            if (int rc = fm3d_encode_tmap_2d_u8(ctx, &A.tmap[l], A.pyr.base[1] + lv.off, lv.w, lv.h, lv.pitch,
+                                                A.win_w[l], A.win_h[l]))
+                return rc;
+        }
+    }
+    const size_t smem = win_bytes + (rays_smem ? per_px * (size_t)A.mcap : 0) + tail;
+
+    auto launch = [&](auto kernel) -> int {
+        FM3D_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        FM3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nt, smem));
+        if (occ < 1) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "normals kernel does not fit (smem %zu)", smem);
+        int grid = ctx->prop.multiProcessorCount * occ;
+        if (grid > A.n) grid = A.n;
+        int* ctrl = nullptr;  // [0] work counter, [1] error flag
+        if (int rc = fm3d_scratch(ctx, 1, 256, (void**)&ctrl)) return rc;
+        ctx->n_copy++;
+        FM3D_CUDA(ctx, cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
+        A.work_counter = ctrl;
+        A.error_flag = ctrl + 1;
+        A.stats = reinterpret_cast<unsigned long long*>(ctrl + 16);
+        A.rays_g = nullptr; A.i1_g = nullptr;
+        if (!rays_smem) {
+            char* g = nullptr;
+            if (int rc = fm3d_scratch(ctx, 2, per_px * (size_t)A.mcap * grid, (void**)&g)) return rc;
+            A.rays_g = (float2*)g;
+            A.i1_g = (float*)(g + sizeof(float2) * (size_t)A.mcap * grid);
+        }
+        kernel<<<grid, nt, smem, ctx->stream>>>(A);
+        FM3D_LAUNCH_CHECK(ctx);
+        return FM3D_OK;
+    };
+    return rays_smem ? launch(normals_fast_kernel<true>) : launch(normals_fast_kernel<false>);
+}
+
+}  // namespace fm3d_normals

@@ -219,6 +219,18 @@ int fm3d_optimize_normals_dev(fm3d_ctx* ctx, const double* xyz, int n, int pixel
                               int32_t* status, int32_t* nfev, int32_t* npenalty,
                               double* cost);
 
+/* Work executed by the last fm3d_optimize_normals[_dev] / fm3d_evaluate_normals call of this
+ * context (synchronises the stream):
+ *   out[0] value-only passes over the disc      out[1] value+Jacobian passes at the LM iterate
+ *   out[2] trial passes evaluated with Jacobian out[3] ... of which lmfit accepted the trial
+ *   out[4] passes that sampled from global memory (window miss)
+ *   out[5] pixel evaluations of value-only passes   out[6] of value+Jacobian passes
+ *   out[7] features processed
+ *   out[8..10] SM cycles of thread 0 in: the pixel loop of the passes / waiting for the slowest
+ *   warp / the serial reduction + LM step + homography set-up;  out[11..15] reserved
+ * nfev (above) counts what lmfit would have evaluated; these count what the GPU did. */
+int fm3d_get_normals_stats(fm3d_ctx* ctx, int64_t out[16]);
+
 /* One evaluation of the cost the optimiser minimises (evaluateNormal,
  * normaloptimizer.cpp:65-149) for given normals at pyramid level `level`:
  * cost[i] = sum of squared weighted residuals, m[i] = number of disc pixels,
