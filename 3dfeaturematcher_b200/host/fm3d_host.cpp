@@ -179,7 +179,7 @@ void DescriptorsMatcher::extractDescriptorsFromPatches(const std::vector<cv::Mat
 
 // -------------------------------------------------------------------- SingleCameraTriangulator
 SingleCameraTriangulator::SingleCameraTriangulator(cv::FileStorage& settings)
-    : ctx_(host_ctx()), patch_eps_(0), patch_cmpp_(0), pyramids_(0), write_patch_files_(true) {
+    : ctx_(host_ctx()), patch_eps_(0), patch_cmpp_(0), pyramids_(0), write_patch_files_(getenv("FM3D_NO_PATCH_FILES") == nullptr) {
     std::vector<double> tIC, rIC;
     settings["CameraSettings"]["translationIC"] >> tIC;
     settings["CameraSettings"]["rodriguesIC"] >> rIC;

@@ -6,7 +6,8 @@
 
 A step is one pass of the hot path over one synthetic stereo pair of BASELINE.json configs[1]:
 1280x720, 5 000 SIFT-128 float keypoints per GPU, pixelsRay 64, pyramids 3 (4 LM stages),
-NNDR 0.55, penalty as compiled today (fabs).  Inputs are resident in HBM for `value`; `e2e` is
+NNDR 0.55, penalty wall as the reference's author built it (int abs; the fabs variant of today's
+g++ is measured next to it as `penalty_fabs`).  Inputs are resident in HBM for `value`; `e2e` is
 the same step through the host-buffer C-ABI calls (pinned host inputs, copies inside the
 timed region).  With N ranks every rank owns a contiguous shard of N*5000 query keypoints
 (weak scaling), rank 0's train descriptors and images are broadcast with NCCL and the
@@ -34,8 +35,15 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, N_KP, N_DISTRACT = 1280, 720, 5000, 1000
 PIXELS_RAY, PYRAMIDS, NNDR_EPS, EPS_LMMIN = 64, 3, 0.55, 1e-10
-PENALTY = 0  # FM3D_PENALTY_FABS: the source as compiled by today's g++
-FLOP_PER_PIXEL_EVAL = 64.0  # algorithmic fp32 work of one pixel evaluation
+# Semantics of the unqualified abs() in the reference's penalty wall.  The headline
+# runs the reference as its author built it (int abs(int): the wall is outside the operating range and
+# the normals converge); the same step under today's g++ (fabs: every synthetic feature ends on the
+# wall, 12 deg median error in the oracle too) is measured next to it and reported as `penalty_fabs`.
+PENALTY = 1          # FM3D_PENALTY_INT_ABS
+PENALTY_ALT = 0      # FM3D_PENALTY_FABS
+PENALTY_NAMES = {0: "fabs", 1: "int_abs", 2: "off"}
+FLOP_PER_PIXEL_EVAL = 64.0    # algorithmic fp32 work of one pixel evaluation
+FLOP_PER_PIXEL_JAC = 152.0    # the same plus its analytic derivatives w.r.t. (phi, theta)
 SEED = 1001
 
 
@@ -104,7 +112,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_reference(case, n_features_sample, threads):
+def cpu_reference(case, n_features_sample, threads, penalty=None):
     """Times the CPU port of the reference path (oracle/fm3d_oracle.c) on a bounded sample."""
     from oracle import oracle_c as orc
     cam = case["scene"].cam
@@ -126,7 +134,7 @@ def cpu_reference(case, n_features_sample, threads):
     sel = np.sort(rng.choice(xyz.shape[0], min(n_features_sample, xyz.shape[0]), replace=False))
     t0 = time.perf_counter()
     res = orc.optimize_normals(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
-                               PYRAMIDS, xyz[sel], PIXELS_RAY, EPS_LMMIN, penalty_mode=PENALTY, threads=threads,
+                               PYRAMIDS, xyz[sel], PIXELS_RAY, EPS_LMMIN, penalty_mode=PENALTY if penalty is None else penalty, threads=threads,
                                pyr1=pyr1, pyr2=pyr2)
     t_norm = time.perf_counter() - t0
     n_match = len(qi)
@@ -170,7 +178,8 @@ def run_reference_arm(args):
 def workload_config(n_ranks):
     return {"workload": f"BASELINE configs[1]: {WIDTH}x{HEIGHT} synthetic stereo pair, {N_KP} SIFT-128 float keypoints per GPU "
                         f"(+{N_DISTRACT} distractors), pixelsRay {PIXELS_RAY}, pyramids {PYRAMIDS} (4 LM stages), NNDR {NNDR_EPS}",
-            "penalty_mode": "fabs", "geometry": "f64", "per_gpu_query_keypoints": N_KP, "global_query_keypoints": N_KP * n_ranks,
+            "penalty_mode": PENALTY_NAMES[PENALTY], "normal_search": "fast kernel: fp32 offset-form geometry, analytic Jacobian, fp64 LM state",
+            "per_gpu_query_keypoints": N_KP, "global_query_keypoints": N_KP * n_ranks,
             "parallelism": f"keypoint shards x{n_ranks}", "l2_flush_between_steps": True}
 
 
@@ -240,7 +249,7 @@ def run_gpu_arm(args):
     n_stage = 5
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_stage + 1)] for _ in range(args.steps)]
 
-    def device_step(events=None):
+    def device_step(events=None, penalty=PENALTY):
         """One pass of the hot path on resident inputs (all work on the context's stream)."""
         with torch.cuda.stream(stream):
             if events: events[0].record(stream)
@@ -257,7 +266,7 @@ def run_gpu_arm(args):
             ctx.set_images_dev(d_img1.data_ptr(), d_img2.data_ptr(), W, H, W, PYRAMIDS)
             if events: events[3].record(stream)
             n_inl = int(d_ninl.item())
-            ctx.optimize_normals_dev(d_xyz.data_ptr(), n_inl, PIXELS_RAY, EPS_LMMIN, PENALTY, d_normals.data_ptr(),
+            ctx.optimize_normals_dev(d_xyz.data_ptr(), n_inl, PIXELS_RAY, EPS_LMMIN, penalty, d_normals.data_ptr(),
                                      d_status.data_ptr(), d_nfev.data_ptr(), d_npen.data_ptr(), d_cost.data_ptr())
             if events: events[4].record(stream)
             if world > 1:
@@ -331,27 +340,49 @@ def run_gpu_arm(args):
     barrier()
     t_e2e = time.perf_counter() - t0
 
+    # ---- executed-work counters of the last headline launch, then the same step under fabs semantics
+    stats = ctx.normals_stats()
+    nfev_main = d_nfev[:n_inl].cpu().numpy().astype(np.int64)
+    status_main = d_status[:n_inl].cpu().numpy()
+    npen_main = d_npen[:n_inl].cpu().numpy()
+    alt_steps = max(1, min(args.steps, 3))
+    for _ in range(2):
+        device_step(penalty=PENALTY_ALT)
+        flush_l2()
+    barrier()
+    ev_alt = [[torch.cuda.Event(enable_timing=True) for _ in range(n_stage + 1)] for _ in range(alt_steps)]
+    for s_ in range(alt_steps):
+        n_match_alt, n_inl_alt = device_step(ev_alt[s_], penalty=PENALTY_ALT)
+        flush_l2()
+    barrier()
+    t_alt_ms = sum(ev_alt[s_][0].elapsed_time(ev_alt[s_][n_stage]) for s_ in range(alt_steps)) / alt_steps
+    t_alt_norm_ms = sum(ev_alt[s_][3].elapsed_time(ev_alt[s_][4]) for s_ in range(alt_steps)) / alt_steps
+    stats_alt = ctx.normals_stats()
+    nfev_alt = d_nfev[:n_inl_alt].cpu().numpy().astype(np.int64)
+    npen_alt = d_npen[:n_inl_alt].cpu().numpy()
+
     # ---- reduce over ranks: max time, summed features
-    tm = torch.tensor([t_dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
-    feats = torch.tensor([float(n_match), float(hm)], dtype=torch.float64, device=dev)
+    tm = torch.tensor([t_dev_ms, t_e2e * 1e3, t_alt_ms], dtype=torch.float64, device=dev)
+    feats = torch.tensor([float(n_match), float(hm), float(n_match_alt)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(feats, op=dist.ReduceOp.SUM)
-    t_dev_ms, t_e2e_ms = float(tm[0]), float(tm[1])
-    tot_feat, tot_feat_e2e = float(feats[0]), float(feats[1])
+    t_dev_ms, t_e2e_ms, t_alt_ms = float(tm[0]), float(tm[1]), float(tm[2])
+    tot_feat, tot_feat_e2e, tot_feat_alt = float(feats[0]), float(feats[1]), float(feats[2])
 
     if rank == 0:
-        nfev = d_nfev[:n_inl].cpu().numpy().astype(np.int64)
-        status = d_status[:n_inl].cpu().numpy()
-        npen = d_npen[:n_inl].cpu().numpy()
-        # algorithmic work of the normal optimiser: sum over features and levels of nfev * m;
-        # every bench feature has the full disc (m = 12853 at r = 64)
+        nfev, status, npen = nfev_main, status_main, npen_main
+        # work of the normal search (rank 0's launch).  Executed: pixel evaluations the kernel made
+        # (value-only passes, value + analytic Jacobian passes).  Reference-equivalent: sum over
+        # features and levels of nfev * m, nfev = evaluations lmfit would have made with its
+        # forward-difference Jacobian; every bench feature has the full disc (m = 12853 at r = 64).
         m_disc = sum(2 * int(np.floor(np.sqrt(PIXELS_RAY ** 2 - j * j))) + 1 for j in range(-PIXELS_RAY, PIXELS_RAY + 1))
-        pixel_evals = float(nfev.sum()) * m_disc
+        pixel_evals_ref = float(nfev.sum()) * m_disc
         t_norm_s = stage_ms[3] / args.steps * 1e-3
         sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
         fp32_peak = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
-        achieved = pixel_evals * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12
+        flops_exec = stats["pixel_evals_value"] * FLOP_PER_PIXEL_EVAL + stats["pixel_evals_jacobian"] * FLOP_PER_PIXEL_JAC
+        achieved = flops_exec / t_norm_s / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -361,13 +392,24 @@ def run_gpu_arm(args):
         bf16_peak = peaks.get("bf16_tflops", 1590.0)
         pyr_bytes = sum(2 * 1.25 * (W >> l) * (H >> l) for l in range(PYRAMIDS))
         match_pairs = float(nq) * nt
+        n_pass = stats["passes_value"] + stats["passes_jacobian"] + stats["passes_fused"]
+        cyc = {k: stats[k] for k in ("cycles_pixels", "cycles_barrier", "cycles_serial", "cycles_lm", "cycles_publish")}
+        cyc_tot = max(1, cyc["cycles_pixels"] + cyc["cycles_barrier"] + cyc["cycles_serial"])
         roofline = {
-            "kernel": "normals_kernel<double> (K6: LM normal search, one CTA per feature)",
+            "kernel": "normals_fast_kernel<true> (K6: LM normal search, one persistent CTA per SM, one feature per CTA at a time)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             "traffic": None,
-            "note": "compute-bound kernel (SURVEY 8d): algorithmic 64 flop x sum(nfev*m) pixel evaluations / CUDA-event time; "
-                    "peak = SMs*128*2*f_max (nominal fp32; MEASURED_PEAKS.json has no fp32 figure); geometry runs in fp64",
-            "pixel_evals_per_launch": pixel_evals, "ms_per_launch": t_norm_s * 1e3,
+            "note": "compute-bound kernel (SURVEY 8d): algorithmic flops = 64 x value-only pixel evaluations + 152 x "
+                    "value+analytic-Jacobian pixel evaluations executed (counted by the kernel) / CUDA-event time; peak = "
+                    "SMs*128*2*f_max (nominal fp32; MEASURED_PEAKS.json has no fp32 figure); HBM traffic is compulsory only "
+                    "(~44 KB/feature) and DRAM throughput ~0 (ncu, profiles/)",
+            "pixel_evals_value": stats["pixel_evals_value"], "pixel_evals_jacobian": stats["pixel_evals_jacobian"],
+            "passes": n_pass, "passes_fused": stats["passes_fused"], "fused_accepted": stats["fused_accepted"],
+            "passes_global_taps": stats["passes_slow"],
+            "reference_equivalent_pixel_evals": pixel_evals_ref,
+            "reference_equivalent_tflops": pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12,
+            "thread0_cycle_share": {"pixel_loop": cyc["cycles_pixels"] / cyc_tot, "serial_lm_step": cyc["cycles_serial"] / cyc_tot},
+            "ms_per_launch": t_norm_s * 1e3,
             "hbm_compulsory_gbs": (n_inl * 44e3 / t_norm_s) / 1e9, "hbm_peak_gbs": hbm_peak,
         }
         roofline_other = {
@@ -378,11 +420,12 @@ def run_gpu_arm(args):
                         "unit": "GB/s", "ms": stage_ms[2] / args.steps, "note": "3 launches + 2 device copies of 0.9 MB images: launch-bound"},
         }
         cpu = cpu_reference(case, max(2 * (os.cpu_count() or 1), 32), os.cpu_count() or 1) if world == 1 else None
+        cpu_alt = cpu_reference(case, max(os.cpu_count() or 1, 16), os.cpu_count() or 1, penalty=PENALTY_ALT) if world == 1 else None
         value = tot_feat * args.steps / (t_dev_ms * 1e-3)
         out = {
             "metric": "features/sec (match+triangulate+normal-opt)", "value": value, "unit": "features/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": tot_feat_e2e * args.steps / (t_e2e_ms * 1e-3), "unit": "features/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e_ms / args.steps},
@@ -399,6 +442,14 @@ def run_gpu_arm(args):
                                   "gather": stage_ms[4] / args.steps},
             "features_per_step": {"matches": tot_feat, "inliers_rank0": int(n_inl), "ok_rank0": int((status == 0).sum()),
                                   "wall_touching_rank0": int((npen > 0).sum()), "nfev_mean_per_level": nfev.mean(0).tolist()},
+            "penalty_fabs": {
+                "note": "the same step with the penalty wall as today's g++ compiles it (abs == fabs): every synthetic "
+                        "feature ends on the wall in the reference too (SURVEY fact 11); reported, not the headline",
+                "value": tot_feat_alt / (t_alt_ms * 1e-3), "unit": "features/s", "ms_per_step": t_alt_ms,
+                "normals_ms": t_alt_norm_ms, "wall_touching_rank0": int((npen_alt > 0).sum()),
+                "nfev_mean_per_level": nfev_alt.mean(0).tolist(),
+                "passes": stats_alt["passes_value"] + stats_alt["passes_jacobian"] + stats_alt["passes_fused"],
+                "cpu_baseline_features_per_s": None if cpu_alt is None else cpu_alt["features_per_s"]},
             "wall_s_device_arm": wall_dev, "gpu": info["name"],
         }
         print(json.dumps(out), flush=True)

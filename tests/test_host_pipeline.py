@@ -1,0 +1,185 @@
+"""The reference's own call sequence (main.cpp:91-187) on top of the four class adapters in
+3dfeaturematcher_b200/host/ (same class names and signatures as the reference, implemented over the
+C-ABI), driven through a settings.yml with the reference's layout, compared with the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import angle_deg, cam_tuple, orc, stereo_case, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "3dfeaturematcher_b200", "host")
+EXE = os.path.join(ROOT, "tests", "_build", "pipeline_main")
+
+
+def build_pipeline_main():
+    srcs = [os.path.join(ROOT, "tests", "cpp", "pipeline_main.cpp"), os.path.join(HOST, "fm3d_host.cpp")]
+    deps = srcs + [os.path.join(HOST, "fm3d_cv.h"), os.path.join(ROOT, "include", "fm3d.h")]
+    lib = os.path.join(ROOT, "3dfeaturematcher_b200", "libfm3d.so")
+    if not os.path.exists(lib):
+        __import__("importlib").import_module("3dfeaturematcher_b200.build").build()
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(d) for d in deps + [lib]):
+        os.makedirs(os.path.dirname(EXE), exist_ok=True)
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-I" + os.path.join(HOST, "include"), "-I" + HOST,
+                               "-I" + os.path.join(ROOT, "include")] + srcs +
+                              ["-L" + os.path.dirname(lib), "-lfm3d", "-Wl,-rpath," + os.path.dirname(lib), "-o", EXE])
+    return EXE
+
+
+def test_adapters_compile_and_link_against_the_c_abi():
+    """No GPU needed: the reference-shaped classes build against include/fm3d.h and link with libfm3d.so."""
+    exe = build_pipeline_main()
+    assert os.access(exe, os.X_OK)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 1 and "usage" in p.stderr
+
+
+def _rodrigues(r):
+    import cv2
+    return cv2.Rodrigues(np.asarray(r, np.float64).reshape(3, 1))[0]
+
+
+def _g(rod, t):
+    g = np.eye(4)
+    g[:3, :3] = _rodrigues(rod)
+    g[:3, 3] = t
+    return g
+
+
+def _write_inputs(tmp, case, r, pyramids, eps_m, cmpp):
+    import cv2
+    cam = case["scene"].cam
+    # poses such that g12 = g_IC^-1 g2^-1 g1 g_IC (singlecameratriangulator.cpp:140) is the scene's g12
+    rIC, tIC = np.asarray(synth.SETTINGS_RODRIGUES_IC, float), np.asarray(synth.SETTINGS_TRANSLATION_IC, float)
+    pos1 = np.array([5.301099, 8.031408, 1.977258, 0.153433, 0.149941, -2.658648])   # build/settings.yml:11
+    gIC, g1 = _g(rIC, tIC), _g(pos1[3:], pos1[:3])
+    g2 = g1 @ gIC @ np.linalg.inv(cam.g12) @ np.linalg.inv(gIC)
+    rod2 = cv2.Rodrigues(g2[:3, :3])[0].ravel()
+    pos2 = np.concatenate([g2[:3, 3], rod2])
+    for name, img in (("img1.pgm", case["scene"].img1), ("img2.pgm", case["scene"].img2)):
+        with open(os.path.join(tmp, name), "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+            f.write(np.ascontiguousarray(img).tobytes())
+    K, d = cam.K, cam.dist
+    fmt = lambda v: "[" + ", ".join(repr(float(x)) for x in v) + "]"
+    yml = f"""%YAML:1.0
+IMAGES:
+   img1: {os.path.join(tmp, 'img1.pgm')}
+   img2: {os.path.join(tmp, 'img2.pgm')}
+   pos1: {fmt(pos1)}
+   pos2: {fmt(pos2)}
+
+NNDR:
+   epsilon: 0.55
+
+Neighborhoods:
+   #Part for normal optimization: take pixels in the image
+   epsilonLMMIN: 1e-10
+   pixelsRay: {r}
+   pyramids: {pyramids}
+   method: square
+   cmPerPixel: {cmpp}
+   epsilon: {eps_m}
+
+FeatureOptions:
+   DetectorType: SIFT
+   DetectorMode: STATIC
+   ExtractorType: SIFT
+
+CameraSettings:
+   rodriguesIC: {fmt(rIC)}
+   translationIC: {fmt(tIC)}
+   Fx: {float(K[0, 0])!r}
+   Fy: {float(K[1, 1])!r}
+   Cx: {float(K[0, 2])!r}
+   Cy: {float(K[1, 2])!r}
+   p1: {float(d[2])!r}
+   p2: {float(d[3])!r}
+   k0: {float(d[0])!r}
+   k1: {float(d[1])!r}
+   k2: {float(d[4])!r}
+   zThresholdMin: {float(cam.z_min)!r}
+   zThresholdMax: {float(cam.z_max)!r}
+"""
+    with open(os.path.join(tmp, "settings.yml"), "w") as f:
+        f.write(yml)
+    n1, n2, dim = case["desc1"].shape[0], case["desc2"].shape[0], case["desc1"].shape[1]
+    with open(os.path.join(tmp, "features.bin"), "wb") as f:
+        f.write(struct.pack("iii", n1, n2, dim))
+        f.write(np.ascontiguousarray(case["kp1"], np.float32).tobytes())
+        f.write(np.ascontiguousarray(case["kp2"], np.float32).tobytes())
+        f.write(np.ascontiguousarray(case["desc1"], np.float32).tobytes())
+        f.write(np.ascontiguousarray(case["desc2"], np.float32).tobytes())
+
+
+def _read_result(path):
+    b = open(path, "rb").read()
+    nm, npts, nn, S = struct.unpack_from("iiii", b, 0)
+    o = 16
+    m = np.frombuffer(b, np.dtype([("q", "i4"), ("t", "i4"), ("d", "f4")]), nm, o); o += 12 * nm
+    mask = np.frombuffer(b, np.uint8, nm, o); o += nm
+    g12 = np.frombuffer(b, np.float64, 16, o).reshape(4, 4); o += 128
+    pts = np.frombuffer(b, np.float64, 3 * npts, o).reshape(-1, 3); o += 24 * npts
+    status = np.frombuffer(b, np.int32, npts, o); o += 4 * npts
+    kept = np.frombuffer(b, np.float64, 3 * nn, o).reshape(-1, 3); o += 24 * nn
+    normals = np.frombuffer(b, np.float64, 3 * nn, o).reshape(-1, 3); o += 24 * nn
+    frames = np.frombuffer(b, np.float64, 16 * nn, o).reshape(-1, 4, 4); o += 128 * nn
+    patches = np.frombuffer(b, np.uint8, nn * S * S, o).reshape(nn, S, S); o += nn * S * S
+    last_nb = np.frombuffer(b, np.float64, 3 * nn, o).reshape(-1, 3); o += 24 * nn
+    gravity = np.frombuffer(b, np.float64, 3, o); o += 24
+    assert o == len(b)
+    return dict(matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
+                patches=patches, last_nb=last_nb, gravity=gravity, S=S)
+
+
+@pytest.mark.gpu
+def test_main_cpp_call_sequence_on_the_adapters(tmp_path):
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    cam = case["scene"].cam
+    tmp = str(tmp_path)
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp)
+    env = dict(os.environ, FM3D_PENALTY="2", FM3D_NO_PATCH_FILES="1")
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), os.path.join(tmp, "features.bin"),
+                        os.path.join(tmp, "result.bin")], capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+
+    # matching + NNDR (descriptorsmatcher.cpp:117-129): exact
+    o_idx, o_dist = orc.knn2_f32(case["desc1"], case["desc2"])
+    oq, ot, od = orc.nndr_filter(o_idx, o_dist, 0.55)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    np.testing.assert_array_equal(res["matches"]["d"], od)
+    # setg12 from the poses (singlecameratriangulator.cpp:123-143)
+    np.testing.assert_allclose(res["g12"], cam.g12, rtol=0, atol=1e-9)
+    # triangulation with the composed g12
+    o_all, o_mask, o_xyz = orc.triangulate(cam.K, cam.dist, res["g12"], cam.z_min, cam.z_max, case["kp1"], case["kp2"], oq, ot)
+    np.testing.assert_array_equal(res["mask"].astype(bool), o_mask.astype(bool))
+    np.testing.assert_allclose(res["pts"], o_xyz, rtol=1e-9, atol=1e-12)
+    # normal optimisation: statuses identical, failed features erased from points3D in place
+    o = orc.optimize_normals(cam.K, cam.dist, res["g12"], cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                             pyramids, o_xyz, r, 1e-10, penalty_mode=2, threads=8)
+    np.testing.assert_array_equal(res["status"], o["status"])
+    ok = o["status"] == 0
+    assert ok.sum() >= 20
+    np.testing.assert_allclose(res["kept"], o_xyz[ok], rtol=1e-9, atol=1e-12)
+    assert (angle_deg(res["normals"], o["normals"][ok]) <= 0.5).all()
+    # frames (normaloptimizer.cpp:454-505) with the adapter's gravity = R_IC^-1 (0,0,-1) (:160-176)
+    g_expected = np.linalg.inv(_rodrigues(synth.SETTINGS_RODRIGUES_IC)) @ np.array([0.0, 0.0, -1.0])
+    np.testing.assert_allclose(res["gravity"], g_expected, atol=1e-12)
+    np.testing.assert_allclose(res["frames"], orc.feature_frames(res["kept"], res["normals"], res["gravity"]), rtol=0, atol=1e-12)
+    # patches: transposed write, truncation, +-1 gray level at float-cast boundaries
+    assert res["S"] == orc.patch_size(eps_m, cmpp)
+    o_patches, _ = orc.extract_patches(cam.K, cam.dist, case["scene"].img1, res["frames"], eps_m, cmpp, want_points=False)
+    diff = res["patches"].astype(int) - o_patches.astype(int)
+    assert (np.abs(diff) <= 1).all() and (diff != 0).mean() < 1e-3
+    # computeSquareNeighborhoodsByNormals: last grid point of every feature
+    S = res["S"]
+    ref_last = np.array([-eps_m + 0.01 * cmpp * (S - 1), -eps_m + 0.01 * cmpp * (S - 1), 0.0, 1.0])
+    np.testing.assert_allclose(res["last_nb"], (res["frames"] @ ref_last)[:, :3], rtol=0, atol=1e-12)
