@@ -33,24 +33,34 @@ enum fm3d_lm_cmd {
 };
 
 struct fm3d_lm2 {
-    // control (lm_control_struct)
-    double ftol, xtol, gtol, eps, stepbound;
+    // control: lm_control_double (ftol = xtol = gtol = 30 eps, stepbound 100) with the reference's
+    // epsilon override (normaloptimizer.cpp:272-274); eps = sqrt(max(epsilon, DBL_EPSILON))
+    double eps;
     int maxfev;
     // state
     double x[2], xt[2], h[2];
-    double diag[2], delta, par, xnorm, fnorm, gnorm;
+    double diag[2], delta, par, xnorm, gnorm;
+    double ff;                      // |f(x)|^2           (fnorm = sqrt(ff), kept in fnorm for callers)
+    double fnorm;
     double S00, S01, S11, g0, g1;   // J^T J and J^T f at x
-    double acnorm[2], step[2], pnorm;
+    double step[2], pnorm;
     int iter, nfev, info;
-    int first; // 1 until the first Jacobian pass has been consumed
+    int first;                      // 1 until the first Jacobian pass has been consumed
+    // per-Jacobian cache for lmpar (everything that does not depend on delta)
+    double gn0, gn1, gn_dx2;        // Gauss-Newton step and |D p_gn|^2
+    double id0, id1;                // 1 / diag
+    float a00, a01, a11, b0, b1;    // D^-1 J^T J D^-1, D^-1 J^T f
+    float gnf, gn_w2;               // |b|, and the Newton denominator at par = 0 (0: rank deficient)
+    // per-proposal cache for the trust-region update
+    double iff, prered, dirder;     // 1/ff, predicted reduction, directional derivative
 };
 
-FM3D_HD double fm3d_enorm2(double a, double b) { return sqrt(a * a + b * b); }
+#define FM3D_LM_USERTOL (30.0 * FM3D_DBL_EPS)
 
 // Cheap arithmetic for the serial LM update on the GPU (one thread, dependent chains: what counts
 // is the number of instructions in a row).  Host builds use the plain operators.
-//   fm3d_rcp    1/a in fp64: MUFU.RCP64H seed + two Newton steps (full precision up to the last
-//               ulp, no special-case branch: the operands here are positive and normal)
+//   fm3d_rcp, fm3d_sqrt   fp64 from the MUFU.RCP64H / MUFU.RSQ64H seeds + Newton steps (full
+//               precision up to the last ulp, no special-case branches: operands are positive, normal)
 //   fm3d_fdiv, fm3d_frcp, fm3d_fsqrt   fp32 MUFU forms (lmpar's search for par: 10 % tolerance)
 #if defined(__CUDA_ARCH__)
 FM3D_HD double fm3d_rcp(double a) {
@@ -60,15 +70,28 @@ FM3D_HD double fm3d_rcp(double a) {
     r = fma(r, fma(-a, r, 1.0), r);
     return r;
 }
+FM3D_HD double fm3d_sqrt(double a) {
+    if (!(a > 0.0)) return a == 0.0 ? 0.0 : sqrt(a);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    // r ~ a^-1/2 (20 bits): two Newton steps on r, then s = a r with one correction
+    r = r * fma(-0.5 * a * r, r, 1.5);
+    r = r * fma(-0.5 * a * r, r, 1.5);
+    const double sq = a * r;
+    return fma(0.5 * r, fma(-sq, sq, a), sq);
+}
 FM3D_HD float fm3d_frcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 FM3D_HD float fm3d_fdiv(float a, float b) { return a * fm3d_frcp(b); }
 FM3D_HD float fm3d_fsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 #else
 FM3D_HD double fm3d_rcp(double a) { return 1.0 / a; }
+FM3D_HD double fm3d_sqrt(double a) { return sqrt(a); }
 FM3D_HD float fm3d_frcp(float a) { return 1.0f / a; }
 FM3D_HD float fm3d_fdiv(float a, float b) { return a / b; }
 FM3D_HD float fm3d_fsqrt(float a) { return sqrtf(a); }
 #endif
+
+FM3D_HD double fm3d_enorm2(double a, double b) { return fm3d_sqrt(a * a + b * b); }
 
 // a*d - b*c with one rounding of the products compensated (Kahan)
 FM3D_HD double fm3d_det2(double a, double b, double c, double d) {
@@ -77,20 +100,24 @@ FM3D_HD double fm3d_det2(double a, double b, double c, double d) {
     const double f = fma(a, d, -w);
     return f + e;
 }
+FM3D_HD float fm3d_det2f(float a, float b, float c, float d) {
+    const float w = b * c;
+    const float e = fmaf(-b, c, w);
+    const float f = fmaf(a, d, -w);
+    return f + e;
+}
 
-// MINPACK lmpar for n = 2, on the normal equations.  lmpar works on the pivoted QR factor R of J
-// and calls qrsolv for every candidate parameter; with two unknowns R^T R = J^T J is already at
-// hand (it is what the CTA reduces), every solve (J^T J + par D^2) p = J^T f is a 2x2 Cramer
-// formula and the Newton correction ||R_par^-T D^2 p / |D p| ||^2 is the quadratic form of the same
-// inverse.  The iteration (bounds parl/paru, 0.1 delta tolerance, at most 10 steps, rank handling
-// of the Gauss-Newton step) is MINPACK's; the arithmetic is scalar: no arrays, no data-dependent
-// indexing.  Returns the new par; (*p0, *p1) = step.  This fp64 version is the fall-back of the
-// mixed-precision one below and what the host tests compare it with.
+// MINPACK lmpar for n = 2, on the normal equations, reference version in fp64 (host tests compare
+// the mixed-precision one below with it; it is also the fall-back when fp32 leaves its range).
+// lmpar works on the pivoted QR factor R of J and calls qrsolv for every candidate parameter;
+// with two unknowns R^T R = J^T J is already at hand (it is what the CTA reduces), every solve
+// (J^T J + par D^2) p = J^T f is a 2x2 Cramer formula and the Newton correction
+// ||R_par^-T D^2 p / |D p| ||^2 is the quadratic form of the same inverse.  The iteration (bounds
+// parl/paru, 0.1 delta tolerance, at most 10 steps, rank handling of the Gauss-Newton step) is
+// MINPACK's; the arithmetic is scalar: no arrays, no data-dependent indexing.
 FM3D_HD double fm3d_lmpar2_f64(const fm3d_lm2* s, double delta, double par, double* p0, double* p1) {
     const double S00 = s->S00, S01 = s->S01, S11 = s->S11, g0 = s->g0, g1 = s->g1;
     const double d0 = s->diag[0], d1 = s->diag[1];
-    // Gauss-Newton step; pivot = column of larger norm (first maximum wins), a zero diagonal of
-    // R zeroes the remaining components
     const bool piv1 = S11 > S00;
     const double Spp = piv1 ? S11 : S00, Sqq = piv1 ? S00 : S11;
     const double gp = piv1 ? g1 : g0, gq = piv1 ? g0 : g1;
@@ -144,24 +171,13 @@ FM3D_HD double fm3d_lmpar2_f64(const fm3d_lm2* s, double delta, double par, doub
     return par;
 }
 
-FM3D_HD float fm3d_det2f(float a, float b, float c, float d) {
-    const float w = b * c;
-    const float e = fmaf(-b, c, w);
-    const float f = fmaf(a, d, -w);
-    return f + e;
-}
-
-// The same iteration with the search for par in fp32.  lmpar only asks for |D p| within 10 % of
-// delta, so the Newton iteration on par does not need fp64: it runs in the scaled variables
-// z = D p (A = D^-1 J^T J D^-1 has |a_ij| <= 1 because diag_j >= |J_j|, b = D^-1 J^T f has
-// |b_j| <= |f|), where fp32 neither overflows nor loses the 10 % decision.  The step that is
-// returned solves (J^T J + par D^2) p = J^T f in fp64 for the par found, and the Gauss-Newton
-// step and its acceptance test are fp64 too.  On the GPU this takes the serial LM update between
-// two passes from ~30 dependent fp64 divisions / square roots to 3.
-FM3D_HD double fm3d_lmpar2(const fm3d_lm2* s, double delta, double par, double* p0, double* p1) {
+// Everything lmpar needs that does not depend on delta, computed once per Jacobian: the
+// Gauss-Newton step (fp64; rank test as in the pivoted QR: r11^2 = Sqq - S01^2 / Spp > 0), and the
+// problem in scaled variables z = D p in fp32 (A = D^-1 J^T J D^-1 has |a_ij| <= 1 because
+// diag_j >= |J_j|, b = D^-1 J^T f has |b_j| <= |f|).
+FM3D_HD void fm3d_lm2_cache_jacobian(fm3d_lm2* s) {
     const double S00 = s->S00, S01 = s->S01, S11 = s->S11, g0 = s->g0, g1 = s->g1;
     const double d0 = s->diag[0], d1 = s->diag[1];
-    // Gauss-Newton step (fp64): rank test as in the QR (r11^2 = Sqq - S01^2 / Spp > 0)
     const bool piv1 = S11 > S00;
     const double Spp = piv1 ? S11 : S00, Sqq = piv1 ? S00 : S11;
     const double gp = piv1 ? g1 : g0, gq = piv1 ? g0 : g1;
@@ -180,25 +196,39 @@ FM3D_HD double fm3d_lmpar2(const fm3d_lm2* s, double delta, double par, double* 
     }
     const double x0 = piv1 ? xq : xp, x1 = piv1 ? xp : xq;
     const double dx0 = d0 * x0, dx1 = d1 * x1;
-    const double dx2 = dx0 * dx0 + dx1 * dx1;
-    // fp = |D p| - delta <= 0.1 delta
-    if (dx2 <= 1.21 * delta * delta) { *p0 = x0; *p1 = x1; return 0.0; }
-
-    // Newton iteration on par in fp32, scaled variables
+    s->gn0 = x0; s->gn1 = x1;
+    s->gn_dx2 = dx0 * dx0 + dx1 * dx1;
     const double id0 = fm3d_rcp(d0), id1 = fm3d_rcp(d1);
+    s->id0 = id0; s->id1 = id1;
     const float a00 = (float)(S00 * id0 * id0), a01 = (float)(S01 * id0 * id1), a11 = (float)(S11 * id1 * id1);
     const float b0 = (float)(g0 * id0), b1 = (float)(g1 * id1);
-    const float df = (float)delta, idf = fm3d_frcp(df);
-    float dxn = fm3d_fsqrt((float)dx2);
-    float fp = dxn - df;
-    float parl = 0.0f;
+    s->a00 = a00; s->a01 = a01; s->a11 = a11; s->b0 = b0; s->b1 = b1;
+    s->gnf = fm3d_fsqrt(b0 * b0 + b1 * b1);
+    float w2 = 0.0f;
     if (full_rank) {
+        // Newton denominator at par = 0: y^T A^-1 y with y = z / |z|, z = D p_gn
         const float z0 = (float)dx0, z1 = (float)dx1;
         const float det0 = fm3d_det2f(a00, a01, a01, a11);
-        const float w2 = fm3d_fdiv(a11 * z0 * z0 - 2.0f * a01 * z0 * z1 + a00 * z1 * z1, det0 * dxn * dxn);
-        if (det0 > 0.0f && w2 > 0.0f) parl = fm3d_fdiv(fp * idf, w2);
+        const float q = fm3d_fdiv(a11 * z0 * z0 - 2.0f * a01 * z0 * z1 + a00 * z1 * z1, det0 * (z0 * z0 + z1 * z1));
+        if (det0 > 0.0f && q > 0.0f) w2 = q;
     }
-    const float gnorm = fm3d_fsqrt(b0 * b0 + b1 * b1);
+    s->gn_w2 = w2;
+}
+
+// lmpar with the search for par in fp32.  lmpar only asks for |D p| within 10 % of delta, so the
+// Newton iteration on par does not need fp64; the step that is returned solves
+// (J^T J + par D^2) p = J^T f in fp64 for the par found, and the Gauss-Newton step and its
+// acceptance test are fp64 too.  Needs fm3d_lm2_cache_jacobian.
+FM3D_HD double fm3d_lmpar2(const fm3d_lm2* s, double delta, double par, double* p0, double* p1) {
+    // fp = |D p_gn| - delta <= 0.1 delta: the Gauss-Newton step is inside the trust region
+    if (s->gn_dx2 <= 1.21 * delta * delta) { *p0 = s->gn0; *p1 = s->gn1; return 0.0; }
+    const float a00 = s->a00, a01 = s->a01, a11 = s->a11, b0 = s->b0, b1 = s->b1;
+    const float df = (float)delta, idf = fm3d_frcp(df);
+    float dxn = fm3d_fsqrt((float)s->gn_dx2);
+    float fp = dxn - df;
+    const float gn_w2 = s->gn_w2;
+    float parl = gn_w2 > 0.0f ? fm3d_fdiv(fp * idf, gn_w2) : 0.0f;
+    const float gnorm = s->gnf;
     float paru = gnorm * idf;
     if (paru == 0.0f) paru = 1.1754944e-38f / fminf(df, 0.1f);
     float parf = (float)par;
@@ -225,10 +255,11 @@ FM3D_HD double fm3d_lmpar2(const fm3d_lm2* s, double delta, double par, double* 
     if (!(parf >= 0.0f && parf <= 3.0e38f)) return fm3d_lmpar2_f64(s, delta, par, p0, p1);
     // the step for this par, fp64
     const double pd = (double)parf;
-    const double m00 = fma(pd * d0, d0, S00), m11 = fma(pd * d1, d1, S11);
+    const double d0 = s->diag[0], d1 = s->diag[1], S01 = s->S01;
+    const double m00 = fma(pd * d0, d0, s->S00), m11 = fma(pd * d1, d1, s->S11);
     const double idet = fm3d_rcp(fm3d_det2(m00, S01, S01, m11));
-    *p0 = fm3d_det2(m11, S01, g1, g0) * idet;
-    *p1 = fm3d_det2(m00, S01, g0, g1) * idet;
+    *p0 = fm3d_det2(m11, S01, s->g1, s->g0) * idet;
+    *p1 = fm3d_det2(m00, S01, s->g0, s->g1) * idet;
     return pd;
 }
 
@@ -237,32 +268,39 @@ FM3D_HD void fm3d_lm2_fd_steps(fm3d_lm2* s) {
     s->h[1] = fmax(s->eps * s->eps, s->eps * fabs(s->x[1]));
 }
 
-// lm_control_double with the reference's epsilon override (normaloptimizer.cpp:272-274).
 // Returns the first command (always a Jacobian pass; its f(x) doubles as lmdif's initial
 // evaluation, so the first pass accounts for 1 + 2 evaluations).
 FM3D_HD int fm3d_lm2_init(fm3d_lm2* s, double phi, double theta, double epsilon, int patience) {
-    const double usertol = 30.0 * FM3D_DBL_EPS;
-    s->ftol = usertol; s->xtol = usertol; s->gtol = usertol;
     s->eps = sqrt(fmax(epsilon, FM3D_DBL_EPS));
-    s->stepbound = 100.0;
     s->maxfev = patience * 3;
     s->x[0] = phi; s->x[1] = theta;
     s->iter = 0; s->nfev = 0; s->info = 0; s->first = 1;
-    s->par = 0.0; s->delta = 0.0; s->xnorm = 0.0; s->fnorm = 0.0; s->gnorm = 0.0;
+    s->par = 0.0; s->delta = 0.0; s->xnorm = 0.0; s->fnorm = 0.0; s->ff = 0.0; s->gnorm = 0.0;
     s->diag[0] = s->diag[1] = 0.0;
     fm3d_lm2_fd_steps(s);
     return FM3D_LM_CMD_JAC;
 }
 
-// Inner loop head: solve for the step and publish the trial point.
+// Inner loop head: solve for the step, publish the trial point, and prepare what the
+// trust-region update will need once the trial's residual is known.
 FM3D_HD int fm3d_lm2_propose(fm3d_lm2* s) {
     double p0, p1;
-    s->par = fm3d_lmpar2(s, s->delta, s->par, &p0, &p1);
+    const double par = fm3d_lmpar2(s, s->delta, s->par, &p0, &p1);
+    s->par = par;
     s->step[0] = p0; s->step[1] = p1;
     s->xt[0] = s->x[0] - p0;
     s->xt[1] = s->x[1] - p1;
-    s->pnorm = fm3d_enorm2(s->diag[0] * p0, s->diag[1] * p1);
-    if (s->nfev <= 1 + 2) s->delta = fmin(s->delta, s->pnorm);
+    const double dp0 = s->diag[0] * p0, dp1 = s->diag[1] * p1;
+    const double pn2 = dp0 * dp0 + dp1 * dp1;
+    const double pnorm = fm3d_sqrt(pn2);
+    s->pnorm = pnorm;
+    if (s->nfev <= 1 + 2) s->delta = fmin(s->delta, pnorm);
+    // |J p|^2 = p^T (J^T J) p;  prered = (|J p|^2 + 2 par |D p|^2) / |f|^2
+    const double jp2 = fmax(0.0, s->S00 * p0 * p0 + 2.0 * s->S01 * p0 * p1 + s->S11 * p1 * p1);
+    const double iff = s->iff;
+    const double t1sq = jp2 * iff, t2sq = par * pn2 * iff;
+    s->prered = t1sq + 2.0 * t2sq;
+    s->dirder = -(t1sq + t2sq);
     return FM3D_LM_CMD_TRIAL;
 }
 
@@ -271,72 +309,76 @@ FM3D_HD int fm3d_lm2_propose(fm3d_lm2* s) {
 FM3D_HD int fm3d_lm2_after_jacobian(fm3d_lm2* s, double ff, double S00, double S01, double S11,
                                     double g0, double g1) {
     if (s->first) { s->nfev = 3; s->first = 0; } else { s->nfev += 2; }
-    s->fnorm = sqrt(ff);
+    const double fnorm = fm3d_sqrt(ff);
+    s->ff = ff; s->fnorm = fnorm;
+    s->iff = fm3d_rcp(ff);
     s->S00 = S00; s->S01 = S01; s->S11 = S11; s->g0 = g0; s->g1 = g1;
-    const double an0 = sqrt(S00), an1 = sqrt(S11);
-    s->acnorm[0] = an0; s->acnorm[1] = an1;
+    const double an0 = fm3d_sqrt(S00), an1 = fm3d_sqrt(S11);
     if (s->iter == 0) {
         s->diag[0] = an0 != 0.0 ? an0 : 1.0;
         s->diag[1] = an1 != 0.0 ? an1 : 1.0;
         s->xnorm = fm3d_enorm2(s->diag[0] * s->x[0], s->diag[1] * s->x[1]);
-        s->delta = s->stepbound * s->xnorm;
-        if (s->delta == 0.0) s->delta = s->stepbound;
+        s->delta = 100.0 * s->xnorm;            // stepbound
+        if (s->delta == 0.0) s->delta = 100.0;
     } else {
         s->diag[0] = fmax(s->diag[0], an0);
         s->diag[1] = fmax(s->diag[1], an1);
     }
     // norm of the scaled gradient: max_j |(J^T f)_j| / (|J_j| |f|)
     double gnorm = 0.0;
-    if (s->fnorm != 0.0) {
-        if (an0 != 0.0) gnorm = fmax(gnorm, fabs(g0 * fm3d_rcp(s->fnorm * an0)));
-        if (an1 != 0.0) gnorm = fmax(gnorm, fabs(g1 * fm3d_rcp(s->fnorm * an1)));
+    if (fnorm != 0.0) {
+        if (an0 != 0.0) gnorm = fmax(gnorm, fabs(g0 * fm3d_rcp(fnorm * an0)));
+        if (an1 != 0.0) gnorm = fmax(gnorm, fabs(g1 * fm3d_rcp(fnorm * an1)));
     }
     s->gnorm = gnorm;
-    if (gnorm <= s->gtol) { s->info = 4; return FM3D_LM_CMD_DONE; }
+    if (gnorm <= FM3D_LM_USERTOL) { s->info = 4; return FM3D_LM_CMD_DONE; }
+    fm3d_lm2_cache_jacobian(s);
     return fm3d_lm2_propose(s);
 }
 
 // Consume the squared norm of the trial residual.
 FM3D_HD int fm3d_lm2_after_trial(fm3d_lm2* s, double ff_trial) {
     const double p1 = 0.1, p0001 = 1.0e-4;
-    s->nfev += 1;
-    const double fnorm = s->fnorm, fnorm1 = sqrt(ff_trial);
-    const double iff = fm3d_rcp(fnorm * fnorm);
-    // (fnorm1 / fnorm)^2 without the square root in the chain
-    const double actred = (p1 * fnorm1 < fnorm) ? 1.0 - ff_trial * iff : -1.0;
-    // |J p|^2 = p^T (J^T J) p
-    const double s0 = s->step[0], s1 = s->step[1];
-    const double jp2 = fmax(0.0, s->S00 * s0 * s0 + 2.0 * s->S01 * s0 * s1 + s->S11 * s1 * s1);
-    const double t1sq = jp2 * iff;
-    const double t2sq = s->par * s->pnorm * s->pnorm * iff;      // (sqrt(par) pnorm / fnorm)^2
-    const double prered = t1sq + 2.0 * t2sq;
-    const double dirder = -(t1sq + t2sq);
+    const int nfev = s->nfev + 1;
+    s->nfev = nfev;
+    const double ff = s->ff;
+    // actred = 1 - (fnorm1 / fnorm)^2 unless the trial is more than 10x worse
+    const bool much_worse = p1 * p1 * ff_trial >= ff;          // p1 fnorm1 >= fnorm
+    const double actred = much_worse ? -1.0 : 1.0 - ff_trial * s->iff;
+    const double prered = s->prered, dirder = s->dirder;
     const double ratio = prered != 0.0 ? actred * fm3d_rcp(prered) : 0.0;
+    const double pnorm = s->pnorm;
+    double delta = s->delta, par = s->par;
     if (ratio <= 0.25) {
         double temp;
         if (actred >= 0.0) temp = 0.5;
         else temp = 0.5 * dirder * fm3d_rcp(dirder + 0.55 * actred);
-        if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
-        s->delta = temp * fmin(s->delta, s->pnorm * 10.0);
-        s->par *= fm3d_rcp(temp);
-    } else if (s->par == 0.0 || ratio >= 0.75) {
-        s->delta = s->pnorm / 0.5;
-        s->par *= 0.5;
+        if (much_worse || temp < p1) temp = p1;
+        delta = temp * fmin(delta, pnorm * 10.0);
+        par *= fm3d_rcp(temp);
+    } else if (par == 0.0 || ratio >= 0.75) {
+        delta = pnorm * 2.0;
+        par *= 0.5;
     }
+    s->delta = delta; s->par = par;
     const int accepted = ratio >= p0001;
+    double xnorm = s->xnorm;
     if (accepted) {
         s->x[0] = s->xt[0]; s->x[1] = s->xt[1];
-        s->xnorm = fm3d_enorm2(s->diag[0] * s->x[0], s->diag[1] * s->x[1]);
-        s->fnorm = fnorm1;
+        xnorm = fm3d_enorm2(s->diag[0] * s->xt[0], s->diag[1] * s->xt[1]);
+        s->xnorm = xnorm;
+        s->ff = ff_trial;
+        s->fnorm = fm3d_sqrt(ff_trial);
+        s->iff = fm3d_rcp(ff_trial);
         s->iter++;
     }
     int info = 0;
-    if (fabs(actred) <= s->ftol && prered <= s->ftol && 0.5 * ratio <= 1.0) info = 1;
-    if (s->delta <= s->xtol * s->xnorm) info += 2;
+    if (fabs(actred) <= FM3D_LM_USERTOL && prered <= FM3D_LM_USERTOL && 0.5 * ratio <= 1.0) info = 1;
+    if (delta <= FM3D_LM_USERTOL * xnorm) info += 2;
     if (info != 0) { s->info = info; return FM3D_LM_CMD_DONE; }
-    if (s->nfev >= s->maxfev) info = 5;
+    if (nfev >= s->maxfev) info = 5;
     if (fabs(actred) <= FM3D_DBL_EPS && prered <= FM3D_DBL_EPS && 0.5 * ratio <= 1.0) info = 6;
-    if (s->delta <= FM3D_DBL_EPS * s->xnorm) info = 7;
+    if (delta <= FM3D_DBL_EPS * xnorm) info = 7;
     if (s->gnorm <= FM3D_DBL_EPS) info = 8;
     if (info != 0) { s->info = info; return FM3D_LM_CMD_DONE; }
     if (!accepted) return fm3d_lm2_propose(s);

@@ -492,7 +492,7 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
                 S->normal[1] = cos(lm.x[1]) * sin(lm.x[0]);
                 S->normal[2] = sin(lm.x[1]);
                 if (A.nfev) A.nfev[(size_t)f * (levels + 1) + lvl] = lm.nfev;
-                if (A.cost) A.cost[f] = lm.fnorm * lm.fnorm;
+                if (A.cost) A.cost[f] = lm.ff;
             }
             if (tid == 0 && !alive && A.mode == 0 && A.nfev) A.nfev[(size_t)f * (levels + 1) + lvl] = S->lm.nfev;
             __syncthreads();

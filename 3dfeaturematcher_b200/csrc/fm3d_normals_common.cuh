@@ -48,6 +48,7 @@ struct NormalsArgs {
     int win_bytes;                      // fast kernel: bytes of the window buffer
     int win_tma[FM3D_MAX_LEVELS];       // fast kernel: level window loaded by one TMA tile
     int fuse_trials;                    // fast kernel: evaluate the Jacobian with the first trial
+    int memo_trials;                    // fast kernel: answer coefficient-identical trials without a pass
     float2* rays_g;
     float* i1_g;
     CUtensorMap tmap[FM3D_MAX_LEVELS];

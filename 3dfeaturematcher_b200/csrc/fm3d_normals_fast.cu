@@ -73,6 +73,11 @@ struct FastShared {
     int where;          // AT_*
     int alive;
     int first_row, last_row;
+    float hbase[9];     // value coefficients (FastPass::h[0]) of the current LM iterate ...
+    double s0_base;     // ... and the residual sum the pass at the iterate returned
+    int base_valid;
+    int trial_is_first; // the trial being evaluated opens an LM iteration
+    int fuse_hint;      // the last first trial of an LM iteration was accepted (initially 1)
     unsigned long long stats[16];
 };
 
@@ -91,7 +96,7 @@ struct LevelConst {
 __device__ __forceinline__ float rcp_nr(float a) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-    return fmaf(r, fmaf(-a, r, 1.0f), r);
+    return fmaf(r, fmaf(-a, r, 1.0f), r);   // explicit fmas: identical in every instantiation
 }
 __device__ __forceinline__ float u2f(unsigned b) {  // I2FP (the compiler would pick the slow I2F.U16)
     float f;
@@ -112,20 +117,22 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
     const float B0 = fmaf(P.h[0][3], dv.x, fmaf(P.h[0][4], dv.y, P.h[0][5]));
     const float C0 = fmaf(P.h[0][6], dv.x, fmaf(P.h[0][7], dv.y, P.h[0][8]));
     const float iz = rcp_nr(C0);
-    const float dx = A0 * iz, dy = B0 * iz;
-    const float x = L.xc + dx, y = L.yc + dy;
+    // every operation of the value path is an explicit fma / non-contractible intrinsic: the value-only
+    // and the value+Jacobian instantiation must return bit-identical residuals (a trial is compared
+    // with an iterate that was evaluated by the other one)
+    const float x = fmaf(A0, iz, L.xc), y = fmaf(B0, iz, L.yc);
     // cv::projectPoints: distortion polynomial and K (x scale), singlecameratriangulator.cpp:602,627
-    const float r2 = fmaf(x, x, y * y);
+    const float r2 = fmaf(x, x, __fmul_rn(y, y));
     const float cd = fmaf(r2, fmaf(r2, fmaf(r2, L.k3, L.k2), L.k1), 1.0f);
-    const float x2 = x + x, y2 = y + y;
-    const float xy2 = x2 * y;
+    const float x2 = __fadd_rn(x, x), y2 = __fadd_rn(y, y);
+    const float xy2 = __fmul_rn(x2, y);
     const float a2 = fmaf(x2, x, r2), a3 = fmaf(y2, y, r2);
-    const float xd = fmaf(x, cd, fmaf(L.p1, xy2, L.p2 * a2));
-    const float yd = fmaf(y, cd, fmaf(L.p1, a3, L.p2 * xy2));
+    const float xd = fmaf(x, cd, fmaf(L.p1, xy2, __fmul_rn(L.p2, a2)));
+    const float yd = fmaf(y, cd, fmaf(L.p1, a3, __fmul_rn(L.p2, xy2)));
     const float su = fmaf(xd, L.sfx, L.scx), sv = fmaf(yd, L.sfy, L.scy);
     // floor and fraction without FRND/F2I
     const float tx = __fadd_rd(su, FLOOR_MAGIC), ty = __fadd_rd(sv, FLOOR_MAGIC);
-    const float ax = su - (tx - FLOOR_MAGIC), ay = sv - (ty - FLOOR_MAGIC);
+    const float ax = __fsub_rn(su, __fsub_rn(tx, FLOOR_MAGIC)), ay = __fsub_rn(sv, __fsub_rn(ty, FLOOR_MAGIC));
     float b00, b01, b10, b11;
     if (!SLOW) {
         unsigned a = __float_as_uint(ty) * L.ww + __float_as_uint(tx) - L.coff;
@@ -140,11 +147,11 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
         b10 = u2f(fm3d_at_flat(L.img2, L.w, L.h, L.pitch, x0 + 1, y0));
         b11 = u2f(fm3d_at_flat(L.img2, L.w, L.h, L.pitch, x0 + 1, y0 + 1));
     }
-    const float d0 = b01 - b00, d1 = b11 - b10;
+    const float d0 = __fsub_rn(b01, b00), d1 = __fsub_rn(b11, b10);
     const float c0 = fmaf(ay, d0, b00), c1 = fmaf(ay, d1, b10);
-    const float gx = c1 - c0;
+    const float gx = __fsub_rn(c1, c0);
     const float I2 = fmaf(ax, gx, c0);
-    const float d = I1 - I2;
+    const float d = __fsub_rn(I1, I2);
     acc.s0 = fma((double)d, (double)d, acc.s0);
     if (JAC) {
         const float gy = fmaf(ax, d1 - d0, d0);
@@ -155,6 +162,7 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
         const float Gx = gx * L.sfx, Gy = gy * L.sfy;
         const float Ix = fmaf(Gx, Jxx, Gy * Jxy), Iy = fmaf(Gx, Jxy, Gy * Jyy);   // dI2/d(x,y)
         const float q0 = Ix * iz, q1 = Iy * iz;
+        const float dx = A0 * iz, dy = B0 * iz;
         const float q2 = -fmaf(q0, dx, q1 * dy);
         const float A1 = fmaf(P.h[1][0], dv.x, fmaf(P.h[1][1], dv.y, P.h[1][2]));
         const float B1 = fmaf(P.h[1][3], dv.x, fmaf(P.h[1][4], dv.y, P.h[1][5]));
@@ -547,6 +555,8 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         PP->slow = 0;
                         fm3d_lm2_init(&S->lm, phi, theta, A.eps_lmmin, A.patience);
                         S->where = AT_X_JAC;
+                        S->base_valid = 0;
+                        S->fuse_hint = 1;
                     }
                     publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
                 } else {
@@ -556,6 +566,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         S->lm.nfev = 0;
                         S->lm.eps = 1e-5;
                         S->where = AT_XT_PLAIN;
+                        S->base_valid = 0;
                     }
                     publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
                 }
@@ -620,81 +631,118 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         s[k] = v;
                     }
                     any_flags = __reduce_or_sync(0xffffffffu, any_flags);
-                    int next_kind = PASS_STOP;          // what lane 0 asks the warp to publish
-                    double next_phi = 0.0, next_theta = 0.0;
                     const long long t_r = clock64();
-                    long long t_p = t_r;
-                    if (lane == 0) {
-                        // the LM state works in registers: every access through the shared-memory
-                        // struct would be a 30-cycle load on a single thread's dependent chain
-                        fm3d_lm2 lm = S->lm;
-                        int cmd = -1;   // -1: repeat the pass
-                        {   // executed work (fm3d_get_normals_stats)
-                            const int wh_ = S->where;
-                            const int slot = P.kind == PASS_VALUE ? 0 : (wh_ == AT_X_JAC ? 1 : 2);
-                            S->stats[slot]++;
-                            if (P.slow) S->stats[4]++;
-                            S->stats[P.kind == PASS_VALUE ? 5 : 6] += (unsigned long long)m;
-                        }
-                        if ((any_flags & FLAG_WINDOW) && !(any_flags & 7) && !P.slow) {
-                            PP->slow = 1;               // same pass again, taps from global memory
-                        } else if ((any_flags & 7) || s[0] != s[0]) {
-                            // all bounding-box / NaN tests of an evaluation precede its pixel tests
-                            S->status = ((any_flags & FLAG_NAN) || !(any_flags & 7)) ? FM3D_FEAT_ABORT_NAN
-                                      : (any_flags & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
-                            S->alive = 0;
-                            PP->kind = PASS_STOP;
-                            cmd = 0;
-                        } else if (A.mode != 0) {
-                            A.cost[f] = S->w[0] * S->w[0] * s[0];
-                            PP->kind = PASS_STOP;
-                            cmd = 0;
-                        } else {
-                            const int where = S->where;
-                            bool first_trial = false;   // the next trial opens an LM iteration
-                            if (where == AT_X_JAC) {
-                                if (lm.first && S->w[0] != 1.0) S->npenalty++;
-                                cmd = consume_jacobian(S, lm, s, A.penalty_mode);
-                                first_trial = true;
+                    long long t_lm = 0;
+                    // `memo`: the result in s[0] was not evaluated but taken from the base point: the
+                    // proposed trial point rounds to the same fp32 homography coefficients as the
+                    // current iterate, so the pass would return the iterate's sum bit for bit.  Deep
+                    // in lmfit's tail (steps below 1e-8 rad, tolerances of 30 eps) this is what every
+                    // trial does; those trials are answered here without a pass.
+                    bool memo = false;
+                    bool slow_pass = P.slow != 0;
+                    int pass_kind = P.kind;
+                    for (;;) {
+                        int next_kind = PASS_STOP;          // what lane 0 asks the warp to publish
+                        int take_base = 0;                  // PP->h[0] are the coefficients of the (new) iterate
+                        double next_phi = 0.0, next_theta = 0.0;
+                        const long long t_l0 = clock64();
+                        if (lane == 0) {
+                            fm3d_lm2& lm = S->lm;
+                            if (!memo) {   // executed work (fm3d_get_normals_stats)
+                                const int slot = pass_kind == PASS_VALUE ? 0 : (S->where == AT_X_JAC ? 1 : 2);
+                                S->stats[slot]++;
+                                if (slow_pass) S->stats[4]++;
+                                S->stats[pass_kind == PASS_VALUE ? 5 : 6] += (unsigned long long)m;
                             } else {
-                                if (S->w[0] != 1.0) S->npenalty++;
-                                cmd = fm3d_lm2_after_trial(&lm, S->w[0] * S->w[0] * s[0]);
-                                // accepted (x == xt now) and the Jacobian came with the trial
-                                if (cmd == FM3D_LM_CMD_JAC && where == AT_XT_FUSED) {
-                                    S->stats[3]++;
+                                S->stats[13]++;
+                            }
+                            const unsigned fl = memo ? 0u : any_flags;
+                            if ((fl & FLAG_WINDOW) && !(fl & 7) && !slow_pass) {
+                                PP->slow = 1;               // same pass again, taps from global memory
+                                next_kind = -1;
+                            } else if ((fl & 7) || s[0] != s[0]) {
+                                // all bounding-box / NaN tests of an evaluation precede its pixel tests
+                                S->status = ((fl & FLAG_NAN) || !(fl & 7)) ? FM3D_FEAT_ABORT_NAN
+                                          : (fl & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
+                                S->alive = 0;
+                                PP->kind = PASS_STOP;
+                            } else if (A.mode != 0) {
+                                A.cost[f] = S->w[0] * S->w[0] * s[0];
+                                PP->kind = PASS_STOP;
+                            } else {
+                                const int where = S->where;
+                                bool first_trial = false;   // the next trial opens an LM iteration
+                                int cmd;
+                                if (where == AT_X_JAC) {
+                                    if (lm.first && S->w[0] != 1.0) S->npenalty++;
                                     cmd = consume_jacobian(S, lm, s, A.penalty_mode);
                                     first_trial = true;
+                                    S->s0_base = s[0];      // sum and coefficients of the iterate
+                                    take_base = 1;
+                                } else {
+                                    if (S->w[0] != 1.0) S->npenalty++;
+                                    const int iter_before = lm.iter;
+                                    cmd = fm3d_lm2_after_trial(&lm, S->w[0] * S->w[0] * s[0]);
+                                    const bool accepted = lm.iter != iter_before;
+                                    if (S->trial_is_first) S->fuse_hint = accepted ? 1 : 0;
+                                    if (!memo && accepted) {   // new iterate
+                                        S->s0_base = s[0];
+                                        take_base = 1;
+                                    }
+                                    // accepted (x == xt now) and the Jacobian came with the trial
+                                    if (cmd == FM3D_LM_CMD_JAC && where == AT_XT_FUSED) {
+                                        S->stats[3]++;
+                                        cmd = consume_jacobian(S, lm, s, A.penalty_mode);
+                                        first_trial = true;
+                                    }
+                                }
+                                if (cmd == FM3D_LM_CMD_JAC) {
+                                    S->where = AT_X_JAC;
+                                    next_kind = PASS_JAC; next_phi = lm.x[0]; next_theta = lm.x[1];
+                                } else if (cmd == FM3D_LM_CMD_TRIAL) {
+                                    // first trial of an iteration: evaluate its Jacobian along with it;
+                                    // re-trials after a rejection are value-only
+                                    const bool fuse = first_trial && (A.fuse_trials == 1 || (A.fuse_trials == 2 && S->fuse_hint));
+                                    S->trial_is_first = first_trial ? 1 : 0;
+                                    S->where = fuse ? AT_XT_FUSED : AT_XT_PLAIN;
+                                    next_kind = fuse ? PASS_JAC : PASS_VALUE; next_phi = lm.xt[0]; next_theta = lm.xt[1];
+                                } else {
+                                    PP->kind = PASS_STOP;   // FM3D_LM_CMD_DONE
                                 }
                             }
-                            t_p = clock64();
-                            if (cmd == FM3D_LM_CMD_JAC) {
-                                S->where = AT_X_JAC;
-                                next_kind = PASS_JAC; next_phi = lm.x[0]; next_theta = lm.x[1];
-                            } else if (cmd == FM3D_LM_CMD_TRIAL) {
-                                // first trial of an iteration: evaluate its Jacobian along with it;
-                                // re-trials after a rejection are value-only
-                                const bool fuse = first_trial && A.fuse_trials;
-                                S->where = fuse ? AT_XT_FUSED : AT_XT_PLAIN;
-                                next_kind = fuse ? PASS_JAC : PASS_VALUE; next_phi = lm.xt[0]; next_theta = lm.xt[1];
-                            } else {
-                                PP->kind = PASS_STOP;   // FM3D_LM_CMD_DONE
-                            }
-                            S->lm = lm;
                         }
-                    }
-                    next_kind = __shfl_sync(0xffffffffu, next_kind, 0);
-                    if (next_kind != PASS_STOP) {
+                        t_lm += clock64() - t_l0;
+                        next_kind = __shfl_sync(0xffffffffu, next_kind, 0);
+                        if (next_kind <= PASS_STOP) break;      // stop, or repeat the same pass (-1)
+                        take_base = __shfl_sync(0xffffffffu, take_base, 0);
                         next_phi = __shfl_sync(0xffffffffu, next_phi, 0);
                         next_theta = __shfl_sync(0xffffffffu, next_theta, 0);
+                        // remember the coefficients of the iterate before they are overwritten
+                        if (take_base) {
+                            if (lane < 9) S->hbase[lane] = PP->h[0][lane];
+                            if (lane == 0) S->base_valid = 1;
+                        }
+                        __syncwarp();
                         publish_pass(PP, S, cam, next_phi, next_theta, next_kind, A.penalty_mode, S->lm.eps, lane);
+                        __syncwarp();
+                        if (PP->kind == PASS_STOP) break;       // NaN normal
+                        // would this pass return the iterate's sum?  (trial points only)
+                        bool same = S->where != AT_X_JAC && S->base_valid != 0 && A.memo_trials;
+                        if (lane < 9) same = same && (PP->h[0][lane] == S->hbase[lane]);
+                        same = __all_sync(0xffffffffu, same);
+                        if (!same) break;                       // run the pass
+                        memo = true;
+                        s[0] = S->s0_base;
+                        if (lane == 0) { S->where = AT_XT_PLAIN; }
+                        __syncwarp();
                     }
                     if (lane == 0) {
                         const long long t_c = clock64();
                         S->stats[8] += (unsigned long long)(t_b0 - t_a);   // thread 0: pixel work of the pass
                         S->stats[9] += (unsigned long long)(t_b - t_b0);   // thread 0: wait at the barrier
                         S->stats[10] += (unsigned long long)(t_c - t_b);   // reduction + LM + publish
-                        S->stats[11] += (unsigned long long)(t_p - t_r);   //   of which LM algebra
-                        S->stats[12] += (unsigned long long)(t_c - t_p);   //   of which sincos + homographies
+                        S->stats[11] += (unsigned long long)t_lm;          //   of which LM algebra
+                        S->stats[12] += (unsigned long long)(t_c - t_r - t_lm);   //   of which sincos + homographies
                     }
                 }
                 __syncthreads();
@@ -708,7 +756,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     S->normal[0] = cos(lm.x[1]) * cos(lm.x[0]);
                     S->normal[1] = cos(lm.x[1]) * sin(lm.x[0]);
                     S->normal[2] = sin(lm.x[1]);
-                    if (A.cost) A.cost[f] = lm.fnorm * lm.fnorm;
+                    if (A.cost) A.cost[f] = lm.ff;
                 }
                 if (A.nfev) A.nfev[(size_t)f * (levels + 1) + lvl] = lm.nfev;
             }
@@ -753,6 +801,7 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     A.patience = ctx->opt_lm_patience;
     A.use_tma = ctx->opt_normals_tma;
     A.fuse_trials = ctx->opt_normals_fuse;
+    A.memo_trials = ctx->opt_normals_memo;
     A.mcap = (disc_capacity(A.r) + 31) & ~31;
     int nt = ctx->opt_normals_threads;
     nt = nt < 64 ? 64 : (nt > FAST_NT ? FAST_NT : (nt & ~31));

@@ -51,6 +51,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout)
+# must not share it: file descriptor 1 is pointed at stderr for the whole run and the JSON line
+# goes to a private duplicate of the original stdout.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def make_workload(n_ranks, rank):
     """Global problem: one stereo pair with n_ranks*N_KP query keypoints; returns the global
     arrays (every rank generates the same ones; rank 0's copy is the one that gets broadcast)."""
@@ -172,7 +191,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": v, "unit": "features/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(n_ranks):
@@ -452,7 +471,7 @@ def run_gpu_arm(args):
                 "cpu_baseline_features_per_s": None if cpu_alt is None else cpu_alt["features_per_s"]},
             "wall_s_device_arm": wall_dev, "gpu": info["name"],
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -466,6 +485,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fm3d", choices=["fm3d", "reference"])
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -88,6 +88,13 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *                       CUDA-core fp32 path
  *   "lm_patience"       lm_control.patience / maxcall (default 100 -> 300 evaluations/level)
  *   "normals_threads"   threads per CTA of the normal optimiser (default 512)
+ *   "normals_fast"      1 (default): fm3d_normals_fast.cu (fp32 offset-form geometry, analytic
+ *                       Jacobian); 0: the evaluation-by-evaluation fp64 kernel; 2: also route
+ *                       fm3d_evaluate_normals through the fast kernel
+ *   "normals_fuse"      fast kernel: evaluate the first trial of an LM iteration with its Jacobian (1)
+ *   "normals_memo"      fast kernel: do not re-evaluate trial points whose fp32 coefficients equal
+ *                       the iterate's (1)
+ *   "normals_tma"       stage the image window with a TMA tensor-tile load (1)
  * Returns FM3D_ERR_INVALID_ARG for an unknown key. */
 int fm3d_set_option(fm3d_ctx* ctx, const char* key, double value);
 int fm3d_get_option(fm3d_ctx* ctx, const char* key, double* value);
@@ -227,7 +234,9 @@ int fm3d_optimize_normals_dev(fm3d_ctx* ctx, const double* xyz, int n, int pixel
  *   out[5] pixel evaluations of value-only passes   out[6] of value+Jacobian passes
  *   out[7] features processed
  *   out[8..10] SM cycles of thread 0 in: the pixel loop of the passes / waiting for the slowest
- *   warp / the serial reduction + LM step + homography set-up;  out[11..15] reserved
+ *   warp / the serial reduction + LM step + homography set-up;  out[11], out[12] split of out[10]
+ *   into LM algebra and homography set-up;  out[13] trial points answered without a pass (their
+ *   fp32 homography coefficients equal the iterate's);  out[14..15] reserved
  * nfev (above) counts what lmfit would have evaluated; these count what the GPU did. */
 int fm3d_get_normals_stats(fm3d_ctx* ctx, int64_t out[16]);
 

@@ -39,7 +39,7 @@ else:
     cam = case["scene"].cam
     setup_ctx(ctx, case, pyr)
     xyz = case["X"]
-    for pen in (2, 0):
+    for pen in (1, 0):
         o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, pyr, xyz[:64], r, 1e-10, penalty_mode=pen, threads=16)
         for fast, fuse in ((0, 1), (1, 1), (1, 0)):
             run(ctx, xyz, r, pen, fast, fuse)
