@@ -210,17 +210,36 @@ __device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const Leve
     return flags;
 }
 
-template <bool JAC, bool SLOW, typename RayPtr>
-__device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& L, RayPtr rays, const float* i1, int m,
-                                           int tid, int NT, Acc& acc) {
+template <bool JAC, bool SLOW, bool PREFETCH>
+__device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& L, const float2* __restrict__ rays,
+                                           const float* __restrict__ i1, int m, int tid, int NT, Acc& acc) {
     int idx = tid;
-    for (; idx + NT < m; idx += 2 * NT) {
-        const float2 dva = rays[idx], dvb = rays[idx + NT];
-        const float Ia = i1[idx], Ib = i1[idx + NT];
-        eval_pixel_fast<JAC, SLOW>(P, L, dva, Ia, acc);
-        eval_pixel_fast<JAC, SLOW>(P, L, dvb, Ib, acc);
+    if (PREFETCH) {
+        // rays / image-1 samples stream from the L2-resident scratch: the loads of the next two
+        // pixels are issued before the current two are evaluated
+        float2 dva = make_float2(0.f, 0.f), dvb = dva;
+        float Ia = 0.f, Ib = 0.f;
+        if (idx < m) { dva = rays[idx]; Ia = i1[idx]; }
+        if (idx + NT < m) { dvb = rays[idx + NT]; Ib = i1[idx + NT]; }
+        for (; idx + NT < m; idx += 2 * NT) {
+            const float2 ca = dva, cb = dvb;
+            const float cIa = Ia, cIb = Ib;
+            const int nx = idx + 2 * NT;
+            if (nx < m) { dva = rays[nx]; Ia = i1[nx]; }
+            if (nx + NT < m) { dvb = rays[nx + NT]; Ib = i1[nx + NT]; }
+            eval_pixel_fast<JAC, SLOW>(P, L, ca, cIa, acc);
+            eval_pixel_fast<JAC, SLOW>(P, L, cb, cIb, acc);
+        }
+        if (idx < m) eval_pixel_fast<JAC, SLOW>(P, L, dva, Ia, acc);
+    } else {
+        for (; idx + NT < m; idx += 2 * NT) {
+            const float2 dva = rays[idx], dvb = rays[idx + NT];
+            const float Ia = i1[idx], Ib = i1[idx + NT];
+            eval_pixel_fast<JAC, SLOW>(P, L, dva, Ia, acc);
+            eval_pixel_fast<JAC, SLOW>(P, L, dvb, Ib, acc);
+        }
+        if (idx < m) eval_pixel_fast<JAC, SLOW>(P, L, rays[idx], i1[idx], acc);
     }
-    if (idx < m) eval_pixel_fast<JAC, SLOW>(P, L, rays[idx], i1[idx], acc);
 }
 
 // Warp 0, all lanes, uniform arguments: evaluation point (phi, theta) -> homography coefficients
@@ -312,22 +331,53 @@ __device__ __forceinline__ int consume_jacobian(FastShared* S, fm3d_lm2& lm, con
     return fm3d_lm2_after_jacobian(&lm, ff, S00, S01, S11, g0, g1);
 }
 
-template <bool RAYS_SMEM>
+// A CTA runs `groups` independent feature pipelines side by side (1 or 2): each group of warps has
+// its own window, LM state, queue slot and named barrier, so that the pixel passes of one feature
+// fill the SM while the other feature is in its serial LM step.
+__device__ __forceinline__ void gsync(int groups, int g, int nt) {
+    if (groups == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nt) : "memory");
+}
+__device__ __forceinline__ int gsync_and(int groups, int g, int nt, int pred) {
+    if (groups == 1) return __syncthreads_and(pred);
+    int out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "bar.red.and.pred q, %2, %3, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(out) : "r"(pred), "r"(g + 1), "r"(nt) : "memory");
+    return out;
+}
+
+// RAYS_SMEM / I1_SMEM: where the per-pixel ray offsets (8 B) and image-1 samples (4 B) of the
+// feature live: shared memory, or a per-group scratch in global memory that stays L2-resident
+// (one CTA streams it once per pass: 12 B x 12 853 pixels at r = 64).
+template <bool RAYS_SMEM, bool I1_SMEM>
 __global__ void __launch_bounds__(FAST_NT, 1)
 normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    const int groups = A.groups;
+    const int NT = blockDim.x / groups;
+    const int g = threadIdx.x / NT;
+    const int tid = threadIdx.x - g * NT;
+    uint8_t* smem = smem_all + (size_t)g * A.group_smem;
     uint8_t* win = smem;
     float2* rays;
     float* i1;
-    uint8_t* tail;
+    uint8_t* tail = smem + A.win_bytes;
+    const size_t slot = (size_t)blockIdx.x * groups + g;
     if (RAYS_SMEM) {
-        rays = reinterpret_cast<float2*>(smem + A.win_bytes);
-        i1 = reinterpret_cast<float*>(rays + A.mcap);
-        tail = reinterpret_cast<uint8_t*>(i1 + A.mcap);
+        rays = reinterpret_cast<float2*>(tail);
+        tail += sizeof(float2) * (size_t)A.mcap;
     } else {
-        rays = A.rays_g + (size_t)blockIdx.x * A.mcap;
-        i1 = A.i1_g + (size_t)blockIdx.x * A.mcap;
-        tail = smem + A.win_bytes;
+        rays = A.rays_g + slot * A.mcap;
+    }
+    if (I1_SMEM) {
+        i1 = reinterpret_cast<float*>(tail);
+        tail += sizeof(float) * (size_t)A.mcap;
+    } else {
+        i1 = A.i1_g + slot * A.mcap;
     }
     tail = reinterpret_cast<uint8_t*>(((uintptr_t)tail + 15) & ~(uintptr_t)15);
     RowTable* rows = reinterpret_cast<RowTable*>(tail);
@@ -342,7 +392,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
     tail += (sizeof(FastPass) + 15) & ~(size_t)15;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
 
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
+    const int lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
     const fm3d_cam& cam = A.cam;
     const int r = A.r, W = A.pyr.lv[0].w, H = A.pyr.lv[0].h, levels = A.pyr.levels;
     const float cmax = (float)(int)(2 * cam.zmax);  // int cMax = 2*z_threshold_max_ (:648)
@@ -357,7 +407,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
     for (;;) {
         // ------------------------------------------------------------ fetch a feature
         if (tid == 0) S->feature = atomicAdd(A.work_counter, 1);
-        __syncthreads();
+        gsync(groups, g, NT);
         const int f = S->feature;
         if (f >= A.n) break;
         const double Px = A.xyz[3 * f], Py = A.xyz[3 * f + 1], Pz = A.xyz[3 * f + 2];
@@ -393,7 +443,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             rows->ilo[jr] = (short)lo;
             rows->jrow[jr] = (short)j;
         }
-        __syncthreads();
+        gsync(groups, g, NT);
         if (tid == 0) {
             int acc = 0, first = -1, last = -1;
             rows->start[0] = 0;
@@ -426,7 +476,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             const double iz = Z2 != 0.0 ? 1.0 / Z2 : 1.0;
             S->xc = X2 * iz; S->yc = Y2 * iz;
         }
-        __syncthreads();
+        gsync(groups, g, NT);
         const int m = S->m;
         if (A.m_out && tid == 0) A.m_out[f] = m;
         const double vcx = S->vc[0], vcy = S->vc[1];
@@ -482,7 +532,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 S->wx0 = (((int)wxc - (int)L.ww / 2 + 8) >> 4) << 4;
                 S->wy0 = (int)wyc - wh / 2;
             }
-            __syncthreads();  // also: everybody is done with the previous level's window
+            gsync(groups, g, NT);  // also: everybody is done with the previous level's window
             L.wx0 = S->wx0; L.wy0 = S->wy0;
             bool staged = false;
             if (L.ww > 0 && wh > 0) {
@@ -497,7 +547,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     for (int spin = 0; spin < (1 << 22); spin++) {
                         if (mbar_try_wait(bar, parity)) { ok = true; break; }
                     }
-                    staged = __syncthreads_and(ok ? 1 : 0) != 0;
+                    staged = gsync_and(groups, g, NT, ok ? 1 : 0) != 0;
                     if (tid == 0) {
                         S->tma_phase ^= 1;
                         if (!staged) atomicExch(A.error_flag, 1);
@@ -571,7 +621,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
                 }
             }
-            __syncthreads();
+            gsync(groups, g, NT);
 
             // -------------------------------------------------------- pass loop (two barriers per pass)
             for (;;) {
@@ -599,11 +649,11 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 Acc acc;
                 acc.s0 = 0.0; acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.0f;
                 if (P.kind == PASS_JAC) {
-                    if (!P.slow) run_pixels<true, false>(P, L, rays, i1, m, tid, NT, acc);
-                    else run_pixels<true, true>(P, L, rays, i1, m, tid, NT, acc);
+                    if (!P.slow) run_pixels<true, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
+                    else run_pixels<true, true, false>(P, L, rays, i1, m, tid, NT, acc);
                 } else {
-                    if (!P.slow) run_pixels<false, false>(P, L, rays, i1, m, tid, NT, acc);
-                    else run_pixels<false, true>(P, L, rays, i1, m, tid, NT, acc);
+                    if (!P.slow) run_pixels<false, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
+                    else run_pixels<false, true, false>(P, L, rays, i1, m, tid, NT, acc);
                 }
                 double a0 = warp_sum(acc.s0), a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
                 if (P.kind == PASS_JAC) {
@@ -617,7 +667,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     wflags[wid] = flags;
                 }
                 const long long t_b0 = clock64();
-                __syncthreads();
+                gsync(groups, g, NT);
                 const long long t_b = clock64();
 
                 if (wid == 0) {
@@ -745,7 +795,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         S->stats[12] += (unsigned long long)(t_c - t_r - t_lm);   //   of which sincos + homographies
                     }
                 }
-                __syncthreads();
+                gsync(groups, g, NT);
             }
             alive = S->alive != 0;
 
@@ -760,7 +810,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 }
                 if (A.nfev) A.nfev[(size_t)f * (levels + 1) + lvl] = lm.nfev;
             }
-            __syncthreads();
+            gsync(groups, g, NT);
         }
 
         // ------------------------------------------------------------ epilogue
@@ -784,7 +834,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 A.cost[f] = __longlong_as_double(0x7ff8000000000000LL);
             }
         }
-        __syncthreads();
+        gsync(groups, g, NT);
     }
 }
 
@@ -804,14 +854,12 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     A.memo_trials = ctx->opt_normals_memo;
     A.mcap = (disc_capacity(A.r) + 31) & ~31;
     int nt = ctx->opt_normals_threads;
-    nt = nt < 64 ? 64 : (nt > FAST_NT ? FAST_NT : (nt & ~31));
+    nt = nt < 128 ? 128 : (nt > FAST_NT ? FAST_NT : (nt & ~63));
     const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
-    const size_t per_px = sizeof(float2) + sizeof(float);
     const size_t tail = fast_tail_bytes() + 128;
 
     // window per level: the warp of the disc is close to a similarity, 1.3x the scaled radius
-    // plus margins; if the rays do not fit beside it they live in global memory and the window
-    // may take (almost) all of shared memory
+    // plus margins
     auto plan_windows = [&](size_t budget) -> size_t {
         size_t win_bytes = 0;
         for (int l = 0; l <= A.pyr.levels; l++) {
@@ -825,10 +873,37 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         }
         return (win_bytes + 127) & ~(size_t)127;
     };
-    size_t win_bytes = plan_windows(64 << 10);
-    bool rays_smem = win_bytes + per_px * (size_t)A.mcap + tail <= smem_max;
-    if (!rays_smem) win_bytes = plan_windows(smem_max - tail - 1024);
+    // Layouts, in order of preference.  Two groups per CTA (the passes of one feature hide the
+    // serial LM step of the other) need the rays in global memory (L2-resident per-group scratch);
+    // one group keeps everything in shared memory when it fits.
+    struct Layout { int groups; bool rays_smem, i1_smem; };
+    const Layout two_a = {2, false, true}, two_b = {2, false, false}, one_a = {1, true, true}, one_b = {1, false, false};
+    const Layout four = {4, false, false};
+    Layout order[6];
+    int n_order = 0;
+    const int sms = ctx->prop.multiProcessorCount;
+    if (ctx->opt_normals_groups == 4 || (ctx->opt_normals_groups == 0 && A.n >= 8 * sms)) order[n_order++] = four;
+    const int want = ctx->opt_normals_groups;   // 0: automatic
+    const bool prefer_two = want == 2 || (want == 0 && A.n > ctx->prop.multiProcessorCount);
+    if (prefer_two) { order[n_order++] = two_a; order[n_order++] = two_b; }
+    order[n_order++] = one_a;
+    if (!prefer_two && want != 1) { order[n_order++] = two_a; order[n_order++] = two_b; }
+    order[n_order++] = one_b;
+    Layout lay = one_b;
+    size_t win_bytes = 0, group_smem = 0;
+    bool found = false;
+    for (int k = 0; k < n_order && !found; k++) {
+        const Layout c = order[k];
+        const bool last = (k == n_order - 1);
+        win_bytes = plan_windows(last ? smem_max - tail - 1024 : (size_t)64 << 10);
+        group_smem = (win_bytes + (c.rays_smem ? sizeof(float2) * (size_t)A.mcap : 0) +
+                      (c.i1_smem ? sizeof(float) * (size_t)A.mcap : 0) + tail + 127) & ~(size_t)127;
+        if (group_smem * c.groups <= smem_max) { lay = c; found = true; }
+    }
+    if (!found) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "normals kernel does not fit in shared memory");
     A.win_bytes = (int)win_bytes;
+    A.groups = lay.groups;
+    A.group_smem = (int)group_smem;
     for (int l = 0; l <= A.pyr.levels; l++) {
         if (A.use_tma && A.win_tma[l]) {
             const fm3d_level& lv = A.pyr.lv[l];
@@ -837,7 +912,7 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
                 return rc;
         }
     }
-    const size_t smem = win_bytes + (rays_smem ? per_px * (size_t)A.mcap : 0) + tail;
+    const size_t smem = group_smem * lay.groups;
 
     auto launch = [&](auto kernel) -> int {
         FM3D_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -845,8 +920,9 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         FM3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nt, smem));
         if (occ < 1) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "normals kernel does not fit (smem %zu)", smem);
         int grid = ctx->prop.multiProcessorCount * occ;
-        if (grid > A.n) grid = A.n;
-        int* ctrl = nullptr;  // [0] work counter, [1] error flag
+        const int need = (A.n + lay.groups - 1) / lay.groups;
+        if (grid > need) grid = need;
+        int* ctrl = nullptr;  // [0] work counter, [1] error flag, [16..] counters
         if (int rc = fm3d_scratch(ctx, 1, 256, (void**)&ctrl)) return rc;
         ctx->n_copy++;
         FM3D_CUDA(ctx, cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
@@ -854,17 +930,20 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         A.error_flag = ctrl + 1;
         A.stats = reinterpret_cast<unsigned long long*>(ctrl + 16);
         A.rays_g = nullptr; A.i1_g = nullptr;
-        if (!rays_smem) {
-            char* g = nullptr;
-            if (int rc = fm3d_scratch(ctx, 2, per_px * (size_t)A.mcap * grid, (void**)&g)) return rc;
-            A.rays_g = (float2*)g;
-            A.i1_g = (float*)(g + sizeof(float2) * (size_t)A.mcap * grid);
+        if (!lay.rays_smem || !lay.i1_smem) {
+            const size_t slots = (size_t)grid * lay.groups;
+            char* gm = nullptr;
+            if (int rc = fm3d_scratch(ctx, 2, (sizeof(float2) + sizeof(float)) * (size_t)A.mcap * slots, (void**)&gm)) return rc;
+            A.rays_g = (float2*)gm;
+            A.i1_g = (float*)(gm + sizeof(float2) * (size_t)A.mcap * slots);
         }
         kernel<<<grid, nt, smem, ctx->stream>>>(A);
         FM3D_LAUNCH_CHECK(ctx);
         return FM3D_OK;
     };
-    return rays_smem ? launch(normals_fast_kernel<true>) : launch(normals_fast_kernel<false>);
+    if (lay.rays_smem) return launch(normals_fast_kernel<true, true>);
+    if (lay.i1_smem) return launch(normals_fast_kernel<false, true>);
+    return launch(normals_fast_kernel<false, false>);
 }
 
 }  // namespace fm3d_normals

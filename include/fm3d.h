@@ -94,6 +94,8 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *   "normals_fuse"      fast kernel: evaluate the first trial of an LM iteration with its Jacobian (1)
  *   "normals_memo"      fast kernel: do not re-evaluate trial points whose fp32 coefficients equal
  *                       the iterate's (1)
+ *   "normals_groups"    fast kernel: independent feature pipelines per CTA: 1, 2, or 0 (default:
+ *                       2 when there are more features than SMs and the layout fits)
  *   "normals_tma"       stage the image window with a TMA tensor-tile load (1)
  * Returns FM3D_ERR_INVALID_ARG for an unknown key. */
 int fm3d_set_option(fm3d_ctx* ctx, const char* key, double value);

@@ -169,13 +169,17 @@ def test_match_nndr_and_mutual(ctx, hamming):
 
 
 # ------------------------------------------------------------------ normals (K5-K7)
-@pytest.fixture(params=["fast", "faithful"])
+@pytest.fixture(params=["fast-1group", "fast-2groups", "faithful"])
 def normals_kernel(request, ctx):
-    """Both implementations of the plane-normal search: fm3d_normals_fast.cu (default: fp32 offset
-    geometry, analytic Jacobian) and fm3d_normals.cu (fp64, evaluation by evaluation)."""
-    ctx.set_option("normals_fast", 1 if request.param == "fast" else 0)
+    """The implementations of the plane-normal search: fm3d_normals_fast.cu (default: fp32 offset
+    geometry, analytic Jacobian) with one feature per CTA (rays in shared memory) or two feature
+    pipelines per CTA (rays streamed from an L2-resident scratch), and fm3d_normals.cu (fp64,
+    evaluation by evaluation)."""
+    ctx.set_option("normals_fast", 0 if request.param == "faithful" else 1)
+    ctx.set_option("normals_groups", 2 if request.param == "fast-2groups" else 1)
     yield request.param
     ctx.set_option("normals_fast", 1)
+    ctx.set_option("normals_groups", 0)
 
 
 @pytest.mark.parametrize("level", [0, 1, 2])
