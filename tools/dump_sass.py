@@ -1,0 +1,69 @@
+"""Regenerates profiles/sass/*.txt from the built objects (cuobjdump -sass): the Blackwell-native
+instructions of the matcher (tcgen05 / TMEM / bulk copy) and the hot loops of the normal search."""
+import os, re, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "3dfeaturematcher_b200", "csrc", "_obj")
+OUT = os.path.join(ROOT, "profiles", "sass")
+os.makedirs(OUT, exist_ok=True)
+
+
+def sass(obj, fun=None):
+    cmd = ["cuobjdump", "-sass"] + (["-fun", fun] if fun else []) + [os.path.join(OBJ, obj)]
+    txt = subprocess.run(cmd, capture_output=True, text=True).stdout
+    lines = [re.sub(r"/\* 0x[0-9a-f]+ \*/", "", l).rstrip() for l in txt.splitlines()]
+    return [l for l in lines if l.strip() and not re.match(r"^\s*/\* 0x", l)]
+
+
+def functions(obj):
+    txt = subprocess.run(["cuobjdump", "-sass", os.path.join(OBJ, obj)], capture_output=True, text=True).stdout
+    return re.findall(r"Function : (\S+)", txt)
+
+
+# ---- matcher
+m = sass("fm3d_match.o")
+pat = re.compile(r"UTC[A-Z]*MMA|LDTM|UBLKCP|UTCATOMSWS|UTCBAR|SYNCS\.ARRIVE|POPC")
+with open(os.path.join(OUT, "r01_match_kernels.txt"), "w") as f:
+    f.write("# cuobjdump -sass fm3d_match.o (sm_100a).  tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, cp.async.bulk -> UBLKCP,\n"
+            "# tcgen05.alloc/dealloc -> UTCATOMSWS, tcgen05.commit -> UTCBAR, mbarrier -> SYNCS; Hamming path: POPC.\n")
+    counts = {}
+    for l in m:
+        for k in pat.findall(l):
+            counts[k] = counts.get(k, 0) + 1
+    f.write("# counts: " + ", ".join(f"{k} x{v}" for k, v in sorted(counts.items())) + "\n")
+    for l in m:
+        if re.search(r"UTC[A-Z]*MMA|LDTM|UBLKCP|UTCATOMSWS|UTCBAR", l):
+            f.write(l[:140] + "\n")
+
+# ---- normal search: the value+Jacobian loop of the layout the bench runs (rays streamed from L2)
+for fn in functions("fm3d_normals_fast.o"):
+    tag = "rays_smem" if "ILb1ELb1E" in fn else ("rays_l2_i1_smem" if "ILb0ELb1E" in fn else "rays_l2")
+    s = sass("fm3d_normals_fast.o", fn)
+    # loops: backward branches; pick the ones that contain LDS.U8 (window taps)
+    addr = {}
+    for i, l in enumerate(s):
+        mm = re.match(r"\s*/\*([0-9a-f]+)\*/", l)
+        if mm:
+            addr[int(mm.group(1), 16)] = i
+    loops = []
+    for i, l in enumerate(s):
+        mm = re.search(r"BRA (0x[0-9a-f]+)", l)
+        a = re.match(r"\s*/\*([0-9a-f]+)\*/", l)
+        if mm and a and int(mm.group(1), 16) < int(a.group(1), 16) and int(mm.group(1), 16) in addr:
+            j = addr[int(mm.group(1), 16)]
+            body = s[j:i + 1]
+            if sum("LDS.U8" in b for b in body) >= 8 and len(body) < 400:
+                loops.append((j, i, body))
+    with open(os.path.join(OUT, f"r01_normals_fast_kernel_{tag}.txt"), "w") as f:
+        f.write(f"# cuobjdump -sass -fun {fn}\n# TMA window staging: " +
+                ", ".join(sorted({k for l in s for k in re.findall(r"UTMALDG\.\w+|SYNCS\.[A-Z0-9.]+", l)})) + "\n")
+        for (j, i, body) in loops:
+            ops = {}
+            for b in body:
+                op = re.sub(r"^\s*/\*[0-9a-f]+\*/\s*(@!?U?P\d+\s+)?", "", b).split()[0].split(".")[0]
+                ops[op] = ops.get(op, 0) + 1
+            kind = "value+Jacobian" if ops.get("FFMA", 0) > 90 else "value-only"
+            f.write(f"\n# ---- pixel loop ({kind}, 2 pixels per iteration): {len(body)} instructions; "
+                    + ", ".join(f"{k} {v}" for k, v in sorted(ops.items(), key=lambda kv: -kv[1])) + "\n")
+            for b in body:
+                f.write(b[:120] + "\n")
+print("wrote", os.listdir(OUT))
