@@ -399,7 +399,9 @@ def run_gpu_arm(args):
         pixel_evals_ref = float(nfev.sum()) * m_disc
         t_norm_s = stage_ms[3] / args.steps * 1e-3
         sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
-        fp32_peak = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
+        # nominal SMs*128*2*f; measured on this pool with tools/micro/ffma2_rate.cu: 73.96 TFLOP/s at 1965 MHz
+        # (profiles/r01_fp32_peak_microbench.txt), i.e. 99.3 % of nominal -> the measured figure, scaled by the clock
+        fp32_peak = 0.9934 * info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
         flops_exec = stats["pixel_evals_value"] * FLOP_PER_PIXEL_EVAL + stats["pixel_evals_jacobian"] * FLOP_PER_PIXEL_JAC
         achieved = flops_exec / t_norm_s / 1e12
         peaks = {}
@@ -420,7 +422,8 @@ def run_gpu_arm(args):
             "traffic": None,
             "note": "compute-bound kernel (SURVEY 8d): algorithmic flops = 64 x value-only pixel evaluations + 152 x "
                     "value+analytic-Jacobian pixel evaluations executed (counted by the kernel) / CUDA-event time; peak = "
-                    "SMs*128*2*f_max (nominal fp32; MEASURED_PEAKS.json has no fp32 figure); HBM traffic is compulsory only "
+                    "measured FFMA rate (tools/micro/ffma2_rate.cu: 73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; "
+                    "MEASURED_PEAKS.json has no fp32 figure); HBM traffic is compulsory only "
                     "(~44 KB/feature) and DRAM throughput ~0 (ncu, profiles/)",
             "pixel_evals_value": stats["pixel_evals_value"], "pixel_evals_jacobian": stats["pixel_evals_jacobian"],
             "passes": n_pass, "passes_fused": stats["passes_fused"], "fused_accepted": stats["fused_accepted"],
