@@ -180,6 +180,103 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
     }
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): two pixels per instruction.
+// A scalar operand written as bc(c) is encoded by ptxas as a broadcast register operand, so the
+// pass constants are not duplicated.  Lane results are the IEEE results of the scalar ops.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 bc(float c) { return mk2(c, c); }
+__device__ __forceinline__ float lo2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2_rm(f2 a, f2 b) { f2 r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
+
+// Ray offsets are stored pair-interleaved: pixels 2p and 2p+1 share one 16-byte record
+// (x[2p], x[2p+1], y[2p], y[2p+1]), so that one 128-bit load yields the packed X and Y operands of
+// a pixel pair without register shuffles.  Adjacent disc pixels also share their window taps' banks.
+__device__ __forceinline__ float2 ray_at(const float2* rays, int idx) {
+    const float* r = reinterpret_cast<const float*>(rays) + 4 * (idx >> 1) + (idx & 1);
+    return make_float2(r[0], r[2]);
+}
+__device__ __forceinline__ void ray_set(float2* rays, int idx, float x, float y) {
+    float* r = reinterpret_cast<float*>(rays) + 4 * (idx >> 1) + (idx & 1);
+    r[0] = x; r[2] = y;
+}
+
+struct Acc2 {      // Jacobian sums of the packed loop: lanes are added at the end of the pass
+    f2 s1, s2, s3, s4, s5;
+};
+
+// eval_pixel_fast for two pixels at once (taps from the staged window only).  The value path is
+// the same sequence of IEEE operations as the scalar function, lane by lane.
+template <bool JAC>
+__device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelConst& L, f2 X, f2 Y, f2 I1p, Acc& acc, Acc2& acc2) {
+    const f2 A0 = fma2(bc(P.h[0][0]), X, fma2(bc(P.h[0][1]), Y, bc(P.h[0][2])));
+    const f2 B0 = fma2(bc(P.h[0][3]), X, fma2(bc(P.h[0][4]), Y, bc(P.h[0][5])));
+    const f2 C0 = fma2(bc(P.h[0][6]), X, fma2(bc(P.h[0][7]), Y, bc(P.h[0][8])));
+    float ra, rb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(lo2(C0)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(hi2(C0)));
+    const f2 r0 = mk2(ra, rb);
+    const f2 iz = fma2(r0, fma2(neg2(C0), r0, bc(1.0f)), r0);
+    const f2 x = fma2(A0, iz, bc(L.xc)), y = fma2(B0, iz, bc(L.yc));
+    const f2 r2 = fma2(x, x, mul2(y, y));
+    const f2 cd = fma2(r2, fma2(r2, fma2(r2, bc(L.k3), bc(L.k2)), bc(L.k1)), bc(1.0f));
+    const f2 x2 = add2(x, x), y2 = add2(y, y);
+    const f2 xy2 = mul2(x2, y);
+    const f2 a2 = fma2(x2, x, r2), a3 = fma2(y2, y, r2);
+    const f2 xd = fma2(x, cd, fma2(bc(L.p1), xy2, mul2(bc(L.p2), a2)));
+    const f2 yd = fma2(y, cd, fma2(bc(L.p1), a3, mul2(bc(L.p2), xy2)));
+    const f2 su = fma2(xd, bc(L.sfx), bc(L.scx)), sv = fma2(yd, bc(L.sfy), bc(L.scy));
+    const f2 tx = add2_rm(su, bc(FLOOR_MAGIC)), ty = add2_rm(sv, bc(FLOOR_MAGIC));
+    const f2 ax = sub2(su, sub2(tx, bc(FLOOR_MAGIC))), ay = sub2(sv, sub2(ty, bc(FLOOR_MAGIC)));
+    unsigned aa = __float_as_uint(lo2(ty)) * L.ww + __float_as_uint(lo2(tx)) - L.coff;
+    unsigned ab = __float_as_uint(hi2(ty)) * L.ww + __float_as_uint(hi2(tx)) - L.coff;
+    aa = min(aa, L.amax);   // memory safety only: the boundary test proves the address is in range
+    ab = min(ab, L.amax);
+    const uint8_t* pa = L.win + aa;
+    const uint8_t* pb = L.win + ab;
+    const f2 b00 = mk2(u2f(pa[0]), u2f(pb[0])), b10 = mk2(u2f(pa[1]), u2f(pb[1]));
+    const f2 b01 = mk2(u2f(pa[L.ww]), u2f(pb[L.ww])), b11 = mk2(u2f(pa[L.ww + 1]), u2f(pb[L.ww + 1]));
+    const f2 d0 = sub2(b01, b00), d1 = sub2(b11, b10);
+    const f2 c0 = fma2(ay, d0, b00), c1 = fma2(ay, d1, b10);
+    const f2 gx = sub2(c1, c0);
+    const f2 I2 = fma2(ax, gx, c0);
+    const f2 d = sub2(I1p, I2);
+    const float da = lo2(d), db = hi2(d);
+    acc.s0 = fma((double)da, (double)da, acc.s0);
+    acc.s0 = fma((double)db, (double)db, acc.s0);
+    if (JAC) {
+        const f2 gy = fma2(ax, sub2(d1, d0), d0);
+        const f2 cdp = fma2(r2, fma2(r2, bc(3.0f * L.k3), bc(2.0f * L.k2)), bc(L.k1));   // d cd / d r2
+        const f2 Jxx = fma2(mul2(x2, x), cdp, fma2(bc(2.0f * L.p1), y, fma2(bc(6.0f * L.p2), x, cd)));
+        const f2 Jxy = fma2(xy2, cdp, fma2(bc(2.0f * L.p1), x, mul2(bc(2.0f * L.p2), y)));
+        const f2 Jyy = fma2(mul2(y2, y), cdp, fma2(bc(6.0f * L.p1), y, fma2(bc(2.0f * L.p2), x, cd)));
+        const f2 Gx = mul2(gx, bc(L.sfx)), Gy = mul2(gy, bc(L.sfy));
+        const f2 Ix = fma2(Gx, Jxx, mul2(Gy, Jxy)), Iy = fma2(Gx, Jxy, mul2(Gy, Jyy));   // dI2/d(x,y)
+        const f2 q0 = mul2(Ix, iz), q1 = mul2(Iy, iz);
+        const f2 dx = mul2(A0, iz), dy = mul2(B0, iz);
+        const f2 q2 = neg2(fma2(q0, dx, mul2(q1, dy)));
+        const f2 A1 = fma2(bc(P.h[1][0]), X, fma2(bc(P.h[1][1]), Y, bc(P.h[1][2])));
+        const f2 B1 = fma2(bc(P.h[1][3]), X, fma2(bc(P.h[1][4]), Y, bc(P.h[1][5])));
+        const f2 C1 = fma2(bc(P.h[1][6]), X, fma2(bc(P.h[1][7]), Y, bc(P.h[1][8])));
+        const f2 A2 = fma2(bc(P.h[2][0]), X, fma2(bc(P.h[2][1]), Y, bc(P.h[2][2])));
+        const f2 B2 = fma2(bc(P.h[2][3]), X, fma2(bc(P.h[2][4]), Y, bc(P.h[2][5])));
+        const f2 C2 = fma2(bc(P.h[2][6]), X, fma2(bc(P.h[2][7]), Y, bc(P.h[2][8])));
+        const f2 Ip = fma2(q0, A1, fma2(q1, B1, mul2(q2, C1)));   // dI2/dphi   (residual derivative = -Ip)
+        const f2 It = fma2(q0, A2, fma2(q1, B2, mul2(q2, C2)));   // dI2/dtheta
+        acc2.s1 = fma2(Ip, Ip, acc2.s1);
+        acc2.s2 = fma2(Ip, It, acc2.s2);
+        acc2.s3 = fma2(It, It, acc2.s3);
+        acc2.s4 = fma2(Ip, d, acc2.s4);
+        acc2.s5 = fma2(It, d, acc2.s5);
+    }
+}
+
 // Gates of one boundary pixel (isInBoundingBox :646-655, isPixelGood :657-665) and the proof that its
 // taps are inside the staged window.
 __device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const LevelConst& L, float vcx, float vcy,
@@ -213,32 +310,44 @@ __device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const Leve
 template <bool JAC, bool SLOW, bool PREFETCH>
 __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& L, const float2* __restrict__ rays,
                                            const float* __restrict__ i1, int m, int tid, int NT, Acc& acc) {
-    int idx = tid;
+    if (SLOW) {
+        // taps from global memory (a boundary tap left the staged window): scalar path
+        for (int idx = tid; idx < m; idx += NT) eval_pixel_fast<JAC, true>(P, L, ray_at(rays, idx), i1[idx], acc);
+        return;
+    }
+    Acc2 acc2;
+    acc2.s1 = acc2.s2 = acc2.s3 = acc2.s4 = acc2.s5 = 0ull;
+    const ulonglong2* __restrict__ rp = reinterpret_cast<const ulonglong2*>(rays);   // (X, Y) of a pixel pair
+    const f2* __restrict__ ip = reinterpret_cast<const f2*>(i1);
+    const int npair = m >> 1;
+    int p = tid;
     if (PREFETCH) {
-        // rays / image-1 samples stream from the L2-resident scratch: the loads of the next two
-        // pixels are issued before the current two are evaluated
-        float2 dva = make_float2(0.f, 0.f), dvb = dva;
-        float Ia = 0.f, Ib = 0.f;
-        if (idx < m) { dva = rays[idx]; Ia = i1[idx]; }
-        if (idx + NT < m) { dvb = rays[idx + NT]; Ib = i1[idx + NT]; }
-        for (; idx + NT < m; idx += 2 * NT) {
-            const float2 ca = dva, cb = dvb;
-            const float cIa = Ia, cIb = Ib;
-            const int nx = idx + 2 * NT;
-            if (nx < m) { dva = rays[nx]; Ia = i1[nx]; }
-            if (nx + NT < m) { dvb = rays[nx + NT]; Ib = i1[nx + NT]; }
-            eval_pixel_fast<JAC, SLOW>(P, L, ca, cIa, acc);
-            eval_pixel_fast<JAC, SLOW>(P, L, cb, cIb, acc);
+        // rays / image-1 samples stream from the L2-resident scratch: the loads of the next pair
+        // are issued before the current one is evaluated
+        ulonglong2 r = make_ulonglong2(0ull, 0ull);
+        f2 I = 0ull;
+        if (p < npair) { r = rp[p]; I = ip[p]; }
+        for (; p < npair; p += NT) {
+            const ulonglong2 cr = r;
+            const f2 cI = I;
+            const int nx = p + NT;
+            if (nx < npair) { r = rp[nx]; I = ip[nx]; }
+            eval_pixel_pair<JAC>(P, L, cr.x, cr.y, cI, acc, acc2);
         }
-        if (idx < m) eval_pixel_fast<JAC, SLOW>(P, L, dva, Ia, acc);
     } else {
-        for (; idx + NT < m; idx += 2 * NT) {
-            const float2 dva = rays[idx], dvb = rays[idx + NT];
-            const float Ia = i1[idx], Ib = i1[idx + NT];
-            eval_pixel_fast<JAC, SLOW>(P, L, dva, Ia, acc);
-            eval_pixel_fast<JAC, SLOW>(P, L, dvb, Ib, acc);
+        for (; p < npair; p += NT) {
+            const ulonglong2 r = rp[p];
+            eval_pixel_pair<JAC>(P, L, r.x, r.y, ip[p], acc, acc2);
         }
-        if (idx < m) eval_pixel_fast<JAC, SLOW>(P, L, rays[idx], i1[idx], acc);
+    }
+    // odd pixel count: the last pixel alone (thread chosen so that the summation order is fixed)
+    if ((m & 1) && tid == (npair % NT)) eval_pixel_fast<JAC, false>(P, L, ray_at(rays, m - 1), i1[m - 1], acc);
+    if (JAC) {
+        acc.s1 += lo2(acc2.s1) + hi2(acc2.s1);
+        acc.s2 += lo2(acc2.s2) + hi2(acc2.s2);
+        acc.s3 += lo2(acc2.s3) + hi2(acc2.s3);
+        acc.s4 += lo2(acc2.s4) + hi2(acc2.s4);
+        acc.s5 += lo2(acc2.s5) + hi2(acc2.s5);
     }
 }
 
@@ -491,7 +600,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 const double py = cv + (double)rows->jrow[row];
                 double vx, vy;
                 fm3d_undistort(cam, px, py, vx, vy);
-                rays[idx] = make_float2((float)(vx - vcx), (float)(vy - vcy));
+                ray_set(rays, idx, (float)(vx - vcx), (float)(vy - vcy));
             }
         }
         // boundary lattice: both ends of every row, and the whole first and last row
@@ -643,7 +752,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     } else {
                         idx = rows->start[last_row] + (k - 2 * nrows - n_first);
                     }
-                    flags |= boundary_flags(P, L, vcxf, vcyf, cmax, rays[idx]);
+                    flags |= boundary_flags(P, L, vcxf, vcyf, cmax, ray_at(rays, idx));
                 }
 
                 Acc acc;

@@ -80,6 +80,77 @@ def normals_stress(ctx, stream, n_feat):
                               "nfev_mean_per_level": nfev.float().mean(0).tolist()}), flush=True)
 
 
+def c3_pipeline(ctx, stream):
+    """BASELINE configs[2] on ONE GPU: 4K stereo pair, 20 000 keypoints (+4 000 distractors), 64 px,
+    4 levels; match -> triangulate -> pyramids -> normal search -> frames -> patches (K8)."""
+    dev = torch.device("cuda", 0)
+    t0 = time.time()
+    case = synth.make_stereo_case(3840, 2160, 20000, 1002, pixels_ray=64, n_distractors=4000)
+    gen_s = time.time() - t0
+    cam = case["scene"].cam
+    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
+    ctx.set_g12(cam.g12)
+    H, W = case["scene"].img1.shape
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    q, t, kp1, kp2 = to(case["desc1"]), to(case["desc2"]), to(case["kp1"]), to(case["kp2"])
+    img1, img2 = to(case["scene"].img1), to(case["scene"].img2)
+    nq, nt = q.shape[0], t.shape[0]
+    idx = torch.empty((nq, 2), dtype=torch.int32, device=dev); dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    qi = torch.empty(nq, dtype=torch.int32, device=dev); ti = torch.empty(nq, dtype=torch.int32, device=dev)
+    do = torch.empty(nq, dtype=torch.float32, device=dev); nm = torch.zeros(1, dtype=torch.int32, device=dev)
+    xyz_all = torch.empty((nq, 3), dtype=torch.float64, device=dev); xyz = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+    mask = torch.empty(nq, dtype=torch.uint8, device=dev); src = torch.empty(nq, dtype=torch.int32, device=dev)
+    ninl = torch.zeros(1, dtype=torch.int32, device=dev)
+    normals = torch.empty((nq, 3), dtype=torch.float64, device=dev); status = torch.empty(nq, dtype=torch.int32, device=dev)
+    nfev = torch.zeros((nq, 4), dtype=torch.int32, device=dev); npen = torch.zeros(nq, dtype=torch.int32, device=dev)
+    cost = torch.empty(nq, dtype=torch.float64, device=dev)
+    frames = torch.empty((nq, 16), dtype=torch.float64, device=dev)
+    S = api.patch_size(0.16, 0.25)
+    patches = torch.empty((nq, S, S), dtype=torch.uint8, device=dev)
+    g = np.array([0.006, 0.99992, -0.011])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+    out = {}
+    for rep in range(2):
+        with torch.cuda.stream(stream):
+            ev[0].record(stream)
+            ctx.match_knn2_f32_dev(q.data_ptr(), nq, t.data_ptr(), nt, 128, idx.data_ptr(), dist.data_ptr())
+            ctx.nndr_filter_dev(idx.data_ptr(), dist.data_ptr(), nq, 0.55, qi.data_ptr(), ti.data_ptr(), do.data_ptr(), nm.data_ptr())
+            ev[1].record(stream)
+            n_match = int(nm.item())
+            ctx.triangulate_dev(kp1.data_ptr(), nq, kp2.data_ptr(), nt, qi.data_ptr(), ti.data_ptr(), n_match, xyz_all.data_ptr(),
+                                mask.data_ptr(), xyz.data_ptr(), src.data_ptr(), ninl.data_ptr())
+            ev[2].record(stream)
+            ctx.set_images_dev(img1.data_ptr(), img2.data_ptr(), W, H, W, 3)
+            ev[3].record(stream)
+            n_inl = int(ninl.item())
+            ctx.optimize_normals_dev(xyz.data_ptr(), n_inl, 64, 1e-10, 1, normals.data_ptr(), status.data_ptr(), nfev.data_ptr(),
+                                     npen.data_ptr(), cost.data_ptr())
+            ev[4].record(stream)
+            ctx.feature_frames_dev(xyz.data_ptr(), normals.data_ptr(), n_inl, g, frames.data_ptr())
+            ev[5].record(stream)
+            ctx.extract_patches_dev(frames.data_ptr(), n_inl, 0.16, 0.25, patches.data_ptr(), None)
+            ev[6].record(stream)
+        stream.synchronize()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(6)]
+    st = ctx.normals_stats()
+    src_h = src[:n_inl].cpu().numpy(); qi_h = qi[:n_match].cpu().numpy()
+    feat = qi_h[src_h]                       # query keypoint of every inlier
+    gt_n = case["normal"][feat]
+    ok = status[:n_inl].cpu().numpy() == 0
+    ang = np.degrees(np.arccos(np.clip((normals[:n_inl].cpu().numpy() * gt_n).sum(1), -1, 1)))
+    t_core = ms[0] + ms[1] + ms[2] + ms[3]
+    pyr_bytes = sum(2 * 1.25 * (W >> l) * (H >> l) for l in range(3))
+    print(json.dumps({"case": "c3_4k_20k_one_gpu", "gen_s": gen_s, "matches": n_match, "inliers": n_inl, "ok": int(ok.sum()),
+                      "median_angle_to_gt_deg": float(np.median(ang[ok])), "p99_angle_to_gt_deg": float(np.percentile(ang[ok], 99)),
+                      "stage_ms": {"match+nndr": ms[0], "triangulate": ms[1], "pyramids": ms[2], "normals": ms[3], "frames": ms[4], "patches": ms[5]},
+                      "features_per_s_match_tri_normals": n_match / (t_core * 1e-3),
+                      "matcher_tflops": 256.0 * nq * nt / (ms[0] * 1e-3) / 1e12,
+                      "pyrdown_gbs": pyr_bytes / (ms[2] * 1e-3) / 1e9, "hbm_peak_gbs": PEAKS.get("hbm_gbs"),
+                      "patches_per_s": n_inl / (ms[5] * 1e-3), "patch_px_per_s": n_inl * S * S / (ms[5] * 1e-3),
+                      "normals_pixel_evals_per_s": (st["pixel_evals_value"] + st["pixel_evals_jacobian"]) / (ms[3] * 1e-3),
+                      "passes_global_taps": st["passes_slow"]}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = api.Context(0)
@@ -88,4 +159,6 @@ if __name__ == "__main__":
         match_sweep(ctx, stream, [10000, 50000, 100000, 200000])
     if which in ("all", "normals"):
         normals_stress(ctx, stream, int(sys.argv[2]) if len(sys.argv) > 2 else 2000)
+    if which in ("c3",):
+        c3_pipeline(ctx, stream)
     ctx.close()
