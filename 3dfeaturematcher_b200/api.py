@@ -243,7 +243,7 @@ class Context:
         self._ck(self.lib.fm3d_get_normals_stats(self._h, out))
         keys = ("passes_value", "passes_jacobian", "passes_fused", "fused_accepted", "passes_slow",
                 "pixel_evals_value", "pixel_evals_jacobian", "features", "cycles_pixels", "cycles_barrier",
-                "cycles_serial", "cycles_lm", "cycles_publish", "trials_memoized")
+                "cycles_serial", "cycles_lm", "cycles_publish", "trials_memoized", "cycles_prologue", "cycles_level_setup")
         return dict(zip(keys, [int(v) for v in out]))
 
     def evaluate_normals(self, xyz, phi_theta, pixels_ray, level, penalty_mode=PENALTY_FABS):

@@ -206,6 +206,7 @@ int fm3d_set_camera(fm3d_ctx* ctx, const double K[9], const double dist[5], doub
     FM3D_CHECK_ARG(ctx, K && dist);
     FM3D_CHECK_ARG(ctx, K[0] != 0.0 && K[4] != 0.0);
     ctx->cam.fx = K[0]; ctx->cam.fy = K[4]; ctx->cam.cx = K[2]; ctx->cam.cy = K[5];
+    ctx->cam.ifx = 1.0 / K[0]; ctx->cam.ify = 1.0 / K[4];
     ctx->cam.k1 = dist[0]; ctx->cam.k2 = dist[1]; ctx->cam.p1 = dist[2]; ctx->cam.p2 = dist[3];
     ctx->cam.k3 = dist[4];
     ctx->cam.zmin = z_min; ctx->cam.zmax = z_max;

@@ -17,6 +17,7 @@
 // reference keeps them (Triangulator/singlecameratriangulator.cpp:73-105,123-143).
 struct fm3d_cam {
     double fx, fy, cx, cy;
+    double ifx, ify;                    // 1/fx, 1/fy
     double k1, k2, p1, p2, k3;
     double R[9], t[3];
     double zmin, zmax;

@@ -53,7 +53,8 @@ struct NormalsArgs {
     int group_smem;                     // fast kernel: bytes of shared memory per group
     float2* rays_g;
     float* i1_g;
-    CUtensorMap tmap[FM3D_MAX_LEVELS];
+    CUtensorMap tmap[FM3D_MAX_LEVELS];      // image 2, one per level
+    CUtensorMap tmap1[FM3D_MAX_LEVELS];     // image 1 (fast kernel: image-1 samples are taken from a staged window too)
 };
 
 // Parameters of one pass, written by thread 0 and read by everybody.

@@ -68,7 +68,8 @@ struct FastShared {
     int status;
     int npenalty;
     int m;
-    int wx0, wy0;
+    int wx0, wy0;       // image-2 window origin (level pixels)
+    int w1x0, w1y0;     // image-1 window origin
     int tma_phase;
     int where;          // AT_*
     int alive;
@@ -102,6 +103,26 @@ __device__ __forceinline__ float u2f(unsigned b) {  // I2FP (the compiler would 
     float f;
     asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(b));
     return f;
+}
+
+// cv::undistortPoints (5 fixed-point iterations, fp64) for the rays of the disc.  The reciprocal is
+// the MUFU-seeded one: the rays are stored as fp32 offsets, the last ulp of the fp64 iteration is
+// far below their resolution.
+__device__ __forceinline__ void undistort_ray(const fm3d_cam& c, double u, double v, double& xo, double& yo) {
+    const double x0 = (u - c.cx) * c.ifx, y0 = (v - c.cy) * c.ify;
+    double x = x0, y = y0;
+#pragma unroll 1
+    for (int it = 0; it < 5; it++) {
+        const double r2 = x * x + y * y;
+        const double icd = fm3d_rcp(1.0 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
+        if (icd < 0) { x = x0; y = y0; break; }
+        const double xy2 = 2.0 * x * y;
+        const double dx = c.p1 * xy2 + c.p2 * (r2 + 2 * x * x);
+        const double dy = c.p1 * (r2 + 2 * y * y) + c.p2 * xy2;
+        x = (x0 - dx) * icd;
+        y = (y0 - dy) * icd;
+    }
+    xo = x; yo = y;
 }
 
 struct Acc {
@@ -459,6 +480,49 @@ __device__ __forceinline__ int gsync_and(int groups, int g, int nt, int pred) {
     return out;
 }
 
+// Stages the ww x wh window of a pyramid level whose origin is (wx0, wy0) into `win`: one TMA
+// tensor-tile load (zero fill outside the image) waited on by the whole group, or cooperative
+// 16-byte loads for boxes wider than a TMA tile.  Returns false if the TMA wait timed out.
+__device__ __forceinline__ bool stage_window(const NormalsArgs& A, const CUtensorMap* tmap, bool by_tma, const uint8_t* img,
+                                             const fm3d_level& lv, uint8_t* win, int ww, int wh, int wx0, int wy0,
+                                             uint64_t* bar, int* tma_phase, int groups, int g, int NT, int tid) {
+    if (ww <= 0 || wh <= 0) return false;
+    if (by_tma) {
+        const uint32_t parity = (uint32_t)*tma_phase;
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, (uint32_t)(ww * wh));
+            tma_load_2d(win, tmap, wx0, wy0, bar);
+        }
+        bool ok = false;
+        for (int spin = 0; spin < (1 << 22); spin++) {
+            if (mbar_try_wait(bar, parity)) { ok = true; break; }
+        }
+        const bool staged = gsync_and(groups, g, NT, ok ? 1 : 0) != 0;
+        if (tid == 0) {
+            *tma_phase ^= 1;
+            if (!staged) atomicExch(A.error_flag, 1);
+        }
+        return staged;
+    }
+    const int wq = ww >> 4;
+    for (int i = tid; i < wq * wh; i += NT) {
+        const int yy = i / wq, xq = i - yy * wq;
+        const int gx = wx0 + 16 * xq, gy = wy0 + yy;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gy >= 0 && gy < lv.h && gx >= 0 && gx + 16 <= lv.pitch) {
+            v = *reinterpret_cast<const uint4*>(img + (size_t)gy * lv.pitch + gx);
+        } else if (gy >= 0 && gy < lv.h) {
+            __align__(16) uint8_t b[16];
+            for (int k = 0; k < 16; k++) b[k] = (gx + k >= 0 && gx + k < lv.w) ? img[(size_t)gy * lv.pitch + gx + k] : 0;
+            v = *reinterpret_cast<uint4*>(b);
+        }
+        *reinterpret_cast<uint4*>(win + (size_t)yy * ww + 16 * xq) = v;
+    }
+    gsync(groups, g, NT);
+    return true;
+}
+
 // RAYS_SMEM / I1_SMEM: where the per-pixel ray offsets (8 B) and image-1 samples (4 B) of the
 // feature live: shared memory, or a per-group scratch in global memory that stays L2-resident
 // (one CTA streams it once per pass: 12 B x 12 853 pixels at r = 64).
@@ -519,6 +583,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
         gsync(groups, g, NT);
         const int f = S->feature;
         if (f >= A.n) break;
+        const long long t_f0 = clock64();
         const double Px = A.xyz[3 * f], Py = A.xyz[3 * f + 1], Pz = A.xyz[3 * f + 2];
 
         // ------------------------------------------------------------ prologue: disc lattice
@@ -599,7 +664,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
                 const double py = cv + (double)rows->jrow[row];
                 double vx, vy;
-                fm3d_undistort(cam, px, py, vx, vy);
+                undistort_ray(cam, px, py, vx, vy);
                 ray_set(rays, idx, (float)(vx - vcx), (float)(vy - vcy));
             }
         }
@@ -614,7 +679,9 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
         const int lvl_hi = A.mode == 0 ? levels : A.eval_level;
         const int lvl_lo = A.mode == 0 ? 0 : A.eval_level;
         bool alive = m > 0;
+        if (tid == 0) S->stats[14] += (unsigned long long)(clock64() - t_f0);   // prologue: lattice + rays
         for (int lvl = lvl_hi; lvl >= lvl_lo && alive; lvl--) {
+            const long long t_l0 = clock64();
             const fm3d_level lv = A.pyr.lv[lvl];
             const double scale = 1.0 / (double)(1 << lvl);      // actual_scale_ (:226-241)
             const double inv_scale = 1.0 / scale;
@@ -630,56 +697,62 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             L.cols = (float)lv.w; L.rows = (float)lv.h;     // scale * (cols_l / scale)
             L.xc = (float)S->xc; L.yc = (float)S->yc;
 
-            // window origin: centred on the projection of P into image 2
+            // window origins.  Image 2: centred on the projection of P (P lies on every candidate plane).
+            // Image 1: the disc itself, scaled.  TMA needs the box start address 16-byte aligned: x
+            // origins are multiples of 16 pixels.
             if (tid == 0) {
                 double u2, v2;
                 fm3d_distort_K<double>(S->xc, S->yc, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, cam.fx, cam.fy, cam.cx, cam.cy, u2, v2);
                 double wxc = floor(scale * u2), wyc = floor(scale * v2);
                 if (!(wxc > -1e6 && wxc < 1e6)) wxc = 0;
                 if (!(wyc > -1e6 && wyc < 1e6)) wyc = 0;
-                // TMA needs the box start address 16-byte aligned: x origin is a multiple of 16 pixels
                 S->wx0 = (((int)wxc - (int)L.ww / 2 + 8) >> 4) << 4;
                 S->wy0 = (int)wyc - wh / 2;
+                double w1x = floor(scale * (cu - (double)r)) - 1.0, w1y = floor(scale * (cv - (double)r)) - 1.0;
+                if (!(w1x > -1e6 && w1x < 1e6)) w1x = 0;
+                if (!(w1y > -1e6 && w1y < 1e6)) w1y = 0;
+                S->w1x0 = ((int)w1x >> 4) << 4;
+                S->w1y0 = (int)w1y;
             }
             gsync(groups, g, NT);  // also: everybody is done with the previous level's window
             L.wx0 = S->wx0; L.wy0 = S->wy0;
-            bool staged = false;
-            if (L.ww > 0 && wh > 0) {
-                if (A.use_tma && A.win_tma[lvl]) {
-                    const uint32_t parity = (uint32_t)S->tma_phase;
-                    if (tid == 0) {
-                        fence_proxy_async();
-                        mbar_expect_tx(bar, (uint32_t)(L.ww * wh));
-                        tma_load_2d(win, &A.tmap[lvl], L.wx0, L.wy0, bar);
+            const bool by_tma = A.use_tma && A.win_tma[lvl];
+
+            // image-1 intensities of the level (updateImage1PixelsIntensity, :576-589), sampled from the
+            // staged image-1 window; a pixel whose taps leave window or image takes the global path
+            unsigned lvl_flags = 0;
+            {
+                const int w1x0 = S->w1x0, w1y0 = S->w1y0;
+                const bool staged1 = stage_window(A, &A.tmap1[lvl], by_tma, img1, lv, win, (int)L.ww, wh, w1x0, w1y0, bar,
+                                                  &S->tma_phase, groups, g, NT, tid);
+                const int x_lo = max(w1x0, 0), x_hi = min(w1x0 + (int)L.ww, lv.w) - 1;   // x0 in [x_lo, x_hi)
+                const int y_lo = max(w1y0, 0), y_hi = min(w1y0 + wh, lv.h) - 1;
+                const int x_cnt = staged1 ? max(x_hi - x_lo, 0) : 0, y_cnt = staged1 ? max(y_hi - y_lo, 0) : 0;
+                int row = 0;
+                for (int idx = tid; idx < m; idx += NT) {
+                    while (idx >= rows->start[row + 1]) row++;
+                    const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
+                    const double py = cv + (double)rows->jrow[row];
+                    if (!fm3d_pixel_good(px, py, inv_scale, lv.w, lv.h)) lvl_flags |= FLAG_PIX;
+                    const float sx = (float)(scale * px), sy = (float)(scale * py);
+                    const float fx0 = floorf(sx), fy0 = floorf(sy);
+                    const int x0 = (int)fx0, y0 = (int)fy0;
+                    float v;
+                    if ((unsigned)(x0 - x_lo) < (unsigned)x_cnt && (unsigned)(y0 - y_lo) < (unsigned)y_cnt) {
+                        const uint8_t* pw = win + (y0 - w1y0) * (int)L.ww + (x0 - w1x0);
+                        v = fm3d_lerp4(fm3d_u8f(pw[0]), fm3d_u8f(pw[L.ww]), fm3d_u8f(pw[1]), fm3d_u8f(pw[L.ww + 1]),
+                                       __fsub_rn(sx, fx0), __fsub_rn(sy, fy0));
+                    } else {
+                        v = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, sx, sy);
                     }
-                    bool ok = false;
-                    for (int spin = 0; spin < (1 << 22); spin++) {
-                        if (mbar_try_wait(bar, parity)) { ok = true; break; }
-                    }
-                    staged = gsync_and(groups, g, NT, ok ? 1 : 0) != 0;
-                    if (tid == 0) {
-                        S->tma_phase ^= 1;
-                        if (!staged) atomicExch(A.error_flag, 1);
-                    }
-                } else {
-                    // boxes wider than a TMA tile (or TMA switched off): cooperative 16-byte loads
-                    const int ww = (int)L.ww, wq = ww >> 4;
-                    for (int i = tid; i < wq * wh; i += NT) {
-                        const int yy = i / wq, xq = i - yy * wq;
-                        const int gx = L.wx0 + 16 * xq, gy = L.wy0 + yy;
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (gy >= 0 && gy < lv.h && gx >= 0 && gx + 16 <= lv.pitch) {
-                            v = *reinterpret_cast<const uint4*>(L.img2 + (size_t)gy * lv.pitch + gx);
-                        } else if (gy >= 0 && gy < lv.h) {
-                            __align__(16) uint8_t b[16];
-                            for (int k = 0; k < 16; k++) b[k] = (gx + k >= 0 && gx + k < lv.w) ? L.img2[(size_t)gy * lv.pitch + gx + k] : 0;
-                            v = *reinterpret_cast<uint4*>(b);
-                        }
-                        *reinterpret_cast<uint4*>(win + (size_t)yy * ww + 16 * xq) = v;
-                    }
-                    staged = true;
+                    i1[idx] = v;
                 }
+                gsync(groups, g, NT);   // everybody is done with the image-1 window
             }
+
+            // image-2 window
+            const bool staged = stage_window(A, &A.tmap[lvl], by_tma, L.img2, lv, win, (int)L.ww, wh, L.wx0, L.wy0, bar,
+                                             &S->tma_phase, groups, g, NT, tid);
             // taps (x0,y0),(x0+1,y0+1) must lie inside the window and inside the image
             {
                 int x_lo = max(L.wx0, 0), x_hi = min(L.wx0 + (int)L.ww, lv.w) - 1;  // x0 in [x_lo, x_hi)
@@ -689,19 +762,6 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             }
             L.coff = (FLOOR_MAGIC_BITS + (unsigned)L.wy0) * L.ww + FLOOR_MAGIC_BITS + (unsigned)L.wx0;
             L.amax = L.ww * (unsigned)wh - L.ww - 2u;
-
-            // image-1 intensities of the level (updateImage1PixelsIntensity, :576-589)
-            unsigned lvl_flags = 0;
-            {
-                int row = 0;
-                for (int idx = tid; idx < m; idx += NT) {
-                    while (idx >= rows->start[row + 1]) row++;
-                    const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
-                    const double py = cv + (double)rows->jrow[row];
-                    if (!fm3d_pixel_good(px, py, inv_scale, lv.w, lv.h)) lvl_flags |= FLAG_PIX;
-                    i1[idx] = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, (float)(scale * px), (float)(scale * py));
-                }
-            }
 
             // warp 0: start the LM of this level (optimize(), :247-292)
             if (wid == 0) {
@@ -732,6 +792,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             }
             gsync(groups, g, NT);
 
+            if (tid == 0) S->stats[15] += (unsigned long long)(clock64() - t_l0);   // level set-up: window + image-1 samples
             // -------------------------------------------------------- pass loop (two barriers per pass)
             for (;;) {
                 const FastPass P = *PP;
@@ -1017,6 +1078,9 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         if (A.use_tma && A.win_tma[l]) {
             const fm3d_level& lv = A.pyr.lv[l];
             if (int rc = fm3d_encode_tmap_2d_u8(ctx, &A.tmap[l], A.pyr.base[1] + lv.off, lv.w, lv.h, lv.pitch,
+                                                A.win_w[l], A.win_h[l]))
+                return rc;
+            if (int rc = fm3d_encode_tmap_2d_u8(ctx, &A.tmap1[l], A.pyr.base[0] + lv.off, lv.w, lv.h, lv.pitch,
                                                 A.win_w[l], A.win_h[l]))
                 return rc;
         }

@@ -238,7 +238,8 @@ int fm3d_optimize_normals_dev(fm3d_ctx* ctx, const double* xyz, int n, int pixel
  *   out[8..10] SM cycles of thread 0 in: the pixel loop of the passes / waiting for the slowest
  *   warp / the serial reduction + LM step + homography set-up;  out[11], out[12] split of out[10]
  *   into LM algebra and homography set-up;  out[13] trial points answered without a pass (their
- *   fp32 homography coefficients equal the iterate's);  out[14..15] reserved
+ *   fp32 homography coefficients equal the iterate's);  out[14] cycles of the per-feature prologue
+ *   (disc lattice + undistorted rays), out[15] of the per-level set-up (window staging + image-1 samples)
  * nfev (above) counts what lmfit would have evaluated; these count what the GPU did. */
 int fm3d_get_normals_stats(fm3d_ctx* ctx, int64_t out[16]);
 
