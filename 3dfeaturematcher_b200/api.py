@@ -30,7 +30,8 @@ SYMBOLS = [
     "fm3d_match_nndr_hamming", "fm3d_match_knn2_f32_dev", "fm3d_match_knn2_hamming_dev",
     "fm3d_nndr_filter_dev", "fm3d_triangulate", "fm3d_triangulate_dev", "fm3d_undistort_points",
     "fm3d_set_images", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
-    "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_get_normals_stats", "fm3d_feature_frames",
+    "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_get_normals_stats",
+    "fm3d_sweep_normals", "fm3d_sweep_normals_dev", "fm3d_feature_frames",
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
 ]
@@ -254,6 +255,26 @@ class Context:
         self._ck(self.lib.fm3d_evaluate_normals(self._h, _ptr(xyz, _dp), _ptr(pt, _dp), n, int(pixels_ray), int(level),
                                                 int(penalty_mode), _ptr(cost, _dp), _ptr(m, _ip), _ptr(status, _ip)))
         return cost, m, status
+
+    def sweep_normals(self, xyz, pixels_ray, level, n_phi, n_theta, dphi, dtheta, center_phi_theta=None,
+                      penalty_mode=PENALTY_FABS, want_cost=True):
+        xyz = _arr(xyz, np.float64).reshape(-1, 3)
+        n = xyz.shape[0]
+        pt = None if center_phi_theta is None else _arr(center_phi_theta, np.float64).reshape(-1, 2)
+        cost = np.empty((n, n_phi, n_theta)) if want_cost else None
+        best, bcost, status = np.empty(n, np.int32), np.empty(n), np.empty(n, np.int32)
+        self._ck(self.lib.fm3d_sweep_normals(self._h, _ptr(xyz, _dp), None if pt is None else _ptr(pt, _dp), n, int(pixels_ray),
+                                             int(level), int(penalty_mode), int(n_phi), int(n_theta), C.c_double(dphi),
+                                             C.c_double(dtheta), None if cost is None else _ptr(cost, _dp), _ptr(best, _ip),
+                                             _ptr(bcost, _dp), _ptr(status, _ip)))
+        return {"cost": cost, "best_idx": best, "best_cost": bcost, "status": status}
+
+    def sweep_normals_dev(self, xyz, n, pixels_ray, level, n_phi, n_theta, dphi, dtheta, status, center_phi_theta=None,
+                          penalty_mode=PENALTY_FABS, cost=None, best_idx=None, best_cost=None):
+        self._ck(self.lib.fm3d_sweep_normals_dev(self._h, C.c_void_p(xyz), C.c_void_p(center_phi_theta), n, int(pixels_ray),
+                                                 int(level), int(penalty_mode), int(n_phi), int(n_theta), C.c_double(dphi),
+                                                 C.c_double(dtheta), C.c_void_p(cost), C.c_void_p(best_idx),
+                                                 C.c_void_p(best_cost), C.c_void_p(status)))
 
     def feature_frames(self, xyz, normals, gravity):
         xyz = _arr(xyz, np.float64).reshape(-1, 3)

@@ -698,6 +698,59 @@ int fm3d_evaluate_normals(fm3d_ctx* ctx, const double* xyz, const double* normal
     return FM3D_OK;
 }
 
+int fm3d_sweep_normals_dev(fm3d_ctx* ctx, const double* xyz, const double* center_phi_theta, int n,
+                           int pixels_ray, int level, int penalty_mode, int n_phi, int n_theta,
+                           double dphi, double dtheta, double* cost, int32_t* best_idx,
+                           double* best_cost, int32_t* status) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && (n == 0 || (xyz && status)));
+    FM3D_CHECK_ARG(ctx, penalty_mode >= 0 && penalty_mode <= 2);
+    FM3D_CHECK_ARG(ctx, n_phi >= 1 && n_theta >= 1 && (long long)n_phi * n_theta <= (1 << 20));
+    if (!ctx->has_cam || !ctx->has_g12) return fm3d_fail(ctx, FM3D_ERR_STATE, "camera / g12 not set");
+    if (!ctx->has_images) return fm3d_fail(ctx, FM3D_ERR_STATE, "images not set");
+    FM3D_CHECK_ARG(ctx, level >= 0 && level <= ctx->pyr.levels);
+    if (pixels_ray < 0 || pixels_ray > MAX_RAY) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "pixels_ray must be in [0,%d]", MAX_RAY);
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    NormalsArgs A{};
+    A.xyz = xyz; A.n = n; A.r = pixels_ray; A.eps_lmmin = 1e-10; A.penalty_mode = penalty_mode;
+    A.mode = 2; A.eval_level = level; A.phi_theta = center_phi_theta;
+    A.sweep_nphi = n_phi; A.sweep_ntheta = n_theta; A.sweep_dphi = dphi; A.sweep_dtheta = dtheta;
+    A.cost = cost; A.best_idx = best_idx; A.best_cost = best_cost; A.status = status;
+    return run_normals_fast(ctx, A);
+}
+
+int fm3d_sweep_normals(fm3d_ctx* ctx, const double* xyz, const double* center_phi_theta, int n,
+                       int pixels_ray, int level, int penalty_mode, int n_phi, int n_theta,
+                       double dphi, double dtheta, double* cost, int32_t* best_idx,
+                       double* best_cost, int32_t* status) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && (n == 0 || (xyz && status)));
+    FM3D_CHECK_ARG(ctx, n_phi >= 1 && n_theta >= 1 && (long long)n_phi * n_theta <= (1 << 20));
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t K = (size_t)n_phi * n_theta;
+    const size_t b3 = sizeof(double) * 3 * (size_t)n, b2 = sizeof(double) * 2 * (size_t)n, bi = sizeof(int32_t) * (size_t)n;
+    const size_t bc = cost ? sizeof(double) * K * (size_t)n : 0, bd = sizeof(double) * (size_t)n;
+    size_t o_xyz = 0, o_pt = o_xyz + al(b3), o_c = o_pt + al(b2), o_bi = o_c + al(bc), o_bc = o_bi + al(bi);
+    size_t o_st = o_bc + al(bd), o_end = o_st + al(bi);
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, o_end, (void**)&d)) return rc;
+    if (int rc = fm3d_h2d(ctx, d + o_xyz, xyz, b3)) return rc;
+    if (center_phi_theta) if (int rc = fm3d_h2d(ctx, d + o_pt, center_phi_theta, b2)) return rc;
+    if (int rc = fm3d_sweep_normals_dev(ctx, (const double*)(d + o_xyz), center_phi_theta ? (const double*)(d + o_pt) : nullptr, n,
+                                        pixels_ray, level, penalty_mode, n_phi, n_theta, dphi, dtheta,
+                                        cost ? (double*)(d + o_c) : nullptr, (int32_t*)(d + o_bi), (double*)(d + o_bc),
+                                        (int32_t*)(d + o_st))) return rc;
+    if (cost) if (int rc = fm3d_d2h(ctx, cost, d + o_c, bc)) return rc;
+    if (best_idx) if (int rc = fm3d_d2h(ctx, best_idx, d + o_bi, bi)) return rc;
+    if (best_cost) if (int rc = fm3d_d2h(ctx, best_cost, d + o_bc, bd)) return rc;
+    if (int rc = fm3d_d2h(ctx, status, d + o_st, bi)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
+
 int fm3d_feature_frames_dev(fm3d_ctx* ctx, const double* xyz, const double* normals, int n,
                             const double gravity[3], double* frames) {
     if (!ctx) return FM3D_ERR_INVALID_ARG;

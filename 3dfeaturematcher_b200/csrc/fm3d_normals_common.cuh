@@ -30,7 +30,11 @@ struct NormalsArgs {
     double eps_lmmin;
     int penalty_mode;
     int patience;
-    int mode;               // 0 optimise, 1 evaluate the cost at phi_theta / level only
+    int mode;               // 0 optimise, 1 evaluate the cost at phi_theta / level only, 2 sweep a grid of candidates
+    int sweep_nphi, sweep_ntheta;       // mode 2: grid size, centred on phi_theta[f] (or the viewing ray)
+    double sweep_dphi, sweep_dtheta;    // mode 2: grid steps (rad)
+    int32_t* best_idx;                  // mode 2: argmin over the grid (nullable)
+    double* best_cost;                  // mode 2: its cost (nullable)
     int eval_level;
     const double* phi_theta;
     double* normals;

@@ -77,6 +77,10 @@ struct FastShared {
     float hbase[9];     // value coefficients (FastPass::h[0]) of the current LM iterate ...
     double s0_base;     // ... and the residual sum the pass at the iterate returned
     int base_valid;
+    int cand;           // mode 2 (sweep): candidate being evaluated
+    double sweep_c[2];  // mode 2: centre (phi, theta) of the candidate grid
+    double best_cost;   // mode 2: running minimum
+    int best_idx;
     int trial_is_first; // the trial being evaluated opens an LM iteration
     int fuse_hint;      // the last first trial of an LM iteration was accepted (initially 1)
     unsigned long long stats[16];
@@ -779,13 +783,27 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     }
                     publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
                 } else {
-                    phi = A.phi_theta[2 * f]; theta = A.phi_theta[2 * f + 1];
+                    if (A.phi_theta) {
+                        phi = A.phi_theta[2 * f]; theta = A.phi_theta[2 * f + 1];
+                    } else {   // the initial normal of the optimiser: the viewing ray (normaloptimizer.cpp:343)
+                        const double* nv = S->normal;
+                        theta = atan2(nv[2], sqrt(nv[0] * nv[0] + nv[1] * nv[1]));
+                        phi = atan2(nv[1], nv[0]);
+                    }
                     if (lane == 0) {
                         PP->slow = 0;
                         S->lm.nfev = 0;
                         S->lm.eps = 1e-5;
                         S->where = AT_XT_PLAIN;
                         S->base_valid = 0;
+                        S->cand = 0;
+                        S->sweep_c[0] = phi; S->sweep_c[1] = theta;
+                        S->best_cost = __longlong_as_double(0x7ff0000000000000LL);
+                        S->best_idx = -1;
+                    }
+                    if (A.mode == 2) {   // first candidate of the grid
+                        phi -= 0.5 * (double)(A.sweep_nphi - 1) * A.sweep_dphi;
+                        theta -= 0.5 * (double)(A.sweep_ntheta - 1) * A.sweep_dtheta;
                     }
                     publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
                 }
@@ -880,6 +898,22 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                             if ((fl & FLAG_WINDOW) && !(fl & 7) && !slow_pass) {
                                 PP->slow = 1;               // same pass again, taps from global memory
                                 next_kind = -1;
+                            } else if (A.mode == 2) {
+                                // dense candidate sweep: cost of this candidate (NaN if it fails a gate), next one
+                                const int K = A.sweep_nphi * A.sweep_ntheta, c = S->cand;
+                                const bool bad = (fl & 7) || s[0] != s[0];
+                                const double cval = bad ? __longlong_as_double(0x7ff8000000000000LL) : S->w[0] * S->w[0] * s[0];
+                                if (A.cost) A.cost[(size_t)f * K + c] = cval;
+                                if (!bad && cval < S->best_cost) { S->best_cost = cval; S->best_idx = c; }
+                                if (c + 1 < K) {
+                                    S->cand = c + 1;
+                                    const int ip = (c + 1) / A.sweep_ntheta, it = (c + 1) - ip * A.sweep_ntheta;
+                                    next_kind = PASS_VALUE;
+                                    next_phi = S->sweep_c[0] + ((double)ip - 0.5 * (double)(A.sweep_nphi - 1)) * A.sweep_dphi;
+                                    next_theta = S->sweep_c[1] + ((double)it - 0.5 * (double)(A.sweep_ntheta - 1)) * A.sweep_dtheta;
+                                } else {
+                                    PP->kind = PASS_STOP;
+                                }
                             } else if ((fl & 7) || s[0] != s[0]) {
                                 // all bounding-box / NaN tests of an evaluation precede its pixel tests
                                 S->status = ((fl & FLAG_NAN) || !(fl & 7)) ? FM3D_FEAT_ABORT_NAN
@@ -1000,6 +1034,9 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     if (A.cost) A.cost[f] = __longlong_as_double(0x7ff8000000000000LL);
                 }
                 if (A.npenalty) A.npenalty[f] = S->npenalty;
+            } else if (A.mode == 2) {
+                if (A.best_idx) A.best_idx[f] = st == FM3D_FEAT_OK ? S->best_idx : -1;
+                if (A.best_cost) A.best_cost[f] = S->best_cost;
             } else if (st != FM3D_FEAT_OK) {
                 A.cost[f] = __longlong_as_double(0x7ff8000000000000LL);
             }
@@ -1065,7 +1102,9 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     for (int k = 0; k < n_order && !found; k++) {
         const Layout c = order[k];
         const bool last = (k == n_order - 1);
-        win_bytes = plan_windows(last ? smem_max - tail - 1024 : (size_t)64 << 10);
+        // every layout but the last resort must hold the full-size window (a shrunken window sends
+        // the level-0 passes to the global-memory tap path)
+        win_bytes = plan_windows(last ? smem_max - tail - 1024 : (size_t)1 << 30);
         group_smem = (win_bytes + (c.rays_smem ? sizeof(float2) * (size_t)A.mcap : 0) +
                       (c.i1_smem ? sizeof(float) * (size_t)A.mcap : 0) + tail + 127) & ~(size_t)127;
         if (group_smem * c.groups <= smem_max) { lay = c; found = true; }

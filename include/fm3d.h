@@ -251,6 +251,25 @@ int fm3d_evaluate_normals(fm3d_ctx* ctx, const double* xyz, const double* normal
                           int n, int pixels_ray, int level, int penalty_mode, double* cost,
                           int32_t* m, int32_t* status);
 
+/* Dense search over candidate plane normals (BASELINE configs[4]): evaluates the same cost on a
+ * regular n_phi x n_theta grid of (phi, theta) = centre + ((i - (n_phi-1)/2) dphi, (j - (n_theta-1)/2) dtheta),
+ * candidate index c = i * n_theta + j, at pyramid level `level`.  The centre is center_phi_theta[f]
+ * (n x 2), or, when NULL, the optimiser's initial normal P/|P| (normaloptimizer.cpp:343).  One CTA
+ * group per feature stages rays, image-1 samples and the image-2 window once and then runs one
+ * value-only pass per candidate.
+ *   cost       n x n_phi*n_theta  (nullable; NaN where a candidate fails a bounding-box / pixel gate)
+ *   best_idx   n   argmin over the grid, -1 if no candidate is valid (nullable)
+ *   best_cost  n   (nullable)
+ *   status     n   FM3D_FEAT_OK / FM3D_FEAT_NO_PIXELS */
+int fm3d_sweep_normals(fm3d_ctx* ctx, const double* xyz, const double* center_phi_theta, int n,
+                       int pixels_ray, int level, int penalty_mode, int n_phi, int n_theta,
+                       double dphi, double dtheta, double* cost, int32_t* best_idx,
+                       double* best_cost, int32_t* status);
+int fm3d_sweep_normals_dev(fm3d_ctx* ctx, const double* xyz, const double* center_phi_theta, int n,
+                           int pixels_ray, int level, int penalty_mode, int n_phi, int n_theta,
+                           double dphi, double dtheta, double* cost, int32_t* best_idx,
+                           double* best_cost, int32_t* status);
+
 /* Replaces NormalOptimizer::computeFeaturesFrames (normaloptimizer.cpp:454-505):
  * frame = [x y z P; 0 0 0 1], z = n, x = normalize(g x z), y = normalize(z x x),
  * row-major 4x4 per feature.  gravity as NormalOptimizer::getGravity (:185-188). */

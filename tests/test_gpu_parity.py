@@ -169,14 +169,14 @@ def test_match_nndr_and_mutual(ctx, hamming):
 
 
 # ------------------------------------------------------------------ normals (K5-K7)
-@pytest.fixture(params=["fast-1group", "fast-2groups", "faithful"])
+@pytest.fixture(params=["fast-1group", "fast-2groups", "fast-4groups", "faithful"])
 def normals_kernel(request, ctx):
     """The implementations of the plane-normal search: fm3d_normals_fast.cu (default: fp32 offset
     geometry, analytic Jacobian) with one feature per CTA (rays in shared memory) or two feature
     pipelines per CTA (rays streamed from an L2-resident scratch), and fm3d_normals.cu (fp64,
     evaluation by evaluation)."""
     ctx.set_option("normals_fast", 0 if request.param == "faithful" else 1)
-    ctx.set_option("normals_groups", 2 if request.param == "fast-2groups" else 1)
+    ctx.set_option("normals_groups", {"fast-2groups": 2, "fast-4groups": 4}.get(request.param, 1))
     yield request.param
     ctx.set_option("normals_fast", 1)
     ctx.set_option("normals_groups", 0)
@@ -273,6 +273,85 @@ def test_optimize_normals_default_settings_r64(ctx, normals_kernel):
     assert (angle_deg(res["normals"], case["normal"])[ok] <= angle_deg(o["normals"], case["normal"])[ok] + 0.1).all()
     print(normals_kernel, "nfev gpu", res["nfev"].sum(0), "oracle", o["nfev"].sum(0), "max angle", ang[ok].max(),
           "median", np.median(ang[ok]))
+
+
+def test_sweep_normals_dense_candidate_grid(ctx):
+    """BASELINE configs[4] 'dense candidate-normal sampling': every grid point equals a single cost
+    evaluation at that (phi, theta) (bitwise: same kernel path) and the oracle's cost (1e-3)."""
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    xyz = case["X"][:10]
+    n0 = xyz / np.linalg.norm(xyz, axis=1, keepdims=True)
+    centre = car2sph(n0)
+    n_phi, n_theta, dphi, dtheta = 5, 3, 0.04, 0.03
+    for level in (0, 2):
+        sw = ctx.sweep_normals(xyz, 32, level, n_phi, n_theta, dphi, dtheta, penalty_mode=2)
+        sw2 = ctx.sweep_normals(xyz, 32, level, n_phi, n_theta, dphi, dtheta, center_phi_theta=centre, penalty_mode=2, want_cost=False)
+        assert (sw["status"] == 0).all()
+        np.testing.assert_array_equal(sw["best_idx"], sw2["best_idx"])     # default centre = the viewing ray
+        np.testing.assert_array_equal(sw["best_idx"], np.nanargmin(sw["cost"].reshape(len(xyz), -1), axis=1))
+        np.testing.assert_array_equal(sw["best_cost"], np.nanmin(sw["cost"].reshape(len(xyz), -1), axis=1))
+        ctx.set_option("normals_fast", 2)
+        try:
+            for i in (0, 2, 4):
+                for j in (0, 1, 2):
+                    pt = centre + np.array([(i - 2) * dphi, (j - 1) * dtheta])
+                    c, m, st = ctx.evaluate_normals(xyz, pt, 32, level, 2)
+                    np.testing.assert_array_equal(c, sw["cost"][:, i, j])
+                    oc, om, ost = orc.evaluate_cost(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, pt, 32, level, 2)
+                    ok = ost == 0
+                    np.testing.assert_allclose(c[ok], oc[ok], rtol=1e-3)
+        finally:
+            ctx.set_option("normals_fast", 1)
+
+
+def test_optimize_normals_large_disc_r128(ctx):
+    """pixelsRay 128 (BASELINE configs[4]): m = 51 433 pixels do not fit in shared memory -- rays and
+    image-1 samples stream from the L2-resident scratch and the level-0 window is wider than a TMA tile."""
+    case = stereo_case(1280, 720, 6, 1004, 128)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    xyz = case["X"]
+    res = ctx.optimize_normals(xyz, 128, 1e-10, 2)
+    o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, 128, 1e-10,
+                             penalty_mode=2, threads=8)
+    np.testing.assert_array_equal(res["status"], o["status"])
+    ok = o["status"] == 0
+    assert ok.sum() >= 4
+    ang = angle_deg(res["normals"], o["normals"])
+    st = ctx.normals_stats()
+    print("r=128 angles", np.round(ang[ok], 5), "global-tap passes", st["passes_slow"])
+    assert (ang[ok] <= 0.5).all()
+    assert st["passes_slow"] == 0        # the full-size window is staged: no pass falls back to global taps
+    np.testing.assert_allclose(res["cost"][ok], o["cost"][ok], rtol=0.01)
+
+
+def test_fast_kernel_schedule_options_do_not_change_results(ctx):
+    """Fusing the first trial with its Jacobian and answering coefficient-identical trials without a
+    pass are exact: same evaluations counted, bit-identical normals."""
+    case = stereo_case(640, 480, 40, 1001, 32)
+    setup_ctx(ctx, case, 2)
+    xyz = case["X"]
+    ctx.set_option("normals_groups", 1)
+    try:
+        base = ctx.optimize_normals(xyz, 32, 1e-10, 1)
+        st0 = ctx.normals_stats()
+        for key in ("normals_fuse", "normals_memo"):
+            ctx.set_option(key, 0)
+            try:
+                alt = ctx.optimize_normals(xyz, 32, 1e-10, 1)
+                st = ctx.normals_stats()
+            finally:
+                ctx.set_option(key, 1)
+            np.testing.assert_array_equal(alt["nfev"], base["nfev"])
+            np.testing.assert_array_equal(alt["normals"], base["normals"])
+            np.testing.assert_array_equal(alt["status"], base["status"])
+            passes = lambda s_: s_["passes_value"] + s_["passes_jacobian"] + s_["passes_fused"]
+            assert passes(st) > passes(st0)          # the option did save passes
+    finally:
+        ctx.set_option("normals_groups", 0)
+    assert st0["trials_memoized"] > 0 and st0["fused_accepted"] > 0
 
 
 def test_optimize_normals_fp32_geometry(ctx):

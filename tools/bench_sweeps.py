@@ -78,6 +78,17 @@ def normals_stress(ctx, stream, n_feat):
                               "pixel_evals_per_s": (st["pixel_evals_value"] + st["pixel_evals_jacobian"]) / (ms * 1e-3),
                               "tflops_fp32_algorithmic": flops / (ms * 1e-3) / 1e12, "passes_global_taps": st["passes_slow"],
                               "nfev_mean_per_level": nfev.float().mean(0).tolist()}), flush=True)
+            if pyr == 3:
+                # dense candidate-normal sampling: 33 x 33 grid around the initial normal at level 0
+                best = torch.empty(n, dtype=torch.int32, device=dev); bcost = torch.empty(n, dtype=torch.float64, device=dev)
+                nsw = min(n, 592)
+                fn2 = lambda: ctx.sweep_normals_dev(xyz.data_ptr(), nsw, r, 0, 33, 33, 0.01, 0.01, status.data_ptr(), penalty_mode=1,
+                                                    best_idx=best.data_ptr(), best_cost=bcost.data_ptr())
+                ms2 = timed(stream, fn2, 1)
+                print(json.dumps({"case": "normals_dense_sweep_33x33_level0", "pixels_ray": r, "m": m_disc, "features": nsw, "ms": ms2,
+                                  "pixel_evals_per_s": nsw * 1089.0 * m_disc / (ms2 * 1e-3),
+                                  "tflops_fp32_algorithmic": nsw * 1089.0 * m_disc * 64.0 / (ms2 * 1e-3) / 1e12,
+                                  "candidates_per_s": nsw * 1089.0 / (ms2 * 1e-3)}), flush=True)
 
 
 def c3_pipeline(ctx, stream):
