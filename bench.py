@@ -289,9 +289,9 @@ def run_gpu_arm(args):
                                      d_status.data_ptr(), d_nfev.data_ptr(), d_npen.data_ptr(), d_cost.data_ptr())
             if events: events[4].record(stream)
             if world > 1:
-                g_q, g_t, g_d, counts = shard.gather_matches(d_qi, d_ti, d_do, n_match, lo, nq)
-                g_n, _ = shard.gather_rows(d_normals, n_inl, nq)
-                g_s, _ = shard.gather_rows(d_status, n_inl, nq)
+                # one collective: (global query index, train index, distance) of the matches, normal and
+                # status of the inliers of every shard
+                shard.gather_packed([d_qi + lo, d_ti, d_do, d_normals, d_status], [n_match, n_match, n_match, n_inl, n_inl], nq)
             if events: events[5].record(stream)
         return n_match, n_inl
 

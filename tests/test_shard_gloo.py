@@ -30,8 +30,14 @@ def _worker(rank, world, port, ret):
     cap = max(shard.shard_sizes(q.shape[0], world))
     pad = lambda a, dt: torch.from_numpy(np.concatenate([a, np.zeros(cap - n, a.dtype)]).astype(dt))  # noqa: E731
     gq, gt, gd, counts = shard.gather_matches(pad(qi, np.int32), pad(ti, np.int32), pad(d, np.float32), n, lo, cap)
+    # the single-collective form the bench uses: same rows, plus a second result set with its own count
+    extra = torch.arange(cap * 3, dtype=torch.float64).reshape(cap, 3) + 1000.0 * rank
+    n_extra = max(n - 2, 0)
+    (pq, pt_, pd, pe), pc = shard.gather_packed([pad(qi, np.int32) + lo, pad(ti, np.int32), pad(d, np.float32), extra],
+                                                [n, n, n, n_extra], cap)
     if rank == 0:
         ret["q"], ret["t"], ret["d"], ret["counts"] = gq.numpy(), gt.numpy(), gd.numpy(), counts
+        ret["pq"], ret["pt"], ret["pd"], ret["pe"], ret["pc"] = pq.numpy(), pt_.numpy(), pd.numpy(), pe.numpy(), pc
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,3 +59,9 @@ def test_sharded_matching_equals_single_process():
         np.testing.assert_array_equal(ret["t"], ti)
         np.testing.assert_array_equal(ret["d"], d)
         assert sum(ret["counts"]) == len(qi)
+        np.testing.assert_array_equal(ret["pq"], qi)
+        np.testing.assert_array_equal(ret["pt"], ti)
+        np.testing.assert_array_equal(ret["pd"], d)
+        pc = ret["pc"]
+        assert [c[0] for c in pc] == list(ret["counts"]) and ret["pe"].shape == (sum(c[3] for c in pc), 3)
+        assert ret["pe"][0, 0] == 0.0 and ret["pe"][pc[0][3], 0] == 1000.0      # rank 1's block follows rank 0's valid rows
