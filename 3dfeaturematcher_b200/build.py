@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + os.environ.get("FM3D_EXTRA_NVCC", "").split() + ["-c", src, "-o", obj]
         p = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)

@@ -38,7 +38,13 @@ using namespace fm3d_normals;
 namespace fm3d_normals {
 namespace {
 
-constexpr int FAST_NT = 512;
+#ifndef FM3D_NORMALS_NT
+#define FM3D_NORMALS_NT 512
+#endif
+#ifndef FM3D_NORMALS_UNROLL2
+#define FM3D_NORMALS_UNROLL2 0
+#endif
+constexpr int FAST_NT = FM3D_NORMALS_NT;
 constexpr float FLOOR_MAGIC = 12582912.0f;          // 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x)
 constexpr unsigned FLOOR_MAGIC_BITS = 0x4B400000u;
 enum { FLAG_WINDOW = 8 };
@@ -352,6 +358,21 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
         ulonglong2 r = make_ulonglong2(0ull, 0ull);
         f2 I = 0ull;
         if (p < npair) { r = rp[p]; I = ip[p]; }
+#if FM3D_NORMALS_UNROLL2
+        ulonglong2 r2 = make_ulonglong2(0ull, 0ull);
+        f2 I2 = 0ull;
+        if (p + NT < npair) { r2 = rp[p + NT]; I2 = ip[p + NT]; }
+        for (; p + NT < npair; p += 2 * NT) {
+            const ulonglong2 cr = r, cr2 = r2;
+            const f2 cI = I, cI2 = I2;
+            const int nx = p + 2 * NT;
+            if (nx < npair) { r = rp[nx]; I = ip[nx]; }
+            if (nx + NT < npair) { r2 = rp[nx + NT]; I2 = ip[nx + NT]; }
+            eval_pixel_pair<JAC>(P, L, cr.x, cr.y, cI, acc, acc2);
+            eval_pixel_pair<JAC>(P, L, cr2.x, cr2.y, cI2, acc, acc2);
+        }
+        if (p < npair) eval_pixel_pair<JAC>(P, L, r.x, r.y, I, acc, acc2);
+#else
         for (; p < npair; p += NT) {
             const ulonglong2 cr = r;
             const f2 cI = I;
@@ -359,6 +380,7 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
             if (nx < npair) { r = rp[nx]; I = ip[nx]; }
             eval_pixel_pair<JAC>(P, L, cr.x, cr.y, cI, acc, acc2);
         }
+#endif
     } else {
         for (; p < npair; p += NT) {
             const ulonglong2 r = rp[p];
@@ -1086,10 +1108,11 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     struct Layout { int groups; bool rays_smem, i1_smem; };
     const Layout two_a = {2, false, true}, two_b = {2, false, false}, one_a = {1, true, true}, one_b = {1, false, false};
     const Layout four = {4, false, false};
-    Layout order[6];
+    Layout order[7];
     int n_order = 0;
     const int sms = ctx->prop.multiProcessorCount;
-    if (ctx->opt_normals_groups == 4 || (ctx->opt_normals_groups == 0 && A.n >= 8 * sms)) order[n_order++] = four;
+    if (ctx->opt_normals_groups == 3 && nt % 96 == 0) { const Layout three = {3, false, false}; order[n_order++] = three; }
+    if ((ctx->opt_normals_groups == 4 || (ctx->opt_normals_groups == 0 && A.n >= 8 * sms)) && nt % 128 == 0) order[n_order++] = four;
     const int want = ctx->opt_normals_groups;   // 0: automatic
     const bool prefer_two = want == 2 || (want == 0 && A.n > ctx->prop.multiProcessorCount);
     if (prefer_two) { order[n_order++] = two_a; order[n_order++] = two_b; }
