@@ -31,7 +31,8 @@ SYMBOLS = [
     "fm3d_nndr_filter_dev", "fm3d_triangulate", "fm3d_triangulate_dev", "fm3d_undistort_points",
     "fm3d_set_images", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
     "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_get_normals_stats",
-    "fm3d_sweep_normals", "fm3d_sweep_normals_dev", "fm3d_feature_frames",
+    "fm3d_sweep_normals", "fm3d_sweep_normals_dev",
+    "fm3d_disc_pixels", "fm3d_plane_points", "fm3d_sample_pixels", "fm3d_project_to_image2", "fm3d_feature_frames",
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
 ]
@@ -275,6 +276,40 @@ class Context:
                                                  int(level), int(penalty_mode), int(n_phi), int(n_theta), C.c_double(dphi),
                                                  C.c_double(dtheta), C.c_void_p(cost), C.c_void_p(best_idx),
                                                  C.c_void_p(best_cost), C.c_void_p(status)))
+
+    # ------------------------------------------------------------------ per-evaluation helpers
+    def disc_pixels(self, P, pixels_ray):
+        P = _arr(P, np.float64).reshape(3)
+        cap = (2 * int(pixels_ray) + 1) ** 2
+        xy = np.empty((cap, 2))
+        m = C.c_int()
+        self._ck(self.lib.fm3d_disc_pixels(self._h, _ptr(P, _dp), int(pixels_ray), _ptr(xy, _dp), cap, C.byref(m)))
+        return xy[:m.value].copy()
+
+    def plane_points(self, P, normal, xy):
+        P, normal = _arr(P, np.float64).reshape(3), _arr(normal, np.float64).reshape(3)
+        xy = _arr(xy, np.float64).reshape(-1, 2)
+        out = np.empty((xy.shape[0], 3))
+        info = C.c_int()
+        self._ck(self.lib.fm3d_plane_points(self._h, _ptr(P, _dp), _ptr(normal, _dp), _ptr(xy, _dp), xy.shape[0], _ptr(out, _dp), C.byref(info)))
+        return out, info.value
+
+    def sample_pixels(self, image, level, scale, xy, gate=True):
+        xy = _arr(xy, np.float64).reshape(-1, 2)
+        out = np.empty(xy.shape[0], np.float32)
+        info = C.c_int()
+        self._ck(self.lib.fm3d_sample_pixels(self._h, int(image), int(level), C.c_double(scale), int(bool(gate)), _ptr(xy, _dp),
+                                             xy.shape[0], out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(info)))
+        return out, info.value
+
+    def project_to_image2(self, xyz, level, scale, want_intensity=True):
+        xyz = _arr(xyz, np.float64).reshape(-1, 3)
+        xy2 = np.empty((xyz.shape[0], 2))
+        inten = np.empty(xyz.shape[0], np.float32) if want_intensity else None
+        info = C.c_int()
+        self._ck(self.lib.fm3d_project_to_image2(self._h, _ptr(xyz, _dp), xyz.shape[0], int(level), C.c_double(scale), _ptr(xy2, _dp),
+                                                 None if inten is None else inten.ctypes.data_as(C.POINTER(C.c_float)), C.byref(info)))
+        return xy2, inten, info.value
 
     def feature_frames(self, xyz, normals, gravity):
         xyz = _arr(xyz, np.float64).reshape(-1, 3)

@@ -298,6 +298,137 @@ void SingleCameraTriangulator::projectPointsToImage(const IMAGE_ID id, const std
     unpack_patches(n, S, p, ip, patchesVector, imagePointsVector, write_patch_files_);
 }
 
+// ---- the per-evaluation helpers (singlecameratriangulator.cpp:279-339, 341-397, 472-665)
+void SingleCameraTriangulator::extractPixelsContour(const cv::Vec3d& point, std::vector<Pixel>& pixels) {
+    const int cap = (2 * pixels_ray_ + 1) * (2 * pixels_ray_ + 1);
+    std::vector<double> xy((size_t)cap * 2);
+    int m = 0;
+    check(ctx_, fm3d_disc_pixels(ctx_, point.val, pixels_ray_, xy.data(), cap, &m), "disc_pixels");
+    pixels.clear();                                               // (:396)
+    pixels.reserve(m);
+    for (int i = 0; i < m; i++) { Pixel p = {xy[2 * i], xy[2 * i + 1], 0}; pixels.push_back(p); }
+}
+
+int SingleCameraTriangulator::get3dPointsFromImage1Pixels(const cv::Vec3d& point, const cv::Vec3d& normal, const cv::Mat& pixelMat,
+                                                          std::vector<cv::Vec3d>& pointsGroup) {
+    const int m = pixelMat.rows;                                  // m x 1 CV_64FC2
+    if (m == 0) return 0;
+    std::vector<double> xyz((size_t)m * 3);
+    int info = 0;
+    check(ctx_, fm3d_plane_points(ctx_, point.val, normal.val, (const double*)pixelMat.data, m, xyz.data(), &info), "plane_points");
+    if (info == -6) throw std::runtime_error("fm3d: NaN plane point (the reference exits with -6)");
+    const int cmax = (int)(2 * z_threshold_max_);                 // isInBoundingBox (:646-655)
+    for (int i = 0; i < m; i++) {
+        const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
+        if (!((X > -cmax && X < cmax) && (Y > -cmax && Y < cmax) && (Z > 0 && Z < cmax))) return -1;
+        pointsGroup.push_back(cv::Vec3d(X, Y, Z));
+    }
+    return 0;
+}
+
+void SingleCameraTriangulator::extractPixelsContourAndGet3DPoints(const cv::Vec3d& point, const cv::Vec3d& normal,
+                                                                  std::vector<Pixel>& pixels, std::vector<cv::Vec3d>& pointsGroup) {
+    extractPixelsContour(point, pixels);
+    const int m = (int)pixels.size();
+    if (m == 0) return;
+    std::vector<double> xy((size_t)m * 2), xyz((size_t)m * 3);
+    for (int i = 0; i < m; i++) { xy[2 * i] = pixels[i].x_; xy[2 * i + 1] = pixels[i].y_; }
+    int info = 0;
+    check(ctx_, fm3d_plane_points(ctx_, point.val, normal.val, xy.data(), m, xyz.data(), &info), "plane_points");
+    // no bounding-box gate here (:509-518); the debug drawing into test1.pgm (:520-525) is not reproduced
+    for (int i = 0; i < m; i++) pointsGroup.push_back(cv::Vec3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+}
+
+static bool pixel_good(double x, double y, double scale, int cols, int rows) {   // isPixelGood (:657-665)
+    return !((x < 0) || (x > ((1 / scale) * cols)) || (y < 0) || (y > ((1 / scale) * rows)));
+}
+
+int SingleCameraTriangulator::updateImage1PixelsIntensity(const double scale, std::vector<Pixel>& pixels) {
+    const int m = (int)pixels.size();
+    if (m == 0) return 0;
+    std::vector<double> xy((size_t)m * 2);
+    std::vector<float> inten(m);
+    for (int i = 0; i < m; i++) { xy[2 * i] = pixels[i].x_; xy[2 * i + 1] = pixels[i].y_; }
+    int info = 0;
+    check(ctx_, fm3d_sample_pixels(ctx_, 1, 0, scale, 1, xy.data(), m, inten.data(), &info), "sample_pixels");
+    for (int i = 0; i < m; i++) {
+        if (!pixel_good(pixels[i].x_, pixels[i].y_, scale, img_1_.cols, img_1_.rows)) return -1;
+        pixels[i].i_ = inten[i];
+    }
+    return 0;
+}
+
+int SingleCameraTriangulator::projectPointsToImage2(const std::vector<cv::Vec3d>& pointsGroup, const double scale,
+                                                    std::vector<Pixel>& pixels) {
+    const int m = (int)pointsGroup.size();
+    if (m == 0) return 0;
+    std::vector<double> xyz((size_t)m * 3), xy2((size_t)m * 2);
+    std::vector<float> inten(m);
+    for (int i = 0; i < m; i++) for (int c = 0; c < 3; c++) xyz[3 * i + c] = pointsGroup[i][c];
+    int info = 0;
+    check(ctx_, fm3d_project_to_image2(ctx_, xyz.data(), m, 0, scale, xy2.data(), inten.data(), &info), "project_to_image2");
+    for (int i = 0; i < m; i++) {
+        if (!pixel_good(xy2[2 * i], xy2[2 * i + 1], scale, img_1_.cols, img_1_.rows)) return -1;
+        Pixel p = {xy2[2 * i], xy2[2 * i + 1], inten[i]};
+        pixels.push_back(p);
+    }
+    return 0;
+}
+
+void SingleCameraTriangulator::projectPointsAndComputeResidual(const cv::Mat& pointsGroup, cv::Mat& imagePoints1, cv::Mat& imagePoints2,
+                                                               std::vector<double>& residualsVector) {
+    // single-group variant (:322-339): residual of the ROUNDED pixels, uchar arithmetic promoted to int
+    const int n = pointsGroup.cols;
+    if (n == 0) return;
+    std::vector<double> xyz((size_t)n * 3);
+    for (int k = 0; k < n; k++) for (int c = 0; c < 3; c++) xyz[3 * k + c] = pointsGroup.ptr<double>(c)[k];
+    imagePoints1 = cv::Mat(n, 1, CV_64FC2);
+    imagePoints2 = cv::Mat(n, 1, CV_64FC2);
+    std::vector<uint8_t> dummy((size_t)n);
+    // image 1: projectPoints with r = t = 0 (n groups of one point); image 2: with g12 (projectPointsToImages, :260-276)
+    check(ctx_, fm3d_project_groups(ctx_, 1, xyz.data(), n, 1, dummy.data(), (double*)imagePoints1.data), "project_groups");
+    int info = 0;
+    check(ctx_, fm3d_project_to_image2(ctx_, xyz.data(), n, 0, 1.0, (double*)imagePoints2.data, nullptr, &info), "project_to_image2");
+    for (int k = 0; k < n; k++) {
+        const double* p1 = imagePoints1.ptr<double>(k);
+        const double* p2 = imagePoints2.ptr<double>(k);
+        const int x1 = (int)std::round(p1[0]), y1 = (int)std::round(p1[1]), x2 = (int)std::round(p2[0]), y2 = (int)std::round(p2[1]);
+        const int a = (x1 >= 0 && y1 >= 0 && x1 < img_1_.cols && y1 < img_1_.rows) ? img_1_.ptr<uchar>(y1)[x1] : 0;
+        const int b = (x2 >= 0 && y2 >= 0 && x2 < img_2_.cols && y2 < img_2_.rows) ? img_2_.ptr<uchar>(y2)[x2] : 0;
+        residualsVector.push_back((double)(a - b));
+    }
+}
+
+void SingleCameraTriangulator::projectPointsAndComputeResidual(const std::vector<cv::Mat>& pointsGroupVector,
+                                                               std::vector<cv::Mat>& imagePointsVector1,
+                                                               std::vector<cv::Mat>& imagePointsVector2,
+                                                               std::vector<std::vector<double> >& residualsVectors) {
+    // vector variant (:279-320): bilinear samples of both images at the projected points
+    imagePointsVector1.clear();
+    imagePointsVector2.clear();
+    for (size_t g = 0; g < pointsGroupVector.size(); g++) {
+        const cv::Mat& pg = pointsGroupVector[g];
+        const int n = pg.cols;
+        std::vector<double> xyz((size_t)n * 3);
+        for (int k = 0; k < n; k++) for (int c = 0; c < 3; c++) xyz[3 * k + c] = pg.ptr<double>(c)[k];
+        cv::Mat ip1(n, 1, CV_64FC2), ip2(n, 1, CV_64FC2);
+        std::vector<float> i1(n), i2(n);
+        int info = 0;
+        if (n > 0) {
+            std::vector<uint8_t> dummy((size_t)n);
+            check(ctx_, fm3d_project_groups(ctx_, 1, xyz.data(), n, 1, dummy.data(), (double*)ip1.data), "project_groups");
+            check(ctx_, fm3d_project_to_image2(ctx_, xyz.data(), n, 0, 1.0, (double*)ip2.data, nullptr, &info), "project_to_image2");
+            check(ctx_, fm3d_sample_pixels(ctx_, 1, 0, 1.0, 0, (const double*)ip1.data, n, i1.data(), &info), "sample_pixels");
+            check(ctx_, fm3d_sample_pixels(ctx_, 2, 0, 1.0, 0, (const double*)ip2.data, n, i2.data(), &info), "sample_pixels");
+        }
+        imagePointsVector1.push_back(ip1);
+        imagePointsVector2.push_back(ip2);
+        std::vector<double> res(n);
+        for (int k = 0; k < n; k++) res[k] = (double)i1[k] - (double)i2[k];       // double pixel1 - double pixel2 (:305-309)
+        residualsVectors.push_back(res);
+    }
+}
+
 // ------------------------------------------------------------------------------ NormalOptimizer
 NormalOptimizer::NormalOptimizer(const cv::FileStorage settings, SingleCameraTriangulator* sct)
     : sct_(sct), penalty_mode_(FM3D_PENALTY_FABS) {

@@ -25,6 +25,28 @@ public:
     void setKeypoints(const std::vector<cv::KeyPoint>& kpts1, const std::vector<cv::KeyPoint>& kpts2, const std::vector<cv::DMatch>& matches);
     void triangulate(std::vector<cv::Vec3d>& triangulatedPoints, std::vector<bool>& outliersMask);
 
+    // Older residual formulation (singlecameratriangulator.cpp:279-339).  Point groups are 3 x N CV_64FC1
+    // (N = cols, as the reference counts them); image points come back as N x 1 CV_64FC2.
+    void projectPointsAndComputeResidual(const std::vector<cv::Mat>& pointsGroupVector, std::vector<cv::Mat>& imagePointsVector1,
+                                         std::vector<cv::Mat>& imagePointsVector2, std::vector<std::vector<double> >& residualsVectors);
+    void projectPointsAndComputeResidual(const cv::Mat& pointsGroup, cv::Mat& imagePoints1, cv::Mat& imagePoints2,
+                                         std::vector<double>& residualsVector);
+
+    // The four steps of NormalOptimizer::evaluateNormal (normaloptimizer.cpp:65-149), one by one.  They act
+    // on the images given to setImages (the reference passes one pyramid level at a time) with the
+    // caller's scale.  Return values as in the reference: 0, or -1 at the first point outside the
+    // bounding box / pixel that is not good (the output then holds the elements before it).
+    void extractPixelsContourAndGet3DPoints(const cv::Vec3d& point, const cv::Vec3d& normal, std::vector<Pixel>& pixels,
+                                            std::vector<cv::Vec3d>& pointsGroup);
+    void extractPixelsContour(const cv::Vec3d& point, std::vector<Pixel>& pixels);
+    int get3dPointsFromImage1Pixels(const cv::Vec3d& point, const cv::Vec3d& normal, const cv::Mat& pixelMat,
+                                    std::vector<cv::Vec3d>& pointsGroup);
+    inline void projectPointsToImage2(const std::vector<cv::Vec3d>& pointsGroup, std::vector<Pixel>& pixels) {
+        projectPointsToImage2(pointsGroup, 1.0, pixels);
+    }
+    int projectPointsToImage2(const std::vector<cv::Vec3d>& pointsGroup, const double scale, std::vector<Pixel>& pixels);
+    int updateImage1PixelsIntensity(const double scale, std::vector<Pixel>& pixels);
+
     void projectPointsToImage(const IMAGE_ID id, const std::vector<std::vector<cv::Vec3d> >& pointsGroupVector,
                               std::vector<cv::Mat>& patchesVector, std::vector<cv::Mat>& imagePointsVector);
     void projectReferencePointsToImageWithFrames(const std::vector<cv::Vec3d>& referenceNeighborhooh,

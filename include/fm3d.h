@@ -251,6 +251,36 @@ int fm3d_evaluate_normals(fm3d_ctx* ctx, const double* xyz, const double* normal
                           int n, int pixels_ray, int level, int penalty_mode, double* cost,
                           int32_t* m, int32_t* status);
 
+/* ---- the public per-evaluation helpers of SingleCameraTriangulator, one by one ----
+ * evaluateNormal (normaloptimizer.cpp:65-149) is built from four public methods; the normal-search
+ * kernels fuse them, these entry points keep them callable (element-wise kernels; host pointers).
+ * `info` mirrors the reference's return value: 0, -1 (a point left the bounding box / a pixel is
+ * not good), -6 (NaN plane point: the reference exit(-6)s, singlecameratriangulator.cpp:465-469). */
+
+/* SingleCameraTriangulator::extractPixelsContour(Vec3d) (singlecameratriangulator.cpp:341-397): the
+ * disc of image-1 pixels around the projection of P, in the reference's order (x offset outer loop),
+ * clipped to the image given to fm3d_set_images (the reference hard-codes 1024x768).  *m = number of
+ * pixels; at most `cap` are written to xy (m x 2). */
+int fm3d_disc_pixels(fm3d_ctx* ctx, const double P[3], int pixels_ray, double* xy, int cap, int* m);
+
+/* ::get3dPointsFromImage1Pixels (:530-565) with projectPointToPlane (:421-470) and isInBoundingBox
+ * (:646-655): undistort every pixel, intersect its ray with the plane (P, normal).  All m points are
+ * written (the reference stops at the first one outside the box). */
+int fm3d_plane_points(fm3d_ctx* ctx, const double P[3], const double normal[3], const double* xy, int m,
+                      double* xyz, int* info);
+
+/* ::updateImage1PixelsIntensity (:576-589) for image = 1; the same sampler on image 2.  Samples
+ * pyramid level `level` of the image at (float)(scale x), (float)(scale y) with
+ * getBilinearInterpPix32f (tools.cpp:129-142); gate != 0 applies isPixelGood (:657-665). */
+int fm3d_sample_pixels(fm3d_ctx* ctx, int image, int level, double scale, int gate, const double* xy, int m,
+                       float* intensity, int* info);
+
+/* ::projectPointsToImage2 (:591-632): cv::projectPoints with g12, isPixelGood, bilinear sample of
+ * image 2 at pyramid level `level`.  intensity may be NULL (projection only, no gate: the first half of
+ * projectPointsToImages, :232-276). */
+int fm3d_project_to_image2(fm3d_ctx* ctx, const double* xyz, int m, int level, double scale, double* xy2,
+                           float* intensity, int* info);
+
 /* Dense search over candidate plane normals (BASELINE configs[4]): evaluates the same cost on a
  * regular n_phi x n_theta grid of (phi, theta) = centre + ((i - (n_phi-1)/2) dphi, (j - (n_theta-1)/2) dtheta),
  * candidate index c = i * n_theta + j, at pyramid level `level`.  The centre is center_phi_theta[f]

@@ -97,6 +97,23 @@ int main(int argc, char** argv) {
     for (int i = 0; i < nn; i++) fwrite(neighborhoodsVector[i][S * S - 1].val, 8, 3, o);
     cv::Vec3d g = no.getGravity();
     fwrite(g.val, 8, 3, o);
+    // evaluateNormal (normaloptimizer.cpp:65-149) by hand through the four public helpers of
+    // SingleCameraTriangulator, for the first surviving feature at its refined normal, full resolution
+    int hm = 0, rc1 = 0, rc2 = 0, rc3 = 0;
+    double hcost = 0;
+    if (nn > 0) {
+        std::vector<Pixel> px, px2;
+        std::vector<cv::Vec3d> pts;
+        sct.extractPixelsContour(triagulated[0], px);
+        hm = (int)px.size();
+        cv::Mat pixelMat(hm, 1, CV_64FC2);
+        for (int i = 0; i < hm; i++) { pixelMat.ptr<double>(i)[0] = px[i].x_; pixelMat.ptr<double>(i)[1] = px[i].y_; }
+        rc1 = sct.get3dPointsFromImage1Pixels(triagulated[0], normalsVector[0], pixelMat, pts);
+        rc2 = sct.updateImage1PixelsIntensity(1.0, px);
+        rc3 = sct.projectPointsToImage2(pts, 1.0, px2);
+        for (size_t i = 0; i < px2.size() && i < px.size(); i++) { const double d = (double)(px[i].i_ - px2[i].i_); hcost += d * d; }
+    }
+    fwrite(&hm, 4, 1, o); fwrite(&rc1, 4, 1, o); fwrite(&rc2, 4, 1, o); fwrite(&rc3, 4, 1, o); fwrite(&hcost, 8, 1, o);
     fclose(o);
     std::cout << nm << " matches, " << np << " inliers, " << nn << " normals, patches " << S << "x" << S << std::endl;
     return 0;

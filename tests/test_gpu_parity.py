@@ -275,6 +275,58 @@ def test_optimize_normals_default_settings_r64(ctx, normals_kernel):
           "median", np.median(ang[ok]))
 
 
+def test_per_evaluation_helpers_against_oracle(ctx):
+    """extractPixelsContour / get3dPointsFromImage1Pixels / updateImage1PixelsIntensity /
+    projectPointsToImage2 as stand-alone entry points, against the cv2-based restatement, and
+    chained by hand against the fused cost kernel."""
+    from oracle import oracle_cv as ocv
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    setup_ctx(ctx, case, 2)
+    ccam = ocv.Camera(cam.K, cam.dist, cam.z_min, cam.z_max, g12=cam.g12)
+    pyr1, pyr2 = ocv.compute_pyramids(case["scene"].img1, 2), ocv.compute_pyramids(case["scene"].img2, 2)
+    H, W = case["scene"].img1.shape
+    for f, level in ((0, 0), (3, 1), (7, 2)):
+        P = case["X"][f]
+        n = P / np.linalg.norm(P)
+        n = n + np.array([0.05, -0.03, 0.0]); n /= np.linalg.norm(n)
+        scale = 1.0 / (1 << level)
+        pix = ctx.disc_pixels(P, 32)
+        o_pix = ocv.extract_pixels_contour(ccam, P, 32, W, H)
+        np.testing.assert_allclose(pix, o_pix, rtol=0, atol=1e-9)          # same pixels, same (x-outer) order
+        pts, info = ctx.plane_points(P, n, pix)
+        u = ocv.undistort_points(ccam, o_pix)
+        v = np.concatenate([u, np.ones((u.shape[0], 1))], axis=1)
+        o_pts = (float(n @ P) / (v @ n))[:, None] * v
+        assert info == 0
+        np.testing.assert_allclose(pts, o_pts, rtol=1e-12, atol=1e-12)
+        i1, info = ctx.sample_pixels(1, level, scale, pix)
+        assert info == 0
+        np.testing.assert_array_equal(i1, ocv.bilinear32f(pyr1[level], scale * o_pix[:, 0], scale * o_pix[:, 1]))
+        xy2, i2, info = ctx.project_to_image2(pts, level, scale)
+        r2, t2 = ocv.decompose_transformation(cam.g12)
+        o_xy2 = ocv.project_points(ccam, o_pts, r2, t2)
+        assert info == 0
+        np.testing.assert_allclose(xy2, o_xy2, rtol=0, atol=1e-9)
+        o_i2 = ocv.bilinear32f(pyr2[level], scale * o_xy2[:, 0], scale * o_xy2[:, 1])
+        assert (i2 != o_i2).mean() < 2e-3                                  # float-cast boundaries of the coordinates only
+        # chained by hand == the fused kernel's cost
+        ctx.set_option("normals_fast", 0)
+        try:
+            pt = car2sph(n[None])
+            cost, m, st = ctx.evaluate_normals(P[None], pt, 32, level, 2)
+        finally:
+            ctx.set_option("normals_fast", 1)
+        assert m[0] == pix.shape[0] and st[0] == 0
+        np.testing.assert_allclose(((i1.astype(np.float64) - i2.astype(np.float64)) ** 2).sum(), cost[0], rtol=1e-6)
+    # gates: a plane almost parallel to the rays leaves the bounding box; a point behind image 2's border is not good
+    P = case["X"][0]
+    pts, info = ctx.plane_points(P, np.array([1.0, 0.0, 0.02]) / np.hypot(1.0, 0.02), ctx.disc_pixels(P, 32))
+    assert info == -1
+    xy2, i2, info = ctx.project_to_image2(np.array([[5.0, 0.0, 2.0]]), 0, 1.0)
+    assert info == -1
+
+
 def test_sweep_normals_dense_candidate_grid(ctx):
     """BASELINE configs[4] 'dense candidate-normal sampling': every grid point equals a single cost
     evaluation at that (phi, theta) (bitwise: same kernel path) and the oracle's cost (1e-3)."""

@@ -131,8 +131,10 @@ def _read_result(path):
     patches = np.frombuffer(b, np.uint8, nn * S * S, o).reshape(nn, S, S); o += nn * S * S
     last_nb = np.frombuffer(b, np.float64, 3 * nn, o).reshape(-1, 3); o += 24 * nn
     gravity = np.frombuffer(b, np.float64, 3, o); o += 24
+    hm, rc1, rc2, rc3 = struct.unpack_from("iiii", b, o); o += 16
+    hcost = struct.unpack_from("d", b, o)[0]; o += 8
     assert o == len(b)
-    return dict(matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
+    return dict(helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
                 patches=patches, last_nb=last_nb, gravity=gravity, S=S)
 
 
@@ -179,6 +181,15 @@ def test_main_cpp_call_sequence_on_the_adapters(tmp_path):
     o_patches, _ = orc.extract_patches(cam.K, cam.dist, case["scene"].img1, res["frames"], eps_m, cmpp, want_points=False)
     diff = res["patches"].astype(int) - o_patches.astype(int)
     assert (np.abs(diff) <= 1).all() and (diff != 0).mean() < 1e-3
+    # the four public per-evaluation helpers chained by hand == one evaluateNormal of the oracle
+    h = res["helpers"]
+    assert h["rc"] == (0, 0, 0)
+    pt = np.array([[np.arctan2(res["normals"][0, 1], res["normals"][0, 0]),
+                    np.arctan2(res["normals"][0, 2], np.hypot(res["normals"][0, 0], res["normals"][0, 1]))]])
+    oc, om, ost = orc.evaluate_cost(cam.K, cam.dist, res["g12"], cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                                    pyramids, res["kept"][:1], pt, r, 0, 2)
+    assert h["m"] == om[0] and ost[0] == 0
+    np.testing.assert_allclose(h["cost"], oc[0], rtol=1e-6)
     # computeSquareNeighborhoodsByNormals: last grid point of every feature
     S = res["S"]
     ref_last = np.array([-eps_m + 0.01 * cmpp * (S - 1), -eps_m + 0.01 * cmpp * (S - 1), 0.0, 1.0])
