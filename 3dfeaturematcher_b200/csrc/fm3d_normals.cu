@@ -213,6 +213,9 @@ normals_kernel(const __grid_constant__ NormalsArgs A) {
             rows->nrows = 2 * r + 1;
             S->m = acc;
             S->status = acc > 0 ? FM3D_FEAT_OK : FM3D_FEAT_NO_PIXELS;
+            // a non-finite centre passes every `p < 0 || p >= size` test of the reference's lattice loop,
+            // the feature then dies in its first evaluation with a NaN plane point
+            if (cu != cu || cv != cv) S->status = FM3D_FEAT_ABORT_NAN;
             S->npenalty = 0;
             S->P[0] = Px; S->P[1] = Py; S->P[2] = Pz;
             const double nrm = sqrt(Px * Px + Py * Py + Pz * Pz);

@@ -657,6 +657,9 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             S->first_row = first; S->last_row = last;
             S->m = acc;
             S->status = acc > 0 ? FM3D_FEAT_OK : FM3D_FEAT_NO_PIXELS;
+            // a non-finite centre passes every `p < 0 || p >= size` test of the reference's lattice loop,
+            // the feature then dies in its first evaluation with a NaN plane point
+            if (cu != cu || cv != cv) S->status = FM3D_FEAT_ABORT_NAN;
             S->alive = acc > 0;
             S->npenalty = 0;
             for (int k = 0; k < 16; k++) S->stats[k] = 0;

@@ -275,6 +275,40 @@ def test_optimize_normals_default_settings_r64(ctx, normals_kernel):
           "median", np.median(ang[ok]))
 
 
+@pytest.mark.parametrize("fast", [1, 0])
+def test_optimize_normals_edge_inputs(ctx, fast):
+    """Empty input, non-finite points, points behind the camera, a single pyramid image, five
+    pyramid images, the smallest disc: statuses as the oracle's, no crash, no hang."""
+    case = stereo_case(640, 480, 40, 1001, 32)
+    cam = case["scene"].cam
+    ctx.set_option("normals_fast", fast)
+    try:
+        setup_ctx(ctx, case, 2)
+        res = ctx.optimize_normals(np.zeros((0, 3)), 32, 1e-10, 2)
+        assert res["normals"].shape == (0, 3) and res["status"].shape == (0,)
+        bad = np.array([[np.nan, 0.1, 1.9], [0.1, np.inf, 1.9], [0.0, 0.0, -1.9], [0.0, 0.0, 0.0], [1e9, 1e9, 1.0]])
+        xyz = np.concatenate([case["X"][:2], bad, case["X"][2:4]])
+        res = ctx.optimize_normals(xyz, 32, 1e-10, 2)
+        o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, 2, xyz, 32, 1e-10, penalty_mode=2, threads=4)
+        print("edge statuses gpu", res["status"], "oracle", o["status"])
+        good = [0, 1, 7, 8]
+        np.testing.assert_array_equal(res["status"], o["status"])
+        assert (res["status"][2:7] != 0).all()                                        # every degenerate point is dropped
+        assert (angle_deg(res["normals"][good], o["normals"][good]) <= 0.5).all()
+        for pyramids, r in ((0, 32), (5, 32), (2, 1), (2, 3)):
+            setup_ctx(ctx, case, pyramids)
+            xyz = case["X"][:6]
+            res = ctx.optimize_normals(xyz, r, 1e-10, 2)
+            o = orc.optimize_normals(*cam_tuple(cam), case["scene"].img1, case["scene"].img2, pyramids, xyz, r, 1e-10,
+                                     penalty_mode=2, threads=4)
+            np.testing.assert_array_equal(res["status"], o["status"])
+            assert res["nfev"].shape == (6, pyramids + 1)
+            if r >= 16:
+                assert (angle_deg(res["normals"], o["normals"])[o["status"] == 0] <= 0.5).all()
+    finally:
+        ctx.set_option("normals_fast", 1)
+
+
 def test_per_evaluation_helpers_against_oracle(ctx):
     """extractPixelsContour / get3dPointsFromImage1Pixels / updateImage1PixelsIntensity /
     projectPointsToImage2 as stand-alone entry points, against the cv2-based restatement, and
