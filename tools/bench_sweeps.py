@@ -45,7 +45,9 @@ def match_sweep(ctx, stream, sizes):
                           "note": "includes operand re-tiling (tc_prep) and finalize"}), flush=True)
         ms = timed(stream, lambda: ctx.match_knn2_hamming_dev(qb.data_ptr(), n, tb.data_ptr(), n, 32, idx.data_ptr(), dist.data_ptr()), reps)
         print(json.dumps({"case": "match_hamming_orb256_popc", "nq": n, "nt": n, "ms": ms, "pairs_per_s": n * n / (ms * 1e-3),
-                          "word_ops_per_s": 8.0 * n * n / (ms * 1e-3)}), flush=True)
+                          "word_ops_per_s": 8.0 * n * n / (ms * 1e-3),
+                          "frac_of_measured_popc_peak": 8.0 * n * n / (ms * 1e-3) / 4.54e12,
+                          "note": "POPC roofline 4.54e12/s measured with tools/micro/popc_rate.cu (16 lanes/clk/SM)"}), flush=True)
 
 
 def normals_stress(ctx, stream, n_feat):
