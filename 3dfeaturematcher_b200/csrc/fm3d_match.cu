@@ -377,7 +377,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -387,7 +387,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Running top-2 of one query row over 32 accumulator columns.  The group minimum is a tree (depth 5,
+// FMNMX3 where the compiler finds it) rather than a 31-deep dependent chain: with one epilogue warp
+// per scheduler the chain latency, not the issue rate, was what kept the tensor pipe waiting.
+__device__ __forceinline__ void top2_chunk(const uint32_t (&v)[32], int col0, float& m0, int& i0, float& m1, int& i1) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        p[j] = fminf(fminf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                     fminf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+    const float gmin = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), fminf(fminf(p[4], p[5]), fminf(p[6], p[7])));
+    if (gmin < m1) {
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const float d = __uint_as_float(v[k]);
+            if (d < m1) {   // ascending index scan: strict < keeps the lower index on ties
+                const int j = col0 + k;
+                if (d < m0) { m1 = m0; i1 = i0; m0 = d; i0 = j; }
+                else { m1 = d; i1 = j; }
+            }
+        }
+    }
 }
 
 // grid = (query tiles of 128, train splits).  qa / tb: re-tiled operands (tc_prep_kernel).
@@ -472,24 +495,20 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
             mbar_wait(&acc_full[acc], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const int col_base = (tile_lo + it) * TC_N;
+            // two register buffers: the tcgen05.ld of the next 32 columns is in flight while the
+            // current 32 are scanned
+            const uint32_t t0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * TC_N);
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(t0, va);
+            tmem_ld_wait();
 #pragma unroll 1
-            for (int c = 0; c < TC_N / 32; c++) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * TC_N + c * 32), v);
-                float gmin = __uint_as_float(v[0]);
-#pragma unroll
-                for (int k = 1; k < 32; k++) gmin = fminf(gmin, __uint_as_float(v[k]));
-                if (gmin < m1) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) {
-                        const float d = __uint_as_float(v[k]);
-                        if (d < m1) {   // ascending index scan: strict < keeps the lower index on ties
-                            const int j = col_base + c * 32 + k;
-                            if (d < m0) { m1 = m0; i1 = i0; m0 = d; i0 = j; }
-                            else { m1 = d; i1 = j; }
-                        }
-                    }
-                }
+            for (int c = 0; c < TC_N / 32; c += 2) {
+                tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
+                top2_chunk(va, col_base + c * 32, m0, i0, m1, i1);
+                tmem_ld_wait();
+                if (c + 2 < TC_N / 32) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+                top2_chunk(vb, col_base + (c + 1) * 32, m0, i0, m1, i1);
+                tmem_ld_wait();
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);

@@ -169,7 +169,7 @@ if __name__ == "__main__":
     ctx = api.Context(0)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", 0))
     if which in ("all", "match"):
-        match_sweep(ctx, stream, [10000, 50000, 100000, 200000])
+        match_sweep(ctx, stream, [int(a) for a in sys.argv[2:]] if which == "match" and len(sys.argv) > 2 else [10000, 50000, 100000, 200000])
     if which in ("all", "normals"):
         normals_stress(ctx, stream, int(sys.argv[2]) if len(sys.argv) > 2 else 2000)
     if which in ("c3",):
