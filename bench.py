@@ -171,7 +171,7 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     case = make_workload(1, 0)
-    n_sample = max(2 * threads, 32)
+    n_sample = max(16 * threads, 256)       # a seeded random subset of >= 256 features
     vals, t_all = [], []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -419,7 +419,10 @@ def run_gpu_arm(args):
         roofline = {
             "kernel": "normals_fast_kernel<true> (K6: LM normal search, one persistent CTA per SM, one feature per CTA at a time)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload under `ncu --set full`
+            # (profiles/r01c_normals_fast_kernel_ncu_raw_selected.csv: 325 MB + 702 MB, the L2-resident ray scratch
+            # being written back); 0.7 % of DRAM throughput -- the kernel is not HBM-bound
+            "traffic": 1.0275e9, "traffic_unit": "bytes per launch (ncu, round-1 capture)",
             "note": "compute-bound kernel (SURVEY 8d): algorithmic flops = 64 x value-only pixel evaluations + 152 x "
                     "value+analytic-Jacobian pixel evaluations executed (counted by the kernel) / CUDA-event time; peak = "
                     "measured FFMA rate (tools/micro/ffma2_rate.cu: 73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; "
@@ -441,8 +444,8 @@ def run_gpu_arm(args):
             "pyrdown": {"bound": "hbm", "achieved": pyr_bytes / (stage_ms[2] / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
                         "unit": "GB/s", "ms": stage_ms[2] / args.steps, "note": "3 launches + 2 device copies of 0.9 MB images: launch-bound"},
         }
-        cpu = cpu_reference(case, max(2 * (os.cpu_count() or 1), 32), os.cpu_count() or 1) if world == 1 else None
-        cpu_alt = cpu_reference(case, max(os.cpu_count() or 1, 16), os.cpu_count() or 1, penalty=PENALTY_ALT) if world == 1 else None
+        cpu = cpu_reference(case, max(16 * (os.cpu_count() or 1), 256), os.cpu_count() or 1) if world == 1 else None
+        cpu_alt = cpu_reference(case, max(8 * (os.cpu_count() or 1), 128), os.cpu_count() or 1, penalty=PENALTY_ALT) if world == 1 else None
         value = tot_feat * args.steps / (t_dev_ms * 1e-3)
         out = {
             "metric": "features/sec (match+triangulate+normal-opt)", "value": value, "unit": "features/s",
