@@ -168,6 +168,60 @@ def test_match_nndr_and_mutual(ctx, hamming):
     assert inl.mean() > 0.95 and (ti[inl] == gt[qi][inl]).all()
 
 
+def test_match_full_size_properties(ctx):
+    """BASELINE configs[3] at its largest size (200 k x 200 k) through size-independent properties:
+    a set matched against itself returns every descriptor as its own nearest neighbour at distance
+    0, with the second neighbour a different index; 64 random queries agree bit-exactly with the CPU
+    oracle over the full train set.  Float (tcgen05 path) and binary (popc path)."""
+    n = 200_000
+    rng = np.random.default_rng(2003)
+    t = rng.integers(0, 256, (n, 128)).astype(np.float32)
+    idx, dist = ctx.match_knn2_f32(t, t)
+    assert (idx[:, 0] == np.arange(n)).all() and (dist[:, 0] == 0).all()
+    assert (idx[:, 1] != np.arange(n)).all() and (dist[:, 1] > 0).all()
+    sel = rng.choice(n, 64, replace=False)
+    q = np.clip(t[sel] + rng.integers(-8, 9, (64, 128)), 0, 255).astype(np.float32)
+    gi, gd = ctx.match_knn2_f32(q, t)
+    oi, od = orc.knn2_f32(q, t, threads=8)
+    np.testing.assert_array_equal(gi, oi)
+    np.testing.assert_array_equal(gd, od)
+    tb = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    idx, dist = ctx.match_knn2_hamming(tb, tb)
+    assert (dist[:, 0] == 0).all() and (dist[:, 1] >= dist[:, 0]).all()
+    dup = idx[:, 0] != np.arange(n)                 # exact duplicates in the random set: the lower index wins
+    assert dup.sum() <= 4 and (idx[dup, 0] < np.arange(n)[dup]).all()
+    qb = tb[sel].copy(); qb[:, :3] ^= 0x5A
+    gi, gd = ctx.match_knn2_hamming(qb, tb)
+    oi, od = orc.knn2_hamming(qb, tb, threads=8)
+    np.testing.assert_array_equal(gi, oi)
+    np.testing.assert_array_equal(gd, od)
+
+
+def test_normal_search_at_bench_scale_properties(ctx):
+    """2 000 features of the 1280x720 bench scene (every group layout the scheduler picks): all survive,
+    no pass falls back to global taps, the refined normals are within 0.05 deg (median) of ground truth,
+    every level stays below lmfit's evaluation cap, and the 1-group and 4-group layouts agree."""
+    case = stereo_case(1280, 720, 2000, 1001, 64)
+    setup_ctx(ctx, case, 3)
+    xyz = case["X"]
+    out = {}
+    for groups in (1, 4, 0):
+        ctx.set_option("normals_groups", groups)
+        try:
+            out[groups] = ctx.optimize_normals(xyz, 64, 1e-10, 1)
+            st = ctx.normals_stats()
+        finally:
+            ctx.set_option("normals_groups", 0)
+        res = out[groups]
+        assert (res["status"] == 0).all() and st["passes_slow"] == 0 and st["features"] == xyz.shape[0]
+        gt = angle_deg(res["normals"], case["normal"])
+        assert np.median(gt) < 0.05 and np.percentile(gt, 99) < 0.5, (np.median(gt), np.percentile(gt, 99))
+        assert (res["nfev"] <= 300 + 2).all() and (res["nfev"] >= 4).all()
+        np.testing.assert_allclose(np.linalg.norm(res["normals"], axis=1), 1.0, atol=1e-12)
+    ang = angle_deg(out[1]["normals"], out[4]["normals"])
+    assert np.percentile(ang, 99) < 0.05 and np.median(ang) < 0.005, (np.median(ang), ang.max())
+
+
 # ------------------------------------------------------------------ normals (K5-K7)
 @pytest.fixture(params=["fast-1group", "fast-2groups", "fast-4groups", "faithful"])
 def normals_kernel(request, ctx):
