@@ -9,7 +9,7 @@
  * Why it exists: the reference cannot be compiled in this image (needs OpenCV 2.4 C++ with
  * `nonfree`, PCL, Boost, lmfit), and oracle/oracle_cv.py (Python on real cv2 calls) is too
  * slow to check thousands of features or to serve as the same-run CPU baseline.  This file
- * restates the same arithmetic without OpenCV, function by function; tests/test_oracle_c.py
+ * restates the same arithmetic without OpenCV, function by function; tests/test_oracle_pins.py and tests/test_golden_oracle.py
  * pins it against oracle_cv.py (i.e. against cv2.undistortPoints / triangulatePoints /
  * projectPoints / pyrDown / BFMatcher) and against the committed tests/golden vectors.
  *

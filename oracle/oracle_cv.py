@@ -24,7 +24,7 @@ line and delegates to `cv2` wherever the reference delegates to `cv::`:
 Pinned by: the cv2 calls themselves (this module IS the reference's arithmetic wherever the
 reference calls OpenCV); the hand-written parts (disc lattice, ray/plane intersection,
 bilinear sampler, penalty weight, frames, patch layout) are short restatements checked by
-tests/test_oracle_*.py on analytic scenes.  The LM library boundary is unpinned (see
+tests/test_oracle_pins.py on analytic scenes.  The LM library boundary is unpinned (see
 oracle/lmmin_py.py).  Documented deviations from the reference as written:
   D1  the 1024x768 bound hard-coded at singlecameratriangulator.cpp:359 is the image size;
   D2  the sampler reads a continuous cv::Mat with flat addressing like at<uchar>() without
