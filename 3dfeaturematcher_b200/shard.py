@@ -61,34 +61,46 @@ def gather_matches(qidx_local: torch.Tensor, tidx: torch.Tensor, dist_: torch.Te
     return q, t, d, counts
 
 
-def gather_packed(parts, counts, max_count: int):
+def gather_packed(parts, counts, max_count: int, unpack: bool = True):
     """ONE collective for all per-shard results of a step.
 
     parts:  tensors of shape (>= max_count, ...) (any dtypes); counts[i] = valid rows of parts[i].
     Every rank contributes a header with its counts plus the first `max_count` rows of every part
-    as raw bytes; returns a list (one entry per part) of the valid rows of all ranks concatenated
-    in rank order, and the per-rank counts (world x len(parts)).
+    as raw bytes.  With unpack=True returns (list with, per part, the valid rows of all ranks
+    concatenated in rank order; per-rank counts, world x len(parts)).  With unpack=False returns the
+    gathered (world x bytes) buffer and the layout needed by `unpack_packed` -- no host
+    synchronisation, which is what a latency-sensitive caller wants inside its step.
     """
     world = dist.get_world_size() if dist.is_initialized() else 1
-    if world == 1:
-        return [p[:c].clone() for p, c in zip(parts, counts)], [list(counts)]
     dev = parts[0].device
-    header = torch.tensor(list(counts), dtype=torch.int64, device=dev).view(torch.uint8)
+    header = torch.tensor(list(counts), dtype=torch.int64, device="cpu").to(dev, non_blocking=True).view(torch.uint8)
     blobs = [header] + [p[:max_count].contiguous().view(torch.uint8).reshape(-1) for p in parts]
-    sizes = [b.numel() for b in blobs]
+    layout = {"sizes": [b.numel() for b in blobs], "dtypes": [p.dtype for p in parts],
+              "rows": [(max_count,) + tuple(p.shape[1:]) for p in parts], "world": world}
     buf = torch.cat(blobs)
     out = torch.empty((world, buf.numel()), dtype=torch.uint8, device=dev)
-    dist.all_gather(list(out.unbind(0)), buf)     # equal-sized blocks: one ncclAllGather on the GPU box, portable to gloo
+    if world == 1:
+        out[0].copy_(buf)
+    else:
+        dist.all_gather(list(out.unbind(0)), buf)     # equal-sized blocks: one ncclAllGather on the GPU box, portable to gloo
+    if not unpack:
+        return out, layout
+    return unpack_packed(out, layout)
+
+
+def unpack_packed(out: torch.Tensor, layout):
+    """Host-side view of a gather_packed(..., unpack=False) result (synchronises once for the counts)."""
+    sizes, world, nparts = layout["sizes"], layout["world"], len(layout["dtypes"])
     offs = [0]
     for z in sizes:
         offs.append(offs[-1] + z)
-    all_counts = out[:, :sizes[0]].clone().view(torch.int64).reshape(world, len(parts)).cpu().tolist()
+    all_counts = out[:, :sizes[0]].clone().view(torch.int64).reshape(world, nparts).cpu().tolist()
     res = []
-    for i, p in enumerate(parts):
-        row = (max_count,) + tuple(p.shape[1:])
+    for i in range(nparts):
         chunks = []
         for r in range(world):
-            blk = out[r, offs[i + 1]:offs[i + 2]].clone().view(p.dtype).reshape(row)   # clone: aligned storage for the wider view
+            # clone: aligned storage for the wider view
+            blk = out[r, offs[i + 1]:offs[i + 2]].clone().view(layout["dtypes"][i]).reshape(layout["rows"][i])
             chunks.append(blk[:all_counts[r][i]])
         res.append(torch.cat(chunks, dim=0))
     return res, all_counts

