@@ -104,6 +104,16 @@ struct LevelConst {
     int w, h, pitch;
 };
 
+constexpr int MAX_GROUPS = 4;
+struct GroupCtl {
+    RowTable rows;
+    double red[16 * 6];
+    unsigned wflags[16];
+    FastShared S;
+    FastPass PP;
+    uint64_t bar;
+};
+
 __device__ __forceinline__ float rcp_nr(float a) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
@@ -578,18 +588,17 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
     } else {
         i1 = A.i1_g + slot * A.mcap;
     }
-    tail = reinterpret_cast<uint8_t*>(((uintptr_t)tail + 15) & ~(uintptr_t)15);
-    RowTable* rows = reinterpret_cast<RowTable*>(tail);
-    tail += (sizeof(RowTable) + 15) & ~(size_t)15;
-    double* red = reinterpret_cast<double*>(tail);        // [16 warps][6]
-    tail += sizeof(double) * 16 * 6;
-    unsigned* wflags = reinterpret_cast<unsigned*>(tail);  // [16 warps]
-    tail += sizeof(unsigned) * 16;
-    FastShared* S = reinterpret_cast<FastShared*>(tail);
-    tail += (sizeof(FastShared) + 15) & ~(size_t)15;
-    FastPass* PP = reinterpret_cast<FastPass*>(tail);
-    tail += (sizeof(FastPass) + 15) & ~(size_t)15;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+    // per-group control state in STATIC shared memory: the compiler then knows the address space
+    // (LDS/STS with immediate offsets instead of generic loads with 64-bit address arithmetic), which
+    // matters most in the single-lane LM step
+    __shared__ GroupCtl ctl[MAX_GROUPS];
+    GroupCtl& G = ctl[g];
+    RowTable* rows = &G.rows;
+    double* red = G.red;            // [16 warps][6]
+    unsigned* wflags = G.wflags;    // [16 warps]
+    FastShared* S = &G.S;
+    FastPass* PP = &G.PP;
+    uint64_t* bar = &G.bar;
 
     const int lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
     const fm3d_cam& cam = A.cam;
@@ -1070,10 +1079,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
     }
 }
 
-size_t fast_tail_bytes() {
-    return 16 + ((sizeof(RowTable) + 15) & ~(size_t)15) + sizeof(double) * 16 * 6 + sizeof(unsigned) * 16 +
-           ((sizeof(FastShared) + 15) & ~(size_t)15) + ((sizeof(FastPass) + 15) & ~(size_t)15) + 16;
-}
+size_t fast_static_bytes() { return sizeof(GroupCtl) * MAX_GROUPS + 256; }   // static __shared__ of the kernel (+ slack)
 
 }  // namespace
 
@@ -1087,8 +1093,9 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     A.mcap = (disc_capacity(A.r) + 31) & ~31;
     int nt = ctx->opt_normals_threads;
     nt = nt < 128 ? 128 : (nt > FAST_NT ? FAST_NT : (nt & ~63));
-    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
-    const size_t tail = fast_tail_bytes() + 128;
+    // the opt-in maximum covers static + dynamic shared memory: the control structs are static
+    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin - fast_static_bytes();
+    const size_t tail = 128;
 
     // window per level: the warp of the disc is close to a similarity, 1.3x the scaled radius
     // plus margins
