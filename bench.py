@@ -93,7 +93,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -325,6 +325,13 @@ def run_gpu_arm(args):
         with torch.cuda.stream(stream):
             flush.fill_(1)
 
+    # ---- clocks are sampled from the warm-up on (nvidia-smi needs ~0.1 s to deliver its first sample and the
+    # timed region of the default run is only ~0.1 s long): every sample is taken under the same load
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         n_match, n_inl = device_step()
@@ -332,9 +339,6 @@ def run_gpu_arm(args):
     barrier()
 
     # ---- timed region: device-resident arm
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     k0, c0 = ctx.launch_counters()
     t_dev_ms = 0.0
     barrier()
