@@ -42,7 +42,7 @@ namespace {
 #define FM3D_NORMALS_NT 512
 #endif
 #ifndef FM3D_NORMALS_UNROLL2
-#define FM3D_NORMALS_UNROLL2 0
+#define FM3D_NORMALS_UNROLL2 1
 #endif
 constexpr int FAST_NT = FM3D_NORMALS_NT;
 constexpr float FLOOR_MAGIC = 12582912.0f;          // 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x)
