@@ -32,7 +32,8 @@ SYMBOLS = [
     "fm3d_set_images", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
     "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_get_normals_stats",
     "fm3d_sweep_normals", "fm3d_sweep_normals_dev",
-    "fm3d_disc_pixels", "fm3d_plane_points", "fm3d_sample_pixels", "fm3d_project_to_image2", "fm3d_feature_frames",
+    "fm3d_disc_pixels", "fm3d_plane_points", "fm3d_sample_pixels", "fm3d_project_to_image2",
+    "fm3d_circular_neighborhoods", "fm3d_feature_frames",
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
 ]
@@ -276,6 +277,15 @@ class Context:
                                                  int(level), int(penalty_mode), int(n_phi), int(n_theta), C.c_double(dphi),
                                                  C.c_double(dtheta), C.c_void_p(cost), C.c_void_p(best_idx),
                                                  C.c_void_p(best_cost), C.c_void_p(status)))
+
+    def circular_neighborhoods(self, points, normals, epsilon_m, n_angles, n_rays):
+        points = _arr(points, np.float64).reshape(-1, 3)
+        normals = _arr(normals, np.float64).reshape(-1, 3).copy()
+        n = points.shape[0]
+        out = np.empty((n, n_angles * n_rays, 3))
+        self._ck(self.lib.fm3d_circular_neighborhoods(self._h, _ptr(points, _dp), _ptr(normals, _dp), n, C.c_double(epsilon_m),
+                                                      int(n_angles), int(n_rays), _ptr(out, _dp)))
+        return out, normals
 
     # ------------------------------------------------------------------ per-evaluation helpers
     def disc_pixels(self, P, pixels_ray):

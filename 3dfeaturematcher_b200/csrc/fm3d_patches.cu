@@ -134,6 +134,49 @@ int patch_args(fm3d_ctx* ctx, PatchArgs& A, int image, double eps_m, double cm_p
     return FM3D_OK;
 }
 
+// NeighborhoodsGenerator::computeCircularNeighborhood(s)ByNormal(s) (neighborhoodsgenerator.cpp:160-277):
+// samples on concentric circles of the feature plane by Rodrigues' rotation of a spanner vector,
+//   sample k = (ray i in 1..n_rays, angle j):  r = i eps / n_rays, theta = j 2 pi / n_angles,
+//   s = (0, 1, -ny/nz) / |.| * eps,   p_k = P + r (s + sin(theta) n x s + 2 sin^2(theta/2) n x (n x s))
+// (the radius ends up scaled by eps twice: as in the reference).  An all-zero normal is replaced
+// by P/|P| and written back.
+__global__ void circular_kernel(const double* __restrict__ pts, double* __restrict__ normals, int n, double eps,
+                                int n_angles, int n_rays, double* __restrict__ out) {
+    const int S = n_angles * n_rays;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * S) return;
+    const int f = (int)(gid / S), k = (int)(gid - (long long)f * S);
+    const double Px = pts[3 * f], Py = pts[3 * f + 1], Pz = pts[3 * f + 2];
+    double nx = normals[3 * f], ny = normals[3 * f + 1], nz = normals[3 * f + 2];
+    if (nx == 0 && ny == 0 && nz == 0) {
+        const double nr = sqrt(Px * Px + Py * Py + Pz * Pz);
+        nx = Px / nr; ny = Py / nr; nz = Pz / nr;
+    }
+    const int i = k / n_angles + 1, j = k - (k / n_angles) * n_angles;
+    const double r = (double)i * (eps / (double)n_rays);
+    const double theta = (double)j * (2 * 3.14159265358979323846 / (double)n_angles);
+    const double st = sin(theta), sh = sin(theta / 2), st2 = 2 * sh * sh;
+    double sx = 0.0, sy = 1.0, sz = -ny / nz;                   // <spanner, normal> = 0
+    const double sn = sqrt(sx * sx + sy * sy + sz * sz);
+    sx = sx / sn * eps; sy = sy / sn * eps; sz = sz / sn * eps;
+    const double ax = ny * sz - nz * sy, ay = nz * sx - nx * sz, az = nx * sy - ny * sx;      // W s  = n x s
+    const double bx = ny * az - nz * ay, by = nz * ax - nx * az, bz = nx * ay - ny * ax;      // W W s
+    double* o = out + 3 * (size_t)gid;
+    o[0] = Px + r * (sx + ax * st + st2 * bx);
+    o[1] = Py + r * (sy + ay * st + st2 * by);
+    o[2] = Pz + r * (sz + az * st + st2 * bz);
+}
+
+__global__ void fill_default_normals_kernel(const double* __restrict__ pts, double* __restrict__ normals, int n) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    if (normals[3 * f] == 0 && normals[3 * f + 1] == 0 && normals[3 * f + 2] == 0) {
+        const double Px = pts[3 * f], Py = pts[3 * f + 1], Pz = pts[3 * f + 2];
+        const double nr = sqrt(Px * Px + Py * Py + Pz * Pz);
+        normals[3 * f] = Px / nr; normals[3 * f + 1] = Py / nr; normals[3 * f + 2] = Pz / nr;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -227,6 +270,31 @@ int fm3d_square_neighborhoods(fm3d_ctx* ctx, const double* frames, int n, double
                                                         (double*)(d + al(bf)));
     FM3D_LAUNCH_CHECK(ctx);
     if (int rc = fm3d_d2h(ctx, out, d + al(bf), bo)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
+
+int fm3d_circular_neighborhoods(fm3d_ctx* ctx, const double* points, double* normals, int n, double epsilon_m,
+                                int n_angles, int n_rays, double* out) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && n_angles >= 1 && n_rays >= 1 && (n == 0 || (points && normals && out)));
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t S = (size_t)n_angles * n_rays;
+    const size_t b3 = sizeof(double) * 3 * (size_t)n, bo = sizeof(double) * 3 * S * (size_t)n;
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, 2 * al(b3) + al(bo), (void**)&d)) return rc;
+    double* d_p = (double*)d; double* d_n = (double*)(d + al(b3)); double* d_o = (double*)(d + 2 * al(b3));
+    if (int rc = fm3d_h2d(ctx, d_p, points, b3)) return rc;
+    if (int rc = fm3d_h2d(ctx, d_n, normals, b3)) return rc;
+    const long long total = (long long)n * (long long)S;
+    circular_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_p, d_n, n, epsilon_m, n_angles, n_rays, d_o);
+    FM3D_LAUNCH_CHECK(ctx);
+    fill_default_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_p, d_n, n);
+    FM3D_LAUNCH_CHECK(ctx);
+    if (int rc = fm3d_d2h(ctx, out, d_o, bo)) return rc;
+    if (int rc = fm3d_d2h(ctx, normals, d_n, b3)) return rc;
     FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FM3D_OK;
 }

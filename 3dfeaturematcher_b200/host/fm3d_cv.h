@@ -35,6 +35,7 @@ typedef unsigned char uchar;
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #define CV_64FC2 CV_MAKETYPE(CV_64F, 2)
+#define CV_64FC3 CV_MAKETYPE(CV_64F, 3)
 #define CV_LOAD_IMAGE_GRAYSCALE 0
 
 namespace cv {

@@ -492,12 +492,50 @@ void NormalOptimizer::computeFeaturesFrames(std::vector<cv::Vec3d>& points3D, st
 }
 
 // ----------------------------------------------------------------------- NeighborhoodsGenerator
-NeighborhoodsGenerator::NeighborhoodsGenerator(cv::FileStorage settings) : epsilon_(0), cm_per_pixel_(0) {
+NeighborhoodsGenerator::NeighborhoodsGenerator(cv::FileStorage settings)
+    : epsilon_(0), cm_per_pixel_(0), number_of_angles_(0), number_of_rays_(0), circular_(false) {
     std::string method = (std::string)settings["Neighborhoods"]["method"];
-    if (method != "square")
-        throw std::runtime_error("fm3d: Neighborhoods.method '" + method + "' is not supported (square only)");  // exit(-10) (:69-73)
-    settings["Neighborhoods"]["epsilon"] >> epsilon_;
-    settings["Neighborhoods"]["cmPerPixel"] >> cm_per_pixel_;
+    if (method == "square") {
+        settings["Neighborhoods"]["epsilon"] >> epsilon_;
+        settings["Neighborhoods"]["cmPerPixel"] >> cm_per_pixel_;
+    } else if (method == "circular") {                                    // (:46-66)
+        circular_ = true;
+        settings["Neighborhoods"]["epsilon"] >> epsilon_;
+        settings["Neighborhoods"]["thetas"] >> number_of_angles_;
+        settings["Neighborhoods"]["rays"] >> number_of_rays_;
+        if (number_of_angles_ < 1 || number_of_rays_ < 1) throw std::runtime_error("fm3d: Neighborhoods.thetas / rays missing");
+    } else {
+        throw std::runtime_error("fm3d: unsupported method for plane neighborhood extraction: '" + method + "'");  // exit(-10) (:69-73)
+    }
+}
+
+void NeighborhoodsGenerator::computeCircularNeighborhoodsByNormals(const cv::Mat& points, cv::Mat& normals,
+                                                                   std::vector<cv::Mat>& neighborhoodsVector) {
+    if (!circular_) throw std::runtime_error("fm3d: NeighborhoodsGenerator was not configured with method: circular");
+    fm3d_ctx* ctx = host_ctx();
+    const int n = points.cols, S = number_of_angles_ * number_of_rays_;
+    if (n == 0) return;
+    if (normals.empty()) normals = cv::Mat::zeros(cv::Size(n, 3), CV_64FC1);    // zeros = "use P/|P|" (:166-181)
+    std::vector<double> p((size_t)n * 3), nn((size_t)n * 3), out((size_t)n * S * 3);
+    for (int f = 0; f < n; f++)
+        for (int c = 0; c < 3; c++) { p[3 * f + c] = points.ptr<double>(c)[f]; nn[3 * f + c] = normals.ptr<double>(c)[f]; }
+    check(ctx, fm3d_circular_neighborhoods(ctx, p.data(), nn.data(), n, epsilon_, number_of_angles_, number_of_rays_, out.data()),
+          "circular_neighborhoods");
+    for (int f = 0; f < n; f++) {
+        for (int c = 0; c < 3; c++) normals.ptr<double>(c)[f] = nn[3 * f + c];
+        cv::Mat nb = cv::Mat::zeros(cv::Size(S, 1), CV_64FC3);
+        memcpy(nb.data, &out[(size_t)f * S * 3], sizeof(double) * 3 * (size_t)S);
+        neighborhoodsVector.push_back(nb);                                // appended, as the reference (:215)
+    }
+}
+
+void NeighborhoodsGenerator::computeCircularNeighborhoodByNormal(const cv::Vec3d& point, cv::Vec3d& normal, cv::Mat& neighborhood) {
+    if (!circular_) throw std::runtime_error("fm3d: NeighborhoodsGenerator was not configured with method: circular");
+    fm3d_ctx* ctx = host_ctx();
+    const int S = number_of_angles_ * number_of_rays_;
+    neighborhood = cv::Mat::zeros(cv::Size(S, 1), CV_64FC3);
+    check(ctx, fm3d_circular_neighborhoods(ctx, point.val, normal.val, 1, epsilon_, number_of_angles_, number_of_rays_,
+                                           (double*)neighborhood.data), "circular_neighborhoods");
 }
 
 void NeighborhoodsGenerator::getReferenceSquaredNeighborhood(std::vector<cv::Vec3d>& neighborhood) {

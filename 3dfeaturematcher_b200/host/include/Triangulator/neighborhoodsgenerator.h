@@ -1,7 +1,6 @@
-// NeighborhoodsGenerator -- public interface of the reference class for the `square` method
-// (Triangulator/neighborhoodsgenerator.h:81-97).  The circular variant is never called by
-// main.cpp / mosaic.cpp (settings.yml: method: square) and is not provided: constructing with
-// method: circular throws (the reference exit(-10)s only for unknown methods).
+// NeighborhoodsGenerator -- same public interface as the reference class
+// (Triangulator/neighborhoodsgenerator.h:81-97): `square` (the method main.cpp / mosaic.cpp use) and
+// `circular` (neighborhoodsgenerator.cpp:160-277).  An unknown method throws (the reference exit(-10)s).
 #ifndef FM3D_HOST_NEIGHBORHOODSGENERATOR_H_
 #define FM3D_HOST_NEIGHBORHOODSGENERATOR_H_
 #include <vector>
@@ -10,6 +9,10 @@
 class NeighborhoodsGenerator {
 public:
     NeighborhoodsGenerator(cv::FileStorage settings);
+    // points / normals: 3 x N CV_64FC1 (one column per feature); an empty normals Mat is filled with the
+    // initial guess P/|P|; every neighbourhood is a 1 x (thetas*rays) CV_64FC3 Mat
+    void computeCircularNeighborhoodsByNormals(const cv::Mat& points, cv::Mat& normals, std::vector<cv::Mat>& neighborhoodsVector);
+    void computeCircularNeighborhoodByNormal(const cv::Vec3d& point, cv::Vec3d& normal, cv::Mat& neighborhood);
     void computeSquareNeighborhoodsByNormals(const std::vector<cv::Matx44d>& featuresFrames,
                                              std::vector<std::vector<cv::Vec3d> >& neighborhoodsVector);
     void computeSquareNeighborhoodByNormal(const cv::Matx44d& featureFrame, std::vector<cv::Vec3d>& neighborhood);
@@ -20,5 +23,7 @@ public:
 private:
     NeighborhoodsGenerator();
     double epsilon_, cm_per_pixel_;
+    int number_of_angles_, number_of_rays_;
+    bool circular_;
 };
 #endif

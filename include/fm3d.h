@@ -338,6 +338,14 @@ int fm3d_project_groups(fm3d_ctx* ctx, int image, const double* groups, int n, i
 int fm3d_square_neighborhoods(fm3d_ctx* ctx, const double* frames, int n, double epsilon_m,
                               double cm_per_pixel, double* out);
 
+/* Replaces NeighborhoodsGenerator::computeCircularNeighborhood(s)ByNormal(s)
+ * (neighborhoodsgenerator.cpp:160-277, look-up table of the constructor :46-66): n_rays concentric
+ * circles of n_angles samples each on the plane through points[f] with normal normals[f]; sample
+ * k = (ray - 1) * n_angles + angle.  An all-zero normal means "initial guess": it is replaced by
+ * P/|P| and written back.  out: n x n_rays*n_angles x 3.  (Settings: Neighborhoods.epsilon, thetas, rays.) */
+int fm3d_circular_neighborhoods(fm3d_ctx* ctx, const double* points, double* normals, int n, double epsilon_m,
+                                int n_angles, int n_rays, double* out);
+
 #ifdef __cplusplus
 }
 #endif

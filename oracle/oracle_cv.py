@@ -451,6 +451,26 @@ def square_neighborhood(frame, epsilon_m, cm_per_pixel):
     return h[:, :3] / h[:, 3:4]
 
 
+def circular_neighborhood(P, normal, epsilon_m, n_angles, n_rays):
+    """computeCircularNeighborhoodByNormal (neighborhoodsgenerator.cpp:238-277) with the look-up
+    table of the constructor (:46-66): ray i = 1..rays outer, angle j inner; an all-zero normal
+    means P/|P|.  Returns (samples (rays*angles, 3), the normal used)."""
+    P = np.asarray(P, dtype=np.float64)
+    n = np.asarray(normal, dtype=np.float64).copy()
+    if not n.any():
+        n = P / np.linalg.norm(P)
+    W = np.array([[0, -n[2], n[1]], [n[2], 0, -n[0]], [-n[1], n[0], 0]])   # getSkewMatrix (tools.cpp:122-127)
+    s = np.array([0.0, 1.0, -n[1] / n[2]])
+    s = s / np.linalg.norm(s) * epsilon_m
+    out = []
+    for i in range(1, n_rays + 1):
+        for j in range(n_angles):
+            r, t = i * (epsilon_m / n_rays), j * (2 * math.pi / n_angles)
+            st, st2 = math.sin(t), 2 * math.sin(t / 2) * math.sin(t / 2)
+            out.append(P + r * (s + W @ s * st + st2 * (W @ W @ s)))
+    return np.array(out), n
+
+
 def project_reference_points(cam: Camera, img1, ref, frame):
     """projectReferencePointsToImageWithFrame (singlecameratriangulator.cpp:805-849).
     Returns patch (S,S) uint8 and image points (S*S,2)."""

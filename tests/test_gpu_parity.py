@@ -580,6 +580,23 @@ def test_frames_and_patches(ctx):
     assert (np.abs(gp1.astype(int) - p1.astype(int)) <= 1).all()
 
 
+def test_circular_neighborhoods(ctx):
+    """NeighborhoodsGenerator's circular variant (never called by main.cpp, kept for the interface)."""
+    from oracle import oracle_cv as ocv
+    rng = np.random.default_rng(5)
+    P = rng.normal(0, 0.3, (7, 3)) + np.array([0, 0, 2.0])
+    N = rng.normal(0, 0.3, (7, 3)) + np.array([0, 0, 1.0])
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    N[2] = 0                                            # "initial guess": P/|P|
+    out, used = ctx.circular_neighborhoods(P, N, 0.16, 15, 5)
+    assert out.shape == (7, 75, 3)
+    for f in range(7):
+        o, n_used = ocv.circular_neighborhood(P[f], N[f], 0.16, 15, 5)
+        np.testing.assert_allclose(out[f], o, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(used[f], n_used, rtol=0, atol=1e-15)
+        np.testing.assert_allclose((out[f] - P[f]) @ n_used, 0, atol=1e-12)      # every sample lies in the plane
+
+
 # ------------------------------------------------------------------ committed golden vectors (cv2)
 def test_gpu_against_golden_vectors(ctx):
     """The CUDA path against tests/golden/*.npz: outputs of cv2.undistortPoints / triangulatePoints /
