@@ -15,7 +15,7 @@
 static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 
 int main(int argc, char** argv) {
-    if (argc < 5 || strcmp(argv[1], "-s") != 0) { std::cerr << "usage: -s <settings.yml> <features.bin> <result.bin>\n"; return 1; }
+    if (argc < 5 || strcmp(argv[1], "-s") != 0) { std::cerr << "usage: -s <settings.yml> <features.bin> <result.bin> [circular-settings.yml]\n"; return 1; }
     cv::FileStorage fs;
     fs.open(argv[2], cv::FileStorage::READ);
     if (!fs.isOpened()) { std::cerr << "Could not open settings file: " << argv[2] << std::endl; return 1; }
@@ -114,6 +114,22 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < px2.size() && i < px.size(); i++) { const double d = (double)(px[i].i_ - px2[i].i_); hcost += d * d; }
     }
     fwrite(&hm, 4, 1, o); fwrite(&rc1, 4, 1, o); fwrite(&rc2, 4, 1, o); fwrite(&rc3, 4, 1, o); fwrite(&hcost, 8, 1, o);
+    // optional: the circular variant of NeighborhoodsGenerator from a second settings file (method: circular)
+    int cs = 0;
+    if (argc > 5 && nn > 0) {
+        cv::FileStorage fs2;
+        fs2.open(argv[5], cv::FileStorage::READ);
+        NeighborhoodsGenerator ngc(fs2);
+        cv::Mat nb;
+        cv::Vec3d nrm(0, 0, 0);                       // "initial guess"
+        ngc.computeCircularNeighborhoodByNormal(triagulated[0], nrm, nb);
+        cs = nb.cols;
+        fwrite(&cs, 4, 1, o);
+        fwrite(nrm.val, 8, 3, o);
+        fwrite(nb.data, 8, (size_t)3 * cs, o);
+    } else {
+        fwrite(&cs, 4, 1, o);
+    }
     fclose(o);
     std::cout << nm << " matches, " << np << " inliers, " << nn << " normals, patches " << S << "x" << S << std::endl;
     return 0;

@@ -133,8 +133,14 @@ def _read_result(path):
     gravity = np.frombuffer(b, np.float64, 3, o); o += 24
     hm, rc1, rc2, rc3 = struct.unpack_from("iiii", b, o); o += 16
     hcost = struct.unpack_from("d", b, o)[0]; o += 8
+    cs = struct.unpack_from("i", b, o)[0]; o += 4
+    circ = None
+    if cs > 0:
+        cn = np.frombuffer(b, np.float64, 3, o); o += 24
+        cpts = np.frombuffer(b, np.float64, 3 * cs, o).reshape(-1, 3); o += 24 * cs
+        circ = dict(normal=cn, pts=cpts)
     assert o == len(b)
-    return dict(helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
+    return dict(circular=circ, helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
                 patches=patches, last_nb=last_nb, gravity=gravity, S=S)
 
 
@@ -147,8 +153,11 @@ def test_main_cpp_call_sequence_on_the_adapters(tmp_path):
     tmp = str(tmp_path)
     _write_inputs(tmp, case, r, pyramids, eps_m, cmpp)
     env = dict(os.environ, FM3D_PENALTY="2", FM3D_NO_PATCH_FILES="1")
+    with open(os.path.join(tmp, "circular.yml"), "w") as f:
+        f.write("%YAML:1.0\nNeighborhoods:\n   method: circular\n   epsilon: 0.16\n   thetas: 15\n   rays: 5\n")
     p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), os.path.join(tmp, "features.bin"),
-                        os.path.join(tmp, "result.bin")], capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+                        os.path.join(tmp, "result.bin"), os.path.join(tmp, "circular.yml")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     res = _read_result(os.path.join(tmp, "result.bin"))
 
@@ -190,6 +199,11 @@ def test_main_cpp_call_sequence_on_the_adapters(tmp_path):
                                     pyramids, res["kept"][:1], pt, r, 0, 2)
     assert h["m"] == om[0] and ost[0] == 0
     np.testing.assert_allclose(h["cost"], oc[0], rtol=1e-6)
+    # circular neighbourhood of the first feature with the initial-guess normal (neighborhoodsgenerator.cpp:238-277)
+    from oracle import oracle_cv as ocv
+    o_c, o_n = ocv.circular_neighborhood(res["kept"][0], np.zeros(3), 0.16, 15, 5)
+    np.testing.assert_allclose(res["circular"]["pts"], o_c, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(res["circular"]["normal"], o_n, rtol=0, atol=1e-15)
     # computeSquareNeighborhoodsByNormals: last grid point of every feature
     S = res["S"]
     ref_last = np.array([-eps_m + 0.01 * cmpp * (S - 1), -eps_m + 0.01 * cmpp * (S - 1), 0.0, 1.0])
