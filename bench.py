@@ -208,6 +208,9 @@ def run_gpu_arm(args):
     import torch.distributed as dist
     api = importlib.import_module("3dfeaturematcher_b200.api")
     shard = importlib.import_module("3dfeaturematcher_b200.shard")
+    if not os.path.exists(api.LIB_PATH) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        # the library normally travels with the tree; nvcc is in the image if it does not
+        importlib.import_module("3dfeaturematcher_b200.build").build()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
