@@ -1122,7 +1122,7 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     int n_order = 0;
     const int sms = ctx->prop.multiProcessorCount;
     if (ctx->opt_normals_groups == 3 && nt % 96 == 0) { const Layout three = {3, false, false}; order[n_order++] = three; }
-    if ((ctx->opt_normals_groups == 4 || (ctx->opt_normals_groups == 0 && A.n >= 8 * sms)) && nt % 128 == 0) order[n_order++] = four;
+    if ((ctx->opt_normals_groups == 4 || (ctx->opt_normals_groups == 0 && A.n >= 5 * sms)) && nt % 128 == 0) order[n_order++] = four;
     const int want = ctx->opt_normals_groups;   // 0: automatic
     const bool prefer_two = want == 2 || (want == 0 && A.n > ctx->prop.multiProcessorCount);
     if (prefer_two) { order[n_order++] = two_a; order[n_order++] = two_b; }
