@@ -389,14 +389,17 @@ void SingleCameraTriangulator::projectPointsAndComputeResidual(const cv::Mat& po
     check(ctx_, fm3d_project_groups(ctx_, 1, xyz.data(), n, 1, dummy.data(), (double*)imagePoints1.data), "project_groups");
     int info = 0;
     check(ctx_, fm3d_project_to_image2(ctx_, xyz.data(), n, 0, 1.0, (double*)imagePoints2.data, nullptr, &info), "project_to_image2");
+    // img.at<uchar>(round(y), round(x)) of both images: the bilinear sampler at integer coordinates
+    // returns exactly that pixel, so the lookup runs on the GPU like everything else
+    std::vector<double> r1((size_t)n * 2), r2((size_t)n * 2);
     for (int k = 0; k < n; k++) {
-        const double* p1 = imagePoints1.ptr<double>(k);
-        const double* p2 = imagePoints2.ptr<double>(k);
-        const int x1 = (int)std::round(p1[0]), y1 = (int)std::round(p1[1]), x2 = (int)std::round(p2[0]), y2 = (int)std::round(p2[1]);
-        const int a = (x1 >= 0 && y1 >= 0 && x1 < img_1_.cols && y1 < img_1_.rows) ? img_1_.ptr<uchar>(y1)[x1] : 0;
-        const int b = (x2 >= 0 && y2 >= 0 && x2 < img_2_.cols && y2 < img_2_.rows) ? img_2_.ptr<uchar>(y2)[x2] : 0;
-        residualsVector.push_back((double)(a - b));
+        r1[2 * k] = std::round(imagePoints1.ptr<double>(k)[0]); r1[2 * k + 1] = std::round(imagePoints1.ptr<double>(k)[1]);
+        r2[2 * k] = std::round(imagePoints2.ptr<double>(k)[0]); r2[2 * k + 1] = std::round(imagePoints2.ptr<double>(k)[1]);
     }
+    std::vector<float> i1(n), i2(n);
+    check(ctx_, fm3d_sample_pixels(ctx_, 1, 0, 1.0, 0, r1.data(), n, i1.data(), &info), "sample_pixels");
+    check(ctx_, fm3d_sample_pixels(ctx_, 2, 0, 1.0, 0, r2.data(), n, i2.data(), &info), "sample_pixels");
+    for (int k = 0; k < n; k++) residualsVector.push_back((double)((int)i1[k] - (int)i2[k]));   // uchar - uchar, promoted to int
 }
 
 void SingleCameraTriangulator::projectPointsAndComputeResidual(const std::vector<cv::Mat>& pointsGroupVector,
