@@ -31,6 +31,16 @@
 //              the warp is a homeomorphism of the disc, so the interior cannot leave a rectangle
 //              its boundary stays in.  The same test proves that every tap of the pass lies in the
 //              staged window; if not, the pass is repeated with taps from global memory.
+//   memo       a trial point whose fp32 homography coefficients equal the iterate's would return
+//              the iterate's residual sum bit for bit (the value path is a fixed sequence of
+//              explicit fma / non-contractible operations in every instantiation): warp 0 answers
+//              it without a pass.  This is what lmfit's tail (tolerances of 30 eps) mostly asks for.
+//   arithmetic packed fp32x2 (FFMA2 / FMUL2 / FADD2): one instruction for two adjacent disc pixels,
+//              rays stored pair-interleaved so that one 128-bit load is the packed operand pair.
+//   pipelines  the CTA is split into 1, 2 or 4 groups of warps, each with its own feature, window,
+//              LM state and named barrier: the pixel passes of one group fill the SM while another
+//              is in its single-lane LM step.  With several groups the rays and image-1 samples
+//              stream from an L2-resident per-group scratch (next loads issued ahead of use).
 #include "fm3d_normals_common.cuh"
 
 using namespace fm3d_normals;
@@ -51,7 +61,7 @@ enum { FLAG_WINDOW = 8 };
 enum { PASS_STOP = 0, PASS_VALUE = 1, PASS_JAC = 2 };
 enum { AT_X_JAC = 0, AT_XT_PLAIN = 1, AT_XT_FUSED = 2 };
 
-// Everything a pass needs, written by thread 0.
+// Everything a pass needs, written by the lanes of warp 0 of the group.
 struct FastPass {
     // e = 0: value, 1: d/dphi, 2: d/dtheta.  A_e = h[e][0] dx + h[e][1] dy + h[e][2] (x numerator, offset form),
     // B_e = h[e][3] dx + h[e][4] dy + h[e][5], C_e = h[e][6] dx + h[e][7] dy + h[e][8] (common denominator)
@@ -227,8 +237,8 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f2 bc(float c) { return mk2(c, c); }
-__device__ __forceinline__ float lo2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo2(f2 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi2(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }

@@ -61,8 +61,10 @@ for fn in functions("fm3d_normals_fast.o"):
             for b in body:
                 op = re.sub(r"^\s*/\*[0-9a-f]+\*/\s*(@!?U?P\d+\s+)?", "", b).split()[0].split(".")[0]
                 ops[op] = ops.get(op, 0) + 1
-            kind = "value+Jacobian" if ops.get("FFMA", 0) > 90 else "value-only"
-            f.write(f"\n# ---- pixel loop ({kind}, 2 pixels per iteration): {len(body)} instructions; "
+            npix = max(1, sum("LDS.U8" in b for b in body) // 4)
+            fp = ops.get("FFMA", 0) + 2 * (ops.get("FFMA2", 0) + ops.get("FMUL2", 0) + ops.get("FADD2", 0)) + ops.get("FMUL", 0) + ops.get("FADD", 0)
+            kind = "value+Jacobian" if fp / npix > 60 else "value-only"
+            f.write(f"\n# ---- pixel loop ({kind}, {npix} pixels per iteration): {len(body)} instructions; "
                     + ", ".join(f"{k} {v}" for k, v in sorted(ops.items(), key=lambda kv: -kv[1])) + "\n")
             for b in body:
                 f.write(b[:120] + "\n")
