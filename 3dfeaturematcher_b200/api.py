@@ -36,6 +36,7 @@ SYMBOLS = [
     "fm3d_circular_neighborhoods", "fm3d_feature_frames",
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
+    "fm3d_describe_patches_sift", "fm3d_describe_patches_sift_dev",
 ]
 
 
@@ -358,7 +359,18 @@ class Context:
         self._ck(self.lib.fm3d_square_neighborhoods(self._h, _ptr(frames, _dp), n, C.c_double(epsilon_m), C.c_double(cm_per_pixel), _ptr(out, _dp)))
         return out
 
+    def describe_patches_sift(self, patches):
+        """extractDescriptorsFromPatches with ExtractorType SIFT: n x S x S u8 -> n x 128 f32."""
+        patches = _arr(patches, np.uint8)
+        n, S = patches.shape[0], patches.shape[1]
+        desc = np.empty((n, 128), np.float32)
+        self._ck(self.lib.fm3d_describe_patches_sift(self._h, _ptr(patches, _bp), n, S, _ptr(desc, _fp)))
+        return desc
+
     # ------------------------------------------------------------------ device-pointer entry points
+    def describe_patches_sift_dev(self, patches, n, S, descriptors):
+        self._ck(self.lib.fm3d_describe_patches_sift_dev(self._h, C.c_void_p(patches), n, S, C.c_void_p(descriptors)))
+
     def match_knn2_f32_dev(self, q, nq, t, nt, dim, idx, dist):
         self._ck(self.lib.fm3d_match_knn2_f32_dev(self._h, C.c_void_p(q), nq, C.c_void_p(t), nt, dim, C.c_void_p(idx), C.c_void_p(dist)))
 

@@ -346,6 +346,18 @@ int fm3d_square_neighborhoods(fm3d_ctx* ctx, const double* frames, int n, double
 int fm3d_circular_neighborhoods(fm3d_ctx* ctx, const double* points, double* normals, int n, double epsilon_m,
                                 int n_angles, int n_rays, double* out);
 
+/* ---------------------------------------------------------- patch descriptors ---- */
+
+/* Replaces DescriptorsMatcher::extractDescriptorsFromPatches
+ * (DescriptorsMatcher/descriptorsmatcher.cpp:133-174) for ExtractorType SIFT (:246): one keypoint
+ * per patch at (floor(S/2), floor(S/2)) with size = S, angle = -1, octave = 0, response = 1,
+ * described by cv::SIFT::compute (nOctaveLayers 3, sigma 1.6).  patches: n x S x S u8 as written by
+ * fm3d_extract_patches; descriptors: n x 128 f32, integer-valued in [0, 255] (cv::SIFT's CV_32F
+ * output), row k = patch k (the reference copies descriptorsVector[k] into row k, :168-172).
+ * 8 <= S <= 164 (two S x S float planes in shared memory). */
+int fm3d_describe_patches_sift(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, float* descriptors);
+int fm3d_describe_patches_sift_dev(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, float* descriptors);
+
 #ifdef __cplusplus
 }
 #endif

@@ -506,3 +506,21 @@ def project_groups(cam: Camera, img, group, image_id):
     idx = np.arange(S * S)
     patch[idx % S, idx // S] = u8
     return patch, ip
+
+
+# ---------------------------------------------------------------------------------------------
+# patch descriptors (DescriptorsMatcher/descriptorsmatcher.cpp:133-174, ExtractorType SIFT :246)
+def describe_patches_sift(patches):
+    """extractDescriptorsFromPatches: one keypoint per patch at (floor(S/2), floor(S/2)), size = S,
+    angle = -1, response = 1, octave = 0, class_id = 0 (:150-157), then
+    descriptor_extractor_->compute (:164) and one descriptor row per patch (:166-172)."""
+    sift = cv2.SIFT_create()
+    out = []
+    for patch in np.asarray(patches, np.uint8):
+        size = patch.shape[0]
+        center = float(int(math.floor(size / 2)))
+        kp = cv2.KeyPoint(center, center, float(size), -1.0, 1.0, 0, 0)
+        kps, d = sift.compute(np.ascontiguousarray(patch), [kp])
+        assert len(kps) == 1 and d.shape == (1, 128)
+        out.append(d[0])
+    return np.stack(out) if out else np.zeros((0, 128), np.float32)

@@ -79,3 +79,31 @@ def test_cost_frames_patches(nrm):
     p, ip = orc.extract_patches(nrm["K"], nrm["dist"], nrm["img1"], nrm["frames"], 0.05, 0.25)
     np.testing.assert_array_equal(p, nrm["patches"])
     np.testing.assert_allclose(ip, nrm["image_points"], rtol=0, atol=1e-10)
+
+
+# ------------------------------------------------------------------ patch descriptors (K9 oracle)
+def _desc_close(got, want, frac_exact=0.97):
+    """Quantised SIFT values: +-1 on isolated entries (summation order of float sums), else equal."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert diff.max(initial=0) <= 1, diff.max()
+    assert (diff == 0).mean() >= frac_exact if diff.size else True
+
+
+def test_sift_patch_restatement_against_cv2_golden_vectors():
+    from oracle import sift_patch_np as sp
+    g = np.load(os.path.join(GOLD, "sift_patches.npz"))
+    for S in (128, 64, 40, 16, 8):
+        d = sp.describe_patches_sift(g[f"p{S}"])
+        _desc_close(d, g[f"d{S}"])
+        # the reference's keypoint (size = S at the patch centre) only ever fills the 2 x 2 central cells,
+        # plus orientation bin 1 of column 0 (o0 = -1 under flat addressing, see oracle/sift_patch_np.py)
+        cells = g[f"d{S}"].reshape(-1, 4, 4, 8).copy()
+        assert np.count_nonzero(cells[:, [0, 3], :, :]) == 0 and np.count_nonzero(cells[:, :, 3, :]) == 0
+        assert np.count_nonzero(cells[:, 1:3, 0, 1]) > 0       # the step-edge patch exercises it
+        cells[:, 1:3, 0, 1] = 0
+        assert np.count_nonzero(cells[:, :, 0, :]) == 0
+        assert np.count_nonzero(g[f"d{S}"][-2]) == 0          # constant patch -> zero descriptor
+    pipe = np.load(os.path.join(GOLD, "normals.npz"))["patches"]
+    _desc_close(sp.describe_patches_sift(pipe), g["d_pipeline"])

@@ -641,3 +641,75 @@ def test_gpu_against_golden_vectors(ctx):
     np.testing.assert_allclose(ip, g["image_points"], rtol=0, atol=1e-9)
     diff = patches.astype(int) - g["patches"].astype(int)
     assert (np.abs(diff) <= 1).all() and (diff != 0).mean() < 1e-3
+
+
+# ------------------------------------------------------------------ patch descriptors (K9)
+def _desc_close(got, want, frac_exact=0.97):
+    diff = np.abs(np.asarray(got).astype(np.int32) - np.asarray(want).astype(np.int32))
+    assert got.shape == want.shape and diff.max(initial=0) <= 1, diff.max(initial=0)
+    if diff.size:
+        assert (diff == 0).mean() >= frac_exact, (diff == 0).mean()
+
+
+def test_describe_patches_sift_golden_vectors(ctx):
+    """extractDescriptorsFromPatches (descriptorsmatcher.cpp:133-174, SIFT): the committed outputs of
+    cv2.SIFT_create().compute.  Values are quantised to integers: +-1 on isolated entries."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "sift_patches.npz"))
+    for S in (128, 64, 40, 16, 8):
+        d = ctx.describe_patches_sift(g[f"p{S}"])
+        assert d.dtype == np.float32 and d.shape == (g[f"p{S}"].shape[0], 128)
+        _desc_close(d, g[f"d{S}"])
+        assert np.count_nonzero(d[-2]) == 0            # constant patch
+    pipe = np.load(os.path.join(gold, "normals.npz"))["patches"]
+    _desc_close(ctx.describe_patches_sift(pipe), g["d_pipeline"])
+
+
+def test_describe_patches_sift_against_oracle_and_edges(ctx, api):
+    from oracle import sift_patch_np as sp
+    rng = np.random.default_rng(123)
+    for S, n in ((128, 40), (130, 5), (164, 3), (66, 17), (9, 6)):
+        patches = rng.integers(0, 256, (n, S, S), dtype=np.uint8)
+        # smooth half of them (box filter) so that orientations are not uniform
+        sm = patches.astype(np.float32)
+        sm = (sm + np.roll(sm, 1, 1) + np.roll(sm, 1, 2) + np.roll(np.roll(sm, 1, 1), 1, 2)) / 4
+        patches[::2] = sm[::2].astype(np.uint8)
+        patches[-1, :, :] = 0
+        patches[-1, :, S // 3:] = 255                  # saturated step edge
+        got = ctx.describe_patches_sift(patches)
+        _desc_close(got, sp.describe_patches_sift(patches))
+        # deterministic: fixed summation order, no atomics
+        assert np.array_equal(got, ctx.describe_patches_sift(patches))
+        # one patch alone gives the row it gave in the batch
+        assert np.array_equal(ctx.describe_patches_sift(patches[1:2])[0], got[1])
+    assert ctx.describe_patches_sift(np.zeros((0, 128, 128), np.uint8)).shape == (0, 128)
+    for S in (4, 200):                                 # outside the supported patch edges
+        with pytest.raises(api.Fm3dError):
+            ctx.describe_patches_sift(np.zeros((1, S, S), np.uint8))
+
+
+def test_describe_patches_pipeline_on_device(ctx, api):
+    """frames -> K8 patches -> K9 descriptors without leaving the device equals the host-buffer calls."""
+    torch = pytest.importorskip("torch")
+    case = stereo_case(640, 480, 40, 1001, 32)
+    setup_ctx(ctx, case, 2)
+    X = case["X"][:24]
+    frames = ctx.feature_frames(X, case["normal"][:24], np.array([0.006, 0.99992, -0.011]))
+    patches, _ = ctx.extract_patches(frames, 0.16, 0.25, want_points=False)
+    want = ctx.describe_patches_sift(patches)
+    S = api.patch_size(0.16, 0.25)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    d_frames = torch.from_numpy(frames.reshape(-1, 16)).to(dev)
+    d_patches = torch.empty((len(X), S, S), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((len(X), 128), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ctx.extract_patches_dev(d_frames.data_ptr(), len(X), 0.16, 0.25, d_patches.data_ptr(), None)
+    ctx.describe_patches_sift_dev(d_patches.data_ptr(), len(X), S, d_desc.data_ptr())
+    stream.synchronize()
+    assert np.array_equal(d_patches.cpu().numpy(), patches)
+    assert np.array_equal(d_desc.cpu().numpy(), want)
+    from oracle import sift_patch_np as sp
+    _desc_close(want, sp.describe_patches_sift(patches))
+    assert np.count_nonzero(want) > 0

@@ -121,3 +121,29 @@ def test_c_port_against_cv2_restatement():
         np.testing.assert_array_equal(rc["nfev"], rp["nfev"])
         np.testing.assert_array_equal(rc["status"], rp["status"])
         np.testing.assert_allclose(rc["normals"], rp["normals"], rtol=0, atol=1e-7)
+
+
+def test_sift_patch_restatement_against_live_cv2():
+    """oracle/sift_patch_np.py against cv2.SIFT_create().compute with the reference's keypoint
+    (descriptorsmatcher.cpp:150-164), on fresh random patches."""
+    pytest.importorskip("cv2")
+    from oracle import oracle_cv as oc
+    from oracle import sift_patch_np as sp
+    rng = np.random.default_rng(99)
+    import cv2
+    for S in (128, 96, 50, 24, 10):
+        patches = []
+        for k in range(4):
+            img = rng.integers(0, 256, (S, S)).astype(np.uint8)
+            if k:
+                img = cv2.normalize(cv2.GaussianBlur(img, (0, 0), float(k)), None, 0, 255, cv2.NORM_MINMAX)
+            patches.append(img)
+        patches = np.array(patches)
+        want = oc.describe_patches_sift(patches)
+        got = sp.describe_patches_sift(patches)
+        diff = np.abs(want - got)
+        assert diff.max() <= 1 and (diff == 0).mean() > 0.97
+        # blur stage alone
+        sigma = (1.6 * 1.6 - 0.25) ** 0.5
+        np.testing.assert_allclose(sp.gaussian_blur_f32(patches[1], sigma),
+                                   cv2.GaussianBlur(patches[1].astype(np.float32), (0, 0), sigma), rtol=0, atol=2e-4)

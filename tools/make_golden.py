@@ -82,9 +82,44 @@ def normals():
     np.savez_compressed(os.path.join(OUT, "normals.npz"), **out)
 
 
+def sift_test_patches(S, count, seed):
+    """Patches for the SIFT-descriptor fixtures: band-limited textures, white noise, a step edge, a
+    constant patch (all-zero histogram) and a linear ramp (one orientation bin)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(count):
+        img = rng.integers(0, 256, (S, S)).astype(np.uint8)
+        if k % 4 != 3:      # every fourth patch stays white noise
+            img = cv2.GaussianBlur(img, (0, 0), 1.0 + (k % 3))
+            img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX)
+        out.append(img)
+    edge = np.zeros((S, S), np.uint8)
+    edge[:, S // 2 + 1:] = 200
+    ramp = np.clip(np.add.outer(np.arange(S) * 1.5, np.arange(S) * 0.5), 0, 255).astype(np.uint8)
+    out += [edge, np.full((S, S), 77, np.uint8), ramp]
+    return np.array(out)
+
+
+def sift_patches():
+    """K9 fixtures: cv2.SIFT_create().compute with the keypoint of extractDescriptorsFromPatches
+    (descriptorsmatcher.cpp:150-157) on patches of several edge lengths, and on the rectified
+    patches of normals.npz."""
+    out = {}
+    for S, count in ((128, 3), (64, 4), (40, 4), (16, 4), (8, 2)):
+        p = sift_test_patches(S, count, 5000 + S)
+        out[f"p{S}"] = p
+        out[f"d{S}"] = oc.describe_patches_sift(p)
+    pipe = np.load(os.path.join(OUT, "normals.npz"))["patches"]
+    out["d_pipeline"] = oc.describe_patches_sift(pipe)      # patches themselves live in normals.npz
+    np.savez_compressed(os.path.join(OUT, "sift_patches.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    primitives()
-    normals()
+    if "--sift-only" not in sys.argv:
+        primitives()
+        normals()
+    sift_patches()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
