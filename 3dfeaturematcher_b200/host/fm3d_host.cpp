@@ -100,6 +100,7 @@ void sph2car(const double phi, const double theta, cv::Vec3d& v) {
 DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv::Mat& frame_b)
     : image_a_(frame_a), image_b_(frame_b), binary_(false), have_features_(false) {
     std::string extractorType = (std::string)fs["FeatureOptions"]["ExtractorType"];
+    extractor_type_ = extractorType;
     // the reference picks the LSH (binary) matcher for these (descriptorsmatcher.cpp:64-67)
     binary_ = extractorType == "ORB" || extractorType == "BRISK" || extractorType == "FREAK";
     host_ctx();
@@ -173,8 +174,25 @@ void DescriptorsMatcher::compareWithNNDR(double epsilon, std::vector<cv::DMatch>
     for (int i = 0; i < n; i++) matches.push_back(cv::DMatch(qi[i], ti[i], d[i]));  // appended, not cleared (:126)
 }
 
-void DescriptorsMatcher::extractDescriptorsFromPatches(const std::vector<cv::Mat>&, cv::Mat&) {
-    throw std::runtime_error("fm3d: extractDescriptorsFromPatches needs the upstream OpenCV extractor (SURVEY 8f, next)");
+// descriptorsmatcher.cpp:133-174: one keypoint per patch (centre, size = patch edge, angle -1), one
+// descriptor row per patch.  ExtractorType SIFT runs on the GPU (K9); the other extractors of the
+// reference (SURF / ORB / BRISK / FREAK of OpenCV 2.4) are upstream code this library does not carry.
+void DescriptorsMatcher::extractDescriptorsFromPatches(const std::vector<cv::Mat>& patchesVector, cv::Mat& descriptors) {
+    if (extractor_type_ != "SIFT")
+        throw std::runtime_error("fm3d: extractDescriptorsFromPatches runs on the GPU for ExtractorType SIFT only (settings: " +
+                                 extractor_type_ + ")");
+    const int n = (int)patchesVector.size();
+    if (n == 0) { descriptors = cv::Mat(); return; }
+    const int S = patchesVector[0].rows;
+    std::vector<uint8_t> packed((size_t)n * S * S);
+    for (int k = 0; k < n; k++) {
+        const cv::Mat& p = patchesVector[k];
+        if (p.rows != S || p.cols != S || p.type() != CV_8UC1) throw std::runtime_error("fm3d: patches must be square CV_8UC1 of one size");
+        for (int r = 0; r < S; r++) memcpy(packed.data() + ((size_t)k * S + r) * S, p.ptr<uint8_t>(r), (size_t)S);
+    }
+    descriptors = cv::Mat::zeros(cv::Size(128, n), CV_32F);
+    fm3d_ctx* ctx = host_ctx();
+    check(ctx, fm3d_describe_patches_sift(ctx, packed.data(), n, S, descriptors.ptr<float>()), "extractDescriptorsFromPatches");
 }
 
 // -------------------------------------------------------------------- SingleCameraTriangulator

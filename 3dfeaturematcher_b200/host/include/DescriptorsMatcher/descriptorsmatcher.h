@@ -5,9 +5,11 @@
 // factories of OpenCV 2.4 nonfree) are upstream of the hot path and out of scope: features are
 // injected with setFeatures() (or taken from the output arguments if the caller pre-filled
 // them); the three compare* methods then behave as in the reference, with the exact
-// brute-force search replacing FLANN.
+// brute-force search replacing FLANN.  extractDescriptorsFromPatches (:133-174) runs on the GPU
+// for ExtractorType SIFT (fm3d_describe_patches_sift).
 #ifndef FM3D_HOST_DESCRIPTORSMATCHER_H_
 #define FM3D_HOST_DESCRIPTORSMATCHER_H_
+#include <string>
 #include <vector>
 #include "../../fm3d_cv.h"
 
@@ -39,5 +41,6 @@ private:
     std::vector<std::vector<cv::DMatch> > matches_;
     std::vector<unsigned char> mutual_;
     bool binary_, have_features_;
+    std::string extractor_type_;
 };
 #endif

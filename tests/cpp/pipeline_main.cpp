@@ -130,6 +130,12 @@ int main(int argc, char** argv) {
     } else {
         fwrite(&cs, 4, 1, o);
     }
+    // MOSAIC descriptors of the rectified patches (main.cpp:182-183)
+    cv::Mat patchDescriptors;
+    dm.extractDescriptorsFromPatches(patchesVector, patchDescriptors);
+    int dr = patchDescriptors.rows, dc = patchDescriptors.cols;
+    fwrite(&dr, 4, 1, o); fwrite(&dc, 4, 1, o);
+    if (dr > 0) fwrite(patchDescriptors.data, 4, (size_t)dr * dc, o);
     fclose(o);
     std::cout << nm << " matches, " << np << " inliers, " << nn << " normals, patches " << S << "x" << S << std::endl;
     return 0;

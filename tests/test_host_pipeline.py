@@ -139,8 +139,10 @@ def _read_result(path):
         cn = np.frombuffer(b, np.float64, 3, o); o += 24
         cpts = np.frombuffer(b, np.float64, 3 * cs, o).reshape(-1, 3); o += 24 * cs
         circ = dict(normal=cn, pts=cpts)
+    dr, dc = struct.unpack_from("ii", b, o); o += 8
+    desc = np.frombuffer(b, np.float32, dr * dc, o).reshape(dr, dc); o += 4 * dr * dc
     assert o == len(b)
-    return dict(circular=circ, helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
+    return dict(patch_descriptors=desc, circular=circ, helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
                 patches=patches, last_nb=last_nb, gravity=gravity, S=S)
 
 
@@ -204,6 +206,12 @@ def test_main_cpp_call_sequence_on_the_adapters(tmp_path):
     o_c, o_n = ocv.circular_neighborhood(res["kept"][0], np.zeros(3), 0.16, 15, 5)
     np.testing.assert_allclose(res["circular"]["pts"], o_c, rtol=0, atol=1e-13)
     np.testing.assert_allclose(res["circular"]["normal"], o_n, rtol=0, atol=1e-15)
+    # extractDescriptorsFromPatches (main.cpp:182-183, ExtractorType SIFT): one row per patch
+    from oracle import sift_patch_np as sp
+    o_desc = sp.describe_patches_sift(res["patches"])
+    assert res["patch_descriptors"].shape == (len(res["patches"]), 128)
+    ddiff = np.abs(res["patch_descriptors"] - o_desc)
+    assert ddiff.max() <= 1 and (ddiff == 0).mean() > 0.97
     # computeSquareNeighborhoodsByNormals: last grid point of every feature
     S = res["S"]
     ref_last = np.array([-eps_m + 0.01 * cmpp * (S - 1), -eps_m + 0.01 * cmpp * (S - 1), 0.0, 1.0])

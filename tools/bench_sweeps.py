@@ -120,6 +120,7 @@ def c3_pipeline(ctx, stream):
     frames = torch.empty((nq, 16), dtype=torch.float64, device=dev)
     S = api.patch_size(0.16, 0.25)
     patches = torch.empty((nq, S, S), dtype=torch.uint8, device=dev)
+    pdesc = torch.empty((nq, 128), dtype=torch.float32, device=dev)
     g = np.array([0.006, 0.99992, -0.011])
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
     out = {}
@@ -143,8 +144,10 @@ def c3_pipeline(ctx, stream):
             ev[5].record(stream)
             ctx.extract_patches_dev(frames.data_ptr(), n_inl, 0.16, 0.25, patches.data_ptr(), None)
             ev[6].record(stream)
+            ctx.describe_patches_sift_dev(patches.data_ptr(), n_inl, S, pdesc.data_ptr())
+            ev[7].record(stream)
         stream.synchronize()
-    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(6)]
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(7)]
     st = ctx.normals_stats()
     src_h = src[:n_inl].cpu().numpy(); qi_h = qi[:n_match].cpu().numpy()
     feat = qi_h[src_h]                       # query keypoint of every inlier
@@ -155,13 +158,28 @@ def c3_pipeline(ctx, stream):
     pyr_bytes = sum(2 * 1.25 * (W >> l) * (H >> l) for l in range(3))
     print(json.dumps({"case": "c3_4k_20k_one_gpu", "gen_s": gen_s, "matches": n_match, "inliers": n_inl, "ok": int(ok.sum()),
                       "median_angle_to_gt_deg": float(np.median(ang[ok])), "p99_angle_to_gt_deg": float(np.percentile(ang[ok], 99)),
-                      "stage_ms": {"match+nndr": ms[0], "triangulate": ms[1], "pyramids": ms[2], "normals": ms[3], "frames": ms[4], "patches": ms[5]},
+                      "stage_ms": {"match+nndr": ms[0], "triangulate": ms[1], "pyramids": ms[2], "normals": ms[3], "frames": ms[4], "patches": ms[5], "patch_descriptors": ms[6]},
                       "features_per_s_match_tri_normals": n_match / (t_core * 1e-3),
                       "matcher_tflops": 256.0 * nq * nt / (ms[0] * 1e-3) / 1e12,
                       "pyrdown_gbs": pyr_bytes / (ms[2] * 1e-3) / 1e9, "hbm_peak_gbs": PEAKS.get("hbm_gbs"),
+                      "patch_descriptors_per_s": n_inl / (ms[6] * 1e-3), "patch_descriptors_nonzero": int((pdesc[:n_inl] != 0).sum().item()),
                       "patches_per_s": n_inl / (ms[5] * 1e-3), "patch_px_per_s": n_inl * S * S / (ms[5] * 1e-3),
                       "normals_pixel_evals_per_s": (st["pixel_evals_value"] + st["pixel_evals_jacobian"]) / (ms[3] * 1e-3),
                       "passes_global_taps": st["passes_slow"]}), flush=True)
+
+
+def describe_sweep(ctx, stream):
+    """K9 alone: SIFT descriptors of n rectified patches (extractDescriptorsFromPatches), S = 128 and 64."""
+    dev = torch.device("cuda", 0)
+    for S, n in ((128, 16384), (64, 65536), (40, 65536)):
+        patches = torch.randint(0, 256, (n, S, S), dtype=torch.uint8, device=dev)
+        desc = torch.empty((n, 128), dtype=torch.float32, device=dev)
+        fn = lambda: ctx.describe_patches_sift_dev(patches.data_ptr(), n, S, desc.data_ptr())
+        ms = timed(stream, fn, 3)
+        # algorithmic work per pixel: separable 13-tap symmetric blur 2 x 19 flop, gradient + weight + trilinear split ~ 60 flop
+        print(json.dumps({"case": "describe_patches_sift", "S": S, "patches": n, "ms": ms, "patches_per_s": n / (ms * 1e-3),
+                          "pixels_per_s": n * S * S / (ms * 1e-3), "hbm_gbs_compulsory": (n * S * S + n * 512) / (ms * 1e-3) / 1e9,
+                          "hbm_peak_gbs": PEAKS.get("hbm_gbs"), "tflops_fp32_algorithmic": n * S * S * 98.0 / (ms * 1e-3) / 1e12}), flush=True)
 
 
 if __name__ == "__main__":
@@ -172,6 +190,8 @@ if __name__ == "__main__":
         match_sweep(ctx, stream, [int(a) for a in sys.argv[2:]] if which == "match" and len(sys.argv) > 2 else [10000, 50000, 100000, 200000])
     if which in ("all", "normals"):
         normals_stress(ctx, stream, int(sys.argv[2]) if len(sys.argv) > 2 else 2000)
+    if which in ("all", "describe"):
+        describe_sweep(ctx, stream)
     if which in ("c3",):
         c3_pipeline(ctx, stream)
     ctx.close()
