@@ -25,7 +25,9 @@ namespace {
 
 constexpr int DESC_NT = 512;
 constexpr int DESC_KHALF = 6;        // ksize 13 for sigma 1.5199: cvRound(sigma * 8 + 1) | 1
-constexpr int DESC_BINS = 34;        // 2 x 2 central cells x 8 orientations + 2 spill slots (see o0 == -1 below)
+constexpr int DESC_SLOTS = 34;       // 2 x 2 central cells x 8 orientations + 2 spill slots (see o0 == -1 below)
+constexpr int DESC_ROWS = 9;         // accumulator rows per thread: 8 orientation bins x float4 (cells) + the spill row
+constexpr int DESC_HALO = 8;         // reflected columns kept on either side of a patch row (>= DESC_KHALF, 16-byte aligned)
 
 struct DescArgs {
     int S, n;
@@ -33,6 +35,7 @@ struct DescArgs {
     float cos_t, sin_t;              // already divided by hist_width
     float ori, bins_per_rad, exp_scale;
     int pt;                          // keypoint pixel (both coordinates)
+    int bufA_floats;                 // S * (S + 2 DESC_HALO)
 };
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -49,14 +52,12 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
     const float eps = 2.220446049250313e-16f;
     const float ax = fabsf(x), ay = fabsf(y);
-    float a;
-    if (ax >= ay) {
-        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps)), c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-    } else {
-        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps)), c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.0f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-    }
+    const bool ge = ax >= ay;
+    // one approximate division (2 ulp): the polynomial itself is only good to 0.3 degrees, and a bin
+    // decision can only change within ~1e-5 degrees of a bin edge
+    const float c = __fdividef(ge ? ay : ax, __fadd_rn(ge ? ax : ay, eps)), c2 = __fmul_rn(c, c);
+    float a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    if (!ge) a = __fsub_rn(90.0f, a);
     if (x < 0) a = __fsub_rn(180.0f, a);
     if (y < 0) a = __fsub_rn(360.0f, a);
     return a;
@@ -78,74 +79,104 @@ __device__ __forceinline__ int desc_order(int k) {
     return k - 2;
 }
 
+__device__ __forceinline__ float sqrt_approx(float a) {   // MUFU.RSQ-based, 2^-22 relative
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+
+// i / S and i % S for 0 <= i < S*S <= 2^15 without the integer-division sequence
+__device__ __forceinline__ void divmod_small(int i, int S, float inv_S, int& q, int& rem) {
+    q = __float2int_rd(((float)i + 0.5f) * inv_S);
+    rem = i - q * S;
+}
+
 __global__ void __launch_bounds__(DESC_NT, 1)
 describe_sift_kernel(const DescArgs A, const uint8_t* __restrict__ patches, float* __restrict__ desc) {
     extern __shared__ __align__(16) float sm[];
     const int S = A.S, S2 = S * S, tid = threadIdx.x;
-    float* bufA = sm;                // float(patch), then the blurred image
-    float* bufB = sm + S2;           // row pass, then the private accumulators [DESC_BINS][DESC_NT]
-    __shared__ float part[DESC_NT / 32][DESC_BINS];
-    __shared__ float hist[DESC_BINS];
+    const int SA = S + 2 * DESC_HALO;            // bufA row stride: DESC_HALO reflected columns on either side
+    float* bufA = sm;                            // float(patch) with column halo; later the blurred image (stride S)
+    float* bufB = sm + A.bufA_floats;            // row pass with DESC_KHALF halo rows above and below; later the accumulators
+    __shared__ float part[DESC_NT / 32][DESC_SLOTS];
+    __shared__ float hist[DESC_SLOTS];
     const size_t f = blockIdx.x;
     const uint8_t* __restrict__ src = patches + f * (size_t)S2;
+    const float inv_S = 1.0f / (float)S;
 
-    // u8 -> float (16-byte loads when the patch start is aligned: S even => S2 % 4 == 0)
-    if ((S2 & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    // u8 -> float (16-byte loads when rows and the patch start are 16-byte aligned)
+    if ((S & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
         const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        const int qpr = S >> 4;                  // 16-pixel groups per row
         for (int q = tid; q < (S2 >> 4); q += DESC_NT) {
+            const int r = q / qpr, c = (q - r * qpr) << 4;
             const uint4 v = s4[q];
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            float4* dst = reinterpret_cast<float4*>(bufA + r * SA + DESC_HALO + c);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 float4 o;
                 o.x = fm3d_u8f(w[k] & 255u); o.y = fm3d_u8f((w[k] >> 8) & 255u);
                 o.z = fm3d_u8f((w[k] >> 16) & 255u); o.w = fm3d_u8f(w[k] >> 24);
-                reinterpret_cast<float4*>(bufA)[4 * q + k] = o;
+                dst[k] = o;
             }
         }
     } else {
-        for (int i = tid; i < S2; i += DESC_NT) bufA[i] = fm3d_u8f(src[i]);
+        for (int i = tid; i < S2; i += DESC_NT) {
+            int r, c;
+            divmod_small(i, S, inv_S, r, c);
+            bufA[r * SA + DESC_HALO + c] = fm3d_u8f(src[i]);
+        }
+    }
+    // BORDER_REFLECT_101 columns: -k <- k, S-1+k <- S-1-k (read from global: no barrier needed before)
+    for (int i = tid; i < 2 * DESC_KHALF * S; i += DESC_NT) {
+        const int r = i / (2 * DESC_KHALF), k = i - r * (2 * DESC_KHALF);
+        const int kk = k < DESC_KHALF ? k + 1 : k - DESC_KHALF + 1;            // 1..KHALF
+        const int cdst = k < DESC_KHALF ? -kk : S - 1 + kk, csrc = k < DESC_KHALF ? kk : S - 1 - kk;
+        bufA[r * SA + DESC_HALO + cdst] = fm3d_u8f(src[r * S + csrc]);
     }
     __syncthreads();
-    // row pass (symmetric form: k0 x0 + sum_i k_i (x_-i + x_+i))
+    // row pass (symmetric form: k0 x0 + sum_i k_i (x_-i + x_+i)) -> bufB rows KHALF .. KHALF+S-1
     for (int i = tid; i < S2; i += DESC_NT) {
-        const int r = i / S, c = i - r * S;
-        const float* row = bufA + r * S;
-        float s = __fmul_rn(A.kern[0], row[c]);
-        if (c >= DESC_KHALF && c + DESC_KHALF < S) {
+        int r, c;
+        divmod_small(i, S, inv_S, r, c);
+        const float* px = bufA + r * SA + DESC_HALO + c;
+        float s = __fmul_rn(A.kern[0], px[0]);
 #pragma unroll
-            for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(row[c - k], row[c + k]), s);
-        } else {
-#pragma unroll
-            for (int k = 1; k <= DESC_KHALF; k++)
-                s = fmaf(A.kern[k], __fadd_rn(row[reflect101(c - k, S)], row[reflect101(c + k, S)]), s);
-        }
-        bufB[i] = s;
+        for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k], px[k]), s);
+        bufB[i + DESC_KHALF * S] = s;
     }
     __syncthreads();
-    // column pass
+    // BORDER_REFLECT_101 rows of the row-pass image
+    for (int i = tid; i < 2 * DESC_KHALF * S; i += DESC_NT) {
+        int k, c;
+        divmod_small(i, S, inv_S, k, c);
+        const int kk = k < DESC_KHALF ? k + 1 : k - DESC_KHALF + 1;
+        const int rdst = k < DESC_KHALF ? -kk : S - 1 + kk, rsrc = k < DESC_KHALF ? kk : S - 1 - kk;
+        bufB[(rdst + DESC_KHALF) * S + c] = bufB[(rsrc + DESC_KHALF) * S + c];
+    }
+    __syncthreads();
+    // column pass -> bufA (stride S)
     for (int i = tid; i < S2; i += DESC_NT) {
-        const int r = i / S, c = i - r * S;
-        float s = __fmul_rn(A.kern[0], bufB[i]);
-        if (r >= DESC_KHALF && r + DESC_KHALF < S) {
+        const float* px = bufB + i + DESC_KHALF * S;
+        float s = __fmul_rn(A.kern[0], px[0]);
 #pragma unroll
-            for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(bufB[i - k * S], bufB[i + k * S]), s);
-        } else {
-#pragma unroll
-            for (int k = 1; k <= DESC_KHALF; k++)
-                s = fmaf(A.kern[k], __fadd_rn(bufB[reflect101(r - k, S) * S + c], bufB[reflect101(r + k, S) * S + c]), s);
-        }
+        for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k * S], px[k * S]), s);
         bufA[i] = s;
     }
     __syncthreads();
-    // private accumulators: acc[bin][tid]
-    float* acc = bufB;
+    // private accumulators: one float4 (the four central cells 2 dr + dc) per orientation bin and thread,
+    // row 8 = the two spill slots
+    float4* acc = reinterpret_cast<float4*>(bufB);
 #pragma unroll
-    for (int b = 0; b < DESC_BINS; b++) acc[b * DESC_NT + tid] = 0.0f;
+    for (int b = 0; b < DESC_ROWS; b++) acc[b * DESC_NT + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     // gradient histogram over the interior pixels (r, c in [1, S-2]), row-major as OpenCV walks them
     const int SI = S - 2;
+    const float inv_SI = 1.0f / (float)SI;
     for (int i = tid; i < SI * SI; i += DESC_NT) {
-        const int rr = i / SI, r = rr + 1, c = i - rr * SI + 1;
+        int rr, cc;
+        divmod_small(i, SI, inv_SI, rr, cc);
+        const int r = rr + 1, c = cc + 1;
         const float fi = (float)(r - A.pt), fj = (float)(c - A.pt);
         const float c_rot = __fsub_rn(__fmul_rn(fj, A.cos_t), __fmul_rn(fi, A.sin_t));
         const float r_rot = __fadd_rn(__fmul_rn(fj, A.sin_t), __fmul_rn(fi, A.cos_t));
@@ -153,8 +184,9 @@ describe_sift_kernel(const DescArgs A, const uint8_t* __restrict__ patches, floa
         const float cbin = __fsub_rn(__fadd_rn(c_rot, 2.0f), 0.5f) - 1.0f;
         const float* p = bufA + r * S + c;
         const float dx = __fsub_rn(p[1], p[-1]), dy = __fsub_rn(p[-S], p[S]);
-        const float w = expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), A.exp_scale));
-        const float mag = __fmul_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), w);
+        // weight in [0.94, 1] (|rot| < 0.5): ex2.approx is good to 1e-7 here, like cv::exp's table
+        const float w = __expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), A.exp_scale));
+        const float mag = __fmul_rn(sqrt_approx(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), w);
         float obin = __fmul_rn(__fsub_rn(fast_atan2_deg(dy, dx), A.ori), A.bins_per_rad);
         const float of = floorf(obin);
         obin = __fsub_rn(obin, of);
@@ -167,35 +199,58 @@ describe_sift_kernel(const DescArgs A, const uint8_t* __restrict__ patches, floa
         o0 = o0 < 0 ? o0 + 8 : o0;
         o0 = o0 >= 8 ? o0 - 8 : o0;
         const bool spill = o0 < 0;
-        o0 = spill ? 0 : (o0 & 7);                // & 7: memory safety only
-        const int o1 = spill ? 0 : ((o0 + 1) & 7);   // slot n folds onto bin 0
         const float v_r1 = __fmul_rn(mag, rbin), v_r0 = __fsub_rn(mag, v_r1);
         const float v_rc11 = __fmul_rn(v_r1, cbin), v_rc10 = __fsub_rn(v_r1, v_rc11);
         const float v_rc01 = __fmul_rn(v_r0, cbin), v_rc00 = __fsub_rn(v_r0, v_rc01);
-        const float v[4] = {v_rc00, v_rc01, v_rc10, v_rc11};
-#pragma unroll
-        for (int cell = 0; cell < 4; cell++) {    // cell = 2 dr + dc
-            const float v1 = __fmul_rn(v[cell], obin), v0 = __fsub_rn(v[cell], v1);
-            // v0 -> (cell, o0); with spill -> bin 1 of the cell one column to the left: the other central
-            // cell (dc = 1) or the spill slot of column 0 (dc = 0)
-            const int b0 = !spill ? cell * 8 + o0 : ((cell & 1) ? (cell - 1) * 8 + 1 : 32 + (cell >> 1));
-            float* a0 = acc + b0 * DESC_NT + tid;
-            float* a1 = acc + (cell * 8 + o1) * DESC_NT + tid;
-            *a0 = __fadd_rn(*a0, v0);
-            *a1 = __fadd_rn(*a1, v1);
+        float4 v1, v0;                            // .x .y .z .w = cells (0,0) (0,1) (1,0) (1,1)
+        v1.x = __fmul_rn(v_rc00, obin); v0.x = __fsub_rn(v_rc00, v1.x);
+        v1.y = __fmul_rn(v_rc01, obin); v0.y = __fsub_rn(v_rc01, v1.y);
+        v1.z = __fmul_rn(v_rc10, obin); v0.z = __fsub_rn(v_rc10, v1.z);
+        v1.w = __fmul_rn(v_rc11, obin); v0.w = __fsub_rn(v_rc11, v1.w);
+        if (!spill) {
+            o0 &= 7;                              // memory safety only
+            float4* a0 = acc + o0 * DESC_NT + tid;
+            float4* a1 = acc + ((o0 + 1) & 7) * DESC_NT + tid;      // slot n folds onto bin 0
+            float4 t = *a0;
+            t.x = __fadd_rn(t.x, v0.x); t.y = __fadd_rn(t.y, v0.y); t.z = __fadd_rn(t.z, v0.z); t.w = __fadd_rn(t.w, v0.w);
+            *a0 = t;
+            t = *a1;
+            t.x = __fadd_rn(t.x, v1.x); t.y = __fadd_rn(t.y, v1.y); t.z = __fadd_rn(t.z, v1.z); t.w = __fadd_rn(t.w, v1.w);
+            *a1 = t;
+        } else {
+            // v1 -> bin 0 of the proper cells; v0 -> bin 1 one column to the left: cell (dr,1) -> cell (dr,0),
+            // cell (dr,0) -> spill slot dr
+            float4* a = acc + tid;
+            float4 t = *a;
+            t.x = __fadd_rn(t.x, v1.x); t.y = __fadd_rn(t.y, v1.y); t.z = __fadd_rn(t.z, v1.z); t.w = __fadd_rn(t.w, v1.w);
+            *a = t;
+            a = acc + DESC_NT + tid;
+            t = *a;
+            t.x = __fadd_rn(t.x, v0.y); t.z = __fadd_rn(t.z, v0.w);
+            *a = t;
+            a = acc + 8 * DESC_NT + tid;
+            t = *a;
+            t.x = __fadd_rn(t.x, v0.x); t.y = __fadd_rn(t.y, v0.z);
+            *a = t;
         }
     }
     // fixed-order reduction: lanes (xor tree), then warps in order
     const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll 4
-    for (int b = 0; b < DESC_BINS; b++) {
-        float s = acc[b * DESC_NT + tid];
+#pragma unroll 3
+    for (int b = 0; b < DESC_ROWS; b++) {
+        float4 s = acc[b * DESC_NT + tid];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) part[wid][b] = s;
+        for (int o = 16; o > 0; o >>= 1) {
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+            s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+        }
+        if (lane == 0) {
+            if (b < 8) { part[wid][b] = s.x; part[wid][8 + b] = s.y; part[wid][16 + b] = s.z; part[wid][24 + b] = s.w; }
+            else { part[wid][32] = s.x; part[wid][33] = s.y; }
+        }
     }
     __syncthreads();
-    if (tid < DESC_BINS) {
+    if (tid < DESC_SLOTS) {
         float s = 0.0f;
         for (int w = 0; w < DESC_NT / 32; w++) s += part[w][tid];
         hist[tid] = s;
@@ -206,10 +261,10 @@ describe_sift_kernel(const DescArgs A, const uint8_t* __restrict__ patches, floa
     if (tid == 0) {
         // dst order: row 1 = {spill slot 32 at (1,0,1)}, cells 0, 1; row 2 = {slot 33}, cells 2, 3 (zeros add nothing)
         float nrm2 = 0.0f;
-        for (int k = 0; k < DESC_BINS; k++) { const float h = hist[desc_order(k)]; nrm2 = __fadd_rn(nrm2, __fmul_rn(h, h)); }
+        for (int k = 0; k < DESC_SLOTS; k++) { const float h = hist[desc_order(k)]; nrm2 = __fadd_rn(nrm2, __fmul_rn(h, h)); }
         const float thr = __fmul_rn(__fsqrt_rn(nrm2), 0.2f);
         nrm2 = 0.0f;
-        for (int k = 0; k < DESC_BINS; k++) {
+        for (int k = 0; k < DESC_SLOTS; k++) {
             const float val = fminf(hist[desc_order(k)], thr);
             nrm2 = __fadd_rn(nrm2, __fmul_rn(val, val));
         }
@@ -280,9 +335,10 @@ int fm3d_describe_patches_sift_dev(fm3d_ctx* ctx, const uint8_t* patches, int n,
     DescArgs A;
     if (!desc_args(S, n, A))
         return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "patch edge %d: the SIFT window of the reference's keypoint does not cover the patch", S);
-    const size_t s2 = (size_t)S * S * sizeof(float);
-    const size_t accb = (size_t)DESC_BINS * DESC_NT * sizeof(float);
-    const size_t smem = s2 + (s2 > accb ? s2 : accb);
+    A.bufA_floats = (S * (S + 2 * DESC_HALO) + 3) & ~3;      // the float4 accumulators follow: keep 16-byte alignment
+    const size_t rowpass = (size_t)(S + 2 * DESC_KHALF) * S * sizeof(float);
+    const size_t accb = (size_t)DESC_ROWS * DESC_NT * sizeof(float4);
+    const size_t smem = (size_t)A.bufA_floats * sizeof(float) + (rowpass > accb ? rowpass : accb);
     if (smem + 4096 > ctx->prop.sharedMemPerBlockOptin)
         return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "patch edge %d needs %zu bytes of shared memory", S, smem);
     FM3D_CUDA(ctx, cudaFuncSetAttribute(describe_sift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -393,6 +393,38 @@ def run_gpu_arm(args):
     nfev_alt = d_nfev[:n_inl_alt].cpu().numpy().astype(np.int64)
     npen_alt = d_npen[:n_inl_alt].cpu().numpy()
 
+    # ---- after the path ("patch extraction separately"): frames -> K8 patches -> K9 SIFT descriptors of
+    # this rank's refined features, device-resident, NOT part of `value`
+    EPS_M, CM_PP = 0.16, 0.25           # build/settings.yml Neighborhoods: epsilon 0.16 m, cmPerPixel 0.25 -> 128 x 128 patches
+    S_patch = api.patch_size(EPS_M, CM_PP)
+    device_step()                       # headline normals again (the fabs pass overwrote them)
+    with torch.cuda.stream(stream):
+        d_frames = torch.empty((max(n_inl, 1), 16), dtype=torch.float64, device=dev)
+        d_patches = torch.empty((max(n_inl, 1), S_patch, S_patch), dtype=torch.uint8, device=dev)
+        d_pdesc = torch.empty((max(n_inl, 1), 128), dtype=torch.float32, device=dev)
+    gravity = np.array([0.006, 0.99992, -0.011])
+
+    def after_path(events=None):
+        with torch.cuda.stream(stream):
+            if events: events[0].record(stream)
+            ctx.feature_frames_dev(d_xyz.data_ptr(), d_normals.data_ptr(), n_inl, gravity, d_frames.data_ptr())
+            if events: events[1].record(stream)
+            ctx.extract_patches_dev(d_frames.data_ptr(), n_inl, EPS_M, CM_PP, d_patches.data_ptr(), None)
+            if events: events[2].record(stream)
+            ctx.describe_patches_sift_dev(d_patches.data_ptr(), n_inl, S_patch, d_pdesc.data_ptr())
+            if events: events[3].record(stream)
+    for _ in range(2):
+        after_path()
+        flush_l2()
+    barrier()
+    ev_after = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(alt_steps)]
+    for s_ in range(alt_steps):
+        after_path(ev_after[s_])
+        flush_l2()
+    barrier()
+    after_ms = [sum(ev_after[s_][j].elapsed_time(ev_after[s_][j + 1]) for s_ in range(alt_steps)) / alt_steps for j in range(3)]
+    pdesc_nonzero = int((d_pdesc[:n_inl] != 0).sum().item())
+
     # ---- reduce over ranks: max time, summed features
     tm = torch.tensor([t_dev_ms, t_e2e * 1e3, t_alt_ms], dtype=torch.float64, device=dev)
     feats = torch.tensor([float(n_match), float(hm), float(n_match_alt)], dtype=torch.float64, device=dev)
@@ -488,6 +520,15 @@ def run_gpu_arm(args):
                 "nfev_mean_per_level": nfev_alt.mean(0).tolist(),
                 "passes": stats_alt["passes_value"] + stats_alt["passes_jacobian"] + stats_alt["passes_fused"],
                 "cpu_baseline_features_per_s": None if cpu_alt is None else cpu_alt["features_per_s"]},
+            "after_path_rank0": {
+                "note": "frames -> rectified patches (K8) -> SIFT descriptors of the patches (K9, extractDescriptorsFromPatches) for "
+                        "rank 0's refined features, device-resident, CUDA events; not part of `value`",
+                "patch_edge": S_patch, "features": int(n_inl),
+                "ms": {"frames": after_ms[0], "patches": after_ms[1], "patch_descriptors": after_ms[2]},
+                "patches_per_s": n_inl / (after_ms[1] * 1e-3) if after_ms[1] > 0 else None,
+                "patch_descriptors_per_s": n_inl / (after_ms[2] * 1e-3) if after_ms[2] > 0 else None,
+                "patches_hbm_write_gbs": n_inl * S_patch * S_patch / (after_ms[1] * 1e-3) / 1e9 if after_ms[1] > 0 else None,
+                "descriptor_values_nonzero": pdesc_nonzero},
             "wall_s_device_arm": wall_dev, "gpu": info["name"],
         }
         emit(out)

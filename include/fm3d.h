@@ -354,7 +354,7 @@ int fm3d_circular_neighborhoods(fm3d_ctx* ctx, const double* points, double* nor
  * described by cv::SIFT::compute (nOctaveLayers 3, sigma 1.6).  patches: n x S x S u8 as written by
  * fm3d_extract_patches; descriptors: n x 128 f32, integer-valued in [0, 255] (cv::SIFT's CV_32F
  * output), row k = patch k (the reference copies descriptorsVector[k] into row k, :168-172).
- * 8 <= S <= 164 (two S x S float planes in shared memory). */
+ * 8 <= S <= 160 (two padded S x S float planes in shared memory). */
 int fm3d_describe_patches_sift(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, float* descriptors);
 int fm3d_describe_patches_sift_dev(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, float* descriptors);
 

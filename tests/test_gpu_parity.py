@@ -669,7 +669,7 @@ def test_describe_patches_sift_golden_vectors(ctx):
 def test_describe_patches_sift_against_oracle_and_edges(ctx, api):
     from oracle import sift_patch_np as sp
     rng = np.random.default_rng(123)
-    for S, n in ((128, 40), (130, 5), (164, 3), (66, 17), (9, 6)):
+    for S, n in ((128, 40), (130, 5), (160, 3), (66, 17), (9, 6)):
         patches = rng.integers(0, 256, (n, S, S), dtype=np.uint8)
         # smooth half of them (box filter) so that orientations are not uniform
         sm = patches.astype(np.float32)
