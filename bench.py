@@ -70,6 +70,18 @@ def emit(obj):
     _JSON_OUT.flush()
 
 
+WORKLOAD, SCALING = "c2", "weak"
+
+
+def select_workload(name, n_ranks):
+    """`c2` (default, the driver's contract): BASELINE configs[1], 5 000 keypoints PER GPU (weak scaling).
+    `c3`: BASELINE configs[2], one 4K pair with 20 000 keypoints in total, sharded over the ranks (strong scaling)."""
+    global WIDTH, HEIGHT, N_KP, N_DISTRACT, SEED, WORKLOAD, SCALING
+    if name == "c3":
+        WIDTH, HEIGHT, SEED, WORKLOAD, SCALING = 3840, 2160, 1002, "c3", "strong"
+        N_KP, N_DISTRACT = 20000 // n_ranks, 4000 // n_ranks
+
+
 def make_workload(n_ranks, rank):
     """Global problem: one stereo pair with n_ranks*N_KP query keypoints; returns the global
     arrays (every rank generates the same ones; rank 0's copy is the one that gets broadcast)."""
@@ -186,7 +198,7 @@ def run_reference_arm(args):
     out = {
         "impl": "reference", "metric": "features/sec (match+triangulate+normal-opt)", "value": v, "unit": "features/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(t_all)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(1),
         "cpu_baseline": {"value": v, "unit": "features/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,7 +207,7 @@ def run_reference_arm(args):
 
 
 def workload_config(n_ranks):
-    return {"workload": f"BASELINE configs[1]: {WIDTH}x{HEIGHT} synthetic stereo pair, {N_KP} SIFT-128 float keypoints per GPU "
+    return {"workload": f"BASELINE configs[{2 if WORKLOAD == 'c3' else 1}]: {WIDTH}x{HEIGHT} synthetic stereo pair, {N_KP} SIFT-128 float keypoints per GPU "
                         f"(+{N_DISTRACT} distractors), pixelsRay {PIXELS_RAY}, pyramids {PYRAMIDS} (4 LM stages), NNDR {NNDR_EPS}",
             "penalty_mode": PENALTY_NAMES[PENALTY], "normal_search": "fast kernel: fp32 offset-form geometry, analytic Jacobian, fp64 LM state",
             "per_gpu_query_keypoints": N_KP, "global_query_keypoints": N_KP * n_ranks,
@@ -495,7 +507,7 @@ def run_gpu_arm(args):
         out = {
             "metric": "features/sec (match+triangulate+normal-opt)", "value": value, "unit": "features/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": tot_feat_e2e * args.steps / (t_e2e_ms * 1e-3), "unit": "features/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e_ms / args.steps},
@@ -544,7 +556,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fm3d", choices=["fm3d", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2: BASELINE configs[1], weak scaling (default, the driver's contract); c3: configs[2], 4K / 20k keypoints sharded")
     args = ap.parse_args()
+    select_workload(args.workload, 1 if args.impl == "reference" else int(os.environ.get("WORLD_SIZE", "1")))
     _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
