@@ -9,6 +9,8 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/fm3d.h"
 #include "include/DescriptorsMatcher/descriptorsmatcher.h"
@@ -19,15 +21,56 @@
 
 namespace {
 
-fm3d_ctx* host_ctx() {
-    static fm3d_ctx* ctx = nullptr;
-    if (!ctx) {
-        int dev = 0;
-        if (const char* e = getenv("FM3D_DEVICE")) dev = atoi(e);
-        int rc = fm3d_ctx_create(dev, &ctx);
-        if (rc != FM3D_OK) throw std::runtime_error("fm3d: no usable sm_100 GPU (libfm3d has no CPU path), code " + std::to_string(rc));
+// One fm3d_ctx per GPU of the process.  FM3D_DEVICE=<i> picks a single device (default 0);
+// FM3D_DEVICES=<i,j,...> lists several: the first is the primary context (matching, triangulation,
+// patches), all of them share the per-feature normal search, each with its own copy of camera, g12 and
+// image pyramids ("each GPU uploads its own copy"; host buffers are the interface, so no
+// collective is needed inside one process).
+std::vector<fm3d_ctx*>& host_ctxs() {
+    static std::vector<fm3d_ctx*> ctxs;
+    if (ctxs.empty()) {
+        std::vector<int> devs;
+        if (const char* e = getenv("FM3D_DEVICES")) {
+            for (const char* p = e; *p;) {
+                char* end = nullptr;
+                const long d = strtol(p, &end, 10);
+                if (end == p) break;
+                devs.push_back((int)d);
+                p = *end == ',' ? end + 1 : end;
+            }
+        }
+        if (devs.empty()) devs.push_back(getenv("FM3D_DEVICE") ? atoi(getenv("FM3D_DEVICE")) : 0);
+        for (size_t k = 0; k < devs.size(); k++) {
+            fm3d_ctx* c = nullptr;
+            const int rc = fm3d_ctx_create(devs[k], &c);
+            if (rc != FM3D_OK) {
+                for (size_t j = 0; j < ctxs.size(); j++) fm3d_ctx_destroy(ctxs[j]);
+                ctxs.clear();
+                throw std::runtime_error("fm3d: no usable sm_100 GPU at device " + std::to_string(devs[k]) +
+                                         " (libfm3d has no CPU path), code " + std::to_string(rc));
+            }
+            ctxs.push_back(c);
+        }
     }
-    return ctx;
+    return ctxs;
+}
+
+fm3d_ctx* host_ctx() { return host_ctxs()[0]; }
+
+// fn(context index) on every context, concurrently when there are several; returns the first failure
+template <typename F>
+void for_each_ctx(const char* what, F fn) {
+    std::vector<fm3d_ctx*>& cs = host_ctxs();
+    std::vector<int> rc(cs.size(), FM3D_OK);
+    if (cs.size() == 1) {
+        rc[0] = fn(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < cs.size(); k++) th.emplace_back([&rc, &fn, k]() { rc[k] = fn((int)k); });
+        for (size_t k = 0; k < th.size(); k++) th[k].join();
+    }
+    for (size_t k = 0; k < cs.size(); k++)
+        if (rc[k] != FM3D_OK) throw std::runtime_error(std::string("fm3d: ") + what + " (context " + std::to_string(k) + "): " + fm3d_last_error(cs[k]));
 }
 
 void check(fm3d_ctx* ctx, int rc, const char* what) {
@@ -220,12 +263,16 @@ SingleCameraTriangulator::SingleCameraTriangulator(cv::FileStorage& settings)
     settings["Neighborhoods"]["pyramids"] >> pyramids_;
     settings["Neighborhoods"]["epsilon"] >> patch_eps_;
     settings["Neighborhoods"]["cmPerPixel"] >> patch_cmpp_;
-    check(ctx_, fm3d_set_camera(ctx_, K, dist, z_threshold_min_, z_threshold_max_), "set_camera");
+    const double zmin = z_threshold_min_, zmax = z_threshold_max_;
+    for_each_ctx("set_camera", [&](int k) { return fm3d_set_camera(host_ctxs()[k], K, dist, zmin, zmax); });
 }
 
 void SingleCameraTriangulator::setImages(const cv::Mat& img1, const cv::Mat& img2) {
     img_1_ = img1; img_2_ = img2;  // shallow, like new cv::Mat(img) in the reference (:118-119)
-    check(ctx_, fm3d_set_images(ctx_, img1.data, img2.data, img1.cols, img1.rows, (int)img1.step(), pyramids_), "set_images");
+    const int levels = pyramids_;
+    for_each_ctx("set_images", [&](int k) {
+        return fm3d_set_images(host_ctxs()[k], img1.data, img2.data, img1.cols, img1.rows, (int)img1.step(), levels);
+    });
 }
 
 void SingleCameraTriangulator::setg12(const cv::Vec3d& T1, const cv::Vec3d& T2, const cv::Vec3d& rod1, const cv::Vec3d& rod2,
@@ -235,7 +282,7 @@ void SingleCameraTriangulator::setg12(const cv::Vec3d& T1, const cv::Vec3d& T2, 
         throw std::runtime_error("fm3d: setg12 failed");
     for (int i = 0; i < 16; i++) g_12_.val[i] = out[i];
     g12 = g_12_;
-    check(ctx_, fm3d_set_g12(ctx_, out), "set_g12");
+    for_each_ctx("set_g12", [&](int k) { return fm3d_set_g12(host_ctxs()[k], out); });
 }
 
 void SingleCameraTriangulator::setKeypoints(const std::vector<cv::KeyPoint>& kpts1, const std::vector<cv::KeyPoint>& kpts2,
@@ -483,8 +530,16 @@ void NormalOptimizer::computeOptimizedNormals(std::vector<cv::Vec3d>& points3D, 
     std::vector<double> xyz((size_t)n * 3), normals((size_t)n * 3), cost(n);
     std::vector<int32_t> status(n), nfev((size_t)n * L1), npen(n);
     for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) xyz[3 * i + c] = points3D[i][c];
-    check(ctx, fm3d_optimize_normals(ctx, xyz.data(), n, sct_->pixelsRay(), epsilon_lmmin_, penalty_mode_, normals.data(),
-                                     status.data(), nfev.data(), npen.data(), cost.data()), "optimize_normals");
+    // features are independent: contiguous shards, one per GPU context, written into disjoint ranges
+    (void)ctx;
+    const int G = (int)host_ctxs().size(), r = sct_->pixelsRay(), pm = penalty_mode_;
+    const double eps = epsilon_lmmin_;
+    for_each_ctx("optimize_normals", [&](int k) {
+        const int lo = (int)((long long)n * k / G), hi = (int)((long long)n * (k + 1) / G);
+        if (hi <= lo) return (int)FM3D_OK;
+        return fm3d_optimize_normals(host_ctxs()[k], xyz.data() + 3 * (size_t)lo, hi - lo, r, eps, pm, normals.data() + 3 * (size_t)lo,
+                                     status.data() + lo, nfev.data() + (size_t)lo * L1, npen.data() + lo, cost.data() + lo);
+    });
     status_.assign(status.begin(), status.end());
     nfev_.assign(n, 0);
     for (int i = 0; i < n; i++) for (int l = 0; l < L1; l++) nfev_[i] += nfev[(size_t)i * L1 + l];

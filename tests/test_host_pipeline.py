@@ -24,7 +24,7 @@ def build_pipeline_main():
     if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(d) for d in deps + [lib]):
         os.makedirs(os.path.dirname(EXE), exist_ok=True)
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([gxx, "-O2", "-std=c++17", "-I" + os.path.join(HOST, "include"), "-I" + HOST,
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(HOST, "include"), "-I" + HOST,
                                "-I" + os.path.join(ROOT, "include")] + srcs +
                               ["-L" + os.path.dirname(lib), "-lfm3d", "-Wl,-rpath," + os.path.dirname(lib), "-o", EXE])
     return EXE
@@ -216,3 +216,27 @@ def test_main_cpp_call_sequence_on_the_adapters(tmp_path):
     S = res["S"]
     ref_last = np.array([-eps_m + 0.01 * cmpp * (S - 1), -eps_m + 0.01 * cmpp * (S - 1), 0.0, 1.0])
     np.testing.assert_allclose(res["last_nb"], (res["frames"] @ ref_last)[:, :3], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_adapters_shard_the_normal_search_over_the_gpus_of_the_process(tmp_path):
+    """FM3D_DEVICES=0,1: every context gets its own camera / g12 / pyramids and a contiguous shard of the
+    features (host threads, no collective); results must be byte-identical to the single-GPU run."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in the process")
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    tmp = str(tmp_path)
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp)
+    outs = []
+    for devices in ("0", "0,1", "1,0"):
+        env = dict(os.environ, FM3D_PENALTY="2", FM3D_NO_PATCH_FILES="1", FM3D_DEVICES=devices)
+        out = os.path.join(tmp, f"result_{devices.replace(',', '_')}.bin")
+        p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), os.path.join(tmp, "features.bin"), out],
+                           capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] == outs[2]
+    assert len(_read_result(os.path.join(tmp, "result_0_1.bin"))["normals"]) >= 20
