@@ -174,6 +174,7 @@ static int* fm3d_option_slot(fm3d_ctx* ctx, const char* key) {
     if (!strcmp(key, "normals_fuse")) return &ctx->opt_normals_fuse;
     if (!strcmp(key, "normals_memo")) return &ctx->opt_normals_memo;
     if (!strcmp(key, "normals_groups")) return &ctx->opt_normals_groups;
+    if (!strcmp(key, "normals_sweep_batch")) return &ctx->opt_normals_sweep_batch;
     return nullptr;
 }
 

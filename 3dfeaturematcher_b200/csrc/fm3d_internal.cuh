@@ -48,6 +48,7 @@ struct fm3d_ctx {
     int opt_normals_groups = 0;    // fast kernel: feature pipelines per CTA; 0 = automatic (2 when there are more features than SMs)
     int opt_normals_memo = 1;      // fast kernel: trials whose fp32 coefficients equal the iterate's are not re-evaluated
     int opt_normals_fuse = 1;      // fast kernel: Jacobian evaluated together with the first trial of an iteration
+    int opt_normals_sweep_batch = 4;  // fast kernel, dense sweep: candidates per pass (1: one pass per candidate)
     int opt_normals_fast = 1;      // 1: fm3d_normals_fast.cu (default), 0: the faithful fp64 kernel
     // camera
     fm3d_cam cam{};

@@ -53,6 +53,7 @@ struct NormalsArgs {
     int win_tma[FM3D_MAX_LEVELS];       // fast kernel: level window loaded by one TMA tile
     int fuse_trials;                    // fast kernel: evaluate the Jacobian with the first trial
     int memo_trials;                    // fast kernel: answer coefficient-identical trials without a pass
+    int sweep_batch;                    // fast kernel, mode 2: > 1 evaluates the candidate grid in batches of SWEEP_B per pass
     int groups;                         // fast kernel: independent feature pipelines per CTA (1 or 2)
     int group_smem;                     // fast kernel: bytes of shared memory per group
     float2* rays_g;

@@ -115,12 +115,17 @@ struct LevelConst {
 };
 
 constexpr int MAX_GROUPS = 4;
+constexpr int SWEEP_B = 4;           // mode 2: candidate normals evaluated per pass (one barrier pair per batch)
 struct GroupCtl {
     RowTable rows;
     double red[16 * 6];
     unsigned wflags[16];
     FastShared S;
     FastPass PP;
+    FastPass PPk[SWEEP_B];           // mode 2, batched: the candidates of the current batch ...
+    double wk[SWEEP_B];              // ... and their penalty weights
+    unsigned wflagsk[16 * SWEEP_B];
+    int resume_at;                   // mode 2, batched: candidate the one-by-one loop takes over at (or -1)
     uint64_t bar;
 };
 
@@ -415,6 +420,43 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
         acc.s3 += lo2(acc2.s3) + hi2(acc2.s3);
         acc.s4 += lo2(acc2.s4) + hi2(acc2.s4);
         acc.s5 += lo2(acc2.s5) + hi2(acc2.s5);
+    }
+}
+
+// Mode 2 (dense candidate sweep): NE candidate normals per pass.  Every thread walks the pixel pairs the
+// single-candidate loop gives it, in the same order, and evaluates all candidates of the batch on a pair
+// before moving on: the per-candidate sums are bit-identical to NE single passes, the rays / image-1
+// samples are read once per batch, the NE dependency chains are independent, and the barriers, the
+// reduction and the serial publish step are paid once per batch.
+template <int NE, bool PREFETCH>
+__device__ __forceinline__ void run_pixels_multi(const FastPass* __restrict__ PPk, const LevelConst& L,
+                                                 const float2* __restrict__ rays, const float* __restrict__ i1, int m,
+                                                 int tid, int NT, Acc* acc) {
+    Acc2 unused;
+    const ulonglong2* __restrict__ rp = reinterpret_cast<const ulonglong2*>(rays);
+    const f2* __restrict__ ip = reinterpret_cast<const f2*>(i1);
+    const int npair = m >> 1;
+    int p = tid;
+    ulonglong2 r = make_ulonglong2(0ull, 0ull);
+    f2 I = 0ull;
+    if (p < npair) { r = rp[p]; I = ip[p]; }
+    for (; p < npair; p += NT) {
+        const ulonglong2 cr = r;
+        const f2 cI = I;
+        if (PREFETCH) {
+            const int nx = p + NT;
+            if (nx < npair) { r = rp[nx]; I = ip[nx]; }
+        }
+#pragma unroll
+        for (int k = 0; k < NE; k++) eval_pixel_pair<false>(PPk[k], L, cr.x, cr.y, cI, acc[k], unused);
+        if (!PREFETCH) {
+            const int nx = p + NT;
+            if (nx < npair) { r = rp[nx]; I = ip[nx]; }
+        }
+    }
+    if ((m & 1) && tid == (npair % NT)) {
+#pragma unroll
+        for (int k = 0; k < NE; k++) eval_pixel_fast<false, false>(PPk[k], L, ray_at(rays, m - 1), i1[m - 1], acc[k]);
     }
 }
 
@@ -855,6 +897,118 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             gsync(groups, g, NT);
 
             if (tid == 0) S->stats[15] += (unsigned long long)(clock64() - t_l0);   // level set-up: window + image-1 samples
+            // -------------------------------------------------------- mode 2: the candidate grid in batches
+            if (A.mode == 2 && A.sweep_batch > 1) {
+                const int K = A.sweep_nphi * A.sweep_ntheta;
+                bool fall_back = false;         // a tap left the staged window: the one-by-one loop takes over
+                for (int c0 = 0; c0 < K && !fall_back; c0 += SWEEP_B) {
+                    const int nb = min(SWEEP_B, K - c0);
+                    const long long t_a = clock64();
+                    if (wid == 0) {
+                        for (int k = 0; k < nb; k++) {
+                            const int c = c0 + k, ip = c / A.sweep_ntheta, it = c - ip * A.sweep_ntheta;
+                            const double phi = S->sweep_c[0] + ((double)ip - 0.5 * (double)(A.sweep_nphi - 1)) * A.sweep_dphi;
+                            const double theta = S->sweep_c[1] + ((double)it - 0.5 * (double)(A.sweep_ntheta - 1)) * A.sweep_dtheta;
+                            if (lane == 0) G.PPk[k].slow = 0;
+                            publish_pass(&G.PPk[k], S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
+                            __syncwarp();
+                            if (lane == 0) G.wk[k] = S->w[0];
+                            __syncwarp();
+                        }
+                    }
+                    gsync(groups, g, NT);
+                    // a NaN candidate normal ends the feature (normaloptimizer.cpp:81-85): evaluate the ones before it
+                    int ne = nb;
+                    for (int k = nb - 1; k >= 0; k--) if (G.PPk[k].kind == PASS_STOP) ne = k;
+                    unsigned fl[SWEEP_B];
+#pragma unroll
+                    for (int k = 0; k < SWEEP_B; k++) fl[k] = 0u;
+                    fl[0] = lvl_flags;          // image-1 gate of the level: charged to the first evaluation, as below
+                    lvl_flags = 0;
+                    for (int k = tid; k < n_boundary; k += NT) {
+                        int idx;
+                        if (k < 2 * nrows) {
+                            const int row = k >> 1;
+                            const int s0 = rows->start[row], s1 = rows->start[row + 1];
+                            if (s1 <= s0) continue;
+                            idx = (k & 1) ? s1 - 1 : s0;
+                        } else if (k < 2 * nrows + n_first) {
+                            idx = rows->start[first_row] + (k - 2 * nrows);
+                        } else {
+                            idx = rows->start[last_row] + (k - 2 * nrows - n_first);
+                        }
+                        const float2 ray = ray_at(rays, idx);
+#pragma unroll
+                        for (int kk = 0; kk < SWEEP_B; kk++)
+                            if (kk < ne) fl[kk] |= boundary_flags(G.PPk[kk], L, vcxf, vcyf, cmax, ray);
+                    }
+                    Acc acc[SWEEP_B];
+#pragma unroll
+                    for (int k = 0; k < SWEEP_B; k++) { acc[k].s0 = 0.0; acc[k].s1 = acc[k].s2 = acc[k].s3 = acc[k].s4 = acc[k].s5 = 0.0f; }
+                    if (ne == SWEEP_B) run_pixels_multi<SWEEP_B, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
+                    else if (ne == 3) run_pixels_multi<3, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
+                    else if (ne == 2) run_pixels_multi<2, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
+                    else if (ne == 1) run_pixels_multi<1, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
+#pragma unroll
+                    for (int k = 0; k < SWEEP_B; k++) {
+                        const double a = warp_sum(acc[k].s0);
+                        const unsigned f_or = __reduce_or_sync(0xffffffffu, fl[k]);
+                        if (lane == 0) { red[wid * 6 + k] = a; G.wflagsk[wid * SWEEP_B + k] = f_or; }
+                    }
+                    const long long t_b0 = clock64();
+                    gsync(groups, g, NT);
+                    const long long t_b = clock64();
+                    if (wid == 0) {
+                        double sk[SWEEP_B];
+                        unsigned fk[SWEEP_B];
+#pragma unroll
+                        for (int k = 0; k < SWEEP_B; k++) {
+                            double v = lane < NW ? red[lane * 6 + k] : 0.0;
+#pragma unroll
+                            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            sk[k] = v;
+                            fk[k] = __reduce_or_sync(0xffffffffu, lane < NW ? G.wflagsk[lane * SWEEP_B + k] : 0u);
+                        }
+                        if (lane == 0) {
+                            int resume = -1;
+                            for (int k = 0; k < ne && resume < 0; k++)
+                                if ((fk[k] & FLAG_WINDOW) && !(fk[k] & 7)) resume = c0 + k;
+                            const int n_rec = resume >= 0 ? resume - c0 : ne;
+                            for (int k = 0; k < n_rec; k++) {
+                                const int c = c0 + k;
+                                const bool bad = (fk[k] & 7) || sk[k] != sk[k];
+                                const double cval = bad ? __longlong_as_double(0x7ff8000000000000LL) : G.wk[k] * G.wk[k] * sk[k];
+                                if (A.cost) A.cost[(size_t)f * K + c] = cval;
+                                if (!bad && cval < S->best_cost) { S->best_cost = cval; S->best_idx = c; }
+                            }
+                            S->stats[0] += (unsigned long long)n_rec;
+                            S->stats[5] += (unsigned long long)m * (unsigned long long)ne;
+                            S->lm.nfev += n_rec;
+                            G.resume_at = resume;
+                            S->cand = resume >= 0 ? resume : c0 + n_rec;
+                            const long long t_c = clock64();
+                            S->stats[8] += (unsigned long long)(t_b0 - t_a);
+                            S->stats[9] += (unsigned long long)(t_b - t_b0);
+                            S->stats[10] += (unsigned long long)(t_c - t_b);
+                        }
+                    }
+                    gsync(groups, g, NT);
+                    if (G.resume_at >= 0) fall_back = true;
+                    if (ne < nb) break;         // NaN candidate: S->status / S->alive were set by publish_pass
+                }
+                if (wid == 0) {
+                    if (fall_back && S->alive) {
+                        // candidate S->cand again, one by one from here on (taps from global memory when needed)
+                        const int c = S->cand, ip = c / A.sweep_ntheta, it = c - ip * A.sweep_ntheta;
+                        const double phi = S->sweep_c[0] + ((double)ip - 0.5 * (double)(A.sweep_nphi - 1)) * A.sweep_dphi;
+                        const double theta = S->sweep_c[1] + ((double)it - 0.5 * (double)(A.sweep_ntheta - 1)) * A.sweep_dtheta;
+                        publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
+                    } else if (lane == 0) {
+                        PP->kind = PASS_STOP;
+                    }
+                }
+                gsync(groups, g, NT);
+            }
             // -------------------------------------------------------- pass loop (two barriers per pass)
             for (;;) {
                 const FastPass P = *PP;
@@ -1100,6 +1254,7 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     A.use_tma = ctx->opt_normals_tma;
     A.fuse_trials = ctx->opt_normals_fuse;
     A.memo_trials = ctx->opt_normals_memo;
+    A.sweep_batch = ctx->opt_normals_sweep_batch;
     A.mcap = (disc_capacity(A.r) + 31) & ~31;
     int nt = ctx->opt_normals_threads;
     nt = nt < 128 ? 128 : (nt > FAST_NT ? FAST_NT : (nt & ~63));

@@ -96,6 +96,8 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *                       the iterate's (1)
  *   "normals_groups"    fast kernel: independent feature pipelines per CTA: 1, 2, or 0 (default:
  *                       2 when there are more features than SMs and the layout fits)
+ *   "normals_sweep_batch"  fast kernel, fm3d_sweep_normals: 4 (default) evaluates four candidate normals per
+ *                       pass over the disc (bit-identical costs, one barrier pair per batch); 1: one pass each
  *   "normals_tma"       stage the image window with a TMA tensor-tile load (1)
  * Returns FM3D_ERR_INVALID_ARG for an unknown key. */
 int fm3d_set_option(fm3d_ctx* ctx, const char* key, double value);

@@ -446,6 +446,31 @@ def test_sweep_normals_dense_candidate_grid(ctx):
             ctx.set_option("normals_fast", 1)
 
 
+def test_sweep_normals_batched_equals_one_pass_per_candidate(ctx):
+    """normals_sweep_batch = 4 (default) evaluates four candidates per pass over the disc: costs, argmin and
+    statuses must be bit-identical to one pass per candidate, for grids that are not multiples of the batch,
+    for clipped discs and for every layout of the kernel."""
+    case = stereo_case(640, 480, 40, 1001, 32)
+    setup_ctx(ctx, case, 2)
+    xyz = np.concatenate([case["X"][:12], case["X"][:2] * np.array([1.0, 1.0, 1.6])])   # two points that project elsewhere
+    try:
+        for groups in (1, 2, 4):
+            ctx.set_option("normals_groups", groups)
+            for (n_phi, n_theta, level, pen) in ((5, 3, 0, 2), (1, 1, 1, 2), (2, 1, 2, 1), (7, 7, 0, 0), (3, 2, 1, 2)):
+                out = []
+                for batch in (4, 1):
+                    ctx.set_option("normals_sweep_batch", batch)
+                    out.append(ctx.sweep_normals(xyz, 32, level, n_phi, n_theta, 0.05, 0.04, penalty_mode=pen))
+                np.testing.assert_array_equal(out[0]["status"], out[1]["status"])
+                np.testing.assert_array_equal(out[0]["cost"], out[1]["cost"])          # NaNs in the same places too
+                np.testing.assert_array_equal(out[0]["best_idx"], out[1]["best_idx"])
+                np.testing.assert_array_equal(out[0]["best_cost"], out[1]["best_cost"])
+                assert np.isfinite(out[0]["cost"][:12]).all()
+    finally:
+        ctx.set_option("normals_groups", 0)
+        ctx.set_option("normals_sweep_batch", 4)
+
+
 def test_optimize_normals_large_disc_r128(ctx):
     """pixelsRay 128 (BASELINE configs[4]): m = 51 433 pixels do not fit in shared memory -- rays and
     image-1 samples stream from the L2-resident scratch and the level-0 window is wider than a TMA tile."""
