@@ -477,9 +477,9 @@ def run_gpu_arm(args):
             "kernel": "normals_fast_kernel<true> (K6: LM normal search, one persistent CTA per SM, one feature per CTA at a time)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload under `ncu --set full`
-            # (profiles/r01c_normals_fast_kernel_ncu_raw_selected.csv: 325 MB + 702 MB, the L2-resident ray scratch
-            # being written back); 0.7 % of DRAM throughput -- the kernel is not HBM-bound
-            "traffic": 1.0275e9, "traffic_unit": "bytes per launch (ncu, round-1 capture)",
+            # (profiles/r01f_normals_fast_kernel_ncu_raw_selected.csv: 199 MB + 691 MB, the L2-resident ray scratch
+            # being written back); 0.6 % of DRAM throughput -- the kernel is not HBM-bound
+            "traffic": 0.8902e9, "traffic_unit": "bytes per launch (ncu, profiles/r01f_*)",
             "note": "compute-bound kernel (SURVEY 8d): algorithmic flops = 64 x value-only pixel evaluations + 152 x "
                     "value+analytic-Jacobian pixel evaluations executed (counted by the kernel) / CUDA-event time; peak = "
                     "measured FFMA rate (tools/micro/ffma2_rate.cu: 73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; "
