@@ -240,3 +240,49 @@ def test_adapters_shard_the_normal_search_over_the_gpus_of_the_process(tmp_path)
         outs.append(open(out, "rb").read())
     assert outs[0] == outs[1] == outs[2]
     assert len(_read_result(os.path.join(tmp, "result_0_1.bin"))["normals"]) >= 20
+
+
+@pytest.mark.gpu
+def test_c1_main_cpp_pipeline_at_the_reference_defaults(tmp_path):
+    """BASELINE configs[0]: the main.cpp call sequence with build/settings.yml defaults (pixelsRay 64, pyramids 3,
+    epsilon 0.16 m at 0.25 cm/pixel -> 128 x 128 patches) on a 640 x 480 synthetic pair with ~1k keypoints, through
+    the C++ adapters; every stage against the CPU oracle."""
+    import time
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 64, 3, 0.16, 0.25
+    case = stereo_case(640, 480, 1000, 1000, r)
+    cam = case["scene"].cam
+    tmp = str(tmp_path)
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp)
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")     # the wall as the author's toolchain built it
+    t0 = time.perf_counter()
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), os.path.join(tmp, "features.bin"), os.path.join(tmp, "result.bin")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=600)
+    t_gpu = time.perf_counter() - t0
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+    o_idx, o_dist = orc.knn2_f32(case["desc1"], case["desc2"])
+    oq, ot, od = orc.nndr_filter(o_idx, o_dist, 0.55)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    assert len(oq) >= 600
+    o_all, o_mask, o_xyz = orc.triangulate(cam.K, cam.dist, res["g12"], cam.z_min, cam.z_max, case["kp1"], case["kp2"], oq, ot)
+    np.testing.assert_array_equal(res["mask"].astype(bool), o_mask.astype(bool))
+    np.testing.assert_allclose(res["pts"], o_xyz, rtol=1e-9, atol=1e-12)
+    t0 = time.perf_counter()
+    o = orc.optimize_normals(cam.K, cam.dist, res["g12"], cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                             pyramids, o_xyz, r, 1e-10, penalty_mode=1, threads=os.cpu_count() or 8)
+    t_cpu_normals = time.perf_counter() - t0
+    np.testing.assert_array_equal(res["status"], o["status"])
+    ok = o["status"] == 0
+    interior = o["npenalty"][ok] == 0
+    ang = angle_deg(res["normals"], o["normals"][ok])
+    assert interior.sum() >= 500 and (ang[interior] <= 0.5).all()
+    assert np.median(ang[interior]) < 0.02
+    assert res["S"] == 128 and res["patches"].shape == (int(ok.sum()), 128, 128)
+    from oracle import sift_patch_np as sp
+    sel = np.arange(0, len(res["patches"]), max(1, len(res["patches"]) // 24))
+    ddiff = np.abs(res["patch_descriptors"][sel] - sp.describe_patches_sift(res["patches"][sel]))
+    assert ddiff.max() <= 1
+    print(f"C1: {len(oq)} matches, {int(ok.sum())} normals; whole C++ process {t_gpu:.2f} s (incl. CUDA start-up), "
+          f"CPU oracle normal search alone {t_cpu_normals:.1f} s on {os.cpu_count()} threads")
