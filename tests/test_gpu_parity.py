@@ -466,6 +466,18 @@ def test_sweep_normals_batched_equals_one_pass_per_candidate(ctx):
                 np.testing.assert_array_equal(out[0]["best_idx"], out[1]["best_idx"])
                 np.testing.assert_array_equal(out[0]["best_cost"], out[1]["best_cost"])
                 assert np.isfinite(out[0]["cost"][:12]).all()
+        # wide grid (steps of 0.35 rad): some candidates stretch the warp beyond the staged window, the batch
+        # then hands the rest of the grid to the one-by-one loop with taps from global memory
+        ctx.set_option("normals_groups", 4)
+        out, slow = [], []
+        for batch in (4, 1):
+            ctx.set_option("normals_sweep_batch", batch)
+            out.append(ctx.sweep_normals(xyz[:12], 32, 0, 9, 9, 0.35, 0.35, penalty_mode=2))
+            slow.append(ctx.normals_stats()["passes_slow"])
+        assert slow[0] > 0 and slow[0] == slow[1]
+        assert np.array_equal(out[0]["cost"], out[1]["cost"], equal_nan=True)
+        np.testing.assert_array_equal(out[0]["best_idx"], out[1]["best_idx"])
+        np.testing.assert_array_equal(out[0]["status"], out[1]["status"])
     finally:
         ctx.set_option("normals_groups", 0)
         ctx.set_option("normals_sweep_batch", 4)
