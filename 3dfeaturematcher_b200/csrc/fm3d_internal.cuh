@@ -65,6 +65,7 @@ struct fm3d_ctx {
     size_t pinned_bytes = 0;
     // counters
     int64_t n_launch = 0, n_copy = 0;
+    int n_matcher_exact_fallback = 0;   // queries the last filtered float match handed to the exact path
 };
 
 // ---------------------------------------------------------------- error plumbing

@@ -22,6 +22,12 @@
 //                    ring, one thread issues tcgen05.mma (M128 N256 K16 x 9) into a double-
 //                    buffered 2 x 256-column TMEM accumulator, four warps drain it with
 //                    tcgen05.ld (one query row per thread) keeping a running top-2 in registers.
+//  match_sp_kernel   real-valued float descriptors (SURF, RootSIFT, ...; dim <= 128, dim % 4 == 0, at least
+//                    2^22 pairs): bf16 hi/lo split contraction on the tensor cores as a FILTER that keeps the
+//                    four smallest approximate distances per query and train split, then sp_refine_kernel
+//                    decides exactly with match_f32_kernel's arithmetic and proves that no other train
+//                    descriptor can win; queries it cannot prove go to match_f32_kernel.  Same results as
+//                    the exact path, bit for bit.
 //  match_f32_kernel  any other float descriptors: exact CUDA-core path, sum of squared
 //                    differences accumulated in ascending dimension order with separately
 //                    rounded multiply and add (bit-identical to the scalar oracle).
@@ -529,6 +535,326 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core path for REAL-VALUED float descriptors (SURF, RootSIFT, learned descriptors; dim <= 128):
+// filter on the tensor cores, decide exactly on CUDA cores.
+//   filter   every value is split x = hi + lo with hi, lo in bf16 (|x - hi - lo| <= 2^-18 |x|); the
+//            accumulator collects (-2q)_hi.t_hi + (-2q)_hi.t_lo + (-2q)_lo.t_hi + |t|^2 (three bf16 pieces),
+//            i.e. d^2 - |q|^2 up to E = 2^-12 (|q||t| + |t|^2) (a deliberately loose bound: the split leaves
+//            6 x 2^-18 |q||t|, the rest covers the fp32 accumulation inside the tensor core).  Each query
+//            row keeps its FOUR smallest values per train split.
+//   decide   the candidates are re-evaluated with the arithmetic of match_f32_kernel (ascending
+//            dimensions, separately rounded multiply and add), the two smallest by (d, index) win.  A train
+//            descriptor that is not a candidate has approximate value >= the smallest 4th value L of any
+//            split, hence exact d^2 >= L + |q|^2 - E: if the exact second-best is below that, the result
+//            is the exact brute-force answer; otherwise the query is handed to match_f32_kernel.
+// M128 N256 K16 x (1 + 3 ceil(dim/16)) per tile; operands 34 K-chunks per row (16 hi, 16 lo, 2 extras).
+// ------------------------------------------------------------------------------------------
+constexpr int SP_KCHUNKS = 34;
+constexpr int SP_GROUP_BYTES = SP_KCHUNKS * 128;            // 4352
+#ifndef FM3D_SP_N
+#define FM3D_SP_N 256
+#endif
+constexpr int SP_M = 128, SP_N = FM3D_SP_N;
+constexpr int SP_A_BYTES = (SP_M / 8) * SP_GROUP_BYTES;     // 69632
+constexpr int SP_B_BYTES = (SP_N / 8) * SP_GROUP_BYTES;     // 139264 (N = 256) / 69632 (N = 128)
+constexpr int SP_STAGES = SP_N == 256 ? 1 : 2;              // what fits next to the query tile in 227 KB
+constexpr int SP_SMEM = SP_A_BYTES + SP_STAGES * SP_B_BYTES + 256;
+constexpr int SP_TOPK = 4;
+
+struct Cand4 { float d[SP_TOPK]; int idx[SP_TOPK]; };
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// One warp per row: re-tile into [hi chunks 0..15 | lo chunks 16..31 | extras 32..33]; norms[row] = |x|^2.
+__global__ void __launch_bounds__(256)
+sp_prep_kernel(const float* __restrict__ src, int n, int n_pad, int dim, int is_query, uint8_t* __restrict__ dst,
+               float* __restrict__ norms, unsigned* __restrict__ max_norm_bits) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < n && lane * 4 < dim) {
+        const float4 x = *reinterpret_cast<const float4*>(src + (size_t)row * dim + lane * 4);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    }
+    float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    uint8_t* g = dst + (size_t)(row >> 3) * SP_GROUP_BYTES + (row & 7) * 16;
+    const float sc = is_query ? -2.f : 1.f;
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) split_bf16(sc * v[k], h[k], l[k]);
+    uint2 ph, pl;
+    ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(g + (lane >> 1) * 128 + (lane & 1) * 8) = ph;
+    *reinterpret_cast<uint2*>(g + (16 + (lane >> 1)) * 128 + (lane & 1) * 8) = pl;
+    if (lane == 0) {
+        float ex[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ex[k] = 0.f;
+        if (is_query) {
+            ex[0] = ex[1] = ex[2] = 1.f;
+        } else {
+            // |t|^2 in three bf16 pieces; padded rows get a huge norm so that they never enter a top-4
+            const float nn = row < n ? ss : 1.0e30f;
+            __nv_bfloat16 n0 = __float2bfloat16_rn(nn);
+            const float r1 = nn - __bfloat162float(n0);
+            __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
+            const float r2 = r1 - __bfloat162float(n1);
+            ex[0] = __bfloat162float(n0); ex[1] = __bfloat162float(n1); ex[2] = __bfloat162float(__float2bfloat16_rn(r2));
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(ex[c * 8 + 2 * k], ex[c * 8 + 2 * k + 1]);
+                w[k] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            *reinterpret_cast<uint4*>(g + (32 + c) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (row < n) {
+            norms[row] = ss;
+            if (ss == ss && ss < 3.0e38f) atomicMax(max_norm_bits, __float_as_uint(ss));
+            else atomicMax(max_norm_bits, 0x7f800000u);      // NaN / inf in the data: the exact path decides
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t umma_smem_desc_g(uint32_t saddr, uint32_t group_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((128u >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((group_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return v;
+}
+
+// Running top-4 (ascending) of one query row over 32 accumulator columns.  The common case is a min tree and one
+// vote; columns that beat some row's 4th value are few, and they are handled by a COMPACT loop that re-reads the
+// column from TMEM (a 32-way unrolled insertion sequence per chunk is several thousand instructions: the kernel
+// then stalls on instruction fetch, `no_instruction` 4.5 cycles per issue in profiles/r01f_match_sp_*).
+__device__ __forceinline__ void top4_chunk(const uint32_t (&v)[32], uint32_t taddr, int col0, float (&m)[SP_TOPK], int (&ix)[SP_TOPK]) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        p[j] = fminf(fminf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                     fminf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+    const float gmin = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), fminf(fminf(p[4], p[5]), fminf(p[6], p[7])));
+    if (__any_sync(0xffffffffu, gmin < m[3])) {
+        unsigned mask = 0u;
+#pragma unroll
+        for (int k = 0; k < 32; k++) mask |= (__uint_as_float(v[k]) < m[3]) ? (1u << k) : 0u;
+        unsigned um = __reduce_or_sync(0xffffffffu, mask);
+        while (um) {                                        // warp-uniform: ascending columns, so ties keep the lower index
+            const int k = __ffs(um) - 1;
+            um &= um - 1u;
+            const float d = __uint_as_float(tmem_ld1(taddr + (uint32_t)k));
+            if (d < m[3]) {
+                const int j = col0 + k;
+                if (d < m[0]) { m[3] = m[2]; ix[3] = ix[2]; m[2] = m[1]; ix[2] = ix[1]; m[1] = m[0]; ix[1] = ix[0]; m[0] = d; ix[0] = j; }
+                else if (d < m[1]) { m[3] = m[2]; ix[3] = ix[2]; m[2] = m[1]; ix[2] = ix[1]; m[1] = d; ix[1] = j; }
+                else if (d < m[2]) { m[3] = m[2]; ix[3] = ix[2]; m[2] = d; ix[2] = j; }
+                else { m[3] = d; ix[3] = j; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int nt_tiles,
+                int tiles_per_split, int ksteps, Cand4* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + SP_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_A_BYTES + SP_STAGES * SP_B_BYTES);
+    uint64_t* a_full = bars + 0;
+    uint64_t* b_full = bars + 1;
+    uint64_t* b_empty = bars + 1 + SP_STAGES;
+    uint64_t* acc_full = bars + 1 + 2 * SP_STAGES;
+    uint64_t* acc_empty = bars + 3 + 2 * SP_STAGES;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 5 + 2 * SP_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x, split = blockIdx.y;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(nt_tiles, tile_lo + tiles_per_split);
+    const int ntiles = tile_hi - tile_lo;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < SP_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        const uint32_t ncols = 2 * SP_N;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(a_full, SP_A_BYTES);
+            bulk_g2s(sA, qa + (size_t)qtile * SP_A_BYTES, SP_A_BYTES, a_full);
+            for (int it = 0; it < ntiles; it++) {
+                const int s = it % SP_STAGES;
+                const uint32_t ph = (uint32_t)(it / SP_STAGES) & 1u;
+                mbar_wait(&b_empty[s], ph ^ 1u);
+                mbar_expect_tx(&b_full[s], SP_B_BYTES);
+                bulk_g2s(sB + (size_t)s * SP_B_BYTES, tb + (size_t)(tile_lo + it) * SP_B_BYTES, SP_B_BYTES, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SP_N >> 3) << 17) | ((uint32_t)(SP_M >> 4) << 24);
+            mbar_wait(a_full, 0);
+            const uint32_t a_addr = s32(sA);
+            for (int it = 0; it < ntiles; it++) {
+                const int s = it % SP_STAGES, acc = it & 1;
+                mbar_wait(&b_full[s], (uint32_t)(it / SP_STAGES) & 1u);
+                mbar_wait(&acc_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t b_addr = s32(sB + (size_t)s * SP_B_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SP_N);
+                // extras first (|t|^2), then per K16 step hi.hi, hi.lo, lo.hi
+                umma_bf16(d_tmem, umma_smem_desc_g(a_addr + 32 * 128, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + 32 * 128, SP_GROUP_BYTES), idesc, 0);
+#pragma unroll 2
+                for (int k = 0; k < ksteps; k++) {          // K16 steps that hold data: ceil(dim / 16)
+                    const uint32_t hi = k * 256, lo = 16 * 128 + k * 256;
+                    umma_bf16(d_tmem, umma_smem_desc_g(a_addr + hi, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + hi, SP_GROUP_BYTES), idesc, 1);
+                    umma_bf16(d_tmem, umma_smem_desc_g(a_addr + hi, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + lo, SP_GROUP_BYTES), idesc, 1);
+                    umma_bf16(d_tmem, umma_smem_desc_g(a_addr + lo, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + hi, SP_GROUP_BYTES), idesc, 1);
+                }
+                umma_commit(&b_empty[s]);
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;
+        float m[SP_TOPK];
+        int ix[SP_TOPK];
+#pragma unroll
+        for (int k = 0; k < SP_TOPK; k++) { m[k] = INFINITY; ix[k] = 0x7fffffff; }
+        for (int it = 0; it < ntiles; it++) {
+            const int acc = it & 1;
+            mbar_wait(&acc_full[acc], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const int col_base = (tile_lo + it) * SP_N;
+            const uint32_t t0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * SP_N);
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(t0, va);
+            tmem_ld_wait();
+#pragma unroll 1
+            for (int c = 0; c < SP_N / 32; c += 2) {
+                tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
+                top4_chunk(va, t0 + (uint32_t)(c * 32), col_base + c * 32, m, ix);
+                tmem_ld_wait();
+                if (c + 2 < SP_N / 32) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+                top4_chunk(vb, t0 + (uint32_t)((c + 1) * 32), col_base + (c + 1) * 32, m, ix);
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+        }
+        const int qrow = qtile * SP_M + row;
+        if (qrow < nq) {
+            Cand4* o = partial + (size_t)split * nq + qrow;
+#pragma unroll
+            for (int k = 0; k < SP_TOPK; k++) { o->d[k] = m[k]; o->idx[k] = ix[k]; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        const uint32_t ncols = 2 * SP_N;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// Exact decision for one query per thread: re-evaluate its candidates with match_f32_kernel's arithmetic, keep
+// the two smallest by (d, index), and prove that no other train descriptor can beat the second (else: flag).
+__global__ void sp_refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim,
+                                 const Cand4* __restrict__ partial, int nsplit, const float* __restrict__ qnorm,
+                                 const unsigned* __restrict__ max_tnorm_bits, int32_t* __restrict__ idx, float* __restrict__ dist,
+                                 int* __restrict__ n_flagged, int32_t* __restrict__ flagged) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float* qi = q + (size_t)i * dim;
+    float m0 = INFINITY, m1 = INFINITY, low = INFINITY;
+    int j0 = 0x7fffffff, j1 = 0x7fffffff;
+    for (int s = 0; s < nsplit; s++) {
+        const Cand4 c = partial[(size_t)s * nq + i];
+        low = fminf(low, c.d[SP_TOPK - 1]);           // +inf when the split holds fewer than four descriptors
+#pragma unroll
+        for (int k = 0; k < SP_TOPK; k++) {
+            const int j = c.idx[k];
+            if (j < 0 || j >= nt) continue;
+            const float* tj = t + (size_t)j * dim;
+            float acc = 0.f;
+            for (int d = 0; d < dim; d += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(qi + d);
+                const float4 b = *reinterpret_cast<const float4*>(tj + d);
+                float e = __fsub_rn(a.x, b.x); acc = __fadd_rn(acc, __fmul_rn(e, e));
+                e = __fsub_rn(a.y, b.y); acc = __fadd_rn(acc, __fmul_rn(e, e));
+                e = __fsub_rn(a.z, b.z); acc = __fadd_rn(acc, __fmul_rn(e, e));
+                e = __fsub_rn(a.w, b.w); acc = __fadd_rn(acc, __fmul_rn(e, e));
+            }
+            top2_insert(acc, j, m0, j0, m1, j1);
+        }
+    }
+    // exact d^2 of every non-candidate >= low + |q|^2 - E,  E = 2^-12 (|q||t|max + |t|max^2) (+ the rounding of this
+    // very expression and of the exact sum: 2^-20 relative)
+    const float qn = qnorm[i], tmax = __uint_as_float(*max_tnorm_bits);
+    const float E = 2.44140625e-4f * (sqrtf(qn) * sqrtf(tmax) + tmax);
+    const float bound = (low + qn) - E - 1.0e-6f * (fabsf(low) + qn + tmax);
+    const bool safe = j1 < nt && m1 < bound;      // low = +inf: every train descriptor was a candidate
+    if (safe) {
+        idx[2 * i] = j0; idx[2 * i + 1] = j1;
+        dist[2 * i] = sqrtf(m0); dist[2 * i + 1] = sqrtf(m1);
+    } else {
+        idx[2 * i] = -2;                              // decided by the exact path
+        flagged[atomicAdd(n_flagged, 1)] = i;
+    }
+}
+
+__global__ void sp_gather_rows_kernel(const float* __restrict__ q, int dim, const int32_t* __restrict__ rows, int n,
+                                      float* __restrict__ out) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) out[(size_t)r * dim + d] = q[(size_t)rows[r] * dim + d];
+}
+__global__ void sp_scatter_kernel(const int32_t* __restrict__ rows, int n, const int32_t* __restrict__ sidx, const float* __restrict__ sdist,
+                                  int32_t* __restrict__ idx, float* __restrict__ dist) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int i = rows[r];
+    idx[2 * i] = sidx[2 * r]; idx[2 * i + 1] = sidx[2 * r + 1];
+    dist[2 * i] = sdist[2 * r]; dist[2 * i + 1] = sdist[2 * r + 1];
+}
+
 int pick_splits(int work_tiles, int nt_tiles, int sms, int* tiles_per_split) {
     int splits = 1;
     if (work_tiles < 2 * sms) splits = (2 * sms + work_tiles - 1) / work_tiles;
@@ -538,6 +864,22 @@ int pick_splits(int work_tiles, int nt_tiles, int sms, int* tiles_per_split) {
     if (*tiles_per_split < 1) *tiles_per_split = 1;
     const int eff = (nt_tiles + *tiles_per_split - 1) / *tiles_per_split;
     return eff > 0 ? eff : 1;
+}
+
+// exact CUDA-core path (K1')
+int knn2_f32_generic(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, int32_t* idx, float* dist) {
+    const int sms = ctx->prop.multiProcessorCount;
+    const int q_tiles = (nq + FT - 1) / FT, nt_tiles = (nt + FT - 1) / FT;
+    int tps = 1;
+    const int splits = nt_tiles > 0 ? pick_splits(q_tiles, nt_tiles, sms, &tps) : 1;
+    Cand* partial = nullptr;
+    if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * nq, (void**)&partial)) return rc;
+    dim3 grid(q_tiles, splits);
+    match_f32_kernel<<<grid, 256, 0, ctx->stream>>>(q, nq, t, nt, dim, tps, partial);
+    FM3D_LAUNCH_CHECK(ctx);
+    finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits, nq, nt, idx, dist);
+    FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
 }
 
 int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, int32_t* idx,
@@ -575,17 +917,60 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
             return FM3D_OK;
         }
     }
-    const int q_tiles = (nq + FT - 1) / FT, nt_tiles = (nt + FT - 1) / FT;
-    int tps = 1;
-    const int splits = nt_tiles > 0 ? pick_splits(q_tiles, nt_tiles, sms, &tps) : 1;
-    Cand* partial = nullptr;
-    if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * nq, (void**)&partial)) return rc;
-    dim3 grid(q_tiles, splits);
-    match_f32_kernel<<<grid, 256, 0, ctx->stream>>>(q, nq, t, nt, dim, tps, partial);
-    FM3D_LAUNCH_CHECK(ctx);
-    finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits, nq, nt, idx, dist);
-    FM3D_LAUNCH_CHECK(ctx);
-    return FM3D_OK;
+    // real-valued descriptors: bf16 hi/lo filter on the tensor cores + exact decision (see match_sp_kernel)
+    const bool use_sp = ctx->opt_matcher_tensor && dim <= TC_DIM && (dim & 3) == 0 && nt >= 1 &&
+                        (((uintptr_t)q | (uintptr_t)t) & 15) == 0 && (long long)nq * (long long)nt >= (1ll << 22);
+    if (use_sp) {
+        const int nq_pad = (nq + SP_M - 1) / SP_M * SP_M, nt_pad = (nt + SP_N - 1) / SP_N * SP_N;
+        const size_t ba = (size_t)(nq_pad / 8) * SP_GROUP_BYTES, bb = (size_t)(nt_pad / 8) * SP_GROUP_BYTES;
+        const size_t bn = (sizeof(float) * ((size_t)nq + nt) + 255) & ~(size_t)255;
+        uint8_t* ops = nullptr;
+        if (int rc = fm3d_scratch(ctx, 3, ba + bb + bn + 256, (void**)&ops)) return rc;
+        float* qnorm = reinterpret_cast<float*>(ops + ba + bb);
+        float* tnorm = qnorm + nq;
+        unsigned* flags = reinterpret_cast<unsigned*>(ops + ba + bb + bn);   // [0] max |q|^2 bits, [1] max |t|^2 bits, [2] flagged count
+        ctx->n_copy++;
+        FM3D_CUDA(ctx, cudaMemsetAsync(flags, 0, 16, ctx->stream));
+        sp_prep_kernel<<<nq_pad / 8, 256, 0, ctx->stream>>>(q, nq, nq_pad, dim, 1, ops, qnorm, flags);
+        FM3D_LAUNCH_CHECK(ctx);
+        sp_prep_kernel<<<nt_pad / 8, 256, 0, ctx->stream>>>(t, nt, nt_pad, dim, 0, ops + ba, tnorm, flags + 1);
+        FM3D_LAUNCH_CHECK(ctx);
+        const int q_tiles = nq_pad / SP_M, nt_tiles = nt_pad / SP_N;
+        int tps = 1;
+        const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
+        Cand4* partial4 = nullptr;
+        if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * nq, (void**)&partial4)) return rc;
+        int32_t* flagged = nullptr;
+        if (int rc = fm3d_scratch(ctx, 5, sizeof(int32_t) * (size_t)nq, (void**)&flagged)) return rc;
+        FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        dim3 grid(q_tiles, splits);
+        match_sp_kernel<<<grid, TC_THREADS, SP_SMEM, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, partial4);
+        FM3D_LAUNCH_CHECK(ctx);
+        sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, splits, qnorm, flags + 1, idx, dist,
+                                                                    reinterpret_cast<int*>(flags + 2), flagged);
+        FM3D_LAUNCH_CHECK(ctx);
+        int n_flagged = 0;
+        if (int rc = fm3d_d2h(ctx, &n_flagged, flags + 2, sizeof(int))) return rc;
+        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->n_matcher_exact_fallback = n_flagged;
+        if (n_flagged > 0) {
+            // the filter could not prove these queries: exact brute force for them alone
+            auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+            const size_t b_rows = al(sizeof(float) * (size_t)n_flagged * dim), b_i = al(sizeof(int32_t) * 2 * (size_t)n_flagged);
+            char* sub = nullptr;
+            if (int rc = fm3d_scratch(ctx, 6, b_rows + 2 * b_i, (void**)&sub)) return rc;
+            float* qsub = reinterpret_cast<float*>(sub);
+            int32_t* sidx = reinterpret_cast<int32_t*>(sub + b_rows);
+            float* sdist = reinterpret_cast<float*>(sub + b_rows + b_i);
+            sp_gather_rows_kernel<<<n_flagged, 128, 0, ctx->stream>>>(q, dim, flagged, n_flagged, qsub);
+            FM3D_LAUNCH_CHECK(ctx);
+            if (int rc = knn2_f32_generic(ctx, qsub, n_flagged, t, nt, dim, sidx, sdist)) return rc;
+            sp_scatter_kernel<<<(n_flagged + 255) / 256, 256, 0, ctx->stream>>>(flagged, n_flagged, sidx, sdist, idx, dist);
+            FM3D_LAUNCH_CHECK(ctx);
+        }
+        return FM3D_OK;
+    }
+    return knn2_f32_generic(ctx, q, nq, t, nt, dim, idx, dist);
 }
 
 int knn2_ham_dev(fm3d_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int nbytes,

@@ -126,6 +126,57 @@ def test_match_f32_generic_path(ctx):
     _check_knn(a[0], a[1], b[0], b[1])
 
 
+def test_match_f32_real_valued_tensor_filter_is_exact(ctx):
+    """Real-valued float descriptors (SURF-like; not integer-valued, any dim <= 128): the bf16 hi/lo tensor-core
+    filter + exact decision must return what the exact CUDA-core path and the oracle return, bit for bit --
+    including exact ties (lower index), duplicates, near-duplicates inside the filter's error (handed to the exact
+    path), and train sets smaller than the candidate list."""
+    rng = np.random.default_rng(5)
+
+    def both(q, t):
+        ctx.set_option("matcher_tensor", 1)
+        idx, dist = ctx.match_knn2_f32(q, t)
+        fb = int(ctx.get_option("matcher_exact_fallback"))
+        ctx.set_option("matcher_tensor", 0)
+        idx0, dist0 = ctx.match_knn2_f32(q, t)
+        ctx.set_option("matcher_tensor", 1)
+        np.testing.assert_array_equal(idx, idx0)
+        np.testing.assert_array_equal(dist, dist0)
+        return idx, dist, fb
+
+    for dim in (64, 128, 100, 36):
+        nq, nt = 2300, 2000                               # >= 2^22 pairs: the filtered path
+        t = rng.normal(size=(nt, dim)).astype(np.float32)
+        t /= np.linalg.norm(t, axis=1, keepdims=True)
+        q = (t[rng.integers(0, nt, nq)] + 0.1 * rng.normal(size=(nq, dim))).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        idx, dist, _ = both(q, t)
+        o_idx, o_dist = orc.knn2_f32(q[:200], t)          # the plain-C oracle on a slice
+        np.testing.assert_array_equal(idx[:200], o_idx)
+        np.testing.assert_array_equal(dist[:200], o_dist)
+    dim, nq, nt = 64, 2200, 2100
+    t = rng.normal(size=(nt, dim)).astype(np.float32)
+    t[100] = t[50]; t[2000] = t[50]; t[7] = t[1999]
+    q = t[rng.integers(0, nt, nq)].copy()
+    q[5] = t[50]; q[6] = t[7]
+    idx, dist, _ = both(q, t)
+    assert tuple(idx[5]) == (50, 100) and dist[5, 0] == 0 and dist[5, 1] == 0      # three-way tie: the two lowest indices
+    assert tuple(idx[6]) == (7, 1999)
+    t2 = t.copy()
+    t2[300:340] = t2[299] + rng.normal(size=(40, dim)).astype(np.float32) * 1e-6
+    q2 = q.copy()
+    q2[:50] = t2[299] + rng.normal(size=(50, dim)).astype(np.float32) * 1e-4
+    _, _, fb = both(q2, t2)
+    assert fb >= 50                                       # the filter cannot separate them: exact path, same answer
+    t3 = rng.uniform(0, 255, size=(2100, 128)).astype(np.float32)                  # SIFT range, not integer-valued
+    q3 = (t3[rng.integers(0, 2100, 2000)] + rng.normal(size=(2000, 128)) * 3).astype(np.float32)
+    both(q3, t3)
+    idx, dist, _ = both(rng.normal(size=(1 << 21, 8)).astype(np.float32), rng.normal(size=(3, 8)).astype(np.float32))
+    assert idx.min() >= 0 and idx.max() <= 2
+    qn = q3.copy(); qn[3, 5] = np.nan                     # NaN in the data: decided by the exact path
+    both(qn, t3)
+
+
 @pytest.mark.parametrize("nbytes", [32, 64])
 @pytest.mark.parametrize("nq,nt", [(300, 360), (3, 1), (1500, 2100)])
 def test_match_hamming(ctx, nbytes, nq, nt):

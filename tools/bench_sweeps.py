@@ -168,6 +168,26 @@ def c3_pipeline(ctx, stream):
                       "passes_global_taps": st["passes_slow"]}), flush=True)
 
 
+def match_real_sweep(ctx, stream):
+    """Real-valued float descriptors (SURF-like unit vectors): tensor-core filter + exact decision vs the exact CUDA-core path."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1007)
+    for n, dim in ((10000, 64), (50000, 64), (50000, 128), (100000, 128), (200000, 128)):
+        q = torch.randn((n, dim), device=dev, generator=g); t = torch.randn((n, dim), device=dev, generator=g)
+        q = q / q.norm(dim=1, keepdim=True); t = t / t.norm(dim=1, keepdim=True)
+        idx = torch.empty((n, 2), dtype=torch.int32, device=dev); dist = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        fn = lambda: ctx.match_knn2_f32_dev(q.data_ptr(), n, t.data_ptr(), n, dim, idx.data_ptr(), dist.data_ptr())
+        ms = timed(stream, fn, 2)
+        fb = int(ctx.get_option("matcher_exact_fallback"))
+        out = {"case": "match_f32_real_valued_tensor_filter", "nq": n, "nt": n, "dim": dim, "ms": ms, "pairs_per_s": float(n) * n / (ms * 1e-3),
+               "mma_tflops": float(n) * n * (3 * ((dim + 15) // 16) + 1) * 16 * 2 / (ms * 1e-3) / 1e12, "queries_decided_by_exact_path": fb}
+        if n <= 50000:
+            ctx.set_option("matcher_tensor", 0)
+            out["ms_exact_cuda_core_path"] = timed(stream, fn, 1)
+            ctx.set_option("matcher_tensor", 1)
+        print(json.dumps(out), flush=True)
+
+
 def describe_sweep(ctx, stream):
     """K9 alone: SIFT descriptors of n rectified patches (extractDescriptorsFromPatches), S = 128 and 64."""
     dev = torch.device("cuda", 0)
@@ -190,6 +210,8 @@ if __name__ == "__main__":
         match_sweep(ctx, stream, [int(a) for a in sys.argv[2:]] if which == "match" and len(sys.argv) > 2 else [10000, 50000, 100000, 200000])
     if which in ("all", "normals"):
         normals_stress(ctx, stream, int(sys.argv[2]) if len(sys.argv) > 2 else 2000)
+    if which in ("all", "match_real"):
+        match_real_sweep(ctx, stream)
     if which in ("all", "describe"):
         describe_sweep(ctx, stream)
     if which in ("c3",):
