@@ -399,18 +399,28 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Running top-2 of one query row over 32 accumulator columns.  The group minimum is a tree (depth 5,
 // FMNMX3 where the compiler finds it) rather than a 31-deep dependent chain: with one epilogue warp
 // per scheduler the chain latency, not the issue rate, was what kept the tensor pipe waiting.
-__device__ __forceinline__ void top2_chunk(const uint32_t (&v)[32], int col0, float& m0, int& i0, float& m1, int& i1) {
+__device__ __forceinline__ void top2_chunk(const uint32_t (&v)[32], uint32_t taddr, int col0, float& m0, int& i0, float& m1, int& i1) {
     float p[8];
 #pragma unroll
     for (int j = 0; j < 8; j++)
         p[j] = fminf(fminf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
                      fminf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
     const float gmin = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), fminf(fminf(p[4], p[5]), fminf(p[6], p[7])));
-    if (gmin < m1) {
+    if (__any_sync(0xffffffffu, gmin < m1)) {
+        // columns that beat some row's second value: few; a compact warp-uniform loop re-reads them from TMEM
+        // (ascending columns and strict <: the lower index wins ties) instead of a 32-way unrolled insertion
+        unsigned mask = 0u;
 #pragma unroll
-        for (int k = 0; k < 32; k++) {
-            const float d = __uint_as_float(v[k]);
-            if (d < m1) {   // ascending index scan: strict < keeps the lower index on ties
+        for (int k = 0; k < 32; k++) mask |= (__uint_as_float(v[k]) < m1) ? (1u << k) : 0u;
+        unsigned um = __reduce_or_sync(0xffffffffu, mask);
+        while (um) {
+            const int k = __ffs(um) - 1;
+            um &= um - 1u;
+            uint32_t x;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(taddr + (uint32_t)k));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float d = __uint_as_float(x);
+            if (d < m1) {
                 const int j = col0 + k;
                 if (d < m0) { m1 = m0; i1 = i0; m0 = d; i0 = j; }
                 else { m1 = d; i1 = j; }
@@ -510,10 +520,10 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
 #pragma unroll 1
             for (int c = 0; c < TC_N / 32; c += 2) {
                 tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
-                top2_chunk(va, col_base + c * 32, m0, i0, m1, i1);
+                top2_chunk(va, t0 + (uint32_t)(c * 32), col_base + c * 32, m0, i0, m1, i1);
                 tmem_ld_wait();
                 if (c + 2 < TC_N / 32) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
-                top2_chunk(vb, col_base + (c + 1) * 32, m0, i0, m1, i1);
+                top2_chunk(vb, t0 + (uint32_t)((c + 1) * 32), col_base + (c + 1) * 32, m0, i0, m1, i1);
                 tmem_ld_wait();
             }
             tc_fence_before();
