@@ -561,17 +561,28 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
 //            is the exact brute-force answer; otherwise the query is handed to match_f32_kernel.
 // M128 N256 K16 x (1 + 3 ceil(dim/16)) per tile; operands 34 K-chunks per row (16 hi, 16 lo, 2 extras).
 // ------------------------------------------------------------------------------------------
-constexpr int SP_KCHUNKS = 34;
-constexpr int SP_GROUP_BYTES = SP_KCHUNKS * 128;            // 4352
-#ifndef FM3D_SP_N
-#define FM3D_SP_N 256
-#endif
-constexpr int SP_M = 128, SP_N = FM3D_SP_N;
-constexpr int SP_A_BYTES = (SP_M / 8) * SP_GROUP_BYTES;     // 69632
-constexpr int SP_B_BYTES = (SP_N / 8) * SP_GROUP_BYTES;     // 139264 (N = 256) / 69632 (N = 128)
-constexpr int SP_STAGES = SP_N == 256 ? 1 : 2;              // what fits next to the query tile in 227 KB
-constexpr int SP_SMEM = SP_A_BYTES + SP_STAGES * SP_B_BYTES + 256;
+constexpr int SP_M = 128, SP_N = 256;
 constexpr int SP_TOPK = 4;
+// Row layout: [hi: dpad/8 chunks | lo: dpad/8 chunks | extras: 2 chunks] of 16 bytes, dpad = dim rounded up to 16.
+// dim 128: 34 chunks, 136 KB train tile -> one stage next to the 68 KB query tile; dim <= 80: two stages fit.
+struct SpLayout {
+    int half_chunks;    // dpad / 8
+    int kchunks;        // 2 * half_chunks + 2
+    int group_bytes;    // kchunks * 128 (8 rows)
+    int a_bytes, b_bytes, stages, smem;
+};
+inline SpLayout sp_layout(int dim, size_t smem_optin) {
+    SpLayout L;
+    const int dpad = (dim + 15) / 16 * 16;
+    L.half_chunks = dpad / 8;
+    L.kchunks = 2 * L.half_chunks + 2;
+    L.group_bytes = L.kchunks * 128;
+    L.a_bytes = (SP_M / 8) * L.group_bytes;
+    L.b_bytes = (SP_N / 8) * L.group_bytes;
+    L.stages = (size_t)L.a_bytes + 2 * (size_t)L.b_bytes + 256 <= smem_optin ? 2 : 1;
+    L.smem = L.a_bytes + L.stages * L.b_bytes + 256;
+    return L;
+}
 
 struct Cand4 { float d[SP_TOPK]; int idx[SP_TOPK]; };
 
@@ -582,7 +593,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 
 // One warp per row: re-tile into [hi chunks 0..15 | lo chunks 16..31 | extras 32..33]; norms[row] = |x|^2.
 __global__ void __launch_bounds__(256)
-sp_prep_kernel(const float* __restrict__ src, int n, int n_pad, int dim, int is_query, uint8_t* __restrict__ dst,
+sp_prep_kernel(const float* __restrict__ src, int n, int n_pad, int dim, int is_query, int half_chunks, uint8_t* __restrict__ dst,
                float* __restrict__ norms, unsigned* __restrict__ max_norm_bits) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -595,7 +606,8 @@ sp_prep_kernel(const float* __restrict__ src, int n, int n_pad, int dim, int is_
     float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    uint8_t* g = dst + (size_t)(row >> 3) * SP_GROUP_BYTES + (row & 7) * 16;
+    const int group_bytes = (2 * half_chunks + 2) * 128;
+    uint8_t* g = dst + (size_t)(row >> 3) * group_bytes + (row & 7) * 16;
     const float sc = is_query ? -2.f : 1.f;
     __nv_bfloat16 h[4], l[4];
 #pragma unroll
@@ -605,8 +617,10 @@ sp_prep_kernel(const float* __restrict__ src, int n, int n_pad, int dim, int is_
     ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
     pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
     pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-    *reinterpret_cast<uint2*>(g + (lane >> 1) * 128 + (lane & 1) * 8) = ph;
-    *reinterpret_cast<uint2*>(g + (16 + (lane >> 1)) * 128 + (lane & 1) * 8) = pl;
+    if ((lane >> 1) < half_chunks) {
+        *reinterpret_cast<uint2*>(g + (lane >> 1) * 128 + (lane & 1) * 8) = ph;
+        *reinterpret_cast<uint2*>(g + (half_chunks + (lane >> 1)) * 128 + (lane & 1) * 8) = pl;
+    }
     if (lane == 0) {
         float ex[16];
 #pragma unroll
@@ -630,7 +644,7 @@ sp_prep_kernel(const float* __restrict__ src, int n, int n_pad, int dim, int is_
                 __nv_bfloat162 p = __floats2bfloat162_rn(ex[c * 8 + 2 * k], ex[c * 8 + 2 * k + 1]);
                 w[k] = *reinterpret_cast<uint32_t*>(&p);
             }
-            *reinterpret_cast<uint4*>(g + (32 + c) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(g + (2 * half_chunks + c) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         if (row < n) {
             norms[row] = ss;
@@ -689,17 +703,18 @@ __device__ __forceinline__ void top4_chunk(const uint32_t (&v)[32], uint32_t tad
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int nt_tiles,
-                int tiles_per_split, int ksteps, Cand4* __restrict__ partial) {
+                int tiles_per_split, int ksteps, const SpLayout lay, Cand4* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const int SP_A_BYTES = lay.a_bytes, SP_B_BYTES = lay.b_bytes, SP_STAGES = lay.stages, SP_GROUP_BYTES = lay.group_bytes;
     uint8_t* sA = smem;
     uint8_t* sB = smem + SP_A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_A_BYTES + SP_STAGES * SP_B_BYTES);
     uint64_t* a_full = bars + 0;
-    uint64_t* b_full = bars + 1;
-    uint64_t* b_empty = bars + 1 + SP_STAGES;
-    uint64_t* acc_full = bars + 1 + 2 * SP_STAGES;
-    uint64_t* acc_empty = bars + 3 + 2 * SP_STAGES;
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 5 + 2 * SP_STAGES);
+    uint64_t* b_full = bars + 1;            // [2]
+    uint64_t* b_empty = bars + 3;           // [2]
+    uint64_t* acc_full = bars + 5;          // [2]
+    uint64_t* acc_empty = bars + 7;         // [2]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -748,10 +763,11 @@ match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
                 const uint32_t b_addr = s32(sB + (size_t)s * SP_B_BYTES);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SP_N);
                 // extras first (|t|^2), then per K16 step hi.hi, hi.lo, lo.hi
-                umma_bf16(d_tmem, umma_smem_desc_g(a_addr + 32 * 128, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + 32 * 128, SP_GROUP_BYTES), idesc, 0);
+                const uint32_t ex_off = (uint32_t)(2 * lay.half_chunks) * 128u, lo_off = (uint32_t)lay.half_chunks * 128u;
+                umma_bf16(d_tmem, umma_smem_desc_g(a_addr + ex_off, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + ex_off, SP_GROUP_BYTES), idesc, 0);
 #pragma unroll 2
-                for (int k = 0; k < ksteps; k++) {          // K16 steps that hold data: ceil(dim / 16)
-                    const uint32_t hi = k * 256, lo = 16 * 128 + k * 256;
+                for (int k = 0; k < ksteps; k++) {          // K16 steps: ceil(dim / 16)
+                    const uint32_t hi = k * 256, lo = lo_off + k * 256;
                     umma_bf16(d_tmem, umma_smem_desc_g(a_addr + hi, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + hi, SP_GROUP_BYTES), idesc, 1);
                     umma_bf16(d_tmem, umma_smem_desc_g(a_addr + hi, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + lo, SP_GROUP_BYTES), idesc, 1);
                     umma_bf16(d_tmem, umma_smem_desc_g(a_addr + lo, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + hi, SP_GROUP_BYTES), idesc, 1);
@@ -931,8 +947,9 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
     const bool use_sp = ctx->opt_matcher_tensor && dim <= TC_DIM && (dim & 3) == 0 && nt >= 1 &&
                         (((uintptr_t)q | (uintptr_t)t) & 15) == 0 && (long long)nq * (long long)nt >= (1ll << 22);
     if (use_sp) {
+        const SpLayout lay = sp_layout(dim, ctx->prop.sharedMemPerBlockOptin);
         const int nq_pad = (nq + SP_M - 1) / SP_M * SP_M, nt_pad = (nt + SP_N - 1) / SP_N * SP_N;
-        const size_t ba = (size_t)(nq_pad / 8) * SP_GROUP_BYTES, bb = (size_t)(nt_pad / 8) * SP_GROUP_BYTES;
+        const size_t ba = (size_t)(nq_pad / 8) * lay.group_bytes, bb = (size_t)(nt_pad / 8) * lay.group_bytes;
         const size_t bn = (sizeof(float) * ((size_t)nq + nt) + 255) & ~(size_t)255;
         uint8_t* ops = nullptr;
         if (int rc = fm3d_scratch(ctx, 3, ba + bb + bn + 256, (void**)&ops)) return rc;
@@ -941,9 +958,9 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         unsigned* flags = reinterpret_cast<unsigned*>(ops + ba + bb + bn);   // [0] max |q|^2 bits, [1] max |t|^2 bits, [2] flagged count
         ctx->n_copy++;
         FM3D_CUDA(ctx, cudaMemsetAsync(flags, 0, 16, ctx->stream));
-        sp_prep_kernel<<<nq_pad / 8, 256, 0, ctx->stream>>>(q, nq, nq_pad, dim, 1, ops, qnorm, flags);
+        sp_prep_kernel<<<nq_pad / 8, 256, 0, ctx->stream>>>(q, nq, nq_pad, dim, 1, lay.half_chunks, ops, qnorm, flags);
         FM3D_LAUNCH_CHECK(ctx);
-        sp_prep_kernel<<<nt_pad / 8, 256, 0, ctx->stream>>>(t, nt, nt_pad, dim, 0, ops + ba, tnorm, flags + 1);
+        sp_prep_kernel<<<nt_pad / 8, 256, 0, ctx->stream>>>(t, nt, nt_pad, dim, 0, lay.half_chunks, ops + ba, tnorm, flags + 1);
         FM3D_LAUNCH_CHECK(ctx);
         const int q_tiles = nq_pad / SP_M, nt_tiles = nt_pad / SP_N;
         int tps = 1;
@@ -952,9 +969,9 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * nq, (void**)&partial4)) return rc;
         int32_t* flagged = nullptr;
         if (int rc = fm3d_scratch(ctx, 5, sizeof(int32_t) * (size_t)nq, (void**)&flagged)) return rc;
-        FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
         dim3 grid(q_tiles, splits);
-        match_sp_kernel<<<grid, TC_THREADS, SP_SMEM, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, partial4);
+        match_sp_kernel<<<grid, TC_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
         FM3D_LAUNCH_CHECK(ctx);
         sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, splits, qnorm, flags + 1, idx, dist,
                                                                     reinterpret_cast<int*>(flags + 2), flagged);
