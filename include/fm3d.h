@@ -83,9 +83,11 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
 /* Tuning / mode knobs that are not part of the reference's settings.yml:
  *   "geometry_f32"      0 (default): fp64 ray/plane/projection arithmetic as the reference;
  *                       1: fp32 geometry (faster, normals agree to <<0.5 deg)
- *   "matcher_tensor"    1 (default): use the tcgen05 contraction when descriptors are
- *                       integer-valued in [0,255] and dim == 128;  0: always the exact
- *                       CUDA-core fp32 path
+ *   "matcher_tensor"    1 (default): use the tcgen05 contraction -- directly when descriptors are
+ *                       integer-valued in [0,255] and dim == 128, as a filter followed by an exact
+ *                       fp32 decision for other float descriptors (dim <= 128, dim % 4 == 0, >= 2^22
+ *                       pairs); results are identical either way.  0: always the exact CUDA-core path
+ *   "matcher_exact_fallback"  read-only: queries of the last filtered match that the exact path decided
  *   "lm_patience"       lm_control.patience / maxcall (default 100 -> 300 evaluations/level)
  *   "normals_threads"   threads per CTA of the normal optimiser (default 512)
  *   "normals_fast"      1 (default): fm3d_normals_fast.cu (fp32 offset-form geometry, analytic
