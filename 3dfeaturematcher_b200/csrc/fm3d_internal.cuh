@@ -42,6 +42,7 @@ struct fm3d_ctx {
     // options
     int opt_geometry_f32 = 0;
     int opt_matcher_tensor = 1;
+    int opt_matcher_sp_tile = 128;   // real-valued tensor filter at dim > 80: 128 = two stages of 128 train rows (default, measured faster), 256 = one stage of 256
     int opt_lm_patience = 100;
     int opt_normals_threads = 512;
     int opt_normals_tma = 1;

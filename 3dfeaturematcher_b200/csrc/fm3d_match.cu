@@ -561,25 +561,32 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
 //            is the exact brute-force answer; otherwise the query is handed to match_f32_kernel.
 // M128 N256 K16 x (1 + 3 ceil(dim/16)) per tile; operands 34 K-chunks per row (16 hi, 16 lo, 2 extras).
 // ------------------------------------------------------------------------------------------
-constexpr int SP_M = 128, SP_N = 256;
+constexpr int SP_M = 128;
 constexpr int SP_TOPK = 4;
 // Row layout: [hi: dpad/8 chunks | lo: dpad/8 chunks | extras: 2 chunks] of 16 bytes, dpad = dim rounded up to 16.
 // dim 128: 34 chunks, 136 KB train tile -> one stage next to the 68 KB query tile; dim <= 80: two stages fit.
 struct SpLayout {
+    int n_tile;         // train rows per tile: 256, or 128 when that is what allows two stages
     int half_chunks;    // dpad / 8
     int kchunks;        // 2 * half_chunks + 2
     int group_bytes;    // kchunks * 128 (8 rows)
     int a_bytes, b_bytes, stages, smem;
 };
-inline SpLayout sp_layout(int dim, size_t smem_optin) {
+inline SpLayout sp_layout(int dim, size_t smem_optin, int n_tile_option) {
     SpLayout L;
     const int dpad = (dim + 15) / 16 * 16;
     L.half_chunks = dpad / 8;
     L.kchunks = 2 * L.half_chunks + 2;
     L.group_bytes = L.kchunks * 128;
     L.a_bytes = (SP_M / 8) * L.group_bytes;
-    L.b_bytes = (SP_N / 8) * L.group_bytes;
+    L.n_tile = 256;
+    L.b_bytes = (L.n_tile / 8) * L.group_bytes;
     L.stages = (size_t)L.a_bytes + 2 * (size_t)L.b_bytes + 256 <= smem_optin ? 2 : 1;
+    if (L.stages == 1 && n_tile_option == 128) {            // two stages of 128 rows instead of one of 256
+        L.n_tile = 128;
+        L.b_bytes = (L.n_tile / 8) * L.group_bytes;
+        L.stages = 2;
+    }
     L.smem = L.a_bytes + L.stages * L.b_bytes + 256;
     return L;
 }
@@ -701,6 +708,7 @@ __device__ __forceinline__ void top4_chunk(const uint32_t (&v)[32], uint32_t tad
     }
 }
 
+template <int SP_N>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int nt_tiles,
                 int tiles_per_split, int ksteps, const SpLayout lay, Cand4* __restrict__ partial) {
@@ -947,7 +955,8 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
     const bool use_sp = ctx->opt_matcher_tensor && dim <= TC_DIM && (dim & 3) == 0 && nt >= 1 &&
                         (((uintptr_t)q | (uintptr_t)t) & 15) == 0 && (long long)nq * (long long)nt >= (1ll << 22);
     if (use_sp) {
-        const SpLayout lay = sp_layout(dim, ctx->prop.sharedMemPerBlockOptin);
+        const SpLayout lay = sp_layout(dim, ctx->prop.sharedMemPerBlockOptin, ctx->opt_matcher_sp_tile);
+        const int SP_N = lay.n_tile;
         const int nq_pad = (nq + SP_M - 1) / SP_M * SP_M, nt_pad = (nt + SP_N - 1) / SP_N * SP_N;
         const size_t ba = (size_t)(nq_pad / 8) * lay.group_bytes, bb = (size_t)(nt_pad / 8) * lay.group_bytes;
         const size_t bn = (sizeof(float) * ((size_t)nq + nt) + 255) & ~(size_t)255;
@@ -969,9 +978,14 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * nq, (void**)&partial4)) return rc;
         int32_t* flagged = nullptr;
         if (int rc = fm3d_scratch(ctx, 5, sizeof(int32_t) * (size_t)nq, (void**)&flagged)) return rc;
-        FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
         dim3 grid(q_tiles, splits);
-        match_sp_kernel<<<grid, TC_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+        if (SP_N == 256) {
+            FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
+            match_sp_kernel<256><<<grid, TC_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+        } else {
+            FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
+            match_sp_kernel<128><<<grid, TC_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+        }
         FM3D_LAUNCH_CHECK(ctx);
         sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, splits, qnorm, flags + 1, idx, dist,
                                                                     reinterpret_cast<int*>(flags + 2), flagged);

@@ -87,6 +87,7 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *                       integer-valued in [0,255] and dim == 128, as a filter followed by an exact
  *                       fp32 decision for other float descriptors (dim <= 128, dim % 4 == 0, >= 2^22
  *                       pairs); results are identical either way.  0: always the exact CUDA-core path
+ *   "matcher_sp_tile"   train rows per tile of that filter when dim > 80: 128 (default, two stages) or 256 (one stage)
  *   "matcher_exact_fallback"  read-only: queries of the last filtered match that the exact path decided
  *   "lm_patience"       lm_control.patience / maxcall (default 100 -> 300 evaluations/level)
  *   "normals_threads"   threads per CTA of the normal optimiser (default 512)
