@@ -491,6 +491,11 @@ def run_gpu_arm(args):
             "reference_equivalent_pixel_evals": pixel_evals_ref,
             "reference_equivalent_tflops": pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12,
             "thread0_cycle_share": {"pixel_loop": cyc["cycles_pixels"] / cyc_tot, "serial_lm_step": cyc["cycles_serial"] / cyc_tot},
+            # the packed FMAs of the pixel loop read {64-bit, 32-bit broadcast constant, 64-bit} register sources: that form
+            # sustains 54.6 TFLOP/s on this pool (three distinct 64-bit sources: 47.1), not the 73.96 of re-used operands --
+            # vector register-file bandwidth (tools/micro/ffma2_operands.cu, profiles/r01f_ffma2_operand_microbench.txt)
+            "peak_operand_limited": 54.63 * sm_max / 1965.0,
+            "frac_of_operand_limited_peak": achieved / (54.63 * sm_max / 1965.0),
             "ms_per_launch": t_norm_s * 1e3,
             "hbm_compulsory_gbs": (n_inl * 44e3 / t_norm_s) / 1e9, "hbm_peak_gbs": hbm_peak,
         }
