@@ -277,7 +277,12 @@ constexpr int TC_A_BYTES = (TC_M / 8) * TC_GROUP_BYTES;   // 36864
 constexpr int TC_B_BYTES = (TC_N / 8) * TC_GROUP_BYTES;   // 73728
 constexpr int TC_STAGES = 2;
 constexpr int TC_SMEM = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 256;
-constexpr int TC_THREADS = 192;
+#ifndef FM3D_TC_EPI_WARPS
+#define FM3D_TC_EPI_WARPS 8                         // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, half the columns each)
+#endif
+constexpr int TC_EPI_WARPS = FM3D_TC_EPI_WARPS;
+constexpr int TC_EPI_HALVES = TC_EPI_WARPS / 4;     // column halves of a tile, one per epilogue warp of a lane quarter
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 // Re-tile n x 128 float descriptors into the UMMA K-major no-swizzle core-matrix layout
 // (8 rows x 16 B core matrices; 18 K-chunks of a row group contiguous) as bf16, rows padded
@@ -453,7 +458,7 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -501,8 +506,11 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
             }
         }
     } else {
-        // ===== epilogue: 4 warps, thread <-> TMEM lane <-> query row; running top-2 in registers
+        // ===== epilogue: thread <-> TMEM lane <-> query row; running top-2 in registers.  The epilogue is co-critical
+        // with the MMA (latency-bound min trees and TMEM loads), so two warps share a lane quarter and take half the
+        // columns of every tile each; their lists are merged by finalize like two more train splits.
         const int lane_grp = warp & 3;                  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const int half = (warp - 2) >> 2;               // 0 .. TC_EPI_HALVES-1
         const int row = lane_grp * 32 + lane;
         float m0 = INFINITY, m1 = INFINITY;
         int i0 = 0x7fffffff, i1 = 0x7fffffff;
@@ -514,15 +522,17 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
             // two register buffers: the tcgen05.ld of the next 32 columns is in flight while the
             // current 32 are scanned
             const uint32_t t0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * TC_N);
+            constexpr int CH = TC_N / 32 / TC_EPI_HALVES;            // 32-column chunks per warp and tile
+            const int c_lo = half * CH;
             uint32_t va[32], vb[32];
-            tmem_ld32_issue(t0, va);
+            tmem_ld32_issue(t0 + (uint32_t)(c_lo * 32), va);
             tmem_ld_wait();
 #pragma unroll 1
-            for (int c = 0; c < TC_N / 32; c += 2) {
+            for (int c = c_lo; c < c_lo + CH; c += 2) {
                 tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
                 top2_chunk(va, t0 + (uint32_t)(c * 32), col_base + c * 32, m0, i0, m1, i1);
                 tmem_ld_wait();
-                if (c + 2 < TC_N / 32) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+                if (c + 2 < c_lo + CH) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
                 top2_chunk(vb, t0 + (uint32_t)((c + 1) * 32), col_base + (c + 1) * 32, m0, i0, m1, i1);
                 tmem_ld_wait();
             }
@@ -531,7 +541,7 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
         }
         const int qrow = qtile * TC_M + row;
         if (qrow < nq) {
-            Cand* o = partial + ((size_t)split * nq + qrow) * 2;
+            Cand* o = partial + ((size_t)(split * TC_EPI_HALVES + half) * nq + qrow) * 2;
             o[0].d = m0; o[0].idx = i0;
             o[1].d = m1; o[1].idx = i1;
         }
@@ -708,8 +718,10 @@ __device__ __forceinline__ void top4_chunk(const uint32_t (&v)[32], uint32_t tad
     }
 }
 
+constexpr int SP_EPI_HALVES = 1;                    // measured: a second epilogue warp per lane quarter does not pay at N = 128
+constexpr int SP_THREADS = 64 + 128 * SP_EPI_HALVES;
 template <int SP_N>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(SP_THREADS, 1)
 match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int nt_tiles,
                 int tiles_per_split, int ksteps, const SpLayout lay, Cand4* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -733,7 +745,7 @@ match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < SP_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128 * SP_EPI_HALVES); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -786,6 +798,7 @@ match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
         }
     } else {
         const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2;               // two epilogue warps per lane quarter, half the columns each
         const int row = lane_grp * 32 + lane;
         float m[SP_TOPK];
         int ix[SP_TOPK];
@@ -797,15 +810,17 @@ match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
             tc_fence_after();
             const int col_base = (tile_lo + it) * SP_N;
             const uint32_t t0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * SP_N);
+            constexpr int CH = SP_N / 32 / SP_EPI_HALVES;
+            const int c_lo = half * CH;
             uint32_t va[32], vb[32];
-            tmem_ld32_issue(t0, va);
+            tmem_ld32_issue(t0 + (uint32_t)(c_lo * 32), va);
             tmem_ld_wait();
 #pragma unroll 1
-            for (int c = 0; c < SP_N / 32; c += 2) {
+            for (int c = c_lo; c < c_lo + CH; c += 2) {
                 tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
                 top4_chunk(va, t0 + (uint32_t)(c * 32), col_base + c * 32, m, ix);
                 tmem_ld_wait();
-                if (c + 2 < SP_N / 32) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+                if (c + 2 < c_lo + CH) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
                 top4_chunk(vb, t0 + (uint32_t)((c + 1) * 32), col_base + (c + 1) * 32, m, ix);
                 tmem_ld_wait();
             }
@@ -814,7 +829,7 @@ match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
         }
         const int qrow = qtile * SP_M + row;
         if (qrow < nq) {
-            Cand4* o = partial + (size_t)split * nq + qrow;
+            Cand4* o = partial + (size_t)(split * SP_EPI_HALVES + half) * nq + qrow;
 #pragma unroll
             for (int k = 0; k < SP_TOPK; k++) { o->d[k] = m[k]; o->idx[k] = ix[k]; }
         }
@@ -941,12 +956,12 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
             int tps = 1;
             const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
             Cand* partial = nullptr;
-            if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * nq, (void**)&partial)) return rc;
+            if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * TC_EPI_HALVES * nq, (void**)&partial)) return rc;
             FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
             dim3 grid(q_tiles, splits);
             match_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, partial);
             FM3D_LAUNCH_CHECK(ctx);
-            finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits, nq, nt, idx, dist);
+            finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits * TC_EPI_HALVES, nq, nt, idx, dist);
             FM3D_LAUNCH_CHECK(ctx);
             return FM3D_OK;
         }
@@ -975,19 +990,19 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         int tps = 1;
         const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
         Cand4* partial4 = nullptr;
-        if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * nq, (void**)&partial4)) return rc;
+        if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * SP_EPI_HALVES * nq, (void**)&partial4)) return rc;
         int32_t* flagged = nullptr;
         if (int rc = fm3d_scratch(ctx, 5, sizeof(int32_t) * (size_t)nq, (void**)&flagged)) return rc;
         dim3 grid(q_tiles, splits);
         if (SP_N == 256) {
             FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
-            match_sp_kernel<256><<<grid, TC_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+            match_sp_kernel<256><<<grid, SP_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
         } else {
             FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
-            match_sp_kernel<128><<<grid, TC_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+            match_sp_kernel<128><<<grid, SP_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
         }
         FM3D_LAUNCH_CHECK(ctx);
-        sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, splits, qnorm, flags + 1, idx, dist,
+        sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, splits * SP_EPI_HALVES, qnorm, flags + 1, idx, dist,
                                                                     reinterpret_cast<int*>(flags + 2), flagged);
         FM3D_LAUNCH_CHECK(ctx);
         int n_flagged = 0;
