@@ -111,6 +111,10 @@ void matrixToRodrigues(const cv::Matx33d& R, cv::Vec3d& r) {
     r = cv::Vec3d(rx * vth, ry * vth, rz * vth);
 }
 
+// The five helpers below are also defined by the reference's tools.cpp (tools.cpp:87-127, 767-777).  When the
+// adapters are linked next to that file (main.cpp keeps tools.cpp for its drawing and viewer
+// functions), compile this file with -DFM3D_EXTERNAL_TOOLS so that there is one definition of each.
+#ifndef FM3D_EXTERNAL_TOOLS
 void composeTransformation(const cv::Matx33d& R, const cv::Vec3d& T, cv::Matx44d& G) {
     for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) G(i, j) = R(i, j); G(i, 3) = T(i); }
     G(3, 0) = 0; G(3, 1) = 0; G(3, 2) = 0; G(3, 3) = 1;
@@ -138,6 +142,7 @@ void sph2car(const double phi, const double theta, cv::Vec3d& v) {
     v[1] = std::cos(theta) * std::sin(phi);
     v[2] = std::sin(theta);
 }
+#endif  // FM3D_EXTERNAL_TOOLS
 
 // ------------------------------------------------------------------------- DescriptorsMatcher
 DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv::Mat& frame_b)
