@@ -117,6 +117,7 @@ public:
     int channels() const { return (type_ >> 3) + 1; }
     size_t elemSize() const { return (size_t)channels() * (depth() == CV_8U ? 1 : depth() == CV_32F ? 4 : 8); }
     size_t step() const { return (size_t)cols * elemSize(); }
+    size_t step1(int = 0) const { return (size_t)cols * channels(); }   // cv::Mat::step1: row pitch in elements of one channel
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     bool isContinuous() const { return true; }
     Size size() const { return Size(cols, rows); }

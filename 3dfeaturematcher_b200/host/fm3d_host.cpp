@@ -276,7 +276,7 @@ void SingleCameraTriangulator::setImages(const cv::Mat& img1, const cv::Mat& img
     img_1_ = img1; img_2_ = img2;  // shallow, like new cv::Mat(img) in the reference (:118-119)
     const int levels = pyramids_;
     for_each_ctx("set_images", [&](int k) {
-        return fm3d_set_images(host_ctxs()[k], img1.data, img2.data, img1.cols, img1.rows, (int)img1.step(), levels);
+        return fm3d_set_images(host_ctxs()[k], img1.data, img2.data, img1.cols, img1.rows, (int)img1.step1(), levels);   // CV_8UC1: elements = bytes; step1() exists in cv::Mat and in the stand-in
     });
 }
 
