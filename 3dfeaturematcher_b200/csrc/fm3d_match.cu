@@ -561,7 +561,7 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
 // filter on the tensor cores, decide exactly on CUDA cores.
 //   filter   every value is split x = hi + lo with hi, lo in bf16 (|x - hi - lo| <= 2^-18 |x|); the
 //            accumulator collects (-2q)_hi.t_hi + (-2q)_hi.t_lo + (-2q)_lo.t_hi + |t|^2 (three bf16 pieces),
-//            i.e. d^2 - |q|^2 up to E = 2^-12 (|q||t| + |t|^2) (a deliberately loose bound: the split leaves
+//            i.e. d^2 - |q|^2 up to E = 2^-11 (|q||t| + |t|^2) (a deliberately loose bound: the split leaves
 //            6 x 2^-18 |q||t|, the rest covers the fp32 accumulation inside the tensor core).  Each query
 //            row keeps its FOUR smallest values per train split.
 //   decide   the candidates are re-evaluated with the arithmetic of match_f32_kernel (ascending
@@ -874,11 +874,15 @@ __global__ void sp_refine_kernel(const float* __restrict__ q, int nq, const floa
             top2_insert(acc, j, m0, j0, m1, j1);
         }
     }
-    // exact d^2 of every non-candidate >= low + |q|^2 - E,  E = 2^-12 (|q||t|max + |t|max^2) (+ the rounding of this
-    // very expression and of the exact sum: 2^-20 relative)
+    // The filter value of every non-candidate is >= low, so its exact d^2 is >= low + |q|^2 - E with
+    //   E = 2^-11 (|q||t|max + |t|max^2): the bf16 split leaves 6 x 2^-18 |q||t| and 2^-24 |t|^2, a few hundred fp32
+    //       additions inside the tensor core at most ~1e-4 (2|q||t| + |t|^2) even if they truncated;
+    // and what match_f32_kernel would compute for it (the value the result is defined by) is within
+    //   2 dim 2^-24 d^2 <= 1.6e-5 (|q| + |t|max)^2 of the exact d^2 (sequential fp32 sum of dim <= 128 terms).
     const float qn = qnorm[i], tmax = __uint_as_float(*max_tnorm_bits);
-    const float E = 2.44140625e-4f * (sqrtf(qn) * sqrtf(tmax) + tmax);
-    const float bound = (low + qn) - E - 1.0e-6f * (fabsf(low) + qn + tmax);
+    const float qt = sqrtf(qn) * sqrtf(tmax);
+    const float E = 4.8828125e-4f * (qt + tmax) + 1.6e-5f * (qn + 2.0f * qt + tmax);
+    const float bound = (low + qn) - E - 1.0e-6f * (fabsf(low) + qn);    // last term: rounding of this expression itself
     const bool safe = j1 < nt && m1 < bound;      // low = +inf: every train descriptor was a candidate
     if (safe) {
         idx[2 * i] = j0; idx[2 * i + 1] = j1;
