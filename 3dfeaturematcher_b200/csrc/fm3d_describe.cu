@@ -136,15 +136,39 @@ describe_sift_kernel(const DescArgs A, const uint8_t* __restrict__ patches, floa
         bufA[r * SA + DESC_HALO + cdst] = fm3d_u8f(src[r * S + csrc]);
     }
     __syncthreads();
-    // row pass (symmetric form: k0 x0 + sum_i k_i (x_-i + x_+i)) -> bufB rows KHALF .. KHALF+S-1
-    for (int i = tid; i < S2; i += DESC_NT) {
-        int r, c;
-        divmod_small(i, S, inv_S, r, c);
-        const float* px = bufA + r * SA + DESC_HALO + c;
-        float s = __fmul_rn(A.kern[0], px[0]);
+    // row pass (symmetric form: k0 x0 + sum_i k_i (x_-i + x_+i)) -> bufB rows KHALF .. KHALF+S-1.  Four outputs per
+    // thread from five aligned 16-byte loads (columns c-8 .. c+11) instead of 13 loads per output: the kernel is
+    // bound by the shared-memory pipe (profiles/r01f_describe_kernel_ncu_*).
+    if ((S & 3) == 0) {
+        const int S4 = S >> 2;
+        for (int i = tid; i < S * S4; i += DESC_NT) {
+            int r, c4;
+            divmod_small(i, S4, 1.0f / (float)S4, r, c4);
+            const float4* q = reinterpret_cast<const float4*>(bufA + r * SA + DESC_HALO + 4 * c4 - 8);
+            float w[20];
 #pragma unroll
-        for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k], px[k]), s);
-        bufB[i + DESC_KHALF * S] = s;
+            for (int k = 0; k < 5; k++) { const float4 v = q[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+            float4 o;
+            float* op = &o.x;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float s = __fmul_rn(A.kern[0], w[8 + j]);
+#pragma unroll
+                for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(w[8 + j - k], w[8 + j + k]), s);
+                op[j] = s;
+            }
+            *reinterpret_cast<float4*>(bufB + (r + DESC_KHALF) * S + 4 * c4) = o;
+        }
+    } else {
+        for (int i = tid; i < S2; i += DESC_NT) {
+            int r, c;
+            divmod_small(i, S, inv_S, r, c);
+            const float* px = bufA + r * SA + DESC_HALO + c;
+            float s = __fmul_rn(A.kern[0], px[0]);
+#pragma unroll
+            for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k], px[k]), s);
+            bufB[i + DESC_KHALF * S] = s;
+        }
     }
     __syncthreads();
     // BORDER_REFLECT_101 rows of the row-pass image
@@ -156,13 +180,32 @@ describe_sift_kernel(const DescArgs A, const uint8_t* __restrict__ patches, floa
         bufB[(rdst + DESC_KHALF) * S + c] = bufB[(rsrc + DESC_KHALF) * S + c];
     }
     __syncthreads();
-    // column pass -> bufA (stride S)
-    for (int i = tid; i < S2; i += DESC_NT) {
-        const float* px = bufB + i + DESC_KHALF * S;
-        float s = __fmul_rn(A.kern[0], px[0]);
+    // column pass -> bufA (stride S): four consecutive rows per thread from 16 loads (rows r-6 .. r+9 of one column)
+    if ((S & 3) == 0) {
+        const int R4 = S >> 2;
+        for (int i = tid; i < R4 * S; i += DESC_NT) {
+            int r4, c;
+            divmod_small(i, S, inv_S, r4, c);
+            const float* px = bufB + (4 * r4) * S + c;          // row 4 r4 - KHALF of the padded row-pass image
+            float w[16];
 #pragma unroll
-        for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k * S], px[k * S]), s);
-        bufA[i] = s;
+            for (int k = 0; k < 16; k++) w[k] = px[k * S];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float s = __fmul_rn(A.kern[0], w[6 + j]);
+#pragma unroll
+                for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(w[6 + j - k], w[6 + j + k]), s);
+                bufA[(4 * r4 + j) * S + c] = s;
+            }
+        }
+    } else {
+        for (int i = tid; i < S2; i += DESC_NT) {
+            const float* px = bufB + i + DESC_KHALF * S;
+            float s = __fmul_rn(A.kern[0], px[0]);
+#pragma unroll
+            for (int k = 1; k <= DESC_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k * S], px[k * S]), s);
+            bufA[i] = s;
+        }
     }
     __syncthreads();
     // private accumulators: one float4 (the four central cells 2 dr + dc) per orientation bin and thread,
