@@ -938,6 +938,7 @@ int knn2_f32_generic(fm3d_ctx* ctx, const float* q, int nq, const float* t, int 
 int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, int32_t* idx,
                  float* dist) {
     const int sms = ctx->prop.multiProcessorCount;
+    ctx->n_matcher_exact_fallback = 0;
     bool use_tc = ctx->opt_matcher_tensor && dim == TC_DIM && nt >= 1 &&
                   (((uintptr_t)q | (uintptr_t)t) & 15) == 0;
     if (use_tc) {

@@ -177,6 +177,37 @@ def test_match_f32_real_valued_tensor_filter_is_exact(ctx):
     both(qn, t3)
 
 
+def test_match_f32_real_valued_tile_edges(ctx):
+    """The tensor filter at the edges of its tiles: train counts around multiples of 128 / 256, 1-3 train descriptors,
+    dimensions that are not multiples of 16, large magnitudes, quantised values with many exact ties, exact copies."""
+    rng = np.random.default_rng(11)
+    cases = [(4, 1), (8, 3), (20, 127), (36, 128), (48, 129), (64, 255), (84, 256), (100, 257), (112, 1000), (128, 4097), (96, 9000), (12, 5)]
+    for it, (dim, nt) in enumerate(cases):
+        nq = (1 << 22) // nt + 37
+        kind = it % 5
+        t = rng.normal(size=(nt, dim)).astype(np.float32)
+        if kind == 0:
+            t /= np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-9)
+        elif kind == 1:
+            t *= 1000.0
+        elif kind == 2:
+            t = np.round(t * 4) / 4
+        elif kind == 3:
+            t = np.abs(t) * 50 + 0.5
+        q = (t[rng.integers(0, nt, nq)] + (0.05 if kind != 1 else 50.0) * rng.normal(size=(nq, dim))).astype(np.float32)
+        if kind == 2:
+            q = np.round(q * 4) / 4
+        if kind == 4:
+            q[: nq // 3] = t[rng.integers(0, nt, nq // 3)]
+        ctx.set_option("matcher_tensor", 1)
+        i1, d1 = ctx.match_knn2_f32(q, t)
+        ctx.set_option("matcher_tensor", 0)
+        i0, d0 = ctx.match_knn2_f32(q, t)
+        ctx.set_option("matcher_tensor", 1)
+        np.testing.assert_array_equal(i1, i0, err_msg=f"dim {dim} nt {nt} kind {kind}")
+        np.testing.assert_array_equal(d1, d0, err_msg=f"dim {dim} nt {nt} kind {kind}")
+
+
 @pytest.mark.parametrize("nbytes", [32, 64])
 @pytest.mark.parametrize("nq,nt", [(300, 360), (3, 1), (1500, 2100)])
 def test_match_hamming(ctx, nbytes, nq, nt):
