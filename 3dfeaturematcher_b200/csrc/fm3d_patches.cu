@@ -64,7 +64,7 @@ patches_kernel(PatchArgs A, const double* __restrict__ frames, uint8_t* __restri
             fm3d_project(A.cam, X, Y, Z, u, v);
             patches[(size_t)f * S * S + (size_t)j * S + i] = sample_patch(A, u, v);
         }
-        s_ip[tj][ti] = make_double2(u, v);
+        if (image_points) s_ip[tj][ti] = make_double2(u, v);
     }
     if (image_points) {
         __syncthreads();
