@@ -37,6 +37,7 @@ SYMBOLS = [
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
     "fm3d_describe_patches_sift", "fm3d_describe_patches_sift_dev",
+    "fm3d_detect_fast", "fm3d_detect_fast_dev",
 ]
 
 
@@ -367,7 +368,30 @@ class Context:
         self._ck(self.lib.fm3d_describe_patches_sift(self._h, _ptr(patches, _bp), n, S, _ptr(desc, _fp)))
         return desc
 
+    def detect_fast(self, img, threshold, nonmax=True, max_keypoints=None):
+        """feature_detector_->detect for DetectorType FAST: H x W u8 -> (n x 2 f32 xy, n f32 response),
+        row-major order like cv::FAST.  max_keypoints=None counts first, then fetches all of them."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        n = C.c_int(0)
+        if max_keypoints is None:
+            self._ck(self.lib.fm3d_detect_fast(self._h, _ptr(img, _bp), w, h, img.strides[0], int(threshold), int(bool(nonmax)), 0, None, None, C.byref(n)))
+            max_keypoints = n.value
+        xy = np.empty((max(max_keypoints, 1), 2), np.float32)
+        resp = np.empty(max(max_keypoints, 1), np.float32)
+        if max_keypoints > 0:
+            self._ck(self.lib.fm3d_detect_fast(self._h, _ptr(img, _bp), w, h, img.strides[0], int(threshold), int(bool(nonmax)), int(max_keypoints),
+                                               _ptr(xy, _fp), _ptr(resp, _fp), C.byref(n)))
+        got = min(n.value, max_keypoints)
+        return xy[:got].copy(), resp[:got].copy(), n.value
+
     # ------------------------------------------------------------------ device-pointer entry points
+    def detect_fast_dev(self, img, w, h, stride, threshold, nonmax, max_keypoints, xy, response, n_dev):
+        self._ck(self.lib.fm3d_detect_fast_dev(self._h, C.c_void_p(img), w, h, stride, int(threshold), int(bool(nonmax)), int(max_keypoints),
+                                               C.c_void_p(xy), C.c_void_p(response), C.c_void_p(n_dev)))
+
     def describe_patches_sift_dev(self, patches, n, S, descriptors):
         self._ck(self.lib.fm3d_describe_patches_sift_dev(self._h, C.c_void_p(patches), n, S, C.c_void_p(descriptors)))
 

@@ -363,6 +363,25 @@ int fm3d_circular_neighborhoods(fm3d_ctx* ctx, const double* points, double* nor
 int fm3d_describe_patches_sift(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, float* descriptors);
 int fm3d_describe_patches_sift_dev(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, float* descriptors);
 
+/* ---------------------------------------------------------- keypoint detection ---- */
+
+/* Replaces feature_detector_->detect(frame, keypoints) of DescriptorsMatcher::compareWithNNDR /
+ * compare / crosscompare (DescriptorsMatcher/descriptorsmatcher.cpp:110-111, :92-93, :77-78) for
+ * DetectorType FAST, DetectorMode STATIC (:215-222: cv::FastFeatureDetector(Threshold,
+ * NonMaxSuppression)): FAST-9-16 corners, keypoints in row-major order (ascending y, then x).
+ *   img            h rows of w u8 pixels, `stride` bytes apart
+ *   threshold      FeatureOptions.FastDetector.Threshold (clamped to [0, 255] as cv::FAST does)
+ *   nonmax         FeatureOptions.FastDetector.NonMaxSuppression != 0: keep a corner only if its
+ *                  cornerScore is strictly above its 8 neighbours'; response = score (else 0)
+ *   xy             max_keypoints x 2 f32 (KeyPoint::pt), response max_keypoints f32
+ *   n              total number of corners found; when n > max_keypoints only the first
+ *                  max_keypoints (row-major order) were written.  max_keypoints = 0 only counts.
+ * KeyPoint::size is 7, angle -1, octave 0, class_id -1 for every keypoint (constant, not returned). */
+int fm3d_detect_fast(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int threshold,
+                     int nonmax, int max_keypoints, float* xy, float* response, int* n);
+int fm3d_detect_fast_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int threshold,
+                         int nonmax, int max_keypoints, float* xy, float* response, int* n_dev);
+
 #ifdef __cplusplus
 }
 #endif

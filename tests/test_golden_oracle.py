@@ -107,3 +107,24 @@ def test_sift_patch_restatement_against_cv2_golden_vectors():
         assert np.count_nonzero(g[f"d{S}"][-2]) == 0          # constant patch -> zero descriptor
     pipe = np.load(os.path.join(GOLD, "normals.npz"))["patches"]
     _desc_close(sp.describe_patches_sift(pipe), g["d_pipeline"])
+
+
+FAST_THRESHOLDS = (0, 1, 10, 20, 40, 100, 255)
+
+
+def test_fast_restatement_against_cv2_golden_vectors():
+    """oracle/fast_np.py against the committed outputs of cv2.FastFeatureDetector (integer work: exact,
+    order included)."""
+    from oracle import fast_np as fo
+    g = np.load(os.path.join(GOLD, "fast_keypoints.npz"))
+    total = 0
+    for name in ("noise", "blur", "frame", "tiny7", "tiny6"):
+        img = g[f"img_{name}"]
+        for t in FAST_THRESHOLDS:
+            for nm in (0, 1):
+                xy, r = fo.detect_fast(img, t, bool(nm))
+                assert xy.dtype == np.float32 and r.dtype == np.float32
+                np.testing.assert_array_equal(xy, g[f"xy_{name}_{t}_{nm}"].astype(np.float32).reshape(-1, 2))
+                np.testing.assert_array_equal(r, g[f"r_{name}_{t}_{nm}"].astype(np.float32))
+                total += len(xy)
+    assert total > 50000

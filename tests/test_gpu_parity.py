@@ -832,3 +832,68 @@ def test_describe_patches_pipeline_on_device(ctx, api):
     from oracle import sift_patch_np as sp
     _desc_close(want, sp.describe_patches_sift(patches))
     assert np.count_nonzero(want) > 0
+
+
+# ------------------------------------------------------------------ K10: FAST keypoint detection
+def test_detect_fast_golden_vectors(ctx):
+    """feature_detector_->detect for DetectorType FAST (descriptorsmatcher.cpp:110-111, :215-222): the committed
+    outputs of cv2.FastFeatureDetector.  Integer work: positions, order and responses identical."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fast_keypoints.npz"))
+    for name in ("noise", "blur", "frame", "tiny7", "tiny6"):
+        img = g[f"img_{name}"]
+        for t in (0, 1, 10, 20, 40, 100, 255):
+            for nm in (0, 1):
+                xy, r, n = ctx.detect_fast(img, t, bool(nm))
+                want = g[f"xy_{name}_{t}_{nm}"].astype(np.float32).reshape(-1, 2)
+                assert n == len(want), (name, t, nm, n, len(want))
+                assert np.array_equal(xy, want) and np.array_equal(r, g[f"r_{name}_{t}_{nm}"].astype(np.float32)), (name, t, nm)
+
+
+def test_detect_fast_against_oracle_and_edges(ctx, api):
+    from oracle import fast_np as fo
+    rng = np.random.default_rng(808)
+    for h, w in ((480, 640), (33, 1025), (1000, 9), (7, 7), (3, 40), (1, 1)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if h >= 32 and w >= 32:
+            img[: h // 2] = (img[: h // 2].astype(np.int32) * 3 // 8 + 90).astype(np.uint8)      # a low-contrast half
+        for t, nm in ((12, True), (30, False), (0, True)):
+            xy, r, n = ctx.detect_fast(img, t, nm)
+            oxy, orr = fo.detect_fast(img, t, nm)
+            assert n == len(oxy) and np.array_equal(xy, oxy) and np.array_equal(r, orr), (h, w, t, nm)
+    # a padded (strided) image gives what its packed copy gives
+    big = rng.integers(0, 256, (120, 256), dtype=np.uint8)
+    view = big[:, 13:173]
+    a = ctx.detect_fast(view, 25, True)
+    b = ctx.detect_fast(np.ascontiguousarray(view), 25, True)
+    assert a[2] == b[2] > 0 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # truncation keeps the first keypoints in row-major order and still reports the total
+    full = ctx.detect_fast(big, 25, True)
+    part = ctx.detect_fast(big, 25, True, max_keypoints=10)
+    assert part[2] == full[2] and len(part[0]) == 10 and np.array_equal(part[0], full[0][:10]) and np.array_equal(part[1], full[1][:10])
+    # thresholds outside [0, 255] are clamped as cv::FAST's C++ path clamps them
+    assert ctx.detect_fast(big, 300, True)[2] == 0
+    assert ctx.detect_fast(big, -4, False)[2] == ctx.detect_fast(big, 0, False)[2]
+    # constant image: no corners
+    assert ctx.detect_fast(np.full((64, 64), 128, np.uint8), 0, False)[2] == 0
+
+
+def test_detect_fast_full_size_properties(ctx):
+    """4K frame (BASELINE C3 shape): oracle parity, and size-independent properties -- suppressed keypoints are a
+    subset of the unsuppressed ones, raising the threshold only removes corners, detection is deterministic."""
+    from oracle import fast_np as fo
+    rng = np.random.default_rng(4)
+    small = rng.integers(0, 256, (2160 // 8 + 1, 3840 // 8 + 1)).astype(np.float32)
+    img = np.kron(small, np.ones((8, 8), np.float32))[:2160, :3840]
+    img = np.clip(img * 0.6 + rng.integers(0, 100, img.shape), 0, 255).astype(np.uint8)
+    xy, r, n = ctx.detect_fast(img, 20, True)
+    oxy, orr = fo.detect_fast(img, 20, True)
+    assert n == len(oxy) > 1000 and np.array_equal(xy, oxy) and np.array_equal(r, orr)
+    allc = ctx.detect_fast(img, 20, False)
+    key = lambda a: set(map(tuple, a.astype(np.int64)))
+    assert key(xy) <= key(allc[0])
+    higher = ctx.detect_fast(img, 35, False)
+    assert key(higher[0]) <= key(allc[0]) and higher[2] < allc[2]
+    again = ctx.detect_fast(img, 20, True)
+    assert np.array_equal(again[0], xy) and np.array_equal(again[1], r)
+    assert (np.diff(xy[:, 1] * 4096 + xy[:, 0]) > 0).all()          # strictly row-major

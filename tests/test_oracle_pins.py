@@ -147,3 +147,21 @@ def test_sift_patch_restatement_against_live_cv2():
         sigma = (1.6 * 1.6 - 0.25) ** 0.5
         np.testing.assert_allclose(sp.gaussian_blur_f32(patches[1], sigma),
                                    cv2.GaussianBlur(patches[1].astype(np.float32), (0, 0), sigma), rtol=0, atol=2e-4)
+
+
+def test_fast_restatement_against_live_cv2():
+    """oracle/fast_np.py against cv2.FastFeatureDetector (what cv::FastFeatureDetector(threshold, nonmax)
+    of descriptorsmatcher.cpp:215-222 runs) on fresh random images, thresholds inside [0, 255]."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import fast_np as fo
+    rng = np.random.default_rng(2024)
+    for k, (h, w) in enumerate(((37, 53), (64, 64), (101, 77), (8, 200))):
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        if k % 2:
+            img = cv2.normalize(cv2.GaussianBlur(img, (0, 0), 1.2), None, 0, 255, cv2.NORM_MINMAX)
+        for t in (0, 5, 17, 60, 254, 255):
+            for nm in (False, True):
+                kps = cv2.FastFeatureDetector_create(threshold=t, nonmaxSuppression=nm).detect(img, None)
+                xy, r = fo.detect_fast(img, t, nm)
+                np.testing.assert_array_equal(xy, np.array([p.pt for p in kps], np.float32).reshape(-1, 2))
+                np.testing.assert_array_equal(r, np.array([p.response for p in kps], np.float32))

@@ -115,11 +115,49 @@ def sift_patches():
     np.savez_compressed(os.path.join(OUT, "sift_patches.npz"), **out)
 
 
+def fast_test_images():
+    """Images for the FAST fixtures: white noise with odd edge lengths (dense corners, every border case),
+    a band-limited texture, a rendered synthetic frame, the smallest image that has an interior pixel and
+    one that has none."""
+    import cv2
+    rng = np.random.default_rng(7100)
+    blur = cv2.GaussianBlur(rng.integers(0, 256, (120, 160)).astype(np.uint8), (0, 0), 1.5)
+    return {"noise": rng.integers(0, 256, (61, 83)).astype(np.uint8),
+            "blur": cv2.normalize(blur, None, 0, 255, cv2.NORM_MINMAX),
+            "frame": synth.make_stereo_case(200, 152, 6, 99, pixels_ray=8, n_distractors=10)["scene"].img1,
+            "tiny7": rng.integers(0, 2, (7, 7)).astype(np.uint8) * 255,
+            "tiny6": rng.integers(0, 256, (6, 9)).astype(np.uint8)}
+
+
+FAST_THRESHOLDS = (0, 1, 10, 20, 40, 100, 255)
+
+
+def fast_keypoints():
+    """K10 fixtures: cv2.FastFeatureDetector (TYPE_9_16, what cv::FastFeatureDetector(threshold, nonmax) of
+    descriptorsmatcher.cpp:215-222 runs) on the images above, thresholds over the whole valid range, with
+    and without non-maximum suppression.  xy / response in cv2's output order."""
+    import cv2
+    out = {}
+    for name, img in fast_test_images().items():
+        out[f"img_{name}"] = img
+        for t in FAST_THRESHOLDS:
+            for nm in (0, 1):
+                kps = cv2.FastFeatureDetector_create(threshold=t, nonmaxSuppression=bool(nm)).detect(img, None)
+                assert all(k.size == 7.0 and k.angle == -1.0 and k.octave == 0 and k.class_id == -1 for k in kps)
+                out[f"xy_{name}_{t}_{nm}"] = np.array([k.pt for k in kps], np.float32).reshape(-1, 2).astype(np.uint16)
+                out[f"r_{name}_{t}_{nm}"] = np.array([k.response for k in kps], np.float32).astype(np.uint8)
+    np.savez_compressed(os.path.join(OUT, "fast_keypoints.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "--sift-only" not in sys.argv:
-        primitives()
-        normals()
-    sift_patches()
+    if "--fast-only" in sys.argv:
+        fast_keypoints()
+    else:
+        if "--sift-only" not in sys.argv:
+            primitives()
+            normals()
+        sift_patches()
+        fast_keypoints()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
