@@ -38,6 +38,7 @@ SYMBOLS = [
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
     "fm3d_describe_patches_sift", "fm3d_describe_patches_sift_dev",
     "fm3d_detect_fast", "fm3d_detect_fast_dev",
+    "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_sift_base_image_dev",
 ]
 
 
@@ -387,7 +388,26 @@ class Context:
         got = min(n.value, max_keypoints)
         return xy[:got].copy(), resp[:got].copy(), n.value
 
+    def describe_keypoints_sift(self, img, kps):
+        """descriptor_extractor_->compute for ExtractorType SIFT on octave-0 keypoints: H x W u8 image,
+        n x 4 f32 (x, y, size, angle) -> n x 128 f32."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        kps = _arr(np.asarray(kps, np.float32).reshape(-1, 4), np.float32)
+        n = kps.shape[0]
+        desc = np.zeros((n, 128), np.float32)
+        self._ck(self.lib.fm3d_describe_keypoints_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], _ptr(kps, _fp), n, _ptr(desc, _fp)))
+        return desc
+
     # ------------------------------------------------------------------ device-pointer entry points
+    def describe_keypoints_sift_dev(self, img, w, h, stride, kps, n, descriptors):
+        self._ck(self.lib.fm3d_describe_keypoints_sift_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(kps), n, C.c_void_p(descriptors)))
+
+    def sift_base_image_dev(self, img, w, h, stride, base):
+        self._ck(self.lib.fm3d_sift_base_image_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(base)))
+
     def detect_fast_dev(self, img, w, h, stride, threshold, nonmax, max_keypoints, xy, response, n_dev):
         self._ck(self.lib.fm3d_detect_fast_dev(self._h, C.c_void_p(img), w, h, stride, int(threshold), int(bool(nonmax)), int(max_keypoints),
                                                C.c_void_p(xy), C.c_void_p(response), C.c_void_p(n_dev)))

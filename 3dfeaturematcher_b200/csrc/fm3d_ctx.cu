@@ -133,7 +133,7 @@ void fm3d_ctx_destroy(fm3d_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < FM3D_SCRATCH_SLOTS; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pyr_mem) cudaFree(ctx->pyr_mem);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

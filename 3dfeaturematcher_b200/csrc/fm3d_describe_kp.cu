@@ -1,0 +1,326 @@
+// fm3d_describe_kp.cu -- K11: SIFT descriptors at the keypoints of a whole frame.
+//
+// Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
+// DescriptorsMatcher::compareWithNNDR / compare / crosscompare
+// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType SIFT (:246) and
+// keypoints of octave 0 (what cv::FastFeatureDetector produces, :215-222: size 7, angle -1).  With such
+// keypoints cv::SIFT::compute builds no scale space: every descriptor is read from
+//     base = GaussianBlur(float(gray), sigma = sqrt(1.6^2 - 0.5^2))            (createInitialImage)
+// by calcSIFTDescriptor(base, round(pt), ori = 360 - angle, scl = size / 2, d = 4, n = 8).
+//
+// Two kernels:
+//   sift_base_kernel      u8 frame -> float base image, separable 13-tap blur fused in shared memory
+//                         (HBM-bound: 1 B read + 4 B written per pixel).
+//   describe_kp_kernel    one CTA per keypoint, one WARP PER SPATIAL CELL of the 4 x 4 descriptor grid.
+//                         A warp walks the bounding box of its cell's trilinear support, evaluates
+//                         calcSIFTDescriptor's per-pixel arithmetic and keeps the part that falls into
+//                         its own cell in eight orientation accumulators per lane (registers), so
+//                         there are no atomics and the summation order is fixed: results are
+//                         bit-reproducible.  A pixel is evaluated by the (up to four) warps whose cells
+//                         it touches; the base image is L2-resident.
+// OpenCV addresses its (d+2)(d+2)(n+2) histogram flat.  A keypoint with angle -1 has ori = 361, so a
+// gradient orientation below 1 degree keeps o0 = -1 after calcSIFTDescriptor's single wrap and its v0
+// share lands in slot n+1 of the previous COLUMN cell, which the circular fold adds to that cell's
+// orientation bin 1 (see fm3d_describe.cu).  A warp therefore also walks the support of its right-hand
+// neighbour when ori >= 360 and collects those shares ("spill").
+#include "fm3d_internal.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int KP_KHALF = 6;          // ksize 13 = cvRound(8 sigma + 1) | 1 for sigma 1.5199
+constexpr int BT_W = 64, BT_H = 32;  // base-image tile per CTA
+constexpr int BT_NT = 256;
+constexpr int KP_NT = 512;           // 16 warps = 16 cells
+
+struct BlurArgs {
+    float kern[KP_KHALF + 1];        // kern[i] = coefficient at distance i from the centre tap
+};
+
+__device__ __forceinline__ int reflect101_any(int i, int n) {
+    // cv::borderInterpolate(BORDER_REFLECT_101) for any offset (n >= 2)
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+__global__ void __launch_bounds__(BT_NT)
+sift_base_kernel(const BlurArgs A, const uint8_t* __restrict__ img, int w, int h, int stride, float* __restrict__ base) {
+    constexpr int IW = BT_W + 2 * KP_KHALF, IH = BT_H + 2 * KP_KHALF;
+    __shared__ float in[IH][IW + 1];
+    __shared__ float rowp[IH][BT_W];
+    const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H, tid = threadIdx.x;
+    for (int i = tid; i < IH * IW; i += BT_NT) {
+        const int r = i / IW, c = i - r * IW;
+        const int gy = reflect101_any(y0 + r - KP_KHALF, h), gx = reflect101_any(x0 + c - KP_KHALF, w);
+        in[r][c] = fm3d_u8f(img[(size_t)gy * stride + gx]);
+    }
+    __syncthreads();
+    // row pass, symmetric form k0 x0 + sum_i k_i (x_-i + x_+i) as cv::sepFilter2D's symmetric row filter
+    for (int i = tid; i < IH * BT_W; i += BT_NT) {
+        const int r = i / BT_W, c = i - r * BT_W;
+        const float* px = &in[r][c + KP_KHALF];
+        float s = __fmul_rn(A.kern[0], px[0]);
+#pragma unroll
+        for (int k = 1; k <= KP_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k], px[k]), s);
+        rowp[r][c] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < BT_H * BT_W; i += BT_NT) {
+        const int r = i / BT_W, c = i - r * BT_W;
+        const int gy = y0 + r, gx = x0 + c;
+        if (gy >= h || gx >= w) continue;
+        float s = __fmul_rn(A.kern[0], rowp[r + KP_KHALF][c]);
+#pragma unroll
+        for (int k = 1; k <= KP_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(rowp[r + KP_KHALF - k][c], rowp[r + KP_KHALF + k][c]), s);
+        base[(size_t)gy * w + gx] = s;
+    }
+}
+
+// cv::fastAtan2 (degrees in [0, 360)); same evaluation as K9 (fm3d_describe.cu)
+__device__ __forceinline__ float kp_fast_atan2_deg(float y, float x) {
+    const float s = 57.29577951308232f;
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float eps = 2.220446049250313e-16f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool ge = ax >= ay;
+    const float c = __fdividef(ge ? ay : ax, __fadd_rn(ge ? ax : ay, eps)), c2 = __fmul_rn(c, c);
+    float a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    if (!ge) a = __fsub_rn(90.0f, a);
+    if (x < 0) a = __fsub_rn(180.0f, a);
+    if (y < 0) a = __fsub_rn(360.0f, a);
+    return a;
+}
+
+__device__ __forceinline__ float kp_sqrt_approx(float a) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+
+struct KpGeom {
+    float cos_t, sin_t;      // divided by hist_width
+    float ori;
+    int ptx, pty, radius;
+    int valid;
+};
+
+__global__ void __launch_bounds__(KP_NT)
+describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __restrict__ kps, float* __restrict__ desc) {
+    __shared__ KpGeom G;
+    __shared__ float hist[128];
+    __shared__ float scale_thr[2];
+    const int tid = threadIdx.x, lane = tid & 31, cell = tid >> 5;
+    const size_t f = blockIdx.x;
+    if (tid == 0) {
+        const float x = kps[4 * f], y = kps[4 * f + 1], size = kps[4 * f + 2], angle = kps[4 * f + 3];
+        KpGeom g;
+        // DescriptorExtractor::compute drops keypoints outside the image or of size <= FLT_EPSILON before SIFT
+        // sees them (KeyPointsFilter::runByImageBorder / runByKeypointSize); such rows are written as zeros
+        g.valid = (x >= 0.f && y >= 0.f && x < (float)w && y < (float)h && size > 1.1920929e-07f && isfinite(size) && isfinite(angle)) ? 1 : 0;
+        g.ptx = __float2int_rn(x); g.pty = __float2int_rn(y);                  // cvRound
+        float ori = __fsub_rn(360.0f, angle);
+        if (fabsf(ori - 360.0f) < 1.1920929e-07f) ori = 0.0f;
+        const float scl = __fmul_rn(size, 0.5f);
+        const float rad = __fmul_rn(ori, (float)(M_PI / 180));
+        // cosf / sinf of the C library are correctly rounded for almost every argument: fp64 evaluation rounded once
+        const float cos_t = (float)cos((double)rad), sin_t = (float)sin((double)rad);
+        const float hist_width = __fmul_rn(3.0f, scl);
+        int radius = __float2int_rn(__fmul_rn(__fmul_rn(__fmul_rn(hist_width, 1.4142135623730951f), 5.0f), 0.5f));
+        const int diag = (int)sqrt((double)w * w + (double)h * h);
+        g.radius = radius < diag ? radius : diag;
+        g.cos_t = __fdiv_rn(cos_t, hist_width);
+        g.sin_t = __fdiv_rn(sin_t, hist_width);
+        g.ori = ori;
+        G = g;
+    }
+    __syncthreads();
+    const KpGeom g = G;
+    if (!g.valid) {
+        if (tid < 128) desc[f * 128 + tid] = 0.0f;
+        return;
+    }
+    const int ci = cell >> 2, cj = cell & 3;
+    const bool spill_possible = g.ori >= 360.0f;
+    // bounding box (pixel offsets i = row, j = column) of the support of cell (ci, cj):
+    // rbin in [ci-1, ci+1), cbin in [cj-1, cj+1) (+ [cj, cj+2) for the spill shares); *_rot = *bin - 1.5
+    int i_lo, i_hi, j_lo, j_hi;
+    {
+        const float inv = 1.0f / (g.cos_t * g.cos_t + g.sin_t * g.sin_t);
+        const float rr[2] = {(float)ci - 2.5f, (float)ci - 0.5f};
+        const float cc[2] = {(float)cj - 2.5f, (float)cj + (spill_possible ? 0.5f : -0.5f)};
+        float fi_lo = 1e30f, fi_hi = -1e30f, fj_lo = 1e30f, fj_hi = -1e30f;
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const float fj = (cc[b] * g.cos_t + rr[a] * g.sin_t) * inv;
+                const float fi = (-cc[b] * g.sin_t + rr[a] * g.cos_t) * inv;
+                fi_lo = fminf(fi_lo, fi); fi_hi = fmaxf(fi_hi, fi);
+                fj_lo = fminf(fj_lo, fj); fj_hi = fmaxf(fj_hi, fj);
+            }
+        const float R = (float)g.radius;
+        i_lo = (int)floorf(fmaxf(fi_lo, -R - 1.0f)) - 1; i_hi = (int)ceilf(fminf(fi_hi, R + 1.0f)) + 1;
+        j_lo = (int)floorf(fmaxf(fj_lo, -R - 1.0f)) - 1; j_hi = (int)ceilf(fminf(fj_hi, R + 1.0f)) + 1;
+        i_lo = max(i_lo, max(-g.radius, 1 - g.pty)); i_hi = min(i_hi, min(g.radius, h - 2 - g.pty));
+        j_lo = max(j_lo, max(-g.radius, 1 - g.ptx)); j_hi = min(j_hi, min(g.radius, w - 2 - g.ptx));
+    }
+    float acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) acc[b] = 0.0f;
+    const int bw = j_hi - j_lo + 1, bh = i_hi - i_lo + 1;
+    if (bw > 0 && bh > 0) {
+        const float inv_bw = 1.0f / (float)bw;
+        const int total = bw * bh;
+        for (int k = lane; k < total; k += 32) {
+            int q = __float2int_rd(((float)k + 0.5f) * inv_bw);
+            int rem = k - q * bw;
+            if (rem < 0) { q--; rem += bw; } else if (rem >= bw) { q++; rem -= bw; }   // float quotient off by one for huge boxes
+            const int i = i_lo + q, j = j_lo + rem;
+            const float fi = (float)i, fj = (float)j;
+            const float c_rot = __fsub_rn(__fmul_rn(fj, g.cos_t), __fmul_rn(fi, g.sin_t));
+            const float r_rot = __fadd_rn(__fmul_rn(fj, g.sin_t), __fmul_rn(fi, g.cos_t));
+            const float rbin = __fsub_rn(__fadd_rn(r_rot, 2.0f), 0.5f);
+            const float cbin = __fsub_rn(__fadd_rn(c_rot, 2.0f), 0.5f);
+            if (!(rbin > -1.0f && rbin < 4.0f && cbin > -1.0f && cbin < 4.0f)) continue;
+            const float r0f = floorf(rbin), c0f = floorf(cbin);
+            const int dr = ci - (int)r0f;                    // this cell is row r0 (dr = 0) or r0 + 1 (dr = 1) of the split
+            if (dr != 0 && dr != 1) continue;
+            const int dcn = cj - (int)c0f;                   // normal share: column c0 + dcn
+            const int dcs = dcn + 1;                         // spill share of the right-hand neighbour cell
+            const bool normal_ok = dcn == 0 || dcn == 1;
+            const bool spill_ok = spill_possible && (dcs == 0 || dcs == 1);
+            if (!normal_ok && !spill_ok) continue;
+            const float* p = base + (size_t)(g.pty + i) * w + (g.ptx + j);
+            const float dx = __fsub_rn(__ldg(p + 1), __ldg(p - 1)), dy = __fsub_rn(__ldg(p - w), __ldg(p + w));
+            const float wgt = __expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), -0.125f));
+            const float mag = __fmul_rn(kp_sqrt_approx(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), wgt);
+            float obin = __fmul_rn(__fsub_rn(kp_fast_atan2_deg(dy, dx), g.ori), 8 / 360.0f);
+            const float of = floorf(obin);
+            obin = __fsub_rn(obin, of);
+            int o0 = (int)of;
+            o0 = o0 < 0 ? o0 + 8 : o0;
+            o0 = o0 >= 8 ? o0 - 8 : o0;
+            const bool spill = o0 < 0;                       // only o0 == -1 is reachable (ori <= 361)
+            const float rb = __fsub_rn(rbin, r0f), cb = __fsub_rn(cbin, c0f);
+            const float v_r1 = __fmul_rn(mag, rb);
+            const float v_r = dr ? v_r1 : __fsub_rn(mag, v_r1);
+            const float v_rc1 = __fmul_rn(v_r, cb), v_rc0 = __fsub_rn(v_r, v_rc1);
+            float add_a = 0.0f, add_b = 0.0f;                // shares for bins oa, ob
+            int oa = -1, ob = -1;
+            if (normal_ok) {
+                const float v_rc = dcn ? v_rc1 : v_rc0;
+                const float v1 = __fmul_rn(v_rc, obin), v0 = __fsub_rn(v_rc, v1);
+                if (!spill) { oa = o0 & 7; add_a = v0; ob = (o0 + 1) & 7; add_b = v1; }      // slot n folds onto bin 0
+                else { ob = 0; add_b = v1; }                                                  // slot o0 + 1 = 0 of the proper cell
+            }
+            if (spill_ok && spill) {
+                const float v_rc = dcs ? v_rc1 : v_rc0;
+                const float v1 = __fmul_rn(v_rc, obin);
+                oa = 1; add_a = __fsub_rn(v_rc, v1);         // v0 -> slot n+1 of this (left-hand) cell -> bin 1
+            }
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                acc[b] = __fadd_rn(acc[b], b == oa ? add_a : 0.0f);
+                acc[b] = __fadd_rn(acc[b], b == ob ? add_b : 0.0f);
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        float s = acc[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hist[cell * 8 + b] = s;
+    }
+    __syncthreads();
+    // normalisation (calcSIFTDescriptor's tail): clip at 0.2 |h|, scale to 512, saturate to u8
+    if (tid < 32) {
+        float v[4], s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = hist[tid * 4 + k]; s = fmaf(v[k], v[k], s); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float thr = __fmul_rn(__fsqrt_rn(s), 0.2f);
+        s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const float c = fminf(v[k], thr); s = fmaf(c, c, s); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) {
+            scale_thr[0] = __fdiv_rn(512.0f, fmaxf(__fsqrt_rn(s), 1.1920929e-07f));
+            scale_thr[1] = thr;
+        }
+    }
+    __syncthreads();
+    if (tid < 128)
+        desc[f * 128 + tid] = fminf(fmaxf(rintf(__fmul_rn(fminf(hist[tid], scale_thr[1]), scale_thr[0])), 0.0f), 255.0f);
+}
+
+void blur_args(BlurArgs& A) {
+    const double sigma = sqrt(fmax(1.6 * 1.6 - 0.5 * 0.5, 0.01));       // createInitialImage, no up-sampling
+    double t[2 * KP_KHALF + 1], sum = 0;
+    for (int i = 0; i <= 2 * KP_KHALF; i++) {                            // cv::getGaussianKernel(13, sigma, CV_32F)
+        const double x = i - KP_KHALF;
+        t[i] = exp(-0.5 / (sigma * sigma) * x * x);
+        sum += t[i];
+    }
+    for (int i = 0; i <= KP_KHALF; i++) A.kern[i] = (float)(t[KP_KHALF + i] / sum);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fm3d_sift_base_image_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* base) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, img && base && w >= 2 && h >= 2 && stride >= w);
+    if (int rc = fm3d_bind(ctx)) return rc;
+    BlurArgs A;
+    blur_args(A);
+    dim3 grid((w + BT_W - 1) / BT_W, (h + BT_H - 1) / BT_H);
+    sift_base_kernel<<<grid, BT_NT, 0, ctx->stream>>>(A, img, w, h, stride, base);
+    FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
+}
+
+int fm3d_describe_keypoints_sift_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps, int n,
+                                     float* descriptors) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && (n == 0 || (img && kps && descriptors && w >= 2 && h >= 2 && stride >= w)));
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    float* base = nullptr;
+    if (int rc = fm3d_scratch(ctx, 8, sizeof(float) * (size_t)w * h, (void**)&base)) return rc;
+    if (int rc = fm3d_sift_base_image_dev(ctx, img, w, h, stride, base)) return rc;
+    describe_kp_kernel<<<n, KP_NT, 0, ctx->stream>>>(base, w, h, kps, descriptors);
+    FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
+}
+
+int fm3d_describe_keypoints_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps, int n,
+                                 float* descriptors) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && (n == 0 || (img && kps && descriptors && w >= 2 && h >= 2 && stride >= w)));
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t bi = (size_t)w * h, bk = sizeof(float) * 4 * (size_t)n, bd = sizeof(float) * 128 * (size_t)n;
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, al(bi) + al(bk) + al(bd), (void**)&d)) return rc;
+    FM3D_CUDA(ctx, cudaMemcpy2DAsync(d, (size_t)w, img, (size_t)stride, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_copy++;
+    if (int rc = fm3d_h2d(ctx, d + al(bi), kps, bk)) return rc;
+    float* d_desc = reinterpret_cast<float*>(d + al(bi) + al(bk));
+    if (int rc = fm3d_describe_keypoints_sift_dev(ctx, reinterpret_cast<const uint8_t*>(d), w, h, w,
+                                                  reinterpret_cast<const float*>(d + al(bi)), n, d_desc)) return rc;
+    if (int rc = fm3d_d2h(ctx, descriptors, d_desc, bd)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@
 #include "../../include/fm3d.h"
 
 #define FM3D_MAX_LEVELS 8
+#define FM3D_SCRATCH_SLOTS 12
 
 // ---------------------------------------------------------------- device-side camera model
 // K, dist (OpenCV order k1,k2,p1,p2,k3) and g12 = [R|t] (X2 = R X1 + t), all fp64 as the
@@ -60,8 +61,8 @@ struct fm3d_ctx {
     fm3d_pyramid_desc pyr{};
     bool has_images = false;
     // grow-only scratch (device) and pinned host staging
-    void* scratch[8] = {nullptr};
-    size_t scratch_bytes[8] = {0};
+    void* scratch[FM3D_SCRATCH_SLOTS] = {nullptr};
+    size_t scratch_bytes[FM3D_SCRATCH_SLOTS] = {0};
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     // counters

@@ -382,6 +382,26 @@ int fm3d_detect_fast(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
 int fm3d_detect_fast_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int threshold,
                          int nonmax, int max_keypoints, float* xy, float* response, int* n_dev);
 
+/* ---------------------------------------------------------- keypoint description ---- */
+
+/* Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
+ * DescriptorsMatcher::compareWithNNDR / compare / crosscompare
+ * (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType SIFT (:246,
+ * default octave layers 3 / sigma 1.6) and keypoints of octave 0 -- what DetectorType FAST produces
+ * (:215-222: size 7, angle -1) -- for which cv::SIFT::compute reads every descriptor from
+ * GaussianBlur(float(frame), sqrt(1.6^2 - 0.5^2)) without building a scale space.
+ *   img            h rows of w u8 pixels, `stride` bytes apart
+ *   kps            n x 4 f32: KeyPoint::pt.x, pt.y, size, angle (angle -1 = "not set", as FAST leaves it)
+ *   descriptors    n x 128 f32, integer-valued in [0, 255] (cv::SIFT's CV_32F rows), row k = keypoint k
+ * A keypoint outside the image or of size <= FLT_EPSILON (DescriptorExtractor::compute removes those before
+ * the extractor runs; the adapters do the same) gets an all-zero row. */
+int fm3d_describe_keypoints_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
+                                 int n, float* descriptors);
+int fm3d_describe_keypoints_sift_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                                     const float* kps, int n, float* descriptors);
+/* The base image alone (createInitialImage): base is w x h f32, rows w floats apart, device memory. */
+int fm3d_sift_base_image_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* base);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,3 +128,26 @@ def test_fast_restatement_against_cv2_golden_vectors():
                 np.testing.assert_array_equal(r, g[f"r_{name}_{t}_{nm}"].astype(np.float32))
                 total += len(xy)
     assert total > 50000
+
+
+def test_sift_keypoint_restatement_against_cv2_golden_vectors():
+    """oracle/sift_kp_np.py (K11: descriptor_extractor_->compute, ExtractorType SIFT, octave-0 keypoints) against
+    the committed outputs of cv2.SIFT_create().compute on FAST keypoints and on keypoints with real sizes /
+    angles / border positions."""
+    from oracle import sift_kp_np as sk
+    g = np.load(os.path.join(GOLD, "sift_keypoints.npz"))
+    imgs = np.load(os.path.join(GOLD, "fast_keypoints.npz"))
+    seen = 0
+    for key in g.files:
+        if not key.startswith("k_"):
+            continue
+        name = key.split("_")[1]
+        d = sk.describe_keypoints_sift(imgs[f"img_{name}"], g[key])
+        _desc_close(d, g["d" + key[1:]], frac_exact=0.999)
+        seen += len(d)
+    assert seen > 1000
+    # FAST keypoints carry angle -1 (ori = 361): the flat-addressing spill fills bins a wrapped ori would not
+    k = g["k_frame_fast"].copy()
+    k[:, 3] = 359.0                 # 360 - 359 = 1 degree: the same rotation without the out-of-range ori
+    alt = sk.describe_keypoints_sift(imgs["img_frame"], k)
+    assert (alt != g["d_frame_fast"]).any()

@@ -897,3 +897,90 @@ def test_detect_fast_full_size_properties(ctx):
     again = ctx.detect_fast(img, 20, True)
     assert np.array_equal(again[0], xy) and np.array_equal(again[1], r)
     assert (np.diff(xy[:, 1] * 4096 + xy[:, 0]) > 0).all()          # strictly row-major
+
+
+# ------------------------------------------------------------------ K11: SIFT descriptors at frame keypoints
+def test_describe_keypoints_sift_golden_vectors(ctx):
+    """descriptor_extractor_->compute (descriptorsmatcher.cpp:114-115, ExtractorType SIFT) on octave-0 keypoints:
+    the committed outputs of cv2.SIFT_create().compute.  Values are quantised to integers: +-1 on isolated
+    entries (summation order)."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "sift_keypoints.npz"))
+    imgs = np.load(os.path.join(gold, "fast_keypoints.npz"))
+    seen = 0
+    for key in g.files:
+        if not key.startswith("k_"):
+            continue
+        name = key.split("_")[1]
+        d = ctx.describe_keypoints_sift(imgs[f"img_{name}"], g[key])
+        assert d.dtype == np.float32 and d.shape == (len(g[key]), 128)
+        _desc_close(d, g["d" + key[1:]])
+        seen += len(d)
+    assert seen > 1000
+
+
+def test_describe_keypoints_sift_against_oracle_and_edges(ctx):
+    from oracle import sift_kp_np as sk
+    rng = np.random.default_rng(321)
+    for h, w in ((97, 141), (64, 200), (33, 35)):
+        img = rng.integers(0, 256, (h, w)).astype(np.float32)
+        img = ((img + np.roll(img, 1, 0) + np.roll(img, 1, 1) + np.roll(np.roll(img, 1, 0), 1, 1)) / 4).astype(np.uint8)
+        n = 90
+        k = np.stack([rng.uniform(0, w - 1, n), rng.uniform(0, h - 1, n), rng.uniform(1.2, 40, n), rng.uniform(0, 360, n)], 1).astype(np.float32)
+        k[:15, 3] = -1                                       # FAST's "no orientation"
+        k[15:30, 2] = 7                                      # FAST's size
+        k[30:34, :2] = [[0, 0], [w - 1, h - 1], [0, h - 1], [w - 1, 0]]
+        k[34, 3] = 0
+        k[35, 2] = 300                                       # window larger than the image
+        got = ctx.describe_keypoints_sift(img, k)
+        _desc_close(got, sk.describe_keypoints_sift(img, k))
+        # deterministic: fixed summation order, no atomics
+        assert np.array_equal(got, ctx.describe_keypoints_sift(img, k))
+        # one keypoint alone gives the row it gave in the batch; a strided image gives what its packed copy gives
+        assert np.array_equal(ctx.describe_keypoints_sift(img, k[7:8])[0], got[7])
+        big = np.zeros((h, w + 37), np.uint8)
+        big[:, 5:5 + w] = img
+        assert np.array_equal(ctx.describe_keypoints_sift(big[:, 5:5 + w], k), got)
+        # keypoints DescriptorExtractor::compute would have removed: zero rows, the others unchanged
+        bad = k.copy()
+        bad[[2, 40], 0] = [-1.0, w]
+        bad[41, 1] = h + 3
+        bad[42, 2] = 0
+        z = ctx.describe_keypoints_sift(img, bad)
+        assert not z[[2, 40, 41, 42]].any()
+        keep = np.setdiff1d(np.arange(n), [2, 40, 41, 42])
+        assert np.array_equal(z[keep], got[keep])
+    assert ctx.describe_keypoints_sift(np.zeros((40, 40), np.uint8), np.zeros((0, 4), np.float32)).shape == (0, 128)
+    assert not ctx.describe_keypoints_sift(np.full((40, 40), 9, np.uint8), [[20, 20, 7, -1]]).any()     # constant image
+
+
+def test_detect_describe_match_chain_full_size(ctx):
+    """DetectorType FAST + ExtractorType SIFT on a 1280 x 720 frame (BASELINE C2 shape), all three steps of
+    compareWithNNDR (descriptorsmatcher.cpp:110-117) on the GPU: oracle parity on a sample of the keypoints, and
+    size-independent properties -- describing a frame against itself matches every keypoint to itself at
+    distance 0, a translated copy of the frame gives the same descriptors at the translated keypoints."""
+    from oracle import sift_kp_np as sk
+    from oracle import fast_np as fo
+    rng = np.random.default_rng(11)
+    small = rng.integers(0, 256, (720 // 6 + 4, 1280 // 6 + 4)).astype(np.float32)
+    big = np.kron(small, np.ones((6, 6), np.float32))
+    big = np.clip(big * 0.7 + rng.integers(0, 77, big.shape), 0, 255).astype(np.uint8)
+    img = np.ascontiguousarray(big[:720, :1280])
+    xy, r, n = ctx.detect_fast(img, 30, True)
+    assert n == len(xy) > 2000
+    k = np.concatenate([xy, np.full((n, 1), 7, np.float32), np.full((n, 1), -1, np.float32)], 1)
+    d = ctx.describe_keypoints_sift(img, k)
+    pick = rng.choice(n, 200, replace=False)
+    _desc_close(d[pick], sk.describe_keypoints_sift(img, k[pick]))
+    idx, dist = ctx.match_knn2_f32(d, d)
+    same = idx[:, 0] == np.arange(n)
+    assert (dist[:, 0] == 0).all() and (same | (dist[:, 1] == 0)).all()       # itself, or an exact duplicate with a lower index
+    # translation by (dx, dy): keypoints whose window stays inside both frames keep their descriptor exactly
+    dx, dy = 9, 5
+    img2 = np.ascontiguousarray(big[dy:dy + 720, dx:dx + 1280])
+    inner = (xy[:, 0] > 60 + dx) & (xy[:, 0] < 1280 - 60) & (xy[:, 1] > 60 + dy) & (xy[:, 1] < 720 - 60)
+    k2 = k[inner].copy()
+    k2[:, 0] -= dx
+    k2[:, 1] -= dy
+    assert inner.sum() > 1000 and np.array_equal(ctx.describe_keypoints_sift(img2, k2), d[inner])

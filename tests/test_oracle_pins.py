@@ -165,3 +165,26 @@ def test_fast_restatement_against_live_cv2():
                 xy, r = fo.detect_fast(img, t, nm)
                 np.testing.assert_array_equal(xy, np.array([p.pt for p in kps], np.float32).reshape(-1, 2))
                 np.testing.assert_array_equal(r, np.array([p.response for p in kps], np.float32))
+
+
+def test_sift_keypoint_restatement_against_live_cv2():
+    """oracle/sift_kp_np.py against cv2.SIFT_create().compute on fresh images: FAST keypoints (size 7, angle -1,
+    what DetectorType FAST + ExtractorType SIFT of descriptorsmatcher.cpp:215-222, :246 hands to compute) and
+    keypoints with arbitrary size / angle, including positions on the image border."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import sift_kp_np as sk
+    rng = np.random.default_rng(77)
+    sift = cv2.SIFT_create()
+    for h, w in ((90, 131), (64, 64)):
+        img = cv2.normalize(cv2.GaussianBlur(rng.integers(0, 256, (h, w)).astype(np.uint8), (0, 0), 1.3), None, 0, 255, cv2.NORM_MINMAX)
+        kps = cv2.FastFeatureDetector_create(threshold=15, nonmaxSuppression=True).detect(img, None)[:150]
+        arr = np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32).reshape(-1, 4)
+        extra = np.stack([rng.uniform(0, w - 1, 60), rng.uniform(0, h - 1, 60), rng.uniform(1.5, 30, 60), rng.uniform(0, 360, 60)], 1).astype(np.float32)
+        extra[:3, :2] = [[0, 0], [w - 1, h - 1], [w - 1, 0]]
+        arr = np.concatenate([arr, extra])
+        cvk = [cv2.KeyPoint(float(a[0]), float(a[1]), float(a[2]), float(a[3])) for a in arr]
+        cvk2, want = sift.compute(img, cvk)
+        assert len(cvk2) == len(cvk)
+        got = sk.describe_keypoints_sift(img, arr)
+        diff = np.abs(got - want)
+        assert diff.max() <= 1 and (diff == 0).mean() >= 0.999

@@ -149,9 +149,50 @@ def fast_keypoints():
     np.savez_compressed(os.path.join(OUT, "fast_keypoints.npz"), **out)
 
 
+def sift_general_keypoints(w, h, count, seed):
+    """Keypoints with real sizes and angles (what a caller can inject), some on the image border, some with
+    angle -1 / 0 / 360-epsilon."""
+    rng = np.random.default_rng(seed)
+    k = np.stack([rng.uniform(0, w - 1, count), rng.uniform(0, h - 1, count), rng.uniform(2, 24, count),
+                  rng.uniform(0, 360, count)], 1).astype(np.float32)
+    k[:count // 10, 3] = -1
+    k[count // 10:count // 10 + 5, 3] = 0
+    k[count // 10 + 5:count // 10 + 8, 3] = 359.99997
+    k[-4:, :2] = [[0, 0], [w - 1, h - 1], [0.4, h - 1.4], [w - 1, 3]]
+    return k
+
+
+def sift_keypoints():
+    """K11 fixtures: cv2.SIFT_create().compute (descriptor_extractor_->compute of descriptorsmatcher.cpp:114-115
+    with ExtractorType SIFT) on the FAST keypoints (threshold 20, non-maximum suppression, at most 300 per
+    image) of the images of fast_keypoints.npz, and on keypoints with real sizes / angles.  The images
+    themselves live in fast_keypoints.npz."""
+    import cv2
+    sift = cv2.SIFT_create()
+    out = {}
+    for name, img in fast_test_images().items():
+        kps = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True).detect(img, None)[:300]
+        sets = {"fast": np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32).reshape(-1, 4)}
+        if name in ("blur", "frame"):
+            sets["general"] = sift_general_keypoints(img.shape[1], img.shape[0], 120, 7200 + len(name))
+        for tag, arr in sets.items():
+            cvk = [cv2.KeyPoint(float(a[0]), float(a[1]), float(a[2]), float(a[3])) for a in arr]
+            if cvk:
+                cvk2, d = sift.compute(img, cvk)
+                assert len(cvk2) == len(cvk)            # nothing filtered: row k belongs to keypoint k
+            else:
+                d = np.zeros((0, 128), np.float32)
+            assert np.array_equal(d, np.rint(d)) and d.min(initial=0) >= 0 and d.max(initial=0) <= 255
+            out[f"k_{name}_{tag}"] = arr
+            out[f"d_{name}_{tag}"] = d.astype(np.uint8)
+    np.savez_compressed(os.path.join(OUT, "sift_keypoints.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "--fast-only" in sys.argv:
+    if "--sift-kp-only" in sys.argv:
+        sift_keypoints()
+    elif "--fast-only" in sys.argv:
         fast_keypoints()
     else:
         if "--sift-only" not in sys.argv:
@@ -159,5 +200,6 @@ if __name__ == "__main__":
             normals()
         sift_patches()
         fast_keypoints()
+        sift_keypoints()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
