@@ -151,6 +151,11 @@ DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv
     extractor_type_ = extractorType;
     // the reference picks the LSH (binary) matcher for these (descriptorsmatcher.cpp:64-67)
     binary_ = extractorType == "ORB" || extractorType == "BRISK" || extractorType == "FREAK";
+    // generateDetector (descriptorsmatcher.cpp:176-289)
+    detector_type_ = (std::string)fs["FeatureOptions"]["DetectorType"];
+    detector_mode_ = (std::string)fs["FeatureOptions"]["DetectorMode"];
+    fast_threshold_ = (int)fs["FeatureOptions"]["FastDetector"]["Threshold"];                 // :218
+    fast_nonmax_ = (int)fs["FeatureOptions"]["FastDetector"]["NonMaxSuppression"] > 0;        // :219-220
     host_ctx();
 }
 
@@ -165,8 +170,44 @@ void DescriptorsMatcher::setFeatures(const std::vector<cv::KeyPoint>& ka, const 
 void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv::KeyPoint>& kb, cv::Mat& da, cv::Mat& db) {
     if (have_features_) { ka = kpts_a_; kb = kpts_b_; da = desc_a_; db = desc_b_; return; }
     if (!da.empty() && !db.empty()) return;  // pre-filled by the caller
-    throw std::runtime_error("fm3d: DescriptorsMatcher needs injected features (setFeatures): detection and "
-                             "description are upstream of the GPU hot path");
+    // descriptorsmatcher.cpp:110-115: detect on both frames, then compute on both frames.  DetectorType FAST
+    // (STATIC) with ExtractorType SIFT runs on the GPU (K10 + K11); the other detectors / extractors of the
+    // reference (SURF, STAR, MSER, ORB, BRISK, FREAK of OpenCV 2.4) are upstream code this library does not carry.
+    if (detector_type_ == "FAST" && detector_mode_ == "STATIC" && extractor_type_ == "SIFT") {
+        detectAndDescribe(image_a_, ka, da);
+        detectAndDescribe(image_b_, kb, db);
+        return;
+    }
+    throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC) + "
+                             "ExtractorType SIFT only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
+                             "); inject the features of other detectors with setFeatures");
+}
+
+// feature_detector_->detect + descriptor_extractor_->compute for one frame.  cv::FastFeatureDetector appends
+// KeyPoint(x, y, 7.f, -1, score) in row-major order; DescriptorExtractor::compute would drop keypoints outside the
+// image or of size 0 before cv::SIFT sees them -- FAST produces neither.
+void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv::KeyPoint>& kpts, cv::Mat& desc) {
+    if (image.empty() || image.type() != CV_8UC1) throw std::runtime_error("fm3d: DescriptorsMatcher needs CV_8UC1 frames");
+    fm3d_ctx* ctx = host_ctx();
+    const uint8_t* px = image.ptr<uint8_t>(0);
+    const int w = image.cols, h = image.rows, stride = (int)image.step1();
+    int n = 0;
+    check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, fast_threshold_, fast_nonmax_, 0, nullptr, nullptr, &n), "detect (count)");
+    std::vector<float> xy((size_t)2 * (n > 0 ? n : 1)), resp((size_t)(n > 0 ? n : 1));
+    if (n > 0) check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, fast_threshold_, fast_nonmax_, n, xy.data(), resp.data(), &n), "detect");
+    kpts.clear();
+    kpts.reserve(n);
+    std::vector<float> k4((size_t)4 * (n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        cv::KeyPoint kp(xy[2 * i], xy[2 * i + 1], 7.f);
+        kp.angle = -1.f;
+        kp.response = resp[i];
+        kpts.push_back(kp);
+        k4[4 * i] = kp.pt.x; k4[4 * i + 1] = kp.pt.y; k4[4 * i + 2] = kp.size; k4[4 * i + 3] = kp.angle;
+    }
+    if (n == 0) { desc = cv::Mat(); return; }
+    desc = cv::Mat::zeros(cv::Size(128, n), CV_32F);
+    check(ctx, fm3d_describe_keypoints_sift(ctx, px, w, h, stride, k4.data(), n, desc.ptr<float>()), "compute (SIFT)");
 }
 
 void DescriptorsMatcher::knn(const cv::Mat& q, const cv::Mat& t, std::vector<std::vector<cv::DMatch> >& out) {

@@ -40,7 +40,9 @@ private:
     std::vector<cv::KeyPoint> kpts_a_, kpts_b_;
     std::vector<std::vector<cv::DMatch> > matches_;
     std::vector<unsigned char> mutual_;
+    void detectAndDescribe(const cv::Mat& image, std::vector<cv::KeyPoint>& kpts, cv::Mat& desc);
     bool binary_, have_features_;
-    std::string extractor_type_;
+    std::string extractor_type_, detector_type_, detector_mode_;
+    int fast_threshold_, fast_nonmax_;
 };
 #endif

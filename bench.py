@@ -437,6 +437,50 @@ def run_gpu_arm(args):
     after_ms = [sum(ev_after[s_][j].elapsed_time(ev_after[s_][j + 1]) for s_ in range(alt_steps)) / alt_steps for j in range(3)]
     pdesc_nonzero = int((d_pdesc[:n_inl] != 0).sum().item())
 
+    # ---- before the path: what compareWithNNDR does first (descriptorsmatcher.cpp:110-115) with
+    # DetectorType FAST + ExtractorType SIFT: K10 detection and K11 description of BOTH frames, device-resident,
+    # NOT part of `value` (the headline matches the synthetic descriptors BASELINE.json names)
+    FAST_T, KP_CAP = 20, 1 << 17
+    with torch.cuda.stream(stream):
+        d_kxy = torch.zeros((2, KP_CAP, 2), dtype=torch.float32, device=dev)
+        d_kresp = torch.zeros((2, KP_CAP), dtype=torch.float32, device=dev)
+        d_kn = torch.zeros(2, dtype=torch.int32, device=dev)
+        d_k4 = torch.zeros((2, KP_CAP, 4), dtype=torch.float32, device=dev)
+        d_kdesc = torch.zeros((2, KP_CAP, 128), dtype=torch.float32, device=dev)
+    stream.synchronize()
+    n_kp = [0, 0]
+
+    def before_path(events=None, describe=True):
+        with torch.cuda.stream(stream):
+            if events: events[0].record(stream)
+            for a, img in enumerate((d_img1, d_img2)):
+                ctx.detect_fast_dev(img.data_ptr(), W, H, W, FAST_T, True, KP_CAP, d_kxy[a].data_ptr(), d_kresp[a].data_ptr(),
+                                    d_kn[a:].data_ptr())
+            if events: events[1].record(stream)
+            if describe:
+                for a, img in enumerate((d_img1, d_img2)):
+                    if n_kp[a] > 0:
+                        ctx.describe_keypoints_sift_dev(img.data_ptr(), W, H, W, d_k4[a].data_ptr(), n_kp[a], d_kdesc[a].data_ptr())
+            if events: events[2].record(stream)
+    before_path(describe=False)
+    stream.synchronize()
+    n_kp = [min(int(v), KP_CAP) for v in d_kn.cpu().tolist()]
+    with torch.cuda.stream(stream):
+        d_k4[:, :, :2] = d_kxy
+        d_k4[:, :, 2] = 7.0             # cv::FastFeatureDetector: KeyPoint(x, y, 7.f, -1, score)
+        d_k4[:, :, 3] = -1.0
+    for _ in range(2):
+        before_path()
+        flush_l2()
+    barrier()
+    ev_before = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(alt_steps)]
+    for s_ in range(alt_steps):
+        before_path(ev_before[s_])
+        flush_l2()
+    barrier()
+    before_ms = [sum(ev_before[s_][j].elapsed_time(ev_before[s_][j + 1]) for s_ in range(alt_steps)) / alt_steps for j in range(2)]
+    kdesc_rows_nonzero = [int((d_kdesc[a, :n_kp[a]] != 0).any(1).sum().item()) for a in range(2)]
+
     # ---- reduce over ranks: max time, summed features
     tm = torch.tensor([t_dev_ms, t_e2e * 1e3, t_alt_ms], dtype=torch.float64, device=dev)
     feats = torch.tensor([float(n_match), float(hm), float(n_match_alt)], dtype=torch.float64, device=dev)
@@ -546,6 +590,15 @@ def run_gpu_arm(args):
                 "patch_descriptors_per_s": n_inl / (after_ms[2] * 1e-3) if after_ms[2] > 0 else None,
                 "patches_hbm_write_gbs": n_inl * S_patch * S_patch / (after_ms[1] * 1e-3) / 1e9 if after_ms[1] > 0 else None,
                 "descriptor_values_nonzero": pdesc_nonzero},
+            "before_path_rank0": {
+                "note": "what compareWithNNDR does first with DetectorType FAST + ExtractorType SIFT (descriptorsmatcher.cpp:110-115): "
+                        "FAST-9-16 detection (K10) and SIFT description at the detected keypoints (K11) of BOTH frames, "
+                        "device-resident, CUDA events; not part of `value`",
+                "fast_threshold": FAST_T, "keypoints": n_kp,
+                "ms": {"detect_both_frames": before_ms[0], "describe_both_frames": before_ms[1]},
+                "detect_hbm_gbs": 2 * W * H / (before_ms[0] * 1e-3) / 1e9 if before_ms[0] > 0 else None,
+                "descriptors_per_s": sum(n_kp) / (before_ms[1] * 1e-3) if before_ms[1] > 0 else None,
+                "descriptor_rows_nonzero": kdesc_rows_nonzero},
             "wall_s_device_arm": wall_dev, "gpu": info["name"],
         }
         emit(out)

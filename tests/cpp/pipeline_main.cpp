@@ -1,6 +1,7 @@
 // Test driver: the call sequence of the reference's main.cpp (main.cpp:91-187) on top of the
-// fm3d class adapters.  Features come from a file because keypoint detection/description is
-// upstream of the hot path.  Usage: pipeline_main -s settings.yml features.bin result.bin
+// fm3d class adapters.  Features come from a file (any upstream detector / extractor), or -- with "-" in place
+// of the file and DetectorType FAST + ExtractorType SIFT in the settings -- from the frames themselves, as in
+// main.cpp.  Usage: pipeline_main -s settings.yml <features.bin | -> result.bin [circular-settings.yml]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +26,12 @@ int main(int argc, char** argv) {
     cv::Mat img1 = cv::imread(IMG_1, CV_LOAD_IMAGE_GRAYSCALE), img2 = cv::imread(IMG_2, CV_LOAD_IMAGE_GRAYSCALE);
     if (img1.empty() || img2.empty()) { std::cerr << "could not read images\n"; return 1; }
 
+    const bool detect_here = strcmp(argv[3], "-") == 0;
+    std::vector<cv::KeyPoint> kpts1, kpts2;
+    cv::Mat desc1, desc2;
+    std::vector<cv::DMatch> matches;
+    DescriptorsMatcher dm(fs, img1, img2);
+    if (!detect_here) {
     // upstream features
     FILE* f = fopen(argv[3], "rb");
     if (!f) { std::cerr << "no features file\n"; return 1; }
@@ -39,11 +46,8 @@ int main(int argc, char** argv) {
     for (int i = 0; i < n1; i++) in1[i] = cv::KeyPoint(k1[2 * i], k1[2 * i + 1], 1.f);
     for (int i = 0; i < n2; i++) in2[i] = cv::KeyPoint(k2[2 * i], k2[2 * i + 1], 1.f);
 
-    std::vector<cv::KeyPoint> kpts1, kpts2;
-    cv::Mat desc1, desc2;
-    std::vector<cv::DMatch> matches;
-    DescriptorsMatcher dm(fs, img1, img2);
     dm.setFeatures(in1, d1, in2, d2);
+    }
     dm.compareWithNNDR(fs["NNDR"]["epsilon"], matches, kpts1, kpts2, desc1, desc2);
 
     std::vector<double> pos1, pos2;
@@ -136,6 +140,21 @@ int main(int argc, char** argv) {
     int dr = patchDescriptors.rows, dc = patchDescriptors.cols;
     fwrite(&dr, 4, 1, o); fwrite(&dc, 4, 1, o);
     if (dr > 0) fwrite(patchDescriptors.data, 4, (size_t)dr * dc, o);
+    if (detect_here) {
+        // what compareWithNNDR returned for the two frames: keypoints (pt, size, angle, response) and descriptors
+        const std::vector<cv::KeyPoint>* ks[2] = {&kpts1, &kpts2};
+        const cv::Mat* ds[2] = {&desc1, &desc2};
+        for (int a = 0; a < 2; a++) {
+            int n = (int)ks[a]->size(), cols = ds[a]->cols;
+            fwrite(&n, 4, 1, o); fwrite(&cols, 4, 1, o);
+            for (int i = 0; i < n; i++) {
+                const cv::KeyPoint& k = (*ks[a])[i];
+                const float v[5] = {k.pt.x, k.pt.y, k.size, k.angle, k.response};
+                fwrite(v, 4, 5, o);
+            }
+            if (n > 0) fwrite(ds[a]->data, 4, (size_t)n * cols, o);
+        }
+    }
     fclose(o);
     std::cout << nm << " matches, " << np << " inliers, " << nn << " normals, patches " << S << "x" << S << std::endl;
     return 0;

@@ -50,7 +50,14 @@ def _g(rod, t):
     return g
 
 
-def _write_inputs(tmp, case, r, pyramids, eps_m, cmpp):
+_DEFAULT_FEATURE_OPTIONS = """FeatureOptions:
+   DetectorType: SIFT
+   DetectorMode: STATIC
+   ExtractorType: SIFT
+"""
+
+
+def _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=None):
     import cv2
     cam = case["scene"].cam
     # poses such that g12 = g_IC^-1 g2^-1 g1 g_IC (singlecameratriangulator.cpp:140) is the scene's g12
@@ -85,10 +92,7 @@ Neighborhoods:
    cmPerPixel: {cmpp}
    epsilon: {eps_m}
 
-FeatureOptions:
-   DetectorType: SIFT
-   DetectorMode: STATIC
-   ExtractorType: SIFT
+{feature_options or _DEFAULT_FEATURE_OPTIONS}
 
 CameraSettings:
    rodriguesIC: {fmt(rIC)}
@@ -141,8 +145,14 @@ def _read_result(path):
         circ = dict(normal=cn, pts=cpts)
     dr, dc = struct.unpack_from("ii", b, o); o += 8
     desc = np.frombuffer(b, np.float32, dr * dc, o).reshape(dr, dc); o += 4 * dr * dc
+    detected = []
+    while o < len(b) and len(detected) < 2:          # "-" mode: the features compareWithNNDR produced itself
+        n, cols = struct.unpack_from("ii", b, o); o += 8
+        k = np.frombuffer(b, np.float32, 5 * n, o).reshape(n, 5); o += 20 * n
+        d = np.frombuffer(b, np.float32, n * cols, o).reshape(n, cols); o += 4 * n * cols
+        detected.append((k, d))
     assert o == len(b)
-    return dict(patch_descriptors=desc, circular=circ, helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
+    return dict(detected=detected, patch_descriptors=desc, circular=circ, helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
                 patches=patches, last_nb=last_nb, gravity=gravity, S=S)
 
 
@@ -286,3 +296,57 @@ def test_c1_main_cpp_pipeline_at_the_reference_defaults(tmp_path):
     assert ddiff.max() <= 1
     print(f"C1: {len(oq)} matches, {int(ok.sum())} normals; whole C++ process {t_gpu:.2f} s (incl. CUDA start-up), "
           f"CPU oracle normal search alone {t_cpu_normals:.1f} s on {os.cpu_count()} threads")
+
+
+@pytest.mark.gpu
+def test_main_cpp_from_the_frames_alone_with_fast_and_sift(tmp_path):
+    """main.cpp:91-187 with DetectorType FAST + ExtractorType SIFT and NO injected features: compareWithNNDR
+    detects (K10), describes (K11) and matches on the GPU, the rest of the pipeline runs on what it found.
+    Keypoints, descriptors and matches against the oracles; the refined normals of the genuine matches against
+    the scene's ground truth."""
+    from oracle import fast_np as fo
+    from oracle import sift_kp_np as sk
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    cam = case["scene"].cam
+    tmp = str(tmp_path)
+    opts = """FeatureOptions:
+   DetectorType: FAST
+   DetectorMode: STATIC
+   FastDetector:
+      Threshold: 25
+      NonMaxSuppression: 1
+   ExtractorType: SIFT
+"""
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+    assert len(res["detected"]) == 2
+    descs = []
+    for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
+        oxy, orr = fo.detect_fast(img, 25, True)
+        assert len(oxy) > 100
+        np.testing.assert_array_equal(k[:, :2], oxy)
+        np.testing.assert_array_equal(k[:, 4], orr)
+        assert (k[:, 2] == 7).all() and (k[:, 3] == -1).all()
+        sel = np.arange(0, len(k), max(1, len(k) // 150))
+        od = sk.describe_keypoints_sift(img, k[sel, :4])
+        dd = np.abs(d[sel] - od)
+        assert d.shape == (len(k), 128) and dd.max() <= 1 and (dd == 0).mean() > 0.97
+        descs.append(d)
+    o_idx, o_dist = orc.knn2_f32(descs[0], descs[1])
+    oq, ot, od = orc.nndr_filter(o_idx, o_dist, 0.55)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    np.testing.assert_array_equal(res["matches"]["d"], od)
+    k1, k2 = res["detected"][0][0], res["detected"][1][0]
+    o_all, o_mask, o_xyz = orc.triangulate(cam.K, cam.dist, res["g12"], cam.z_min, cam.z_max, k1[:, :2], k2[:, :2], oq, ot)
+    np.testing.assert_array_equal(res["mask"].astype(bool), o_mask.astype(bool))
+    np.testing.assert_allclose(res["pts"], o_xyz, rtol=1e-9, atol=1e-12)
+    print(f"FAST+SIFT from the frames: {len(k1)} / {len(k2)} keypoints, {len(oq)} NNDR matches, {int(o_mask.sum())} in depth range, "
+          f"{len(res['normals'])} refined normals")
+    assert len(res["normals"]) == int((res["status"] == 0).sum())

@@ -202,6 +202,34 @@ def describe_sweep(ctx, stream):
                           "hbm_peak_gbs": PEAKS.get("hbm_gbs"), "tflops_fp32_algorithmic": n * S * S * 98.0 / (ms * 1e-3) / 1e12}), flush=True)
 
 
+def frontend_sweep(ctx, stream):
+    """K10 + K11 alone: FAST detection, the SIFT base image and the SIFT descriptors at the detected keypoints of
+    one frame (the front end of compareWithNNDR with DetectorType FAST + ExtractorType SIFT), 720p and 4K."""
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    for W, H in ((1280, 720), (3840, 2160)):
+        small = rng.integers(0, 256, (H // 6 + 1, W // 6 + 1)).astype(np.float32)
+        img = np.kron(small, np.ones((6, 6), np.float32))[:H, :W]
+        img = np.clip(img * 0.7 + rng.integers(0, 77, img.shape), 0, 255).astype(np.uint8)
+        d_img = torch.from_numpy(img).to(dev)
+        cap = 1 << 20
+        xy = torch.zeros((cap, 2), dtype=torch.float32, device=dev)
+        resp = torch.zeros(cap, dtype=torch.float32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        base = torch.zeros((H, W), dtype=torch.float32, device=dev)
+        det = lambda: ctx.detect_fast_dev(d_img.data_ptr(), W, H, W, 30, True, cap, xy.data_ptr(), resp.data_ptr(), cnt.data_ptr())
+        ms_det = timed(stream, det, 5)
+        n = min(int(cnt.item()), cap)
+        k4 = torch.cat([xy[:n], torch.full((n, 1), 7.0, device=dev), torch.full((n, 1), -1.0, device=dev)], 1).contiguous()
+        desc = torch.empty((n, 128), dtype=torch.float32, device=dev)
+        ms_base = timed(stream, lambda: ctx.sift_base_image_dev(d_img.data_ptr(), W, H, W, base.data_ptr()), 5)
+        ms_all = timed(stream, lambda: ctx.describe_keypoints_sift_dev(d_img.data_ptr(), W, H, W, k4.data_ptr(), n, desc.data_ptr()), 5)
+        print(json.dumps({"case": "frontend_fast_sift", "W": W, "H": H, "keypoints": n, "ms_detect": ms_det, "ms_base_image": ms_base,
+                          "ms_describe_incl_base": ms_all, "detect_hbm_gbs_compulsory": W * H / (ms_det * 1e-3) / 1e9,
+                          "base_hbm_gbs_compulsory": 5.0 * W * H / (ms_base * 1e-3) / 1e9, "hbm_peak_gbs": PEAKS.get("hbm_gbs"),
+                          "descriptors_per_s": n / ((ms_all - ms_base) * 1e-3) if ms_all > ms_base else None}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = api.Context(0)
@@ -214,6 +242,8 @@ if __name__ == "__main__":
         match_real_sweep(ctx, stream)
     if which in ("all", "describe"):
         describe_sweep(ctx, stream)
+    if which in ("all", "frontend"):
+        frontend_sweep(ctx, stream)
     if which in ("c3",):
         c3_pipeline(ctx, stream)
     ctx.close()
