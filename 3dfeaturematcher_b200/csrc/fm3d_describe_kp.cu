@@ -11,18 +11,18 @@
 // Two kernels:
 //   sift_base_kernel      u8 frame -> float base image, separable 13-tap blur fused in shared memory
 //                         (HBM-bound: 1 B read + 4 B written per pixel).
-//   describe_kp_kernel    one CTA per keypoint, one WARP PER SPATIAL CELL of the 4 x 4 descriptor grid.
-//                         A warp walks the bounding box of its cell's trilinear support, evaluates
-//                         calcSIFTDescriptor's per-pixel arithmetic and keeps the part that falls into
-//                         its own cell in eight orientation accumulators per lane (registers), so
-//                         there are no atomics and the summation order is fixed: results are
-//                         bit-reproducible.  A pixel is evaluated by the (up to four) warps whose cells
-//                         it touches; the base image is L2-resident.
+//   describe_kp_kernel    four warps per keypoint, one WARP PER ROW OF CELLS of the 4 x 4 descriptor grid.
+//                         A warp walks the bounding box of its row's trilinear support (rbin within one
+//                         cell of the row), evaluates calcSIFTDescriptor's per-pixel arithmetic and adds the
+//                         shares of its own row to per-lane PRIVATE accumulators in shared memory
+//                         (4 cells x 8 orientations per lane, bank = lane: no conflicts, no atomics, fixed
+//                         summation order => bit-reproducible).  A pixel is evaluated by the two warps
+//                         whose rows it touches; the base image is L1/L2-resident.
 // OpenCV addresses its (d+2)(d+2)(n+2) histogram flat.  A keypoint with angle -1 has ori = 361, so a
 // gradient orientation below 1 degree keeps o0 = -1 after calcSIFTDescriptor's single wrap and its v0
 // share lands in slot n+1 of the previous COLUMN cell, which the circular fold adds to that cell's
-// orientation bin 1 (see fm3d_describe.cu).  A warp therefore also walks the support of its right-hand
-// neighbour when ori >= 360 and collects those shares ("spill").
+// orientation bin 1 (see fm3d_describe.cu).  A warp owns a whole row of cells, so that share stays inside the
+// warp ("spill" below); the share of column 0 falls into the padding and is dropped, as in OpenCV.
 #include "fm3d_internal.cuh"
 
 #include <math.h>
@@ -32,7 +32,8 @@ namespace {
 constexpr int KP_KHALF = 6;          // ksize 13 = cvRound(8 sigma + 1) | 1 for sigma 1.5199
 constexpr int BT_W = 64, BT_H = 32;  // base-image tile per CTA
 constexpr int BT_NT = 256;
-constexpr int KP_NT = 512;           // 16 warps = 16 cells
+constexpr int KP_PER_CTA = 2;        // keypoints per CTA
+constexpr int KP_NT = KP_PER_CTA * 128;   // four warps per keypoint: one per ROW of descriptor cells
 
 struct BlurArgs {
     float kern[KP_KHALF + 1];        // kern[i] = coefficient at distance i from the centre tap
@@ -110,139 +111,144 @@ struct KpGeom {
 };
 
 __global__ void __launch_bounds__(KP_NT)
-describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __restrict__ kps, float* __restrict__ desc) {
-    __shared__ KpGeom G;
-    __shared__ float hist[128];
-    __shared__ float scale_thr[2];
-    const int tid = threadIdx.x, lane = tid & 31, cell = tid >> 5;
-    const size_t f = blockIdx.x;
-    if (tid == 0) {
-        const float x = kps[4 * f], y = kps[4 * f + 1], size = kps[4 * f + 2], angle = kps[4 * f + 3];
+describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __restrict__ kps, int n, float* __restrict__ desc) {
+    __shared__ KpGeom G[KP_PER_CTA];
+    __shared__ float acc[KP_NT / 32][32][32];        // [warp][cell column * 8 + orientation bin][lane]: bank = lane
+    __shared__ float hist[KP_PER_CTA][128];
+    __shared__ float scale_thr[KP_PER_CTA][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = warp >> 2, ci = warp & 3;       // keypoint of this CTA, row of descriptor cells
+    const size_t f = (size_t)blockIdx.x * KP_PER_CTA + slot;
+    if ((tid & 127) == 0) {
         KpGeom g;
-        // DescriptorExtractor::compute drops keypoints outside the image or of size <= FLT_EPSILON before SIFT
-        // sees them (KeyPointsFilter::runByImageBorder / runByKeypointSize); such rows are written as zeros
-        g.valid = (x >= 0.f && y >= 0.f && x < (float)w && y < (float)h && size > 1.1920929e-07f && isfinite(size) && isfinite(angle)) ? 1 : 0;
-        g.ptx = __float2int_rn(x); g.pty = __float2int_rn(y);                  // cvRound
-        float ori = __fsub_rn(360.0f, angle);
-        if (fabsf(ori - 360.0f) < 1.1920929e-07f) ori = 0.0f;
-        const float scl = __fmul_rn(size, 0.5f);
-        const float rad = __fmul_rn(ori, (float)(M_PI / 180));
-        // cosf / sinf of the C library are correctly rounded for almost every argument: fp64 evaluation rounded once
-        const float cos_t = (float)cos((double)rad), sin_t = (float)sin((double)rad);
-        const float hist_width = __fmul_rn(3.0f, scl);
-        int radius = __float2int_rn(__fmul_rn(__fmul_rn(__fmul_rn(hist_width, 1.4142135623730951f), 5.0f), 0.5f));
-        const int diag = (int)sqrt((double)w * w + (double)h * h);
-        g.radius = radius < diag ? radius : diag;
-        g.cos_t = __fdiv_rn(cos_t, hist_width);
-        g.sin_t = __fdiv_rn(sin_t, hist_width);
-        g.ori = ori;
-        G = g;
+        g.valid = 0;
+        if (f < (size_t)n) {
+            const float x = kps[4 * f], y = kps[4 * f + 1], size = kps[4 * f + 2], angle = kps[4 * f + 3];
+            // DescriptorExtractor::compute drops keypoints outside the image or of size <= FLT_EPSILON before SIFT
+            // sees them (KeyPointsFilter::runByImageBorder / runByKeypointSize); such rows are written as zeros
+            g.valid = (x >= 0.f && y >= 0.f && x < (float)w && y < (float)h && size > 1.1920929e-07f && isfinite(size) && isfinite(angle)) ? 1 : 0;
+            g.ptx = __float2int_rn(x); g.pty = __float2int_rn(y);                  // cvRound
+            float ori = __fsub_rn(360.0f, angle);
+            if (fabsf(ori - 360.0f) < 1.1920929e-07f) ori = 0.0f;
+            const float scl = __fmul_rn(size, 0.5f);
+            const float rad = __fmul_rn(ori, (float)(M_PI / 180));
+            // cosf / sinf of the C library are correctly rounded for almost every argument: fp64 evaluation rounded once
+            const float cos_t = (float)cos((double)rad), sin_t = (float)sin((double)rad);
+            const float hist_width = __fmul_rn(3.0f, scl);
+            const int radius = __float2int_rn(__fmul_rn(__fmul_rn(__fmul_rn(hist_width, 1.4142135623730951f), 5.0f), 0.5f));
+            const int diag = (int)sqrt((double)w * w + (double)h * h);
+            g.radius = radius < diag ? radius : diag;
+            g.cos_t = __fdiv_rn(cos_t, hist_width);
+            g.sin_t = __fdiv_rn(sin_t, hist_width);
+            g.ori = ori;
+        }
+        G[slot] = g;
     }
+    float* my = &acc[warp][0][lane];                 // bin b of this lane: my[b * 32]
+#pragma unroll
+    for (int b = 0; b < 32; b++) my[b * 32] = 0.0f;
     __syncthreads();
-    const KpGeom g = G;
-    if (!g.valid) {
-        if (tid < 128) desc[f * 128 + tid] = 0.0f;
-        return;
-    }
-    const int ci = cell >> 2, cj = cell & 3;
-    const bool spill_possible = g.ori >= 360.0f;
-    // bounding box (pixel offsets i = row, j = column) of the support of cell (ci, cj):
-    // rbin in [ci-1, ci+1), cbin in [cj-1, cj+1) (+ [cj, cj+2) for the spill shares); *_rot = *bin - 1.5
-    int i_lo, i_hi, j_lo, j_hi;
-    {
-        const float inv = 1.0f / (g.cos_t * g.cos_t + g.sin_t * g.sin_t);
-        const float rr[2] = {(float)ci - 2.5f, (float)ci - 0.5f};
-        const float cc[2] = {(float)cj - 2.5f, (float)cj + (spill_possible ? 0.5f : -0.5f)};
-        float fi_lo = 1e30f, fi_hi = -1e30f, fj_lo = 1e30f, fj_hi = -1e30f;
+    const KpGeom g = G[slot];
+    if (g.valid) {
+        // bounding box (pixel offsets i = row, j = column) of the band rbin in [ci-1, ci+1), cbin in (-1, 4);
+        // *_rot = *bin - 1.5
+        int i_lo, i_hi, j_lo, j_hi;
+        {
+            const float inv = 1.0f / (g.cos_t * g.cos_t + g.sin_t * g.sin_t);
+            const float rr[2] = {(float)ci - 2.5f, (float)ci - 0.5f};
+            const float cc[2] = {-2.5f, 2.5f};
+            float fi_lo = 1e30f, fi_hi = -1e30f, fj_lo = 1e30f, fj_hi = -1e30f;
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+            for (int a = 0; a < 2; a++)
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
-                const float fj = (cc[b] * g.cos_t + rr[a] * g.sin_t) * inv;
-                const float fi = (-cc[b] * g.sin_t + rr[a] * g.cos_t) * inv;
-                fi_lo = fminf(fi_lo, fi); fi_hi = fmaxf(fi_hi, fi);
-                fj_lo = fminf(fj_lo, fj); fj_hi = fmaxf(fj_hi, fj);
-            }
-        const float R = (float)g.radius;
-        i_lo = (int)floorf(fmaxf(fi_lo, -R - 1.0f)) - 1; i_hi = (int)ceilf(fminf(fi_hi, R + 1.0f)) + 1;
-        j_lo = (int)floorf(fmaxf(fj_lo, -R - 1.0f)) - 1; j_hi = (int)ceilf(fminf(fj_hi, R + 1.0f)) + 1;
-        i_lo = max(i_lo, max(-g.radius, 1 - g.pty)); i_hi = min(i_hi, min(g.radius, h - 2 - g.pty));
-        j_lo = max(j_lo, max(-g.radius, 1 - g.ptx)); j_hi = min(j_hi, min(g.radius, w - 2 - g.ptx));
-    }
-    float acc[8];
+                for (int b = 0; b < 2; b++) {
+                    const float fj = (cc[b] * g.cos_t + rr[a] * g.sin_t) * inv;
+                    const float fi = (-cc[b] * g.sin_t + rr[a] * g.cos_t) * inv;
+                    fi_lo = fminf(fi_lo, fi); fi_hi = fmaxf(fi_hi, fi);
+                    fj_lo = fminf(fj_lo, fj); fj_hi = fmaxf(fj_hi, fj);
+                }
+            const float R = (float)g.radius;
+            i_lo = (int)floorf(fmaxf(fi_lo, -R - 1.0f)) - 1; i_hi = (int)ceilf(fminf(fi_hi, R + 1.0f)) + 1;
+            j_lo = (int)floorf(fmaxf(fj_lo, -R - 1.0f)) - 1; j_hi = (int)ceilf(fminf(fj_hi, R + 1.0f)) + 1;
+            i_lo = max(i_lo, max(-g.radius, 1 - g.pty)); i_hi = min(i_hi, min(g.radius, h - 2 - g.pty));
+            j_lo = max(j_lo, max(-g.radius, 1 - g.ptx)); j_hi = min(j_hi, min(g.radius, w - 2 - g.ptx));
+        }
+        const int bw = j_hi - j_lo + 1, bh = i_hi - i_lo + 1;
+        if (bw > 0 && bh > 0) {
+            const long long total = (long long)bw * bh;
+            int q = lane / bw, rem = lane - q * bw;
+            const int step_q = 32 / bw, step_r = 32 - step_q * bw;
+            for (long long k = lane; k < total; k += 32, q += step_q, rem += step_r) {
+                if (rem >= bw) { rem -= bw; q++; }
+                const int i = i_lo + q, j = j_lo + rem;
+                const float fi = (float)i, fj = (float)j;
+                const float c_rot = __fsub_rn(__fmul_rn(fj, g.cos_t), __fmul_rn(fi, g.sin_t));
+                const float r_rot = __fadd_rn(__fmul_rn(fj, g.sin_t), __fmul_rn(fi, g.cos_t));
+                const float rbin = __fsub_rn(__fadd_rn(r_rot, 2.0f), 0.5f);
+                const float cbin = __fsub_rn(__fadd_rn(c_rot, 2.0f), 0.5f);
+                if (!(rbin > -1.0f && rbin < 4.0f && cbin > -1.0f && cbin < 4.0f)) continue;
+                const float r0f = floorf(rbin), c0f = floorf(cbin);
+                const int dr = ci - (int)r0f;            // this row of cells is row r0 (dr = 0) or r0 + 1 (dr = 1) of the split
+                if (dr != 0 && dr != 1) continue;
+                const int c0 = (int)c0f;                 // -1 .. 3
+                const float* p = base + (size_t)(g.pty + i) * w + (g.ptx + j);
+                const float dx = __fsub_rn(__ldg(p + 1), __ldg(p - 1)), dy = __fsub_rn(__ldg(p - w), __ldg(p + w));
+                const float wgt = __expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), -0.125f));
+                const float mag = __fmul_rn(kp_sqrt_approx(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), wgt);
+                float obin = __fmul_rn(__fsub_rn(kp_fast_atan2_deg(dy, dx), g.ori), 8 / 360.0f);
+                const float of = floorf(obin);
+                obin = __fsub_rn(obin, of);
+                int o0 = (int)of;
+                o0 = o0 < 0 ? o0 + 8 : o0;
+                o0 = o0 >= 8 ? o0 - 8 : o0;
+                const float rb = __fsub_rn(rbin, r0f), cb = __fsub_rn(cbin, c0f);
+                const float v_r1 = __fmul_rn(mag, rb);
+                const float v_r = dr ? v_r1 : __fsub_rn(mag, v_r1);
+                const float v_rc1 = __fmul_rn(v_r, cb), v_rc0 = __fsub_rn(v_r, v_rc1);
+                if (o0 >= 0) {
+                    // slot o0 and slot o0 + 1 (slot n folds onto bin 0) of the cells in columns c0 and c0 + 1
+                    const int oa = (o0 & 7) * 32, ob = ((o0 + 1) & 7) * 32;
+                    if (c0 >= 0) {
+                        const float v1 = __fmul_rn(v_rc0, obin), v0 = __fsub_rn(v_rc0, v1);
+                        float* cell = my + c0 * 256;
+                        cell[oa] = __fadd_rn(cell[oa], v0);
+                        cell[ob] = __fadd_rn(cell[ob], v1);
+                    }
+                    if (c0 < 3) {
+                        const float v1 = __fmul_rn(v_rc1, obin), v0 = __fsub_rn(v_rc1, v1);
+                        float* cell = my + (c0 + 1) * 256;
+                        cell[oa] = __fadd_rn(cell[oa], v0);
+                        cell[ob] = __fadd_rn(cell[ob], v1);
+                    }
+                } else {
+                    // o0 == -1 (ori = 361, orientation below 1 degree): the v1 share is slot 0 of the proper cell, the v0
+                    // share is flat slot n+1 of the cell one column to the LEFT, which the circular fold adds to its bin 1
 #pragma unroll
-    for (int b = 0; b < 8; b++) acc[b] = 0.0f;
-    const int bw = j_hi - j_lo + 1, bh = i_hi - i_lo + 1;
-    if (bw > 0 && bh > 0) {
-        const float inv_bw = 1.0f / (float)bw;
-        const int total = bw * bh;
-        for (int k = lane; k < total; k += 32) {
-            int q = __float2int_rd(((float)k + 0.5f) * inv_bw);
-            int rem = k - q * bw;
-            if (rem < 0) { q--; rem += bw; } else if (rem >= bw) { q++; rem -= bw; }   // float quotient off by one for huge boxes
-            const int i = i_lo + q, j = j_lo + rem;
-            const float fi = (float)i, fj = (float)j;
-            const float c_rot = __fsub_rn(__fmul_rn(fj, g.cos_t), __fmul_rn(fi, g.sin_t));
-            const float r_rot = __fadd_rn(__fmul_rn(fj, g.sin_t), __fmul_rn(fi, g.cos_t));
-            const float rbin = __fsub_rn(__fadd_rn(r_rot, 2.0f), 0.5f);
-            const float cbin = __fsub_rn(__fadd_rn(c_rot, 2.0f), 0.5f);
-            if (!(rbin > -1.0f && rbin < 4.0f && cbin > -1.0f && cbin < 4.0f)) continue;
-            const float r0f = floorf(rbin), c0f = floorf(cbin);
-            const int dr = ci - (int)r0f;                    // this cell is row r0 (dr = 0) or r0 + 1 (dr = 1) of the split
-            if (dr != 0 && dr != 1) continue;
-            const int dcn = cj - (int)c0f;                   // normal share: column c0 + dcn
-            const int dcs = dcn + 1;                         // spill share of the right-hand neighbour cell
-            const bool normal_ok = dcn == 0 || dcn == 1;
-            const bool spill_ok = spill_possible && (dcs == 0 || dcs == 1);
-            if (!normal_ok && !spill_ok) continue;
-            const float* p = base + (size_t)(g.pty + i) * w + (g.ptx + j);
-            const float dx = __fsub_rn(__ldg(p + 1), __ldg(p - 1)), dy = __fsub_rn(__ldg(p - w), __ldg(p + w));
-            const float wgt = __expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), -0.125f));
-            const float mag = __fmul_rn(kp_sqrt_approx(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), wgt);
-            float obin = __fmul_rn(__fsub_rn(kp_fast_atan2_deg(dy, dx), g.ori), 8 / 360.0f);
-            const float of = floorf(obin);
-            obin = __fsub_rn(obin, of);
-            int o0 = (int)of;
-            o0 = o0 < 0 ? o0 + 8 : o0;
-            o0 = o0 >= 8 ? o0 - 8 : o0;
-            const bool spill = o0 < 0;                       // only o0 == -1 is reachable (ori <= 361)
-            const float rb = __fsub_rn(rbin, r0f), cb = __fsub_rn(cbin, c0f);
-            const float v_r1 = __fmul_rn(mag, rb);
-            const float v_r = dr ? v_r1 : __fsub_rn(mag, v_r1);
-            const float v_rc1 = __fmul_rn(v_r, cb), v_rc0 = __fsub_rn(v_r, v_rc1);
-            float add_a = 0.0f, add_b = 0.0f;                // shares for bins oa, ob
-            int oa = -1, ob = -1;
-            if (normal_ok) {
-                const float v_rc = dcn ? v_rc1 : v_rc0;
-                const float v1 = __fmul_rn(v_rc, obin), v0 = __fsub_rn(v_rc, v1);
-                if (!spill) { oa = o0 & 7; add_a = v0; ob = (o0 + 1) & 7; add_b = v1; }      // slot n folds onto bin 0
-                else { ob = 0; add_b = v1; }                                                  // slot o0 + 1 = 0 of the proper cell
-            }
-            if (spill_ok && spill) {
-                const float v_rc = dcs ? v_rc1 : v_rc0;
-                const float v1 = __fmul_rn(v_rc, obin);
-                oa = 1; add_a = __fsub_rn(v_rc, v1);         // v0 -> slot n+1 of this (left-hand) cell -> bin 1
-            }
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                acc[b] = __fadd_rn(acc[b], b == oa ? add_a : 0.0f);
-                acc[b] = __fadd_rn(acc[b], b == ob ? add_b : 0.0f);
+                    for (int dc = 0; dc < 2; dc++) {
+                        const int col = c0 + dc;
+                        const float v_rc = dc ? v_rc1 : v_rc0;
+                        const float v1 = __fmul_rn(v_rc, obin), v0 = __fsub_rn(v_rc, v1);
+                        if (col >= 0 && col <= 3) my[col * 256] = __fadd_rn(my[col * 256], v1);
+                        if (col >= 1 && col <= 4) my[(col - 1) * 256 + 32] = __fadd_rn(my[(col - 1) * 256 + 32], v0);
+                    }
+                }
             }
         }
     }
+    __syncwarp();
+    {   // lane L sums bin L over the 32 private copies, skewed so that every lane reads another bank; fixed order
+        const float* row = &acc[warp][lane][0];
+        float s = 0.0f;
 #pragma unroll
-    for (int b = 0; b < 8; b++) {
-        float s = acc[b];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) hist[cell * 8 + b] = s;
+        for (int k = 0; k < 32; k++) s = __fadd_rn(s, row[(k + lane) & 31]);
+        hist[slot][ci * 32 + lane] = s;              // (ci * 4 + column) * 8 + orientation
     }
     __syncthreads();
     // normalisation (calcSIFTDescriptor's tail): clip at 0.2 |h|, scale to 512, saturate to u8
-    if (tid < 32) {
+    if (ci == 0) {
         float v[4], s = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { v[k] = hist[tid * 4 + k]; s = fmaf(v[k], v[k], s); }
+        for (int k = 0; k < 4; k++) { v[k] = hist[slot][lane * 4 + k]; s = fmaf(v[k], v[k], s); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float thr = __fmul_rn(__fsqrt_rn(s), 0.2f);
@@ -251,14 +257,16 @@ describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __
         for (int k = 0; k < 4; k++) { const float c = fminf(v[k], thr); s = fmaf(c, c, s); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) {
-            scale_thr[0] = __fdiv_rn(512.0f, fmaxf(__fsqrt_rn(s), 1.1920929e-07f));
-            scale_thr[1] = thr;
+        if (lane == 0) {
+            scale_thr[slot][0] = __fdiv_rn(512.0f, fmaxf(__fsqrt_rn(s), 1.1920929e-07f));
+            scale_thr[slot][1] = thr;
         }
     }
     __syncthreads();
-    if (tid < 128)
-        desc[f * 128 + tid] = fminf(fmaxf(rintf(__fmul_rn(fminf(hist[tid], scale_thr[1]), scale_thr[0])), 0.0f), 255.0f);
+    if (f < (size_t)n) {
+        const int e = tid & 127;
+        desc[f * 128 + e] = g.valid ? fminf(fmaxf(rintf(__fmul_rn(fminf(hist[slot][e], scale_thr[slot][1]), scale_thr[slot][0])), 0.0f), 255.0f) : 0.0f;
+    }
 }
 
 void blur_args(BlurArgs& A) {
@@ -297,7 +305,7 @@ int fm3d_describe_keypoints_sift_dev(fm3d_ctx* ctx, const uint8_t* img, int w, i
     float* base = nullptr;
     if (int rc = fm3d_scratch(ctx, 8, sizeof(float) * (size_t)w * h, (void**)&base)) return rc;
     if (int rc = fm3d_sift_base_image_dev(ctx, img, w, h, stride, base)) return rc;
-    describe_kp_kernel<<<n, KP_NT, 0, ctx->stream>>>(base, w, h, kps, descriptors);
+    describe_kp_kernel<<<(n + KP_PER_CTA - 1) / KP_PER_CTA, KP_NT, 0, ctx->stream>>>(base, w, h, kps, n, descriptors);
     FM3D_LAUNCH_CHECK(ctx);
     return FM3D_OK;
 }
