@@ -39,6 +39,7 @@ SYMBOLS = [
     "fm3d_describe_patches_sift", "fm3d_describe_patches_sift_dev",
     "fm3d_detect_fast", "fm3d_detect_fast_dev",
     "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_sift_base_image_dev",
+    "fm3d_describe_keypoints_brisk", "fm3d_describe_keypoints_brisk_dev",
 ]
 
 
@@ -401,7 +402,27 @@ class Context:
         self._ck(self.lib.fm3d_describe_keypoints_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], _ptr(kps, _fp), n, _ptr(desc, _fp)))
         return desc
 
+    def describe_keypoints_brisk(self, img, kps, compute_orientation=True):
+        """descriptor_extractor_->compute for ExtractorType BRISK: H x W u8 image, n x 4 f32 (x, y, size, angle) ->
+        (n x 64 u8 rows, n bool kept, n f32 angles); rows of removed keypoints are zero."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        kps = _arr(np.asarray(kps, np.float32).reshape(-1, 4), np.float32)
+        n = kps.shape[0]
+        desc = np.zeros((n, 64), np.uint8)
+        kept = np.zeros(n, np.uint8)
+        ang = np.zeros(n, np.float32)
+        self._ck(self.lib.fm3d_describe_keypoints_brisk(self._h, _ptr(img, _bp), w, h, img.strides[0], _ptr(kps, _fp), n,
+                                                        int(bool(compute_orientation)), _ptr(desc, _bp), _ptr(kept, _bp), _ptr(ang, _fp)))
+        return desc, kept.astype(bool), ang
+
     # ------------------------------------------------------------------ device-pointer entry points
+    def describe_keypoints_brisk_dev(self, img, w, h, stride, kps, n, compute_orientation, descriptors, kept, angles):
+        self._ck(self.lib.fm3d_describe_keypoints_brisk_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(kps), n, int(bool(compute_orientation)),
+                                                            C.c_void_p(descriptors), C.c_void_p(kept), C.c_void_p(angles)))
+
     def describe_keypoints_sift_dev(self, img, w, h, stride, kps, n, descriptors):
         self._ck(self.lib.fm3d_describe_keypoints_sift_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(kps), n, C.c_void_p(descriptors)))
 

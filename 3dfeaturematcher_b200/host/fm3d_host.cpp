@@ -171,15 +171,15 @@ void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv:
     if (have_features_) { ka = kpts_a_; kb = kpts_b_; da = desc_a_; db = desc_b_; return; }
     if (!da.empty() && !db.empty()) return;  // pre-filled by the caller
     // descriptorsmatcher.cpp:110-115: detect on both frames, then compute on both frames.  DetectorType FAST
-    // (STATIC) with ExtractorType SIFT runs on the GPU (K10 + K11); the other detectors / extractors of the
-    // reference (SURF, STAR, MSER, ORB, BRISK, FREAK of OpenCV 2.4) are upstream code this library does not carry.
-    if (detector_type_ == "FAST" && detector_mode_ == "STATIC" && extractor_type_ == "SIFT") {
+    // (STATIC) with ExtractorType SIFT or BRISK runs on the GPU (K10 + K11 / K12); the other detectors / extractors of
+    // the reference (SURF, STAR, MSER, ORB, FREAK of OpenCV 2.4) are upstream code this library does not carry.
+    if (detector_type_ == "FAST" && detector_mode_ == "STATIC" && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK")) {
         detectAndDescribe(image_a_, ka, da);
         detectAndDescribe(image_b_, kb, db);
         return;
     }
     throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC) + "
-                             "ExtractorType SIFT only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
+                             "ExtractorType SIFT or BRISK only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
                              "); inject the features of other detectors with setFeatures");
 }
 
@@ -206,6 +206,29 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
         k4[4 * i] = kp.pt.x; k4[4 * i + 1] = kp.pt.y; k4[4 * i + 2] = kp.size; k4[4 * i + 3] = kp.angle;
     }
     if (n == 0) { desc = cv::Mat(); return; }
+    if (extractor_type_ == "BRISK") {
+        // cv::BRISK::compute erases the keypoints whose pattern would leave the image and returns one CV_8U row of 64
+        // bytes per survivor, with KeyPoint::angle set.  FM3D_BRISK_ORIENTATION=0 reproduces OpenCV 2.4, which skips the
+        // orientation step for provided keypoints (FAST's angle -1 then means "unrotated").
+        const char* e = getenv("FM3D_BRISK_ORIENTATION");
+        const int orient = e ? atoi(e) : 1;
+        std::vector<uint8_t> rows((size_t)64 * n), kept(n);
+        std::vector<float> ang(n);
+        check(ctx, fm3d_describe_keypoints_brisk(ctx, px, w, h, stride, k4.data(), n, orient, rows.data(), kept.data(), ang.data()), "compute (BRISK)");
+        int m = 0;
+        for (int i = 0; i < n; i++) m += kept[i] ? 1 : 0;
+        std::vector<cv::KeyPoint> survivors;
+        survivors.reserve(m);
+        desc = m > 0 ? cv::Mat::zeros(cv::Size(64, m), CV_8U) : cv::Mat();
+        for (int i = 0, j = 0; i < n; i++) {
+            if (!kept[i]) continue;
+            kpts[i].angle = ang[i];
+            survivors.push_back(kpts[i]);
+            memcpy(desc.ptr<uint8_t>(j++), rows.data() + (size_t)64 * i, 64);
+        }
+        kpts.swap(survivors);
+        return;
+    }
     desc = cv::Mat::zeros(cv::Size(128, n), CV_32F);
     check(ctx, fm3d_describe_keypoints_sift(ctx, px, w, h, stride, k4.data(), n, desc.ptr<float>()), "compute (SIFT)");
 }

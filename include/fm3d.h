@@ -402,6 +402,23 @@ int fm3d_describe_keypoints_sift_dev(fm3d_ctx* ctx, const uint8_t* img, int w, i
 /* The base image alone (createInitialImage): base is w x h f32, rows w floats apart, device memory. */
 int fm3d_sift_base_image_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* base);
 
+/* The same call for ExtractorType BRISK (:337-342: cv::BRISK(BriskDetector.Threshold, BriskDetector.Octaves) -- both
+ * knobs only steer BRISK's own detector, which the reference does not run): the binary descriptors that the Hamming
+ * matcher consumes (:64-67).
+ *   kps                  n x 4 f32 as above
+ *   compute_orientation  != 0: orientation from the long pairs, as cv::BRISK::compute of OpenCV >= 3 does for provided
+ *                        keypoints (pinned against cv2 4.13); 0: the keypoint's own angle is used and angle -1 means
+ *                        "unrotated" (OpenCV 2.4's behaviour for provided keypoints)
+ *   descriptors          n x 64 u8; kept n u8; angles n f32 (KeyPoint::angle after the call, degrees in [0, 360))
+ * cv::BRISK REMOVES keypoints whose pattern would leave the image (and their rows): here kept[k] = 0 and row k is
+ * zero; the adapters erase those keypoints as the reference's call would.  w * h * 255 must fit an int32 (the integral
+ * image is CV_32S as in cv::integral). */
+int fm3d_describe_keypoints_brisk(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
+                                  int n, int compute_orientation, uint8_t* descriptors, uint8_t* kept, float* angles);
+int fm3d_describe_keypoints_brisk_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                                      const float* kps, int n, int compute_orientation, uint8_t* descriptors,
+                                      uint8_t* kept, float* angles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <stdexcept>
 #include <vector>
 
 #include "DescriptorsMatcher/descriptorsmatcher.h"
@@ -136,7 +137,12 @@ int main(int argc, char** argv) {
     }
     // MOSAIC descriptors of the rectified patches (main.cpp:182-183)
     cv::Mat patchDescriptors;
-    dm.extractDescriptorsFromPatches(patchesVector, patchDescriptors);
+    try {
+        dm.extractDescriptorsFromPatches(patchesVector, patchDescriptors);
+    } catch (const std::exception& e) {      // runs for ExtractorType SIFT only (the adapter says so)
+        std::cerr << e.what() << std::endl;
+        patchDescriptors = cv::Mat();
+    }
     int dr = patchDescriptors.rows, dc = patchDescriptors.cols;
     fwrite(&dr, 4, 1, o); fwrite(&dc, 4, 1, o);
     if (dr > 0) fwrite(patchDescriptors.data, 4, (size_t)dr * dc, o);
@@ -145,14 +151,14 @@ int main(int argc, char** argv) {
         const std::vector<cv::KeyPoint>* ks[2] = {&kpts1, &kpts2};
         const cv::Mat* ds[2] = {&desc1, &desc2};
         for (int a = 0; a < 2; a++) {
-            int n = (int)ks[a]->size(), cols = ds[a]->cols;
-            fwrite(&n, 4, 1, o); fwrite(&cols, 4, 1, o);
+            int n = (int)ks[a]->size(), cols = ds[a]->cols, es = n > 0 ? (int)ds[a]->elemSize() : 4;
+            fwrite(&n, 4, 1, o); fwrite(&cols, 4, 1, o); fwrite(&es, 4, 1, o);
             for (int i = 0; i < n; i++) {
                 const cv::KeyPoint& k = (*ks[a])[i];
                 const float v[5] = {k.pt.x, k.pt.y, k.size, k.angle, k.response};
                 fwrite(v, 4, 5, o);
             }
-            if (n > 0) fwrite(ds[a]->data, 4, (size_t)n * cols, o);
+            if (n > 0) fwrite(ds[a]->data, (size_t)es, (size_t)n * cols, o);
         }
     }
     fclose(o);

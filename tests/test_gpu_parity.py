@@ -984,3 +984,105 @@ def test_detect_describe_match_chain_full_size(ctx):
     k2[:, 0] -= dx
     k2[:, 1] -= dy
     assert inner.sum() > 1000 and np.array_equal(ctx.describe_keypoints_sift(img2, k2), d[inner])
+
+
+# ------------------------------------------------------------------ K12: BRISK descriptors at frame keypoints
+def test_describe_keypoints_brisk_golden_vectors(ctx):
+    """descriptor_extractor_->compute (descriptorsmatcher.cpp:114-115, ExtractorType BRISK): the committed outputs of
+    cv2.BRISK_create(25, 0).compute.  Integer work: removed keypoints and all 512 bits identical."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "brisk_keypoints.npz"))
+    imgs = np.load(os.path.join(gold, "fast_keypoints.npz"))
+    seen = 0
+    for key in g.files:
+        if not key.startswith("k_"):
+            continue
+        name, tag = key.split("_")[1:3]
+        d, kept, ang = ctx.describe_keypoints_brisk(imgs[f"img_{name}"], g[key])
+        assert d.dtype == np.uint8 and d.shape == (len(g[key]), 64)
+        np.testing.assert_array_equal(np.nonzero(kept)[0], g[f"kept_{name}_{tag}"])
+        np.testing.assert_array_equal(d[kept], g[f"d_{name}_{tag}"])
+        assert not d[~kept].any()
+        np.testing.assert_allclose(ang[kept], g[f"a_{name}_{tag}"], rtol=0, atol=1e-4 if tag == "fast" else 0.02)
+        seen += int(kept.sum())
+    assert seen > 800
+
+
+def test_describe_keypoints_brisk_against_oracle_and_edges(ctx):
+    from oracle import brisk_np as bn
+    rng = np.random.default_rng(654)
+    for h, w in ((120, 171), (90, 300)):
+        img = rng.integers(0, 256, (h, w)).astype(np.float32)
+        img = ((img + np.roll(img, 1, 0) + np.roll(img, 1, 1) + np.roll(np.roll(img, 1, 0), 1, 1)) / 4).astype(np.uint8)
+        n = 150
+        k = np.stack([rng.uniform(0, w - 1, n), rng.uniform(0, h - 1, n), rng.uniform(2, 26, n), rng.uniform(0, 360, n)], 1).astype(np.float32)
+        k[:40, 2] = 7
+        k[:40, 3] = -1                                       # FAST keypoints
+        k[:20, :2] = np.floor(k[:20, :2])
+        k[40:44, :2] = [[0, 0], [w - 1, h - 1], [13, 13], [w - 14, h - 14]]      # the border rule: 13 <= x < w - 13 at scale 0
+        k[40:44, 2] = 7
+        k[44, 2] = 0                                         # size 0
+        k[45, 2] = 200                                       # scale index saturates at 63: the pattern cannot fit
+        for orient in (True, False):
+            d, kept, ang = ctx.describe_keypoints_brisk(img, k, compute_orientation=orient)
+            okept, oang, od = bn.describe_keypoints_brisk(img, k, compute_orientation=orient)
+            np.testing.assert_array_equal(np.nonzero(kept)[0], okept)
+            assert kept[42] and kept[43] and not kept[40] and not kept[41] and not kept[44] and not kept[45]
+            np.testing.assert_allclose(ang[kept], oang, rtol=0, atol=1e-4)
+            np.testing.assert_array_equal(d[kept], od)
+            assert not d[~kept].any()
+            # deterministic, independent of the batch, independent of the row pitch
+            again = ctx.describe_keypoints_brisk(img, k, compute_orientation=orient)
+            assert np.array_equal(again[0], d) and np.array_equal(again[2], ang)
+            one = ctx.describe_keypoints_brisk(img, k[60:61], compute_orientation=orient)
+            assert np.array_equal(one[0][0], d[60]) and one[1][0] == kept[60]
+            big = np.zeros((h, w + 19), np.uint8)
+            big[:, 7:7 + w] = img
+            assert np.array_equal(ctx.describe_keypoints_brisk(big[:, 7:7 + w], k, compute_orientation=orient)[0], d)
+        # without the orientation step a keypoint with angle -1 is sampled unrotated: the row of rotation index 0
+        d0 = ctx.describe_keypoints_brisk(img, k[:40], compute_orientation=False)
+        z = k[:40].copy()
+        z[:, 3] = 0.0
+        assert np.array_equal(d0[0], ctx.describe_keypoints_brisk(img, z, compute_orientation=False)[0])
+    d, kept, ang = ctx.describe_keypoints_brisk(np.zeros((40, 40), np.uint8), np.zeros((0, 4), np.float32))
+    assert d.shape == (0, 64) and kept.shape == (0,)
+
+
+def test_detect_brisk_hamming_chain_full_size(ctx):
+    """DetectorType FAST + ExtractorType BRISK on a 1280 x 720 frame (BASELINE C2 shape): detection, binary description
+    and the Hamming matcher on the GPU; oracle parity on a sample, and size-independent properties -- a frame matched
+    against itself returns every keypoint at distance 0, an integer translation of the frame leaves the rows of the
+    translated keypoints unchanged up to the float rounding of pattern point + keypoint position (a changed sub-pixel
+    weight can move a smoothed value by one unit: isolated bits)."""
+    from oracle import brisk_np as bn
+    rng = np.random.default_rng(12)
+    small = rng.integers(0, 256, (720 // 6 + 4, 1280 // 6 + 4)).astype(np.float32)
+    big = np.kron(small, np.ones((6, 6), np.float32))
+    big = np.clip(big * 0.7 + rng.integers(0, 77, big.shape), 0, 255).astype(np.uint8)
+    img = np.ascontiguousarray(big[:720, :1280])
+    xy, r, n = ctx.detect_fast(img, 30, True)
+    k = np.concatenate([xy, np.full((n, 1), 7, np.float32), np.full((n, 1), -1, np.float32)], 1)
+    d, kept, ang = ctx.describe_keypoints_brisk(img, k)
+    assert kept.sum() > 2000 and (ang[kept] >= 0).all() and (ang[kept] < 360).all()
+    pick = rng.choice(np.nonzero(kept)[0], 150, replace=False)
+    okept, oang, od = bn.describe_keypoints_brisk(img, k[pick])
+    assert len(okept) == len(pick)
+    np.testing.assert_array_equal(d[pick], od)
+    np.testing.assert_allclose(ang[pick], oang, rtol=0, atol=1e-4)
+    dk = d[kept]
+    idx, dist = ctx.match_knn2_hamming(dk, dk)
+    assert (dist[:, 0] == 0).all() and ((idx[:, 0] == np.arange(len(dk))) | (dist[:, 1] == 0)).all()
+    dx, dy = 11, 4
+    img2 = np.ascontiguousarray(big[dy:dy + 720, dx:dx + 1280])
+    inner = kept & (xy[:, 0] > 20 + dx) & (xy[:, 0] < 1280 - 20) & (xy[:, 1] > 20 + dy) & (xy[:, 1] < 720 - 20)
+    k2 = k[inner].copy()
+    k2[:, 0] -= dx
+    k2[:, 1] -= dy
+    d2, kept2, ang2 = ctx.describe_keypoints_brisk(img2, k2)
+    assert inner.sum() > 1500 and kept2.all()
+    ham = np.unpackbits(d2 ^ d[inner], axis=1).sum(1)
+    print("translated frame: rows identical", (ham == 0).mean(), "mean Hamming", ham.mean(), "max", ham.max())
+    assert (ham == 0).mean() > 0.9 and ham.mean() < 1.0
+    idx2, dist2 = ctx.match_knn2_hamming(d2, d[inner])
+    assert (idx2[:, 0] == np.arange(len(d2))).mean() > 0.99          # every translated keypoint finds itself

@@ -147,9 +147,9 @@ def _read_result(path):
     desc = np.frombuffer(b, np.float32, dr * dc, o).reshape(dr, dc); o += 4 * dr * dc
     detected = []
     while o < len(b) and len(detected) < 2:          # "-" mode: the features compareWithNNDR produced itself
-        n, cols = struct.unpack_from("ii", b, o); o += 8
+        n, cols, es = struct.unpack_from("iii", b, o); o += 12
         k = np.frombuffer(b, np.float32, 5 * n, o).reshape(n, 5); o += 20 * n
-        d = np.frombuffer(b, np.float32, n * cols, o).reshape(n, cols); o += 4 * n * cols
+        d = np.frombuffer(b, np.float32 if es == 4 else np.uint8, n * cols, o).reshape(n, cols); o += es * n * cols
         detected.append((k, d))
     assert o == len(b)
     return dict(detected=detected, patch_descriptors=desc, circular=circ, helpers=dict(m=hm, rc=(rc1, rc2, rc3), cost=hcost), matches=m, mask=mask, g12=g12, pts=pts, status=status, kept=kept, normals=normals, frames=frames,
@@ -350,3 +350,60 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_sift(tmp_path):
     print(f"FAST+SIFT from the frames: {len(k1)} / {len(k2)} keypoints, {len(oq)} NNDR matches, {int(o_mask.sum())} in depth range, "
           f"{len(res['normals'])} refined normals")
     assert len(res["normals"]) == int((res["status"] == 0).sum())
+
+
+@pytest.mark.gpu
+def test_main_cpp_from_the_frames_alone_with_fast_and_brisk(tmp_path):
+    """The same with ExtractorType BRISK (descriptorsmatcher.cpp:337-342; build/settings.yml carries its knobs): binary
+    rows from K12, the Hamming matcher (:64-67), keypoints near the border erased as cv::BRISK::compute erases them."""
+    from oracle import fast_np as fo
+    from oracle import brisk_np as bn
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    cam = case["scene"].cam
+    tmp = str(tmp_path)
+    opts = """FeatureOptions:
+   DetectorType: FAST
+   DetectorMode: STATIC
+   FastDetector:
+      Threshold: 25
+      NonMaxSuppression: 1
+   BriskDetector:
+      Threshold: 25
+      Octaves: 0
+   ExtractorType: BRISK
+"""
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+    with open(os.path.join(tmp, "settings.yml")) as f:
+        yml = f.read().replace("epsilon: 0.55", "epsilon: 0.8")      # binary descriptors: a looser ratio, as usual for Hamming
+    with open(os.path.join(tmp, "settings.yml"), "w") as f:
+        f.write(yml)
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+    descs = []
+    for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
+        oxy, orr = fo.detect_fast(img, 25, True)
+        k4 = np.concatenate([oxy, np.full((len(oxy), 1), 7, np.float32), np.full((len(oxy), 1), -1, np.float32)], 1)
+        sel = np.arange(0, len(k4), max(1, len(k4) // 400))
+        okept, oang, od = bn.describe_keypoints_brisk(img, k4[sel])
+        # the survivors of the full list, restricted to the sample
+        inside = (oxy[:, 0] >= 13) & (oxy[:, 0] < img.shape[1] - 13) & (oxy[:, 1] >= 13) & (oxy[:, 1] < img.shape[0] - 13)
+        np.testing.assert_array_equal(k[:, :2], oxy[inside])
+        assert d.dtype == np.uint8 and d.shape == (int(inside.sum()), 64)
+        pos = np.cumsum(inside) - 1                       # row of keypoint i among the survivors
+        rows = pos[sel[okept]]
+        np.testing.assert_array_equal(d[rows], od)
+        np.testing.assert_allclose(k[rows, 3], oang, rtol=0, atol=1e-4)
+        descs.append(d)
+    o_idx, o_dist = orc.knn2_hamming(descs[0], descs[1])
+    oq, ot, od_ = orc.nndr_filter(o_idx, o_dist, 0.8)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    np.testing.assert_array_equal(res["matches"]["d"], od_)
+    print(f"FAST+BRISK from the frames: {len(descs[0])} / {len(descs[1])} described keypoints, {len(oq)} NNDR matches, "
+          f"{int(res['mask'].sum())} in depth range, {len(res['normals'])} refined normals")
+    assert len(oq) > 50

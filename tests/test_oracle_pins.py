@@ -188,3 +188,24 @@ def test_sift_keypoint_restatement_against_live_cv2():
         got = sk.describe_keypoints_sift(img, arr)
         diff = np.abs(got - want)
         assert diff.max() <= 1 and (diff == 0).mean() >= 0.999
+
+
+def test_brisk_restatement_against_live_cv2():
+    """oracle/brisk_np.py against cv2.BRISK_create().compute on a fresh image: FAST keypoints (what DetectorType FAST +
+    ExtractorType BRISK of descriptorsmatcher.cpp:215-222, :337-342 hands to compute) and sub-pixel keypoints of many
+    sizes.  Survivors and bits identical."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import brisk_np as bn
+    rng = np.random.default_rng(78)
+    img = cv2.normalize(cv2.GaussianBlur(rng.integers(0, 256, (150, 210)).astype(np.uint8), (0, 0), 1.6), None, 0, 255, cv2.NORM_MINMAX)
+    kps = cv2.FastFeatureDetector_create(threshold=12, nonmaxSuppression=True).detect(img, None)[:250]
+    arr = np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32).reshape(-1, 4)
+    extra = np.stack([rng.uniform(0, 209, 120), rng.uniform(0, 149, 120), rng.uniform(2, 30, 120), rng.uniform(0, 360, 120)], 1).astype(np.float32)
+    arr = np.concatenate([arr, extra])
+    cvk = [cv2.KeyPoint(float(a[0]), float(a[1]), float(a[2]), float(a[3])) for a in arr]
+    cvk2, want = cv2.BRISK_create(25, 0).compute(img, cvk)
+    kept, ang, got = bn.describe_keypoints_brisk(img, arr)
+    assert len(kept) == len(cvk2) > 150
+    np.testing.assert_array_equal(arr[kept, :2], np.array([k.pt for k in cvk2], np.float32))
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_allclose(ang, np.array([k.angle for k in cvk2], np.float32), rtol=0, atol=0.02)

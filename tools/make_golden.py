@@ -188,9 +188,47 @@ def sift_keypoints():
     np.savez_compressed(os.path.join(OUT, "sift_keypoints.npz"), **out)
 
 
+def brisk_keypoints():
+    """K12 fixtures: cv2.BRISK_create(25, 0).compute (descriptor_extractor_->compute of descriptorsmatcher.cpp:114-115
+    with ExtractorType BRISK, :337-342, knobs of build/settings.yml) on the FAST keypoints (threshold 20, non-maximum
+    suppression, at most 400 per image) of the images of fast_keypoints.npz, and on keypoints with sub-pixel
+    positions and sizes 3 ... 36 (scale indices 0 ... 30).  cv::BRISK removes keypoints near the border: `kept`
+    holds the indices of the survivors, `d` / `a` their rows and angles."""
+    import cv2
+    brisk = cv2.BRISK_create(25, 0)
+    out = {}
+    for name, img in fast_test_images().items():
+        if name.startswith("tiny"):
+            continue
+        kps = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True).detect(img, None)[:400]
+        sets = {"fast": np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32).reshape(-1, 4)}
+        if name in ("blur", "frame"):
+            g = sift_general_keypoints(img.shape[1], img.shape[0], 160, 7300 + len(name))
+            g[:, 2] = np.random.default_rng(7400).uniform(3, 36, len(g)).astype(np.float32)
+            sets["general"] = g
+        for tag, arr in sets.items():
+            cvk = [cv2.KeyPoint(float(a[0]), float(a[1]), float(a[2]), float(a[3])) for a in arr]
+            cvk2, d = brisk.compute(img, cvk)
+            d = np.zeros((0, 64), np.uint8) if d is None else d
+            # survivors keep their order: recover their indices from the positions
+            kept, j = [], 0
+            for i, a in enumerate(arr):
+                if j < len(cvk2) and cvk2[j].pt == (float(a[0]), float(a[1])) and cvk2[j].size == float(a[2]):
+                    kept.append(i)
+                    j += 1
+            assert j == len(cvk2) == len(d)
+            out[f"k_{name}_{tag}"] = arr
+            out[f"kept_{name}_{tag}"] = np.array(kept, np.int32)
+            out[f"d_{name}_{tag}"] = d
+            out[f"a_{name}_{tag}"] = np.array([k.angle for k in cvk2], np.float32)
+    np.savez_compressed(os.path.join(OUT, "brisk_keypoints.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "--sift-kp-only" in sys.argv:
+    if "--brisk-only" in sys.argv:
+        brisk_keypoints()
+    elif "--sift-kp-only" in sys.argv:
         sift_keypoints()
     elif "--fast-only" in sys.argv:
         fast_keypoints()
@@ -201,5 +239,6 @@ if __name__ == "__main__":
         sift_patches()
         fast_keypoints()
         sift_keypoints()
+        brisk_keypoints()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
