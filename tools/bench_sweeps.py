@@ -224,6 +224,13 @@ def frontend_sweep(ctx, stream):
         desc = torch.empty((n, 128), dtype=torch.float32, device=dev)
         ms_base = timed(stream, lambda: ctx.sift_base_image_dev(d_img.data_ptr(), W, H, W, base.data_ptr()), 5)
         ms_all = timed(stream, lambda: ctx.describe_keypoints_sift_dev(d_img.data_ptr(), W, H, W, k4.data_ptr(), n, desc.data_ptr()), 5)
+        bdesc = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+        bkept = torch.empty(n, dtype=torch.uint8, device=dev)
+        bang = torch.empty(n, dtype=torch.float32, device=dev)
+        ms_brisk = timed(stream, lambda: ctx.describe_keypoints_brisk_dev(d_img.data_ptr(), W, H, W, k4.data_ptr(), n, True, bdesc.data_ptr(),
+                                                                          bkept.data_ptr(), bang.data_ptr()), 5)
+        print(json.dumps({"case": "frontend_fast_brisk", "W": W, "H": H, "keypoints": n, "kept": int(bkept.sum().item()),
+                          "ms_describe_incl_integral": ms_brisk, "descriptors_per_s": n / (ms_brisk * 1e-3)}), flush=True)
         print(json.dumps({"case": "frontend_fast_sift", "W": W, "H": H, "keypoints": n, "ms_detect": ms_det, "ms_base_image": ms_base,
                           "ms_describe_incl_base": ms_all, "detect_hbm_gbs_compulsory": W * H / (ms_det * 1e-3) / 1e9,
                           "base_hbm_gbs_compulsory": 5.0 * W * H / (ms_base * 1e-3) / 1e9, "hbm_peak_gbs": PEAKS.get("hbm_gbs"),
