@@ -158,7 +158,7 @@ brisk_kp_kernel(const BriskTables T, const BriskPairs* __restrict__ P, const uin
     int scale;
     {
         const float log2f_ = 0.693147180559945f;
-        const float lb_scalerange = (float)(log(30.0) / (double)log2f_);
+        const float lb_scalerange = __fdiv_rn(3.4011974334716797f, log2f_);       // logf(30.f) / log2, float division
         const float basic06 = __fmul_rn(12.0f, 0.6f);
         // std::log(float) is logf; evaluated in fp64 and rounded once (logf of the C library is correctly rounded)
         const float lg = (float)log((double)__fdiv_rn(size, basic06));
@@ -231,7 +231,8 @@ const HostBrisk& host_brisk() {
     std::call_once(once, [] {
         const float rList[5] = {(float)(0.85 * 0.0), (float)(0.85 * 2.9), (float)(0.85 * 4.9), (float)(0.85 * 7.4), (float)(0.85 * 10.8)};
         const int nList[5] = {1, 10, 14, 15, 20};
-        const float lb_scale = (float)(log(30.0) / log(2.0));
+        // scalerange_ is a float member of cv::BRISK, so std::log(scalerange_) is logf (pinned through the angles cv2 returns)
+        const float lb_scale = (float)((double)logf(30.0f) / log(2.0));
         const float lb_scale_step = lb_scale / (float)BK_SCALES;
         const float sigma_scale = 1.3f;
         std::vector<float> x0(BK_POINTS), y0(BK_POINTS);

@@ -20,7 +20,7 @@ reference (unpinned, 2.4.x era); the published algorithm restated here is cv::BR
 
 Pinned by: cv2.BRISK_create().compute itself (tests/test_oracle_pins.py, where cv2 is importable) and the committed
 golden vectors tests/golden/brisk_keypoints.npz written from cv2 by tools/make_golden.py; integer work, agreement
-is exact (bits and surviving keypoints).  Only tests/ may import this module.
+is exact (surviving keypoints, bits and angles).  Only tests/ may import this module.
 """
 from __future__ import annotations
 
@@ -34,7 +34,10 @@ SCALERANGE, BASIC_SIZE = 30.0, 12.0
 R_LIST = [f32(0.85 * 0.0), f32(0.85 * 2.9), f32(0.85 * 4.9), f32(0.85 * 7.4), f32(0.85 * 10.8)]
 N_LIST = [1, 10, 14, 15, 20]
 D_MAX, D_MIN = f32(5.85), f32(8.2)
-LB_SCALE = f32(math.log(SCALERANGE) / math.log(2.0))
+# scalerange_ is a float member, so std::log(scalerange_) is logf: lb_scale = (float)(logf(30.f) / log(2.0)) =
+# 4.906890869140625 (the double logarithm would round to 4.90689039...; pinned through the angles cv2 returns)
+LOGF_30 = f32(math.log(SCALERANGE))
+LB_SCALE = f32(float(LOGF_30) / math.log(2.0))
 LB_SCALE_STEP = f32(LB_SCALE / f32(SCALES))
 
 
@@ -157,7 +160,7 @@ def _wrap32(v: int) -> int:
 
 
 def keypoint_scale(size: float) -> int:
-    lb_scalerange = f32(math.log(SCALERANGE) / float(f32(0.693147180559945)))
+    lb_scalerange = f32(LOGF_30 / f32(0.693147180559945))
     basic06 = f32(f32(BASIC_SIZE) * f32(0.6))
     v = float(f32(f32(f32(SCALES) / lb_scalerange) * f32(f32(math.log(float(f32(f32(size) / basic06)))) / f32(0.693147180559945)))) + 0.5
     return min(max(int(v), 0), SCALES - 1)

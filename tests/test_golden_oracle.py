@@ -155,9 +155,8 @@ def test_sift_keypoint_restatement_against_cv2_golden_vectors():
 
 def test_brisk_restatement_against_cv2_golden_vectors():
     """oracle/brisk_np.py (K12: descriptor_extractor_->compute, ExtractorType BRISK) against the committed outputs of
-    cv2.BRISK_create(25, 0).compute: surviving keypoints and all 512 bits identical; angles identical for FAST
-    keypoints (scale index 0), within 0.02 degrees at larger scales (the sums that feed atan2 differ in the last digits
-    there; the rotation index, 360/1024 degrees wide, and with it every bit, agrees on all pinned keypoints)."""
+    cv2.BRISK_create(25, 0).compute: surviving keypoints, all 512 bits and the angles identical (scale indices 0 ... 30,
+    sub-pixel positions)."""
     from oracle import brisk_np as bn
     g = np.load(os.path.join(GOLD, "brisk_keypoints.npz"))
     imgs = np.load(os.path.join(GOLD, "fast_keypoints.npz"))
@@ -171,10 +170,7 @@ def test_brisk_restatement_against_cv2_golden_vectors():
         kept, ang, d = bn.describe_keypoints_brisk(imgs[f"img_{name}"], g[key])
         np.testing.assert_array_equal(kept, g[f"kept_{name}_{tag}"])
         np.testing.assert_array_equal(d, g[f"d_{name}_{tag}"])
-        if tag == "fast":
-            np.testing.assert_array_equal(ang, g[f"a_{name}_{tag}"])
-        else:
-            np.testing.assert_allclose(ang, g[f"a_{name}_{tag}"], rtol=0, atol=0.02)
+        np.testing.assert_array_equal(ang, g[f"a_{name}_{tag}"])
         assert len(kept) < len(g[key])               # the border rule removed some
         seen += len(kept)
     assert seen > 800

@@ -1004,7 +1004,7 @@ def test_describe_keypoints_brisk_golden_vectors(ctx):
         np.testing.assert_array_equal(np.nonzero(kept)[0], g[f"kept_{name}_{tag}"])
         np.testing.assert_array_equal(d[kept], g[f"d_{name}_{tag}"])
         assert not d[~kept].any()
-        np.testing.assert_allclose(ang[kept], g[f"a_{name}_{tag}"], rtol=0, atol=1e-4 if tag == "fast" else 0.02)
+        np.testing.assert_allclose(ang[kept], g[f"a_{name}_{tag}"], rtol=0, atol=1e-4)
         seen += int(kept.sum())
     assert seen > 800
 
