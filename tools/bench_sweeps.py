@@ -224,6 +224,20 @@ def frontend_sweep(ctx, stream):
         desc = torch.empty((n, 128), dtype=torch.float32, device=dev)
         ms_base = timed(stream, lambda: ctx.sift_base_image_dev(d_img.data_ptr(), W, H, W, base.data_ptr()), 5)
         ms_all = timed(stream, lambda: ctx.describe_keypoints_sift_dev(d_img.data_ptr(), W, H, W, k4.data_ptr(), n, desc.data_ptr()), 5)
+        # the same three steps with OpenCV on this box's host cores, where cv2 is importable (a reported baseline)
+        try:
+            import cv2
+            t0 = time.perf_counter()
+            cvk = cv2.FastFeatureDetector_create(threshold=30, nonmaxSuppression=True).detect(img, None)
+            t1 = time.perf_counter()
+            cv2.SIFT_create().compute(img, cvk)
+            t2 = time.perf_counter()
+            cv2.BRISK_create(25, 0).compute(img, cvk)
+            t3 = time.perf_counter()
+            print(json.dumps({"case": "frontend_opencv_cpu", "W": W, "H": H, "keypoints": len(cvk), "threads": cv2.getNumThreads(),
+                              "ms_detect_fast": (t1 - t0) * 1e3, "ms_sift_compute": (t2 - t1) * 1e3, "ms_brisk_compute": (t3 - t2) * 1e3}), flush=True)
+        except ImportError:
+            pass
         bdesc = torch.empty((n, 64), dtype=torch.uint8, device=dev)
         bkept = torch.empty(n, dtype=torch.uint8, device=dev)
         bang = torch.empty(n, dtype=torch.float32, device=dev)
