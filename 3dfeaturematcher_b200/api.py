@@ -40,6 +40,7 @@ SYMBOLS = [
     "fm3d_detect_fast", "fm3d_detect_fast_dev",
     "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_sift_base_image_dev",
     "fm3d_describe_keypoints_brisk", "fm3d_describe_keypoints_brisk_dev",
+    "fm3d_describe_keypoints_orb", "fm3d_describe_keypoints_orb_dev",
 ]
 
 
@@ -418,7 +419,24 @@ class Context:
                                                         int(bool(compute_orientation)), _ptr(desc, _bp), _ptr(kept, _bp), _ptr(ang, _fp)))
         return desc, kept.astype(bool), ang
 
+    def describe_keypoints_orb(self, img, kps):
+        """descriptor_extractor_->compute for ExtractorType ORB: H x W u8 image, n x 4 f32 (x, y, size, angle), octave 0 ->
+        (n x 32 u8 rows, n bool kept); rows of removed keypoints are zero."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        kps = _arr(np.asarray(kps, np.float32).reshape(-1, 4), np.float32)
+        n = kps.shape[0]
+        desc = np.zeros((n, 32), np.uint8)
+        kept = np.zeros(n, np.uint8)
+        self._ck(self.lib.fm3d_describe_keypoints_orb(self._h, _ptr(img, _bp), w, h, img.strides[0], _ptr(kps, _fp), n, _ptr(desc, _bp), _ptr(kept, _bp)))
+        return desc, kept.astype(bool)
+
     # ------------------------------------------------------------------ device-pointer entry points
+    def describe_keypoints_orb_dev(self, img, w, h, stride, kps, n, descriptors, kept):
+        self._ck(self.lib.fm3d_describe_keypoints_orb_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(kps), n, C.c_void_p(descriptors), C.c_void_p(kept)))
+
     def describe_keypoints_brisk_dev(self, img, w, h, stride, kps, n, compute_orientation, descriptors, kept, angles):
         self._ck(self.lib.fm3d_describe_keypoints_brisk_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(kps), n, int(bool(compute_orientation)),
                                                             C.c_void_p(descriptors), C.c_void_p(kept), C.c_void_p(angles)))

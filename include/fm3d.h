@@ -419,6 +419,17 @@ int fm3d_describe_keypoints_brisk_dev(fm3d_ctx* ctx, const uint8_t* img, int w, 
                                       const float* kps, int n, int compute_orientation, uint8_t* descriptors,
                                       uint8_t* kept, float* angles);
 
+/* The same call for ExtractorType ORB (:325-330: cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels); the knobs
+ * steer ORB's own detector and pyramid, which keypoints of octave 0 do not touch): 256-bit rBRIEF rows.
+ *   kps            n x 4 f32 as above (octave 0; angle in degrees -- FAST's -1 is a rotation by -1 degree, as in cv::ORB)
+ *   descriptors    n x 32 u8; kept n u8
+ * cv::ORB REMOVES keypoints whose rounded position is within 31 pixels of the border (and their rows): here
+ * kept[k] = 0 and row k is zero; the adapters erase those keypoints as the reference's call would. */
+int fm3d_describe_keypoints_orb(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps, int n,
+                                uint8_t* descriptors, uint8_t* kept);
+int fm3d_describe_keypoints_orb_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
+                                    int n, uint8_t* descriptors, uint8_t* kept);
+
 #ifdef __cplusplus
 }
 #endif

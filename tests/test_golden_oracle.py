@@ -174,3 +174,24 @@ def test_brisk_restatement_against_cv2_golden_vectors():
         assert len(kept) < len(g[key])               # the border rule removed some
         seen += len(kept)
     assert seen > 800
+
+
+def test_orb_restatement_against_cv2_golden_vectors():
+    """oracle/orb_np.py (K13: descriptor_extractor_->compute, ExtractorType ORB) against the committed outputs of
+    cv2.ORB_create().compute: survivors of the border rule and all 256 bits, for FAST keypoints and for sub-pixel
+    keypoints with arbitrary angles.  The pattern itself is recovered from cv2 (tools/recover_orb_pattern.py)."""
+    from oracle import orb_np as on
+    g = np.load(os.path.join(GOLD, "orb_keypoints.npz"))
+    imgs = np.load(os.path.join(GOLD, "fast_keypoints.npz"))
+    assert on.PATTERN.shape == (256, 4) and np.abs(on.PATTERN).max() <= 15
+    assert on.PATTERN[0].tolist() == [-3, 8, 5, 9]        # (y, x) of both points of bit 0: Rublee et al.'s first pair (8,-3)-(9,5)
+    seen = 0
+    for key in g.files:
+        if not key.startswith("k_"):
+            continue
+        name, tag = key.split("_")[1:3]
+        kept, d = on.describe_keypoints_orb(imgs[f"img_{name}"], g[key])
+        np.testing.assert_array_equal(kept, g[f"kept_{name}_{tag}"])
+        np.testing.assert_array_equal(d, g[f"d_{name}_{tag}"])
+        seen += len(kept)
+    assert seen > 600

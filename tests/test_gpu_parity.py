@@ -1086,3 +1086,79 @@ def test_detect_brisk_hamming_chain_full_size(ctx):
     assert (ham == 0).mean() > 0.9 and ham.mean() < 1.0
     idx2, dist2 = ctx.match_knn2_hamming(d2, d[inner])
     assert (idx2[:, 0] == np.arange(len(d2))).mean() > 0.99          # every translated keypoint finds itself
+
+
+# ------------------------------------------------------------------ K13: ORB descriptors at frame keypoints
+def test_describe_keypoints_orb_golden_vectors_and_oracle(ctx):
+    """descriptor_extractor_->compute (descriptorsmatcher.cpp:114-115, ExtractorType ORB): the committed outputs of
+    cv2.ORB_create().compute -- survivors identical, rows identical up to a blurred value at a float rounding boundary
+    -- and the numpy restatement, which evaluates the blur in the kernel's order: identical."""
+    import os
+    from oracle import orb_np as on
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "orb_keypoints.npz"))
+    imgs = np.load(os.path.join(gold, "fast_keypoints.npz"))
+    seen = 0
+    for key in g.files:
+        if not key.startswith("k_"):
+            continue
+        name, tag = key.split("_")[1:3]
+        d, kept = ctx.describe_keypoints_orb(imgs[f"img_{name}"], g[key])
+        assert d.dtype == np.uint8 and d.shape == (len(g[key]), 32)
+        np.testing.assert_array_equal(np.nonzero(kept)[0], g[f"kept_{name}_{tag}"])
+        assert not d[~kept].any()
+        okept, od = on.describe_keypoints_orb(imgs[f"img_{name}"], g[key])
+        np.testing.assert_array_equal(d[kept], od)
+        if kept.any():
+            ham = np.unpackbits(d[kept] ^ g[f"d_{name}_{tag}"], axis=1).sum(1)
+            assert (ham == 0).mean() >= 0.995 and ham.max() <= 2
+        seen += int(kept.sum())
+    assert seen > 600
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (150, 333)).astype(np.uint8)
+    k = np.stack([rng.uniform(-5, 340, 300), rng.uniform(-5, 155, 300), rng.uniform(1, 40, 300), rng.uniform(-1, 360, 300)], 1).astype(np.float32)
+    k[:5, 0] = [30.4, 30.5, 30.6, 301.49, 301.51]       # the border rule sees the ROUNDED position: 31 <= round(x) < w - 31
+    k[:5, 1] = 70
+    k[5, 0] = np.nan
+    d, kept = ctx.describe_keypoints_orb(img, k)
+    okept, od = on.describe_keypoints_orb(img, k)
+    np.testing.assert_array_equal(np.nonzero(kept)[0], okept)
+    np.testing.assert_array_equal(d[kept], od)
+    assert kept[:6].tolist() == [False, False, True, True, False, False]
+    big = np.zeros((150, 350), np.uint8)
+    big[:, 9:9 + 333] = img
+    assert np.array_equal(ctx.describe_keypoints_orb(big[:, 9:9 + 333], k)[0], d)          # row pitch
+    assert np.array_equal(ctx.describe_keypoints_orb(img, k[100:101])[0][0], d[100])      # batch independence
+    assert ctx.describe_keypoints_orb(img, np.zeros((0, 4), np.float32))[0].shape == (0, 32)
+
+
+def test_detect_orb_hamming_chain_full_size(ctx):
+    """DetectorType FAST + ExtractorType ORB on a 1280 x 720 frame (BASELINE C2 shape; ORB-256 is the binary descriptor the
+    matching sweep is quoted on): detection, description and the Hamming matcher on the GPU; oracle parity on a sample;
+    a frame matched against itself returns every keypoint at distance 0; an integer translation of the frame leaves the rows
+    of the translated keypoints unchanged (integer positions: the same pixels are compared)."""
+    from oracle import orb_np as on
+    rng = np.random.default_rng(13)
+    small = rng.integers(0, 256, (720 // 6 + 4, 1280 // 6 + 4)).astype(np.float32)
+    big = np.kron(small, np.ones((6, 6), np.float32))
+    big = np.clip(big * 0.7 + rng.integers(0, 77, big.shape), 0, 255).astype(np.uint8)
+    img = np.ascontiguousarray(big[:720, :1280])
+    xy, r, n = ctx.detect_fast(img, 30, True)
+    k = np.concatenate([xy, np.full((n, 1), 7, np.float32), np.full((n, 1), -1, np.float32)], 1)
+    d, kept = ctx.describe_keypoints_orb(img, k)
+    assert kept.sum() > 2000
+    pick = rng.choice(np.nonzero(kept)[0], 300, replace=False)
+    okept, od = on.describe_keypoints_orb(img, k[pick])
+    assert len(okept) == len(pick)
+    np.testing.assert_array_equal(d[pick], od)
+    dk = d[kept]
+    idx, dist = ctx.match_knn2_hamming(dk, dk)
+    assert (dist[:, 0] == 0).all() and ((idx[:, 0] == np.arange(len(dk))) | (dist[:, 1] == 0)).all()
+    dx, dy = 11, 4
+    img2 = np.ascontiguousarray(big[dy:dy + 720, dx:dx + 1280])
+    inner = kept & (xy[:, 0] > 40 + dx) & (xy[:, 0] < 1280 - 40) & (xy[:, 1] > 40 + dy) & (xy[:, 1] < 720 - 40)
+    k2 = k[inner].copy()
+    k2[:, 0] -= dx
+    k2[:, 1] -= dy
+    d2, kept2 = ctx.describe_keypoints_orb(img2, k2)
+    assert inner.sum() > 1500 and kept2.all() and np.array_equal(d2, d[inner])

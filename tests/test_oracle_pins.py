@@ -209,3 +209,29 @@ def test_brisk_restatement_against_live_cv2():
     np.testing.assert_array_equal(arr[kept, :2], np.array([k.pt for k in cvk2], np.float32))
     np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(ang, np.array([k.angle for k in cvk2], np.float32))
+
+
+def test_orb_restatement_against_live_cv2():
+    """oracle/orb_np.py against cv2.ORB_create().compute on a fresh image (FAST keypoints + sub-pixel keypoints with
+    arbitrary angles), and the recovered pattern against a fresh recovery."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import orb_np as on
+    rng = np.random.default_rng(79)
+    img = cv2.normalize(cv2.GaussianBlur(rng.integers(0, 256, (170, 230)).astype(np.uint8), (0, 0), 1.2), None, 0, 255, cv2.NORM_MINMAX)
+    kps = cv2.FastFeatureDetector_create(threshold=12, nonmaxSuppression=True).detect(img, None)
+    kps = kps[::max(1, len(kps) // 300)]                 # row-major list: spread over the whole frame
+    arr = np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32).reshape(-1, 4)
+    extra = np.stack([rng.uniform(0, 229, 200), rng.uniform(0, 169, 200), rng.uniform(2, 30, 200), rng.uniform(0, 360, 200)], 1).astype(np.float32)
+    arr = np.concatenate([arr, extra])
+    cvk = [cv2.KeyPoint(float(a[0]), float(a[1]), float(a[2]), float(a[3]), 0.0, 0, i) for i, a in enumerate(arr)]
+    cvk2, want = cv2.ORB_create().compute(img, cvk)
+    kept, got = on.describe_keypoints_orb(img, arr)
+    np.testing.assert_array_equal(kept, np.array([k.class_id for k in cvk2]))
+    ham = np.unpackbits(got ^ want, axis=1).sum(1)
+    assert len(kept) > 150 and (ham == 0).mean() >= 0.995 and ham.max() <= 2      # a blurred value at a rounding boundary
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("recover_orb_pattern", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                      "tools", "recover_orb_pattern.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    np.testing.assert_array_equal(mod.recover(), on.PATTERN)

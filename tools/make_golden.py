@@ -224,9 +224,39 @@ def brisk_keypoints():
     np.savez_compressed(os.path.join(OUT, "brisk_keypoints.npz"), **out)
 
 
+def orb_keypoints():
+    """K13 fixtures: cv2.ORB_create().compute (descriptor_extractor_->compute of descriptorsmatcher.cpp:114-115 with
+    ExtractorType ORB, :325-330) on the FAST keypoints (threshold 20, non-maximum suppression, at most 500 per image) of
+    the images of fast_keypoints.npz and on octave-0 keypoints with sub-pixel positions and arbitrary angles.  cv::ORB
+    removes keypoints within 31 pixels of the border: `kept` holds the indices of the survivors (carried through
+    KeyPoint::class_id), `d` their rows."""
+    import cv2
+    orb = cv2.ORB_create()
+    out = {}
+    for name, img in fast_test_images().items():
+        if name.startswith("tiny"):
+            continue
+        kps = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True).detect(img, None)[:500]
+        sets = {"fast": np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32).reshape(-1, 4)}
+        if name in ("blur", "frame"):
+            sets["general"] = sift_general_keypoints(img.shape[1], img.shape[0], 400, 7500 + len(name))
+        for tag, arr in sets.items():
+            cvk = [cv2.KeyPoint(float(a[0]), float(a[1]), float(a[2]), float(a[3]), 0.0, 0, i) for i, a in enumerate(arr)]
+            cvk2, d = orb.compute(img, cvk)
+            d = np.zeros((0, 32), np.uint8) if d is None else d
+            kept = np.array([k.class_id for k in cvk2], np.int32)
+            assert (np.diff(kept) > 0).all() and len(kept) == len(d)          # survivors keep their order
+            out[f"k_{name}_{tag}"] = arr
+            out[f"kept_{name}_{tag}"] = kept
+            out[f"d_{name}_{tag}"] = d
+    np.savez_compressed(os.path.join(OUT, "orb_keypoints.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "--brisk-only" in sys.argv:
+    if "--orb-only" in sys.argv:
+        orb_keypoints()
+    elif "--brisk-only" in sys.argv:
         brisk_keypoints()
     elif "--sift-kp-only" in sys.argv:
         sift_keypoints()
@@ -240,5 +270,6 @@ if __name__ == "__main__":
         fast_keypoints()
         sift_keypoints()
         brisk_keypoints()
+        orb_keypoints()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
