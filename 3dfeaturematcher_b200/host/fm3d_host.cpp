@@ -171,15 +171,15 @@ void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv:
     if (have_features_) { ka = kpts_a_; kb = kpts_b_; da = desc_a_; db = desc_b_; return; }
     if (!da.empty() && !db.empty()) return;  // pre-filled by the caller
     // descriptorsmatcher.cpp:110-115: detect on both frames, then compute on both frames.  DetectorType FAST
-    // (STATIC) with ExtractorType SIFT or BRISK runs on the GPU (K10 + K11 / K12); the other detectors / extractors of
-    // the reference (SURF, STAR, MSER, ORB, FREAK of OpenCV 2.4) are upstream code this library does not carry.
-    if (detector_type_ == "FAST" && detector_mode_ == "STATIC" && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK")) {
+    // (STATIC) with ExtractorType SIFT, BRISK or ORB runs on the GPU (K10 + K11 / K12 / K13); the other detectors /
+    // extractors of the reference (SURF, STAR, MSER, FREAK, ORB's own detector) are upstream code this library does not carry.
+    if (detector_type_ == "FAST" && detector_mode_ == "STATIC" && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK" || extractor_type_ == "ORB")) {
         detectAndDescribe(image_a_, ka, da);
         detectAndDescribe(image_b_, kb, db);
         return;
     }
     throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC) + "
-                             "ExtractorType SIFT or BRISK only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
+                             "ExtractorType SIFT, BRISK or ORB only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
                              "); inject the features of other detectors with setFeatures");
 }
 
@@ -225,6 +225,24 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
             kpts[i].angle = ang[i];
             survivors.push_back(kpts[i]);
             memcpy(desc.ptr<uint8_t>(j++), rows.data() + (size_t)64 * i, 64);
+        }
+        kpts.swap(survivors);
+        return;
+    }
+    if (extractor_type_ == "ORB") {
+        // cv::ORB::compute erases the keypoints within 31 pixels of the border and returns one CV_8U row of 32 bytes per
+        // survivor; FAST's angle -1 is used as it is (a rotation by -1 degree).
+        std::vector<uint8_t> rows((size_t)32 * n), kept(n);
+        check(ctx, fm3d_describe_keypoints_orb(ctx, px, w, h, stride, k4.data(), n, rows.data(), kept.data()), "compute (ORB)");
+        int m = 0;
+        for (int i = 0; i < n; i++) m += kept[i] ? 1 : 0;
+        std::vector<cv::KeyPoint> survivors;
+        survivors.reserve(m);
+        desc = m > 0 ? cv::Mat::zeros(cv::Size(32, m), CV_8U) : cv::Mat();
+        for (int i = 0, j = 0; i < n; i++) {
+            if (!kept[i]) continue;
+            survivors.push_back(kpts[i]);
+            memcpy(desc.ptr<uint8_t>(j++), rows.data() + (size_t)32 * i, 32);
         }
         kpts.swap(survivors);
         return;

@@ -407,3 +407,54 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_brisk(tmp_path):
     print(f"FAST+BRISK from the frames: {len(descs[0])} / {len(descs[1])} described keypoints, {len(oq)} NNDR matches, "
           f"{int(res['mask'].sum())} in depth range, {len(res['normals'])} refined normals")
     assert len(oq) > 50
+
+
+@pytest.mark.gpu
+def test_main_cpp_from_the_frames_alone_with_fast_and_orb(tmp_path):
+    """The same with ExtractorType ORB (descriptorsmatcher.cpp:325-330): 32-byte rows from K13, the Hamming matcher,
+    keypoints within 31 pixels of the border erased as cv::ORB::compute erases them."""
+    from oracle import fast_np as fo
+    from oracle import orb_np as on
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    tmp = str(tmp_path)
+    opts = """FeatureOptions:
+   DetectorType: FAST
+   DetectorMode: STATIC
+   FastDetector:
+      Threshold: 25
+      NonMaxSuppression: 1
+   OrbDetector:
+      NumFeatures: 500
+      ScaleFactor: 1.2
+      NumLevels: 8
+   ExtractorType: ORB
+"""
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+    with open(os.path.join(tmp, "settings.yml")) as f:
+        yml = f.read().replace("epsilon: 0.55", "epsilon: 0.8")
+    with open(os.path.join(tmp, "settings.yml"), "w") as f:
+        f.write(yml)
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+    descs = []
+    for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
+        oxy, orr = fo.detect_fast(img, 25, True)
+        k4 = np.concatenate([oxy, np.full((len(oxy), 1), 7, np.float32), np.full((len(oxy), 1), -1, np.float32)], 1)
+        okept, od = on.describe_keypoints_orb(img, k4)
+        np.testing.assert_array_equal(k[:, :2], oxy[okept])
+        assert d.dtype == np.uint8 and d.shape == (len(okept), 32)
+        np.testing.assert_array_equal(d, od)
+        descs.append(d)
+    o_idx, o_dist = orc.knn2_hamming(descs[0], descs[1])
+    oq, ot, od_ = orc.nndr_filter(o_idx, o_dist, 0.8)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    np.testing.assert_array_equal(res["matches"]["d"], od_)
+    print(f"FAST+ORB from the frames: {len(descs[0])} / {len(descs[1])} described keypoints, {len(oq)} NNDR matches, "
+          f"{int(res['mask'].sum())} in depth range, {len(res['normals'])} refined normals")
+    assert len(oq) > 50

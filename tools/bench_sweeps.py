@@ -234,8 +234,11 @@ def frontend_sweep(ctx, stream):
             t2 = time.perf_counter()
             cv2.BRISK_create(25, 0).compute(img, cvk)
             t3 = time.perf_counter()
+            cv2.ORB_create().compute(img, cvk)
+            t4 = time.perf_counter()
             print(json.dumps({"case": "frontend_opencv_cpu", "W": W, "H": H, "keypoints": len(cvk), "threads": cv2.getNumThreads(),
-                              "ms_detect_fast": (t1 - t0) * 1e3, "ms_sift_compute": (t2 - t1) * 1e3, "ms_brisk_compute": (t3 - t2) * 1e3}), flush=True)
+                              "ms_detect_fast": (t1 - t0) * 1e3, "ms_sift_compute": (t2 - t1) * 1e3, "ms_brisk_compute": (t3 - t2) * 1e3,
+                              "ms_orb_compute": (t4 - t3) * 1e3}), flush=True)
         except ImportError:
             pass
         bdesc = torch.empty((n, 64), dtype=torch.uint8, device=dev)
@@ -245,6 +248,11 @@ def frontend_sweep(ctx, stream):
                                                                           bkept.data_ptr(), bang.data_ptr()), 5)
         print(json.dumps({"case": "frontend_fast_brisk", "W": W, "H": H, "keypoints": n, "kept": int(bkept.sum().item()),
                           "ms_describe_incl_integral": ms_brisk, "descriptors_per_s": n / (ms_brisk * 1e-3)}), flush=True)
+        odesc = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+        ms_orb = timed(stream, lambda: ctx.describe_keypoints_orb_dev(d_img.data_ptr(), W, H, W, k4.data_ptr(), n, odesc.data_ptr(), bkept.data_ptr()), 5)
+        print(json.dumps({"case": "frontend_fast_orb", "W": W, "H": H, "keypoints": n, "kept": int(bkept.sum().item()),
+                          "ms_describe_incl_blur": ms_orb, "descriptors_per_s": n / (ms_orb * 1e-3),
+                          "hbm_gbs_compulsory": (2.0 * W * H + 48.0 * n) / (ms_orb * 1e-3) / 1e9, "hbm_peak_gbs": PEAKS.get("hbm_gbs")}), flush=True)
         print(json.dumps({"case": "frontend_fast_sift", "W": W, "H": H, "keypoints": n, "ms_detect": ms_det, "ms_base_image": ms_base,
                           "ms_describe_incl_base": ms_all, "detect_hbm_gbs_compulsory": W * H / (ms_det * 1e-3) / 1e9,
                           "base_hbm_gbs_compulsory": 5.0 * W * H / (ms_base * 1e-3) / 1e9, "hbm_peak_gbs": PEAKS.get("hbm_gbs"),
