@@ -450,6 +450,8 @@ def run_gpu_arm(args):
         d_bdesc = torch.zeros((2, KP_CAP, 64), dtype=torch.uint8, device=dev)
         d_bkept = torch.zeros((2, KP_CAP), dtype=torch.uint8, device=dev)
         d_bang = torch.zeros((2, KP_CAP), dtype=torch.float32, device=dev)
+        d_odesc = torch.zeros((2, KP_CAP, 32), dtype=torch.uint8, device=dev)
+        d_okept = torch.zeros((2, KP_CAP), dtype=torch.uint8, device=dev)
     stream.synchronize()
     n_kp = [0, 0]
 
@@ -471,6 +473,11 @@ def run_gpu_arm(args):
                         ctx.describe_keypoints_brisk_dev(img.data_ptr(), W, H, W, d_k4[a].data_ptr(), n_kp[a], True, d_bdesc[a].data_ptr(),
                                                          d_bkept[a].data_ptr(), d_bang[a].data_ptr())
             if events: events[3].record(stream)
+            if describe:
+                for a, img in enumerate((d_img1, d_img2)):
+                    if n_kp[a] > 0:
+                        ctx.describe_keypoints_orb_dev(img.data_ptr(), W, H, W, d_k4[a].data_ptr(), n_kp[a], d_odesc[a].data_ptr(), d_okept[a].data_ptr())
+            if events: events[4].record(stream)
     before_path(describe=False)
     stream.synchronize()
     n_kp = [min(int(v), KP_CAP) for v in d_kn.cpu().tolist()]
@@ -482,13 +489,14 @@ def run_gpu_arm(args):
         before_path()
         flush_l2()
     barrier()
-    ev_before = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(alt_steps)]
+    ev_before = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(alt_steps)]
     for s_ in range(alt_steps):
         before_path(ev_before[s_])
         flush_l2()
     barrier()
-    before_ms = [sum(ev_before[s_][j].elapsed_time(ev_before[s_][j + 1]) for s_ in range(alt_steps)) / alt_steps for j in range(3)]
+    before_ms = [sum(ev_before[s_][j].elapsed_time(ev_before[s_][j + 1]) for s_ in range(alt_steps)) / alt_steps for j in range(4)]
     brisk_kept = [int(d_bkept[a, :n_kp[a]].sum().item()) for a in range(2)]
+    orb_kept = [int(d_okept[a, :n_kp[a]].sum().item()) for a in range(2)]
     kdesc_rows_nonzero = [int((d_kdesc[a, :n_kp[a]] != 0).any(1).sum().item()) for a in range(2)]
 
     # ---- reduce over ranks: max time, summed features
@@ -603,12 +611,13 @@ def run_gpu_arm(args):
             "before_path_rank0": {
                 "note": "what compareWithNNDR does first with DetectorType FAST + ExtractorType SIFT (descriptorsmatcher.cpp:110-115): "
                         "FAST-9-16 detection (K10), SIFT description at the detected keypoints (K11) and, separately, their BRISK "
-                        "description (K12, ExtractorType BRISK) of BOTH frames, "
+                        "and ORB descriptions (K12 / K13, ExtractorType BRISK / ORB) of BOTH frames, "
                         "device-resident, CUDA events; not part of `value`",
                 "fast_threshold": FAST_T, "keypoints": n_kp,
                 "ms": {"detect_both_frames": before_ms[0], "describe_both_frames": before_ms[1],
-                       "describe_brisk_both_frames": before_ms[2]},
-                "brisk_keypoints_kept": brisk_kept,
+                       "describe_brisk_both_frames": before_ms[2], "describe_orb_both_frames": before_ms[3]},
+                "brisk_keypoints_kept": brisk_kept, "orb_keypoints_kept": orb_kept,
+                "orb_descriptors_per_s": sum(n_kp) / (before_ms[3] * 1e-3) if before_ms[3] > 0 else None,
                 "brisk_descriptors_per_s": sum(n_kp) / (before_ms[2] * 1e-3) if before_ms[2] > 0 else None,
                 "detect_hbm_gbs": 2 * W * H / (before_ms[0] * 1e-3) / 1e9 if before_ms[0] > 0 else None,
                 "descriptors_per_s": sum(n_kp) / (before_ms[1] * 1e-3) if before_ms[1] > 0 else None,
