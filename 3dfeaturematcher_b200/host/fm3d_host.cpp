@@ -156,6 +156,9 @@ DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv
     detector_mode_ = (std::string)fs["FeatureOptions"]["DetectorMode"];
     fast_threshold_ = (int)fs["FeatureOptions"]["FastDetector"]["Threshold"];                 // :218
     fast_nonmax_ = (int)fs["FeatureOptions"]["FastDetector"]["NonMaxSuppression"] > 0;        // :219-220
+    adaptive_min_ = (int)fs["FeatureOptions"]["Adaptive"]["MinFeatures"];                     // :194-197
+    adaptive_max_ = (int)fs["FeatureOptions"]["Adaptive"]["MaxFeatures"];
+    adaptive_iters_ = (int)fs["FeatureOptions"]["Adaptive"]["MaxIters"];
     host_ctx();
 }
 
@@ -173,13 +176,13 @@ void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv:
     // descriptorsmatcher.cpp:110-115: detect on both frames, then compute on both frames.  DetectorType FAST
     // (STATIC) with ExtractorType SIFT, BRISK or ORB runs on the GPU (K10 + K11 / K12 / K13); the other detectors /
     // extractors of the reference (SURF, STAR, MSER, FREAK, ORB's own detector) are upstream code this library does not carry.
-    if (detector_type_ == "FAST" && detector_mode_ == "STATIC" && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK" || extractor_type_ == "ORB")) {
+    if (detector_type_ == "FAST" && (detector_mode_ == "STATIC" || detector_mode_ == "ADAPTIVE") && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK" || extractor_type_ == "ORB")) {
         detectAndDescribe(image_a_, ka, da);
         detectAndDescribe(image_b_, kb, db);
         return;
     }
     throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC) + "
-                             "ExtractorType SIFT, BRISK or ORB only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
+                             "ExtractorType SIFT, BRISK or ORB only (STATIC or ADAPTIVE; settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
                              "); inject the features of other detectors with setFeatures");
 }
 
@@ -192,9 +195,37 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
     const uint8_t* px = image.ptr<uint8_t>(0);
     const int w = image.cols, h = image.rows, stride = (int)image.step1();
     int n = 0;
-    check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, fast_threshold_, fast_nonmax_, 0, nullptr, nullptr, &n), "detect (count)");
+    int threshold = fast_threshold_, nonmax = fast_nonmax_;
+    if (detector_mode_ == "ADAPTIVE") {
+        // descriptorsmatcher.cpp:186-199: cv::DynamicAdaptedFeatureDetector(AdjusterAdapter::create("FAST"), MinFeatures,
+        // MaxFeatures, MaxIters) of OpenCV 2.4 (removed in 3.0, so not in the cv2 of this image: restated from the published
+        // 2.4 algorithm, parity unpinned).  cv::FastAdjuster starts at threshold 20 with non-maximum suppression and moves the
+        // threshold by one per iteration: down when there are too few keypoints, up when there are too many; the loop ends
+        // when the count is inside [MinFeatures, MaxFeatures], after MaxIters detections, when it has gone both ways
+        // (oscillation), or when the threshold leaves (1, 200).  The keypoints of the LAST detection are the result.
+        threshold = 20; nonmax = 1;
+        bool down = false, up = false, good = false;
+        int iters = adaptive_iters_, last = threshold;
+        while (iters > 0 && !(down && up) && !good && threshold > 1 && threshold < 200) {
+            last = threshold;
+            check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, threshold, nonmax, 0, nullptr, nullptr, &n), "detect (adaptive)");
+            if (n < adaptive_min_) { down = true; threshold--; }
+            else if (n > adaptive_max_) { up = true; threshold++; }
+            else good = true;
+            iters--;
+        }
+        if (iters == adaptive_iters_) {          // the loop never ran (MaxIters <= 0): cv leaves the keypoint list empty
+            kpts.clear();
+            desc = cv::Mat();
+            adaptive_threshold_used_ = -1;
+            return;
+        }
+        threshold = last;
+        adaptive_threshold_used_ = last;
+    }
+    check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, threshold, nonmax, 0, nullptr, nullptr, &n), "detect (count)");
     std::vector<float> xy((size_t)2 * (n > 0 ? n : 1)), resp((size_t)(n > 0 ? n : 1));
-    if (n > 0) check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, fast_threshold_, fast_nonmax_, n, xy.data(), resp.data(), &n), "detect");
+    if (n > 0) check(ctx, fm3d_detect_fast(ctx, px, w, h, stride, threshold, nonmax, n, xy.data(), resp.data(), &n), "detect");
     kpts.clear();
     kpts.reserve(n);
     std::vector<float> k4((size_t)4 * (n > 0 ? n : 1));

@@ -32,6 +32,8 @@ public:
                      const std::vector<cv::KeyPoint>& kpts_b, const cv::Mat& desc_b);
     // fm3d extension: mutual-best flags of the last compareWithNNDR (the fused cross-check)
     const std::vector<unsigned char>& mutualFlags() const { return mutual_; }
+    // fm3d extension: the FAST threshold the ADAPTIVE mode ended on for the frame described last (-1: STATIC mode)
+    int adaptiveThreshold() const { return adaptive_threshold_used_; }
 
 private:
     void features(std::vector<cv::KeyPoint>& ka, std::vector<cv::KeyPoint>& kb, cv::Mat& da, cv::Mat& db);
@@ -44,5 +46,7 @@ private:
     bool binary_, have_features_;
     std::string extractor_type_, detector_type_, detector_mode_;
     int fast_threshold_, fast_nonmax_;
+    int adaptive_min_, adaptive_max_, adaptive_iters_;
+    int adaptive_threshold_used_ = -1;
 };
 #endif

@@ -458,3 +458,60 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_orb(tmp_path):
     print(f"FAST+ORB from the frames: {len(descs[0])} / {len(descs[1])} described keypoints, {len(oq)} NNDR matches, "
           f"{int(res['mask'].sum())} in depth range, {len(res['normals'])} refined normals")
     assert len(oq) > 50
+
+
+def _adaptive_fast(img, nmin, nmax, iters):
+    """cv::DynamicAdaptedFeatureDetector(FastAdjuster) of OpenCV 2.4 (descriptorsmatcher.cpp:186-199), restated over the
+    FAST oracle: threshold 20, non-maximum suppression, one step per iteration."""
+    from oracle import fast_np as fo
+    t, down, up, good, out = 20, False, False, False, (np.zeros((0, 2), np.float32), np.zeros(0, np.float32))
+    while iters > 0 and not (down and up) and not good and 1 < t < 200:
+        out = fo.detect_fast(img, t, True)
+        n = len(out[0])
+        if n < nmin:
+            down, t = True, t - 1
+        elif n > nmax:
+            up, t = True, t + 1
+        else:
+            good = True
+        iters -= 1
+    return out
+
+
+@pytest.mark.gpu
+def test_main_cpp_with_the_adaptive_fast_detector(tmp_path):
+    """DetectorMode ADAPTIVE + DetectorType FAST (descriptorsmatcher.cpp:186-199): the adapter iterates the GPU detector as
+    cv::DynamicAdaptedFeatureDetector iterates cv::FastAdjuster.  The class left OpenCV with 3.0 (not in cv2 here): the check
+    is against the same loop over the FAST oracle -- parity of the loop itself is unpinned."""
+    from oracle import fast_np as fo
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    tmp = str(tmp_path)
+    counts = [len(fo.detect_fast(case["scene"].img1, t, True)[0]) for t in (20, 23)]
+    for nmin, nmax, iters in ((counts[1] - 5, counts[1] + 5, 10),         # reaches the window at threshold 23
+                              (counts[0] + 50, counts[0] + 60, 10),       # too few at 20: steps down
+                              (10, 20, 3)):                               # far too many: stops after MaxIters detections
+        opts = f"""FeatureOptions:
+   DetectorType: FAST
+   DetectorMode: ADAPTIVE
+   Adaptive:
+      MinFeatures: {nmin}
+      MaxFeatures: {nmax}
+      MaxIters: {iters}
+   FastDetector:
+      Threshold: 77
+      NonMaxSuppression: 0
+   ExtractorType: ORB
+"""
+        _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+        env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+        p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
+                           capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        res = _read_result(os.path.join(tmp, "result.bin"))
+        for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
+            oxy, orr = _adaptive_fast(img, nmin, nmax, iters)
+            inside = (oxy[:, 0] >= 31) & (oxy[:, 0] < img.shape[1] - 31) & (oxy[:, 1] >= 31) & (oxy[:, 1] < img.shape[0] - 31)   # ORB's border rule
+            np.testing.assert_array_equal(k[:, :2], oxy[inside])
+            np.testing.assert_array_equal(k[:, 4], orr[inside])
