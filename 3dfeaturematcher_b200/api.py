@@ -41,6 +41,7 @@ SYMBOLS = [
     "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_sift_base_image_dev",
     "fm3d_describe_keypoints_brisk", "fm3d_describe_keypoints_brisk_dev",
     "fm3d_describe_keypoints_orb", "fm3d_describe_keypoints_orb_dev",
+    "fm3d_describe_patches_orb", "fm3d_describe_patches_orb_dev",
 ]
 
 
@@ -433,7 +434,19 @@ class Context:
         self._ck(self.lib.fm3d_describe_keypoints_orb(self._h, _ptr(img, _bp), w, h, img.strides[0], _ptr(kps, _fp), n, _ptr(desc, _bp), _ptr(kept, _bp)))
         return desc, kept.astype(bool)
 
+    def describe_patches_orb(self, patches):
+        """extractDescriptorsFromPatches for ExtractorType ORB: n x S x S u8 -> n x 32 u8."""
+        patches = _arr(patches, np.uint8)
+        n = patches.shape[0]
+        S = patches.shape[1] if patches.ndim == 3 else 0
+        desc = np.zeros((n, 32), np.uint8)
+        self._ck(self.lib.fm3d_describe_patches_orb(self._h, _ptr(patches, _bp), n, S, _ptr(desc, _bp)))
+        return desc
+
     # ------------------------------------------------------------------ device-pointer entry points
+    def describe_patches_orb_dev(self, patches, n, S, descriptors):
+        self._ck(self.lib.fm3d_describe_patches_orb_dev(self._h, C.c_void_p(patches), n, S, C.c_void_p(descriptors)))
+
     def describe_keypoints_orb_dev(self, img, w, h, stride, kps, n, descriptors, kept):
         self._ck(self.lib.fm3d_describe_keypoints_orb_dev(self._h, C.c_void_p(img), w, h, stride, C.c_void_p(kps), n, C.c_void_p(descriptors), C.c_void_p(kept)))
 

@@ -104,6 +104,17 @@ orb_kp_kernel(const uint8_t* __restrict__ blur, int w, int h, const float* __res
     if (lane == 0) kept[f] = 1;
 }
 
+// keypoint k of extractDescriptorsFromPatches on the patches stacked into one S-wide image: (S/2, k S + S/2), size S, angle -1
+__global__ void orb_patch_centres_kernel(float* __restrict__ kps, int n, int S) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float c = (float)(S / 2);
+    kps[4 * (size_t)k] = c;
+    kps[4 * (size_t)k + 1] = (float)k * (float)S + c;
+    kps[4 * (size_t)k + 2] = (float)S;
+    kps[4 * (size_t)k + 3] = -1.0f;
+}
+
 }  // namespace
 
 extern "C" {
@@ -130,6 +141,43 @@ int fm3d_describe_keypoints_orb_dev(fm3d_ctx* ctx, const uint8_t* img, int w, in
     FM3D_LAUNCH_CHECK(ctx);
     orb_kp_kernel<<<(n + OB_WARPS - 1) / OB_WARPS, OB_WARPS * 32, 0, ctx->stream>>>(blur, w, h, kps, n, descriptors, kept);
     FM3D_LAUNCH_CHECK(ctx);
+    return FM3D_OK;
+}
+
+int fm3d_describe_patches_orb_dev(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, uint8_t* descriptors) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && S >= 1 && (n == 0 || (patches && descriptors)));
+    if (n == 0) return FM3D_OK;
+    // cv::ORB keeps the keypoint (S/2, S/2) only if 31 <= S/2 < S - 31; the compared pixels (centre +- 13) and their 7 x 7
+    // blur support then lie inside the patch, so the patches can be described as ONE image of n S rows: nothing a patch's
+    // row depends on crosses into its neighbours, and the border rule on the stacked image is the per-patch rule.
+    if (S / 2 < OB_EDGE || S / 2 >= S - OB_EDGE)
+        return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "patch edge %d: cv::ORB removes the keypoint of extractDescriptorsFromPatches (needs 31 <= S/2 < S - 31)", S);
+    FM3D_CHECK_ARG(ctx, (double)n * S < 2147483647.0 && (double)n * S < 16777216.0);      // row coordinates stay exact in float
+    if (int rc = fm3d_bind(ctx)) return rc;
+    char* d = nullptr;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    if (int rc = fm3d_scratch(ctx, 11, al(sizeof(float) * 4 * (size_t)n) + al((size_t)n), (void**)&d)) return rc;
+    float* kps = reinterpret_cast<float*>(d);
+    uint8_t* kept = reinterpret_cast<uint8_t*>(d + al(sizeof(float) * 4 * (size_t)n));
+    orb_patch_centres_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(kps, n, S);
+    FM3D_LAUNCH_CHECK(ctx);
+    return fm3d_describe_keypoints_orb_dev(ctx, patches, S, n * S, S, kps, n, descriptors, kept);
+}
+
+int fm3d_describe_patches_orb(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, uint8_t* descriptors) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && S >= 1 && (n == 0 || (patches && descriptors)));
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t bp = (size_t)n * S * S, bd = 32 * (size_t)n;
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, al(bp) + al(bd), (void**)&d)) return rc;
+    if (int rc = fm3d_h2d(ctx, d, patches, bp)) return rc;
+    if (int rc = fm3d_describe_patches_orb_dev(ctx, reinterpret_cast<const uint8_t*>(d), n, S, reinterpret_cast<uint8_t*>(d + al(bp)))) return rc;
+    if (int rc = fm3d_d2h(ctx, descriptors, d + al(bp), bd)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FM3D_OK;
 }
 

@@ -339,8 +339,8 @@ void DescriptorsMatcher::compareWithNNDR(double epsilon, std::vector<cv::DMatch>
 // descriptor row per patch.  ExtractorType SIFT runs on the GPU (K9); the other extractors of the
 // reference (SURF / ORB / BRISK / FREAK of OpenCV 2.4) are upstream code this library does not carry.
 void DescriptorsMatcher::extractDescriptorsFromPatches(const std::vector<cv::Mat>& patchesVector, cv::Mat& descriptors) {
-    if (extractor_type_ != "SIFT")
-        throw std::runtime_error("fm3d: extractDescriptorsFromPatches runs on the GPU for ExtractorType SIFT only (settings: " +
+    if (extractor_type_ != "SIFT" && extractor_type_ != "ORB")
+        throw std::runtime_error("fm3d: extractDescriptorsFromPatches runs on the GPU for ExtractorType SIFT and ORB only (settings: " +
                                  extractor_type_ + ")");
     const int n = (int)patchesVector.size();
     if (n == 0) { descriptors = cv::Mat(); return; }
@@ -351,8 +351,13 @@ void DescriptorsMatcher::extractDescriptorsFromPatches(const std::vector<cv::Mat
         if (p.rows != S || p.cols != S || p.type() != CV_8UC1) throw std::runtime_error("fm3d: patches must be square CV_8UC1 of one size");
         for (int r = 0; r < S; r++) memcpy(packed.data() + ((size_t)k * S + r) * S, p.ptr<uint8_t>(r), (size_t)S);
     }
-    descriptors = cv::Mat::zeros(cv::Size(128, n), CV_32F);
     fm3d_ctx* ctx = host_ctx();
+    if (extractor_type_ == "ORB") {
+        descriptors = cv::Mat::zeros(cv::Size(32, n), CV_8U);
+        check(ctx, fm3d_describe_patches_orb(ctx, packed.data(), n, S, descriptors.ptr<uint8_t>()), "extractDescriptorsFromPatches (ORB)");
+        return;
+    }
+    descriptors = cv::Mat::zeros(cv::Size(128, n), CV_32F);
     check(ctx, fm3d_describe_patches_sift(ctx, packed.data(), n, S, descriptors.ptr<float>()), "extractDescriptorsFromPatches");
 }
 

@@ -430,6 +430,12 @@ int fm3d_describe_keypoints_orb(fm3d_ctx* ctx, const uint8_t* img, int w, int h,
 int fm3d_describe_keypoints_orb_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
                                     int n, uint8_t* descriptors, uint8_t* kept);
 
+/* DescriptorsMatcher::extractDescriptorsFromPatches (:133-174) with ExtractorType ORB: one keypoint per patch at
+ * (floor(S/2), floor(S/2)), size S, angle -1; descriptors n x 32 u8.  cv::ORB keeps that keypoint only when
+ * 31 <= S/2 < S - 31 (FM3D_ERR_UNSUPPORTED otherwise: the reference's own call would return an empty row). */
+int fm3d_describe_patches_orb(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, uint8_t* descriptors);
+int fm3d_describe_patches_orb_dev(fm3d_ctx* ctx, const uint8_t* patches, int n, int S, uint8_t* descriptors);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,8 +144,10 @@ int main(int argc, char** argv) {
         patchDescriptors = cv::Mat();
     }
     int dr = patchDescriptors.rows, dc = patchDescriptors.cols;
-    fwrite(&dr, 4, 1, o); fwrite(&dc, 4, 1, o);
-    if (dr > 0) fwrite(patchDescriptors.data, 4, (size_t)dr * dc, o);
+    const int pes = dr > 0 ? (int)patchDescriptors.elemSize() : 4;
+    int dc_tagged = pes == 1 ? -dc : dc;                 // negative column count: CV_8U rows (binary extractors)
+    fwrite(&dr, 4, 1, o); fwrite(&dc_tagged, 4, 1, o);
+    if (dr > 0) fwrite(patchDescriptors.data, (size_t)pes, (size_t)dr * dc, o);
     if (detect_here) {
         // what compareWithNNDR returned for the two frames: keypoints (pt, size, angle, response) and descriptors
         const std::vector<cv::KeyPoint>* ks[2] = {&kpts1, &kpts2};

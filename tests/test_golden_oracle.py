@@ -195,3 +195,8 @@ def test_orb_restatement_against_cv2_golden_vectors():
         np.testing.assert_array_equal(d, g[f"d_{name}_{tag}"])
         seen += len(kept)
     assert seen > 600
+    # extractDescriptorsFromPatches with ExtractorType ORB: one keypoint per patch
+    for S in (128, 64, 63):
+        for patch, want in zip(g[f"p{S}"], g[f"dp{S}"]):
+            kept, d = on.describe_keypoints_orb(patch, np.array([[S // 2, S // 2, S, -1]], np.float32))
+            assert len(kept) == 1 and np.unpackbits(d[0] ^ want).sum() <= 2

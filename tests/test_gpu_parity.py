@@ -1132,6 +1132,30 @@ def test_describe_keypoints_orb_golden_vectors_and_oracle(ctx):
     assert ctx.describe_keypoints_orb(img, np.zeros((0, 4), np.float32))[0].shape == (0, 32)
 
 
+def test_describe_patches_orb(ctx, api):
+    """extractDescriptorsFromPatches (descriptorsmatcher.cpp:133-174) with ExtractorType ORB: the committed outputs of
+    cv2.ORB_create().compute on one keypoint per patch (centre, size S, angle -1), and the restatement on random patches.
+    The patches are described as one stacked image: rows must not depend on their neighbours."""
+    import os
+    from oracle import orb_np as on
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orb_keypoints.npz"))
+    for S in (128, 64, 63):
+        d = ctx.describe_patches_orb(g[f"p{S}"])
+        ham = np.unpackbits(d ^ g[f"dp{S}"], axis=1).sum(1)
+        assert d.shape == (len(g[f"p{S}"]), 32) and ham.max() <= 2 and (ham == 0).mean() >= 0.8, ham
+    rng = np.random.default_rng(77)
+    for S, n in ((128, 37), (100, 9), (63, 5)):
+        patches = rng.integers(0, 256, (n, S, S), dtype=np.uint8)
+        got = ctx.describe_patches_orb(patches)
+        want = np.stack([on.describe_keypoints_orb(p, np.array([[S // 2, S // 2, S, -1]], np.float32))[1][0] for p in patches])
+        np.testing.assert_array_equal(got, want)
+        assert np.array_equal(ctx.describe_patches_orb(patches[3:4])[0], got[3])        # independent of the neighbours in the stack
+    assert ctx.describe_patches_orb(np.zeros((0, 128, 128), np.uint8)).shape == (0, 32)
+    for S in (62, 40):                                  # cv::ORB would remove the keypoint
+        with pytest.raises(api.Fm3dError):
+            ctx.describe_patches_orb(np.zeros((2, S, S), np.uint8))
+
+
 def test_detect_orb_hamming_chain_full_size(ctx):
     """DetectorType FAST + ExtractorType ORB on a 1280 x 720 frame (BASELINE C2 shape; ORB-256 is the binary descriptor the
     matching sweep is quoted on): detection, description and the Hamming matcher on the GPU; oracle parity on a sample;

@@ -144,7 +144,10 @@ def _read_result(path):
         cpts = np.frombuffer(b, np.float64, 3 * cs, o).reshape(-1, 3); o += 24 * cs
         circ = dict(normal=cn, pts=cpts)
     dr, dc = struct.unpack_from("ii", b, o); o += 8
-    desc = np.frombuffer(b, np.float32, dr * dc, o).reshape(dr, dc); o += 4 * dr * dc
+    if dc < 0:
+        desc = np.frombuffer(b, np.uint8, dr * -dc, o).reshape(dr, -dc); o += dr * -dc
+    else:
+        desc = np.frombuffer(b, np.float32, dr * dc, o).reshape(dr, dc); o += 4 * dr * dc
     detected = []
     while o < len(b) and len(detected) < 2:          # "-" mode: the features compareWithNNDR produced itself
         n, cols, es = struct.unpack_from("iii", b, o); o += 12
@@ -416,7 +419,7 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_orb(tmp_path):
     from oracle import fast_np as fo
     from oracle import orb_np as on
     exe = build_pipeline_main()
-    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    r, pyramids, eps_m, cmpp = 32, 2, 0.16, 0.25          # 128 x 128 patches: cv::ORB needs 31 <= S/2 < S - 31
     case = stereo_case(640, 480, 60, 1000, r)
     tmp = str(tmp_path)
     opts = """FeatureOptions:
@@ -455,6 +458,13 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_orb(tmp_path):
     np.testing.assert_array_equal(res["matches"]["q"], oq)
     np.testing.assert_array_equal(res["matches"]["t"], ot)
     np.testing.assert_array_equal(res["matches"]["d"], od_)
+    # extractDescriptorsFromPatches with ExtractorType ORB (main.cpp:182-183): one 32-byte row per rectified patch
+    pd = res["patch_descriptors"]
+    assert pd.dtype == np.uint8 and pd.shape == (len(res["patches"]), 32) and res["S"] >= 63
+    S = res["S"]
+    for j in range(0, len(pd), max(1, len(pd) // 40)):
+        ok_, od1 = on.describe_keypoints_orb(res["patches"][j], np.array([[S // 2, S // 2, S, -1]], np.float32))
+        assert len(ok_) == 1 and np.array_equal(od1[0], pd[j])
     print(f"FAST+ORB from the frames: {len(descs[0])} / {len(descs[1])} described keypoints, {len(oq)} NNDR matches, "
           f"{int(res['mask'].sum())} in depth range, {len(res['normals'])} refined normals")
     assert len(oq) > 50

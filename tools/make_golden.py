@@ -249,6 +249,17 @@ def orb_keypoints():
             out[f"k_{name}_{tag}"] = arr
             out[f"kept_{name}_{tag}"] = kept
             out[f"d_{name}_{tag}"] = d
+    # extractDescriptorsFromPatches (descriptorsmatcher.cpp:133-174) with ExtractorType ORB: one keypoint per patch
+    for S, count in ((128, 3), (64, 4), (63, 2)):
+        p = sift_test_patches(S, count, 6000 + S)
+        rows = []
+        for patch in p:
+            kp = cv2.KeyPoint(float(S // 2), float(S // 2), float(S), -1.0, 1.0, 0, 0)
+            k2, d = orb.compute(patch, [kp])
+            assert len(k2) == 1
+            rows.append(d[0])
+        out[f"p{S}"] = p
+        out[f"dp{S}"] = np.array(rows, np.uint8)
     np.savez_compressed(os.path.join(OUT, "orb_keypoints.npz"), **out)
 
 
