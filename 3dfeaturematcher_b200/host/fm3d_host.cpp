@@ -444,6 +444,19 @@ static void unpack_patches(int n, int S, const std::vector<uint8_t>& p, const st
         patchesVector.push_back(patch);
         imagePointsVector.push_back(pts);
     }
+    // FM3D_PATCH_ATLAS=<file.pgm>: every patch into ONE binary PGM (a grid of ceil(sqrt(n)) patches per row, patch f at row
+    // f / cols, column f % cols) instead of n files -- the reference's 20 000 imwrite calls are its I/O bottleneck at C3 size
+    if (const char* atlas = getenv("FM3D_PATCH_ATLAS")) {
+        if (n > 0) {
+            const int cols = (int)std::ceil(std::sqrt((double)n)), rows = (n + cols - 1) / cols;
+            cv::Mat sheet = cv::Mat::zeros(cv::Size(cols * S, rows * S), CV_8UC1);
+            for (int f = 0; f < n; f++)
+                for (int r = 0; r < S; r++)
+                    memcpy(sheet.ptr<uint8_t>((f / cols) * S + r) + (size_t)(f % cols) * S, p.data() + ((size_t)f * S + r) * S, (size_t)S);
+            cv::imwrite(atlas, sheet);
+        }
+        return;
+    }
     if (write_files)
         for (int f = 0; f < n; f++) cv::imwrite("patch_" + NumberToString<int>(f) + ".pgm", patchesVector[f]);  // (:799-802)
 }

@@ -439,11 +439,23 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_orb(tmp_path):
         yml = f.read().replace("epsilon: 0.55", "epsilon: 0.8")
     with open(os.path.join(tmp, "settings.yml"), "w") as f:
         f.write(yml)
-    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_PATCH_ATLAS=os.path.join(tmp, "patches.pgm"))
     p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
                        capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     res = _read_result(os.path.join(tmp, "result.bin"))
+    # FM3D_PATCH_ATLAS: all patches in ONE PGM (the reference writes patch_N.pgm per feature), none as single files
+    assert not [f for f in os.listdir(tmp) if f.startswith("patch_")]
+    raw = open(os.path.join(tmp, "patches.pgm"), "rb").read()
+    hdr = raw.split(b"\n", 3)
+    assert hdr[0] == b"P5" and hdr[2] == b"255"
+    aw, ah = map(int, hdr[1].split())
+    sheet = np.frombuffer(hdr[3], np.uint8).reshape(ah, aw)
+    S_, n_ = res["S"], len(res["patches"])
+    cols_ = int(np.ceil(np.sqrt(n_)))
+    assert aw == cols_ * S_ and ah == -(-n_ // cols_) * S_
+    for f_ in (0, 1, cols_, n_ - 1):
+        assert np.array_equal(sheet[(f_ // cols_) * S_:(f_ // cols_ + 1) * S_, (f_ % cols_) * S_:(f_ % cols_ + 1) * S_], res["patches"][f_])
     descs = []
     for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
         oxy, orr = fo.detect_fast(img, 25, True)
