@@ -69,3 +69,22 @@ for fn in functions("fm3d_normals_fast.o"):
             for b in body:
                 f.write(b[:120] + "\n")
 print("wrote", os.listdir(OUT))
+
+# ---- the front end (K10-K13): opcode mix per kernel and the inner loops of the two descriptor kernels
+import collections
+with open(os.path.join(OUT, "r01_frontend_kernels.txt"), "w") as f:
+    f.write("# cuobjdump -sass of fm3d_detect.o, fm3d_describe_kp.o, fm3d_describe_brisk.o, fm3d_describe_orb.o (sm_100a):\n"
+            "# instruction count and opcode mix per kernel (static), then the full listing of brisk_kp_kernel's and orb_kp_kernel's bodies.\n")
+    for obj in ("fm3d_detect.o", "fm3d_describe_kp.o", "fm3d_describe_brisk.o", "fm3d_describe_orb.o"):
+        for fn in functions(obj):
+            body = [l for l in sass(obj, fn) if re.match(r"^\s+/\*[0-9a-f]{4}\*/", l)]
+            ops = collections.Counter()
+            for l in body:
+                m_ = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", l)
+                if m_:
+                    ops[m_.group(1)] += 1
+            short = re.sub(r"^_ZN\d+_GLOBAL__N__[0-9a-f]+_\d+_", "", fn)
+            f.write(f"\n## {obj}: {short}\n# {len(body)} instructions: " + ", ".join(f"{k} {v}" for k, v in ops.most_common(14)) + "\n")
+            if "brisk_kp_kernel" in fn or "orb_kp_kernel" in fn:
+                for l in body:
+                    f.write(l[:120] + "\n")
