@@ -50,34 +50,67 @@ __device__ __forceinline__ int reflect101_any(int i, int n) {
 
 __global__ void __launch_bounds__(BT_NT)
 sift_base_kernel(const BlurArgs A, const uint8_t* __restrict__ img, int w, int h, int stride, float* __restrict__ base) {
-    constexpr int IW = BT_W + 2 * KP_KHALF, IH = BT_H + 2 * KP_KHALF;
-    __shared__ float in[IH][IW + 1];
-    __shared__ float rowp[IH][BT_W];
+    constexpr int IW = BT_W + 2 * KP_KHALF, IH = BT_H + 2 * KP_KHALF;      // 76 x 44: rows of 304 B, 16-byte aligned
+    __shared__ __align__(16) float in[IH][IW];
+    __shared__ __align__(16) float rowp[IH][BT_W];
     const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H, tid = threadIdx.x;
-    for (int i = tid; i < IH * IW; i += BT_NT) {
-        const int r = i / IW, c = i - r * IW;
-        const int gy = reflect101_any(y0 + r - KP_KHALF, h), gx = reflect101_any(x0 + c - KP_KHALF, w);
-        in[r][c] = fm3d_u8f(img[(size_t)gy * stride + gx]);
+    const int lane = tid & 31, wid = tid >> 5;
+    // interior tiles (no reflection, 4-byte aligned rows): 32-bit loads of columns x0 - 8 .. x0 + 71, of which x0 - 6 .. x0 + 69 are kept
+    const bool interior = x0 >= 8 && x0 + BT_W + 8 <= w && y0 >= KP_KHALF && y0 + BT_H + KP_KHALF <= h &&
+                          (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+    if (interior) {
+        constexpr int Q = (BT_W + 16) / 4;       // 20 words per row
+        for (int i = tid; i < IH * Q; i += BT_NT) {
+            const int r = i / Q, q = i - r * Q;
+            const unsigned v = *reinterpret_cast<const unsigned*>(img + (size_t)(y0 + r - KP_KHALF) * stride + (x0 - 8 + 4 * q));
+            const int c = 4 * q - 2;             // column of the word's first byte in `in`
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (c + b >= 0 && c + b < IW) in[r][c + b] = fm3d_u8f((v >> (8 * b)) & 255u);
+        }
+    } else {
+        for (int r = wid; r < IH; r += BT_NT / 32) {
+            const uint8_t* src = img + (size_t)reflect101_any(y0 + r - KP_KHALF, h) * stride;
+            for (int c = lane; c < IW; c += 32) in[r][c] = fm3d_u8f(src[reflect101_any(x0 + c - KP_KHALF, w)]);
+        }
     }
     __syncthreads();
-    // row pass, symmetric form k0 x0 + sum_i k_i (x_-i + x_+i) as cv::sepFilter2D's symmetric row filter
-    for (int i = tid; i < IH * BT_W; i += BT_NT) {
-        const int r = i / BT_W, c = i - r * BT_W;
-        const float* px = &in[r][c + KP_KHALF];
-        float s = __fmul_rn(A.kern[0], px[0]);
+    // row pass, symmetric form k0 x0 + sum_i k_i (x_-i + x_+i) as cv::sepFilter2D's symmetric row filter.  Register-tiled like
+    // K9's passes: four outputs per thread from four 16-byte loads instead of 13 loads per output (the kernel is bound by the
+    // shared-memory pipe and instruction issue, not by HBM: profiles/r01i_sift_base_4k_kernel_ncu_*).
+    for (int i = tid; i < IH * (BT_W / 4); i += BT_NT) {
+        const int r = i / (BT_W / 4), c4 = i - r * (BT_W / 4);
+        const float4* q = reinterpret_cast<const float4*>(&in[r][4 * c4]);
+        float v[16];
 #pragma unroll
-        for (int k = 1; k <= KP_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(px[-k], px[k]), s);
-        rowp[r][c] = s;
+        for (int k = 0; k < 4; k++) { const float4 t = q[k]; v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+        float4 o;
+        float* op = &o.x;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = __fmul_rn(A.kern[0], v[KP_KHALF + j]);
+#pragma unroll
+            for (int k = 1; k <= KP_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(v[KP_KHALF + j - k], v[KP_KHALF + j + k]), s);
+            op[j] = s;
+        }
+        *reinterpret_cast<float4*>(&rowp[r][4 * c4]) = o;
     }
     __syncthreads();
-    for (int i = tid; i < BT_H * BT_W; i += BT_NT) {
-        const int r = i / BT_W, c = i - r * BT_W;
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy >= h || gx >= w) continue;
-        float s = __fmul_rn(A.kern[0], rowp[r + KP_KHALF][c]);
+    // column pass: four consecutive rows per thread from 16 loads
+    for (int i = tid; i < (BT_H / 4) * BT_W; i += BT_NT) {
+        const int r4 = i / BT_W, c = i - r4 * BT_W;
+        const int gx = x0 + c;
+        float v[16];
 #pragma unroll
-        for (int k = 1; k <= KP_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(rowp[r + KP_KHALF - k][c], rowp[r + KP_KHALF + k][c]), s);
-        base[(size_t)gy * w + gx] = s;
+        for (int k = 0; k < 16; k++) v[k] = rowp[4 * r4 + k][c];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gy = y0 + 4 * r4 + j;
+            float s = __fmul_rn(A.kern[0], v[KP_KHALF + j]);
+#pragma unroll
+            for (int k = 1; k <= KP_KHALF; k++) s = fmaf(A.kern[k], __fadd_rn(v[KP_KHALF + j - k], v[KP_KHALF + j + k]), s);
+            if (gy < h && gx < w) base[(size_t)gy * w + gx] = s;
+        }
     }
 }
 
