@@ -14,8 +14,9 @@
 // Integer work, bit-exact against cv2.FastFeatureDetector (tests/golden/fast_keypoints.npz).
 //
 // Three small kernels: scores (one pixel per thread, 32 x 8 tiles with a 3-pixel halo staged in shared memory: every
-// image byte is read from HBM once, one score byte written per pixel), suppression + per-row counts, and an
-// order-preserving emit (one warp per row, ballot compaction behind the exclusive scan of the row counts).
+// image byte is read from HBM once, one score byte written per pixel), suppression + per-row counts + keep masks (one
+// bit per pixel), and an order-preserving emit (one warp per row walks the set bits of the row's mask words behind the
+// exclusive scan of the row counts).
 #include "fm3d_internal.cuh"
 
 namespace {
@@ -95,14 +96,20 @@ __device__ __forceinline__ bool fast_keep(const uint8_t* __restrict__ smap, int 
     return true;
 }
 
-// one warp per row: number of keypoints of the row
-__global__ void fast_count_kernel(const uint8_t* __restrict__ smap, int w, int h, int nonmax, int* __restrict__ row_count) {
+// one warp per row: number of keypoints of the row, and the keep decisions as one 32-bit mask per 32 pixels (the emit pass
+// reads the masks instead of repeating the 9-pixel suppression test)
+__global__ void fast_count_kernel(const uint8_t* __restrict__ smap, int w, int h, int nonmax, int* __restrict__ row_count,
+                                  unsigned* __restrict__ mask) {
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (y >= h) return;
+    const int mw = (w + 31) >> 5;
     int cnt = 0;
-    for (int x = lane; x < w; x += 32) cnt += fast_keep(smap, w, h, x, y, nonmax) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int x = x0 + lane;
+        const unsigned bal = __ballot_sync(0xffffffffu, x < w && fast_keep(smap, w, h, x, y, nonmax));
+        if (lane == 0) mask[(size_t)y * mw + (x0 >> 5)] = bal;
+        cnt += __popc(bal);
+    }
     if (lane == 0) row_count[y] = cnt;
 }
 
@@ -126,23 +133,31 @@ __global__ void __launch_bounds__(1024) fast_scan_kernel(const int* __restrict__
 }
 
 // one warp per row: keypoints in ascending x behind the row's offset
-__global__ void fast_emit_kernel(const uint8_t* __restrict__ smap, int w, int h, int nonmax, const int* __restrict__ row_off,
-                                 int max_kp, float* __restrict__ xy, float* __restrict__ response) {
+__global__ void fast_emit_kernel(const uint8_t* __restrict__ smap, const unsigned* __restrict__ mask, int w, int h, int nonmax,
+                                 const int* __restrict__ row_off, int max_kp, float* __restrict__ xy, float* __restrict__ response) {
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (y >= h) return;
+    const int mw = (w + 31) >> 5;
     int base = row_off[y];
-    for (int x0 = 0; x0 < w; x0 += 32) {
-        const int x = x0 + lane;
-        const bool keep = x < w && fast_keep(smap, w, h, x, y, nonmax);
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int o = base + __popc(bal & ((1u << lane) - 1u));
+    for (int m0 = 0; m0 < mw; m0 += 32) {
+        // 32 mask words per step; every lane then walks the set bits of the words in order
+        const unsigned mine = m0 + lane < mw ? mask[(size_t)y * mw + m0 + lane] : 0u;
+        int cnt = __popc(mine), off = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+        int o = base + off - cnt;                                   // exclusive prefix: first output slot of this lane's word
+        unsigned bits = mine;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int x = ((m0 + lane) << 5) + b;
             if (o < max_kp) {
                 xy[2 * o] = (float)x; xy[2 * o + 1] = (float)y;
                 response[o] = nonmax ? (float)((int)smap[(size_t)y * w + x] - 1) : 0.0f;
             }
+            o++;
         }
-        base += __popc(bal);
+        base += __shfl_sync(0xffffffffu, off, 31);
     }
 }
 
@@ -158,19 +173,21 @@ int fm3d_detect_fast_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int st
     threshold = threshold < 0 ? 0 : (threshold > 255 ? 255 : threshold);      // as cv::FAST clamps it
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     char* d = nullptr;
-    if (int rc = fm3d_scratch(ctx, 7, al((size_t)w * h) + 2 * al(sizeof(int) * (size_t)h), (void**)&d)) return rc;
+    const size_t bm = sizeof(unsigned) * (size_t)((w + 31) >> 5) * h;
+    if (int rc = fm3d_scratch(ctx, 7, al((size_t)w * h) + 2 * al(sizeof(int) * (size_t)h) + al(bm), (void**)&d)) return rc;
     uint8_t* smap = reinterpret_cast<uint8_t*>(d);
     int* row_count = reinterpret_cast<int*>(d + al((size_t)w * h));
     int* row_off = reinterpret_cast<int*>(d + al((size_t)w * h) + al(sizeof(int) * (size_t)h));
+    unsigned* mask = reinterpret_cast<unsigned*>(d + al((size_t)w * h) + 2 * al(sizeof(int) * (size_t)h));
     dim3 grid((w + FT_W - 1) / FT_W, (h + FT_H - 1) / FT_H);
     fast_score_kernel<<<grid, FT_W * FT_H, 0, ctx->stream>>>(img, w, h, stride, threshold, smap);
     FM3D_LAUNCH_CHECK(ctx);
-    fast_count_kernel<<<(h + 7) / 8, 256, 0, ctx->stream>>>(smap, w, h, nonmax ? 1 : 0, row_count);
+    fast_count_kernel<<<(h + 7) / 8, 256, 0, ctx->stream>>>(smap, w, h, nonmax ? 1 : 0, row_count, mask);
     FM3D_LAUNCH_CHECK(ctx);
     fast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(row_count, h, row_off, n_dev);
     FM3D_LAUNCH_CHECK(ctx);
     if (max_keypoints > 0) {
-        fast_emit_kernel<<<(h + 7) / 8, 256, 0, ctx->stream>>>(smap, w, h, nonmax ? 1 : 0, row_off, max_keypoints, xy, response);
+        fast_emit_kernel<<<(h + 7) / 8, 256, 0, ctx->stream>>>(smap, mask, w, h, nonmax ? 1 : 0, row_off, max_keypoints, xy, response);
         FM3D_LAUNCH_CHECK(ctx);
     }
     return FM3D_OK;
