@@ -29,7 +29,7 @@ SYMBOLS = [
     "fm3d_match_knn2_f32", "fm3d_match_knn2_hamming", "fm3d_match_nndr_f32",
     "fm3d_match_nndr_hamming", "fm3d_match_knn2_f32_dev", "fm3d_match_knn2_hamming_dev",
     "fm3d_nndr_filter_dev", "fm3d_triangulate", "fm3d_triangulate_dev", "fm3d_undistort_points",
-    "fm3d_set_images", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
+    "fm3d_set_images", "fm3d_set_images2", "fm3d_set_images_dev", "fm3d_get_pyramid_level", "fm3d_optimize_normals",
     "fm3d_optimize_normals_dev", "fm3d_evaluate_normals", "fm3d_get_normals_stats",
     "fm3d_sweep_normals", "fm3d_sweep_normals_dev",
     "fm3d_disc_pixels", "fm3d_plane_points", "fm3d_sample_pixels", "fm3d_project_to_image2",

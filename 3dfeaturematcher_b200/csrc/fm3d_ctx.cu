@@ -146,6 +146,14 @@ const char* fm3d_last_error(const fm3d_ctx* ctx) { return ctx ? ctx->err.c_str()
 int fm3d_sync(fm3d_ctx* ctx) {
     if (!ctx) return FM3D_ERR_INVALID_ARG;
     FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->normals_flag_pending && ctx->scratch[1]) {
+        // the device-resident normal search reports a timed-out TMA window load here (the host-buffer entry point
+        // reports it itself): the results are valid, taken through the global-memory sampler, but slow
+        ctx->normals_flag_pending = false;
+        int flags[2] = {0, 0};
+        FM3D_CUDA(ctx, cudaMemcpy(flags, ctx->scratch[1], sizeof(flags), cudaMemcpyDeviceToHost));
+        if (flags[1]) return fm3d_fail(ctx, FM3D_ERR_CUDA, "normal optimiser: a TMA window load timed out (results used the global-memory path)");
+    }
     return FM3D_OK;
 }
 

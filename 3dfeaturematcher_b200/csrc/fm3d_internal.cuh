@@ -68,6 +68,9 @@ struct fm3d_ctx {
     // counters
     int64_t n_launch = 0, n_copy = 0;
     int n_matcher_exact_fallback = 0;   // queries the last filtered float match handed to the exact path
+    // an asynchronous (_dev) normal search was launched since the last fm3d_sync: its TMA-timeout flag (scratch[1][1])
+    // has not been looked at yet
+    bool normals_flag_pending = false;
 };
 
 // ---------------------------------------------------------------- error plumbing

@@ -636,6 +636,7 @@ int fm3d_optimize_normals_dev(fm3d_ctx* ctx, const double* xyz, int n, int pixel
     A.xyz = xyz; A.n = n; A.r = pixels_ray; A.eps_lmmin = epsilon_lmmin; A.penalty_mode = penalty_mode;
     A.mode = 0;
     A.normals = normals; A.status = status; A.nfev = nfev; A.npenalty = npenalty; A.cost = cost;
+    ctx->normals_flag_pending = true;       // looked at by fm3d_sync (or by the host-buffer entry point below)
     return run_normals(ctx, A);
 }
 
@@ -667,6 +668,7 @@ int fm3d_optimize_normals(fm3d_ctx* ctx, const double* xyz, int n, int pixels_ra
     int flags[2] = {0, 0};
     if (int r2 = fm3d_d2h(ctx, flags, ctx->scratch[1], sizeof(flags))) return r2;
     FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->normals_flag_pending = false;
     if (flags[1]) return fm3d_fail(ctx, FM3D_ERR_CUDA, "normal optimiser: a TMA window load timed out (results used the global-memory path)");
     return FM3D_OK;
 }

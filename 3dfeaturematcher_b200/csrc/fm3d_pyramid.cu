@@ -109,7 +109,9 @@ int layout_pyramid(fm3d_ctx* ctx, int w, int h, int levels) {
 
 int build_levels(fm3d_ctx* ctx) {
     fm3d_pyramid_desc& P = ctx->pyr;
-    // the pad bytes of every row are zeroed once so that 32-bit tile stores never leave garbage
+    // rows are pitched to 16 bytes; the pad bytes of level 0 are whatever cudaMalloc left there and those of the other
+    // levels whatever the 32-bit tile stores put there: every reader (this kernel, the TMA tensor maps, the samplers) is
+    // bounded by the level's width, so they are never read
     for (int l = 1; l <= P.levels; l++) {
         const fm3d_level& s = P.lv[l - 1];
         const fm3d_level& d = P.lv[l];
@@ -123,10 +125,10 @@ int build_levels(fm3d_ctx* ctx) {
     return FM3D_OK;
 }
 
-int set_images_common(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int w, int h, int stride,
+int set_images_common(fm3d_ctx* ctx, const uint8_t* img1, int stride1, const uint8_t* img2, int stride2, int w, int h,
                       int pyramids, cudaMemcpyKind kind) {
     if (!ctx) return FM3D_ERR_INVALID_ARG;
-    FM3D_CHECK_ARG(ctx, img1 && img2 && w > 0 && h > 0 && stride >= w);
+    FM3D_CHECK_ARG(ctx, img1 && img2 && w > 0 && h > 0 && stride1 >= w && stride2 >= w);
     FM3D_CHECK_ARG(ctx, pyramids >= 0 && pyramids < FM3D_MAX_LEVELS);
     if (int rc = fm3d_bind(ctx)) return rc;
     ctx->has_images = false;
@@ -135,7 +137,7 @@ int set_images_common(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, i
     for (int k = 0; k < 2; k++) {
         uint8_t* d = const_cast<uint8_t*>(ctx->pyr.base[k]) + l0.off;
         ctx->n_copy++;
-        FM3D_CUDA(ctx, cudaMemcpy2DAsync(d, l0.pitch, k ? img2 : img1, stride, w, h, kind, ctx->stream));
+        FM3D_CUDA(ctx, cudaMemcpy2DAsync(d, l0.pitch, k ? img2 : img1, k ? stride2 : stride1, w, h, kind, ctx->stream));
     }
     return build_levels(ctx);
 }
@@ -146,7 +148,15 @@ extern "C" {
 
 int fm3d_set_images(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int w, int h, int stride,
                     int pyramids) {
-    int rc = set_images_common(ctx, img1, img2, w, h, stride, pyramids, cudaMemcpyHostToDevice);
+    int rc = set_images_common(ctx, img1, stride, img2, stride, w, h, pyramids, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
+
+int fm3d_set_images2(fm3d_ctx* ctx, const uint8_t* img1, int stride1, const uint8_t* img2, int stride2, int w, int h,
+                     int pyramids) {
+    int rc = set_images_common(ctx, img1, stride1, img2, stride2, w, h, pyramids, cudaMemcpyHostToDevice);
     if (rc) return rc;
     FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FM3D_OK;
@@ -154,7 +164,7 @@ int fm3d_set_images(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int
 
 int fm3d_set_images_dev(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int w, int h,
                         int stride, int pyramids) {
-    return set_images_common(ctx, img1, img2, w, h, stride, pyramids, cudaMemcpyDeviceToDevice);
+    return set_images_common(ctx, img1, stride, img2, stride, w, h, pyramids, cudaMemcpyDeviceToDevice);
 }
 
 int fm3d_get_pyramid_level(fm3d_ctx* ctx, int image, int level, uint8_t* out, int* w, int* h) {

@@ -159,6 +159,18 @@ DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv
     adaptive_min_ = (int)fs["FeatureOptions"]["Adaptive"]["MinFeatures"];                     // :194-197
     adaptive_max_ = (int)fs["FeatureOptions"]["Adaptive"]["MaxFeatures"];
     adaptive_iters_ = (int)fs["FeatureOptions"]["Adaptive"]["MaxIters"];
+    // generateExtractor (descriptorsmatcher.cpp:291-359).  Of the constructor arguments the reference reads from the settings,
+    // only cv::SIFT's NumOctaveLayers and Sigma change what compute() returns for provided octave-0 keypoints (NumFeatures /
+    // ContrastThreshold / EdgeThreshold act in detect(); cv::ORB's ScaleFactor / NumLevels only on keypoints of octave > 0;
+    // cv::BRISK::compute uses neither Threshold nor Octaves).  The SIFT kernels (K9, K11) are built for 3 layers, sigma 1.6:
+    // a settings file that asks for something else gets an error, not silently different descriptors.
+    if (extractorType == "SIFT" && !fs["FeatureOptions"]["SiftDetector"].empty()) {
+        const cv::FileNode sd = fs["FeatureOptions"]["SiftDetector"];
+        if (!sd["Sigma"].empty() && std::fabs((double)sd["Sigma"] - 1.6) > 1e-12)
+            throw std::runtime_error("fm3d: FeatureOptions.SiftDetector.Sigma must be 1.6 (the SIFT kernels are built for it)");
+        if (!sd["NumOctaveLayers"].empty() && (int)sd["NumOctaveLayers"] != 3)
+            throw std::runtime_error("fm3d: FeatureOptions.SiftDetector.NumOctaveLayers must be 3 (the SIFT kernels are built for it)");
+    }
     host_ctx();
 }
 
@@ -171,8 +183,15 @@ void DescriptorsMatcher::setFeatures(const std::vector<cv::KeyPoint>& ka, const 
 }
 
 void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv::KeyPoint>& kb, cv::Mat& da, cv::Mat& db) {
-    if (have_features_) { ka = kpts_a_; kb = kpts_b_; da = desc_a_; db = desc_b_; return; }
-    if (!da.empty() && !db.empty()) return;  // pre-filled by the caller
+    // Injected features (setFeatures) are the only way around detection: like the reference (descriptorsmatcher.cpp:110-115)
+    // every call otherwise re-detects and OVERWRITES the four output arguments, whatever a previous call left in them.
+    if (have_features_) {
+        if ((int)kpts_a_.size() != desc_a_.rows || (int)kpts_b_.size() != desc_b_.rows)
+            throw std::runtime_error("fm3d: setFeatures needs one descriptor row per keypoint (" + std::to_string(kpts_a_.size()) + " / " +
+                                     std::to_string(desc_a_.rows) + ", " + std::to_string(kpts_b_.size()) + " / " + std::to_string(desc_b_.rows) + ")");
+        ka = kpts_a_; kb = kpts_b_; da = desc_a_; db = desc_b_;
+        return;
+    }
     // descriptorsmatcher.cpp:110-115: detect on both frames, then compute on both frames.  DetectorType FAST
     // (STATIC) with ExtractorType SIFT, BRISK or ORB runs on the GPU (K10 + K11 / K12 / K13); the other detectors /
     // extractors of the reference (SURF, STAR, MSER, FREAK, ORB's own detector) are upstream code this library does not carry.
@@ -391,10 +410,18 @@ SingleCameraTriangulator::SingleCameraTriangulator(cv::FileStorage& settings)
 }
 
 void SingleCameraTriangulator::setImages(const cv::Mat& img1, const cv::Mat& img2) {
+    // The reference keeps each image at its own size and step (:116-120); the device pyramids need two CV_8UC1 frames of
+    // one size.  Each image is uploaded with ITS OWN row pitch (a ROI or a padded frame has step1() != cols).
+    if (img1.empty() || img2.empty() || img1.type() != CV_8UC1 || img2.type() != CV_8UC1)
+        throw std::runtime_error("fm3d: setImages needs two non-empty CV_8UC1 images");
+    if (img1.cols != img2.cols || img1.rows != img2.rows)
+        throw std::runtime_error("fm3d: setImages needs two images of one size (" + std::to_string(img1.cols) + "x" + std::to_string(img1.rows) +
+                                 " / " + std::to_string(img2.cols) + "x" + std::to_string(img2.rows) + ")");
     img_1_ = img1; img_2_ = img2;  // shallow, like new cv::Mat(img) in the reference (:118-119)
     const int levels = pyramids_;
+    const int s1 = (int)img1.step1(), s2 = (int)img2.step1();   // CV_8UC1: elements = bytes; step1() exists in cv::Mat and in the stand-in
     for_each_ctx("set_images", [&](int k) {
-        return fm3d_set_images(host_ctxs()[k], img1.data, img2.data, img1.cols, img1.rows, (int)img1.step1(), levels);   // CV_8UC1: elements = bytes; step1() exists in cv::Mat and in the stand-in
+        return fm3d_set_images2(host_ctxs()[k], img1.data, s1, img2.data, s2, img1.cols, img1.rows, levels);
     });
 }
 
@@ -636,6 +663,9 @@ void SingleCameraTriangulator::projectPointsAndComputeResidual(const std::vector
 // ------------------------------------------------------------------------------ NormalOptimizer
 NormalOptimizer::NormalOptimizer(const cv::FileStorage settings, SingleCameraTriangulator* sct)
     : sct_(sct), penalty_mode_(FM3D_PENALTY_FABS) {
+    // abs() semantics of the penalty wall (normaloptimizer.cpp:126-142): fabs, what today's g++ makes of the
+    // source, unless the environment says otherwise -- the unchanged main.cpp has no other way to choose
+    if (const char* e = getenv("FM3D_PENALTY")) penalty_mode_ = atoi(e);
     settings["Neighborhoods"]["pyramids"] >> pyr_levels_;
     settings["Neighborhoods"]["epsilonLMMIN"] >> epsilon_lmmin_;
     std::vector<double> rIC;

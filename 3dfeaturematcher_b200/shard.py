@@ -104,3 +104,84 @@ def unpack_packed(out: torch.Tensor, layout):
             chunks.append(blk[:all_counts[r][i]])
         res.append(torch.cat(chunks, dim=0))
     return res, all_counts
+
+
+# ------------------------------------------------------------------ one broadcast, one gather per step
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class ReplicatedBuffer:
+    """The inputs every rank needs in full (train descriptors, train keypoints, both frames) as views into ONE device
+    allocation, so that a step replicates them with ONE broadcast instead of one per tensor."""
+
+    def __init__(self, specs, device):
+        """specs: list of (name, shape, torch dtype)."""
+        self.views, off = {}, 0
+        layout = []
+        for name, shape, dtype in specs:
+            nbytes = int(torch.tensor([], dtype=dtype).element_size())
+            for s in shape:
+                nbytes *= int(s)
+            layout.append((name, shape, dtype, off, nbytes))
+            off = _align(off + nbytes)
+        self.buf = torch.zeros(max(off, 1), dtype=torch.uint8, device=device)
+        for name, shape, dtype, o, nbytes in layout:
+            self.views[name] = self.buf[o:o + nbytes].view(dtype).reshape(shape)
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+    def broadcast_(self, src: int = 0):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.buf, src=src)
+
+
+class ShardGather:
+    """All per-shard results of a step in ONE all-gather with nothing on the host: every rank copies its header (the two
+    device-resident counts) and the first `cap` rows of every part into a preallocated send block with device-side copies,
+    then `all_gather_into_tensor` fills a preallocated (world, block) buffer.  `unpack` (outside any timed region) gives the
+    valid rows of all ranks in rank order = ascending global query index."""
+
+    HEADER = 256
+
+    def __init__(self, parts, cap, device, rank=0):
+        """parts: list of (name, row shape tuple, torch dtype, index of the count it is valid up to)."""
+        self.parts, self.cap = parts, int(cap)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        off = self.HEADER
+        self.layout = []
+        for name, row, dtype, which in parts:
+            nbytes = int(torch.tensor([], dtype=dtype).element_size()) * self.cap
+            for s in row:
+                nbytes *= int(s)
+            self.layout.append((name, row, dtype, which, off, nbytes))
+            off = _align(off + nbytes)
+        self.block = off
+        self.send = torch.zeros(self.block, dtype=torch.uint8, device=device)
+        self.recv = torch.zeros((self.world, self.block), dtype=torch.uint8, device=device)
+        self._hdr = self.send[:16].view(torch.int32)        # 4 x int32: counts[0], counts[1], rank, cap
+        self._hdr[2:4] = torch.tensor([rank, self.cap], dtype=torch.int32)      # once, at construction
+
+    def gather(self, tensors, counts_dev):
+        """tensors: dict name -> device tensor with >= cap rows; counts_dev: two 1-element int32 device tensors."""
+        self._hdr[0:1].copy_(counts_dev[0])
+        self._hdr[1:2].copy_(counts_dev[1])
+        for name, row, dtype, which, off, nbytes in self.layout:
+            self.send[off:off + nbytes].view(dtype).reshape((self.cap,) + tuple(row)).copy_(tensors[name][:self.cap])
+        if self.world == 1:
+            self.recv[0].copy_(self.send)
+        else:
+            dist.all_gather_into_tensor(self.recv.view(-1), self.send)
+        return self.recv
+
+    def unpack(self):
+        hdr = self.recv[:, :16].contiguous().view(torch.int32).reshape(self.world, 4).cpu().numpy()
+        out = {}
+        for name, row, dtype, which, off, nbytes in self.layout:
+            chunks = []
+            for r in range(self.world):
+                blk = self.recv[r, off:off + nbytes].clone().view(dtype).reshape((self.cap,) + tuple(row))
+                chunks.append(blk[:int(hdr[r, which])])
+            out[name] = torch.cat(chunks, 0)
+        return out, hdr[:, :2].tolist()

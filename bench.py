@@ -45,6 +45,9 @@ PENALTY_NAMES = {0: "fabs", 1: "int_abs", 2: "off"}
 FLOP_PER_PIXEL_EVAL = 64.0    # algorithmic fp32 work of one pixel evaluation
 FLOP_PER_PIXEL_JAC = 152.0    # the same plus its analytic derivatives w.r.t. (phi, theta)
 SEED = 1001
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of normals_fast_kernel on this workload (ncu --set full)
+NORMALS_TRAFFIC_BYTES = 0.8902e9
+NORMALS_TRAFFIC_SOURCE = "profiles/r01f_normals_fast_kernel_ncu_raw_selected.csv: 199 MB read + 691 MB written, the ray scratch leaving L2"
 
 
 def log(*a):
@@ -199,27 +202,229 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "features/sec (match+triangulate+normal-opt)", "value": v, "unit": "features/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(t_all)),
         "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(1),
+        "config": workload_config(1, impl="reference"),
         "cpu_baseline": {"value": v, "unit": "features/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(out)
 
 
-def workload_config(n_ranks):
-    return {"workload": f"BASELINE configs[{2 if WORKLOAD == 'c3' else 1}]: {WIDTH}x{HEIGHT} synthetic stereo pair, {N_KP} SIFT-128 float keypoints per GPU "
-                        f"(+{N_DISTRACT} distractors), pixelsRay {PIXELS_RAY}, pyramids {PYRAMIDS} (4 LM stages), NNDR {NNDR_EPS}",
-            "penalty_mode": PENALTY_NAMES[PENALTY], "normal_search": "fast kernel: fp32 offset-form geometry, analytic Jacobian, fp64 LM state",
-            "per_gpu_query_keypoints": N_KP, "global_query_keypoints": N_KP * n_ranks,
-            "parallelism": f"keypoint shards x{n_ranks}", "l2_flush_between_steps": True}
+def workload_config(n_ranks, impl="fm3d"):
+    cfg = {"workload": f"BASELINE configs[{2 if WORKLOAD == 'c3' else 1}]: {WIDTH}x{HEIGHT} synthetic stereo pair, {N_KP} SIFT-128 float keypoints per GPU "
+                       f"(+{N_DISTRACT} distractors), pixelsRay {PIXELS_RAY}, pyramids {PYRAMIDS} (4 LM stages), NNDR {NNDR_EPS}",
+           "penalty_mode": PENALTY_NAMES[PENALTY],
+           "per_gpu_query_keypoints": N_KP, "global_query_keypoints": N_KP * n_ranks,
+           "parallelism": f"keypoint shards x{n_ranks}"}
+    if impl == "reference":
+        cfg["normal_search"] = ("CPU port of the reference (oracle/fm3d_oracle.c): fp64 geometry, forward-difference Jacobian, "
+                                "lmfit restatement, OpenMP over features")
+    else:
+        cfg["normal_search"] = ("fast kernel: fp32 offset-form geometry, analytic Jacobian, fp64 LM state (the fp64 / forward-difference "
+                                "kernel is timed next to it as `faithful_fp64`)")
+        cfg["l2_flush_between_steps"] = True
+    return cfg
 
 
 # ------------------------------------------------------------------------------- GPU arm
+class PathState:
+    """Device buffers of one workload and one pass of the hot path over them (all work on the context's stream)."""
+
+    N_STAGE = 5
+    STAGES = ("match+nndr", "triangulate", "pyramids", "normals", "gather")
+
+    def __init__(self, torch, api, shard, ctx, stream, dev, case, world, rank, pixels_ray, pyramids):
+        self.torch, self.shard, self.ctx, self.stream, self.dev = torch, shard, ctx, stream, dev
+        self.case, self.world, self.rank, self.r, self.pyramids = case, world, rank, pixels_ray, pyramids
+        self.cam = case["scene"].cam
+        self.H, self.W = case["scene"].img1.shape
+        nq_glob, self.nt = case["desc1"].shape[0], case["desc2"].shape[0]
+        self.lo, self.hi = shard.shard_bounds(nq_glob, world, rank)
+        self.nq = nq = self.hi - self.lo
+        self.L1 = pyramids + 1
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()      # noqa: E731
+        # pinned host copies (e2e arm)
+        self.h_q, self.h_t = pin(case["desc1"][self.lo:self.hi]), pin(case["desc2"])
+        self.h_kp1, self.h_kp2 = pin(case["kp1"][self.lo:self.hi]), pin(case["kp2"])
+        self.h_img1, self.h_img2 = pin(case["scene"].img1), pin(case["scene"].img2)
+        with torch.cuda.stream(stream):
+            self.d_q, self.d_kp1 = self.h_q.to(dev), self.h_kp1.to(dev)
+            # replicated inputs live in ONE allocation: one broadcast per step; only rank 0's copy is filled
+            self.rep = shard.ReplicatedBuffer([("t", (self.nt, 128), torch.float32), ("kp2", (self.nt, 2), torch.float32),
+                                               ("img1", (self.H, self.W), torch.uint8), ("img2", (self.H, self.W), torch.uint8)], dev)
+            if rank == 0 or world == 1:
+                self.rep["t"].copy_(self.h_t); self.rep["kp2"].copy_(self.h_kp2)
+                self.rep["img1"].copy_(self.h_img1); self.rep["img2"].copy_(self.h_img2)
+            i32, f32, f64 = torch.int32, torch.float32, torch.float64
+            self.d_idx = torch.empty((nq, 2), dtype=i32, device=dev)
+            self.d_dist = torch.empty((nq, 2), dtype=f32, device=dev)
+            self.d_qi, self.d_ti = torch.zeros(nq, dtype=i32, device=dev), torch.zeros(nq, dtype=i32, device=dev)
+            self.d_do = torch.zeros(nq, dtype=f32, device=dev)
+            self.d_nm = torch.zeros(1, dtype=i32, device=dev)
+            self.d_xyz_all = torch.empty((nq, 3), dtype=f64, device=dev)
+            self.d_xyz = torch.zeros((nq, 3), dtype=f64, device=dev)
+            self.d_mask = torch.empty(nq, dtype=torch.uint8, device=dev)
+            self.d_src = torch.zeros(nq, dtype=i32, device=dev)
+            self.d_ninl = torch.zeros(1, dtype=i32, device=dev)
+            self.d_normals = torch.zeros((nq, 3), dtype=f64, device=dev)
+            self.d_status = torch.zeros(nq, dtype=i32, device=dev)
+            self.d_nfev = torch.zeros((nq, self.L1), dtype=i32, device=dev)
+            self.d_npen = torch.zeros(nq, dtype=i32, device=dev)
+            self.d_cost = torch.empty(nq, dtype=f64, device=dev)
+            # ONE all-gather per step: (query, train, distance) of the matches; (match row, normal, status) of the inliers
+            cap = max(shard.shard_sizes(nq_glob, world))
+            self.gatherer = shard.ShardGather([("qi", (), i32, 0), ("ti", (), i32, 0), ("d", (), f32, 0), ("src", (), i32, 1),
+                                               ("normals", (3,), f64, 1), ("status", (), i32, 1)], cap, dev, rank)
+            self.cap = cap
+            if cap > nq:        # ragged last shard: the gather reads `cap` rows of every part
+                grow = lambda t: torch.cat([t, torch.zeros((cap - nq,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)])   # noqa: E731
+                self.d_qi, self.d_ti, self.d_do, self.d_src = grow(self.d_qi), grow(self.d_ti), grow(self.d_do), grow(self.d_src)
+                self.d_normals, self.d_status = grow(self.d_normals), grow(self.d_status)
+        stream.synchronize()
+
+    def bind(self):
+        self.ctx.set_camera(self.cam.K, self.cam.dist, self.cam.z_min, self.cam.z_max)
+        self.ctx.set_g12(self.cam.g12)
+
+    def device_step(self, events=None, penalty=PENALTY):
+        """One pass of the hot path on resident inputs."""
+        torch, ctx, stream = self.torch, self.ctx, self.stream
+        with torch.cuda.stream(stream):
+            if events: events[0].record(stream)
+            self.rep.broadcast_(0)
+            ctx.match_knn2_f32_dev(self.d_q.data_ptr(), self.nq, self.rep["t"].data_ptr(), self.nt, 128, self.d_idx.data_ptr(), self.d_dist.data_ptr())
+            ctx.nndr_filter_dev(self.d_idx.data_ptr(), self.d_dist.data_ptr(), self.nq, NNDR_EPS, self.d_qi.data_ptr(), self.d_ti.data_ptr(),
+                                self.d_do.data_ptr(), self.d_nm.data_ptr())
+            if events: events[1].record(stream)
+            n_match = int(self.d_nm.item())          # sizes the following launches (4-byte D2H, as a host caller needs)
+            ctx.triangulate_dev(self.d_kp1.data_ptr(), self.nq, self.rep["kp2"].data_ptr(), self.nt, self.d_qi.data_ptr(), self.d_ti.data_ptr(), n_match,
+                                self.d_xyz_all.data_ptr(), self.d_mask.data_ptr(), self.d_xyz.data_ptr(), self.d_src.data_ptr(), self.d_ninl.data_ptr())
+            if events: events[2].record(stream)
+            ctx.set_images_dev(self.rep["img1"].data_ptr(), self.rep["img2"].data_ptr(), self.W, self.H, self.W, self.pyramids)
+            if events: events[3].record(stream)
+            n_inl = int(self.d_ninl.item())
+            ctx.optimize_normals_dev(self.d_xyz.data_ptr(), n_inl, self.r, EPS_LMMIN, penalty, self.d_normals.data_ptr(),
+                                     self.d_status.data_ptr(), self.d_nfev.data_ptr(), self.d_npen.data_ptr(), self.d_cost.data_ptr())
+            if events: events[4].record(stream)
+            self.gatherer.gather({"qi": self.d_qi, "ti": self.d_ti, "d": self.d_do, "src": self.d_src, "normals": self.d_normals,
+                                  "status": self.d_status}, (self.d_nm, self.d_ninl))
+            if events: events[5].record(stream)
+        return n_match, n_inl
+
+    def host_step(self):
+        """The same pass through the host-buffer C-ABI entry points (copies inside)."""
+        ctx = self.ctx
+        if self.world > 1:
+            with self.torch.cuda.stream(self.stream):
+                self.rep.broadcast_(0)
+            self.stream.synchronize()
+        qi, ti, d = ctx.match_nndr(self.h_q.numpy(), self.h_t.numpy(), NNDR_EPS)
+        xyz_all, mask, xyz, src = ctx.triangulate(self.h_kp1.numpy(), self.h_kp2.numpy(), qi, ti)
+        ctx.set_images(self.h_img1.numpy(), self.h_img2.numpy(), self.pyramids)
+        res = ctx.optimize_normals(xyz, self.r, EPS_LMMIN, PENALTY)
+        h2d = (self.h_q.numel() + self.h_t.numel()) * 4 + (self.h_kp1.numel() + self.h_kp2.numel()) * 4 + qi.nbytes + ti.nbytes + \
+            self.h_img1.numel() + self.h_img2.numel() + xyz.nbytes
+        d2h = qi.nbytes + ti.nbytes + d.nbytes + xyz_all.nbytes + mask.nbytes + xyz.nbytes + src.nbytes + \
+            res["normals"].nbytes + res["status"].nbytes + res["nfev"].nbytes + res["npenalty"].nbytes + res["cost"].nbytes
+        return len(qi), xyz.shape[0], h2d, d2h
+
+    def timed(self, steps, flush_l2, barrier, penalty=PENALTY, warm=2):
+        """`steps` device passes with CUDA events per stage; returns (ms per stage summed over steps, last n_match, n_inl)."""
+        torch = self.torch
+        for _ in range(warm):
+            self.device_step(penalty=penalty)
+            flush_l2()
+        barrier()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(self.N_STAGE + 1)] for _ in range(steps)]
+        for s in range(steps):
+            n_match, n_inl = self.device_step(ev[s], penalty=penalty)
+            flush_l2()                      # not between events 0..5 of a step: excluded from the step time
+        barrier()
+        stage_ms = np.zeros(self.N_STAGE)
+        for s in range(steps):
+            for j in range(self.N_STAGE):
+                stage_ms[j] += ev[s][j].elapsed_time(ev[s][j + 1])
+        return stage_ms, n_match, n_inl
+
+    def check_gathered(self, penalty, n_query_sample=2048, n_normal_sample=64):
+        """CONTENT check of what the step gathered from all ranks (rank 0, outside any timed region): the matches of a
+        seeded sample of global query indices must be exactly the CPU oracle's (indices and distances bit for bit), and
+        the normals / statuses of a seeded sample of gathered inliers, spread over all ranks, must agree with the CPU
+        oracle's normal search on the oracle's own triangulation of those matches (status equal, <= 0.5 deg where the
+        oracle stays off the penalty wall)."""
+        from oracle import oracle_c as orc
+        shard, case, cam = self.shard, self.case, self.cam
+        out, counts = self.gatherer.unpack()
+        los = [shard.shard_bounds(case["desc1"].shape[0], self.world, r)[0] for r in range(self.world)]
+        qi = out["qi"].cpu().numpy().astype(np.int64)
+        ti, dd = out["ti"].cpu().numpy(), out["d"].cpu().numpy()
+        rank_of_match = np.repeat(np.arange(self.world), [c[0] for c in counts])
+        q_glob = qi + np.asarray(los)[rank_of_match]
+        if not (np.diff(q_glob) > 0).all():
+            return "gathered query indices are not ascending"
+        rng = np.random.default_rng(11)
+        nq_glob = case["desc1"].shape[0]
+        sel = np.sort(rng.choice(nq_glob, min(n_query_sample, nq_glob), replace=False))
+        o_idx, o_dist = orc.knn2_f32(case["desc1"][sel], case["desc2"], threads=os.cpu_count() or 1)
+        oq, ot, od = orc.nndr_filter(o_idx, o_dist, NNDR_EPS)
+        in_sel = np.isin(q_glob, sel)
+        if not (np.array_equal(q_glob[in_sel], sel[oq]) and np.array_equal(ti[in_sel], ot) and np.array_equal(dd[in_sel], od)):
+            return f"matches of the sampled queries differ from the oracle ({int(in_sel.sum())} gathered, {len(oq)} expected)"
+        # normals: inlier k of rank r refers to match row src[k] of rank r
+        src = out["src"].cpu().numpy().astype(np.int64)
+        normals, status = out["normals"].cpu().numpy(), out["status"].cpu().numpy()
+        rank_of_inl = np.repeat(np.arange(self.world), [c[1] for c in counts])
+        match_base = np.concatenate([[0], np.cumsum([c[0] for c in counts])])[:-1]
+        row = src + match_base[rank_of_inl]                       # row in the gathered match list
+        pick = np.sort(rng.choice(len(row), min(n_normal_sample, len(row)), replace=False))
+        mq, mt = q_glob[row[pick]], ti[row[pick]].astype(np.int64)
+        _, o_mask, o_xyz = orc.triangulate(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["kp1"], case["kp2"],
+                                           mq.astype(np.int32), mt.astype(np.int32))
+        if not o_mask.astype(bool).all():
+            return "a gathered inlier is outside the oracle's depth gate"
+        o = orc.optimize_normals(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                                 self.pyramids, o_xyz, self.r, EPS_LMMIN, penalty_mode=penalty, threads=os.cpu_count() or 1)
+        if not np.array_equal(o["status"], status[pick]):
+            return "statuses of the sampled normals differ from the oracle"
+        interior = (o["status"] == 0) & (o["npenalty"] == 0)
+        cosang = np.clip((normals[pick] * o["normals"]).sum(1), -1, 1)
+        ang = np.degrees(np.arccos(cosang))
+        if interior.any() and ang[interior].max() > 0.5:
+            return f"normals differ from the oracle by {ang[interior].max():.3f} deg"
+        return {"result": "ok", "ranks_with_matches": int(sum(c[0] > 0 for c in counts)), "queries_checked": int(len(sel)),
+                "matches_checked": int(in_sel.sum()), "normals_checked": int(len(pick)),
+                "normals_interior": int(interior.sum()), "max_angle_deg_interior": float(ang[interior].max()) if interior.any() else None,
+                "ranks_in_normal_sample": int(len(np.unique(rank_of_inl[pick])))}
+
+
+def oracle_agreement_fabs(st, n_sample=96):
+    """`penalty_fabs.oracle_agreement`: a seeded sample of THIS rank's inliers of the fabs step against the CPU oracle in the
+    same mode: statuses, and how many wall features end within 0.5 deg of the oracle's end state."""
+    from oracle import oracle_c as orc
+    cam, case = st.cam, st.case
+    n_inl = int(st.d_ninl.item())
+    xyz = st.d_xyz[:n_inl].cpu().numpy()
+    normals, status = st.d_normals[:n_inl].cpu().numpy(), st.d_status[:n_inl].cpu().numpy()
+    rng = np.random.default_rng(13)
+    pick = np.sort(rng.choice(n_inl, min(n_sample, n_inl), replace=False))
+    o = orc.optimize_normals(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                             st.pyramids, np.ascontiguousarray(xyz[pick]), st.r, EPS_LMMIN, penalty_mode=PENALTY_ALT, threads=os.cpu_count() or 1)
+    ok = o["status"] == 0
+    wall = ok & (o["npenalty"] > 0)
+    ang = np.degrees(np.arccos(np.clip((normals[pick] * o["normals"]).sum(1), -1, 1)))
+    return {"features": int(len(pick)), "status_equal": bool(np.array_equal(o["status"], status[pick])),
+            "wall_features": int(wall.sum()), "wall_within_0p5_deg": float((ang[wall] <= 0.5).mean()) if wall.any() else None,
+            "wall_angle_deg_p50": float(np.median(ang[wall])) if wall.any() else None,
+            "wall_angle_deg_p95": float(np.percentile(ang[wall], 95)) if wall.any() else None,
+            "interior_features": int((ok & ~wall).sum()),
+            "interior_max_angle_deg": float(ang[ok & ~wall].max()) if (ok & ~wall).any() else None}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     api = importlib.import_module("3dfeaturematcher_b200.api")
     shard = importlib.import_module("3dfeaturematcher_b200.shard")
+    synth = importlib.import_module("3dfeaturematcher_b200.synth")
     if not os.path.exists(api.LIB_PATH) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
         # the library normally travels with the tree; nvcc is in the image if it does not
         importlib.import_module("3dfeaturematcher_b200.build").build()
@@ -238,96 +443,13 @@ def run_gpu_arm(args):
     info = ctx.device_info()
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     case = make_workload(world, rank)
-    cam = case["scene"].cam
-    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
-    ctx.set_g12(cam.g12)
-    H, W = case["scene"].img1.shape
-    nq_glob, nt = case["desc1"].shape[0], case["desc2"].shape[0]
-    lo, hi = shard.shard_bounds(nq_glob, world, rank)
-    nq = hi - lo
-    L1 = PYRAMIDS + 1
-
-    # ---- pinned host copies (e2e arm) and resident device copies (value arm)
-    def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
-    h_q, h_t = pin(case["desc1"][lo:hi]), pin(case["desc2"])
-    h_kp1, h_kp2 = pin(case["kp1"][lo:hi]), pin(case["kp2"])
-    h_img1, h_img2 = pin(case["scene"].img1), pin(case["scene"].img2)
+    st = PathState(torch, api, shard, ctx, stream, dev, case, world, rank, PIXELS_RAY, PYRAMIDS)
+    st.bind()
+    H, W, nq, nt, L1 = st.H, st.W, st.nq, st.nt, st.L1
     with torch.cuda.stream(stream):
-        d_q, d_kp1 = h_q.to(dev), h_kp1.to(dev)
-        # replicated inputs: only rank 0's copy is meaningful before the broadcast
-        d_t, d_kp2, d_img1, d_img2 = h_t.to(dev), h_kp2.to(dev), h_img1.to(dev), h_img2.to(dev)
-        if rank != 0 and world > 1:
-            for x in (d_t, d_kp2, d_img1, d_img2):
-                x.zero_()
-        d_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
-        d_dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
-        d_qi = torch.empty(nq, dtype=torch.int32, device=dev)
-        d_ti = torch.empty(nq, dtype=torch.int32, device=dev)
-        d_do = torch.empty(nq, dtype=torch.float32, device=dev)
-        d_nm = torch.zeros(1, dtype=torch.int32, device=dev)
-        d_xyz_all = torch.empty((nq, 3), dtype=torch.float64, device=dev)
-        d_xyz = torch.empty((nq, 3), dtype=torch.float64, device=dev)
-        d_mask = torch.empty(nq, dtype=torch.uint8, device=dev)
-        d_src = torch.empty(nq, dtype=torch.int32, device=dev)
-        d_ninl = torch.zeros(1, dtype=torch.int32, device=dev)
-        d_normals = torch.empty((nq, 3), dtype=torch.float64, device=dev)
-        d_status = torch.empty(nq, dtype=torch.int32, device=dev)
-        d_nfev = torch.zeros((nq, L1), dtype=torch.int32, device=dev)
-        d_npen = torch.zeros(nq, dtype=torch.int32, device=dev)
-        d_cost = torch.empty(nq, dtype=torch.float64, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream.synchronize()
-
-    n_stage = 5
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_stage + 1)] for _ in range(args.steps)]
-
-    def device_step(events=None, penalty=PENALTY):
-        """One pass of the hot path on resident inputs (all work on the context's stream)."""
-        with torch.cuda.stream(stream):
-            if events: events[0].record(stream)
-            if world > 1:
-                shard.broadcast_([d_t, d_kp2, d_img1, d_img2], src=0)
-            ctx.match_knn2_f32_dev(d_q.data_ptr(), nq, d_t.data_ptr(), nt, 128, d_idx.data_ptr(), d_dist.data_ptr())
-            ctx.nndr_filter_dev(d_idx.data_ptr(), d_dist.data_ptr(), nq, NNDR_EPS, d_qi.data_ptr(), d_ti.data_ptr(),
-                                d_do.data_ptr(), d_nm.data_ptr())
-            if events: events[1].record(stream)
-            n_match = int(d_nm.item())          # sizes the following launches (4-byte D2H, as a host caller needs)
-            ctx.triangulate_dev(d_kp1.data_ptr(), nq, d_kp2.data_ptr(), nt, d_qi.data_ptr(), d_ti.data_ptr(), n_match,
-                                d_xyz_all.data_ptr(), d_mask.data_ptr(), d_xyz.data_ptr(), d_src.data_ptr(), d_ninl.data_ptr())
-            if events: events[2].record(stream)
-            ctx.set_images_dev(d_img1.data_ptr(), d_img2.data_ptr(), W, H, W, PYRAMIDS)
-            if events: events[3].record(stream)
-            n_inl = int(d_ninl.item())
-            ctx.optimize_normals_dev(d_xyz.data_ptr(), n_inl, PIXELS_RAY, EPS_LMMIN, penalty, d_normals.data_ptr(),
-                                     d_status.data_ptr(), d_nfev.data_ptr(), d_npen.data_ptr(), d_cost.data_ptr())
-            if events: events[4].record(stream)
-            gathered = None
-            if world > 1:
-                # one collective: (global query index, train index, distance) of the matches, normal and
-                # status of the inliers of every shard
-                gathered = shard.gather_packed([d_qi + lo, d_ti, d_do, d_normals, d_status],
-                                               [n_match, n_match, n_match, n_inl, n_inl], nq, unpack=False)
-            if events: events[5].record(stream)
-        device_step.gathered = gathered if world > 1 else None
-        return n_match, n_inl
-
-    def host_step():
-        """The same pass through the host-buffer C-ABI entry points (copies inside)."""
-        if world > 1:
-            with torch.cuda.stream(stream):
-                shard.broadcast_([d_t, d_kp2, d_img1, d_img2], src=0)
-            stream.synchronize()
-        qi, ti, d = ctx.match_nndr(h_q.numpy(), h_t.numpy(), NNDR_EPS)
-        xyz_all, mask, xyz, src = ctx.triangulate(h_kp1.numpy(), h_kp2.numpy(), qi, ti)
-        ctx.set_images(h_img1.numpy(), h_img2.numpy(), PYRAMIDS)
-        res = ctx.optimize_normals(xyz, PIXELS_RAY, EPS_LMMIN, PENALTY)
-        h2d = (h_q.numel() + h_t.numel()) * 4 + (h_kp1.numel() + h_kp2.numel()) * 4 + qi.nbytes + ti.nbytes + \
-            h_img1.numel() + h_img2.numel() + xyz.nbytes
-        d2h = qi.nbytes + ti.nbytes + d.nbytes + xyz_all.nbytes + mask.nbytes + xyz.nbytes + src.nbytes + \
-            res["normals"].nbytes + res["status"].nbytes + res["nfev"].nbytes + res["npenalty"].nbytes + res["cost"].nbytes
-        return len(qi), xyz.shape[0], h2d, d2h
+    n_stage = st.N_STAGE
 
     def barrier():
         stream.synchronize()
@@ -349,17 +471,17 @@ def run_gpu_arm(args):
 
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
-        n_match, n_inl = device_step()
+        n_match, n_inl = st.device_step()
         flush_l2()
     barrier()
 
     # ---- timed region: device-resident arm
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_stage + 1)] for _ in range(args.steps)]
     k0, c0 = ctx.launch_counters()
-    t_dev_ms = 0.0
     barrier()
     wall0 = time.perf_counter()
     for s in range(args.steps):
-        n_match, n_inl = device_step(ev[s])
+        n_match, n_inl = st.device_step(ev[s])
         flush_l2()                      # not between events 0..5 of a step: excluded from the step time
     barrier()
     wall_dev = time.perf_counter() - wall0
@@ -370,46 +492,62 @@ def run_gpu_arm(args):
             stage_ms[j] += ev[s][j].elapsed_time(ev[s][j + 1])
     t_dev_ms = float(stage_ms.sum())
     clocks = sampler.stop() if rank == 0 else None
+    ctx.sync()                          # also surfaces a TMA time-out of the device-resident normal search
 
     # ---- timed region: end-to-end arm (host buffers)
     for _ in range(2):
-        host_step()
+        st.host_step()
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        hm, hi_, h2d, d2h = host_step()
+        hm, hi_, h2d, d2h = st.host_step()
     barrier()
     t_e2e = time.perf_counter() - t0
 
-    if world > 1:   # the gathered buffer holds every rank's matches and normals: unpack once, outside the timed region
-        (g_q, g_t, g_d, g_n, g_s), g_counts = shard.unpack_packed(*device_step.gathered)
-        assert g_q.shape[0] == sum(c[0] for c in g_counts) and g_n.shape == (sum(c[3] for c in g_counts), 3)
-    # ---- executed-work counters of the last headline launch, then the same step under fabs semantics
+    # ---- what the last headline step gathered from all ranks, checked for CONTENT against the CPU oracle (rank 0)
+    st.device_step()
+    barrier()
+    gather_check = st.check_gathered(PENALTY) if rank == 0 else None
+    # ---- executed-work counters of the last headline launch
     stats = ctx.normals_stats()
-    nfev_main = d_nfev[:n_inl].cpu().numpy().astype(np.int64)
-    status_main = d_status[:n_inl].cpu().numpy()
-    npen_main = d_npen[:n_inl].cpu().numpy()
+    nfev_main = st.d_nfev[:n_inl].cpu().numpy().astype(np.int64)
+    status_main = st.d_status[:n_inl].cpu().numpy()
+    npen_main = st.d_npen[:n_inl].cpu().numpy()
     alt_steps = max(1, min(args.steps, 3))
-    for _ in range(2):
-        device_step(penalty=PENALTY_ALT)
-        flush_l2()
-    barrier()
-    ev_alt = [[torch.cuda.Event(enable_timing=True) for _ in range(n_stage + 1)] for _ in range(alt_steps)]
-    for s_ in range(alt_steps):
-        n_match_alt, n_inl_alt = device_step(ev_alt[s_], penalty=PENALTY_ALT)
-        flush_l2()
-    barrier()
-    t_alt_ms = sum(ev_alt[s_][0].elapsed_time(ev_alt[s_][n_stage]) for s_ in range(alt_steps)) / alt_steps
-    t_alt_norm_ms = sum(ev_alt[s_][3].elapsed_time(ev_alt[s_][4]) for s_ in range(alt_steps)) / alt_steps
+
+    # ---- the same step under fabs semantics (the source as today's g++ compiles it)
+    stage_alt, n_match_alt, n_inl_alt = st.timed(alt_steps, flush_l2, barrier, penalty=PENALTY_ALT)
+    t_alt_ms, t_alt_norm_ms = float(stage_alt.sum()) / alt_steps, float(stage_alt[3]) / alt_steps
     stats_alt = ctx.normals_stats()
-    nfev_alt = d_nfev[:n_inl_alt].cpu().numpy().astype(np.int64)
-    npen_alt = d_npen[:n_inl_alt].cpu().numpy()
+    nfev_alt = st.d_nfev[:n_inl_alt].cpu().numpy().astype(np.int64)
+    npen_alt = st.d_npen[:n_inl_alt].cpu().numpy()
+    fabs_agreement = oracle_agreement_fabs(st) if rank == 0 else None
+
+    # ---- the same step with the faithful kernel (normals_fast = 0: fp64 geometry in the reference's evaluation order,
+    # forward-difference Jacobian, one pass per lmfit evaluation group) -- the precision trade of the headline, in the open
+    ctx.set_option("normals_fast", 0)
+    try:
+        stage_f64, n_match_f64, n_inl_f64 = st.timed(alt_steps, flush_l2, barrier, penalty=PENALTY, warm=1)
+        nfev_f64 = st.d_nfev[:n_inl_f64].cpu().numpy().astype(np.int64)
+        normals_f64 = st.d_normals[:n_inl_f64].cpu().numpy().copy()
+    finally:
+        ctx.set_option("normals_fast", 1)
+    t_f64_ms, t_f64_norm_ms = float(stage_f64.sum()) / alt_steps, float(stage_f64[3]) / alt_steps
 
     # ---- after the path ("patch extraction separately"): frames -> K8 patches -> K9 SIFT descriptors of
     # this rank's refined features, device-resident, NOT part of `value`
     EPS_M, CM_PP = 0.16, 0.25           # build/settings.yml Neighborhoods: epsilon 0.16 m, cmPerPixel 0.25 -> 128 x 128 patches
     S_patch = api.patch_size(EPS_M, CM_PP)
-    device_step()                       # headline normals again (the fabs pass overwrote them)
+    st.device_step()                    # headline normals again (the other passes overwrote them)
+    stream.synchronize()
+    fast_vs_f64 = None
+    if n_inl_f64 == n_inl:
+        nh = st.d_normals[:n_inl].cpu().numpy()
+        ang = np.degrees(np.arccos(np.clip((nh * normals_f64).sum(1), -1, 1)))
+        okm = (status_main == 0)
+        fast_vs_f64 = {"angle_deg_p50": float(np.median(ang[okm])), "angle_deg_p99": float(np.percentile(ang[okm], 99)),
+                       "angle_deg_max_wall_free": float(ang[okm & (npen_main == 0)].max()) if (okm & (npen_main == 0)).any() else None}
+    d_xyz, d_normals, d_img1, d_img2 = st.d_xyz, st.d_normals, st.rep["img1"], st.rep["img2"]
     with torch.cuda.stream(stream):
         d_frames = torch.empty((max(n_inl, 1), 16), dtype=torch.float64, device=dev)
         d_patches = torch.empty((max(n_inl, 1), S_patch, S_patch), dtype=torch.uint8, device=dev)
@@ -498,15 +636,44 @@ def run_gpu_arm(args):
     brisk_kept = [int(d_bkept[a, :n_kp[a]].sum().item()) for a in range(2)]
     orb_kept = [int(d_okept[a, :n_kp[a]].sum().item()) for a in range(2)]
     kdesc_rows_nonzero = [int((d_kdesc[a, :n_kp[a]] != 0).any(1).sum().item()) for a in range(2)]
+    del d_kdesc, d_bdesc, d_odesc, d_patches
+
+    # ---- the north-star configuration in the same run, at the same N: BASELINE configs[2], ONE 4K pair with 20 000 query
+    # keypoints in total sharded over the ranks (strong scaling), pixelsRay 64, pyramids 3
+    c3 = None
+    if WORKLOAD == "c2" and not args.no_c3:
+        t0 = time.time()
+        case3 = synth.make_stereo_case(3840, 2160, 20000, 1002, pixels_ray=PIXELS_RAY, n_distractors=4000)
+        log(f"[rank {rank}] C3 workload generated in {time.time() - t0:.1f}s")
+        st3 = PathState(torch, api, shard, ctx, stream, dev, case3, world, rank, PIXELS_RAY, PYRAMIDS)
+        st3.bind()
+        c3_steps = max(1, min(args.steps, 3))
+        stage3, n_match3, n_inl3 = st3.timed(c3_steps, flush_l2, barrier, penalty=PENALTY, warm=2)
+        ctx.sync()
+        c3_check = st3.check_gathered(PENALTY, n_query_sample=1024, n_normal_sample=48) if rank == 0 else None
+        tm3 = torch.tensor([float(stage3.sum())], dtype=torch.float64, device=dev)
+        f3 = torch.tensor([float(n_match3)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm3, op=dist.ReduceOp.MAX)
+            dist.all_reduce(f3, op=dist.ReduceOp.SUM)
+        c3 = {"workload": "BASELINE configs[2]: ONE 3840x2160 synthetic stereo pair, 20000 SIFT-128 query keypoints (+4000 distractors) in "
+                          f"total, sharded over {world} GPU(s), pixelsRay 64, pyramids 3, NNDR 0.55, penalty int_abs",
+              "scaling": "strong", "n_gpus": world, "steps": c3_steps,
+              "value": float(f3[0]) * c3_steps / (float(tm3[0]) * 1e-3), "unit": "features/s",
+              "ms_per_pair": float(tm3[0]) / c3_steps, "matched_features": float(f3[0]),
+              "stage_ms_rank0": {k: float(v) / c3_steps for k, v in zip(PathState.STAGES, stage3)},
+              "gather_check": c3_check}
+        st.bind()
+        del st3, case3
 
     # ---- reduce over ranks: max time, summed features
-    tm = torch.tensor([t_dev_ms, t_e2e * 1e3, t_alt_ms], dtype=torch.float64, device=dev)
-    feats = torch.tensor([float(n_match), float(hm), float(n_match_alt)], dtype=torch.float64, device=dev)
+    tm = torch.tensor([t_dev_ms, t_e2e * 1e3, t_alt_ms, t_f64_ms], dtype=torch.float64, device=dev)
+    feats = torch.tensor([float(n_match), float(hm), float(n_match_alt), float(n_match_f64)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(feats, op=dist.ReduceOp.SUM)
-    t_dev_ms, t_e2e_ms, t_alt_ms = float(tm[0]), float(tm[1]), float(tm[2])
-    tot_feat, tot_feat_e2e, tot_feat_alt = float(feats[0]), float(feats[1]), float(feats[2])
+    t_dev_ms, t_e2e_ms, t_alt_ms, t_f64_ms = float(tm[0]), float(tm[1]), float(tm[2]), float(tm[3])
+    tot_feat, tot_feat_e2e, tot_feat_alt, tot_feat_f64 = float(feats[0]), float(feats[1]), float(feats[2]), float(feats[3])
 
     if rank == 0:
         nfev, status, npen = nfev_main, status_main, npen_main
@@ -536,12 +703,11 @@ def run_gpu_arm(args):
         cyc = {k: stats[k] for k in ("cycles_pixels", "cycles_barrier", "cycles_serial", "cycles_lm", "cycles_publish")}
         cyc_tot = max(1, cyc["cycles_pixels"] + cyc["cycles_barrier"] + cyc["cycles_serial"])
         roofline = {
-            "kernel": "normals_fast_kernel<true> (K6: LM normal search, one persistent CTA per SM, one feature per CTA at a time)",
+            "kernel": "normals_fast_kernel (K6: LM normal search, persistent CTAs, four feature pipelines per SM)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload under `ncu --set full`
-            # (profiles/r01f_normals_fast_kernel_ncu_raw_selected.csv: 199 MB + 691 MB, the L2-resident ray scratch
-            # being written back); 0.6 % of DRAM throughput -- the kernel is not HBM-bound
-            "traffic": 0.8902e9, "traffic_unit": "bytes per launch (ncu, profiles/r01f_*)",
+            "traffic": NORMALS_TRAFFIC_BYTES, "traffic_unit": "bytes per launch (ncu --set full, " + NORMALS_TRAFFIC_SOURCE + ")",
+            "traffic_algorithmic": n_inl * 44e3,
             "note": "compute-bound kernel (SURVEY 8d): algorithmic flops = 64 x value-only pixel evaluations + 152 x "
                     "value+analytic-Jacobian pixel evaluations executed (counted by the kernel) / CUDA-event time; peak = "
                     "measured FFMA rate (tools/micro/ffma2_rate.cu: 73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; "
@@ -552,6 +718,7 @@ def run_gpu_arm(args):
             "passes_global_taps": stats["passes_slow"],
             "reference_equivalent_pixel_evals": pixel_evals_ref,
             "reference_equivalent_tflops": pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12,
+            "frac_reference_equivalent": pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12 / fp32_peak,
             "thread0_cycle_share": {"pixel_loop": cyc["cycles_pixels"] / cyc_tot, "serial_lm_step": cyc["cycles_serial"] / cyc_tot},
             # the packed FMAs of the pixel loop read {64-bit, 32-bit broadcast constant, 64-bit} register sources: that form
             # sustains 54.6 TFLOP/s on this pool (three distinct 64-bit sources: 47.1), not the 73.96 of re-used operands --
@@ -566,10 +733,13 @@ def run_gpu_arm(args):
                            "peak": bf16_peak, "unit": "TFLOP/s", "ms": stage_ms[0] / args.steps,
                            "note": "includes operand re-tiling, NNDR filter and (N>1) the NCCL broadcast"},
             "pyrdown": {"bound": "hbm", "achieved": pyr_bytes / (stage_ms[2] / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
-                        "unit": "GB/s", "ms": stage_ms[2] / args.steps, "note": "3 launches + 2 device copies of 0.9 MB images: launch-bound"},
+                        "unit": "GB/s", "ms": stage_ms[2] / args.steps, "note": "0.9 MB images: launch-bound"},
         }
-        cpu = cpu_reference(case, max(16 * (os.cpu_count() or 1), 256), os.cpu_count() or 1) if world == 1 else None
-        cpu_alt = cpu_reference(case, max(8 * (os.cpu_count() or 1), 128), os.cpu_count() or 1, penalty=PENALTY_ALT) if world == 1 else None
+        ncpu = os.cpu_count() or 1
+        cpu = cpu_reference(case, max(16 * ncpu, 256), ncpu) if world == 1 else None
+        cpu_alt = cpu_reference(case, max(8 * ncpu, 128), ncpu, penalty=PENALTY_ALT) if world == 1 else None
+        # the reference is single-threaded -- the same port on ONE host thread, on a smaller bounded sample
+        cpu_1t = cpu_reference(case, 32, 1) if world == 1 else None
         value = tot_feat * args.steps / (t_dev_ms * 1e-3)
         out = {
             "metric": "features/sec (match+triangulate+normal-opt)", "value": value, "unit": "features/s",
@@ -583,14 +753,23 @@ def run_gpu_arm(args):
             "roofline": roofline,
             "roofline_other": roofline_other,
             "cpu_baseline": None if cpu is None else {
-                "value": cpu["features_per_s"], "unit": "features/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "value": cpu["features_per_s"], "unit": "features/s", "cores": ncpu, "kind": "port",
                 "sample": f"full {N_KP}x{N_KP + N_DISTRACT} matching + normal optimisation of {cpu['n_sample']} seeded features "
-                          f"of {cpu['n_match']}, per-feature times summed", "detail": cpu},
-            "stage_ms_per_step": {"match+nndr": stage_ms[0] / args.steps, "triangulate": stage_ms[1] / args.steps,
-                                  "pyramids": stage_ms[2] / args.steps, "normals": stage_ms[3] / args.steps,
-                                  "gather": stage_ms[4] / args.steps},
+                          f"of {cpu['n_match']}, per-feature times summed", "detail": cpu,
+                "single_thread": {"value": cpu_1t["features_per_s"], "unit": "features/s", "cores": 1,
+                                  "sample": f"the same port on ONE host thread (the reference is single-threaded, SURVEY 8d-i): full matching + "
+                                            f"normal optimisation of {cpu_1t['n_sample']} seeded features", "detail": cpu_1t}},
+            "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(PathState.STAGES, stage_ms)},
             "features_per_step": {"matches": tot_feat, "inliers_rank0": int(n_inl), "ok_rank0": int((status == 0).sum()),
                                   "wall_touching_rank0": int((npen > 0).sum()), "nfev_mean_per_level": nfev.mean(0).tolist()},
+            "multi_gpu_check": gather_check["result"] if isinstance(gather_check, dict) else str(gather_check),
+            "multi_gpu_check_detail": gather_check,
+            "faithful_fp64": {
+                "note": "the same step with normals_fast = 0 (fm3d_normals.cu): fp64 geometry in the reference's evaluation order, "
+                        "forward-difference Jacobian, one pass per lmfit evaluation group; dtype f64",
+                "value": tot_feat_f64 / (t_f64_ms * 1e-3), "unit": "features/s", "ms_per_step": t_f64_ms, "normals_ms": t_f64_norm_ms,
+                "nfev_mean_per_level": nfev_f64.mean(0).tolist(), "headline_vs_faithful_normals": fast_vs_f64},
+            "c3_strong": c3,
             "penalty_fabs": {
                 "note": "the same step with the penalty wall as today's g++ compiles it (abs == fabs): every synthetic "
                         "feature ends on the wall in the reference too (SURVEY fact 11); reported, not the headline",
@@ -598,6 +777,7 @@ def run_gpu_arm(args):
                 "normals_ms": t_alt_norm_ms, "wall_touching_rank0": int((npen_alt > 0).sum()),
                 "nfev_mean_per_level": nfev_alt.mean(0).tolist(),
                 "passes": stats_alt["passes_value"] + stats_alt["passes_jacobian"] + stats_alt["passes_fused"],
+                "oracle_agreement": fabs_agreement,
                 "cpu_baseline_features_per_s": None if cpu_alt is None else cpu_alt["features_per_s"]},
             "after_path_rank0": {
                 "note": "frames -> rectified patches (K8) -> SIFT descriptors of the patches (K9, extractDescriptorsFromPatches) for "
@@ -637,6 +817,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fm3d", choices=["fm3d", "reference"])
+    ap.add_argument("--no-c3", action="store_true", help="skip the c3_strong block (BASELINE configs[2] in the same run)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2: BASELINE configs[1], weak scaling (default, the driver's contract); c3: configs[2], 4K / 20k keypoints sharded")
     args = ap.parse_args()

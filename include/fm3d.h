@@ -74,6 +74,9 @@ int fm3d_version(void);
 int fm3d_ctx_create(int device, fm3d_ctx** out);
 void fm3d_ctx_destroy(fm3d_ctx* ctx);
 const char* fm3d_last_error(const fm3d_ctx* ctx);
+/* Waits for the context's stream.  Errors that an asynchronous (_dev) call could only detect on the device
+ * are reported here: FM3D_ERR_CUDA if a TMA window load of fm3d_optimize_normals_dev timed out (the results
+ * are then valid but were taken through the slow global-memory sampler). */
 int fm3d_sync(fm3d_ctx* ctx);
 /* cudaStream_t of the context, as an opaque pointer (for event timing by the caller). */
 void* fm3d_stream(fm3d_ctx* ctx);
@@ -204,6 +207,10 @@ int fm3d_set_images(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int
                     int stride, int pyramids);
 int fm3d_set_images_dev(fm3d_ctx* ctx, const uint8_t* img1, const uint8_t* img2, int w,
                         int h, int stride, int pyramids);
+/* The same with one row stride per image: the reference keeps each cv::Mat at its own step
+ * (singlecameratriangulator.cpp:116-120), so a ROI or a padded frame may differ from the other. */
+int fm3d_set_images2(fm3d_ctx* ctx, const uint8_t* img1, int stride1, const uint8_t* img2,
+                     int stride2, int w, int h, int pyramids);
 /* Copies pyramid level `level` of image `image` (1 or 2) to the host (tightly packed). */
 int fm3d_get_pyramid_level(fm3d_ctx* ctx, int image, int level, uint8_t* out, int* w,
                            int* h);

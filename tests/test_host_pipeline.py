@@ -537,3 +537,73 @@ def test_main_cpp_with_the_adaptive_fast_detector(tmp_path):
             inside = (oxy[:, 0] >= 31) & (oxy[:, 0] < img.shape[1] - 31) & (oxy[:, 1] >= 31) & (oxy[:, 1] < img.shape[0] - 31)   # ORB's border rule
             np.testing.assert_array_equal(k[:, :2], oxy[inside])
             np.testing.assert_array_equal(k[:, 4], orr[inside])
+
+
+def _read_knn_lists(b, o):
+    n = struct.unpack_from("i", b, o)[0]; o += 4
+    out = []
+    for _ in range(n):
+        k = struct.unpack_from("i", b, o)[0]; o += 4
+        out.append(np.frombuffer(b, np.dtype([("q", "i4"), ("t", "i4"), ("d", "f4")]), k, o)); o += 12 * k
+    return out, o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source", ["injected", "frames"])
+def test_compare_and_crosscompare_through_the_adapters(tmp_path, source):
+    """DescriptorsMatcher::compare / crosscompare (descriptorsmatcher.cpp:74-105): the raw kNN-2 lists A->B (and B->A)
+    through the C++ adapter, against the exact brute-force oracle (ties -> lower index); a second call with the same
+    output objects overwrites them (stale pre-filled descriptors must never be matched) and compareWithNNDR
+    appends to `matches` (:126)."""
+    exe = os.path.join(ROOT, "tests", "_build", "compare_main")
+    if not os.access(exe, os.X_OK):
+        __import__("importlib").import_module("__graft_entry__").build()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 300, 1000, r)
+    tmp = str(tmp_path)
+    opts = None if source == "injected" else """FeatureOptions:
+   DetectorType: FAST
+   DetectorMode: STATIC
+   FastDetector:
+      Threshold: 25
+      NonMaxSuppression: 1
+   ExtractorType: ORB
+"""
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), os.path.join(tmp, "features.bin") if source == "injected" else "-",
+                        os.path.join(tmp, "out.bin")], capture_output=True, text=True, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    b = open(os.path.join(tmp, "out.bin"), "rb").read()
+    na, nb, dim, es = struct.unpack_from("iiii", b, 0)
+    o = 16
+    dt = np.float32 if es == 4 else np.uint8
+    da = np.frombuffer(b, dt, na * dim, o).reshape(na, dim); o += es * na * dim
+    db = np.frombuffer(b, dt, nb * dim, o).reshape(nb, dim); o += es * nb * dim
+    m1, o = _read_knn_lists(b, o)
+    m2, o = _read_knn_lists(b, o)
+    ab, o = _read_knn_lists(b, o)
+    ba, o = _read_knn_lists(b, o)
+    n_once, n_twice = struct.unpack_from("ii", b, o); o += 8
+    nndr = np.frombuffer(b, np.dtype([("q", "i4"), ("t", "i4"), ("d", "f4")]), n_twice, o); o += 12 * n_twice
+    assert o == len(b)
+    if source == "injected":
+        np.testing.assert_array_equal(da, case["desc1"])
+        knn = orc.knn2_f32
+    else:
+        assert es == 1 and dim == 32 and na > 100 and nb > 100 and da.any()      # overwritten after the poisoning, not all zero
+        knn = orc.knn2_hamming
+    for lists, (q, t) in ((m1, (da, db)), (m2, (da, db)), (ab, (da, db)), (ba, (db, da))):
+        oi, od = knn(q, t)
+        assert len(lists) == q.shape[0]
+        gi = np.array([[l["t"][0], l["t"][1]] for l in lists])
+        gd = np.array([[l["d"][0], l["d"][1]] for l in lists])
+        np.testing.assert_array_equal(gi, oi)
+        np.testing.assert_array_equal(gd, od)
+        assert all((l["q"] == i).all() for i, l in enumerate(lists))
+    oi, od = knn(da, db)
+    oq, ot, odd = orc.nndr_filter(oi, od, 0.55)
+    assert n_once == len(oq) and n_twice == 2 * n_once
+    for half in (nndr[:n_once], nndr[n_once:]):
+        np.testing.assert_array_equal(half["q"], oq)
+        np.testing.assert_array_equal(half["t"], ot)
+        np.testing.assert_array_equal(half["d"], odd)
