@@ -555,6 +555,8 @@ int run_normals(fm3d_ctx* ctx, NormalsArgs& A) {
     // default: the fast kernel for the optimisation; cost evaluations (parity probes) stay on the
     // evaluation-by-evaluation kernel unless normals_fast >= 2
     if (ctx->opt_normals_fast && (A.mode == 0 || ctx->opt_normals_fast >= 2)) return run_normals_fast(ctx, A);
+    if (ctx->opt_normals_cost != FM3D_COST_SSD)
+        return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "normals_cost = NCC runs in the fast kernel only (normals_fast >= 1; fm3d_evaluate_normals: normals_fast = 2)");
     A.cam = ctx->cam;
     A.pyr = ctx->pyr;
     A.patience = ctx->opt_lm_patience;

@@ -54,6 +54,7 @@ struct NormalsArgs {
     int fuse_trials;                    // fast kernel: evaluate the Jacobian with the first trial
     int memo_trials;                    // fast kernel: answer coefficient-identical trials without a pass
     int sweep_batch;                    // fast kernel, mode 2: > 1 evaluates the candidate grid in batches of SWEEP_B per pass
+    int cost_mode;                      // fast kernel: FM3D_COST_SSD (the reference) / FM3D_COST_NCC
     int groups;                         // fast kernel: independent feature pipelines per CTA (1 or 2)
     int group_smem;                     // fast kernel: bytes of shared memory per group
     float2* rays_g;

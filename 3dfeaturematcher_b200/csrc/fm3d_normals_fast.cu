@@ -99,6 +99,7 @@ struct FastShared {
     int best_idx;
     int trial_is_first; // the trial being evaluated opens an LM iteration
     int fuse_hint;      // the last first trial of an LM iteration was accepted (initially 1)
+    double ncc_su, ncc_suu;   // cost_mode NCC: sum and sum of squares of the (approximately centred) image-1 samples of the level
     unsigned long long stats[16];
 };
 
@@ -107,6 +108,7 @@ struct LevelConst {
     float k1, k2, k3, p1, p2;
     float sfx, sfy, scx, scy;    // scale * K
     float cols, rows;            // isPixelGood bounds on the scaled pixel
+    float c0;                    // cost_mode NCC: value subtracted from every image-2 sample before it is summed (~ mean of image 1)
     const uint8_t* win;
     unsigned ww, coff, amax;
     int wx0, wy0, lx_min, lx_cnt, ly_min, ly_cnt;
@@ -115,10 +117,12 @@ struct LevelConst {
 };
 
 constexpr int MAX_GROUPS = 4;
+constexpr int NSUM_SSD = 6;          // sums of a pass: residual^2; J^T J (3), J^T r (2)
+constexpr int NSUM = 12;             // cost_mode NCC: sum v, v^2, u v; sum D (2), v D (2), u D (2), D D (3)
 constexpr int SWEEP_B = 4;           // mode 2: candidate normals evaluated per pass (one barrier pair per batch)
 struct GroupCtl {
     RowTable rows;
-    double red[16 * 6];
+    double red[16 * NSUM];
     unsigned wflags[16];
     FastShared S;
     FastPass PP;
@@ -160,14 +164,18 @@ __device__ __forceinline__ void undistort_ray(const fm3d_cam& c, double u, doubl
     xo = x; yo = y;
 }
 
+// Sums of a pass, per thread.  SSD: s0 = sum d^2 and f[0..4] = sum Ip Ip, Ip It, It It, Ip d, It d (d = I1 - I2, Ip / It =
+// dI2/dphi, dI2/dtheta).  NCC (u = centred image-1 sample, v = image-2 sample - c0): s0 = sum v, t1 = sum v^2, t2 = sum u v and
+// f[0..8] = sum Ip, It, v Ip, v It, u Ip, u It, Ip Ip, Ip It, It It -- everything the zero-mean normalised residual
+// u~/|u~| - v~/|v~| and its Jacobian need (ncc_sums_to_normal_equations).
 struct Acc {
-    double s0;
-    float s1, s2, s3, s4, s5;
+    double s0, t1, t2;
+    float f[9];
 };
 
 // Warp of one disc pixel into image 2 and its residual; with JAC also the derivatives of the
 // sampled intensity with respect to (phi, theta).
-template <bool JAC, bool SLOW>
+template <bool JAC, bool SLOW, bool NCC = false>
 __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelConst& L, float2 dv, float I1, Acc& acc) {
     const float A0 = fmaf(P.h[0][0], dv.x, fmaf(P.h[0][1], dv.y, P.h[0][2]));
     const float B0 = fmaf(P.h[0][3], dv.x, fmaf(P.h[0][4], dv.y, P.h[0][5]));
@@ -207,8 +215,14 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
     const float c0 = fmaf(ay, d0, b00), c1 = fmaf(ay, d1, b10);
     const float gx = __fsub_rn(c1, c0);
     const float I2 = fmaf(ax, gx, c0);
-    const float d = __fsub_rn(I1, I2);
-    acc.s0 = fma((double)d, (double)d, acc.s0);
+    const float d = NCC ? __fsub_rn(I2, L.c0) : __fsub_rn(I1, I2);        // NCC: d is v
+    if (NCC) {
+        acc.s0 += (double)d;
+        acc.t1 = fma((double)d, (double)d, acc.t1);
+        acc.t2 = fma((double)I1, (double)d, acc.t2);
+    } else {
+        acc.s0 = fma((double)d, (double)d, acc.s0);
+    }
     if (JAC) {
         const float gy = fmaf(ax, d1 - d0, d0);
         const float cdp = fmaf(r2, fmaf(r2, 3.0f * L.k3, 2.0f * L.k2), L.k1);   // d cd / d r2
@@ -228,11 +242,18 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
         const float C2 = fmaf(P.h[2][6], dv.x, fmaf(P.h[2][7], dv.y, P.h[2][8]));
         const float Ip = fmaf(q0, A1, fmaf(q1, B1, q2 * C1));   // dI2/dphi   (residual derivative = -Ip)
         const float It = fmaf(q0, A2, fmaf(q1, B2, q2 * C2));   // dI2/dtheta
-        acc.s1 = fmaf(Ip, Ip, acc.s1);
-        acc.s2 = fmaf(Ip, It, acc.s2);
-        acc.s3 = fmaf(It, It, acc.s3);
-        acc.s4 = fmaf(Ip, d, acc.s4);
-        acc.s5 = fmaf(It, d, acc.s5);
+        if (NCC) {
+            acc.f[0] += Ip; acc.f[1] += It;
+            acc.f[2] = fmaf(d, Ip, acc.f[2]); acc.f[3] = fmaf(d, It, acc.f[3]);
+            acc.f[4] = fmaf(I1, Ip, acc.f[4]); acc.f[5] = fmaf(I1, It, acc.f[5]);
+            acc.f[6] = fmaf(Ip, Ip, acc.f[6]); acc.f[7] = fmaf(Ip, It, acc.f[7]); acc.f[8] = fmaf(It, It, acc.f[8]);
+        } else {
+            acc.f[0] = fmaf(Ip, Ip, acc.f[0]);
+            acc.f[1] = fmaf(Ip, It, acc.f[1]);
+            acc.f[2] = fmaf(It, It, acc.f[2]);
+            acc.f[3] = fmaf(Ip, d, acc.f[3]);
+            acc.f[4] = fmaf(It, d, acc.f[4]);
+        }
     }
 }
 
@@ -264,12 +285,12 @@ __device__ __forceinline__ void ray_set(float2* rays, int idx, float x, float y)
 }
 
 struct Acc2 {      // Jacobian sums of the packed loop: lanes are added at the end of the pass
-    f2 s1, s2, s3, s4, s5;
+    f2 a[9];
 };
 
 // eval_pixel_fast for two pixels at once (taps from the staged window only).  The value path is
 // the same sequence of IEEE operations as the scalar function, lane by lane.
-template <bool JAC>
+template <bool JAC, bool NCC = false>
 __device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelConst& L, f2 X, f2 Y, f2 I1p, Acc& acc, Acc2& acc2) {
     const f2 A0 = fma2(bc(P.h[0][0]), X, fma2(bc(P.h[0][1]), Y, bc(P.h[0][2])));
     const f2 B0 = fma2(bc(P.h[0][3]), X, fma2(bc(P.h[0][4]), Y, bc(P.h[0][5])));
@@ -302,10 +323,17 @@ __device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelCo
     const f2 c0 = fma2(ay, d0, b00), c1 = fma2(ay, d1, b10);
     const f2 gx = sub2(c1, c0);
     const f2 I2 = fma2(ax, gx, c0);
-    const f2 d = sub2(I1p, I2);
+    const f2 d = NCC ? sub2(I2, bc(L.c0)) : sub2(I1p, I2);                  // NCC: d is v
     const float da = lo2(d), db = hi2(d);
-    acc.s0 = fma((double)da, (double)da, acc.s0);
-    acc.s0 = fma((double)db, (double)db, acc.s0);
+    if (NCC) {
+        const double va = (double)da, vb = (double)db;
+        acc.s0 += va; acc.s0 += vb;
+        acc.t1 = fma(va, va, acc.t1); acc.t1 = fma(vb, vb, acc.t1);
+        acc.t2 = fma((double)lo2(I1p), va, acc.t2); acc.t2 = fma((double)hi2(I1p), vb, acc.t2);
+    } else {
+        acc.s0 = fma((double)da, (double)da, acc.s0);
+        acc.s0 = fma((double)db, (double)db, acc.s0);
+    }
     if (JAC) {
         const f2 gy = fma2(ax, sub2(d1, d0), d0);
         const f2 cdp = fma2(r2, fma2(r2, bc(3.0f * L.k3), bc(2.0f * L.k2)), bc(L.k1));   // d cd / d r2
@@ -325,11 +353,18 @@ __device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelCo
         const f2 C2 = fma2(bc(P.h[2][6]), X, fma2(bc(P.h[2][7]), Y, bc(P.h[2][8])));
         const f2 Ip = fma2(q0, A1, fma2(q1, B1, mul2(q2, C1)));   // dI2/dphi   (residual derivative = -Ip)
         const f2 It = fma2(q0, A2, fma2(q1, B2, mul2(q2, C2)));   // dI2/dtheta
-        acc2.s1 = fma2(Ip, Ip, acc2.s1);
-        acc2.s2 = fma2(Ip, It, acc2.s2);
-        acc2.s3 = fma2(It, It, acc2.s3);
-        acc2.s4 = fma2(Ip, d, acc2.s4);
-        acc2.s5 = fma2(It, d, acc2.s5);
+        if (NCC) {
+            acc2.a[0] = add2(acc2.a[0], Ip); acc2.a[1] = add2(acc2.a[1], It);
+            acc2.a[2] = fma2(d, Ip, acc2.a[2]); acc2.a[3] = fma2(d, It, acc2.a[3]);
+            acc2.a[4] = fma2(I1p, Ip, acc2.a[4]); acc2.a[5] = fma2(I1p, It, acc2.a[5]);
+            acc2.a[6] = fma2(Ip, Ip, acc2.a[6]); acc2.a[7] = fma2(Ip, It, acc2.a[7]); acc2.a[8] = fma2(It, It, acc2.a[8]);
+        } else {
+            acc2.a[0] = fma2(Ip, Ip, acc2.a[0]);
+            acc2.a[1] = fma2(Ip, It, acc2.a[1]);
+            acc2.a[2] = fma2(It, It, acc2.a[2]);
+            acc2.a[3] = fma2(Ip, d, acc2.a[3]);
+            acc2.a[4] = fma2(It, d, acc2.a[4]);
+        }
     }
 }
 
@@ -363,16 +398,18 @@ __device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const Leve
     return flags;
 }
 
-template <bool JAC, bool SLOW, bool PREFETCH>
+template <bool JAC, bool SLOW, bool PREFETCH, bool NCC = false>
 __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& L, const float2* __restrict__ rays,
                                            const float* __restrict__ i1, int m, int tid, int NT, Acc& acc) {
     if (SLOW) {
         // taps from global memory (a boundary tap left the staged window): scalar path
-        for (int idx = tid; idx < m; idx += NT) eval_pixel_fast<JAC, true>(P, L, ray_at(rays, idx), i1[idx], acc);
+        for (int idx = tid; idx < m; idx += NT) eval_pixel_fast<JAC, true, NCC>(P, L, ray_at(rays, idx), i1[idx], acc);
         return;
     }
+    constexpr int NJ = NCC ? 9 : 5;
     Acc2 acc2;
-    acc2.s1 = acc2.s2 = acc2.s3 = acc2.s4 = acc2.s5 = 0ull;
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc2.a[k] = 0ull;
     const ulonglong2* __restrict__ rp = reinterpret_cast<const ulonglong2*>(rays);   // (X, Y) of a pixel pair
     const f2* __restrict__ ip = reinterpret_cast<const f2*>(i1);
     const int npair = m >> 1;
@@ -393,34 +430,58 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
             const int nx = p + 2 * NT;
             if (nx < npair) { r = rp[nx]; I = ip[nx]; }
             if (nx + NT < npair) { r2 = rp[nx + NT]; I2 = ip[nx + NT]; }
-            eval_pixel_pair<JAC>(P, L, cr.x, cr.y, cI, acc, acc2);
-            eval_pixel_pair<JAC>(P, L, cr2.x, cr2.y, cI2, acc, acc2);
+            eval_pixel_pair<JAC, NCC>(P, L, cr.x, cr.y, cI, acc, acc2);
+            eval_pixel_pair<JAC, NCC>(P, L, cr2.x, cr2.y, cI2, acc, acc2);
         }
-        if (p < npair) eval_pixel_pair<JAC>(P, L, r.x, r.y, I, acc, acc2);
+        if (p < npair) eval_pixel_pair<JAC, NCC>(P, L, r.x, r.y, I, acc, acc2);
 #else
         for (; p < npair; p += NT) {
             const ulonglong2 cr = r;
             const f2 cI = I;
             const int nx = p + NT;
             if (nx < npair) { r = rp[nx]; I = ip[nx]; }
-            eval_pixel_pair<JAC>(P, L, cr.x, cr.y, cI, acc, acc2);
+            eval_pixel_pair<JAC, NCC>(P, L, cr.x, cr.y, cI, acc, acc2);
         }
 #endif
     } else {
         for (; p < npair; p += NT) {
             const ulonglong2 r = rp[p];
-            eval_pixel_pair<JAC>(P, L, r.x, r.y, ip[p], acc, acc2);
+            eval_pixel_pair<JAC, NCC>(P, L, r.x, r.y, ip[p], acc, acc2);
         }
     }
     // odd pixel count: the last pixel alone (thread chosen so that the summation order is fixed)
-    if ((m & 1) && tid == (npair % NT)) eval_pixel_fast<JAC, false>(P, L, ray_at(rays, m - 1), i1[m - 1], acc);
+    if ((m & 1) && tid == (npair % NT)) eval_pixel_fast<JAC, false, NCC>(P, L, ray_at(rays, m - 1), i1[m - 1], acc);
     if (JAC) {
-        acc.s1 += lo2(acc2.s1) + hi2(acc2.s1);
-        acc.s2 += lo2(acc2.s2) + hi2(acc2.s2);
-        acc.s3 += lo2(acc2.s3) + hi2(acc2.s3);
-        acc.s4 += lo2(acc2.s4) + hi2(acc2.s4);
-        acc.s5 += lo2(acc2.s5) + hi2(acc2.s5);
+#pragma unroll
+        for (int k = 0; k < NJ; k++) acc.f[k] += lo2(acc2.a[k]) + hi2(acc2.a[k]);
     }
+}
+
+// cost_mode NCC: the sums of a pass -> what the LM consumes, in the layout of the SSD sums (s[0] = sum of squared residuals
+// without the penalty weight, s[1..3] = J^T J, s[4..5] = -J^T r), for the residual r_i = u~_i/|u~| - v~_i/|v~| with
+// u~ = u - mean u, v~ = v - mean v (squared sum 2 - 2 NCC).  With C = sum u~ v~, A^2 = sum u~^2, B^2 = sum v~^2,
+// E_p = sum D^p v~, F_p = sum D^p u~, Cov_pq = sum (D^p - mean)(D^q - mean), D^p = dI2/dp:
+//   sum r^2 = 2 - 2 C / (A B),   J^T J_pq = Cov_pq / B^2 - E_p E_q / B^4,   J^T r_p = -F_p / (A B) + E_p C / (A B^3).
+__device__ __forceinline__ void ncc_sums_to_normal_equations(double* s, double su, double suu, int m, bool jac) {
+    const double im = 1.0 / (double)m;
+    const double sv = s[0], svv = s[1], suv = s[2];
+    const double A2 = suu - su * su * im, B2 = svv - sv * sv * im, C = suv - su * sv * im;
+    const double AB = sqrt(A2 * B2);            // NaN / 0 for a flat patch: the cost below becomes NaN and the feature is dropped
+    const double ff = 2.0 - 2.0 * C / AB;
+    if (jac) {
+        const double d0 = s[3], d1 = s[4];
+        const double E0 = s[5] - sv * im * d0, E1 = s[6] - sv * im * d1;
+        const double F0 = s[7] - su * im * d0, F1 = s[8] - su * im * d1;
+        const double c00 = s[9] - d0 * d0 * im, c01 = s[10] - d0 * d1 * im, c11 = s[11] - d1 * d1 * im;
+        const double iB2 = 1.0 / B2, iB4 = iB2 * iB2;
+        const double g0 = -F0 / AB + E0 * C / (AB * B2), g1 = -F1 / AB + E1 * C / (AB * B2);
+        s[1] = c00 * iB2 - E0 * E0 * iB4;
+        s[2] = c01 * iB2 - E0 * E1 * iB4;
+        s[3] = c11 * iB2 - E1 * E1 * iB4;
+        s[4] = -g0;
+        s[5] = -g1;
+    }
+    s[0] = ff < 0.0 ? 0.0 : ff;                 // rounding can leave -1e-17 for identical patches
 }
 
 // Mode 2 (dense candidate sweep): NE candidate normals per pass.  Every thread walks the pixel pairs the
@@ -614,7 +675,8 @@ __device__ __forceinline__ bool stage_window(const NormalsArgs& A, const CUtenso
 // RAYS_SMEM / I1_SMEM: where the per-pixel ray offsets (8 B) and image-1 samples (4 B) of the
 // feature live: shared memory, or a per-group scratch in global memory that stays L2-resident
 // (one CTA streams it once per pass: 12 B x 12 853 pixels at r = 64).
-template <bool RAYS_SMEM, bool I1_SMEM>
+// NCC_COST: cost_mode NCC is a separate instantiation so that the reference's SSD kernel keeps its register allocation.
+template <bool RAYS_SMEM, bool I1_SMEM, bool NCC_COST>
 __global__ void __launch_bounds__(FAST_NT, 1)
 normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
     extern __shared__ __align__(128) uint8_t smem_all[];
@@ -653,6 +715,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
     uint64_t* bar = &G.bar;
 
     const int lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
+    constexpr bool ncc = NCC_COST;
     const fm3d_cam& cam = A.cam;
     const int r = A.r, W = A.pyr.lv[0].w, H = A.pyr.lv[0].h, levels = A.pyr.levels;
     const float cmax = (float)(int)(2 * cam.zmax);  // int cMax = 2*z_threshold_max_ (:648)
@@ -786,6 +849,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             L.scx = (float)(scale * cam.cx); L.scy = (float)(scale * cam.cy);
             L.cols = (float)lv.w; L.rows = (float)lv.h;     // scale * (cols_l / scale)
             L.xc = (float)S->xc; L.yc = (float)S->yc;
+            L.c0 = 0.0f;
 
             // window origins.  Image 2: centred on the projection of P (P lies on every candidate plane).
             // Image 1: the disc itself, scaled.  TMA needs the box start address 16-byte aligned: x
@@ -819,6 +883,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 const int y_lo = max(w1y0, 0), y_hi = min(w1y0 + wh, lv.h) - 1;
                 const int x_cnt = staged1 ? max(x_hi - x_lo, 0) : 0, y_cnt = staged1 ? max(y_hi - y_lo, 0) : 0;
                 int row = 0;
+                double i1_part = 0.0;
                 for (int idx = tid; idx < m; idx += NT) {
                     while (idx >= rows->start[row + 1]) row++;
                     const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
@@ -836,6 +901,35 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         v = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, sx, sy);
                     }
                     i1[idx] = v;
+                    i1_part += (double)v;
+                }
+                if (ncc) {
+                    // cost_mode NCC: the image-1 samples are kept CENTRED (u = I1 - c0, c0 = their mean rounded to float) together
+                    // with sum u and sum u^2; image-2 samples are centred with the same constant before they are summed, so that
+                    // the variances below are differences of small numbers' squares (fp64 sums of fp32 products)
+                    const double ws = warp_sum(i1_part);
+                    if (lane == 0) red[wid * NSUM] = ws;
+                    gsync(groups, g, NT);
+                    double tot = 0.0;
+                    for (int w = 0; w < NW; w++) tot += red[w * NSUM];     // same order in every thread: one value for the group
+                    const float c0 = (float)(tot / (double)m);
+                    L.c0 = c0;
+                    double pu = 0.0, puu = 0.0;
+                    for (int idx = tid; idx < m; idx += NT) {
+                        const float a = __fsub_rn(i1[idx], c0);
+                        i1[idx] = a;
+                        pu += (double)a;
+                        puu = fma((double)a, (double)a, puu);
+                    }
+                    const double wu = warp_sum(pu), wuu = warp_sum(puu);
+                    gsync(groups, g, NT);                                  // every thread has read the first totals
+                    if (lane == 0) { red[wid * NSUM] = wu; red[wid * NSUM + 1] = wuu; }
+                    gsync(groups, g, NT);
+                    if (tid == 0) {
+                        double a = 0.0, b = 0.0;
+                        for (int w = 0; w < NW; w++) { a += red[w * NSUM]; b += red[w * NSUM + 1]; }
+                        S->ncc_su = a; S->ncc_suu = b;
+                    }
                 }
                 gsync(groups, g, NT);   // everybody is done with the image-1 window
             }
@@ -944,7 +1038,11 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     }
                     Acc acc[SWEEP_B];
 #pragma unroll
-                    for (int k = 0; k < SWEEP_B; k++) { acc[k].s0 = 0.0; acc[k].s1 = acc[k].s2 = acc[k].s3 = acc[k].s4 = acc[k].s5 = 0.0f; }
+                    for (int k = 0; k < SWEEP_B; k++) {
+                        acc[k].s0 = acc[k].t1 = acc[k].t2 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 9; j++) acc[k].f[j] = 0.0f;
+                    }
                     if (ne == SWEEP_B) run_pixels_multi<SWEEP_B, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
                     else if (ne == 3) run_pixels_multi<3, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
                     else if (ne == 2) run_pixels_multi<2, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
@@ -953,7 +1051,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     for (int k = 0; k < SWEEP_B; k++) {
                         const double a = warp_sum(acc[k].s0);
                         const unsigned f_or = __reduce_or_sync(0xffffffffu, fl[k]);
-                        if (lane == 0) { red[wid * 6 + k] = a; G.wflagsk[wid * SWEEP_B + k] = f_or; }
+                        if (lane == 0) { red[wid * NSUM + k] = a; G.wflagsk[wid * SWEEP_B + k] = f_or; }
                     }
                     const long long t_b0 = clock64();
                     gsync(groups, g, NT);
@@ -963,7 +1061,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         unsigned fk[SWEEP_B];
 #pragma unroll
                         for (int k = 0; k < SWEEP_B; k++) {
-                            double v = lane < NW ? red[lane * 6 + k] : 0.0;
+                            double v = lane < NW ? red[lane * NSUM + k] : 0.0;
 #pragma unroll
                             for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                             sk[k] = v;
@@ -1033,38 +1131,64 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 }
 
                 Acc acc;
-                acc.s0 = 0.0; acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.0f;
-                if (P.kind == PASS_JAC) {
-                    if (!P.slow) run_pixels<true, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
-                    else run_pixels<true, true, false>(P, L, rays, i1, m, tid, NT, acc);
+                acc.s0 = acc.t1 = acc.t2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) acc.f[k] = 0.0f;
+                if (!ncc) {
+                    if (P.kind == PASS_JAC) {
+                        if (!P.slow) run_pixels<true, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<true, true, false>(P, L, rays, i1, m, tid, NT, acc);
+                    } else {
+                        if (!P.slow) run_pixels<false, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<false, true, false>(P, L, rays, i1, m, tid, NT, acc);
+                    }
                 } else {
-                    if (!P.slow) run_pixels<false, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
-                    else run_pixels<false, true, false>(P, L, rays, i1, m, tid, NT, acc);
+                    if (P.kind == PASS_JAC) {
+                        if (!P.slow) run_pixels<true, false, !RAYS_SMEM, true>(P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<true, true, false, true>(P, L, rays, i1, m, tid, NT, acc);
+                    } else {
+                        if (!P.slow) run_pixels<false, false, !RAYS_SMEM, true>(P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<false, true, false, true>(P, L, rays, i1, m, tid, NT, acc);
+                    }
                 }
-                double a0 = warp_sum(acc.s0), a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-                if (P.kind == PASS_JAC) {
-                    a1 = warp_sum((double)acc.s1); a2 = warp_sum((double)acc.s2); a3 = warp_sum((double)acc.s3);
-                    a4 = warp_sum((double)acc.s4); a5 = warp_sum((double)acc.s5);
+                // per-warp sums: SSD 1 (+5 with the Jacobian), NCC 3 (+9)
+                {
+                    double* rw = red + wid * NSUM;
+                    const double a0 = warp_sum(acc.s0);
+                    if (lane == 0) rw[0] = a0;
+                    if (ncc) {
+                        const double a1 = warp_sum(acc.t1), a2 = warp_sum(acc.t2);
+                        if (lane == 0) { rw[1] = a1; rw[2] = a2; }
+                    }
+                    const int nj = P.kind == PASS_JAC ? (ncc ? 9 : 5) : 0, jo = ncc ? 3 : 1;
+                    for (int k = 0; k < 9; k++) {
+                        if (k >= nj) break;
+                        const double a = warp_sum((double)acc.f[k]);
+                        if (lane == 0) rw[jo + k] = a;
+                    }
+                    if (lane == 0 && P.kind != PASS_JAC && !ncc) { rw[1] = rw[2] = rw[3] = rw[4] = rw[5] = 0.0; }
                 }
                 flags = __reduce_or_sync(0xffffffffu, flags);
-                if (lane == 0) {
-                    double* rw = red + wid * 6;
-                    rw[0] = a0; rw[1] = a1; rw[2] = a2; rw[3] = a3; rw[4] = a4; rw[5] = a5;
-                    wflags[wid] = flags;
-                }
+                if (lane == 0) wflags[wid] = flags;
                 const long long t_b0 = clock64();
                 gsync(groups, g, NT);
                 const long long t_b = clock64();
 
                 if (wid == 0) {
-                    double s[6];
+                    double s[NSUM];
                     unsigned any_flags = lane < NW ? wflags[lane] : 0u;
+                    {
+                        const int ns = ncc ? (P.kind == PASS_JAC ? NSUM : 3) : NSUM_SSD;
 #pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        double v = lane < NW ? red[lane * 6 + k] : 0.0;
+                        for (int k = 0; k < NSUM; k++) {
+                            double v = (lane < NW && k < ns) ? red[lane * NSUM + k] : 0.0;
+                            if (k < ns) {
 #pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        s[k] = v;
+                                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            }
+                            s[k] = v;
+                        }
+                        if (ncc) ncc_sums_to_normal_equations(s, S->ncc_su, S->ncc_suu, m, P.kind == PASS_JAC);
                     }
                     any_flags = __reduce_or_sync(0xffffffffu, any_flags);
                     const long long t_r = clock64();
@@ -1255,6 +1379,9 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     A.fuse_trials = ctx->opt_normals_fuse;
     A.memo_trials = ctx->opt_normals_memo;
     A.sweep_batch = ctx->opt_normals_sweep_batch;
+    A.cost_mode = ctx->opt_normals_cost;
+    if (A.cost_mode == FM3D_COST_NCC && A.mode == 2)
+        return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "the dense candidate sweep evaluates the reference's SSD cost only (normals_cost = 0)");
     A.mcap = (disc_capacity(A.r) + 31) & ~31;
     int nt = ctx->opt_normals_threads;
     nt = nt < 128 ? 128 : (nt > FAST_NT ? FAST_NT : (nt & ~63));
@@ -1351,9 +1478,14 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         FM3D_LAUNCH_CHECK(ctx);
         return FM3D_OK;
     };
-    if (lay.rays_smem) return launch(normals_fast_kernel<true, true>);
-    if (lay.i1_smem) return launch(normals_fast_kernel<false, true>);
-    return launch(normals_fast_kernel<false, false>);
+    if (A.cost_mode == FM3D_COST_NCC) {
+        if (lay.rays_smem) return launch(normals_fast_kernel<true, true, true>);
+        if (lay.i1_smem) return launch(normals_fast_kernel<false, true, true>);
+        return launch(normals_fast_kernel<false, false, true>);
+    }
+    if (lay.rays_smem) return launch(normals_fast_kernel<true, true, false>);
+    if (lay.i1_smem) return launch(normals_fast_kernel<false, true, false>);
+    return launch(normals_fast_kernel<false, false, false>);
 }
 
 }  // namespace fm3d_normals

@@ -666,6 +666,9 @@ NormalOptimizer::NormalOptimizer(const cv::FileStorage settings, SingleCameraTri
     // abs() semantics of the penalty wall (normaloptimizer.cpp:126-142): fabs, what today's g++ makes of the
     // source, unless the environment says otherwise -- the unchanged main.cpp has no other way to choose
     if (const char* e = getenv("FM3D_PENALTY")) penalty_mode_ = atoi(e);
+    // what is minimised: the reference's SSD (0, default) or the NCC extension (1); see fm3d_cost_mode in fm3d.h
+    cost_mode_ = FM3D_COST_SSD;
+    if (const char* e = getenv("FM3D_COST")) cost_mode_ = atoi(e);
     settings["Neighborhoods"]["pyramids"] >> pyr_levels_;
     settings["Neighborhoods"]["epsilonLMMIN"] >> epsilon_lmmin_;
     std::vector<double> rIC;
@@ -700,9 +703,11 @@ void NormalOptimizer::computeOptimizedNormals(std::vector<cv::Vec3d>& points3D, 
     (void)ctx;
     const int G = (int)host_ctxs().size(), r = sct_->pixelsRay(), pm = penalty_mode_;
     const double eps = epsilon_lmmin_;
+    const int cm = cost_mode_;
     for_each_ctx("optimize_normals", [&](int k) {
         const int lo = (int)((long long)n * k / G), hi = (int)((long long)n * (k + 1) / G);
         if (hi <= lo) return (int)FM3D_OK;
+        if (int rc = fm3d_set_option(host_ctxs()[k], "normals_cost", (double)cm)) return rc;
         return fm3d_optimize_normals(host_ctxs()[k], xyz.data() + 3 * (size_t)lo, hi - lo, r, eps, pm, normals.data() + 3 * (size_t)lo,
                                      status.data() + lo, nfev.data() + (size_t)lo * L1, npen.data() + lo, cost.data() + lo);
     });

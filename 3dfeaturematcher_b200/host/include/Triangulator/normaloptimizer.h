@@ -21,6 +21,8 @@ public:
 
     // fm3d extensions: abs() semantics of the penalty wall (0 fabs = as compiled today, 1 int abs, 2 off)
     void setPenaltyMode(int mode) { penalty_mode_ = mode; }
+    // what is minimised: 0 the reference's SSD (default), 1 the zero-mean normalised cost (fm3d_cost_mode)
+    void setCostMode(int mode) { cost_mode_ = mode; }
     // per-feature outcome of the last computeOptimizedNormals, indexed like the INPUT points3D
     const std::vector<int>& lastStatus() const { return status_; }
     const std::vector<int>& lastEvaluations() const { return nfev_; }
@@ -28,7 +30,7 @@ public:
 private:
     NormalOptimizer();
     SingleCameraTriangulator* sct_;
-    int pyr_levels_, penalty_mode_;
+    int pyr_levels_, penalty_mode_, cost_mode_;
     double epsilon_lmmin_;
     cv::Vec3d gravity_;
     std::vector<int> status_, nfev_;

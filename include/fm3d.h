@@ -66,6 +66,17 @@ typedef enum fm3d_penalty_mode {
     FM3D_PENALTY_OFF = 2
 } fm3d_penalty_mode;
 
+/* What the normal search minimises (option "normals_cost").  The reference knows only the first: plain SSD of the
+ * bilinear intensities, fvec[i] = w (I1_i - I2_i) (Triangulator/normaloptimizer.cpp:145-148; SURVEY fact 4: "there
+ * is no NCC anywhere").  FM3D_COST_NCC is an extension the north star names: the zero-mean normalised residual
+ * fvec[i] = w ((I1_i - mean I1)/|I1 - mean I1| - (I2_i - mean I2)/|I2 - mean I2|), whose squared sum is
+ * 2 - 2 NCC(I1, I2) -- invariant to gain and offset between the two frames -- minimised by the same
+ * Levenberg-Marquardt, level by level.  Same gates, same statuses; a patch without texture is dropped (NaN). */
+typedef enum fm3d_cost_mode {
+    FM3D_COST_SSD = 0,
+    FM3D_COST_NCC = 1
+} fm3d_cost_mode;
+
 /* ------------------------------------------------------------------ context ---- */
 
 int fm3d_version(void);
@@ -97,6 +108,8 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *   "normals_fast"      1 (default): fm3d_normals_fast.cu (fp32 offset-form geometry, analytic
  *                       Jacobian); 0: the evaluation-by-evaluation fp64 kernel; 2: also route
  *                       fm3d_evaluate_normals through the fast kernel
+ *   "normals_cost"      fm3d_cost_mode: 0 (default) the reference's SSD, 1 NCC (fast kernel only: with
+ *                       normals_fast = 0, and in fm3d_sweep_normals, NCC returns FM3D_ERR_UNSUPPORTED)
  *   "normals_fuse"      fast kernel: evaluate the first trial of an LM iteration with its Jacobian (1)
  *   "normals_memo"      fast kernel: do not re-evaluate trial points whose fp32 coefficients equal
  *                       the iterate's (1)

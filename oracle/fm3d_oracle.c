@@ -47,6 +47,10 @@
 
 enum { FEAT_OK = 0, FEAT_NO_PIXELS = 1, FEAT_ABORT_BBOX = 2, FEAT_ABORT_PIXEL = 3, FEAT_ABORT_NAN = 4 };
 enum { PENALTY_FABS = 0, PENALTY_INT_ABS = 1, PENALTY_OFF = 2 };
+/* COST_SSD: the reference's residual, I1 - I2 (normaloptimizer.cpp:145-148).  COST_NCC: the zero-mean normalised residual
+ * a_i/|a| - b_i/|b| (a = I1 - mean I1, b = I2 - mean I2), whose squared sum is 2 - 2 NCC(I1, I2): not in the reference
+ * (SURVEY fact 4), an option of the new build the north star names; restated here so the kernel has something to equal. */
+enum { COST_SSD = 0, COST_NCC = 1 };
 
 typedef struct {
     double fx, fy, cx, cy;
@@ -330,6 +334,8 @@ typedef struct {
     double scale;
     int penalty_mode;
     int as_written;      /* 1: redo undistort + image-1 sampling at every evaluation like the reference */
+    int cost_mode;       /* COST_SSD / COST_NCC */
+    float* i2;           /* COST_NCC: m image-2 intensities of the evaluation */
     int npenalty;
     int abort_code;
     long long pixel_evals;
@@ -399,7 +405,17 @@ static int eval_normal(const double* par, int m_dat, void* data, double* fvec) {
         distort_project(c, x2, y2, z2, &u, &v);
         if (!pixel_good(u, v, D->scale, D->img1.w, D->img1.h)) { D->abort_code = FEAT_ABORT_PIXEL; return -1; }
         float i2 = bilinear32f(&D->img2, (float)(D->scale * u), (float)(D->scale * v));
-        fvec[i] = w * (double)(D->i1[i] - i2);
+        if (D->cost_mode == COST_NCC) D->i2[i] = i2;
+        else fvec[i] = w * (double)(D->i1[i] - i2);
+    }
+    if (D->cost_mode == COST_NCC) {
+        double m1 = 0, m2 = 0, A = 0, B = 0;
+        for (int i = 0; i < m; i++) { m1 += D->i1[i]; m2 += D->i2[i]; }
+        m1 /= m; m2 /= m;
+        for (int i = 0; i < m; i++) { double a = D->i1[i] - m1, b = D->i2[i] - m2; A += a * a; B += b * b; }
+        A = sqrt(A); B = sqrt(B);
+        if (!(A > 0) || !(B > 0)) { D->abort_code = FEAT_ABORT_NAN; return -1; }   /* a flat patch has no normalised residual */
+        for (int i = 0; i < m; i++) fvec[i] = w * ((D->i1[i] - m1) / A - (D->i2[i] - m2) / B);
     }
     (void)m_dat;
     return 0;
@@ -773,7 +789,7 @@ int orc_build_pyramid(const uint8_t* img, int w, int h, int levels, uint8_t* out
 
 static int optimize_one(const orc_camera* cam, const double* P, const orc_pyramid* p1,
                         const orc_pyramid* p2, int levels, int r, double eps_lmmin,
-                        int penalty_mode, int patience, int as_written, double* normal,
+                        int penalty_mode, int cost_mode, int patience, int as_written, double* normal,
                         int32_t* nfev, int32_t* npenalty, double* cost, int32_t* m_out,
                         long long* pixel_evals) {
     int W = p1->w[0], H = p1->h[0];
@@ -791,6 +807,7 @@ static int optimize_one(const orc_camera* cam, const double* P, const orc_pyrami
     if (m <= 0) { free(pix); return FEAT_NO_PIXELS; }
     double* rays = (double*)malloc(sizeof(double) * 2 * m);
     float* i1 = (float*)malloc(sizeof(float) * m);
+    float* i2 = (float*)malloc(sizeof(float) * m);
     double* work = (double*)malloc(sizeof(double) * (size_t)m * 4);
     for (int i = 0; i < m; i++) undistort1(cam, pix[2 * i], pix[2 * i + 1], &rays[2 * i], &rays[2 * i + 1]);
     int status = FEAT_OK;
@@ -805,6 +822,7 @@ static int optimize_one(const orc_camera* cam, const double* P, const orc_pyrami
         D.img2.p = p2->data + p2->off[lvl]; D.img2.w = p2->w[lvl]; D.img2.h = p2->h[lvl];
         D.scale = 1.0 / img_scale;
         D.penalty_mode = penalty_mode; D.as_written = as_written;
+        D.cost_mode = cost_mode; D.i2 = i2;
         double par[2];
         par[1] = atan2(n[2], sqrt(n[0] * n[0] + n[1] * n[1])); /* theta, car2sph tools.cpp:767-771 */
         par[0] = atan2(n[1], n[0]);                            /* phi */
@@ -820,18 +838,18 @@ static int optimize_one(const orc_camera* cam, const double* P, const orc_pyrami
         img_scale /= 2.0f;
     }
     if (status == FEAT_OK) { normal[0] = n[0]; normal[1] = n[1]; normal[2] = n[2]; }
-    free(pix); free(rays); free(i1); free(work);
+    free(pix); free(rays); free(i1); free(i2); free(work);
     return status;
 }
 
 /* pyr1/pyr2: concatenated pyramids from orc_build_pyramid. Returns total pixel evaluations. */
-long long orc_optimize_normals(const double* K, const double* dist, const double* g12,
-                               double zmin, double zmax, const uint8_t* pyr1,
-                               const uint8_t* pyr2, int w, int h, int levels,
-                               const double* xyz, int n, int pixels_ray, double eps_lmmin,
-                               int penalty_mode, int patience, int as_written, int threads,
-                               double* normals, int32_t* status, int32_t* nfev,
-                               int32_t* npenalty, double* cost, int32_t* m_out) {
+long long orc_optimize_normals2(const double* K, const double* dist, const double* g12,
+                                double zmin, double zmax, const uint8_t* pyr1,
+                                const uint8_t* pyr2, int w, int h, int levels,
+                                const double* xyz, int n, int pixels_ray, double eps_lmmin,
+                                int penalty_mode, int cost_mode, int patience, int as_written, int threads,
+                                double* normals, int32_t* status, int32_t* nfev,
+                                int32_t* npenalty, double* cost, int32_t* m_out) {
     orc_camera cam; cam_init(&cam, K, dist, g12, zmin, zmax);
     orc_pyramid p1, p2;
     pyramid_layout(&p1, pyr1, w, h, levels);
@@ -841,7 +859,7 @@ long long orc_optimize_normals(const double* K, const double* dist, const double
     for (int i = 0; i < n; i++) {
         long long pe = 0;
         status[i] = optimize_one(&cam, xyz + 3 * i, &p1, &p2, levels, pixels_ray, eps_lmmin,
-                                 penalty_mode, patience, as_written, normals + 3 * i,
+                                 penalty_mode, cost_mode, patience, as_written, normals + 3 * i,
                                  nfev ? nfev + (size_t)i * (levels + 1) : 0,
                                  npenalty ? npenalty + i : 0, cost ? cost + i : 0,
                                  m_out ? m_out + i : 0, &pe);
@@ -850,12 +868,23 @@ long long orc_optimize_normals(const double* K, const double* dist, const double
     return total;
 }
 
+long long orc_optimize_normals(const double* K, const double* dist, const double* g12,
+                               double zmin, double zmax, const uint8_t* pyr1,
+                               const uint8_t* pyr2, int w, int h, int levels,
+                               const double* xyz, int n, int pixels_ray, double eps_lmmin,
+                               int penalty_mode, int patience, int as_written, int threads,
+                               double* normals, int32_t* status, int32_t* nfev,
+                               int32_t* npenalty, double* cost, int32_t* m_out) {
+    return orc_optimize_normals2(K, dist, g12, zmin, zmax, pyr1, pyr2, w, h, levels, xyz, n, pixels_ray, eps_lmmin, penalty_mode,
+                                 COST_SSD, patience, as_written, threads, normals, status, nfev, npenalty, cost, m_out);
+}
+
 /* one evaluateNormal call: cost = sum fvec^2 at (phi,theta), level `level` */
-int orc_evaluate_cost(const double* K, const double* dist, const double* g12, double zmin,
-                      double zmax, const uint8_t* pyr1, const uint8_t* pyr2, int w, int h,
-                      int levels, const double* xyz, const double* phi_theta, int n,
-                      int pixels_ray, int level, int penalty_mode, double* cost, int32_t* m_out,
-                      int32_t* status) {
+int orc_evaluate_cost2(const double* K, const double* dist, const double* g12, double zmin,
+                       double zmax, const uint8_t* pyr1, const uint8_t* pyr2, int w, int h,
+                       int levels, const double* xyz, const double* phi_theta, int n,
+                       int pixels_ray, int level, int penalty_mode, int cost_mode, double* cost, int32_t* m_out,
+                       int32_t* status) {
     orc_camera cam; cam_init(&cam, K, dist, g12, zmin, zmax);
     orc_pyramid p1, p2;
     pyramid_layout(&p1, pyr1, w, h, levels);
@@ -864,6 +893,7 @@ int orc_evaluate_cost(const double* K, const double* dist, const double* g12, do
     double* pix = (double*)malloc(sizeof(double) * cap * 2);
     double* rays = (double*)malloc(sizeof(double) * cap * 2);
     float* i1 = (float*)malloc(sizeof(float) * cap);
+    float* i2 = (float*)malloc(sizeof(float) * cap);
     double* fvec = (double*)malloc(sizeof(double) * cap);
     for (int f = 0; f < n; f++) {
         const double* P = xyz + 3 * f;
@@ -879,6 +909,7 @@ int orc_evaluate_cost(const double* K, const double* dist, const double* g12, do
         D.img2.p = p2.data + p2.off[level]; D.img2.w = p2.w[level]; D.img2.h = p2.h[level];
         D.scale = 1.0 / pow(2.0, level);
         D.penalty_mode = penalty_mode;
+        D.cost_mode = cost_mode; D.i2 = i2;
         int info = eval_normal(phi_theta + 2 * f, m, &D, fvec);
         if (info < 0) { status[f] = D.abort_code; continue; }
         status[f] = FEAT_OK;
@@ -886,8 +917,17 @@ int orc_evaluate_cost(const double* K, const double* dist, const double* g12, do
         for (int i = 0; i < m; i++) s += fvec[i] * fvec[i];
         cost[f] = s;
     }
-    free(pix); free(rays); free(i1); free(fvec);
+    free(pix); free(rays); free(i1); free(i2); free(fvec);
     return 0;
+}
+
+int orc_evaluate_cost(const double* K, const double* dist, const double* g12, double zmin,
+                      double zmax, const uint8_t* pyr1, const uint8_t* pyr2, int w, int h,
+                      int levels, const double* xyz, const double* phi_theta, int n,
+                      int pixels_ray, int level, int penalty_mode, double* cost, int32_t* m_out,
+                      int32_t* status) {
+    return orc_evaluate_cost2(K, dist, g12, zmin, zmax, pyr1, pyr2, w, h, levels, xyz, phi_theta, n, pixels_ray, level,
+                              penalty_mode, COST_SSD, cost, m_out, status);
 }
 
 /* ------------------------------------------------------------ frames + patches ---- */

@@ -34,6 +34,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         _lib.orc_optimize_normals.restype = C.c_longlong
+        _lib.orc_optimize_normals2.restype = C.c_longlong
         _lib.orc_pyramid_bytes.restype = C.c_size_t
     return _lib
 
@@ -145,7 +146,7 @@ def disc_pixels(K, dist, P, r, w, h):
 
 def optimize_normals(K, dist, g12, zmin, zmax, img1, img2, levels, xyz, pixels_ray,
                      eps_lmmin, penalty_mode=0, patience=100, as_written=0, threads=1,
-                     pyr1=None, pyr2=None):
+                     pyr1=None, pyr2=None, cost_mode=0):
     h, w = img1.shape
     if pyr1 is None:
         pyr1 = build_pyramid(img1, levels)
@@ -158,16 +159,16 @@ def optimize_normals(K, dist, g12, zmin, zmax, img1, img2, levels, xyz, pixels_r
     npen = np.empty(n, np.int32)
     cost = np.empty(n)
     m = np.empty(n, np.int32)
-    pe = lib().orc_optimize_normals(_p(_d(K), c_dp), _p(_d(dist), c_dp), _p(_d(g12), c_dp), C.c_double(zmin), C.c_double(zmax),
+    pe = lib().orc_optimize_normals2(_p(_d(K), c_dp), _p(_d(dist), c_dp), _p(_d(g12), c_dp), C.c_double(zmin), C.c_double(zmax),
                                     _p(pyr1, c_bp), _p(pyr2, c_bp), w, h, levels, _p(xyz, c_dp), n, pixels_ray,
-                                    C.c_double(eps_lmmin), penalty_mode, patience, as_written, threads,
+                                    C.c_double(eps_lmmin), penalty_mode, cost_mode, patience, as_written, threads,
                                     _p(normals, c_dp), _p(status, c_ip), _p(nfev, c_ip), _p(npen, c_ip), _p(cost, c_dp), _p(m, c_ip))
     return {"normals": normals, "status": status, "nfev": nfev, "npenalty": npen, "cost": cost,
             "m": m, "pixel_evals": int(pe)}
 
 
 def evaluate_cost(K, dist, g12, zmin, zmax, img1, img2, levels, xyz, phi_theta, pixels_ray,
-                  level, penalty_mode=0):
+                  level, penalty_mode=0, cost_mode=0):
     h, w = img1.shape
     pyr1 = build_pyramid(img1, levels)
     pyr2 = build_pyramid(img2, levels)
@@ -177,9 +178,9 @@ def evaluate_cost(K, dist, g12, zmin, zmax, img1, img2, levels, xyz, phi_theta, 
     cost = np.empty(n)
     m = np.empty(n, np.int32)
     status = np.empty(n, np.int32)
-    lib().orc_evaluate_cost(_p(_d(K), c_dp), _p(_d(dist), c_dp), _p(_d(g12), c_dp), C.c_double(zmin), C.c_double(zmax),
-                            _p(pyr1, c_bp), _p(pyr2, c_bp), w, h, levels, _p(xyz, c_dp), _p(pt, c_dp), n, pixels_ray, level,
-                            penalty_mode, _p(cost, c_dp), _p(m, c_ip), _p(status, c_ip))
+    lib().orc_evaluate_cost2(_p(_d(K), c_dp), _p(_d(dist), c_dp), _p(_d(g12), c_dp), C.c_double(zmin), C.c_double(zmax),
+                             _p(pyr1, c_bp), _p(pyr2, c_bp), w, h, levels, _p(xyz, c_dp), _p(pt, c_dp), n, pixels_ray, level,
+                             penalty_mode, cost_mode, _p(cost, c_dp), _p(m, c_ip), _p(status, c_ip))
     return cost, m, status
 
 
