@@ -42,6 +42,10 @@ SYMBOLS = [
     "fm3d_describe_keypoints_brisk", "fm3d_describe_keypoints_brisk_dev",
     "fm3d_describe_keypoints_orb", "fm3d_describe_keypoints_orb_dev",
     "fm3d_describe_patches_orb", "fm3d_describe_patches_orb_dev",
+    "fm3d_comm_unique_id", "fm3d_comm_init_rank", "fm3d_comm_init_all", "fm3d_comm_info", "fm3d_comm_destroy",
+    "fm3d_broadcast_dev", "fm3d_allgather_dev", "fm3d_broadcast_all_dev", "fm3d_allgather_all_dev",
+    "fm3d_shard_block_layout", "fm3d_pack_shard_dev",
+    "fm3d_dev_malloc", "fm3d_dev_free", "fm3d_copy_h2d", "fm3d_copy_d2h",
 ]
 
 
@@ -91,6 +95,50 @@ def patch_size(epsilon_m, cm_per_pixel):
     return load_library().fm3d_patch_size(float(epsilon_m), float(cm_per_pixel))
 
 
+class ShardLayout(C.Structure):
+    """fm3d_shard_layout (include/fm3d.h): byte offsets of the parts of one gather block."""
+    _fields_ = [("cap", C.c_int), ("off_qidx", C.c_size_t), ("off_tidx", C.c_size_t), ("off_dist", C.c_size_t),
+                ("off_src", C.c_size_t), ("off_normals", C.c_size_t), ("off_status", C.c_size_t), ("bytes", C.c_size_t)]
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """fm3d_comm_unique_id: 128 bytes rank 0 creates and hands to the other ranks (any channel)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = load_library().fm3d_comm_unique_id(buf)
+    if rc:
+        raise Fm3dError(rc, "fm3d_comm_unique_id failed (NCCL not loadable?)")
+    return bytes(buf)
+
+
+def shard_block_layout(cap):
+    L = ShardLayout()
+    rc = load_library().fm3d_shard_block_layout(int(cap), C.byref(L))
+    if rc:
+        raise Fm3dError(rc, "fm3d_shard_block_layout failed")
+    return L
+
+
+def unpack_shard_blocks(blocks, layout):
+    """Host view of gathered blocks (numpy uint8, world x layout.bytes): the valid rows of all ranks in rank order."""
+    world = blocks.shape[0]
+    hdr = np.ascontiguousarray(blocks[:, :20]).view(np.int32).reshape(world, 5)
+    cap = layout.cap
+    out = {k: [] for k in ("qidx", "tidx", "dist", "src", "normals", "status")}
+    for r in range(world):
+        nm, ni = int(hdr[r, 0]), int(hdr[r, 1])
+        b = blocks[r]
+        out["qidx"].append(b[layout.off_qidx:layout.off_qidx + 4 * cap].view(np.int32)[:nm])
+        out["tidx"].append(b[layout.off_tidx:layout.off_tidx + 4 * cap].view(np.int32)[:nm])
+        out["dist"].append(b[layout.off_dist:layout.off_dist + 4 * cap].view(np.float32)[:nm])
+        out["src"].append(b[layout.off_src:layout.off_src + 4 * cap].view(np.int32)[:ni])
+        out["normals"].append(b[layout.off_normals:layout.off_normals + 24 * cap].view(np.float64).reshape(cap, 3)[:ni])
+        out["status"].append(b[layout.off_status:layout.off_status + 4 * cap].view(np.int32)[:ni])
+    return {k: np.concatenate(v) for k, v in out.items()}, hdr
+
+
 class Context:
     """One fm3d_ctx: one GPU, one stream."""
 
@@ -119,6 +167,27 @@ class Context:
     def _ck(self, rc):
         if rc:
             raise Fm3dError(rc, self.lib.fm3d_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ several GPUs (one process per GPU)
+    def comm_init_rank(self, unique_id: bytes, nranks: int, rank: int):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._ck(self.lib.fm3d_comm_init_rank(self._h, buf, int(nranks), int(rank)))
+
+    def comm_info(self):
+        n, r, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.fm3d_comm_info(self._h, C.byref(n), C.byref(r), C.byref(v)))
+        return {"nranks": n.value, "rank": r.value, "nccl_version": v.value}
+
+    def broadcast_dev(self, buf_ptr, nbytes, root=0):
+        self._ck(self.lib.fm3d_broadcast_dev(self._h, C.c_void_p(buf_ptr), C.c_size_t(nbytes), int(root)))
+
+    def allgather_dev(self, send_ptr, recv_ptr, bytes_per_rank):
+        self._ck(self.lib.fm3d_allgather_dev(self._h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr), C.c_size_t(bytes_per_rank)))
+
+    def pack_shard_dev(self, cap, rank, query_offset, n_match_dev, n_inl_dev, qidx, tidx, dist, src, normals, status, block):
+        self._ck(self.lib.fm3d_pack_shard_dev(self._h, int(cap), int(rank), int(query_offset), C.c_void_p(n_match_dev),
+                                              C.c_void_p(n_inl_dev), C.c_void_p(qidx), C.c_void_p(tidx), C.c_void_p(dist),
+                                              C.c_void_p(src), C.c_void_p(normals), C.c_void_p(status), C.c_void_p(block)))
 
     # ------------------------------------------------------------------ context
     def sync(self):

@@ -133,6 +133,7 @@ void fm3d_ctx_destroy(fm3d_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    fm3d_comm_destroy(ctx);
     for (int i = 0; i < FM3D_SCRATCH_SLOTS; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pyr_mem) cudaFree(ctx->pyr_mem);
@@ -158,6 +159,43 @@ int fm3d_sync(fm3d_ctx* ctx) {
 }
 
 void* fm3d_stream(fm3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// Device memory for callers of the _dev entry points that have no CUDA runtime of their own (the C++ class adapters).
+int fm3d_dev_malloc(fm3d_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return FM3D_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fm3d_fail(ctx, FM3D_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return FM3D_OK;
+}
+
+int fm3d_dev_free(fm3d_ctx* ctx, void* p) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    if (!p) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FM3D_CUDA(ctx, cudaFree(p));
+    return FM3D_OK;
+}
+
+int fm3d_copy_h2d(fm3d_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, bytes == 0 || (dst_dev && src_host));
+    if (int rc = fm3d_bind(ctx)) return rc;
+    if (int rc = fm3d_h2d(ctx, dst_dev, src_host, bytes)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the host buffer may be reused on return
+    return FM3D_OK;
+}
+
+int fm3d_copy_d2h(fm3d_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, bytes == 0 || (dst_host && src_dev));
+    if (int rc = fm3d_bind(ctx)) return rc;
+    if (int rc = fm3d_d2h(ctx, dst_host, src_dev, bytes)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
 
 int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name,
                      int name_len) {

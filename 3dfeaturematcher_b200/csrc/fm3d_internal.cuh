@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/fm3d.h"
 
@@ -72,6 +73,10 @@ struct fm3d_ctx {
     // an asynchronous (_dev) normal search was launched since the last fm3d_sync: its TMA-timeout flag (scratch[1][1])
     // has not been looked at yet
     bool normals_flag_pending = false;
+    // several GPUs (fm3d_comm.cu): ncclComm_t of this context, its rank, collectives enqueued
+    void* comm = nullptr;
+    int comm_nranks = 1, comm_rank = 0;
+    int64_t n_coll = 0;
 };
 
 // ---------------------------------------------------------------- error plumbing

@@ -22,10 +22,14 @@
 namespace {
 
 // One fm3d_ctx per GPU of the process.  FM3D_DEVICE=<i> picks a single device (default 0);
-// FM3D_DEVICES=<i,j,...> lists several: the first is the primary context (matching, triangulation,
-// patches), all of them share the per-feature normal search, each with its own copy of camera, g12 and
-// image pyramids ("each GPU uploads its own copy"; host buffers are the interface, so no
-// collective is needed inside one process).
+// FM3D_DEVICES=<i,j,...> lists several: matching is sharded by query keypoint and the normal search by feature
+// over all of them (contiguous shards, so concatenating the shards reproduces the single-GPU order); triangulation
+// and patch extraction stay on the first.  What every GPU needs in full -- the train descriptors, both frames --
+// is uploaded ONCE to the first GPU and replicated with one ncclBroadcast over NVLink (fm3d_comm_init_all +
+// fm3d_broadcast_all_dev); when NCCL cannot be loaded every GPU gets its own host upload instead (FM3D_NO_NCCL=1
+// forces that).
+bool& host_comm_ok() { static bool ok = false; return ok; }
+
 std::vector<fm3d_ctx*>& host_ctxs() {
     static std::vector<fm3d_ctx*> ctxs;
     if (ctxs.empty()) {
@@ -51,6 +55,8 @@ std::vector<fm3d_ctx*>& host_ctxs() {
             }
             ctxs.push_back(c);
         }
+        if (ctxs.size() > 1 && !getenv("FM3D_NO_NCCL"))
+            host_comm_ok() = fm3d_comm_init_all(ctxs.data(), (int)ctxs.size()) == FM3D_OK;
     }
     return ctxs;
 }
@@ -75,6 +81,77 @@ void for_each_ctx(const char* what, F fn) {
 
 void check(fm3d_ctx* ctx, int rc, const char* what) {
     if (rc != FM3D_OK) throw std::runtime_error(std::string("fm3d: ") + what + ": " + fm3d_last_error(ctx));
+}
+
+// ---- several GPUs: grow-only device buffers per (context, slot), and replication of a host buffer to all contexts
+enum { SLOT_TRAIN = 0, SLOT_QUERY, SLOT_IDX, SLOT_DIST, SLOT_IMG1, SLOT_IMG2, N_SLOTS };
+struct DevBuf { void* p = nullptr; size_t cap = 0; };
+
+void* dev_buf(int k, int slot, size_t bytes) {
+    static std::vector<std::vector<DevBuf> > bufs;
+    if (bufs.size() < host_ctxs().size()) bufs.resize(host_ctxs().size(), std::vector<DevBuf>(N_SLOTS));
+    DevBuf& b = bufs[k][slot];
+    if (b.cap < bytes) {
+        fm3d_ctx* c = host_ctxs()[k];
+        if (b.p) check(c, fm3d_dev_free(c, b.p), "dev_free");
+        b.p = nullptr; b.cap = 0;
+        check(c, fm3d_dev_malloc(c, bytes, &b.p), "dev_malloc");
+        b.cap = bytes;
+    }
+    return b.p;
+}
+
+// host bytes -> slot `slot` of every context.  One upload + ONE ncclBroadcast over NVLink, or one upload per GPU.
+std::vector<void*> replicate(int slot, const void* host, size_t bytes) {
+    std::vector<fm3d_ctx*>& cs = host_ctxs();
+    std::vector<void*> dev(cs.size());
+    for (size_t k = 0; k < cs.size(); k++) dev[k] = dev_buf((int)k, slot, bytes);     // same thread: allocation is not re-entrant
+    if (host_comm_ok()) {
+        check(cs[0], fm3d_copy_h2d(cs[0], dev[0], host, bytes), "copy_h2d");
+        check(cs[0], fm3d_broadcast_all_dev(cs.data(), (int)cs.size(), dev.data(), bytes, 0), "broadcast");
+        for (size_t k = 0; k < cs.size(); k++) check(cs[k], fm3d_sync(cs[k]), "sync");
+    } else {
+        for_each_ctx("copy_h2d", [&](int k) { return fm3d_copy_h2d(cs[k], dev[k], host, bytes); });
+    }
+    return dev;
+}
+
+// continuous copy of a matrix's rows (descriptor matrices usually are; a ROI is not)
+const unsigned char* packed_rows(const cv::Mat& m, std::vector<unsigned char>& tmp) {
+    const size_t row = (size_t)m.cols * m.elemSize();
+    if (m.isContinuous()) return m.ptr<unsigned char>(0);
+    tmp.resize(row * m.rows);
+    for (int r = 0; r < m.rows; r++) memcpy(tmp.data() + row * r, m.ptr<unsigned char>(r), row);
+    return tmp.data();
+}
+
+// Exact 2-NN of every row of q in t, query rows sharded over the GPUs of the process (descriptorsmatcher.cpp:84-85,101,117).
+void knn_sharded(bool binary, const cv::Mat& q, const cv::Mat& t, std::vector<int32_t>& idx, std::vector<float>& dist) {
+    std::vector<fm3d_ctx*>& cs = host_ctxs();
+    const int G = (int)cs.size(), nq = q.rows, nt = t.rows, cols = q.cols;
+    const size_t row = (size_t)cols * q.elemSize();
+    std::vector<unsigned char> tq, tt;
+    const unsigned char* qh = packed_rows(q, tq);
+    const unsigned char* th = packed_rows(t, tt);
+    std::vector<void*> train = replicate(SLOT_TRAIN, th, row * nt);
+    std::vector<void*> dq(G), di(G), dd(G);
+    for (int k = 0; k < G; k++) {
+        const int lo = (int)((long long)nq * k / G), hi = (int)((long long)nq * (k + 1) / G), n = hi - lo;
+        dq[k] = dev_buf(k, SLOT_QUERY, row * (n > 0 ? n : 1));
+        di[k] = dev_buf(k, SLOT_IDX, sizeof(int32_t) * 2 * (n > 0 ? n : 1));
+        dd[k] = dev_buf(k, SLOT_DIST, sizeof(float) * 2 * (n > 0 ? n : 1));
+    }
+    for_each_ctx("knn (sharded)", [&](int k) {
+        const int lo = (int)((long long)nq * k / G), hi = (int)((long long)nq * (k + 1) / G), n = hi - lo;
+        if (n <= 0) return (int)FM3D_OK;
+        fm3d_ctx* c = cs[k];
+        if (int rc = fm3d_copy_h2d(c, dq[k], qh + row * lo, row * n)) return rc;
+        int rc = binary ? fm3d_match_knn2_hamming_dev(c, (const uint8_t*)dq[k], n, (const uint8_t*)train[k], nt, cols, (int32_t*)di[k], (float*)dd[k])
+                        : fm3d_match_knn2_f32_dev(c, (const float*)dq[k], n, (const float*)train[k], nt, cols, (int32_t*)di[k], (float*)dd[k]);
+        if (rc) return rc;
+        if (int r2 = fm3d_copy_d2h(c, idx.data() + 2 * (size_t)lo, di[k], sizeof(int32_t) * 2 * n)) return r2;
+        return fm3d_copy_d2h(c, dist.data() + 2 * (size_t)lo, dd[k], sizeof(float) * 2 * n);
+    });
 }
 
 }  // namespace
@@ -306,11 +383,13 @@ void DescriptorsMatcher::knn(const cv::Mat& q, const cv::Mat& t, std::vector<std
     const int nq = q.rows, nt = t.rows;
     std::vector<int32_t> idx((size_t)nq * 2, -1);
     std::vector<float> dist((size_t)nq * 2, 0.f);
-    if (binary_) {
-        if (q.depth() != CV_8U) throw std::runtime_error("fm3d: binary extractor needs CV_8U descriptors");
+    if (binary_ && q.depth() != CV_8U) throw std::runtime_error("fm3d: binary extractor needs CV_8U descriptors");
+    if (!binary_ && q.depth() != CV_32F) throw std::runtime_error("fm3d: float extractor needs CV_32F descriptors");
+    if (host_ctxs().size() > 1 && nq > 0 && nt > 0) {
+        knn_sharded(binary_, q, t, idx, dist);
+    } else if (binary_) {
         check(ctx, fm3d_match_knn2_hamming(ctx, q.ptr<uint8_t>(), nq, t.ptr<uint8_t>(), nt, q.cols, idx.data(), dist.data()), "knn (hamming)");
     } else {
-        if (q.depth() != CV_32F) throw std::runtime_error("fm3d: float extractor needs CV_32F descriptors");
         check(ctx, fm3d_match_knn2_f32(ctx, q.ptr<float>(), nq, t.ptr<float>(), nt, q.cols, idx.data(), dist.data()), "knn (L2)");
     }
     out.clear();
@@ -344,7 +423,22 @@ void DescriptorsMatcher::compareWithNNDR(double epsilon, std::vector<cv::DMatch>
     std::vector<float> d(nq);
     mutual_.assign(nq, 0);
     int n = 0;
-    if (binary_)
+    if (host_ctxs().size() > 1 && nq > 0 && nt > 0) {
+        // several GPUs: the 2-NN lists of the query shards, then the reference's own loop (descriptorsmatcher.cpp:119-129) on the
+        // host -- the comparison in double on the float distances -- and the mutual flag from the role-swapped search
+        std::vector<int32_t> ab((size_t)nq * 2, -1), ba((size_t)nt * 2, -1);
+        std::vector<float> dab((size_t)nq * 2, 0.f), dba((size_t)nt * 2, 0.f);
+        knn_sharded(binary_, da, db, ab, dab);
+        knn_sharded(binary_, db, da, ba, dba);
+        for (int i = 0; i < nq; i++) {
+            if (ab[2 * i] < 0 || ab[2 * i + 1] < 0) continue;
+            if ((double)dab[2 * i] <= epsilon * (double)dab[2 * i + 1]) {
+                qi[n] = i; ti[n] = ab[2 * i]; d[n] = dab[2 * i];
+                mutual_[n] = ba[2 * (size_t)ab[2 * i]] == i ? 1 : 0;
+                n++;
+            }
+        }
+    } else if (binary_)
         check(ctx, fm3d_match_nndr_hamming(ctx, da.ptr<uint8_t>(), nq, db.ptr<uint8_t>(), nt, da.cols, epsilon, qi.data(), ti.data(),
                                            d.data(), mutual_.data(), &n), "compareWithNNDR");
     else
@@ -420,6 +514,20 @@ void SingleCameraTriangulator::setImages(const cv::Mat& img1, const cv::Mat& img
     img_1_ = img1; img_2_ = img2;  // shallow, like new cv::Mat(img) in the reference (:118-119)
     const int levels = pyramids_;
     const int s1 = (int)img1.step1(), s2 = (int)img2.step1();   // CV_8UC1: elements = bytes; step1() exists in cv::Mat and in the stand-in
+    if (host_ctxs().size() > 1 && host_comm_ok()) {
+        // several GPUs: both frames go to the first GPU once and reach the others with one ncclBroadcast each (NVLink);
+        // every GPU then builds its own pyramids (K4 is cheaper than shipping them: 1.33 x the frame)
+        const int w = img1.cols, h = img1.rows;
+        std::vector<unsigned char> t1, t2;
+        const size_t bytes = (size_t)w * h;
+        std::vector<void*> d1 = replicate(SLOT_IMG1, packed_rows(img1, t1), bytes);
+        std::vector<void*> d2 = replicate(SLOT_IMG2, packed_rows(img2, t2), bytes);
+        for_each_ctx("set_images", [&](int k) {
+            if (int rc = fm3d_set_images_dev(host_ctxs()[k], (const uint8_t*)d1[k], (const uint8_t*)d2[k], w, h, w, levels)) return rc;
+            return fm3d_sync(host_ctxs()[k]);
+        });
+        return;
+    }
     for_each_ctx("set_images", [&](int k) {
         return fm3d_set_images2(host_ctxs()[k], img1.data, s1, img2.data, s2, img1.cols, img1.rows, levels);
     });

@@ -270,15 +270,13 @@ class PathState:
             self.d_nfev = torch.zeros((nq, self.L1), dtype=i32, device=dev)
             self.d_npen = torch.zeros(nq, dtype=i32, device=dev)
             self.d_cost = torch.empty(nq, dtype=f64, device=dev)
-            # ONE all-gather per step: (query, train, distance) of the matches; (match row, normal, status) of the inliers
-            cap = max(shard.shard_sizes(nq_glob, world))
-            self.gatherer = shard.ShardGather([("qi", (), i32, 0), ("ti", (), i32, 0), ("d", (), f32, 0), ("src", (), i32, 1),
-                                               ("normals", (3,), f64, 1), ("status", (), i32, 1)], cap, dev, rank)
-            self.cap = cap
-            if cap > nq:        # ragged last shard: the gather reads `cap` rows of every part
-                grow = lambda t: torch.cat([t, torch.zeros((cap - nq,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)])   # noqa: E731
-                self.d_qi, self.d_ti, self.d_do, self.d_src = grow(self.d_qi), grow(self.d_ti), grow(self.d_do), grow(self.d_src)
-                self.d_normals, self.d_status = grow(self.d_normals), grow(self.d_status)
+            # ONE all-gather per step (libfm3d's own NCCL communicator): a block per rank with (query, train, distance) of its
+            # matches and (match row, normal, status) of its inliers, written by fm3d_pack_shard_dev from the device-resident counts
+            self.cap = cap = max(shard.shard_sizes(nq_glob, world))
+            self.layout = api.shard_block_layout(cap)
+            self.send = torch.zeros(self.layout.bytes, dtype=torch.uint8, device=dev)
+            self.recv = torch.zeros((world, self.layout.bytes), dtype=torch.uint8, device=dev) if world > 1 else self.send.view(1, -1)
+            self.api = api
         stream.synchronize()
 
     def bind(self):
@@ -290,7 +288,8 @@ class PathState:
         torch, ctx, stream = self.torch, self.ctx, self.stream
         with torch.cuda.stream(stream):
             if events: events[0].record(stream)
-            self.rep.broadcast_(0)
+            if self.world > 1:      # ONE broadcast: train descriptors + train keypoints + both frames live in one allocation
+                ctx.broadcast_dev(self.rep.buf.data_ptr(), self.rep.buf.numel(), 0)
             ctx.match_knn2_f32_dev(self.d_q.data_ptr(), self.nq, self.rep["t"].data_ptr(), self.nt, 128, self.d_idx.data_ptr(), self.d_dist.data_ptr())
             ctx.nndr_filter_dev(self.d_idx.data_ptr(), self.d_dist.data_ptr(), self.nq, NNDR_EPS, self.d_qi.data_ptr(), self.d_ti.data_ptr(),
                                 self.d_do.data_ptr(), self.d_nm.data_ptr())
@@ -305,8 +304,11 @@ class PathState:
             ctx.optimize_normals_dev(self.d_xyz.data_ptr(), n_inl, self.r, EPS_LMMIN, penalty, self.d_normals.data_ptr(),
                                      self.d_status.data_ptr(), self.d_nfev.data_ptr(), self.d_npen.data_ptr(), self.d_cost.data_ptr())
             if events: events[4].record(stream)
-            self.gatherer.gather({"qi": self.d_qi, "ti": self.d_ti, "d": self.d_do, "src": self.d_src, "normals": self.d_normals,
-                                  "status": self.d_status}, (self.d_nm, self.d_ninl))
+            ctx.pack_shard_dev(self.cap, self.rank, self.lo, self.d_nm.data_ptr(), self.d_ninl.data_ptr(), self.d_qi.data_ptr(),
+                               self.d_ti.data_ptr(), self.d_do.data_ptr(), self.d_src.data_ptr(), self.d_normals.data_ptr(),
+                               self.d_status.data_ptr(), self.send.data_ptr())
+            if self.world > 1:
+                ctx.allgather_dev(self.send.data_ptr(), self.recv.data_ptr(), self.layout.bytes)
             if events: events[5].record(stream)
         return n_match, n_inl
 
@@ -314,9 +316,8 @@ class PathState:
         """The same pass through the host-buffer C-ABI entry points (copies inside)."""
         ctx = self.ctx
         if self.world > 1:
-            with self.torch.cuda.stream(self.stream):
-                self.rep.broadcast_(0)
-            self.stream.synchronize()
+            ctx.broadcast_dev(self.rep.buf.data_ptr(), self.rep.buf.numel(), 0)
+            ctx.sync()
         qi, ti, d = ctx.match_nndr(self.h_q.numpy(), self.h_t.numpy(), NNDR_EPS)
         xyz_all, mask, xyz, src = ctx.triangulate(self.h_kp1.numpy(), self.h_kp2.numpy(), qi, ti)
         ctx.set_images(self.h_img1.numpy(), self.h_img2.numpy(), self.pyramids)
@@ -353,12 +354,13 @@ class PathState:
         oracle stays off the penalty wall)."""
         from oracle import oracle_c as orc
         shard, case, cam = self.shard, self.case, self.cam
-        out, counts = self.gatherer.unpack()
+        out, hdr = self.api.unpack_shard_blocks(self.recv.cpu().numpy(), self.layout)
+        counts = hdr[:, :2].tolist()
         los = [shard.shard_bounds(case["desc1"].shape[0], self.world, r)[0] for r in range(self.world)]
-        qi = out["qi"].cpu().numpy().astype(np.int64)
-        ti, dd = out["ti"].cpu().numpy(), out["d"].cpu().numpy()
-        rank_of_match = np.repeat(np.arange(self.world), [c[0] for c in counts])
-        q_glob = qi + np.asarray(los)[rank_of_match]
+        if hdr[:, 2].tolist() != list(range(self.world)) or hdr[:, 4].tolist() != los:
+            return f"block headers out of order: ranks {hdr[:, 2].tolist()} offsets {hdr[:, 4].tolist()}"
+        q_glob = out["qidx"].astype(np.int64)               # fm3d_pack_shard_dev stores GLOBAL query indices
+        ti, dd = out["tidx"], out["dist"]
         if not (np.diff(q_glob) > 0).all():
             return "gathered query indices are not ascending"
         rng = np.random.default_rng(11)
@@ -370,8 +372,8 @@ class PathState:
         if not (np.array_equal(q_glob[in_sel], sel[oq]) and np.array_equal(ti[in_sel], ot) and np.array_equal(dd[in_sel], od)):
             return f"matches of the sampled queries differ from the oracle ({int(in_sel.sum())} gathered, {len(oq)} expected)"
         # normals: inlier k of rank r refers to match row src[k] of rank r
-        src = out["src"].cpu().numpy().astype(np.int64)
-        normals, status = out["normals"].cpu().numpy(), out["status"].cpu().numpy()
+        src = out["src"].astype(np.int64)
+        normals, status = out["normals"], out["status"]
         rank_of_inl = np.repeat(np.arange(self.world), [c[1] for c in counts])
         match_base = np.concatenate([[0], np.cumsum([c[0] for c in counts])])[:-1]
         row = src + match_base[rank_of_inl]                       # row in the gathered match list
@@ -388,11 +390,22 @@ class PathState:
         interior = (o["status"] == 0) & (o["npenalty"] == 0)
         cosang = np.clip((normals[pick] * o["normals"]).sum(1), -1, 1)
         ang = np.degrees(np.arccos(cosang))
-        if interior.any() and ang[interior].max() > 0.5:
-            return f"normals differ from the oracle by {ang[interior].max():.3f} deg"
-        return {"result": "ok", "ranks_with_matches": int(sum(c[0] > 0 for c in counts)), "queries_checked": int(len(sel)),
+        far = interior & (ang > 0.5)
+        better = 0
+        if far.any():
+            # allowed only where the device found a strictly lower value of the reference's own cost function (at 4K the
+            # reference's forward-difference Jacobian stalls lmfit at the coarse levels: tests/test_gpu_parity_scale.py)
+            def cost_at(nrm):
+                pt = np.stack([np.arctan2(nrm[:, 1], nrm[:, 0]), np.arctan2(nrm[:, 2], np.hypot(nrm[:, 0], nrm[:, 1]))], 1)
+                return orc.evaluate_cost(cam.K, cam.dist, cam.g12, cam.z_min, cam.z_max, case["scene"].img1, case["scene"].img2,
+                                         self.pyramids, np.ascontiguousarray(o_xyz[far]), pt, self.r, 0, 2)[0]
+            gc, oc = cost_at(normals[pick][far]), cost_at(o["normals"][far])
+            if not (gc < oc * (1 - 1e-3)).all():
+                return f"normals differ from the oracle by {ang[far].max():.3f} deg without a lower cost"
+            better = int(far.sum())
+        return {"result": "ok", "beyond_0p5_deg_with_lower_cost_than_the_oracle": better, "ranks_with_matches": int(sum(c[0] > 0 for c in counts)), "queries_checked": int(len(sel)),
                 "matches_checked": int(in_sel.sum()), "normals_checked": int(len(pick)),
-                "normals_interior": int(interior.sum()), "max_angle_deg_interior": float(ang[interior].max()) if interior.any() else None,
+                "normals_interior": int(interior.sum()), "max_angle_deg_interior": float(ang[interior & ~far].max()) if (interior & ~far).any() else None,
                 "ranks_in_normal_sample": int(len(np.unique(rank_of_inl[pick])))}
 
 
@@ -441,6 +454,11 @@ def run_gpu_arm(args):
 
     ctx = api.Context(local_rank)
     info = ctx.device_info()
+    if world > 1:
+        # libfm3d's own communicator: rank 0 creates the NCCL id, torch.distributed carries the 128 bytes (plumbing only)
+        ident = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        ctx.comm_init_rank(ident[0], world, rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     case = make_workload(world, rank)
     st = PathState(torch, api, shard, ctx, stream, dev, case, world, rank, PIXELS_RAY, PYRAMIDS)

@@ -26,6 +26,7 @@
 #ifndef FM3D_H_
 #define FM3D_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -43,7 +44,8 @@ typedef enum fm3d_status {
     FM3D_ERR_NO_DEVICE = -3,
     FM3D_ERR_STATE = -4,       /* camera / images / pose not set yet */
     FM3D_ERR_UNSUPPORTED = -5,
-    FM3D_ERR_NOMEM = -6
+    FM3D_ERR_NOMEM = -6,
+    FM3D_ERR_COMM = -7         /* NCCL could not be loaded, or a collective failed */
 } fm3d_status;
 
 /* Per-feature outcome of the normal optimiser.  The reference silently erases a failed
@@ -91,6 +93,13 @@ const char* fm3d_last_error(const fm3d_ctx* ctx);
 int fm3d_sync(fm3d_ctx* ctx);
 /* cudaStream_t of the context, as an opaque pointer (for event timing by the caller). */
 void* fm3d_stream(fm3d_ctx* ctx);
+/* Device memory of the context's GPU for callers of the _dev entry points that do not link a CUDA runtime
+ * themselves (the C++ class adapters when they shard over several GPUs).  The copies run on the context's
+ * stream and return when they are complete. */
+int fm3d_dev_malloc(fm3d_ctx* ctx, size_t bytes, void** out);
+int fm3d_dev_free(fm3d_ctx* ctx, void* p);
+int fm3d_copy_h2d(fm3d_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int fm3d_copy_d2h(fm3d_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
                      char* name, int name_len);
 
@@ -125,6 +134,49 @@ int fm3d_get_option(fm3d_ctx* ctx, const char* key, double* value);
 /* Counters of the last call that launched kernels on this context (for benchmarking):
  * number of kernel launches and of bulk-copy (memcpy/memset) operations. */
 int fm3d_get_launch_counters(fm3d_ctx* ctx, int64_t* kernel_launches, int64_t* copies);
+
+/* ------------------------------------------------------------- several GPUs ---- */
+
+/* The path shards by query keypoint / by feature over the GPUs of one box (the reference is one
+ * sequential loop, Triangulator/normaloptimizer.cpp:335-449, and has no counterpart for any of this).  Two exchanges
+ * exist, both on the context's stream, both asynchronous: replicate the inputs every GPU needs in full (train
+ * descriptors, train keypoints, both frames: pack them into ONE device buffer and call fm3d_broadcast_dev once) and
+ * collect the per-shard results (fm3d_pack_shard_dev writes one fixed-size block from device-resident counts,
+ * fm3d_allgather_dev gathers the blocks of all ranks).  NCCL is loaded at run time; without it these calls return
+ * FM3D_ERR_COMM and everything else keeps working.
+ *
+ * One process per GPU: rank 0 calls fm3d_comm_unique_id and hands the 128 bytes to the other ranks over whatever
+ * channel the application has; every rank then calls fm3d_comm_init_rank (collective).
+ * One process, several GPUs: fm3d_comm_init_all over the contexts of the process; use the *_all_dev forms, which issue
+ * the per-context calls inside one NCCL group (ctxs[k] is rank k). */
+#define FM3D_COMM_ID_BYTES 128
+int fm3d_comm_unique_id(uint8_t id[FM3D_COMM_ID_BYTES]);
+int fm3d_comm_init_rank(fm3d_ctx* ctx, const uint8_t id[FM3D_COMM_ID_BYTES], int nranks, int rank);
+int fm3d_comm_init_all(fm3d_ctx** ctxs, int n);
+int fm3d_comm_info(fm3d_ctx* ctx, int* nranks, int* rank, int* nccl_version);
+int fm3d_comm_destroy(fm3d_ctx* ctx);
+int fm3d_broadcast_dev(fm3d_ctx* ctx, void* buf, size_t bytes, int root);
+int fm3d_allgather_dev(fm3d_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+int fm3d_broadcast_all_dev(fm3d_ctx** ctxs, int n, void* const* bufs, size_t bytes, int root);
+int fm3d_allgather_all_dev(fm3d_ctx** ctxs, int n, const void* const* send, void* const* recv,
+                           size_t bytes_per_rank);
+
+/* Block a rank contributes to the gather of a step.  Header (int32): [0] matches, [1] inliers, [2] rank, [3] cap,
+ * [4] query offset of the shard; then `cap` rows of every part at the byte offsets below (rows beyond the counts are
+ * zero).  qidx are GLOBAL query indices (local index + query_offset), so the blocks of all ranks in rank order list the
+ * matches in ascending query order, as DescriptorsMatcher::compareWithNNDR returns them (descriptorsmatcher.cpp:119-129);
+ * src_idx[k] is the row, in the same block's match list, of the match inlier k was triangulated from. */
+typedef struct fm3d_shard_layout {
+    int cap;
+    size_t off_qidx, off_tidx, off_dist;      /* int32, int32, float   x cap : the NNDR matches of the shard          */
+    size_t off_src, off_normals, off_status;  /* int32, 3 x double, int32 x cap : the depth-gated, refined features   */
+    size_t bytes;                              /* size of one block (multiple of 256)                                  */
+} fm3d_shard_layout;
+int fm3d_shard_block_layout(int cap, fm3d_shard_layout* layout);
+int fm3d_pack_shard_dev(fm3d_ctx* ctx, int cap, int rank, int query_offset, const int32_t* n_match_dev,
+                        const int32_t* n_inl_dev, const int32_t* qidx, const int32_t* tidx,
+                        const float* dist, const int32_t* src_idx, const double* normals,
+                        const int32_t* status, void* block);
 
 /* ------------------------------------------------------------------- camera ---- */
 

@@ -54,8 +54,9 @@ int main(int argc, char** argv) {
         std::vector<std::vector<cv::DMatch> > m1, m2, ab, ba;
         std::vector<cv::DMatch> nndr;
         dm.compare(m1, ka, kb, da, db);
-        // poison the outputs: a second call must overwrite them (stale descriptors of a previous frame must never be matched)
-        if (!da.empty()) memset(da.data, 0, da.rows * da.step());
+        // poison the outputs: a second call must overwrite them (stale descriptors of a previous frame must never be matched).
+        // Only for detected features: injected ones are shallow cv::Mat copies of the caller's own matrices.
+        if (strcmp(argv[3], "-") == 0 && !da.empty()) memset(da.data, 0, da.rows * da.step());
         ka.clear();
         dm.compare(m2, ka, kb, da, db);
         dm.crosscompare(ab, ba, ka, kb, da, db);

@@ -607,3 +607,30 @@ def test_compare_and_crosscompare_through_the_adapters(tmp_path, source):
         np.testing.assert_array_equal(half["q"], oq)
         np.testing.assert_array_equal(half["t"], ot)
         np.testing.assert_array_equal(half["d"], odd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nccl", ["nccl", "host-uploads"])
+def test_adapters_shard_the_matching_over_the_gpus_of_the_process(tmp_path, nccl):
+    """FM3D_DEVICES=0,1: compare / crosscompare / compareWithNNDR shard the QUERY rows over both GPUs, the train set reaches
+    the second GPU by one ncclBroadcast (or by its own host upload with FM3D_NO_NCCL=1); kNN lists, NNDR matches and
+    distances must be byte-identical to the single-GPU run."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in the process")
+    exe = os.path.join(ROOT, "tests", "_build", "compare_main")
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 300, 1000, r)
+    tmp = str(tmp_path)
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp)
+    outs = []
+    for devices in ("0", "0,1", "1,0"):
+        env = dict(os.environ, FM3D_DEVICES=devices)
+        if nccl != "nccl":
+            env["FM3D_NO_NCCL"] = "1"
+        out = os.path.join(tmp, f"out_{devices.replace(',', '_')}.bin")
+        p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), os.path.join(tmp, "features.bin"), out],
+                           capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 1000

@@ -89,9 +89,22 @@ def _oracle_chain(ctx, case, r, pyramids, eps_m, cmpp, penalty_mode):
     import importlib
     synth = importlib.import_module("3dfeaturematcher_b200.synth")
     gravity = np.linalg.inv(cv2.Rodrigues(np.asarray(synth.SETTINGS_RODRIGUES_IC, float).reshape(3, 1))[0]) @ np.array([0.0, 0.0, -1.0])
+    # FAST corners lie anywhere in the frame: for a few of them an LM iterate leaves the image or the bounding box and the
+    # feature is dropped -- which iterate does is trajectory-dependent, so the device run (analytic Jacobian)
+    # and the oracle (forward differences) may drop different marginal features.  The device statuses of the same points are
+    # taken through the C-ABI (the kernel is deterministic); they must agree with the oracle on >= 99 % of the features, and
+    # the artefacts are compared on the features both keep.
+    ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max)
+    ctx.set_g12(cam.g12)
+    ctx.set_images(case["scene"].img1, case["scene"].img2, pyramids)
+    dev = ctx.optimize_normals(o_xyz, r, 1e-10, penalty_mode)
+    dev_ok = dev["status"] == 0
+    assert (dev["status"] == o["status"]).mean() >= 0.99, (dev["status"] != o["status"]).sum()
     frames = orc.feature_frames(o_xyz[ok], o["normals"][ok], gravity)
     patches, points = orc.extract_patches(cam.K, cam.dist, case["scene"].img1, frames, eps_m, cmpp, want_points=True)
-    return dict(kps=kps, q=oq, t=ot, mask=o_mask.astype(bool), xyz=o_xyz, ok=ok, patches=patches, points=points)
+    both = ok & dev_ok
+    return dict(kps=kps, q=oq, t=ot, mask=o_mask.astype(bool), xyz=o_xyz, ok=ok, dev_ok=dev_ok, patches=patches, points=points,
+                in_oracle=np.cumsum(ok)[both] - 1, in_device=np.cumsum(dev_ok)[both] - 1)
 
 
 @pytest.mark.gpu
@@ -118,21 +131,27 @@ def test_unchanged_main_cpp_runs_and_writes_its_three_artefacts(ctx, tmp_path):
     np.testing.assert_array_equal(window, o_window)
 
     # patch_<k>.pgm: one per feature that survived the normal search, in order
-    n_ok = int(o["ok"].sum())
+    n_dev = int(o["dev_ok"].sum())
     files = sorted(f for f in os.listdir(tmp) if f.startswith("patch_"))
-    assert len(files) == n_ok and not os.path.exists(os.path.join(tmp, f"patch_{n_ok}.pgm"))
+    assert len(files) == n_dev and not os.path.exists(os.path.join(tmp, f"patch_{n_dev}.pgm"))
     S = orc.patch_size(eps_m, cmpp)
-    got = np.stack([_read_pnm(os.path.join(tmp, f"patch_{k}.pgm")) for k in range(n_ok)])
-    assert got.shape == (n_ok, S, S)
+    got = np.stack([_read_pnm(os.path.join(tmp, f"patch_{k}.pgm")) for k in range(n_dev)])
+    assert got.shape == (n_dev, S, S)
     # the device normals differ from the oracle's by ~0.002 deg: sampling positions move by ~1e-3 pixel, truncated gray levels by +-1
-    diff = np.abs(got.astype(int) - o["patches"].astype(int))
+    diff = np.abs(got[o["in_device"]].astype(int) - o["patches"][o["in_oracle"]].astype(int))
     assert (diff <= 2).mean() > 0.999 and (diff == 0).mean() > 0.8, ((diff <= 2).mean(), (diff == 0).mean())
 
     # projectedPatches.pgm: image points of every patch painted in colours[i] (main.cpp:190-194; colours are per INLIER, D5)
     proj = _read_pnm(os.path.join(tmp, "projectedPatches.pgm"))
-    o_proj = draw_cv.draw_back_projected_points(case["scene"].img1, o["points"].reshape(n_ok, S * S, 2), np.asarray(colours)[:n_ok, :3])
-    assert proj.shape == o_proj.shape
-    assert (proj == o_proj).all(axis=2).mean() > 0.995
+    n_ok = int(o["ok"].sum())
+    pts = o["points"].reshape(n_ok, S * S, 2)
+    if n_dev == n_ok and (o["dev_ok"] == o["ok"]).all():
+        o_proj = draw_cv.draw_back_projected_points(case["scene"].img1, pts, np.asarray(colours)[:n_ok, :3])
+        assert proj.shape == o_proj.shape and (proj == o_proj).all(axis=2).mean() > 0.995
+    else:       # survivor lists differ by a marginal feature: patch i of the device run takes colours[i] of ITS numbering (D5)
+        o_proj = draw_cv.draw_back_projected_points(case["scene"].img1, pts[o["in_oracle"]], np.asarray(colours)[o["in_device"], :3])
+        painted = (o_proj != cv2.cvtColor(case["scene"].img1, cv2.COLOR_GRAY2BGR)).any(axis=2)
+        assert proj.shape == o_proj.shape and (proj[painted] == o_proj[painted]).all(axis=1).mean() > 0.98
 
 
 @pytest.mark.gpu
@@ -147,9 +166,9 @@ def test_mosaic_constructor_runs_the_pipeline_on_the_adapters(ctx, tmp_path):
     p = subprocess.run([REF_MOSAIC, "-s", os.path.join(tmp, "settings.yml")], capture_output=True, text=True, env=env, cwd=tmp, timeout=600)
     assert p.returncode == 0 and "MOSAIC constructed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
     o = _oracle_chain(ctx, case, r, pyramids, eps_m, cmpp, 1)
-    n_ok = int(o["ok"].sum())
+    n_dev = int(o["dev_ok"].sum())
     files = [f for f in os.listdir(tmp) if f.startswith("patch_")]
-    assert len(files) == n_ok >= 20
-    got = np.stack([_read_pnm(os.path.join(tmp, f"patch_{k}.pgm")) for k in range(n_ok)])
-    diff = np.abs(got.astype(int) - o["patches"].astype(int))
+    assert len(files) == n_dev >= 20
+    got = np.stack([_read_pnm(os.path.join(tmp, f"patch_{k}.pgm")) for k in range(n_dev)])
+    diff = np.abs(got[o["in_device"]].astype(int) - o["patches"][o["in_oracle"]].astype(int))
     assert (diff <= 2).mean() > 0.999 and (diff == 0).mean() > 0.8
