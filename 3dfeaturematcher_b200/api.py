@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfm3d.so")
+# FM3D_LIB: another build of the same library (tools/build_variant.py: A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("FM3D_LIB") or os.path.join(_HERE, "libfm3d.so")
 
 FEAT_OK, FEAT_NO_PIXELS, FEAT_ABORT_BBOX, FEAT_ABORT_PIXEL, FEAT_ABORT_NAN = 0, 1, 2, 3, 4
 PENALTY_FABS, PENALTY_INT_ABS, PENALTY_OFF = 0, 1, 2

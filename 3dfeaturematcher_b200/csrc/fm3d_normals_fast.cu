@@ -54,6 +54,11 @@ namespace {
 #ifndef FM3D_NORMALS_UNROLL2
 #define FM3D_NORMALS_UNROLL2 1
 #endif
+// 1: the per-group ray / image-1 scratch (global memory, meant to stay in L2) is read and written with an L2 evict_last
+// cache hint, everything else keeps the default policy
+#ifndef FM3D_NORMALS_L2HINT
+#define FM3D_NORMALS_L2HINT 0
+#endif
 constexpr int FAST_NT = FM3D_NORMALS_NT;
 constexpr float FLOOR_MAGIC = 12582912.0f;          // 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x)
 constexpr unsigned FLOOR_MAGIC_BITS = 0x4B400000u;
@@ -284,6 +289,27 @@ __device__ __forceinline__ void ray_set(float2* rays, int idx, float x, float y)
     r[0] = x; r[2] = y;
 }
 
+#if FM3D_NORMALS_L2HINT
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ld_scratch(const ulonglong2* a, uint64_t pol) {
+    ulonglong2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ f2 ld_scratch(const f2* a, uint64_t pol) {
+    f2 v;
+    asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+    return v;
+}
+#define LD_SCRATCH(ptr) ld_scratch((ptr), l2pol)
+#else
+#define LD_SCRATCH(ptr) (*(ptr))
+#endif
+
 struct Acc2 {      // Jacobian sums of the packed loop: lanes are added at the end of the pass
     f2 a[9];
 };
@@ -415,21 +441,24 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
     const int npair = m >> 1;
     int p = tid;
     if (PREFETCH) {
+#if FM3D_NORMALS_L2HINT
+        const uint64_t l2pol = l2_evict_last_policy();
+#endif
         // rays / image-1 samples stream from the L2-resident scratch: the loads of the next pair
         // are issued before the current one is evaluated
         ulonglong2 r = make_ulonglong2(0ull, 0ull);
         f2 I = 0ull;
-        if (p < npair) { r = rp[p]; I = ip[p]; }
+        if (p < npair) { r = LD_SCRATCH(rp + p); I = LD_SCRATCH(ip + p); }
 #if FM3D_NORMALS_UNROLL2
         ulonglong2 r2 = make_ulonglong2(0ull, 0ull);
         f2 I2 = 0ull;
-        if (p + NT < npair) { r2 = rp[p + NT]; I2 = ip[p + NT]; }
+        if (p + NT < npair) { r2 = LD_SCRATCH(rp + p + NT); I2 = LD_SCRATCH(ip + p + NT); }
         for (; p + NT < npair; p += 2 * NT) {
             const ulonglong2 cr = r, cr2 = r2;
             const f2 cI = I, cI2 = I2;
             const int nx = p + 2 * NT;
-            if (nx < npair) { r = rp[nx]; I = ip[nx]; }
-            if (nx + NT < npair) { r2 = rp[nx + NT]; I2 = ip[nx + NT]; }
+            if (nx < npair) { r = LD_SCRATCH(rp + nx); I = LD_SCRATCH(ip + nx); }
+            if (nx + NT < npair) { r2 = LD_SCRATCH(rp + nx + NT); I2 = LD_SCRATCH(ip + nx + NT); }
             eval_pixel_pair<JAC, NCC>(P, L, cr.x, cr.y, cI, acc, acc2);
             eval_pixel_pair<JAC, NCC>(P, L, cr2.x, cr2.y, cI2, acc, acc2);
         }
@@ -439,7 +468,7 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
             const ulonglong2 cr = r;
             const f2 cI = I;
             const int nx = p + NT;
-            if (nx < npair) { r = rp[nx]; I = ip[nx]; }
+            if (nx < npair) { r = LD_SCRATCH(rp + nx); I = LD_SCRATCH(ip + nx); }
             eval_pixel_pair<JAC, NCC>(P, L, cr.x, cr.y, cI, acc, acc2);
         }
 #endif

@@ -175,7 +175,44 @@ def render(cam: SynthCamera, planes, tex, view: int, noise_sigma=0.0, rng=None, 
     return img, facet
 
 
+def _scene_cache_path(width, height, seed, pixels_ray, noise_sigma):
+    """Rendering a 4K pair by exact ray casting takes ~30 s of numpy: scenes are cached (compressed pickle) under
+    $FM3D_SCENE_CACHE or <repo>/tools/_cache when that directory exists.  The key carries a digest of this file, so a
+    cached scene can never come from other generator code."""
+    import hashlib
+    import os
+    root = os.environ.get("FM3D_SCENE_CACHE") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "_cache")
+    if not os.path.isdir(root):
+        return None
+    with open(os.path.abspath(__file__), "rb") as f:
+        digest = hashlib.sha256(f.read()).hexdigest()[:12]
+    return os.path.join(root, f"scene_{width}x{height}_s{seed}_r{pixels_ray}_n{noise_sigma}_{digest}.pkl.gz")
+
+
 def make_scene(width, height, seed, pixels_ray=64, noise_sigma=0.0) -> StereoScene:
+    import gzip
+    import os
+    import pickle
+    path = _scene_cache_path(width, height, seed, pixels_ray, noise_sigma) if width * height >= 1920 * 1080 else None
+    if path and os.path.exists(path):
+        try:
+            with gzip.open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+    scene = _make_scene(width, height, seed, pixels_ray, noise_sigma)
+    if path:
+        try:
+            tmp = path + f".{os.getpid()}.tmp"
+            with gzip.open(tmp, "wb", compresslevel=1) as f:
+                pickle.dump(scene, f, protocol=4)
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return scene
+
+
+def _make_scene(width, height, seed, pixels_ray=64, noise_sigma=0.0) -> StereoScene:
     rng = np.random.default_rng(seed)
     cam = make_camera(width, height, rng)
     planes = make_planes(cam, rng, pixels_ray)
