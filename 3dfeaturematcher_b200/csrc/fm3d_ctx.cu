@@ -219,6 +219,7 @@ static int* fm3d_option_slot(fm3d_ctx* ctx, const char* key) {
     if (!strcmp(key, "normals_tma")) return &ctx->opt_normals_tma;
     if (!strcmp(key, "normals_fast")) return &ctx->opt_normals_fast;
     if (!strcmp(key, "normals_cost")) return &ctx->opt_normals_cost;
+    if (!strcmp(key, "pyramid_fused")) return &ctx->opt_pyramid_fused;
     if (!strcmp(key, "normals_fuse")) return &ctx->opt_normals_fuse;
     if (!strcmp(key, "normals_memo")) return &ctx->opt_normals_memo;
     if (!strcmp(key, "normals_groups")) return &ctx->opt_normals_groups;

@@ -53,6 +53,7 @@ struct fm3d_ctx {
     int opt_normals_fuse = 1;      // fast kernel: Jacobian evaluated together with the first trial of an iteration
     int opt_normals_sweep_batch = 4;  // fast kernel, dense sweep: candidates per pass (1: one pass per candidate)
     int opt_normals_fast = 1;      // 1: fm3d_normals_fast.cu (default), 0: the faithful fp64 kernel
+    int opt_pyramid_fused = 1;     // K4: one fused launch per three pyramid levels (0: one pyrdown_kernel launch per level + copies)
     int opt_normals_cost = 0;      // FM3D_COST_SSD: the reference's residual I1 - I2; FM3D_COST_NCC: zero-mean normalised (fast kernel only)
     // camera
     fm3d_cam cam{};

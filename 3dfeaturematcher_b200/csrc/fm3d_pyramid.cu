@@ -80,6 +80,121 @@ pyrdown_kernel(const uint8_t* __restrict__ src1, const uint8_t* __restrict__ src
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused pyramid: ONE launch copies both frames into level 0 (when they come from caller-owned device memory) and
+// builds up to three cv::pyrDown levels of each.  A CTA owns a B x B tile of the base level (B = 64) and everything above
+// it: it stages the base pixels the tile's share of the top level depends on (85 x 85 for three levels), then computes
+// level after level in shared memory, halos included (recomputed by the neighbouring CTAs: 1.76x the base reads, from L2),
+// and writes only the pixels it owns.  Integer arithmetic, sum of the 25 taps before the single (s + 128) >> 8, so the
+// result is bit-identical with the separable two-pass form (and with cv::pyrDown).  720p, 3 levels, both frames:
+// 480 CTAs, one launch instead of three launches and two device-to-device copies.
+constexpr int FB = 64;                 // base tile edge
+constexpr int FMAXL = 3;               // levels per launch
+constexpr int FE0 = 8 * (FB / 8) + 21; // 85: base extent for three levels; level k extent = (FE0 - 3 * (2^k - 1)) / 2^k
+
+struct FusedArgs {
+    const uint8_t* src[2];             // base level of both images (caller's frames, or level `base` of the pyramid)
+    int src_pitch[2];
+    uint8_t* dst[2];                   // pyramid allocations of both images
+    int w[FMAXL + 1], h[FMAXL + 1], pitch[FMAXL + 1];
+    size_t off[FMAXL + 1];             // byte offsets of base level and the levels built from it
+    int nl;                            // levels built by this launch (0..3)
+    int copy_base;                     // also write the base level into dst (it came from outside the pyramid)
+};
+
+__device__ __forceinline__ int fused_extent(int k) { return (FE0 - 3 * ((1 << k) - 1)) >> k; }   // 85, 41, 19, 8
+
+__global__ void __launch_bounds__(256)
+pyramid_fused_kernel(const FusedArgs A) {
+    __shared__ __align__(16) uint8_t s0[FE0 * FE0];
+    __shared__ uint8_t s1[41 * 41];
+    __shared__ uint8_t s2[19 * 19];
+    __shared__ int s_ix[41 * 5];       // reflected source columns / rows of the level being computed, relative to the tile
+    __shared__ int s_iy[41 * 5];
+    const int img = blockIdx.z, tid = threadIdx.x, L = A.nl;
+    const int T = FB >> L;             // tile edge at the top level
+    // needed index range of every level, top down: [lo, hi] before reflection
+    int lox[FMAXL + 1], hix[FMAXL + 1], loy[FMAXL + 1], hiy[FMAXL + 1];
+#pragma unroll
+    for (int k = FMAXL; k >= 0; k--) {          // fully unrolled: the arrays stay in registers
+        if (k == L) {
+            lox[k] = blockIdx.x * T; hix[k] = min(lox[k] + T, A.w[k]) - 1;
+            loy[k] = blockIdx.y * T; hiy[k] = min(loy[k] + T, A.h[k]) - 1;
+        } else if (k < L) {
+            lox[k] = 2 * lox[k + 1 <= FMAXL ? k + 1 : FMAXL] - 2; hix[k] = 2 * hix[k + 1 <= FMAXL ? k + 1 : FMAXL] + 2;
+            loy[k] = 2 * loy[k + 1 <= FMAXL ? k + 1 : FMAXL] - 2; hiy[k] = 2 * hiy[k + 1 <= FMAXL ? k + 1 : FMAXL] + 2;
+        } else {
+            lox[k] = hix[k] = loy[k] = hiy[k] = 0;
+        }
+    }
+    // stored (clipped) range of every level: [c?, c? + n?)
+    int cx[FMAXL + 1], cy[FMAXL + 1], nx[FMAXL + 1], ny[FMAXL + 1];
+#pragma unroll
+    for (int k = 0; k <= FMAXL; k++) {
+        cx[k] = max(lox[k], 0); nx[k] = k <= L ? min(hix[k], A.w[k] - 1) - cx[k] + 1 : 0;
+        cy[k] = max(loy[k], 0); ny[k] = k <= L ? min(hiy[k], A.h[k] - 1) - cy[k] + 1 : 0;
+    }
+    // ---- base level: stage, and (first launch on caller-owned frames) copy the owned B x B tile into the pyramid
+    {
+        const uint8_t* __restrict__ src = A.src[img];
+        const int sp = A.src_pitch[img], n = nx[0] * ny[0];
+        for (int i = tid; i < n; i += 256) {
+            const int y = i / nx[0], x = i - y * nx[0];
+            s0[y * FE0 + x] = src[(size_t)(cy[0] + y) * sp + cx[0] + x];
+        }
+        __syncthreads();
+        if (A.copy_base) {
+            uint8_t* __restrict__ d = A.dst[img] + A.off[0];
+            const int ox0 = blockIdx.x * FB, oy0 = blockIdx.y * FB;
+            const int ow = min(FB, A.w[0] - ox0), oh = min(FB, A.h[0] - oy0);
+            for (int i = tid; i < ow * oh; i += 256) {
+                const int y = i / ow, x = i - y * ow;
+                d[(size_t)(oy0 + y) * A.pitch[0] + ox0 + x] = s0[(oy0 + y - cy[0]) * FE0 + (ox0 + x - cx[0])];
+            }
+        }
+    }
+    // ---- levels 1..L
+#pragma unroll
+    for (int k = 1; k <= FMAXL; k++) {
+        if (k > L) break;
+        const uint8_t* sp = k == 1 ? s0 : (k == 2 ? s1 : s2);
+        const int sstr = k == 1 ? FE0 : (k == 2 ? 41 : 19);
+        uint8_t* dp = k == 1 ? s1 : (k == 2 ? s2 : nullptr);
+        const int dstr = k == 1 ? 41 : 19;
+        // reflected source indices (BORDER_REFLECT_101 on the SOURCE level), once per output column / row
+        for (int i = tid; i < nx[k] * 5; i += 256) {
+            const int x = i / 5, a = i - 5 * x;
+            s_ix[i] = reflect101(2 * (cx[k] + x) + a - 2, A.w[k - 1]) - cx[k - 1];
+        }
+        for (int i = tid; i < ny[k] * 5; i += 256) {
+            const int y = i / 5, a = i - 5 * y;
+            s_iy[i] = reflect101(2 * (cy[k] + y) + a - 2, A.h[k - 1]) - cy[k - 1];
+        }
+        __syncthreads();
+        uint8_t* __restrict__ d = A.dst[img] + A.off[k];
+        const int own = FB >> k;
+        const int ox0 = blockIdx.x * own, oy0 = blockIdx.y * own;
+        for (int i = tid; i < nx[k] * ny[k]; i += 256) {
+            const int y = i / nx[k], x = i - y * nx[k];
+            const int* ix = &s_ix[5 * x];
+            const int* iy = &s_iy[5 * y];
+            int s = 0;
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const uint8_t* r = sp + iy[b] * sstr;
+                const int hsum = r[ix[0]] + 4 * r[ix[1]] + 6 * r[ix[2]] + 4 * r[ix[3]] + r[ix[4]];
+                s += (b == 0 || b == 4 ? 1 : (b == 2 ? 6 : 4)) * hsum;
+            }
+            const uint8_t v = (uint8_t)((s + 128) >> 8);
+            if (dp) dp[y * dstr + x] = v;
+            const int gx = cx[k] + x, gy = cy[k] + y;
+            if (gx >= ox0 && gx < ox0 + own && gy >= oy0 && gy < oy0 + own) d[(size_t)gy * A.pitch[k] + gx] = v;
+        }
+        __syncthreads();
+    }
+}
+
 int layout_pyramid(fm3d_ctx* ctx, int w, int h, int levels) {
     fm3d_pyramid_desc& P = ctx->pyr;
     size_t off = 0;
@@ -104,6 +219,40 @@ int layout_pyramid(fm3d_ctx* ctx, int w, int h, int levels) {
     }
     P.base[0] = ctx->pyr_mem;
     P.base[1] = ctx->pyr_mem + per_image;
+    return FM3D_OK;
+}
+
+// Builds levels 1..L (and level 0 from img1 / img2 when those are device pointers outside the pyramid) with the fused
+// kernel: one launch per three levels.
+int build_levels_fused(fm3d_ctx* ctx, const uint8_t* img1, int stride1, const uint8_t* img2, int stride2) {
+    fm3d_pyramid_desc& P = ctx->pyr;
+    uint8_t* d0 = const_cast<uint8_t*>(P.base[0]);
+    uint8_t* d1 = const_cast<uint8_t*>(P.base[1]);
+    int base = 0;
+    bool first = true;
+    do {
+        FusedArgs A{};
+        const int nl = P.levels - base < FMAXL ? P.levels - base : FMAXL;
+        const bool ext = first && img1 != nullptr;
+        A.src[0] = ext ? img1 : d0 + P.lv[base].off; A.src_pitch[0] = ext ? stride1 : P.lv[base].pitch;
+        A.src[1] = ext ? img2 : d1 + P.lv[base].off; A.src_pitch[1] = ext ? stride2 : P.lv[base].pitch;
+        A.dst[0] = d0; A.dst[1] = d1;
+        for (int k = 0; k <= nl; k++) {
+            const fm3d_level& lv = P.lv[base + k];
+            A.w[k] = lv.w; A.h[k] = lv.h; A.pitch[k] = lv.pitch; A.off[k] = lv.off;
+        }
+        A.nl = nl;
+        A.copy_base = ext ? 1 : 0;
+        if (nl > 0 || A.copy_base) {
+            const int T = FB >> nl;
+            dim3 grid((A.w[nl] + T - 1) / T, (A.h[nl] + T - 1) / T, 2);
+            pyramid_fused_kernel<<<grid, 256, 0, ctx->stream>>>(A);
+            FM3D_LAUNCH_CHECK(ctx);
+        }
+        base += nl;
+        first = false;
+    } while (base < P.levels);
+    ctx->has_images = true;
     return FM3D_OK;
 }
 
@@ -134,6 +283,17 @@ int set_images_common(fm3d_ctx* ctx, const uint8_t* img1, int stride1, const uin
     ctx->has_images = false;
     if (int rc = layout_pyramid(ctx, w, h, pyramids)) return rc;
     const fm3d_level& l0 = ctx->pyr.lv[0];
+    if (ctx->opt_pyramid_fused) {
+        // device frames: the fused kernel reads them where they are and writes level 0 itself; host frames: one upload per
+        // frame straight into level 0, then the same kernel
+        if (kind == cudaMemcpyDeviceToDevice) return build_levels_fused(ctx, img1, stride1, img2, stride2);
+        for (int k = 0; k < 2; k++) {
+            uint8_t* d = const_cast<uint8_t*>(ctx->pyr.base[k]) + l0.off;
+            ctx->n_copy++;
+            FM3D_CUDA(ctx, cudaMemcpy2DAsync(d, l0.pitch, k ? img2 : img1, k ? stride2 : stride1, w, h, kind, ctx->stream));
+        }
+        return build_levels_fused(ctx, nullptr, 0, nullptr, 0);
+    }
     for (int k = 0; k < 2; k++) {
         uint8_t* d = const_cast<uint8_t*>(ctx->pyr.base[k]) + l0.off;
         ctx->n_copy++;

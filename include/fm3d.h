@@ -127,6 +127,8 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *   "normals_sweep_batch"  fast kernel, fm3d_sweep_normals: 4 (default) evaluates four candidate normals per
  *                       pass over the disc (bit-identical costs, one barrier pair per batch); 1: one pass each
  *   "normals_tma"       stage the image window with a TMA tensor-tile load (1)
+ *   "pyramid_fused"     1 (default): fm3d_set_images[_dev] builds three pyramid levels (and, for device frames, level 0)
+ *                       per launch; 0: one launch per level plus the copies into level 0 (same bits)
  * Returns FM3D_ERR_INVALID_ARG for an unknown key. */
 int fm3d_set_option(fm3d_ctx* ctx, const char* key, double value);
 int fm3d_get_option(fm3d_ctx* ctx, const char* key, double* value);

@@ -1186,3 +1186,43 @@ def test_detect_orb_hamming_chain_full_size(ctx):
     k2[:, 1] -= dy
     d2, kept2 = ctx.describe_keypoints_orb(img2, k2)
     assert inner.sum() > 1500 and kept2.all() and np.array_equal(d2, d[inner])
+
+
+@pytest.mark.parametrize("shape,levels", [((480, 640), 3), ((477, 635), 5), ((67, 131), 6), ((5, 9), 2), ((1, 7), 3), ((720, 1280), 3),
+                                          ((2160, 3840), 4), ((130, 65), 1), ((64, 64), 0)])
+def test_pyramid_fused_kernel_bit_exact(ctx, shape, levels):
+    """K4 as ONE launch per three levels (pyramid_fused = 1, the default): every level of both frames bit-identical with the
+    cv2.pyrDown chain and with the one-launch-per-level kernel, for frames in device memory with a row stride larger than
+    the width (fm3d_set_images_dev, where the kernel also writes level 0) and for host frames."""
+    import cv2
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    h, w = shape
+    imgs = [rng.integers(0, 256, (h, w), dtype=np.uint8) for _ in range(2)]
+    refs = []
+    for im in imgs:
+        chain = [im]
+        for _ in range(levels):
+            chain.append(cv2.pyrDown(chain[-1]))
+        refs.append(chain)
+    stride = w + 13
+    dev = torch.device("cuda", 0)
+    d = [torch.zeros((h, stride), dtype=torch.uint8, device=dev) for _ in range(2)]
+    for k in range(2):
+        d[k][:, :w] = torch.from_numpy(imgs[k]).to(dev)
+    torch.cuda.synchronize()
+    for fused in (1, 0):
+        ctx.set_option("pyramid_fused", fused)
+        try:
+            for mode in ("dev", "host"):
+                if mode == "dev":
+                    ctx.set_images_dev(d[0].data_ptr(), d[1].data_ptr(), w, h, stride, levels)
+                    ctx.sync()
+                else:
+                    ctx.set_images(imgs[0], imgs[1], levels)
+                for k in range(2):
+                    for l in range(levels + 1):
+                        got = ctx.get_pyramid_level(k + 1, l)
+                        np.testing.assert_array_equal(got, refs[k][l], err_msg=f"fused={fused} {mode} image {k + 1} level {l}")
+        finally:
+            ctx.set_option("pyramid_fused", 1)
