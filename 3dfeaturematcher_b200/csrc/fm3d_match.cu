@@ -953,10 +953,11 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         FM3D_LAUNCH_CHECK(ctx);
         tc_prep_kernel<<<nt_pad / 8, 256, 0, ctx->stream>>>(t, nt, nt_pad, 0, ops + ba, flag);
         FM3D_LAUNCH_CHECK(ctx);
-        int h_flag = 0;
-        if (int rc = fm3d_d2h(ctx, &h_flag, flag, sizeof(int))) return rc;
-        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h_flag == 0) {
+        // The contraction is launched WITHOUT waiting for the verdict of the two prep kernels ("every value is an integer in
+        // [0, 255]"): the four kernels run back to back and the flag is read once, after them.  Integer descriptors (OpenCV
+        // SIFT, the case this path exists for) never pay a mid-pipeline host round trip; for anything else the speculative
+        // result is simply overwritten by the exact paths below.
+        {
             const int q_tiles = nq_pad / TC_M, nt_tiles = nt_pad / TC_N;
             int tps = 1;
             const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
@@ -968,7 +969,10 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
             FM3D_LAUNCH_CHECK(ctx);
             finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits * TC_EPI_HALVES, nq, nt, idx, dist);
             FM3D_LAUNCH_CHECK(ctx);
-            return FM3D_OK;
+            int h_flag = 0;
+            if (int rc = fm3d_d2h(ctx, &h_flag, flag, sizeof(int))) return rc;
+            FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_flag == 0) return FM3D_OK;
         }
     }
     // real-valued descriptors: bf16 hi/lo filter on the tensor cores + exact decision (see match_sp_kernel)
