@@ -684,6 +684,13 @@ def run_gpu_arm(args):
         st.bind()
         del st3, case3
 
+    # ---- per-stage times of every rank (the stage that follows a slow rank's stage absorbs the skew: at N > 1 the `gather`
+    # stage of a fast rank is mostly the wait for the slowest rank's normal search, not the collective)
+    stage_all = torch.zeros((world, n_stage), dtype=torch.float64, device=dev)
+    stage_all[rank] = torch.from_numpy(stage_ms / args.steps).to(dev)
+    if world > 1:
+        dist.all_reduce(stage_all)
+    stage_all = stage_all.cpu().numpy()
     # ---- reduce over ranks: max time, summed features
     tm = torch.tensor([t_dev_ms, t_e2e * 1e3, t_alt_ms, t_f64_ms], dtype=torch.float64, device=dev)
     feats = torch.tensor([float(n_match), float(hm), float(n_match_alt), float(n_match_f64)], dtype=torch.float64, device=dev)
@@ -778,6 +785,8 @@ def run_gpu_arm(args):
                                   "sample": f"the same port on ONE host thread (the reference is single-threaded, SURVEY 8d-i): full matching + "
                                             f"normal optimisation of {cpu_1t['n_sample']} seeded features", "detail": cpu_1t}},
             "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(PathState.STAGES, stage_ms)},
+            "stage_ms_per_step_min_max_over_ranks": {k: [float(stage_all[:, j].min()), float(stage_all[:, j].max())]
+                                                     for j, k in enumerate(PathState.STAGES)},
             "features_per_step": {"matches": tot_feat, "inliers_rank0": int(n_inl), "ok_rank0": int((status == 0).sum()),
                                   "wall_touching_rank0": int((npen > 0).sum()), "nfev_mean_per_level": nfev.mean(0).tolist()},
             "multi_gpu_check": gather_check["result"] if isinstance(gather_check, dict) else str(gather_check),
