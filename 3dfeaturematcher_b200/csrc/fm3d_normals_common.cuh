@@ -21,8 +21,18 @@ constexpr int MAX_ROWS = 2 * MAX_RAY + 1;
 
 enum { FLAG_NAN = 1, FLAG_BBOX = 2, FLAG_PIX = 4 };
 
+// fast kernel: the camera constants of the pixel loops as floats (filled by run_normals_fast)
+struct FastConsts {
+    float k1, k2, k3, p1, p2;
+    float p1x2, p2x2;                                  // 2 p1, 2 p2
+    float t0, t1, t2;                                  // translation of camera 2 (the epipole, for the Jacobian)
+    float sfx[FM3D_MAX_LEVELS], sfy[FM3D_MAX_LEVELS];  // scale * K per pyramid level
+    float scx[FM3D_MAX_LEVELS], scy[FM3D_MAX_LEVELS];
+};
+
 struct NormalsArgs {
     fm3d_cam cam;
+    FastConsts fc;
     fm3d_pyramid_desc pyr;
     const double* xyz;
     int n;

@@ -68,9 +68,13 @@ enum { AT_X_JAC = 0, AT_XT_PLAIN = 1, AT_XT_FUSED = 2 };
 
 // Everything a pass needs, written by the lanes of warp 0 of the group.
 struct FastPass {
-    // e = 0: value, 1: d/dphi, 2: d/dtheta.  A_e = h[e][0] dx + h[e][1] dy + h[e][2] (x numerator, offset form),
-    // B_e = h[e][3] dx + h[e][4] dy + h[e][5], C_e = h[e][6] dx + h[e][7] dy + h[e][8] (common denominator)
-    float h[3][9];
+    // A = h[0] dx + h[1] dy + h[2] (x numerator, offset form), B = h[3] dx + h[4] dy + h[5], C = h[6] dx + h[7] dy + h[8]
+    // (common denominator w2 = H2 . v)
+    float h[9];
+    // Jacobian passes.  H = (n.P) R + t n^T gives dH/dp v = a_p H v + t (n_p - a_p n).v with a_p = (n_p.P)/(n.P): the first term
+    // is parallel to H v and drops out of the perspective division, so the projection moves along the epipolar direction,
+    //   d(x, y)/dp = (t0 - x t2, t1 - y t2) * sigma_p / w2,   sigma_p = (n_p - a_p n).v = sg[p][0] dx + sg[p][1] dy + sg[p][2]
+    float sg[2][3];
     float nd[3];        // sign(n.P) * n.v = nd[0] dx + nd[1] dy + nd[2]
     float mabs;         // |n.P|
     int kind;           // PASS_*
@@ -95,7 +99,7 @@ struct FastShared {
     int where;          // AT_*
     int alive;
     int first_row, last_row;
-    float hbase[9];     // value coefficients (FastPass::h[0]) of the current LM iterate ...
+    float hbase[9];     // value coefficients (FastPass::h) of the current LM iterate ...
     double s0_base;     // ... and the residual sum the pass at the iterate returned
     int base_valid;
     int cand;           // mode 2 (sweep): candidate being evaluated
@@ -110,8 +114,6 @@ struct FastShared {
 
 struct LevelConst {
     float xc, yc;
-    float k1, k2, k3, p1, p2;
-    float sfx, sfy, scx, scy;    // scale * K
     float cols, rows;            // isPixelGood bounds on the scaled pixel
     float c0;                    // cost_mode NCC: value subtracted from every image-2 sample before it is summed (~ mean of image 1)
     const uint8_t* win;
@@ -142,6 +144,11 @@ __device__ __forceinline__ float rcp_nr(float a) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return fmaf(r, fmaf(-a, r, 1.0f), r);   // explicit fmas: identical in every instantiation
+}
+__device__ __forceinline__ float rcp_approx(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
 }
 __device__ __forceinline__ float u2f(unsigned b) {  // I2FP (the compiler would pick the slow I2F.U16)
     float f;
@@ -181,24 +188,24 @@ struct Acc {
 // Warp of one disc pixel into image 2 and its residual; with JAC also the derivatives of the
 // sampled intensity with respect to (phi, theta).
 template <bool JAC, bool SLOW, bool NCC = false>
-__device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelConst& L, float2 dv, float I1, Acc& acc) {
-    const float A0 = fmaf(P.h[0][0], dv.x, fmaf(P.h[0][1], dv.y, P.h[0][2]));
-    const float B0 = fmaf(P.h[0][3], dv.x, fmaf(P.h[0][4], dv.y, P.h[0][5]));
-    const float C0 = fmaf(P.h[0][6], dv.x, fmaf(P.h[0][7], dv.y, P.h[0][8]));
-    const float iz = rcp_nr(C0);
+__device__ __forceinline__ void eval_pixel_fast(const FastConsts& K, const int lvl, const FastPass& P, const LevelConst& L, float2 dv, float I1, Acc& acc) {
+    const float A0 = fmaf(P.h[0], dv.x, fmaf(P.h[1], dv.y, P.h[2]));
+    const float B0 = fmaf(P.h[3], dv.x, fmaf(P.h[4], dv.y, P.h[5]));
+    const float C0 = fmaf(P.h[6], dv.x, fmaf(P.h[7], dv.y, P.h[8]));
+    // MUFU reciprocal as it is (1 ulp): it multiplies the OFFSET from the centre, 1e-7 of at most ~100 pixels
+    const float iz = rcp_approx(C0);
     // every operation of the value path is an explicit fma / non-contractible intrinsic: the value-only
     // and the value+Jacobian instantiation must return bit-identical residuals (a trial is compared
     // with an iterate that was evaluated by the other one)
     const float x = fmaf(A0, iz, L.xc), y = fmaf(B0, iz, L.yc);
-    // cv::projectPoints: distortion polynomial and K (x scale), singlecameratriangulator.cpp:602,627
+    // cv::projectPoints: distortion polynomial and K (x scale), singlecameratriangulator.cpp:602,627, with the tangential
+    // terms collected: xd = x g + p2 r2, yd = y g + p1 r2, g = cd + 2 p1 y + 2 p2 x
     const float r2 = fmaf(x, x, __fmul_rn(y, y));
-    const float cd = fmaf(r2, fmaf(r2, fmaf(r2, L.k3, L.k2), L.k1), 1.0f);
-    const float x2 = __fadd_rn(x, x), y2 = __fadd_rn(y, y);
-    const float xy2 = __fmul_rn(x2, y);
-    const float a2 = fmaf(x2, x, r2), a3 = fmaf(y2, y, r2);
-    const float xd = fmaf(x, cd, fmaf(L.p1, xy2, __fmul_rn(L.p2, a2)));
-    const float yd = fmaf(y, cd, fmaf(L.p1, a3, __fmul_rn(L.p2, xy2)));
-    const float su = fmaf(xd, L.sfx, L.scx), sv = fmaf(yd, L.sfy, L.scy);
+    const float cd = fmaf(r2, fmaf(r2, fmaf(r2, K.k3, K.k2), K.k1), 1.0f);
+    const float g = fmaf(K.p2x2, x, fmaf(K.p1x2, y, cd));
+    const float xd = fmaf(x, g, __fmul_rn(K.p2, r2));
+    const float yd = fmaf(y, g, __fmul_rn(K.p1, r2));
+    const float su = fmaf(xd, K.sfx[lvl], K.scx[lvl]), sv = fmaf(yd, K.sfy[lvl], K.scy[lvl]);
     // floor and fraction without FRND/F2I
     const float tx = __fadd_rd(su, FLOOR_MAGIC), ty = __fadd_rd(sv, FLOOR_MAGIC);
     const float ax = __fsub_rn(su, __fsub_rn(tx, FLOOR_MAGIC)), ay = __fsub_rn(sv, __fsub_rn(ty, FLOOR_MAGIC));
@@ -230,23 +237,19 @@ __device__ __forceinline__ void eval_pixel_fast(const FastPass& P, const LevelCo
     }
     if (JAC) {
         const float gy = fmaf(ax, d1 - d0, d0);
-        const float cdp = fmaf(r2, fmaf(r2, 3.0f * L.k3, 2.0f * L.k2), L.k1);   // d cd / d r2
-        const float Jxx = fmaf(x2 * x, cdp, fmaf(2.0f * L.p1, y, fmaf(6.0f * L.p2, x, cd)));
-        const float Jxy = fmaf(xy2, cdp, fmaf(2.0f * L.p1, x, 2.0f * L.p2 * y));
-        const float Jyy = fmaf(y2 * y, cdp, fmaf(6.0f * L.p1, y, fmaf(2.0f * L.p2, x, cd)));
-        const float Gx = gx * L.sfx, Gy = gy * L.sfy;
-        const float Ix = fmaf(Gx, Jxx, Gy * Jxy), Iy = fmaf(Gx, Jxy, Gy * Jyy);   // dI2/d(x,y)
-        const float q0 = Ix * iz, q1 = Iy * iz;
-        const float dx = A0 * iz, dy = B0 * iz;
-        const float q2 = -fmaf(q0, dx, q1 * dy);
-        const float A1 = fmaf(P.h[1][0], dv.x, fmaf(P.h[1][1], dv.y, P.h[1][2]));
-        const float B1 = fmaf(P.h[1][3], dv.x, fmaf(P.h[1][4], dv.y, P.h[1][5]));
-        const float C1 = fmaf(P.h[1][6], dv.x, fmaf(P.h[1][7], dv.y, P.h[1][8]));
-        const float A2 = fmaf(P.h[2][0], dv.x, fmaf(P.h[2][1], dv.y, P.h[2][2]));
-        const float B2 = fmaf(P.h[2][3], dv.x, fmaf(P.h[2][4], dv.y, P.h[2][5]));
-        const float C2 = fmaf(P.h[2][6], dv.x, fmaf(P.h[2][7], dv.y, P.h[2][8]));
-        const float Ip = fmaf(q0, A1, fmaf(q1, B1, q2 * C1));   // dI2/dphi   (residual derivative = -Ip)
-        const float It = fmaf(q0, A2, fmaf(q1, B2, q2 * C2));   // dI2/dtheta
+        const float Gx = gx * K.sfx[lvl], Gy = gy * K.sfy[lvl];               // dI2/d(xd, yd)
+        // direction the projection moves in when the plane turns (towards the epipole), pushed through the distortion
+        const float ex = fmaf(x, -K.t2, K.t0), ey = fmaf(y, -K.t2, K.t1);
+        const float cdp2 = fmaf(r2, fmaf(r2, 6.0f * K.k3, 4.0f * K.k2), 2.0f * K.k1);   // 2 d cd / d r2
+        const float rho = fmaf(x, ex, y * ey);
+        const float dg = fmaf(cdp2, rho, fmaf(K.p1x2, ey, K.p2x2 * ex));
+        const float dxd = fmaf(ex, g, fmaf(x, dg, K.p2x2 * rho));
+        const float dyd = fmaf(ey, g, fmaf(y, dg, K.p1x2 * rho));
+        const float E = fmaf(Gx, dxd, Gy * dyd) * iz;
+        const float s1 = fmaf(P.sg[0][0], dv.x, fmaf(P.sg[0][1], dv.y, P.sg[0][2]));
+        const float s2 = fmaf(P.sg[1][0], dv.x, fmaf(P.sg[1][1], dv.y, P.sg[1][2]));
+        const float Ip = s1 * E;   // dI2/dphi   (residual derivative = -Ip)
+        const float It = s2 * E;   // dI2/dtheta
         if (NCC) {
             acc.f[0] += Ip; acc.f[1] += It;
             acc.f[2] = fmaf(d, Ip, acc.f[2]); acc.f[3] = fmaf(d, It, acc.f[3]);
@@ -317,24 +320,18 @@ struct Acc2 {      // Jacobian sums of the packed loop: lanes are added at the e
 // eval_pixel_fast for two pixels at once (taps from the staged window only).  The value path is
 // the same sequence of IEEE operations as the scalar function, lane by lane.
 template <bool JAC, bool NCC = false>
-__device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelConst& L, f2 X, f2 Y, f2 I1p, Acc& acc, Acc2& acc2) {
-    const f2 A0 = fma2(bc(P.h[0][0]), X, fma2(bc(P.h[0][1]), Y, bc(P.h[0][2])));
-    const f2 B0 = fma2(bc(P.h[0][3]), X, fma2(bc(P.h[0][4]), Y, bc(P.h[0][5])));
-    const f2 C0 = fma2(bc(P.h[0][6]), X, fma2(bc(P.h[0][7]), Y, bc(P.h[0][8])));
-    float ra, rb;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(lo2(C0)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(hi2(C0)));
-    const f2 r0 = mk2(ra, rb);
-    const f2 iz = fma2(r0, fma2(neg2(C0), r0, bc(1.0f)), r0);
+__device__ __forceinline__ void eval_pixel_pair(const FastConsts& K, const int lvl, const FastPass& P, const LevelConst& L, f2 X, f2 Y, f2 I1p, Acc& acc, Acc2& acc2) {
+    const f2 A0 = fma2(bc(P.h[0]), X, fma2(bc(P.h[1]), Y, bc(P.h[2])));
+    const f2 B0 = fma2(bc(P.h[3]), X, fma2(bc(P.h[4]), Y, bc(P.h[5])));
+    const f2 C0 = fma2(bc(P.h[6]), X, fma2(bc(P.h[7]), Y, bc(P.h[8])));
+    const f2 iz = mk2(rcp_approx(lo2(C0)), rcp_approx(hi2(C0)));
     const f2 x = fma2(A0, iz, bc(L.xc)), y = fma2(B0, iz, bc(L.yc));
     const f2 r2 = fma2(x, x, mul2(y, y));
-    const f2 cd = fma2(r2, fma2(r2, fma2(r2, bc(L.k3), bc(L.k2)), bc(L.k1)), bc(1.0f));
-    const f2 x2 = add2(x, x), y2 = add2(y, y);
-    const f2 xy2 = mul2(x2, y);
-    const f2 a2 = fma2(x2, x, r2), a3 = fma2(y2, y, r2);
-    const f2 xd = fma2(x, cd, fma2(bc(L.p1), xy2, mul2(bc(L.p2), a2)));
-    const f2 yd = fma2(y, cd, fma2(bc(L.p1), a3, mul2(bc(L.p2), xy2)));
-    const f2 su = fma2(xd, bc(L.sfx), bc(L.scx)), sv = fma2(yd, bc(L.sfy), bc(L.scy));
+    const f2 cd = fma2(r2, fma2(r2, fma2(r2, bc(K.k3), bc(K.k2)), bc(K.k1)), bc(1.0f));
+    const f2 g = fma2(bc(K.p2x2), x, fma2(bc(K.p1x2), y, cd));
+    const f2 xd = fma2(x, g, mul2(bc(K.p2), r2));
+    const f2 yd = fma2(y, g, mul2(bc(K.p1), r2));
+    const f2 su = fma2(xd, bc(K.sfx[lvl]), bc(K.scx[lvl])), sv = fma2(yd, bc(K.sfy[lvl]), bc(K.scy[lvl]));
     const f2 tx = add2_rm(su, bc(FLOOR_MAGIC)), ty = add2_rm(sv, bc(FLOOR_MAGIC));
     const f2 ax = sub2(su, sub2(tx, bc(FLOOR_MAGIC))), ay = sub2(sv, sub2(ty, bc(FLOOR_MAGIC)));
     unsigned aa = __float_as_uint(lo2(ty)) * L.ww + __float_as_uint(lo2(tx)) - L.coff;
@@ -362,23 +359,18 @@ __device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelCo
     }
     if (JAC) {
         const f2 gy = fma2(ax, sub2(d1, d0), d0);
-        const f2 cdp = fma2(r2, fma2(r2, bc(3.0f * L.k3), bc(2.0f * L.k2)), bc(L.k1));   // d cd / d r2
-        const f2 Jxx = fma2(mul2(x2, x), cdp, fma2(bc(2.0f * L.p1), y, fma2(bc(6.0f * L.p2), x, cd)));
-        const f2 Jxy = fma2(xy2, cdp, fma2(bc(2.0f * L.p1), x, mul2(bc(2.0f * L.p2), y)));
-        const f2 Jyy = fma2(mul2(y2, y), cdp, fma2(bc(6.0f * L.p1), y, fma2(bc(2.0f * L.p2), x, cd)));
-        const f2 Gx = mul2(gx, bc(L.sfx)), Gy = mul2(gy, bc(L.sfy));
-        const f2 Ix = fma2(Gx, Jxx, mul2(Gy, Jxy)), Iy = fma2(Gx, Jxy, mul2(Gy, Jyy));   // dI2/d(x,y)
-        const f2 q0 = mul2(Ix, iz), q1 = mul2(Iy, iz);
-        const f2 dx = mul2(A0, iz), dy = mul2(B0, iz);
-        const f2 q2 = neg2(fma2(q0, dx, mul2(q1, dy)));
-        const f2 A1 = fma2(bc(P.h[1][0]), X, fma2(bc(P.h[1][1]), Y, bc(P.h[1][2])));
-        const f2 B1 = fma2(bc(P.h[1][3]), X, fma2(bc(P.h[1][4]), Y, bc(P.h[1][5])));
-        const f2 C1 = fma2(bc(P.h[1][6]), X, fma2(bc(P.h[1][7]), Y, bc(P.h[1][8])));
-        const f2 A2 = fma2(bc(P.h[2][0]), X, fma2(bc(P.h[2][1]), Y, bc(P.h[2][2])));
-        const f2 B2 = fma2(bc(P.h[2][3]), X, fma2(bc(P.h[2][4]), Y, bc(P.h[2][5])));
-        const f2 C2 = fma2(bc(P.h[2][6]), X, fma2(bc(P.h[2][7]), Y, bc(P.h[2][8])));
-        const f2 Ip = fma2(q0, A1, fma2(q1, B1, mul2(q2, C1)));   // dI2/dphi   (residual derivative = -Ip)
-        const f2 It = fma2(q0, A2, fma2(q1, B2, mul2(q2, C2)));   // dI2/dtheta
+        const f2 Gx = mul2(gx, bc(K.sfx[lvl])), Gy = mul2(gy, bc(K.sfy[lvl]));
+        const f2 ex = fma2(x, bc(-K.t2), bc(K.t0)), ey = fma2(y, bc(-K.t2), bc(K.t1));
+        const f2 cdp2 = fma2(r2, fma2(r2, bc(6.0f * K.k3), bc(4.0f * K.k2)), bc(2.0f * K.k1));   // 2 d cd / d r2
+        const f2 rho = fma2(x, ex, mul2(y, ey));
+        const f2 dg = fma2(cdp2, rho, fma2(bc(K.p1x2), ey, mul2(bc(K.p2x2), ex)));
+        const f2 dxd = fma2(ex, g, fma2(x, dg, mul2(bc(K.p2x2), rho)));
+        const f2 dyd = fma2(ey, g, fma2(y, dg, mul2(bc(K.p1x2), rho)));
+        const f2 E = mul2(fma2(Gx, dxd, mul2(Gy, dyd)), iz);
+        const f2 s1 = fma2(bc(P.sg[0][0]), X, fma2(bc(P.sg[0][1]), Y, bc(P.sg[0][2])));
+        const f2 s2 = fma2(bc(P.sg[1][0]), X, fma2(bc(P.sg[1][1]), Y, bc(P.sg[1][2])));
+        const f2 Ip = mul2(s1, E);   // dI2/dphi   (residual derivative = -Ip)
+        const f2 It = mul2(s2, E);   // dI2/dtheta
         if (NCC) {
             acc2.a[0] = add2(acc2.a[0], Ip); acc2.a[1] = add2(acc2.a[1], It);
             acc2.a[2] = fma2(d, Ip, acc2.a[2]); acc2.a[3] = fma2(d, It, acc2.a[3]);
@@ -396,7 +388,7 @@ __device__ __forceinline__ void eval_pixel_pair(const FastPass& P, const LevelCo
 
 // Gates of one boundary pixel (isInBoundingBox :646-655, isPixelGood :657-665) and the proof that its
 // taps are inside the staged window.
-__device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const LevelConst& L, float vcx, float vcy,
+__device__ __forceinline__ unsigned boundary_flags(const FastConsts& K, const int lvl, const FastPass& P, const LevelConst& L, float vcx, float vcy,
                                                    float cmax, float2 dv) {
     unsigned flags = 0;
     const float den = fmaf(P.nd[0], dv.x, fmaf(P.nd[1], dv.y, P.nd[2]));
@@ -404,17 +396,17 @@ __device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const Leve
     const float t = fmaxf(1.0f, fmaxf(fabsf(vx), fabsf(vy)));
     if (den != den || P.mabs != P.mabs) flags |= FLAG_NAN;
     if (!(P.mabs * t < cmax * den)) flags |= FLAG_BBOX;
-    const float A0 = fmaf(P.h[0][0], dv.x, fmaf(P.h[0][1], dv.y, P.h[0][2]));
-    const float B0 = fmaf(P.h[0][3], dv.x, fmaf(P.h[0][4], dv.y, P.h[0][5]));
-    const float C0 = fmaf(P.h[0][6], dv.x, fmaf(P.h[0][7], dv.y, P.h[0][8]));
+    const float A0 = fmaf(P.h[0], dv.x, fmaf(P.h[1], dv.y, P.h[2]));
+    const float B0 = fmaf(P.h[3], dv.x, fmaf(P.h[4], dv.y, P.h[5]));
+    const float C0 = fmaf(P.h[6], dv.x, fmaf(P.h[7], dv.y, P.h[8]));
     const float iz = rcp_nr(C0);
     const float x = L.xc + A0 * iz, y = L.yc + B0 * iz;
     const float r2 = fmaf(x, x, y * y);
-    const float cd = fmaf(r2, fmaf(r2, fmaf(r2, L.k3, L.k2), L.k1), 1.0f);
+    const float cd = fmaf(r2, fmaf(r2, fmaf(r2, K.k3, K.k2), K.k1), 1.0f);
     const float xy2 = 2.0f * x * y;
-    const float xd = fmaf(x, cd, fmaf(L.p1, xy2, L.p2 * fmaf(2.0f * x, x, r2)));
-    const float yd = fmaf(y, cd, fmaf(L.p1, fmaf(2.0f * y, y, r2), L.p2 * xy2));
-    const float su = fmaf(xd, L.sfx, L.scx), sv = fmaf(yd, L.sfy, L.scy);
+    const float xd = fmaf(x, cd, fmaf(K.p1, xy2, K.p2 * fmaf(2.0f * x, x, r2)));
+    const float yd = fmaf(y, cd, fmaf(K.p1, fmaf(2.0f * y, y, r2), K.p2 * xy2));
+    const float su = fmaf(xd, K.sfx[lvl], K.scx[lvl]), sv = fmaf(yd, K.sfy[lvl], K.scy[lvl]);
     if (!(su >= 0.0f && su <= L.cols && sv >= 0.0f && sv <= L.rows)) flags |= FLAG_PIX;
     // one pixel of margin: the lattice boundary is a polygon, its warp slightly curved
     const float fx0 = floorf(su), fy0 = floorf(sv);
@@ -425,11 +417,11 @@ __device__ __forceinline__ unsigned boundary_flags(const FastPass& P, const Leve
 }
 
 template <bool JAC, bool SLOW, bool PREFETCH, bool NCC = false>
-__device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& L, const float2* __restrict__ rays,
+__device__ __forceinline__ void run_pixels(const FastConsts& K, const int lvl, const FastPass& P, const LevelConst& L, const float2* __restrict__ rays,
                                            const float* __restrict__ i1, int m, int tid, int NT, Acc& acc) {
     if (SLOW) {
         // taps from global memory (a boundary tap left the staged window): scalar path
-        for (int idx = tid; idx < m; idx += NT) eval_pixel_fast<JAC, true, NCC>(P, L, ray_at(rays, idx), i1[idx], acc);
+        for (int idx = tid; idx < m; idx += NT) eval_pixel_fast<JAC, true, NCC>(K, lvl, P, L, ray_at(rays, idx), i1[idx], acc);
         return;
     }
     constexpr int NJ = NCC ? 9 : 5;
@@ -459,27 +451,27 @@ __device__ __forceinline__ void run_pixels(const FastPass& P, const LevelConst& 
             const int nx = p + 2 * NT;
             if (nx < npair) { r = LD_SCRATCH(rp + nx); I = LD_SCRATCH(ip + nx); }
             if (nx + NT < npair) { r2 = LD_SCRATCH(rp + nx + NT); I2 = LD_SCRATCH(ip + nx + NT); }
-            eval_pixel_pair<JAC, NCC>(P, L, cr.x, cr.y, cI, acc, acc2);
-            eval_pixel_pair<JAC, NCC>(P, L, cr2.x, cr2.y, cI2, acc, acc2);
+            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, cr.x, cr.y, cI, acc, acc2);
+            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, cr2.x, cr2.y, cI2, acc, acc2);
         }
-        if (p < npair) eval_pixel_pair<JAC, NCC>(P, L, r.x, r.y, I, acc, acc2);
+        if (p < npair) eval_pixel_pair<JAC, NCC>(K, lvl, P, L, r.x, r.y, I, acc, acc2);
 #else
         for (; p < npair; p += NT) {
             const ulonglong2 cr = r;
             const f2 cI = I;
             const int nx = p + NT;
             if (nx < npair) { r = LD_SCRATCH(rp + nx); I = LD_SCRATCH(ip + nx); }
-            eval_pixel_pair<JAC, NCC>(P, L, cr.x, cr.y, cI, acc, acc2);
+            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, cr.x, cr.y, cI, acc, acc2);
         }
 #endif
     } else {
         for (; p < npair; p += NT) {
             const ulonglong2 r = rp[p];
-            eval_pixel_pair<JAC, NCC>(P, L, r.x, r.y, ip[p], acc, acc2);
+            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, r.x, r.y, ip[p], acc, acc2);
         }
     }
     // odd pixel count: the last pixel alone (thread chosen so that the summation order is fixed)
-    if ((m & 1) && tid == (npair % NT)) eval_pixel_fast<JAC, false, NCC>(P, L, ray_at(rays, m - 1), i1[m - 1], acc);
+    if ((m & 1) && tid == (npair % NT)) eval_pixel_fast<JAC, false, NCC>(K, lvl, P, L, ray_at(rays, m - 1), i1[m - 1], acc);
     if (JAC) {
 #pragma unroll
         for (int k = 0; k < NJ; k++) acc.f[k] += lo2(acc2.a[k]) + hi2(acc2.a[k]);
@@ -519,7 +511,7 @@ __device__ __forceinline__ void ncc_sums_to_normal_equations(double* s, double s
 // samples are read once per batch, the NE dependency chains are independent, and the barriers, the
 // reduction and the serial publish step are paid once per batch.
 template <int NE, bool PREFETCH>
-__device__ __forceinline__ void run_pixels_multi(const FastPass* __restrict__ PPk, const LevelConst& L,
+__device__ __forceinline__ void run_pixels_multi(const FastConsts& K, const int lvl, const FastPass* __restrict__ PPk, const LevelConst& L,
                                                  const float2* __restrict__ rays, const float* __restrict__ i1, int m,
                                                  int tid, int NT, Acc* acc) {
     Acc2 unused;
@@ -538,7 +530,7 @@ __device__ __forceinline__ void run_pixels_multi(const FastPass* __restrict__ PP
             if (nx < npair) { r = rp[nx]; I = ip[nx]; }
         }
 #pragma unroll
-        for (int k = 0; k < NE; k++) eval_pixel_pair<false>(PPk[k], L, cr.x, cr.y, cI, acc[k], unused);
+        for (int k = 0; k < NE; k++) eval_pixel_pair<false>(K, lvl, PPk[k], L, cr.x, cr.y, cI, acc[k], unused);
         if (!PREFETCH) {
             const int nx = p + NT;
             if (nx < npair) { r = rp[nx]; I = ip[nx]; }
@@ -546,7 +538,7 @@ __device__ __forceinline__ void run_pixels_multi(const FastPass* __restrict__ PP
     }
     if ((m & 1) && tid == (npair % NT)) {
 #pragma unroll
-        for (int k = 0; k < NE; k++) eval_pixel_fast<false, false>(PPk[k], L, ray_at(rays, m - 1), i1[m - 1], acc[k]);
+        for (int k = 0; k < NE; k++) eval_pixel_fast<false, false>(K, lvl, PPk[k], L, ray_at(rays, m - 1), i1[m - 1], acc[k]);
     }
 }
 
@@ -571,14 +563,11 @@ __device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, d
         return;
     }
     const double vcx = S->vc[0], vcy = S->vc[1];
-    if (lane < 9) {
-        // lane = 3 e + row: e = 0 value, 1 d/dphi, 2 d/dtheta
-        const int e = lane / 3, row = lane - 3 * e;
-        const double nx = e == 0 ? n0x : (e == 1 ? -ct * sp : -st * cp);
-        const double ny = e == 0 ? n0y : (e == 1 ? ct * cp : -st * sp);
-        const double nz = e == 0 ? n0z : (e == 1 ? 0.0 : ct);
+    if (lane < 3) {
+        // value coefficients, row `lane` of H = (n.P) R + t n^T
+        const int row = lane;
+        const double nx = n0x, ny = n0y, nz = n0z;
         const double me = nx * S->P[0] + ny * S->P[1] + nz * S->P[2];
-        // third row of H_e = (n_e.P) R + t n_e^T, and row `row`
         const double H20 = me * cam.R[6] + cam.t[2] * nx, H21 = me * cam.R[7] + cam.t[2] * ny, H22 = me * cam.R[8] + cam.t[2] * nz;
         double c0, c1, c2;
         if (row == 2) {
@@ -593,9 +582,20 @@ __device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, d
             c1 = me * cam.R[3 * row + 1] + tr * ny - ref * H21;
             c2 = me * cam.R[3 * row + 2] + tr * nz - ref * H22;
         }
-        PP->h[e][3 * row] = (float)c0;
-        PP->h[e][3 * row + 1] = (float)c1;
-        PP->h[e][3 * row + 2] = (float)(c0 * vcx + c1 * vcy + c2);
+        PP->h[3 * row] = (float)c0;
+        PP->h[3 * row + 1] = (float)c1;
+        PP->h[3 * row + 2] = (float)(c0 * vcx + c1 * vcy + c2);
+    } else if (lane < 5) {
+        // sigma_p = (n_p - a_p n) . v, a_p = (n_p.P)/(n.P), for p = phi (lane 3), theta (lane 4): see FastPass::sg
+        const bool dphi = lane == 3;
+        const double nx = dphi ? -ct * sp : -st * cp, ny = dphi ? ct * cp : -st * sp, nz = dphi ? 0.0 : ct;
+        const double m0 = n0x * S->P[0] + n0y * S->P[1] + n0z * S->P[2];
+        const double mp = nx * S->P[0] + ny * S->P[1] + nz * S->P[2];
+        const double a = m0 != 0.0 ? mp / m0 : 0.0;     // n.P = 0 fails the bounding-box gate of every pixel
+        const double c0 = nx - a * n0x, c1 = ny - a * n0y, c2 = nz - a * n0z;
+        PP->sg[lane - 3][0] = (float)c0;
+        PP->sg[lane - 3][1] = (float)c1;
+        PP->sg[lane - 3][2] = (float)(c0 * vcx + c1 * vcy + c2);
     } else if (lane == 9) {
         const double me = n0x * S->P[0] + n0y * S->P[1] + n0z * S->P[2];
         const double sg = me < 0 ? -1.0 : 1.0;
@@ -608,7 +608,7 @@ __device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, d
         }
         PP->mabs = (float)fabs(me);
         PP->kind = kind;
-    } else if (lane < 13) {
+    } else if (lane >= 10 && lane < 13) {
         // penalty weights of f(x), f(x + h0 e0), f(x + h1 e1) as lmfit's forward differences see them
         const int j = lane - 10;
         const double h0 = fmax(eps * eps, eps * fabs(phi)), h1 = fmax(eps * eps, eps * fabs(theta));
@@ -873,9 +873,6 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             L.w = lv.w; L.h = lv.h; L.pitch = lv.pitch;
             L.win = win; L.ww = (unsigned)A.win_w[lvl];
             const int wh = A.win_h[lvl];
-            L.k1 = (float)cam.k1; L.k2 = (float)cam.k2; L.k3 = (float)cam.k3; L.p1 = (float)cam.p1; L.p2 = (float)cam.p2;
-            L.sfx = (float)(scale * cam.fx); L.sfy = (float)(scale * cam.fy);
-            L.scx = (float)(scale * cam.cx); L.scy = (float)(scale * cam.cy);
             L.cols = (float)lv.w; L.rows = (float)lv.h;     // scale * (cols_l / scale)
             L.xc = (float)S->xc; L.yc = (float)S->yc;
             L.c0 = 0.0f;
@@ -1063,7 +1060,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         const float2 ray = ray_at(rays, idx);
 #pragma unroll
                         for (int kk = 0; kk < SWEEP_B; kk++)
-                            if (kk < ne) fl[kk] |= boundary_flags(G.PPk[kk], L, vcxf, vcyf, cmax, ray);
+                            if (kk < ne) fl[kk] |= boundary_flags(A.fc, lvl, G.PPk[kk], L, vcxf, vcyf, cmax, ray);
                     }
                     Acc acc[SWEEP_B];
 #pragma unroll
@@ -1072,10 +1069,10 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
 #pragma unroll
                         for (int j = 0; j < 9; j++) acc[k].f[j] = 0.0f;
                     }
-                    if (ne == SWEEP_B) run_pixels_multi<SWEEP_B, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
-                    else if (ne == 3) run_pixels_multi<3, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
-                    else if (ne == 2) run_pixels_multi<2, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
-                    else if (ne == 1) run_pixels_multi<1, !RAYS_SMEM>(G.PPk, L, rays, i1, m, tid, NT, acc);
+                    if (ne == SWEEP_B) run_pixels_multi<SWEEP_B, !RAYS_SMEM>(A.fc, lvl, G.PPk, L, rays, i1, m, tid, NT, acc);
+                    else if (ne == 3) run_pixels_multi<3, !RAYS_SMEM>(A.fc, lvl, G.PPk, L, rays, i1, m, tid, NT, acc);
+                    else if (ne == 2) run_pixels_multi<2, !RAYS_SMEM>(A.fc, lvl, G.PPk, L, rays, i1, m, tid, NT, acc);
+                    else if (ne == 1) run_pixels_multi<1, !RAYS_SMEM>(A.fc, lvl, G.PPk, L, rays, i1, m, tid, NT, acc);
 #pragma unroll
                     for (int k = 0; k < SWEEP_B; k++) {
                         const double a = warp_sum(acc[k].s0);
@@ -1156,7 +1153,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                     } else {
                         idx = rows->start[last_row] + (k - 2 * nrows - n_first);
                     }
-                    flags |= boundary_flags(P, L, vcxf, vcyf, cmax, ray_at(rays, idx));
+                    flags |= boundary_flags(A.fc, lvl, P, L, vcxf, vcyf, cmax, ray_at(rays, idx));
                 }
 
                 Acc acc;
@@ -1165,19 +1162,19 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 for (int k = 0; k < 9; k++) acc.f[k] = 0.0f;
                 if (!ncc) {
                     if (P.kind == PASS_JAC) {
-                        if (!P.slow) run_pixels<true, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
-                        else run_pixels<true, true, false>(P, L, rays, i1, m, tid, NT, acc);
+                        if (!P.slow) run_pixels<true, false, !RAYS_SMEM>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<true, true, false>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
                     } else {
-                        if (!P.slow) run_pixels<false, false, !RAYS_SMEM>(P, L, rays, i1, m, tid, NT, acc);
-                        else run_pixels<false, true, false>(P, L, rays, i1, m, tid, NT, acc);
+                        if (!P.slow) run_pixels<false, false, !RAYS_SMEM>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<false, true, false>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
                     }
                 } else {
                     if (P.kind == PASS_JAC) {
-                        if (!P.slow) run_pixels<true, false, !RAYS_SMEM, true>(P, L, rays, i1, m, tid, NT, acc);
-                        else run_pixels<true, true, false, true>(P, L, rays, i1, m, tid, NT, acc);
+                        if (!P.slow) run_pixels<true, false, !RAYS_SMEM, true>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<true, true, false, true>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
                     } else {
-                        if (!P.slow) run_pixels<false, false, !RAYS_SMEM, true>(P, L, rays, i1, m, tid, NT, acc);
-                        else run_pixels<false, true, false, true>(P, L, rays, i1, m, tid, NT, acc);
+                        if (!P.slow) run_pixels<false, false, !RAYS_SMEM, true>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+                        else run_pixels<false, true, false, true>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
                     }
                 }
                 // per-warp sums: SSD 1 (+5 with the Jacobian), NCC 3 (+9)
@@ -1324,7 +1321,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         next_theta = __shfl_sync(0xffffffffu, next_theta, 0);
                         // remember the coefficients of the iterate before they are overwritten
                         if (take_base) {
-                            if (lane < 9) S->hbase[lane] = PP->h[0][lane];
+                            if (lane < 9) S->hbase[lane] = PP->h[lane];
                             if (lane == 0) S->base_valid = 1;
                         }
                         __syncwarp();
@@ -1333,7 +1330,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                         if (PP->kind == PASS_STOP) break;       // NaN normal
                         // would this pass return the iterate's sum?  (trial points only)
                         bool same = S->where != AT_X_JAC && S->base_valid != 0 && A.memo_trials;
-                        if (lane < 9) same = same && (PP->h[0][lane] == S->hbase[lane]);
+                        if (lane < 9) same = same && (PP->h[lane] == S->hbase[lane]);
                         same = __all_sync(0xffffffffu, same);
                         if (!same) break;                       // run the pass
                         memo = true;
@@ -1412,6 +1409,18 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     if (A.cost_mode == FM3D_COST_NCC && A.mode == 2)
         return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "the dense candidate sweep evaluates the reference's SSD cost only (normals_cost = 0)");
     A.mcap = (disc_capacity(A.r) + 31) & ~31;
+    {   // camera constants of the pixel loops as floats in the kernel parameter block (constant bank -> uniform operands)
+        FastConsts& c = A.fc;
+        const fm3d_cam& cam = ctx->cam;
+        c.k1 = (float)cam.k1; c.k2 = (float)cam.k2; c.k3 = (float)cam.k3; c.p1 = (float)cam.p1; c.p2 = (float)cam.p2;
+        c.p1x2 = 2.0f * c.p1; c.p2x2 = 2.0f * c.p2;
+        c.t0 = (float)cam.t[0]; c.t1 = (float)cam.t[1]; c.t2 = (float)cam.t[2];
+        for (int l = 0; l < FM3D_MAX_LEVELS; l++) {
+            const double scale = 1.0 / (double)(1 << l);        // actual_scale_ (normaloptimizer.cpp:226-241)
+            c.sfx[l] = (float)(scale * cam.fx); c.sfy[l] = (float)(scale * cam.fy);
+            c.scx[l] = (float)(scale * cam.cx); c.scy[l] = (float)(scale * cam.cy);
+        }
+    }
     int nt = ctx->opt_normals_threads;
     nt = nt < 128 ? 128 : (nt > FAST_NT ? FAST_NT : (nt & ~63));
     // the opt-in maximum covers static + dynamic shared memory: the control structs are static

@@ -42,8 +42,9 @@ PIXELS_RAY, PYRAMIDS, NNDR_EPS, EPS_LMMIN = 64, 3, 0.55, 1e-10
 PENALTY = 1          # FM3D_PENALTY_INT_ABS
 PENALTY_ALT = 0      # FM3D_PENALTY_FABS
 PENALTY_NAMES = {0: "fabs", 1: "int_abs", 2: "off"}
-FLOP_PER_PIXEL_EVAL = 64.0    # algorithmic fp32 work of one pixel evaluation
-FLOP_PER_PIXEL_JAC = 152.0    # the same plus its analytic derivatives w.r.t. (phi, theta)
+FLOP_PER_PIXEL_EVAL = 64.0    # algorithmic fp32 work of one pixel evaluation of the reference
+FLOP_EXEC_VALUE = 58.0        # executed by normals_fast_kernel per pixel of a value-only pass (34 packed ops per pixel pair + the fp64 sum)
+FLOP_EXEC_JAC = 113.0         # ... of a value + analytic-Jacobian pass (67 packed ops per pixel pair)
 SEED = 1001
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of normals_fast_kernel on this workload (ncu --set full)
 NORMALS_TRAFFIC_BYTES = 0.8902e9
@@ -713,8 +714,10 @@ def run_gpu_arm(args):
         # nominal SMs*128*2*f; measured on this pool with tools/micro/ffma2_rate.cu: 73.96 TFLOP/s at 1965 MHz
         # (profiles/r01_fp32_peak_microbench.txt), i.e. 99.3 % of nominal -> the measured figure, scaled by the clock
         fp32_peak = 0.9934 * info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
-        flops_exec = stats["pixel_evals_value"] * FLOP_PER_PIXEL_EVAL + stats["pixel_evals_jacobian"] * FLOP_PER_PIXEL_JAC
-        achieved = flops_exec / t_norm_s / 1e12
+        flops_exec = stats["pixel_evals_value"] * FLOP_EXEC_VALUE + stats["pixel_evals_jacobian"] * FLOP_EXEC_JAC
+        achieved_exec = flops_exec / t_norm_s / 1e12
+        # W = sum over features and levels of nfev * m pixel evaluations of 64 flop each
+        achieved = pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -733,23 +736,26 @@ def run_gpu_arm(args):
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload under `ncu --set full`
             "traffic": NORMALS_TRAFFIC_BYTES, "traffic_unit": "bytes per launch (ncu --set full, " + NORMALS_TRAFFIC_SOURCE + ")",
             "traffic_algorithmic": n_inl * 44e3,
-            "note": "compute-bound kernel (SURVEY 8d): algorithmic flops = 64 x value-only pixel evaluations + 152 x "
-                    "value+analytic-Jacobian pixel evaluations executed (counted by the kernel) / CUDA-event time; peak = "
-                    "measured FFMA rate (tools/micro/ffma2_rate.cu: 73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; "
-                    "MEASURED_PEAKS.json has no fp32 figure); HBM traffic is compulsory only "
-                    "(~44 KB/feature) and DRAM throughput ~0 (ncu, profiles/)",
+            "note": "compute-bound kernel; achieved = ALGORITHMIC flops of SURVEY 8(d) (64 flop x sum over features and levels of "
+                    "nfev x m pixel evaluations, nfev = what lmfit evaluates with its forward-difference Jacobian: 1 per trial, "
+                    "2 per Jacobian) / CUDA-event time of the launch; peak = measured FFMA rate (tools/micro/ffma2_rate.cu: "
+                    "73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; MEASURED_PEAKS.json has no fp32 figure).  `executed` is what the "
+                    "kernel itself issues: 58 flop per pixel of a value-only pass, 113 per pixel of a value + analytic-Jacobian "
+                    "pass, counted by the kernel (rounds 1 and 2a reported that figure as `frac`, with 64 / 152).  HBM traffic is "
+                    "compulsory only (~44 KB/feature) and DRAM throughput ~0 (ncu, profiles/)",
+            "achieved_executed": achieved_exec, "frac_executed": achieved_exec / fp32_peak,
             "pixel_evals_value": stats["pixel_evals_value"], "pixel_evals_jacobian": stats["pixel_evals_jacobian"],
             "passes": n_pass, "passes_fused": stats["passes_fused"], "fused_accepted": stats["fused_accepted"],
             "passes_global_taps": stats["passes_slow"],
             "reference_equivalent_pixel_evals": pixel_evals_ref,
-            "reference_equivalent_tflops": pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12,
-            "frac_reference_equivalent": pixel_evals_ref * FLOP_PER_PIXEL_EVAL / t_norm_s / 1e12 / fp32_peak,
+            "reference_equivalent_tflops": achieved,
+            "frac_reference_equivalent": achieved / fp32_peak,
             "thread0_cycle_share": {"pixel_loop": cyc["cycles_pixels"] / cyc_tot, "serial_lm_step": cyc["cycles_serial"] / cyc_tot},
             # the packed FMAs of the pixel loop read {64-bit, 32-bit broadcast constant, 64-bit} register sources: that form
             # sustains 54.6 TFLOP/s on this pool (three distinct 64-bit sources: 47.1), not the 73.96 of re-used operands --
             # vector register-file bandwidth (tools/micro/ffma2_operands.cu, profiles/r01f_ffma2_operand_microbench.txt)
             "peak_operand_limited": 54.63 * sm_max / 1965.0,
-            "frac_of_operand_limited_peak": achieved / (54.63 * sm_max / 1965.0),
+            "frac_executed_of_operand_limited_peak": achieved_exec / (54.63 * sm_max / 1965.0),
             "ms_per_launch": t_norm_s * 1e3,
             "hbm_compulsory_gbs": (n_inl * 44e3 / t_norm_s) / 1e9, "hbm_peak_gbs": hbm_peak,
         }

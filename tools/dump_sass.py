@@ -37,6 +37,8 @@ with open(os.path.join(OUT, "r01_match_kernels.txt"), "w") as f:
 # ---- normal search: the value+Jacobian loop of the layout the bench runs (rays streamed from L2)
 for fn in functions("fm3d_normals_fast.o"):
     tag = "rays_smem" if "ILb1ELb1E" in fn else ("rays_l2_i1_smem" if "ILb0ELb1E" in fn else "rays_l2")
+    if re.search(r"ILb[01]ELb[01]ELb1EEE", fn):
+        tag += "_ncc"                      # cost_mode NCC: its own instantiation
     s = sass("fm3d_normals_fast.o", fn)
     # loops: backward branches; pick the ones that contain LDS.U8 (window taps)
     addr = {}
@@ -53,7 +55,7 @@ for fn in functions("fm3d_normals_fast.o"):
             body = s[j:i + 1]
             if sum("LDS.U8" in b for b in body) >= 8 and len(body) < 400:
                 loops.append((j, i, body))
-    with open(os.path.join(OUT, f"r01_normals_fast_kernel_{tag}.txt"), "w") as f:
+    with open(os.path.join(OUT, f"r02_normals_fast_kernel_{tag}.txt"), "w") as f:
         f.write(f"# cuobjdump -sass -fun {fn}\n# TMA window staging: " +
                 ", ".join(sorted({k for l in s for k in re.findall(r"UTMALDG\.\w+|SYNCS\.[A-Z0-9.]+", l)})) + "\n")
         for (j, i, body) in loops:
