@@ -68,13 +68,10 @@ enum { AT_X_JAC = 0, AT_XT_PLAIN = 1, AT_XT_FUSED = 2 };
 
 // Everything a pass needs, written by the lanes of warp 0 of the group.
 struct FastPass {
-    // A = h[0] dx + h[1] dy + h[2] (x numerator, offset form), B = h[3] dx + h[4] dy + h[5], C = h[6] dx + h[7] dy + h[8]
-    // (common denominator w2 = H2 . v)
+    // A = h[0] dx + h[1] dy (x numerator, offset form), B = h[3] dx + h[4] dy, C = h[6] dx + h[7] dy + h[8] (common
+    // denominator w2 = H2 . v).  The reference ray vc is the ray through P itself, H P is parallel to the camera-2 point
+    // of P, so the numerators have no constant term (h[2] = h[5] = 0).
     float h[9];
-    // Jacobian passes.  H = (n.P) R + t n^T gives dH/dp v = a_p H v + t (n_p - a_p n).v with a_p = (n_p.P)/(n.P): the first term
-    // is parallel to H v and drops out of the perspective division, so the projection moves along the epipolar direction,
-    //   d(x, y)/dp = (t0 - x t2, t1 - y t2) * sigma_p / w2,   sigma_p = (n_p - a_p n).v = sg[p][0] dx + sg[p][1] dy + sg[p][2]
-    float sg[2][3];
     float nd[3];        // sign(n.P) * n.v = nd[0] dx + nd[1] dy + nd[2]
     float mabs;         // |n.P|
     int kind;           // PASS_*
@@ -99,6 +96,12 @@ struct FastShared {
     int where;          // AT_*
     int alive;
     int first_row, last_row;
+    // Jacobian passes.  H = (n.P) R + t n^T gives dH/dp v = a_p H v + t (n_p - a_p n).v with a_p = (n_p.P)/(n.P): the first term
+    // is parallel to H v and drops out of the perspective division, so the projection moves along the epipolar direction,
+    //   d(x, y)/dp = (t0 - x t2, t1 - y t2) * sigma_p / w2,   sigma_p = (n_p - a_p n).v = sg[p][0] dx + sg[p][1] dy
+    // (n_p - a_p n is orthogonal to P, hence to vc: no constant term).  The pixel threads sum the moments of
+    // U = (dx, dy) E, E = dI2/d(x,y) . (t0 - x t2, t1 - y t2) / w2; warp 0 applies sg to the sums (jacobian_sums_from_moments).
+    double sg[2][2];
     float hbase[9];     // value coefficients (FastPass::h) of the current LM iterate ...
     double s0_base;     // ... and the residual sum the pass at the iterate returned
     int base_valid;
@@ -118,6 +121,7 @@ struct LevelConst {
     float c0;                    // cost_mode NCC: value subtracted from every image-2 sample before it is summed (~ mean of image 1)
     const uint8_t* win;
     unsigned ww, coff, amax;
+    unsigned koff, ahi;          // packed loop: shared-memory address of a tap = min(ty_bits * ww + tx_bits + koff, ahi)
     int wx0, wy0, lx_min, lx_cnt, ly_min, ly_cnt;
     const uint8_t* img2;
     int w, h, pitch;
@@ -150,6 +154,9 @@ __device__ __forceinline__ float rcp_approx(float a) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r;
 }
+// window taps by 32-bit shared-memory address (no generic-pointer arithmetic in the pixel loop)
+__device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u8_1(unsigned a) { unsigned v; asm("ld.shared.u8 %0, [%1+1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float u2f(unsigned b) {  // I2FP (the compiler would pick the slow I2F.U16)
     float f;
     asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(b));
@@ -189,8 +196,8 @@ struct Acc {
 // sampled intensity with respect to (phi, theta).
 template <bool JAC, bool SLOW, bool NCC = false>
 __device__ __forceinline__ void eval_pixel_fast(const FastConsts& K, const int lvl, const FastPass& P, const LevelConst& L, float2 dv, float I1, Acc& acc) {
-    const float A0 = fmaf(P.h[0], dv.x, fmaf(P.h[1], dv.y, P.h[2]));
-    const float B0 = fmaf(P.h[3], dv.x, fmaf(P.h[4], dv.y, P.h[5]));
+    const float A0 = fmaf(P.h[0], dv.x, __fmul_rn(P.h[1], dv.y));
+    const float B0 = fmaf(P.h[3], dv.x, __fmul_rn(P.h[4], dv.y));
     const float C0 = fmaf(P.h[6], dv.x, fmaf(P.h[7], dv.y, P.h[8]));
     // MUFU reciprocal as it is (1 ulp): it multiplies the OFFSET from the centre, 1e-7 of at most ~100 pixels
     const float iz = rcp_approx(C0);
@@ -246,10 +253,10 @@ __device__ __forceinline__ void eval_pixel_fast(const FastConsts& K, const int l
         const float dxd = fmaf(ex, g, fmaf(x, dg, K.p2x2 * rho));
         const float dyd = fmaf(ey, g, fmaf(y, dg, K.p1x2 * rho));
         const float E = fmaf(Gx, dxd, Gy * dyd) * iz;
-        const float s1 = fmaf(P.sg[0][0], dv.x, fmaf(P.sg[0][1], dv.y, P.sg[0][2]));
-        const float s2 = fmaf(P.sg[1][0], dv.x, fmaf(P.sg[1][1], dv.y, P.sg[1][2]));
-        const float Ip = s1 * E;   // dI2/dphi   (residual derivative = -Ip)
-        const float It = s2 * E;   // dI2/dtheta
+        // dI2/dp = sigma_p E with sigma_p linear in (dx, dy): the sums below are the moments of (dx E, dy E), the
+        // coefficients of sigma_phi, sigma_theta are applied to the sums (jacobian_sums_from_moments)
+        const float Ip = dv.x * E;
+        const float It = dv.y * E;
         if (NCC) {
             acc.f[0] += Ip; acc.f[1] += It;
             acc.f[2] = fmaf(d, Ip, acc.f[2]); acc.f[3] = fmaf(d, It, acc.f[3]);
@@ -321,8 +328,8 @@ struct Acc2 {      // Jacobian sums of the packed loop: lanes are added at the e
 // the same sequence of IEEE operations as the scalar function, lane by lane.
 template <bool JAC, bool NCC = false>
 __device__ __forceinline__ void eval_pixel_pair(const FastConsts& K, const int lvl, const FastPass& P, const LevelConst& L, f2 X, f2 Y, f2 I1p, Acc& acc, Acc2& acc2) {
-    const f2 A0 = fma2(bc(P.h[0]), X, fma2(bc(P.h[1]), Y, bc(P.h[2])));
-    const f2 B0 = fma2(bc(P.h[3]), X, fma2(bc(P.h[4]), Y, bc(P.h[5])));
+    const f2 A0 = fma2(bc(P.h[0]), X, mul2(bc(P.h[1]), Y));
+    const f2 B0 = fma2(bc(P.h[3]), X, mul2(bc(P.h[4]), Y));
     const f2 C0 = fma2(bc(P.h[6]), X, fma2(bc(P.h[7]), Y, bc(P.h[8])));
     const f2 iz = mk2(rcp_approx(lo2(C0)), rcp_approx(hi2(C0)));
     const f2 x = fma2(A0, iz, bc(L.xc)), y = fma2(B0, iz, bc(L.yc));
@@ -334,14 +341,13 @@ __device__ __forceinline__ void eval_pixel_pair(const FastConsts& K, const int l
     const f2 su = fma2(xd, bc(K.sfx[lvl]), bc(K.scx[lvl])), sv = fma2(yd, bc(K.sfy[lvl]), bc(K.scy[lvl]));
     const f2 tx = add2_rm(su, bc(FLOOR_MAGIC)), ty = add2_rm(sv, bc(FLOOR_MAGIC));
     const f2 ax = sub2(su, sub2(tx, bc(FLOOR_MAGIC))), ay = sub2(sv, sub2(ty, bc(FLOOR_MAGIC)));
-    unsigned aa = __float_as_uint(lo2(ty)) * L.ww + __float_as_uint(lo2(tx)) - L.coff;
-    unsigned ab = __float_as_uint(hi2(ty)) * L.ww + __float_as_uint(hi2(tx)) - L.coff;
-    aa = min(aa, L.amax);   // memory safety only: the boundary test proves the address is in range
-    ab = min(ab, L.amax);
-    const uint8_t* pa = L.win + aa;
-    const uint8_t* pb = L.win + ab;
-    const f2 b00 = mk2(u2f(pa[0]), u2f(pb[0])), b10 = mk2(u2f(pa[1]), u2f(pb[1]));
-    const f2 b01 = mk2(u2f(pa[L.ww]), u2f(pb[L.ww])), b11 = mk2(u2f(pa[L.ww + 1]), u2f(pb[L.ww + 1]));
+    // memory safety only (the boundary test proves the taps are in the window): an index above the window is clamped to its
+    // last tap, one below it wraps around to the same clamp or lands in this CTA's shared memory below the window
+    const unsigned aa = min(__float_as_uint(lo2(ty)) * L.ww + __float_as_uint(lo2(tx)) + L.koff, L.ahi);
+    const unsigned ab = min(__float_as_uint(hi2(ty)) * L.ww + __float_as_uint(hi2(tx)) + L.koff, L.ahi);
+    const unsigned aa1 = aa + L.ww, ab1 = ab + L.ww;
+    const f2 b00 = mk2(u2f(lds_u8(aa)), u2f(lds_u8(ab))), b10 = mk2(u2f(lds_u8_1(aa)), u2f(lds_u8_1(ab)));
+    const f2 b01 = mk2(u2f(lds_u8(aa1)), u2f(lds_u8(ab1))), b11 = mk2(u2f(lds_u8_1(aa1)), u2f(lds_u8_1(ab1)));
     const f2 d0 = sub2(b01, b00), d1 = sub2(b11, b10);
     const f2 c0 = fma2(ay, d0, b00), c1 = fma2(ay, d1, b10);
     const f2 gx = sub2(c1, c0);
@@ -367,10 +373,8 @@ __device__ __forceinline__ void eval_pixel_pair(const FastConsts& K, const int l
         const f2 dxd = fma2(ex, g, fma2(x, dg, mul2(bc(K.p2x2), rho)));
         const f2 dyd = fma2(ey, g, fma2(y, dg, mul2(bc(K.p1x2), rho)));
         const f2 E = mul2(fma2(Gx, dxd, mul2(Gy, dyd)), iz);
-        const f2 s1 = fma2(bc(P.sg[0][0]), X, fma2(bc(P.sg[0][1]), Y, bc(P.sg[0][2])));
-        const f2 s2 = fma2(bc(P.sg[1][0]), X, fma2(bc(P.sg[1][1]), Y, bc(P.sg[1][2])));
-        const f2 Ip = mul2(s1, E);   // dI2/dphi   (residual derivative = -Ip)
-        const f2 It = mul2(s2, E);   // dI2/dtheta
+        const f2 Ip = mul2(X, E);    // moments of (dx E, dy E): see eval_pixel_fast
+        const f2 It = mul2(Y, E);
         if (NCC) {
             acc2.a[0] = add2(acc2.a[0], Ip); acc2.a[1] = add2(acc2.a[1], It);
             acc2.a[2] = fma2(d, Ip, acc2.a[2]); acc2.a[3] = fma2(d, It, acc2.a[3]);
@@ -442,19 +446,21 @@ __device__ __forceinline__ void run_pixels(const FastConsts& K, const int lvl, c
         f2 I = 0ull;
         if (p < npair) { r = LD_SCRATCH(rp + p); I = LD_SCRATCH(ip + p); }
 #if FM3D_NORMALS_UNROLL2
-        ulonglong2 r2 = make_ulonglong2(0ull, 0ull);
-        f2 I2 = 0ull;
-        if (p + NT < npair) { r2 = LD_SCRATCH(rp + p + NT); I2 = LD_SCRATCH(ip + p + NT); }
-        for (; p + NT < npair; p += 2 * NT) {
-            const ulonglong2 cr = r, cr2 = r2;
-            const f2 cI = I, cI2 = I2;
-            const int nx = p + 2 * NT;
-            if (nx < npair) { r = LD_SCRATCH(rp + nx); I = LD_SCRATCH(ip + nx); }
-            if (nx + NT < npair) { r2 = LD_SCRATCH(rp + nx + NT); I2 = LD_SCRATCH(ip + nx + NT); }
-            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, cr.x, cr.y, cI, acc, acc2);
-            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, cr2.x, cr2.y, cI2, acc, acc2);
+        // two register sets take turns (no copies): while one pair is evaluated the loads of the next are in flight
+        const ulonglong2* __restrict__ rq = rp + p;
+        const f2* __restrict__ iq = ip + p;
+        int left = p < npair ? (npair - p + NT - 1) / NT : 0;
+        ulonglong2 rb = make_ulonglong2(0ull, 0ull);
+        f2 Ib = 0ull;
+        while (left >= 2) {
+            rb = LD_SCRATCH(rq + NT); Ib = LD_SCRATCH(iq + NT);
+            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, r.x, r.y, I, acc, acc2);
+            if (left > 2) { r = LD_SCRATCH(rq + 2 * NT); I = LD_SCRATCH(iq + 2 * NT); }
+            eval_pixel_pair<JAC, NCC>(K, lvl, P, L, rb.x, rb.y, Ib, acc, acc2);
+            rq += 2 * NT; iq += 2 * NT;
+            left -= 2;
         }
-        if (p < npair) eval_pixel_pair<JAC, NCC>(K, lvl, P, L, r.x, r.y, I, acc, acc2);
+        if (left == 1) eval_pixel_pair<JAC, NCC>(K, lvl, P, L, r.x, r.y, I, acc, acc2);
 #else
         for (; p < npair; p += NT) {
             const ulonglong2 cr = r;
@@ -475,6 +481,24 @@ __device__ __forceinline__ void run_pixels(const FastConsts& K, const int lvl, c
     if (JAC) {
 #pragma unroll
         for (int k = 0; k < NJ; k++) acc.f[k] += lo2(acc2.a[k]) + hi2(acc2.a[k]);
+    }
+}
+
+// Jacobian pass: the pixel threads summed the moments of U = (dx E, dy E); dI2/dp = sg[p] . U.  In place: SSD s[1..5] =
+// sum U1 U1, U1 U2, U2 U2, U1 d, U2 d -> sum Ip Ip, Ip It, It It, Ip d, It d; NCC s[3..11] = sum U1, U2, v U1, v U2, u U1, u U2,
+// U1 U1, U1 U2, U2 U2 -> the same sums of (Ip, It).
+__device__ __forceinline__ void jacobian_sums_from_moments(double* s, const double (*c)[2], bool ncc) {
+    const double a0 = c[0][0], a1 = c[0][1], b0 = c[1][0], b1 = c[1][1];
+    double* q = s + (ncc ? 9 : 1);
+    const double m11 = q[0], m12 = q[1], m22 = q[2];
+    q[0] = a0 * a0 * m11 + 2.0 * a0 * a1 * m12 + a1 * a1 * m22;
+    q[1] = a0 * b0 * m11 + (a0 * b1 + a1 * b0) * m12 + a1 * b1 * m22;
+    q[2] = b0 * b0 * m11 + 2.0 * b0 * b1 * m12 + b1 * b1 * m22;
+    const int first = ncc ? 3 : 4, npairs = ncc ? 3 : 1;
+    for (int k = 0; k < npairs; k++) {
+        const double u1 = s[first + 2 * k], u2 = s[first + 2 * k + 1];
+        s[first + 2 * k] = a0 * u1 + a1 * u2;
+        s[first + 2 * k + 1] = b0 * u1 + b1 * u2;
     }
 }
 
@@ -574,8 +598,7 @@ __device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, d
             c0 = H20; c1 = H21; c2 = H22;
         } else {
             // numerators in offset form: (H0 - xc H2) . v and (H1 - yc H2) . v with v = vc + dv.  Their
-            // constant terms vanish when the centre ray passes exactly through P; what is left is
-            // the residual of the 5-iteration undistort of the centre pixel
+            // constant terms vanish: vc is the ray through P
             const double ref = row == 0 ? S->xc : S->yc;
             const double tr = cam.t[row];
             c0 = me * cam.R[3 * row] + tr * nx - ref * H20;
@@ -584,7 +607,7 @@ __device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, d
         }
         PP->h[3 * row] = (float)c0;
         PP->h[3 * row + 1] = (float)c1;
-        PP->h[3 * row + 2] = (float)(c0 * vcx + c1 * vcy + c2);
+        PP->h[3 * row + 2] = row == 2 ? (float)(c0 * vcx + c1 * vcy + c2) : 0.0f;   // numerators: (H0 - xc H2) . vc = 0
     } else if (lane < 5) {
         // sigma_p = (n_p - a_p n) . v, a_p = (n_p.P)/(n.P), for p = phi (lane 3), theta (lane 4): see FastPass::sg
         const bool dphi = lane == 3;
@@ -593,9 +616,9 @@ __device__ void publish_pass(FastPass* PP, FastShared* S, const fm3d_cam& cam, d
         const double mp = nx * S->P[0] + ny * S->P[1] + nz * S->P[2];
         const double a = m0 != 0.0 ? mp / m0 : 0.0;     // n.P = 0 fails the bounding-box gate of every pixel
         const double c0 = nx - a * n0x, c1 = ny - a * n0y, c2 = nz - a * n0z;
-        PP->sg[lane - 3][0] = (float)c0;
-        PP->sg[lane - 3][1] = (float)c1;
-        PP->sg[lane - 3][2] = (float)(c0 * vcx + c1 * vcy + c2);
+        S->sg[lane - 3][0] = c0;        // (c0, c1, c2) . vc = 0: n_p - a n is orthogonal to P
+        S->sg[lane - 3][1] = c1;
+        (void)c2;
     } else if (lane == 9) {
         const double me = n0x * S->P[0] + n0y * S->P[1] + n0z * S->P[2];
         const double sg = me < 0 ? -1.0 : 1.0;
@@ -823,9 +846,9 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             // centre ray, and the camera-2 projection of P: P lies on every candidate plane, so this
             // is where the centre of the disc lands whatever the normal (reference point of the
             // offset form)
-            double vcx, vcy;
-            fm3d_undistort(cam, cu, cv, vcx, vcy);
-            S->vc[0] = vcx; S->vc[1] = vcy;
+            // reference ray of the offsets: the ray through P itself (not the 5-iteration undistort of the centre pixel, which
+            // misses it by the residual of that iteration; every disc pixel still gets its own 5-iteration ray below)
+            S->vc[0] = Px / Pz; S->vc[1] = Py / Pz;
             const double X2 = cam.R[0] * Px + cam.R[1] * Py + cam.R[2] * Pz + cam.t[0];
             const double Y2 = cam.R[3] * Px + cam.R[4] * Py + cam.R[5] * Pz + cam.t[1];
             const double Z2 = cam.R[6] * Px + cam.R[7] * Py + cam.R[8] * Pz + cam.t[2];
@@ -972,6 +995,8 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             }
             L.coff = (FLOOR_MAGIC_BITS + (unsigned)L.wy0) * L.ww + FLOOR_MAGIC_BITS + (unsigned)L.wx0;
             L.amax = L.ww * (unsigned)wh - L.ww - 2u;
+            L.koff = smem_u32(win) - L.coff;
+            L.ahi = smem_u32(win) + L.amax;
 
             // warp 0: start the LM of this level (optimize(), :247-292)
             if (wid == 0) {
@@ -1214,6 +1239,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                             }
                             s[k] = v;
                         }
+                        if (P.kind == PASS_JAC) jacobian_sums_from_moments(s, S->sg, ncc);
                         if (ncc) ncc_sums_to_normal_equations(s, S->ncc_su, S->ncc_suu, m, P.kind == PASS_JAC);
                     }
                     any_flags = __reduce_or_sync(0xffffffffu, any_flags);
