@@ -48,6 +48,7 @@ struct fm3d_ctx {
     int opt_lm_patience = 100;
     int opt_normals_threads = 512;
     int opt_normals_tma = 1;
+    int opt_normals_pingpong = 1;  // fast kernel, four-window layout, mode 0: two features per eight warps taking turns (normals_pp_kernel)
     int opt_normals_groups = 0;    // fast kernel: feature pipelines per CTA; 0 = automatic (2 when there are more features than SMs)
     int opt_normals_memo = 1;      // fast kernel: trials whose fp32 coefficients equal the iterate's are not re-evaluated
     int opt_normals_fuse = 1;      // fast kernel: Jacobian evaluated together with the first trial of an iteration

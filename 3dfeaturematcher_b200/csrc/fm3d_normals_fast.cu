@@ -127,6 +127,11 @@ struct LevelConst {
     int w, h, pitch;
 };
 
+struct FeatureLocals {
+    double cu, cv;          // projection of P into image 1: centre of the disc
+    int m;                  // pixels of the disc inside the image
+    float vcxf, vcyf;       // reference ray (fp32, for the bounding-box gate)
+};
 constexpr int MAX_GROUPS = 4;
 constexpr int NSUM_SSD = 6;          // sums of a pass: residual^2; J^T J (3), J^T r (2)
 constexpr int NSUM = 12;             // cost_mode NCC: sum v, v^2, u v; sum D (2), v D (2), u D (2), D D (3)
@@ -141,6 +146,13 @@ struct GroupCtl {
     double wk[SWEEP_B];              // ... and their penalty weights
     unsigned wflagsk[16 * SWEEP_B];
     int resume_at;                   // mode 2, batched: candidate the one-by-one loop takes over at (or -1)
+    // two-slot kernel (normals_pp_kernel): what a slot's next step is, and the registers of the level in progress
+    int kind;                        // STEP_*
+    int ready_gen;                   // steps of the slot that have been made ready so far (written by its LM warp)
+    int lvl;
+    unsigned lvl_flags;              // image-1 gate of the level, charged to its first pass
+    FeatureLocals Fsave;
+    LevelConst Lsave;
     uint64_t bar;
 };
 
@@ -662,6 +674,165 @@ __device__ __forceinline__ int consume_jacobian(FastShared* S, fm3d_lm2& lm, con
     return fm3d_lm2_after_jacobian(&lm, ff, S00, S01, S11, g0, g1);
 }
 
+// The serial step between two passes, on the group's LM warp (all 32 lanes, uniform arguments): reduces the per-warp sums of
+// the pass just evaluated, advances lmfit's state machine on lane 0 (answering trials that round to the iterate's
+// coefficients without a pass), publishes the next pass into *PP (PP->kind = PASS_STOP: level finished or feature dropped).
+template <bool ncc>
+__device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, const FastPass& P, const int m, const int f, const int NW,
+                                           const int lane, const long long t_a, const long long t_b0, const long long t_b) {
+    const fm3d_cam& cam = A.cam;
+    double* red = G.red;
+    unsigned* wflags = G.wflags;
+    FastShared* S = &G.S;
+    FastPass* PP = &G.PP;
+                        double s[NSUM];
+                        unsigned any_flags = lane < NW ? wflags[lane] : 0u;
+                        {
+                            const int ns = ncc ? (P.kind == PASS_JAC ? NSUM : 3) : NSUM_SSD;
+    #pragma unroll
+                            for (int k = 0; k < NSUM; k++) {
+                                double v = (lane < NW && k < ns) ? red[lane * NSUM + k] : 0.0;
+                                if (k < ns) {
+    #pragma unroll
+                                    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                                }
+                                s[k] = v;
+                            }
+                            if (P.kind == PASS_JAC) jacobian_sums_from_moments(s, S->sg, ncc);
+                            if (ncc) ncc_sums_to_normal_equations(s, S->ncc_su, S->ncc_suu, m, P.kind == PASS_JAC);
+                        }
+                        any_flags = __reduce_or_sync(0xffffffffu, any_flags);
+                        const long long t_r = clock64();
+                        long long t_lm = 0;
+                        // `memo`: the result in s[0] was not evaluated but taken from the base point: the
+                        // proposed trial point rounds to the same fp32 homography coefficients as the
+                        // current iterate, so the pass would return the iterate's sum bit for bit.  Deep
+                        // in lmfit's tail (steps below 1e-8 rad, tolerances of 30 eps) this is what every
+                        // trial does; those trials are answered here without a pass.
+                        bool memo = false;
+                        bool slow_pass = P.slow != 0;
+                        int pass_kind = P.kind;
+                        for (;;) {
+                            int next_kind = PASS_STOP;          // what lane 0 asks the warp to publish
+                            int take_base = 0;                  // PP->h[0] are the coefficients of the (new) iterate
+                            double next_phi = 0.0, next_theta = 0.0;
+                            const long long t_l0 = clock64();
+                            if (lane == 0) {
+                                fm3d_lm2& lm = S->lm;
+                                if (!memo) {   // executed work (fm3d_get_normals_stats)
+                                    const int slot = pass_kind == PASS_VALUE ? 0 : (S->where == AT_X_JAC ? 1 : 2);
+                                    S->stats[slot]++;
+                                    if (slow_pass) S->stats[4]++;
+                                    S->stats[pass_kind == PASS_VALUE ? 5 : 6] += (unsigned long long)m;
+                                } else {
+                                    S->stats[13]++;
+                                }
+                                const unsigned fl = memo ? 0u : any_flags;
+                                if ((fl & FLAG_WINDOW) && !(fl & 7) && !slow_pass) {
+                                    PP->slow = 1;               // same pass again, taps from global memory
+                                    next_kind = -1;
+                                } else if (A.mode == 2) {
+                                    // dense candidate sweep: cost of this candidate (NaN if it fails a gate), next one
+                                    const int K = A.sweep_nphi * A.sweep_ntheta, c = S->cand;
+                                    const bool bad = (fl & 7) || s[0] != s[0];
+                                    const double cval = bad ? __longlong_as_double(0x7ff8000000000000LL) : S->w[0] * S->w[0] * s[0];
+                                    if (A.cost) A.cost[(size_t)f * K + c] = cval;
+                                    if (!bad && cval < S->best_cost) { S->best_cost = cval; S->best_idx = c; }
+                                    if (c + 1 < K) {
+                                        S->cand = c + 1;
+                                        const int ip = (c + 1) / A.sweep_ntheta, it = (c + 1) - ip * A.sweep_ntheta;
+                                        next_kind = PASS_VALUE;
+                                        next_phi = S->sweep_c[0] + ((double)ip - 0.5 * (double)(A.sweep_nphi - 1)) * A.sweep_dphi;
+                                        next_theta = S->sweep_c[1] + ((double)it - 0.5 * (double)(A.sweep_ntheta - 1)) * A.sweep_dtheta;
+                                    } else {
+                                        PP->kind = PASS_STOP;
+                                    }
+                                } else if ((fl & 7) || s[0] != s[0]) {
+                                    // all bounding-box / NaN tests of an evaluation precede its pixel tests
+                                    S->status = ((fl & FLAG_NAN) || !(fl & 7)) ? FM3D_FEAT_ABORT_NAN
+                                              : (fl & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
+                                    S->alive = 0;
+                                    PP->kind = PASS_STOP;
+                                } else if (A.mode != 0) {
+                                    A.cost[f] = S->w[0] * S->w[0] * s[0];
+                                    PP->kind = PASS_STOP;
+                                } else {
+                                    const int where = S->where;
+                                    bool first_trial = false;   // the next trial opens an LM iteration
+                                    int cmd;
+                                    if (where == AT_X_JAC) {
+                                        if (lm.first && S->w[0] != 1.0) S->npenalty++;
+                                        cmd = consume_jacobian(S, lm, s, A.penalty_mode);
+                                        first_trial = true;
+                                        S->s0_base = s[0];      // sum and coefficients of the iterate
+                                        take_base = 1;
+                                    } else {
+                                        if (S->w[0] != 1.0) S->npenalty++;
+                                        const int iter_before = lm.iter;
+                                        cmd = fm3d_lm2_after_trial(&lm, S->w[0] * S->w[0] * s[0]);
+                                        const bool accepted = lm.iter != iter_before;
+                                        if (S->trial_is_first) S->fuse_hint = accepted ? 1 : 0;
+                                        if (!memo && accepted) {   // new iterate
+                                            S->s0_base = s[0];
+                                            take_base = 1;
+                                        }
+                                        // accepted (x == xt now) and the Jacobian came with the trial
+                                        if (cmd == FM3D_LM_CMD_JAC && where == AT_XT_FUSED) {
+                                            S->stats[3]++;
+                                            cmd = consume_jacobian(S, lm, s, A.penalty_mode);
+                                            first_trial = true;
+                                        }
+                                    }
+                                    if (cmd == FM3D_LM_CMD_JAC) {
+                                        S->where = AT_X_JAC;
+                                        next_kind = PASS_JAC; next_phi = lm.x[0]; next_theta = lm.x[1];
+                                    } else if (cmd == FM3D_LM_CMD_TRIAL) {
+                                        // first trial of an iteration: evaluate its Jacobian along with it;
+                                        // re-trials after a rejection are value-only
+                                        const bool fuse = first_trial && (A.fuse_trials == 1 || (A.fuse_trials == 2 && S->fuse_hint));
+                                        S->trial_is_first = first_trial ? 1 : 0;
+                                        S->where = fuse ? AT_XT_FUSED : AT_XT_PLAIN;
+                                        next_kind = fuse ? PASS_JAC : PASS_VALUE; next_phi = lm.xt[0]; next_theta = lm.xt[1];
+                                    } else {
+                                        PP->kind = PASS_STOP;   // FM3D_LM_CMD_DONE
+                                    }
+                                }
+                            }
+                            t_lm += clock64() - t_l0;
+                            next_kind = __shfl_sync(0xffffffffu, next_kind, 0);
+                            if (next_kind <= PASS_STOP) break;      // stop, or repeat the same pass (-1)
+                            take_base = __shfl_sync(0xffffffffu, take_base, 0);
+                            next_phi = __shfl_sync(0xffffffffu, next_phi, 0);
+                            next_theta = __shfl_sync(0xffffffffu, next_theta, 0);
+                            // remember the coefficients of the iterate before they are overwritten
+                            if (take_base) {
+                                if (lane < 9) S->hbase[lane] = PP->h[lane];
+                                if (lane == 0) S->base_valid = 1;
+                            }
+                            __syncwarp();
+                            publish_pass(PP, S, cam, next_phi, next_theta, next_kind, A.penalty_mode, S->lm.eps, lane);
+                            __syncwarp();
+                            if (PP->kind == PASS_STOP) break;       // NaN normal
+                            // would this pass return the iterate's sum?  (trial points only)
+                            bool same = S->where != AT_X_JAC && S->base_valid != 0 && A.memo_trials;
+                            if (lane < 9) same = same && (PP->h[lane] == S->hbase[lane]);
+                            same = __all_sync(0xffffffffu, same);
+                            if (!same) break;                       // run the pass
+                            memo = true;
+                            s[0] = S->s0_base;
+                            if (lane == 0) { S->where = AT_XT_PLAIN; }
+                            __syncwarp();
+                        }
+                        if (lane == 0) {
+                            const long long t_c = clock64();
+                            S->stats[8] += (unsigned long long)(t_b0 - t_a);   // thread 0: pixel work of the pass
+                            S->stats[9] += (unsigned long long)(t_b - t_b0);   // thread 0: wait at the barrier
+                            S->stats[10] += (unsigned long long)(t_c - t_b);   // reduction + LM + publish
+                            S->stats[11] += (unsigned long long)t_lm;          //   of which LM algebra
+                            S->stats[12] += (unsigned long long)(t_c - t_r - t_lm);   //   of which sincos + homographies
+                        }
+}
+
 // A CTA runs `groups` independent feature pipelines side by side (1 or 2): each group of warps has
 // its own window, LM state, queue slot and named barrier, so that the pixel passes of one feature
 // fill the SM while the other feature is in its serial LM step.
@@ -722,6 +893,285 @@ __device__ __forceinline__ bool stage_window(const NormalsArgs& A, const CUtenso
     }
     gsync(groups, g, NT);
     return true;
+}
+
+// What a feature needs before its first level, by all threads of its group: the disc lattice of extractPixelsContour as a row
+// table, the per-feature constants (thread 0) and the ideal rays of all disc pixels as offsets from the ray through P.
+__device__ __forceinline__ FeatureLocals feature_prologue(const NormalsArgs& A, GroupCtl& G, float2* rays, const int f, const int tid,
+                                                          const int NT, const int groups, const int g) {
+    const fm3d_cam& cam = A.cam;
+    const int r = A.r, W = A.pyr.lv[0].w, H = A.pyr.lv[0].h, levels = A.pyr.levels;
+    RowTable* rows = &G.rows;
+    FastShared* S = &G.S;
+    const long long t_f0 = clock64();
+    const double Px = A.xyz[3 * f], Py = A.xyz[3 * f + 1], Pz = A.xyz[3 * f + 2];
+
+    // ------------------------------------------------------------ prologue: disc lattice
+    double cu, cv;
+    fm3d_project(cam, Px, Py, Pz, cu, cv);  // extractPixelsContour(Vec3d) (:376-397)
+    for (int jr = tid; jr < 2 * r + 1; jr += NT) {
+        const int j = jr - r;
+        const double py = cv + (double)j;
+        int cnt = 0, lo = 0;
+        if (!(py < 0 || py >= (double)H) && cu == cu && cv == cv) {
+            const int hw = (int)floor(sqrt((double)(r * r - j * j)));
+            int ilo = -hw, ihi = hw;
+            // keep iff !(px < 0 || px >= W) with px = cu + i evaluated exactly as the reference does
+            if (cu + (double)ilo < 0) {
+                int g = (int)ceil(-cu);
+                ilo = g < -hw ? -hw : (g > hw + 1 ? hw + 1 : g);
+                while (ilo <= hw && (cu + (double)ilo) < 0) ilo++;
+                while (ilo - 1 >= -hw && !((cu + (double)(ilo - 1)) < 0)) ilo--;
+            }
+            if (cu + (double)ihi >= (double)W) {
+                int g = (int)ceil((double)W - cu) - 1;
+                ihi = g > hw ? hw : (g < -hw - 1 ? -hw - 1 : g);
+                while (ihi >= -hw && (cu + (double)ihi) >= (double)W) ihi--;
+                while (ihi + 1 <= hw && !((cu + (double)(ihi + 1)) >= (double)W)) ihi++;
+            }
+            cnt = ihi - ilo + 1;
+            if (cnt < 0) cnt = 0;
+            lo = ilo;
+        }
+        rows->start[jr + 1] = cnt;  // counts, prefix-summed below
+        rows->ilo[jr] = (short)lo;
+        rows->jrow[jr] = (short)j;
+    }
+    gsync(groups, g, NT);
+    if (tid == 0) {
+        int acc = 0, first = -1, last = -1;
+        rows->start[0] = 0;
+        for (int jr = 0; jr < 2 * r + 1; jr++) {
+            const int c = rows->start[jr + 1];
+            if (c > 0) { if (first < 0) first = jr; last = jr; }
+            acc += c;
+            rows->start[jr + 1] = acc;
+        }
+        rows->nrows = 2 * r + 1;
+        S->first_row = first; S->last_row = last;
+        S->m = acc;
+        S->status = acc > 0 ? FM3D_FEAT_OK : FM3D_FEAT_NO_PIXELS;
+        // a non-finite centre passes every `p < 0 || p >= size` test of the reference's lattice loop,
+        // the feature then dies in its first evaluation with a NaN plane point
+        if (cu != cu || cv != cv) S->status = FM3D_FEAT_ABORT_NAN;
+        S->alive = acc > 0;
+        S->npenalty = 0;
+        for (int k = 0; k < 16; k++) S->stats[k] = 0;
+        S->P[0] = Px; S->P[1] = Py; S->P[2] = Pz;
+        const double nrm = sqrt(Px * Px + Py * Py + Pz * Pz);
+        S->normal[0] = Px / nrm; S->normal[1] = Py / nrm; S->normal[2] = Pz / nrm;  // (:343)
+        if (A.nfev && A.mode == 0) for (int l = 0; l <= levels; l++) A.nfev[(size_t)f * (levels + 1) + l] = 0;
+        // centre ray, and the camera-2 projection of P: P lies on every candidate plane, so this
+        // is where the centre of the disc lands whatever the normal (reference point of the
+        // offset form)
+        // reference ray of the offsets: the ray through P itself (not the 5-iteration undistort of the centre pixel, which
+        // misses it by the residual of that iteration; every disc pixel still gets its own 5-iteration ray below)
+        S->vc[0] = Px / Pz; S->vc[1] = Py / Pz;
+        const double X2 = cam.R[0] * Px + cam.R[1] * Py + cam.R[2] * Pz + cam.t[0];
+        const double Y2 = cam.R[3] * Px + cam.R[4] * Py + cam.R[5] * Pz + cam.t[1];
+        const double Z2 = cam.R[6] * Px + cam.R[7] * Py + cam.R[8] * Pz + cam.t[2];
+        const double iz = Z2 != 0.0 ? 1.0 / Z2 : 1.0;
+        S->xc = X2 * iz; S->yc = Y2 * iz;
+    }
+    gsync(groups, g, NT);
+    const int m = S->m;
+    if (A.m_out && tid == 0) A.m_out[f] = m;
+    const double vcx = S->vc[0], vcy = S->vc[1];
+    const float vcxf = (float)vcx, vcyf = (float)vcy;
+
+    // ideal rays of all disc pixels (normal-independent), as offsets from the centre ray
+    if (m > 0) {
+        int row = 0;
+        for (int idx = tid; idx < m; idx += NT) {
+            while (idx >= rows->start[row + 1]) row++;
+            const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
+            const double py = cv + (double)rows->jrow[row];
+            double vx, vy;
+            undistort_ray(cam, px, py, vx, vy);
+            ray_set(rays, idx, (float)(vx - vcx), (float)(vy - vcy));
+        }
+    }
+    if (tid == 0) S->stats[14] += (unsigned long long)(clock64() - t_f0);   // prologue: lattice + rays
+    FeatureLocals F;
+    F.cu = cu; F.cv = cv; F.m = m; F.vcxf = vcxf; F.vcyf = vcyf;
+    return F;
+}
+
+// What a pyramid level needs before its first pass, by all threads of the group: window origins (thread 0), the image-1
+// samples of the level (from a staged image-1 window), the image-2 window, the level constants L, and on warp 0 the start of
+// the level's LM (or, modes 1 / 2, the first evaluation point).  Returns the image-1 gate flags of this thread's pixels.
+template <bool ncc>
+__device__ __forceinline__ unsigned level_setup(const NormalsArgs& A, GroupCtl& G, uint8_t* win, float* i1, const int f, const int lvl,
+                                                const FeatureLocals& F, const int tid, const int NT, const int groups, const int g,
+                                                LevelConst& L_out) {
+    const fm3d_cam& cam = A.cam;
+    const int r = A.r;
+    const double cu = F.cu, cv = F.cv;
+    const int m = F.m;
+    RowTable* rows = &G.rows;
+    double* red = G.red;
+    FastShared* S = &G.S;
+    FastPass* PP = &G.PP;
+    uint64_t* bar = &G.bar;
+    const int lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
+    const long long t_l0 = clock64();
+    const fm3d_level lv = A.pyr.lv[lvl];
+    const double scale = 1.0 / (double)(1 << lvl);      // actual_scale_ (:226-241)
+    const double inv_scale = 1.0 / scale;
+    const uint8_t* img1 = A.pyr.base[0] + lv.off;
+    LevelConst L;
+    L.img2 = A.pyr.base[1] + lv.off;
+    L.w = lv.w; L.h = lv.h; L.pitch = lv.pitch;
+    L.win = win; L.ww = (unsigned)A.win_w[lvl];
+    const int wh = A.win_h[lvl];
+    L.cols = (float)lv.w; L.rows = (float)lv.h;     // scale * (cols_l / scale)
+    L.xc = (float)S->xc; L.yc = (float)S->yc;
+    L.c0 = 0.0f;
+
+    // window origins.  Image 2: centred on the projection of P (P lies on every candidate plane).
+    // Image 1: the disc itself, scaled.  TMA needs the box start address 16-byte aligned: x
+    // origins are multiples of 16 pixels.
+    if (tid == 0) {
+        double u2, v2;
+        fm3d_distort_K<double>(S->xc, S->yc, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, cam.fx, cam.fy, cam.cx, cam.cy, u2, v2);
+        double wxc = floor(scale * u2), wyc = floor(scale * v2);
+        if (!(wxc > -1e6 && wxc < 1e6)) wxc = 0;
+        if (!(wyc > -1e6 && wyc < 1e6)) wyc = 0;
+        S->wx0 = (((int)wxc - (int)L.ww / 2 + 8) >> 4) << 4;
+        S->wy0 = (int)wyc - wh / 2;
+        double w1x = floor(scale * (cu - (double)r)) - 1.0, w1y = floor(scale * (cv - (double)r)) - 1.0;
+        if (!(w1x > -1e6 && w1x < 1e6)) w1x = 0;
+        if (!(w1y > -1e6 && w1y < 1e6)) w1y = 0;
+        S->w1x0 = ((int)w1x >> 4) << 4;
+        S->w1y0 = (int)w1y;
+    }
+    gsync(groups, g, NT);  // also: everybody is done with the previous level's window
+    L.wx0 = S->wx0; L.wy0 = S->wy0;
+    const bool by_tma = A.use_tma && A.win_tma[lvl];
+
+    // image-1 intensities of the level (updateImage1PixelsIntensity, :576-589), sampled from the
+    // staged image-1 window; a pixel whose taps leave window or image takes the global path
+    unsigned lvl_flags = 0;
+    {
+        const int w1x0 = S->w1x0, w1y0 = S->w1y0;
+        const bool staged1 = stage_window(A, &A.tmap1[lvl], by_tma, img1, lv, win, (int)L.ww, wh, w1x0, w1y0, bar,
+                                          &S->tma_phase, groups, g, NT, tid);
+        const int x_lo = max(w1x0, 0), x_hi = min(w1x0 + (int)L.ww, lv.w) - 1;   // x0 in [x_lo, x_hi)
+        const int y_lo = max(w1y0, 0), y_hi = min(w1y0 + wh, lv.h) - 1;
+        const int x_cnt = staged1 ? max(x_hi - x_lo, 0) : 0, y_cnt = staged1 ? max(y_hi - y_lo, 0) : 0;
+        int row = 0;
+        double i1_part = 0.0;
+        for (int idx = tid; idx < m; idx += NT) {
+            while (idx >= rows->start[row + 1]) row++;
+            const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
+            const double py = cv + (double)rows->jrow[row];
+            if (!fm3d_pixel_good(px, py, inv_scale, lv.w, lv.h)) lvl_flags |= FLAG_PIX;
+            const float sx = (float)(scale * px), sy = (float)(scale * py);
+            const float fx0 = floorf(sx), fy0 = floorf(sy);
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            float v;
+            if ((unsigned)(x0 - x_lo) < (unsigned)x_cnt && (unsigned)(y0 - y_lo) < (unsigned)y_cnt) {
+                const uint8_t* pw = win + (y0 - w1y0) * (int)L.ww + (x0 - w1x0);
+                v = fm3d_lerp4(fm3d_u8f(pw[0]), fm3d_u8f(pw[L.ww]), fm3d_u8f(pw[1]), fm3d_u8f(pw[L.ww + 1]),
+                               __fsub_rn(sx, fx0), __fsub_rn(sy, fy0));
+            } else {
+                v = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, sx, sy);
+            }
+            i1[idx] = v;
+            i1_part += (double)v;
+        }
+        if (ncc) {
+            // cost_mode NCC: the image-1 samples are kept CENTRED (u = I1 - c0, c0 = their mean rounded to float) together
+            // with sum u and sum u^2; image-2 samples are centred with the same constant before they are summed, so that
+            // the variances below are differences of small numbers' squares (fp64 sums of fp32 products)
+            const double ws = warp_sum(i1_part);
+            if (lane == 0) red[wid * NSUM] = ws;
+            gsync(groups, g, NT);
+            double tot = 0.0;
+            for (int w = 0; w < NW; w++) tot += red[w * NSUM];     // same order in every thread: one value for the group
+            const float c0 = (float)(tot / (double)m);
+            L.c0 = c0;
+            double pu = 0.0, puu = 0.0;
+            for (int idx = tid; idx < m; idx += NT) {
+                const float a = __fsub_rn(i1[idx], c0);
+                i1[idx] = a;
+                pu += (double)a;
+                puu = fma((double)a, (double)a, puu);
+            }
+            const double wu = warp_sum(pu), wuu = warp_sum(puu);
+            gsync(groups, g, NT);                                  // every thread has read the first totals
+            if (lane == 0) { red[wid * NSUM] = wu; red[wid * NSUM + 1] = wuu; }
+            gsync(groups, g, NT);
+            if (tid == 0) {
+                double a = 0.0, b = 0.0;
+                for (int w = 0; w < NW; w++) { a += red[w * NSUM]; b += red[w * NSUM + 1]; }
+                S->ncc_su = a; S->ncc_suu = b;
+            }
+        }
+        gsync(groups, g, NT);   // everybody is done with the image-1 window
+    }
+
+    // image-2 window
+    const bool staged = stage_window(A, &A.tmap[lvl], by_tma, L.img2, lv, win, (int)L.ww, wh, L.wx0, L.wy0, bar,
+                                     &S->tma_phase, groups, g, NT, tid);
+    // taps (x0,y0),(x0+1,y0+1) must lie inside the window and inside the image
+    {
+        int x_lo = max(L.wx0, 0), x_hi = min(L.wx0 + (int)L.ww, lv.w) - 1;  // x0 in [x_lo, x_hi)
+        int y_lo = max(L.wy0, 0), y_hi = min(L.wy0 + wh, lv.h) - 1;
+        L.lx_min = x_lo - L.wx0; L.lx_cnt = staged ? max(x_hi - x_lo, 0) : 0;
+        L.ly_min = y_lo - L.wy0; L.ly_cnt = staged ? max(y_hi - y_lo, 0) : 0;
+    }
+    L.coff = (FLOOR_MAGIC_BITS + (unsigned)L.wy0) * L.ww + FLOOR_MAGIC_BITS + (unsigned)L.wx0;
+    L.amax = L.ww * (unsigned)wh - L.ww - 2u;
+    L.koff = smem_u32(win) - L.coff;
+    L.ahi = smem_u32(win) + L.amax;
+
+    // warp 0: start the LM of this level (optimize(), :247-292)
+    if (wid == 0) {
+        double phi, theta;
+        if (A.mode == 0) {
+            const double* nv = S->normal;
+            theta = atan2(nv[2], sqrt(nv[0] * nv[0] + nv[1] * nv[1]));  // car2sph (tools.cpp:767-771)
+            phi = atan2(nv[1], nv[0]);
+            if (lane == 0) {
+                PP->slow = 0;
+                fm3d_lm2_init(&S->lm, phi, theta, A.eps_lmmin, A.patience);
+                S->where = AT_X_JAC;
+                S->base_valid = 0;
+                S->fuse_hint = 1;
+            }
+            publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
+        } else {
+            if (A.phi_theta) {
+                phi = A.phi_theta[2 * f]; theta = A.phi_theta[2 * f + 1];
+            } else {   // the initial normal of the optimiser: the viewing ray (normaloptimizer.cpp:343)
+                const double* nv = S->normal;
+                theta = atan2(nv[2], sqrt(nv[0] * nv[0] + nv[1] * nv[1]));
+                phi = atan2(nv[1], nv[0]);
+            }
+            if (lane == 0) {
+                PP->slow = 0;
+                S->lm.nfev = 0;
+                S->lm.eps = 1e-5;
+                S->where = AT_XT_PLAIN;
+                S->base_valid = 0;
+                S->cand = 0;
+                S->sweep_c[0] = phi; S->sweep_c[1] = theta;
+                S->best_cost = __longlong_as_double(0x7ff0000000000000LL);
+                S->best_idx = -1;
+            }
+            if (A.mode == 2) {   // first candidate of the grid
+                phi -= 0.5 * (double)(A.sweep_nphi - 1) * A.sweep_dphi;
+                theta -= 0.5 * (double)(A.sweep_ntheta - 1) * A.sweep_dtheta;
+            }
+            publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
+        }
+    }
+    gsync(groups, g, NT);
+
+    if (tid == 0) S->stats[15] += (unsigned long long)(clock64() - t_l0);   // level set-up: window + image-1 samples
+    L_out = L;
+    return lvl_flags;
 }
 
 // RAYS_SMEM / I1_SMEM: where the per-pixel ray offsets (8 B) and image-1 samples (4 B) of the
@@ -785,94 +1235,11 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
         gsync(groups, g, NT);
         const int f = S->feature;
         if (f >= A.n) break;
-        const long long t_f0 = clock64();
+        const FeatureLocals F = feature_prologue(A, G, rays, f, tid, NT, groups, g);
         const double Px = A.xyz[3 * f], Py = A.xyz[3 * f + 1], Pz = A.xyz[3 * f + 2];
-
-        // ------------------------------------------------------------ prologue: disc lattice
-        double cu, cv;
-        fm3d_project(cam, Px, Py, Pz, cu, cv);  // extractPixelsContour(Vec3d) (:376-397)
-        for (int jr = tid; jr < 2 * r + 1; jr += NT) {
-            const int j = jr - r;
-            const double py = cv + (double)j;
-            int cnt = 0, lo = 0;
-            if (!(py < 0 || py >= (double)H) && cu == cu && cv == cv) {
-                const int hw = (int)floor(sqrt((double)(r * r - j * j)));
-                int ilo = -hw, ihi = hw;
-                // keep iff !(px < 0 || px >= W) with px = cu + i evaluated exactly as the reference does
-                if (cu + (double)ilo < 0) {
-                    int g = (int)ceil(-cu);
-                    ilo = g < -hw ? -hw : (g > hw + 1 ? hw + 1 : g);
-                    while (ilo <= hw && (cu + (double)ilo) < 0) ilo++;
-                    while (ilo - 1 >= -hw && !((cu + (double)(ilo - 1)) < 0)) ilo--;
-                }
-                if (cu + (double)ihi >= (double)W) {
-                    int g = (int)ceil((double)W - cu) - 1;
-                    ihi = g > hw ? hw : (g < -hw - 1 ? -hw - 1 : g);
-                    while (ihi >= -hw && (cu + (double)ihi) >= (double)W) ihi--;
-                    while (ihi + 1 <= hw && !((cu + (double)(ihi + 1)) >= (double)W)) ihi++;
-                }
-                cnt = ihi - ilo + 1;
-                if (cnt < 0) cnt = 0;
-                lo = ilo;
-            }
-            rows->start[jr + 1] = cnt;  // counts, prefix-summed below
-            rows->ilo[jr] = (short)lo;
-            rows->jrow[jr] = (short)j;
-        }
-        gsync(groups, g, NT);
-        if (tid == 0) {
-            int acc = 0, first = -1, last = -1;
-            rows->start[0] = 0;
-            for (int jr = 0; jr < 2 * r + 1; jr++) {
-                const int c = rows->start[jr + 1];
-                if (c > 0) { if (first < 0) first = jr; last = jr; }
-                acc += c;
-                rows->start[jr + 1] = acc;
-            }
-            rows->nrows = 2 * r + 1;
-            S->first_row = first; S->last_row = last;
-            S->m = acc;
-            S->status = acc > 0 ? FM3D_FEAT_OK : FM3D_FEAT_NO_PIXELS;
-            // a non-finite centre passes every `p < 0 || p >= size` test of the reference's lattice loop,
-            // the feature then dies in its first evaluation with a NaN plane point
-            if (cu != cu || cv != cv) S->status = FM3D_FEAT_ABORT_NAN;
-            S->alive = acc > 0;
-            S->npenalty = 0;
-            for (int k = 0; k < 16; k++) S->stats[k] = 0;
-            S->P[0] = Px; S->P[1] = Py; S->P[2] = Pz;
-            const double nrm = sqrt(Px * Px + Py * Py + Pz * Pz);
-            S->normal[0] = Px / nrm; S->normal[1] = Py / nrm; S->normal[2] = Pz / nrm;  // (:343)
-            if (A.nfev && A.mode == 0) for (int l = 0; l <= levels; l++) A.nfev[(size_t)f * (levels + 1) + l] = 0;
-            // centre ray, and the camera-2 projection of P: P lies on every candidate plane, so this
-            // is where the centre of the disc lands whatever the normal (reference point of the
-            // offset form)
-            // reference ray of the offsets: the ray through P itself (not the 5-iteration undistort of the centre pixel, which
-            // misses it by the residual of that iteration; every disc pixel still gets its own 5-iteration ray below)
-            S->vc[0] = Px / Pz; S->vc[1] = Py / Pz;
-            const double X2 = cam.R[0] * Px + cam.R[1] * Py + cam.R[2] * Pz + cam.t[0];
-            const double Y2 = cam.R[3] * Px + cam.R[4] * Py + cam.R[5] * Pz + cam.t[1];
-            const double Z2 = cam.R[6] * Px + cam.R[7] * Py + cam.R[8] * Pz + cam.t[2];
-            const double iz = Z2 != 0.0 ? 1.0 / Z2 : 1.0;
-            S->xc = X2 * iz; S->yc = Y2 * iz;
-        }
-        gsync(groups, g, NT);
-        const int m = S->m;
-        if (A.m_out && tid == 0) A.m_out[f] = m;
-        const double vcx = S->vc[0], vcy = S->vc[1];
-        const float vcxf = (float)vcx, vcyf = (float)vcy;
-
-        // ideal rays of all disc pixels (normal-independent), as offsets from the centre ray
-        if (m > 0) {
-            int row = 0;
-            for (int idx = tid; idx < m; idx += NT) {
-                while (idx >= rows->start[row + 1]) row++;
-                const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
-                const double py = cv + (double)rows->jrow[row];
-                double vx, vy;
-                undistort_ray(cam, px, py, vx, vy);
-                ray_set(rays, idx, (float)(vx - vcx), (float)(vy - vcy));
-            }
-        }
+        const double cu = F.cu, cv = F.cv;
+        const int m = F.m;
+        const float vcxf = F.vcxf, vcyf = F.vcyf;
         // boundary lattice: both ends of every row, and the whole first and last row
         const int nrows = 2 * r + 1;
         const int first_row = S->first_row, last_row = S->last_row;
@@ -884,164 +1251,9 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
         const int lvl_hi = A.mode == 0 ? levels : A.eval_level;
         const int lvl_lo = A.mode == 0 ? 0 : A.eval_level;
         bool alive = m > 0;
-        if (tid == 0) S->stats[14] += (unsigned long long)(clock64() - t_f0);   // prologue: lattice + rays
         for (int lvl = lvl_hi; lvl >= lvl_lo && alive; lvl--) {
-            const long long t_l0 = clock64();
-            const fm3d_level lv = A.pyr.lv[lvl];
-            const double scale = 1.0 / (double)(1 << lvl);      // actual_scale_ (:226-241)
-            const double inv_scale = 1.0 / scale;
-            const uint8_t* img1 = A.pyr.base[0] + lv.off;
             LevelConst L;
-            L.img2 = A.pyr.base[1] + lv.off;
-            L.w = lv.w; L.h = lv.h; L.pitch = lv.pitch;
-            L.win = win; L.ww = (unsigned)A.win_w[lvl];
-            const int wh = A.win_h[lvl];
-            L.cols = (float)lv.w; L.rows = (float)lv.h;     // scale * (cols_l / scale)
-            L.xc = (float)S->xc; L.yc = (float)S->yc;
-            L.c0 = 0.0f;
-
-            // window origins.  Image 2: centred on the projection of P (P lies on every candidate plane).
-            // Image 1: the disc itself, scaled.  TMA needs the box start address 16-byte aligned: x
-            // origins are multiples of 16 pixels.
-            if (tid == 0) {
-                double u2, v2;
-                fm3d_distort_K<double>(S->xc, S->yc, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, cam.fx, cam.fy, cam.cx, cam.cy, u2, v2);
-                double wxc = floor(scale * u2), wyc = floor(scale * v2);
-                if (!(wxc > -1e6 && wxc < 1e6)) wxc = 0;
-                if (!(wyc > -1e6 && wyc < 1e6)) wyc = 0;
-                S->wx0 = (((int)wxc - (int)L.ww / 2 + 8) >> 4) << 4;
-                S->wy0 = (int)wyc - wh / 2;
-                double w1x = floor(scale * (cu - (double)r)) - 1.0, w1y = floor(scale * (cv - (double)r)) - 1.0;
-                if (!(w1x > -1e6 && w1x < 1e6)) w1x = 0;
-                if (!(w1y > -1e6 && w1y < 1e6)) w1y = 0;
-                S->w1x0 = ((int)w1x >> 4) << 4;
-                S->w1y0 = (int)w1y;
-            }
-            gsync(groups, g, NT);  // also: everybody is done with the previous level's window
-            L.wx0 = S->wx0; L.wy0 = S->wy0;
-            const bool by_tma = A.use_tma && A.win_tma[lvl];
-
-            // image-1 intensities of the level (updateImage1PixelsIntensity, :576-589), sampled from the
-            // staged image-1 window; a pixel whose taps leave window or image takes the global path
-            unsigned lvl_flags = 0;
-            {
-                const int w1x0 = S->w1x0, w1y0 = S->w1y0;
-                const bool staged1 = stage_window(A, &A.tmap1[lvl], by_tma, img1, lv, win, (int)L.ww, wh, w1x0, w1y0, bar,
-                                                  &S->tma_phase, groups, g, NT, tid);
-                const int x_lo = max(w1x0, 0), x_hi = min(w1x0 + (int)L.ww, lv.w) - 1;   // x0 in [x_lo, x_hi)
-                const int y_lo = max(w1y0, 0), y_hi = min(w1y0 + wh, lv.h) - 1;
-                const int x_cnt = staged1 ? max(x_hi - x_lo, 0) : 0, y_cnt = staged1 ? max(y_hi - y_lo, 0) : 0;
-                int row = 0;
-                double i1_part = 0.0;
-                for (int idx = tid; idx < m; idx += NT) {
-                    while (idx >= rows->start[row + 1]) row++;
-                    const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
-                    const double py = cv + (double)rows->jrow[row];
-                    if (!fm3d_pixel_good(px, py, inv_scale, lv.w, lv.h)) lvl_flags |= FLAG_PIX;
-                    const float sx = (float)(scale * px), sy = (float)(scale * py);
-                    const float fx0 = floorf(sx), fy0 = floorf(sy);
-                    const int x0 = (int)fx0, y0 = (int)fy0;
-                    float v;
-                    if ((unsigned)(x0 - x_lo) < (unsigned)x_cnt && (unsigned)(y0 - y_lo) < (unsigned)y_cnt) {
-                        const uint8_t* pw = win + (y0 - w1y0) * (int)L.ww + (x0 - w1x0);
-                        v = fm3d_lerp4(fm3d_u8f(pw[0]), fm3d_u8f(pw[L.ww]), fm3d_u8f(pw[1]), fm3d_u8f(pw[L.ww + 1]),
-                                       __fsub_rn(sx, fx0), __fsub_rn(sy, fy0));
-                    } else {
-                        v = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, sx, sy);
-                    }
-                    i1[idx] = v;
-                    i1_part += (double)v;
-                }
-                if (ncc) {
-                    // cost_mode NCC: the image-1 samples are kept CENTRED (u = I1 - c0, c0 = their mean rounded to float) together
-                    // with sum u and sum u^2; image-2 samples are centred with the same constant before they are summed, so that
-                    // the variances below are differences of small numbers' squares (fp64 sums of fp32 products)
-                    const double ws = warp_sum(i1_part);
-                    if (lane == 0) red[wid * NSUM] = ws;
-                    gsync(groups, g, NT);
-                    double tot = 0.0;
-                    for (int w = 0; w < NW; w++) tot += red[w * NSUM];     // same order in every thread: one value for the group
-                    const float c0 = (float)(tot / (double)m);
-                    L.c0 = c0;
-                    double pu = 0.0, puu = 0.0;
-                    for (int idx = tid; idx < m; idx += NT) {
-                        const float a = __fsub_rn(i1[idx], c0);
-                        i1[idx] = a;
-                        pu += (double)a;
-                        puu = fma((double)a, (double)a, puu);
-                    }
-                    const double wu = warp_sum(pu), wuu = warp_sum(puu);
-                    gsync(groups, g, NT);                                  // every thread has read the first totals
-                    if (lane == 0) { red[wid * NSUM] = wu; red[wid * NSUM + 1] = wuu; }
-                    gsync(groups, g, NT);
-                    if (tid == 0) {
-                        double a = 0.0, b = 0.0;
-                        for (int w = 0; w < NW; w++) { a += red[w * NSUM]; b += red[w * NSUM + 1]; }
-                        S->ncc_su = a; S->ncc_suu = b;
-                    }
-                }
-                gsync(groups, g, NT);   // everybody is done with the image-1 window
-            }
-
-            // image-2 window
-            const bool staged = stage_window(A, &A.tmap[lvl], by_tma, L.img2, lv, win, (int)L.ww, wh, L.wx0, L.wy0, bar,
-                                             &S->tma_phase, groups, g, NT, tid);
-            // taps (x0,y0),(x0+1,y0+1) must lie inside the window and inside the image
-            {
-                int x_lo = max(L.wx0, 0), x_hi = min(L.wx0 + (int)L.ww, lv.w) - 1;  // x0 in [x_lo, x_hi)
-                int y_lo = max(L.wy0, 0), y_hi = min(L.wy0 + wh, lv.h) - 1;
-                L.lx_min = x_lo - L.wx0; L.lx_cnt = staged ? max(x_hi - x_lo, 0) : 0;
-                L.ly_min = y_lo - L.wy0; L.ly_cnt = staged ? max(y_hi - y_lo, 0) : 0;
-            }
-            L.coff = (FLOOR_MAGIC_BITS + (unsigned)L.wy0) * L.ww + FLOOR_MAGIC_BITS + (unsigned)L.wx0;
-            L.amax = L.ww * (unsigned)wh - L.ww - 2u;
-            L.koff = smem_u32(win) - L.coff;
-            L.ahi = smem_u32(win) + L.amax;
-
-            // warp 0: start the LM of this level (optimize(), :247-292)
-            if (wid == 0) {
-                double phi, theta;
-                if (A.mode == 0) {
-                    const double* nv = S->normal;
-                    theta = atan2(nv[2], sqrt(nv[0] * nv[0] + nv[1] * nv[1]));  // car2sph (tools.cpp:767-771)
-                    phi = atan2(nv[1], nv[0]);
-                    if (lane == 0) {
-                        PP->slow = 0;
-                        fm3d_lm2_init(&S->lm, phi, theta, A.eps_lmmin, A.patience);
-                        S->where = AT_X_JAC;
-                        S->base_valid = 0;
-                        S->fuse_hint = 1;
-                    }
-                    publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
-                } else {
-                    if (A.phi_theta) {
-                        phi = A.phi_theta[2 * f]; theta = A.phi_theta[2 * f + 1];
-                    } else {   // the initial normal of the optimiser: the viewing ray (normaloptimizer.cpp:343)
-                        const double* nv = S->normal;
-                        theta = atan2(nv[2], sqrt(nv[0] * nv[0] + nv[1] * nv[1]));
-                        phi = atan2(nv[1], nv[0]);
-                    }
-                    if (lane == 0) {
-                        PP->slow = 0;
-                        S->lm.nfev = 0;
-                        S->lm.eps = 1e-5;
-                        S->where = AT_XT_PLAIN;
-                        S->base_valid = 0;
-                        S->cand = 0;
-                        S->sweep_c[0] = phi; S->sweep_c[1] = theta;
-                        S->best_cost = __longlong_as_double(0x7ff0000000000000LL);
-                        S->best_idx = -1;
-                    }
-                    if (A.mode == 2) {   // first candidate of the grid
-                        phi -= 0.5 * (double)(A.sweep_nphi - 1) * A.sweep_dphi;
-                        theta -= 0.5 * (double)(A.sweep_ntheta - 1) * A.sweep_dtheta;
-                    }
-                    publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
-                }
-            }
-            gsync(groups, g, NT);
-
-            if (tid == 0) S->stats[15] += (unsigned long long)(clock64() - t_l0);   // level set-up: window + image-1 samples
+            unsigned lvl_flags = level_setup<ncc>(A, G, win, i1, f, lvl, F, tid, NT, groups, g, L);
             // -------------------------------------------------------- mode 2: the candidate grid in batches
             if (A.mode == 2 && A.sweep_batch > 1) {
                 const int K = A.sweep_nphi * A.sweep_ntheta;
@@ -1225,154 +1437,7 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
                 gsync(groups, g, NT);
                 const long long t_b = clock64();
 
-                if (wid == 0) {
-                    double s[NSUM];
-                    unsigned any_flags = lane < NW ? wflags[lane] : 0u;
-                    {
-                        const int ns = ncc ? (P.kind == PASS_JAC ? NSUM : 3) : NSUM_SSD;
-#pragma unroll
-                        for (int k = 0; k < NSUM; k++) {
-                            double v = (lane < NW && k < ns) ? red[lane * NSUM + k] : 0.0;
-                            if (k < ns) {
-#pragma unroll
-                                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                            }
-                            s[k] = v;
-                        }
-                        if (P.kind == PASS_JAC) jacobian_sums_from_moments(s, S->sg, ncc);
-                        if (ncc) ncc_sums_to_normal_equations(s, S->ncc_su, S->ncc_suu, m, P.kind == PASS_JAC);
-                    }
-                    any_flags = __reduce_or_sync(0xffffffffu, any_flags);
-                    const long long t_r = clock64();
-                    long long t_lm = 0;
-                    // `memo`: the result in s[0] was not evaluated but taken from the base point: the
-                    // proposed trial point rounds to the same fp32 homography coefficients as the
-                    // current iterate, so the pass would return the iterate's sum bit for bit.  Deep
-                    // in lmfit's tail (steps below 1e-8 rad, tolerances of 30 eps) this is what every
-                    // trial does; those trials are answered here without a pass.
-                    bool memo = false;
-                    bool slow_pass = P.slow != 0;
-                    int pass_kind = P.kind;
-                    for (;;) {
-                        int next_kind = PASS_STOP;          // what lane 0 asks the warp to publish
-                        int take_base = 0;                  // PP->h[0] are the coefficients of the (new) iterate
-                        double next_phi = 0.0, next_theta = 0.0;
-                        const long long t_l0 = clock64();
-                        if (lane == 0) {
-                            fm3d_lm2& lm = S->lm;
-                            if (!memo) {   // executed work (fm3d_get_normals_stats)
-                                const int slot = pass_kind == PASS_VALUE ? 0 : (S->where == AT_X_JAC ? 1 : 2);
-                                S->stats[slot]++;
-                                if (slow_pass) S->stats[4]++;
-                                S->stats[pass_kind == PASS_VALUE ? 5 : 6] += (unsigned long long)m;
-                            } else {
-                                S->stats[13]++;
-                            }
-                            const unsigned fl = memo ? 0u : any_flags;
-                            if ((fl & FLAG_WINDOW) && !(fl & 7) && !slow_pass) {
-                                PP->slow = 1;               // same pass again, taps from global memory
-                                next_kind = -1;
-                            } else if (A.mode == 2) {
-                                // dense candidate sweep: cost of this candidate (NaN if it fails a gate), next one
-                                const int K = A.sweep_nphi * A.sweep_ntheta, c = S->cand;
-                                const bool bad = (fl & 7) || s[0] != s[0];
-                                const double cval = bad ? __longlong_as_double(0x7ff8000000000000LL) : S->w[0] * S->w[0] * s[0];
-                                if (A.cost) A.cost[(size_t)f * K + c] = cval;
-                                if (!bad && cval < S->best_cost) { S->best_cost = cval; S->best_idx = c; }
-                                if (c + 1 < K) {
-                                    S->cand = c + 1;
-                                    const int ip = (c + 1) / A.sweep_ntheta, it = (c + 1) - ip * A.sweep_ntheta;
-                                    next_kind = PASS_VALUE;
-                                    next_phi = S->sweep_c[0] + ((double)ip - 0.5 * (double)(A.sweep_nphi - 1)) * A.sweep_dphi;
-                                    next_theta = S->sweep_c[1] + ((double)it - 0.5 * (double)(A.sweep_ntheta - 1)) * A.sweep_dtheta;
-                                } else {
-                                    PP->kind = PASS_STOP;
-                                }
-                            } else if ((fl & 7) || s[0] != s[0]) {
-                                // all bounding-box / NaN tests of an evaluation precede its pixel tests
-                                S->status = ((fl & FLAG_NAN) || !(fl & 7)) ? FM3D_FEAT_ABORT_NAN
-                                          : (fl & FLAG_BBOX) ? FM3D_FEAT_ABORT_BBOX : FM3D_FEAT_ABORT_PIXEL;
-                                S->alive = 0;
-                                PP->kind = PASS_STOP;
-                            } else if (A.mode != 0) {
-                                A.cost[f] = S->w[0] * S->w[0] * s[0];
-                                PP->kind = PASS_STOP;
-                            } else {
-                                const int where = S->where;
-                                bool first_trial = false;   // the next trial opens an LM iteration
-                                int cmd;
-                                if (where == AT_X_JAC) {
-                                    if (lm.first && S->w[0] != 1.0) S->npenalty++;
-                                    cmd = consume_jacobian(S, lm, s, A.penalty_mode);
-                                    first_trial = true;
-                                    S->s0_base = s[0];      // sum and coefficients of the iterate
-                                    take_base = 1;
-                                } else {
-                                    if (S->w[0] != 1.0) S->npenalty++;
-                                    const int iter_before = lm.iter;
-                                    cmd = fm3d_lm2_after_trial(&lm, S->w[0] * S->w[0] * s[0]);
-                                    const bool accepted = lm.iter != iter_before;
-                                    if (S->trial_is_first) S->fuse_hint = accepted ? 1 : 0;
-                                    if (!memo && accepted) {   // new iterate
-                                        S->s0_base = s[0];
-                                        take_base = 1;
-                                    }
-                                    // accepted (x == xt now) and the Jacobian came with the trial
-                                    if (cmd == FM3D_LM_CMD_JAC && where == AT_XT_FUSED) {
-                                        S->stats[3]++;
-                                        cmd = consume_jacobian(S, lm, s, A.penalty_mode);
-                                        first_trial = true;
-                                    }
-                                }
-                                if (cmd == FM3D_LM_CMD_JAC) {
-                                    S->where = AT_X_JAC;
-                                    next_kind = PASS_JAC; next_phi = lm.x[0]; next_theta = lm.x[1];
-                                } else if (cmd == FM3D_LM_CMD_TRIAL) {
-                                    // first trial of an iteration: evaluate its Jacobian along with it;
-                                    // re-trials after a rejection are value-only
-                                    const bool fuse = first_trial && (A.fuse_trials == 1 || (A.fuse_trials == 2 && S->fuse_hint));
-                                    S->trial_is_first = first_trial ? 1 : 0;
-                                    S->where = fuse ? AT_XT_FUSED : AT_XT_PLAIN;
-                                    next_kind = fuse ? PASS_JAC : PASS_VALUE; next_phi = lm.xt[0]; next_theta = lm.xt[1];
-                                } else {
-                                    PP->kind = PASS_STOP;   // FM3D_LM_CMD_DONE
-                                }
-                            }
-                        }
-                        t_lm += clock64() - t_l0;
-                        next_kind = __shfl_sync(0xffffffffu, next_kind, 0);
-                        if (next_kind <= PASS_STOP) break;      // stop, or repeat the same pass (-1)
-                        take_base = __shfl_sync(0xffffffffu, take_base, 0);
-                        next_phi = __shfl_sync(0xffffffffu, next_phi, 0);
-                        next_theta = __shfl_sync(0xffffffffu, next_theta, 0);
-                        // remember the coefficients of the iterate before they are overwritten
-                        if (take_base) {
-                            if (lane < 9) S->hbase[lane] = PP->h[lane];
-                            if (lane == 0) S->base_valid = 1;
-                        }
-                        __syncwarp();
-                        publish_pass(PP, S, cam, next_phi, next_theta, next_kind, A.penalty_mode, S->lm.eps, lane);
-                        __syncwarp();
-                        if (PP->kind == PASS_STOP) break;       // NaN normal
-                        // would this pass return the iterate's sum?  (trial points only)
-                        bool same = S->where != AT_X_JAC && S->base_valid != 0 && A.memo_trials;
-                        if (lane < 9) same = same && (PP->h[lane] == S->hbase[lane]);
-                        same = __all_sync(0xffffffffu, same);
-                        if (!same) break;                       // run the pass
-                        memo = true;
-                        s[0] = S->s0_base;
-                        if (lane == 0) { S->where = AT_XT_PLAIN; }
-                        __syncwarp();
-                    }
-                    if (lane == 0) {
-                        const long long t_c = clock64();
-                        S->stats[8] += (unsigned long long)(t_b0 - t_a);   // thread 0: pixel work of the pass
-                        S->stats[9] += (unsigned long long)(t_b - t_b0);   // thread 0: wait at the barrier
-                        S->stats[10] += (unsigned long long)(t_c - t_b);   // reduction + LM + publish
-                        S->stats[11] += (unsigned long long)t_lm;          //   of which LM algebra
-                        S->stats[12] += (unsigned long long)(t_c - t_r - t_lm);   //   of which sincos + homographies
-                    }
-                }
+                if (wid == 0) lm_advance<ncc>(A, G, P, m, f, NW, lane, t_a, t_b0, t_b);
                 gsync(groups, g, NT);
             }
             alive = S->alive != 0;
@@ -1416,6 +1481,257 @@ normals_fast_kernel(const __grid_constant__ NormalsArgs A) {
             }
         }
         gsync(groups, g, NT);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Two features per group of eight warps, taking turns ("ping-pong"): the serial LM step of one feature runs on its LM
+// warp while the other seven warps evaluate the pass of the partner feature, so the step between two passes leaves the
+// critical path (in normals_fast_kernel the four warps of a group wait for it: a quarter of all warp time, ncu r02l).
+//   * a CTA has two super-groups of eight warps; super-group sg owns slots 2 sg and 2 sg + 1 (window, scratch, LM state:
+//     what a group of normals_fast_kernel owns);
+//   * slot s is served by seven warps: all but the LM warp of the other slot.  With the warps relabelled wr = w xor lm_s the
+//     slot's LM warp is wr = 0 and the excluded warp wr = lm_0 xor lm_1 in both slots, so pixel partition, summation order
+//     and therefore the results are the same in both slots (and a feature stays in its slot);
+//   * a warp serves slot 0, then slot 1, then slot 0 ...; a turn is one STEP of the slot: fetch + prologue + level set-up,
+//     level set-up, or one pass.  A turn starts with the slot's barrier (224 threads): it opens when the slot's LM warp has
+//     published the next pass.  After a pass the six shared warps only ARRIVE at the slot's second barrier and move on to
+//     the other slot; the LM warp waits there for the sums and advances the LM meanwhile.
+// Mode 0 (optimise) with the four-window layout only; everything else runs in normals_fast_kernel.
+enum { STEP_FETCH = 0, STEP_LEVEL = 1, STEP_PASS = 2 };
+
+__device__ __forceinline__ void nbar_arrive(int id, int nt) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nt) : "memory"); }
+__device__ __forceinline__ void nbar_sync(int id, int nt) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nt) : "memory"); }
+
+__device__ __forceinline__ bool nbar_red_or(int id, int nt, bool pred) {
+    int out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, %2, %3, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(out) : "r"(pred ? 1 : 0), "r"(id), "r"(nt) : "memory");
+    return out != 0;
+}
+// The slot's LM warp has decided the slot's next step (everything it wrote before is visible to who sees the new count).
+__device__ __forceinline__ void slot_ready(GroupCtl& G, const int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        *(volatile int*)&G.ready_gen = G.ready_gen + 1;
+    }
+}
+// End of a feature, on its LM warp: counters, status, normal (the epilogue of normals_fast_kernel).
+__device__ __forceinline__ void finish_feature(const NormalsArgs& A, FastShared* S, const int f, const int lane) {
+    if (lane < 16 && A.stats) {
+        const unsigned long long v = lane == 7 ? 1ull : S->stats[lane];
+        if (v) atomicAdd(A.stats + lane, v);
+    }
+    if (lane == 0) {
+        const int st = S->status;
+        A.status[f] = st;
+        if (st == FM3D_FEAT_OK) {
+            A.normals[3 * f] = S->normal[0]; A.normals[3 * f + 1] = S->normal[1]; A.normals[3 * f + 2] = S->normal[2];
+        } else {
+            const double Px = S->P[0], Py = S->P[1], Pz = S->P[2];
+            const double nrm = sqrt(Px * Px + Py * Py + Pz * Pz);
+            A.normals[3 * f] = Px / nrm; A.normals[3 * f + 1] = Py / nrm; A.normals[3 * f + 2] = Pz / nrm;
+            if (A.cost) A.cost[f] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if (A.npenalty) A.npenalty[f] = S->npenalty;
+    }
+}
+
+template <bool NCC_COST>
+__global__ void __launch_bounds__(FAST_NT, 1)
+normals_pp_kernel(const __grid_constant__ NormalsArgs A) {
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    __shared__ GroupCtl ctl[MAX_GROUPS];
+    constexpr bool ncc = NCC_COST;
+    constexpr int NT = 224, NW = 7;             // threads / warps that serve a slot
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sg = warp >> 3, w8 = warp & 7;
+    // LM warps of the two slots of a super-group: warps 0, 5 / 10, 15 of the CTA, one per scheduler (warp % 4); the labels
+    // wr = w8 xor lm differ by lm0 xor lm1 = 5 in both slots
+    const int lm0 = 2 * sg, lm1 = lm0 ^ 5;
+    const fm3d_cam& cam = A.cam;
+    const int r = A.r, levels = A.pyr.levels;
+    const float cmax = (float)(int)(2 * cam.zmax);  // int cMax = 2*z_threshold_max_ (:648)
+    const int nrows = 2 * r + 1;
+
+    if (threadIdx.x < MAX_GROUPS) {
+        GroupCtl& G0 = ctl[threadIdx.x];
+        mbar_init(&G0.bar, 1);
+        fence_mbar_init();
+        G0.S.tma_phase = 0;
+        G0.kind = STEP_FETCH;
+        G0.ready_gen = 1;
+    }
+    __syncthreads();
+
+    // Turn order.  The LM warp of a slot serves its own slot only.  The six shared warps serve whichever slot is ready,
+    // preferring the one they did not serve last: a slot is ready when its LM warp has made more steps ready (ready_gen) than
+    // the shared warps have started (served).  They agree on it with a barrier reduction over their 192 threads (ready_gen
+    // only grows, so "one of us saw it ready" is a safe verdict for all).
+    bool done0 = false, done1 = false;
+    int served0 = 0, served1 = 0, last = 1;
+    const int BAR_TURN = 1 + 2 * MAX_GROUPS + sg;   // named barrier 9 + sg
+    for (;;) {
+        int s;
+        if (w8 == lm0) { if (done0) break; s = 0; }
+        else if (w8 == lm1) { if (done1) break; s = 1; }
+        else {
+            if (done0 && done1) break;
+            const int pref = done0 ? 1 : (done1 ? 0 : 1 - last);
+            const bool other_alive = !(pref ? done0 : done1);
+            for (;;) {
+                const volatile int* gp = &ctl[2 * sg + pref].ready_gen;
+                if (nbar_red_or(BAR_TURN, 192, *gp > (pref ? served1 : served0))) { s = pref; break; }
+                if (other_alive) {
+                    const volatile int* go = &ctl[2 * sg + 1 - pref].ready_gen;
+                    if (nbar_red_or(BAR_TURN, 192, *go > (pref ? served0 : served1))) { s = 1 - pref; break; }
+                }
+            }
+            last = s;
+        }
+        {
+            if (s == 0) served0++; else served1++;
+            const int wr = w8 ^ (s ? lm1 : lm0);
+            const int sl = 2 * sg + s;
+            GroupCtl& G = ctl[sl];
+            RowTable* rows = &G.rows;
+            double* red = G.red;
+            unsigned* wflags = G.wflags;
+            FastShared* S = &G.S;
+            FastPass* PP = &G.PP;
+            uint8_t* win = smem_all + (size_t)sl * A.group_smem;
+            const size_t slot = (size_t)blockIdx.x * MAX_GROUPS + sl;
+            float2* rays = A.rays_g + slot * A.mcap;
+            float* i1 = A.i1_g + slot * A.mcap;
+            const int rank = wr < 5 ? wr : wr - 1;      // 0 (LM warp) .. 6
+            const int tid = rank * 32 + lane;
+            const int BAR = sl;                          // gsync(2, BAR, NT): named barrier 1 + sl
+            const int BAR_SUMS = 1 + MAX_GROUPS + sl;    // named barrier 5 + sl
+
+            gsync(2, BAR, NT);                           // the slot's LM warp has decided what comes next
+            int kind = G.kind;
+            if (kind == STEP_FETCH) {
+                if (tid == 0) S->feature = atomicAdd(A.work_counter, 1);
+                gsync(2, BAR, NT);
+                const int f = S->feature;
+                if (f >= A.n) {                          // queue empty: the slot retires (all seven warps read the same value)
+                    if (s == 0) done0 = true; else done1 = true;
+                    continue;
+                }
+                const FeatureLocals F = feature_prologue(A, G, rays, f, tid, NT, 2, BAR);
+                if (tid == 0) { G.Fsave = F; G.lvl = levels; }
+                if (F.m <= 0) {                          // no pixels: nothing to optimise
+                    if (rank == 0) { finish_feature(A, S, f, lane); slot_ready(G, lane); }
+                    continue;                            // G.kind stays STEP_FETCH
+                }
+                kind = STEP_LEVEL;
+                gsync(2, BAR, NT);
+            }
+            const int f = S->feature;
+            if (kind == STEP_LEVEL) {
+                const FeatureLocals F = G.Fsave;
+                const int lvl = G.lvl;
+                if (tid == 0) G.lvl_flags = 0u;
+                LevelConst L;
+                const unsigned lf = level_setup<ncc>(A, G, win, i1, f, lvl, F, tid, NT, 2, BAR, L);   // ends with the slot's barrier
+                if (lf) atomicOr(&G.lvl_flags, lf);
+                if (tid == 0) { G.Lsave = L; G.kind = STEP_PASS; }
+                if (rank == 0) slot_ready(G, lane);
+                continue;
+            }
+
+            // ---------------------------------------------------------------- one pass
+            const FeatureLocals F = G.Fsave;
+            const LevelConst L = G.Lsave;
+            const int lvl = G.lvl, m = F.m;
+            const FastPass P = *PP;
+            const long long t_a = clock64();
+            const int first_row = S->first_row, last_row = S->last_row;
+            const int n_first = rows->start[first_row + 1] - rows->start[first_row];
+            const int n_last = rows->start[last_row + 1] - rows->start[last_row];
+            const int n_boundary = 2 * nrows + n_first + n_last;
+            unsigned flags = 0u;
+            if (tid == 0) { flags = G.lvl_flags; G.lvl_flags = 0u; }
+            for (int k = tid; k < n_boundary; k += NT) {
+                int idx;
+                if (k < 2 * nrows) {
+                    const int row = k >> 1;
+                    const int s0 = rows->start[row], s1 = rows->start[row + 1];
+                    if (s1 <= s0) continue;
+                    idx = (k & 1) ? s1 - 1 : s0;
+                } else if (k < 2 * nrows + n_first) {
+                    idx = rows->start[first_row] + (k - 2 * nrows);
+                } else {
+                    idx = rows->start[last_row] + (k - 2 * nrows - n_first);
+                }
+                flags |= boundary_flags(A.fc, lvl, P, L, F.vcxf, F.vcyf, cmax, ray_at(rays, idx));
+            }
+            Acc acc;
+            acc.s0 = acc.t1 = acc.t2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) acc.f[k] = 0.0f;
+            if (P.kind == PASS_JAC) {
+                if (!P.slow) run_pixels<true, false, true, ncc>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+                else run_pixels<true, true, false, ncc>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+            } else {
+                if (!P.slow) run_pixels<false, false, true, ncc>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+                else run_pixels<false, true, false, ncc>(A.fc, lvl, P, L, rays, i1, m, tid, NT, acc);
+            }
+            {
+                double* rw = red + rank * NSUM;
+                const double a0 = warp_sum(acc.s0);
+                if (lane == 0) rw[0] = a0;
+                if (ncc) {
+                    const double a1 = warp_sum(acc.t1), a2 = warp_sum(acc.t2);
+                    if (lane == 0) { rw[1] = a1; rw[2] = a2; }
+                }
+                const int nj = P.kind == PASS_JAC ? (ncc ? 9 : 5) : 0, jo = ncc ? 3 : 1;
+                for (int k = 0; k < 9; k++) {
+                    if (k >= nj) break;
+                    const double a = warp_sum((double)acc.f[k]);
+                    if (lane == 0) rw[jo + k] = a;
+                }
+                if (lane == 0 && P.kind != PASS_JAC && !ncc) { rw[1] = rw[2] = rw[3] = rw[4] = rw[5] = 0.0; }
+            }
+            flags = __reduce_or_sync(0xffffffffu, flags);
+            if (lane == 0) wflags[rank] = flags;
+            if (rank != 0) {
+                nbar_arrive(BAR_SUMS, NT);               // on to the other slot
+                continue;
+            }
+            // the slot's LM warp: sums -> LM -> next pass, while the other warps serve the partner slot
+            const long long t_b0 = clock64();
+            nbar_sync(BAR_SUMS, NT);
+            const long long t_b = clock64();
+            lm_advance<ncc>(A, G, P, m, f, NW, lane, t_a, t_b0, t_b);
+            __syncwarp();
+            if (PP->kind == PASS_STOP) {                 // level finished, or the feature was dropped
+                const bool alive = S->alive != 0;
+                if (lane == 0) {
+                    const fm3d_lm2& lm = S->lm;
+                    if (alive) {                         // sph2car of the solution (:289)
+                        S->normal[0] = cos(lm.x[1]) * cos(lm.x[0]);
+                        S->normal[1] = cos(lm.x[1]) * sin(lm.x[0]);
+                        S->normal[2] = sin(lm.x[1]);
+                        if (A.cost) A.cost[f] = lm.ff;
+                    }
+                    if (A.nfev) A.nfev[(size_t)f * (levels + 1) + lvl] = lm.nfev;
+                }
+                __syncwarp();
+                if (alive && lvl > 0) {
+                    if (lane == 0) { G.lvl = lvl - 1; G.kind = STEP_LEVEL; }
+                } else {
+                    finish_feature(A, S, f, lane);
+                    if (lane == 0) G.kind = STEP_FETCH;
+                }
+            }
+            slot_ready(G, lane);
+        }
     }
 }
 
@@ -1514,6 +1830,7 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         }
     }
     const size_t smem = group_smem * lay.groups;
+    const bool two_slot = ctx->opt_normals_pingpong && lay.groups == 4 && !lay.rays_smem && !lay.i1_smem && A.mode == 0 && nt == FAST_NT;
 
     auto launch = [&](auto kernel) -> int {
         FM3D_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1542,6 +1859,11 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
         FM3D_LAUNCH_CHECK(ctx);
         return FM3D_OK;
     };
+    // four windows, rays and image-1 samples in the scratch, mode 0: two features per eight warps taking turns
+    if (two_slot) {
+        if (A.cost_mode == FM3D_COST_NCC) return launch(normals_pp_kernel<true>);
+        return launch(normals_pp_kernel<false>);
+    }
     if (A.cost_mode == FM3D_COST_NCC) {
         if (lay.rays_smem) return launch(normals_fast_kernel<true, true, true>);
         if (lay.i1_smem) return launch(normals_fast_kernel<false, true, true>);

@@ -36,7 +36,7 @@ for pen in (1, 0):
         if ref is None and cfg.get("normals_fast", 1) == 1: ref = (nf.copy(), nr.copy())
         same = None if ref is None else (bool((nf == ref[0]).all()), float(angle_deg(nr, ref[1]).max()))
         passes = st.get("passes_value", 0) + st.get("passes_jacobian", 0) + st.get("passes_fused", 0)
-        cyc = {k: round(st[k] / max(passes, 1)) for k in ("cycles_pixels", "cycles_serial", "cycles_lm", "cycles_publish")} if st else {}
+        cyc = {k: round(st[k] / max(passes, 1)) for k in ("cycles_pixels", "cycles_barrier", "cycles_serial", "cycles_lm", "cycles_publish")} if st else {}
         if st: cyc.update({"per_feature_prologue": round(st["cycles_prologue"] / n), "per_feature_level_setup": round(st["cycles_level_setup"] / n), "per_feature_passes": round((st["cycles_pixels"] + st["cycles_serial"] + st["cycles_barrier"]) / n)})
         print(f"pen {pen} {cfg}: {ms:.2f} ms / {n} features = {n/ms:.1f} feat/ms; nfev {nf.mean(0).round(1).tolist()} GT median {np.median(gt):.4f}; "
               f"passes/feature {passes/max(n,1):.1f} memo {st.get('trials_memoized',0)/max(n,1):.1f} fused {st.get('passes_fused',0)/max(n,1):.1f} acc {st.get('fused_accepted',0)/max(n,1):.1f}; cyc/pass {cyc}; same-as-first-fast {same}", flush=True)
