@@ -39,6 +39,8 @@ for fn in functions("fm3d_normals_fast.o"):
     tag = "rays_smem" if "ILb1ELb1E" in fn else ("rays_l2_i1_smem" if "ILb0ELb1E" in fn else "rays_l2")
     if re.search(r"ILb[01]ELb[01]ELb1EEE", fn):
         tag += "_ncc"                      # cost_mode NCC: its own instantiation
+    if "normals_pp_kernel" in fn:          # the two-slot kernel (mode 0, four windows per CTA)
+        tag = "two_slot_ncc" if "ILb1EEE" in fn else "two_slot"
     s = sass("fm3d_normals_fast.o", fn)
     # loops: backward branches; pick the ones that contain LDS.U8 (window taps)
     addr = {}
