@@ -47,8 +47,8 @@ FLOP_EXEC_VALUE = 58.0        # executed by normals_fast_kernel per pixel of a v
 FLOP_EXEC_JAC = 113.0         # ... of a value + analytic-Jacobian pass (67 packed ops per pixel pair)
 SEED = 1001
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of normals_fast_kernel on this workload (ncu --set full)
-NORMALS_TRAFFIC_BYTES = 0.8902e9
-NORMALS_TRAFFIC_SOURCE = "profiles/r01f_normals_fast_kernel_ncu_raw_selected.csv: 199 MB read + 691 MB written, the ray scratch leaving L2"
+NORMALS_TRAFFIC_BYTES = 0.7471e9
+NORMALS_TRAFFIC_SOURCE = "profiles/r02m_normals_pp_kernel_ncu_raw_selected.csv: 182 MB read + 565 MB written, the ray scratch leaving L2"
 
 
 def log(*a):
@@ -731,7 +731,7 @@ def run_gpu_arm(args):
         cyc = {k: stats[k] for k in ("cycles_pixels", "cycles_barrier", "cycles_serial", "cycles_lm", "cycles_publish")}
         cyc_tot = max(1, cyc["cycles_pixels"] + cyc["cycles_barrier"] + cyc["cycles_serial"])
         roofline = {
-            "kernel": "normals_fast_kernel (K6: LM normal search, persistent CTAs, four feature pipelines per SM)",
+            "kernel": "normals_pp_kernel (K6: LM normal search, persistent CTAs, four features per SM: two per eight warps taking turns)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload under `ncu --set full`
             "traffic": NORMALS_TRAFFIC_BYTES, "traffic_unit": "bytes per launch (ncu --set full, " + NORMALS_TRAFFIC_SOURCE + ")",
