@@ -1059,26 +1059,39 @@ __device__ __forceinline__ unsigned level_setup(const NormalsArgs& A, GroupCtl& 
         const int x_lo = max(w1x0, 0), x_hi = min(w1x0 + (int)L.ww, lv.w) - 1;   // x0 in [x_lo, x_hi)
         const int y_lo = max(w1y0, 0), y_hi = min(w1y0 + wh, lv.h) - 1;
         const int x_cnt = staged1 ? max(x_hi - x_lo, 0) : 0, y_cnt = staged1 ? max(y_hi - y_lo, 0) : 0;
-        int row = 0;
+        // one warp per row of the disc: what depends on the row only (y tap, y weight, the row's part of the isPixelGood gate,
+        // the tap row in the window) is formed once per row, the samples of a row are stored side by side
         double i1_part = 0.0;
-        for (int idx = tid; idx < m; idx += NT) {
-            while (idx >= rows->start[row + 1]) row++;
-            const double px = cu + (double)(rows->ilo[row] + (idx - rows->start[row]));
+        const int n_rows = rows->nrows;
+        for (int row = wid; row < n_rows; row += NW) {
+            const int s0 = rows->start[row], cnt = rows->start[row + 1] - s0;
+            if (cnt <= 0) continue;
+            const int ilo = rows->ilo[row];
             const double py = cv + (double)rows->jrow[row];
-            if (!fm3d_pixel_good(px, py, inv_scale, lv.w, lv.h)) lvl_flags |= FLAG_PIX;
-            const float sx = (float)(scale * px), sy = (float)(scale * py);
-            const float fx0 = floorf(sx), fy0 = floorf(sy);
-            const int x0 = (int)fx0, y0 = (int)fy0;
-            float v;
-            if ((unsigned)(x0 - x_lo) < (unsigned)x_cnt && (unsigned)(y0 - y_lo) < (unsigned)y_cnt) {
-                const uint8_t* pw = win + (y0 - w1y0) * (int)L.ww + (x0 - w1x0);
-                v = fm3d_lerp4(fm3d_u8f(pw[0]), fm3d_u8f(pw[L.ww]), fm3d_u8f(pw[1]), fm3d_u8f(pw[L.ww + 1]),
-                               __fsub_rn(sx, fx0), __fsub_rn(sy, fy0));
-            } else {
-                v = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, sx, sy);
+            const bool y_bad = (py < 0) || (py > inv_scale * lv.h);
+            const float sy = (float)(scale * py);
+            const float fy0 = floorf(sy);
+            const int y0 = (int)fy0;
+            const float ay = __fsub_rn(sy, fy0);
+            const bool y_in = (unsigned)(y0 - y_lo) < (unsigned)y_cnt;
+            const uint8_t* wrow = win + (y0 - w1y0) * (int)L.ww - w1x0;
+            for (int i = lane; i < cnt; i += 32) {
+                const double px = cu + (double)(ilo + i);
+                if (y_bad || (px < 0) || (px > inv_scale * lv.w)) lvl_flags |= FLAG_PIX;   // fm3d_pixel_good
+                const float sx = (float)(scale * px);
+                const float fx0 = floorf(sx);
+                const int x0 = (int)fx0;
+                float v;
+                if (y_in && (unsigned)(x0 - x_lo) < (unsigned)x_cnt) {
+                    const uint8_t* pw = wrow + x0;
+                    v = fm3d_lerp4(fm3d_u8f(pw[0]), fm3d_u8f(pw[L.ww]), fm3d_u8f(pw[1]), fm3d_u8f(pw[L.ww + 1]),
+                                   __fsub_rn(sx, fx0), ay);
+                } else {
+                    v = fm3d_bilinear_global(img1, lv.w, lv.h, lv.pitch, sx, sy);
+                }
+                i1[s0 + i] = v;
+                i1_part += (double)v;
             }
-            i1[idx] = v;
-            i1_part += (double)v;
         }
         if (ncc) {
             // cost_mode NCC: the image-1 samples are kept CENTRED (u = I1 - c0, c0 = their mean rounded to float) together
@@ -1591,6 +1604,7 @@ normals_pp_kernel(const __grid_constant__ NormalsArgs A) {
                     const volatile int* go = &ctl[2 * sg + 1 - pref].ready_gen;
                     if (nbar_red_or(BAR_TURN, 192, *go > (pref ? served0 : served1))) { s = 1 - pref; break; }
                 }
+                __nanosleep(256);       // neither slot is ready: leave the issue slots to the LM warps and the other super-group
             }
             last = s;
         }
