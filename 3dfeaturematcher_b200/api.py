@@ -38,8 +38,8 @@ SYMBOLS = [
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
     "fm3d_describe_patches_sift", "fm3d_describe_patches_sift_dev",
-    "fm3d_detect_fast", "fm3d_detect_fast_dev",
-    "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_sift_base_image_dev",
+    "fm3d_detect_fast", "fm3d_detect_fast_dev", "fm3d_detect_sift",
+    "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_describe_keypoints_sift_oct", "fm3d_sift_base_image_dev",
     "fm3d_describe_keypoints_brisk", "fm3d_describe_keypoints_brisk_dev",
     "fm3d_describe_keypoints_orb", "fm3d_describe_keypoints_orb_dev",
     "fm3d_describe_patches_orb", "fm3d_describe_patches_orb_dev",
@@ -460,6 +460,43 @@ class Context:
                                                _ptr(xy, _fp), _ptr(resp, _fp), C.byref(n)))
         got = min(n.value, max_keypoints)
         return xy[:got].copy(), resp[:got].copy(), n.value
+
+    def detect_sift(self, img, nfeatures=0, n_octave_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma=1.6):
+        """feature_detector_->detect for DetectorType SIFT: H x W u8 -> n x 6 f64 rows (x, y, size, angle, response, octave) in
+        the order KeyPointsFilter::removeDuplicatedSorted leaves (cv2.SIFT_create(...).detect)."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        n = C.c_int(0)
+        args = (int(nfeatures), int(n_octave_layers), C.c_double(contrast_threshold), C.c_double(edge_threshold), C.c_double(sigma))
+        self._ck(self.lib.fm3d_detect_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], *args, 0, None, None, None, None, None, C.byref(n)))
+        m = n.value
+        xy = np.empty((max(m, 1), 2), np.float32)
+        size, angle, resp = (np.empty(max(m, 1), np.float32) for _ in range(3))
+        octave = np.empty(max(m, 1), np.int32)
+        if m > 0:
+            self._ck(self.lib.fm3d_detect_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], *args, m, _ptr(xy, _fp), _ptr(size, _fp),
+                                               _ptr(angle, _fp), _ptr(resp, _fp), _ptr(octave, C.POINTER(C.c_int32)), C.byref(n)))
+        got = min(n.value, m)
+        return np.column_stack([xy[:got].astype(np.float64), size[:got], angle[:got], resp[:got], octave[:got].astype(np.float64)])
+
+    def describe_keypoints_sift_oct(self, img, kps, octaves, n_octave_layers=3, sigma=1.6):
+        """descriptor_extractor_->compute for ExtractorType SIFT on keypoints that carry an octave (cv::SIFT's own): kps n x 4
+        (x, y, size, angle), octaves n packed cv::KeyPoint::octave -> n x 128 f32."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        kps = _arr(kps, np.float32).reshape(-1, 4)
+        octaves = _arr(octaves, np.int32).reshape(-1)
+        n = kps.shape[0]
+        assert octaves.shape[0] == n
+        desc = np.zeros((n, 128), np.float32)
+        self._ck(self.lib.fm3d_describe_keypoints_sift_oct(self._h, _ptr(img, _bp), w, h, img.strides[0], _ptr(kps, _fp),
+                                                           _ptr(octaves, C.POINTER(C.c_int32)), n, int(n_octave_layers), C.c_double(sigma),
+                                                           _ptr(desc, _fp)))
+        return desc
 
     def describe_keypoints_sift(self, img, kps):
         """descriptor_extractor_->compute for ExtractorType SIFT on octave-0 keypoints: H x W u8 image,

@@ -23,6 +23,10 @@
 // share lands in slot n+1 of the previous COLUMN cell, which the circular fold adds to that cell's
 // orientation bin 1 (see fm3d_describe.cu).  A warp owns a whole row of cells, so that share stays inside the
 // warp ("spill" below); the share of column 0 falls into the padding and is dropped, as in OpenCV.
+#include <algorithm>
+#include <climits>
+#include <vector>
+
 #include "fm3d_internal.cuh"
 
 #include <math.h>
@@ -141,10 +145,21 @@ struct KpGeom {
     float ori;
     int ptx, pty, radius;
     int valid;
+    const float* img;        // the Gaussian image the descriptor is read from, and its size
+    int w, h;
+};
+
+// Keypoints that carry an octave (cv::SIFT's own detector): the image of the keypoint's octave / layer in the Gaussian
+// pyramid (float offset from its start), its size, and the factor from frame coordinates to that image
+// (calcDescriptors: unpackOctave, ptf = kpt.pt * scale, size = kpt.size * scale).
+struct KpLayer {
+    int off, w, h;
+    float scale;
 };
 
 __global__ void __launch_bounds__(KP_NT)
-describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __restrict__ kps, int n, float* __restrict__ desc) {
+describe_kp_kernel(const float* __restrict__ base, int fw, int fh, const float* __restrict__ kps, const KpLayer* __restrict__ layers,
+                   int n, float* __restrict__ desc) {
     __shared__ KpGeom G[KP_PER_CTA];
     __shared__ float acc[KP_NT / 32][32][32];        // [warp][cell column * 8 + orientation bin][lane]: bank = lane
     __shared__ float hist[KP_PER_CTA][128];
@@ -156,10 +171,18 @@ describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __
         KpGeom g;
         g.valid = 0;
         if (f < (size_t)n) {
-            const float x = kps[4 * f], y = kps[4 * f + 1], size = kps[4 * f + 2], angle = kps[4 * f + 3];
+            float x = kps[4 * f], y = kps[4 * f + 1], size = kps[4 * f + 2];
+            const float angle = kps[4 * f + 3];
             // DescriptorExtractor::compute drops keypoints outside the image or of size <= FLT_EPSILON before SIFT
             // sees them (KeyPointsFilter::runByImageBorder / runByKeypointSize); such rows are written as zeros
-            g.valid = (x >= 0.f && y >= 0.f && x < (float)w && y < (float)h && size > 1.1920929e-07f && isfinite(size) && isfinite(angle)) ? 1 : 0;
+            g.valid = (x >= 0.f && y >= 0.f && x < (float)fw && y < (float)fh && size > 1.1920929e-07f && isfinite(size) && isfinite(angle)) ? 1 : 0;
+            g.img = base; g.w = fw; g.h = fh;
+            if (layers) {
+                const KpLayer L = layers[f];
+                g.img = base + L.off; g.w = L.w; g.h = L.h;
+                x = __fmul_rn(x, L.scale); y = __fmul_rn(y, L.scale); size = __fmul_rn(size, L.scale);
+            }
+            const int w = g.w, h = g.h;
             g.ptx = __float2int_rn(x); g.pty = __float2int_rn(y);                  // cvRound
             float ori = __fsub_rn(360.0f, angle);
             if (fabsf(ori - 360.0f) < 1.1920929e-07f) ori = 0.0f;
@@ -182,6 +205,8 @@ describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __
     for (int b = 0; b < 32; b++) my[b * 32] = 0.0f;
     __syncthreads();
     const KpGeom g = G[slot];
+    const float* __restrict__ img = g.img;
+    const int w = g.w, h = g.h;
     if (g.valid) {
         // bounding box (pixel offsets i = row, j = column) of the band rbin in [ci-1, ci+1), cbin in (-1, 4);
         // *_rot = *bin - 1.5
@@ -224,7 +249,7 @@ describe_kp_kernel(const float* __restrict__ base, int w, int h, const float* __
                 const int dr = ci - (int)r0f;            // this row of cells is row r0 (dr = 0) or r0 + 1 (dr = 1) of the split
                 if (dr != 0 && dr != 1) continue;
                 const int c0 = (int)c0f;                 // -1 .. 3
-                const float* p = base + (size_t)(g.pty + i) * w + (g.ptx + j);
+                const float* p = img + (size_t)(g.pty + i) * w + (g.ptx + j);
                 const float dx = __fsub_rn(__ldg(p + 1), __ldg(p - 1)), dy = __fsub_rn(__ldg(p - w), __ldg(p + w));
                 const float wgt = __expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), -0.125f));
                 const float mag = __fmul_rn(kp_sqrt_approx(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), wgt);
@@ -338,7 +363,7 @@ int fm3d_describe_keypoints_sift_dev(fm3d_ctx* ctx, const uint8_t* img, int w, i
     float* base = nullptr;
     if (int rc = fm3d_scratch(ctx, 8, sizeof(float) * (size_t)w * h, (void**)&base)) return rc;
     if (int rc = fm3d_sift_base_image_dev(ctx, img, w, h, stride, base)) return rc;
-    describe_kp_kernel<<<(n + KP_PER_CTA - 1) / KP_PER_CTA, KP_NT, 0, ctx->stream>>>(base, w, h, kps, n, descriptors);
+    describe_kp_kernel<<<(n + KP_PER_CTA - 1) / KP_PER_CTA, KP_NT, 0, ctx->stream>>>(base, w, h, kps, nullptr, n, descriptors);
     FM3D_LAUNCH_CHECK(ctx);
     return FM3D_OK;
 }
@@ -361,6 +386,53 @@ int fm3d_describe_keypoints_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h
                                                   reinterpret_cast<const float*>(d + al(bi)), n, d_desc)) return rc;
     if (int rc = fm3d_d2h(ctx, descriptors, d_desc, bd)) return rc;
     FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FM3D_OK;
+}
+
+int fm3d_describe_keypoints_sift_oct(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
+                                     const int32_t* octaves, int n, int n_octave_layers, double sigma, float* descriptors) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, n >= 0 && (n == 0 || (img && kps && octaves && descriptors && w >= 2 && h >= 2 && stride >= w)));
+    FM3D_CHECK_ARG(ctx, n_octave_layers >= 1 && sigma > 0);
+    if (n == 0) return FM3D_OK;
+    if (int rc = fm3d_bind(ctx)) return rc;
+    // detectAndCompute(useProvidedKeypoints): the octave range of the keypoints decides the pyramid
+    int first = 0, last = INT_MIN;
+    std::vector<int> oc(n), ly(n);
+    for (int i = 0; i < n; i++) {
+        int o = octaves[i] & 255;
+        const int l = (octaves[i] >> 8) & 255;
+        o = o < 128 ? o : (-128 | o);
+        oc[i] = o; ly[i] = l;
+        first = std::min(first, o); last = std::max(last, o);
+        if (l > n_octave_layers + 2) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoint %d: layer %d of %d", i, l, n_octave_layers + 3);
+    }
+    if (first < -1) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoints: first octave %d < -1", first);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t bi = (size_t)w * h, bk = sizeof(float) * 4 * (size_t)n, bl = sizeof(KpLayer) * (size_t)n, bd = sizeof(float) * 128 * (size_t)n;
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, al(bi) + al(bk) + al(bl) + al(bd), (void**)&d)) return rc;
+    FM3D_CUDA(ctx, cudaMemcpy2DAsync(d, (size_t)w, img, (size_t)stride, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_copy++;
+    fm3d_sift_pyramid P;
+    if (int rc = fm3d_sift_build_pyramid(ctx, reinterpret_cast<const uint8_t*>(d), w, h, w, first, last - first + 1, n_octave_layers, sigma,
+                                         false, &P)) return rc;
+    std::vector<KpLayer> layers(n);
+    for (int i = 0; i < n; i++) {
+        const int o = oc[i] - first;
+        if (o >= P.n_octaves) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoint %d: octave %d beyond the pyramid of this frame", i, oc[i]);
+        const size_t off = P.gauss_off[o] + (size_t)ly[i] * P.w[o] * P.h[o];
+        if (off > (size_t)INT_MAX) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "SIFT pyramid larger than 2^31 floats");
+        layers[i] = KpLayer{(int)off, P.w[o], P.h[o], oc[i] >= 0 ? 1.f / (float)(1 << oc[i]) : (float)(1 << -oc[i])};
+    }
+    if (int rc = fm3d_h2d(ctx, d + al(bi), kps, bk)) return rc;
+    if (int rc = fm3d_h2d(ctx, d + al(bi) + al(bk), layers.data(), bl)) return rc;
+    float* d_desc = reinterpret_cast<float*>(d + al(bi) + al(bk) + al(bl));
+    describe_kp_kernel<<<(n + KP_PER_CTA - 1) / KP_PER_CTA, KP_NT, 0, ctx->stream>>>(
+        P.gauss, w, h, reinterpret_cast<const float*>(d + al(bi)), reinterpret_cast<const KpLayer*>(d + al(bi) + al(bk)), n, d_desc);
+    FM3D_LAUNCH_CHECK(ctx);
+    if (int rc = fm3d_d2h(ctx, descriptors, d_desc, bd)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // `layers` must outlive the copy
     return FM3D_OK;
 }
 

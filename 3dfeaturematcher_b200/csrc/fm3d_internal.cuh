@@ -12,7 +12,7 @@
 #include "../../include/fm3d.h"
 
 #define FM3D_MAX_LEVELS 8
-#define FM3D_SCRATCH_SLOTS 12
+#define FM3D_SCRATCH_SLOTS 16
 
 // ---------------------------------------------------------------- device-side camera model
 // K, dist (OpenCV order k1,k2,p1,p2,k3) and g12 = [R|t] (X2 = R X1 + t), all fp64 as the
@@ -115,6 +115,20 @@ int fm3d_d2h(fm3d_ctx* ctx, void* dst, const void* src, size_t bytes);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed).
 int fm3d_encode_tmap_2d_u8(fm3d_ctx* ctx, CUtensorMap* map, const void* base, int w, int h,
                            int pitch, int box_w, int box_h);
+
+// cv::SIFT's Gaussian (and DoG) pyramid in scratch slots 12 / 13 (fm3d_detect_sift.cu), shared by the detector (K14) and the
+// descriptor stage for keypoints that carry an octave (K11).  Image i of octave o: gauss + gauss_off[o] + i * w[o] * h[o].
+struct fm3d_sift_pyramid {
+    int first_octave;                   // -1: the base image is the doubled frame
+    int n_octaves, n_octave_layers;
+    int w[16], h[16];
+    size_t gauss_off[16], dog_off[16];  // float offsets
+    size_t gauss_floats, dog_floats;
+    float* gauss;
+    float* dog;
+};
+int fm3d_sift_build_pyramid(fm3d_ctx* ctx, const uint8_t* d_img, int w, int h, int stride, int first_octave, int n_octaves_wanted,
+                            int n_octave_layers, double sigma, bool with_dog, fm3d_sift_pyramid* P);
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

@@ -236,17 +236,20 @@ DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv
     adaptive_min_ = (int)fs["FeatureOptions"]["Adaptive"]["MinFeatures"];                     // :194-197
     adaptive_max_ = (int)fs["FeatureOptions"]["Adaptive"]["MaxFeatures"];
     adaptive_iters_ = (int)fs["FeatureOptions"]["Adaptive"]["MaxIters"];
-    // generateExtractor (descriptorsmatcher.cpp:291-359).  Of the constructor arguments the reference reads from the settings,
-    // only cv::SIFT's NumOctaveLayers and Sigma change what compute() returns for provided octave-0 keypoints (NumFeatures /
-    // ContrastThreshold / EdgeThreshold act in detect(); cv::ORB's ScaleFactor / NumLevels only on keypoints of octave > 0;
-    // cv::BRISK::compute uses neither Threshold nor Octaves).  The SIFT kernels (K9, K11) are built for 3 layers, sigma 1.6:
-    // a settings file that asks for something else gets an error, not silently different descriptors.
-    if (extractorType == "SIFT" && !fs["FeatureOptions"]["SiftDetector"].empty()) {
+    // generateDetector / generateExtractor for SIFT (descriptorsmatcher.cpp:243-256, :304-314): cv::SIFT(NumFeatures,
+    // NumOctaveLayers, ContrastThreshold, EdgeThreshold, Sigma).  build/settings.yml carries no SiftDetector block (the
+    // reference would then hand cv::SIFT zeros): a key that is absent keeps cv::SIFT's own default.  cv::ORB's ScaleFactor /
+    // NumLevels act only on keypoints of octave > 0 and cv::BRISK::compute uses neither Threshold nor Octaves: with FAST
+    // keypoints (octave 0) they change nothing.
+    if (!fs["FeatureOptions"]["SiftDetector"].empty()) {
         const cv::FileNode sd = fs["FeatureOptions"]["SiftDetector"];
-        if (!sd["Sigma"].empty() && std::fabs((double)sd["Sigma"] - 1.6) > 1e-12)
-            throw std::runtime_error("fm3d: FeatureOptions.SiftDetector.Sigma must be 1.6 (the SIFT kernels are built for it)");
-        if (!sd["NumOctaveLayers"].empty() && (int)sd["NumOctaveLayers"] != 3)
-            throw std::runtime_error("fm3d: FeatureOptions.SiftDetector.NumOctaveLayers must be 3 (the SIFT kernels are built for it)");
+        if (!sd["NumFeatures"].empty()) sift_nfeatures_ = (int)sd["NumFeatures"];
+        if (!sd["NumOctaveLayers"].empty()) sift_layers_ = (int)sd["NumOctaveLayers"];
+        if (!sd["ContrastThreshold"].empty()) sift_contrast_ = (double)sd["ContrastThreshold"];
+        if (!sd["EdgeThreshold"].empty()) sift_edge_ = (double)sd["EdgeThreshold"];
+        if (!sd["Sigma"].empty()) sift_sigma_ = (double)sd["Sigma"];
+        if ((detector_type_ == "SIFT" || extractorType == "SIFT") && (sift_layers_ < 1 || sift_layers_ > 5 || !(sift_sigma_ > 0)))
+            throw std::runtime_error("fm3d: FeatureOptions.SiftDetector needs 1 <= NumOctaveLayers <= 5 and Sigma > 0");
     }
     host_ctx();
 }
@@ -272,13 +275,16 @@ void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv:
     // descriptorsmatcher.cpp:110-115: detect on both frames, then compute on both frames.  DetectorType FAST
     // (STATIC) with ExtractorType SIFT, BRISK or ORB runs on the GPU (K10 + K11 / K12 / K13); the other detectors /
     // extractors of the reference (SURF, STAR, MSER, FREAK, ORB's own detector) are upstream code this library does not carry.
-    if (detector_type_ == "FAST" && (detector_mode_ == "STATIC" || detector_mode_ == "ADAPTIVE") && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK" || extractor_type_ == "ORB")) {
+    // DetectorType SIFT (STATIC) with ExtractorType SIFT: cv::SIFT's scale-space detector and its descriptors on the pyramid
+    // layers (K14 + K11).
+    if ((detector_type_ == "FAST" && (detector_mode_ == "STATIC" || detector_mode_ == "ADAPTIVE") && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK" || extractor_type_ == "ORB")) ||
+        (detector_type_ == "SIFT" && detector_mode_ == "STATIC" && extractor_type_ == "SIFT")) {
         detectAndDescribe(image_a_, ka, da);
         detectAndDescribe(image_b_, kb, db);
         return;
     }
-    throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC) + "
-                             "ExtractorType SIFT, BRISK or ORB only (STATIC or ADAPTIVE; settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
+    throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC or ADAPTIVE) + "
+                             "ExtractorType SIFT, BRISK or ORB and for DetectorType SIFT (STATIC) + ExtractorType SIFT only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
                              "); inject the features of other detectors with setFeatures");
 }
 
@@ -291,6 +297,31 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
     const uint8_t* px = image.ptr<uint8_t>(0);
     const int w = image.cols, h = image.rows, stride = (int)image.step1();
     int n = 0;
+    if (detector_type_ == "SIFT") {
+        // cv::SIFT::detect, then cv::SIFT::compute on its keypoints (every descriptor from the keypoint's own pyramid layer)
+        check(ctx, fm3d_detect_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, 0,
+                                    nullptr, nullptr, nullptr, nullptr, nullptr, &n), "detect (SIFT, count)");
+        kpts.clear();
+        desc = cv::Mat();
+        if (n == 0) return;
+        std::vector<float> xy((size_t)2 * n), size(n), angle(n), resp(n), k4((size_t)4 * n);
+        std::vector<int32_t> oct(n);
+        int m = 0;
+        check(ctx, fm3d_detect_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, n,
+                                    xy.data(), size.data(), angle.data(), resp.data(), oct.data(), &m), "detect (SIFT)");
+        n = std::min(n, m);
+        kpts.reserve(n);
+        for (int i = 0; i < n; i++) {
+            cv::KeyPoint kp(xy[2 * i], xy[2 * i + 1], size[i]);
+            kp.angle = angle[i]; kp.response = resp[i]; kp.octave = oct[i];
+            kpts.push_back(kp);
+            k4[4 * i] = kp.pt.x; k4[4 * i + 1] = kp.pt.y; k4[4 * i + 2] = kp.size; k4[4 * i + 3] = kp.angle;
+        }
+        desc = cv::Mat::zeros(cv::Size(128, n), CV_32F);
+        check(ctx, fm3d_describe_keypoints_sift_oct(ctx, px, w, h, stride, k4.data(), oct.data(), n, sift_layers_, sift_sigma_, desc.ptr<float>()),
+              "compute (SIFT on the pyramid)");
+        return;
+    }
     int threshold = fast_threshold_, nonmax = fast_nonmax_;
     if (detector_mode_ == "ADAPTIVE") {
         // descriptorsmatcher.cpp:186-199: cv::DynamicAdaptedFeatureDetector(AdjusterAdapter::create("FAST"), MinFeatures,
@@ -375,6 +406,13 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
         return;
     }
     desc = cv::Mat::zeros(cv::Size(128, n), CV_32F);
+    if (sift_layers_ != 3 || std::fabs(sift_sigma_ - 1.6) > 1e-12) {
+        // the fused base-image kernel of K11 is built for sigma 1.6: other settings take the pyramid builder (octave 0, layer 0)
+        std::vector<int32_t> oct(n, 0);
+        check(ctx, fm3d_describe_keypoints_sift_oct(ctx, px, w, h, stride, k4.data(), oct.data(), n, sift_layers_, sift_sigma_, desc.ptr<float>()),
+              "compute (SIFT, settings of the file)");
+        return;
+    }
     check(ctx, fm3d_describe_keypoints_sift(ctx, px, w, h, stride, k4.data(), n, desc.ptr<float>()), "compute (SIFT)");
 }
 

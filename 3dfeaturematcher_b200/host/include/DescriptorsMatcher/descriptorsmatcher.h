@@ -48,5 +48,8 @@ private:
     int fast_threshold_, fast_nonmax_;
     int adaptive_min_, adaptive_max_, adaptive_iters_;
     int adaptive_threshold_used_ = -1;
+    // FeatureOptions.SiftDetector (descriptorsmatcher.cpp:246-251, :306-311); cv::SIFT's defaults where the file is silent
+    int sift_nfeatures_ = 0, sift_layers_ = 3;
+    double sift_contrast_ = 0.04, sift_edge_ = 10.0, sift_sigma_ = 1.6;
 };
 #endif

@@ -456,6 +456,18 @@ int fm3d_detect_fast(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
 int fm3d_detect_fast_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int threshold,
                          int nonmax, int max_keypoints, float* xy, float* response, int* n_dev);
 
+/* Replaces feature_detector_->detect(frame, keypoints) (DescriptorsMatcher/descriptorsmatcher.cpp:110-111, :91-92, :76-77) for
+ * DetectorType SIFT (:243-256: cv::SIFT(NumFeatures, NumOctaveLayers, ContrastThreshold, EdgeThreshold, Sigma); settings.yml
+ * FeatureOptions.SiftDetector): cv::SIFT's scale-space detector -- doubled base image, Gaussian / DoG pyramids, 26-neighbour
+ * extrema, sub-pixel refinement with the contrast and edge tests, one keypoint per orientation peak -- followed by
+ * KeyPointsFilter::removeDuplicatedSorted (the output order) and retainBest(nfeatures) (nfeatures <= 0: all; the kept SET is
+ * OpenCV's, their order stays the sorted one).  img: host u8, stride bytes per row.  Outputs (host, up to max_keypoints rows):
+ * xy (x, y pairs), size, angle (degrees), response, octave (cv::KeyPoint::octave as cv::SIFT packs it).  *n = keypoints
+ * found (may exceed max_keypoints; only max_keypoints are written). */
+int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
+                     double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
+                     float* angle, float* response, int32_t* octave, int* n);
+
 /* ---------------------------------------------------------- keypoint description ---- */
 
 /* Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
@@ -473,6 +485,14 @@ int fm3d_describe_keypoints_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h
                                  int n, float* descriptors);
 int fm3d_describe_keypoints_sift_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride,
                                      const float* kps, int n, float* descriptors);
+
+/* The same call for keypoints that carry an octave -- what cv::SIFT's own detector (fm3d_detect_sift) returns: cv::SIFT::compute
+ * with provided keypoints builds the Gaussian pyramid over the octave range of the keypoints (the doubled frame first if one
+ * of them has octave -1) and reads every descriptor from the image of the keypoint's octave and layer, at pt * scale with
+ * size * scale (calcDescriptors / unpackOctave).  kps: n x 4 (x, y, size, angle) in frame coordinates, octaves: n packed
+ * cv::KeyPoint::octave values.  n_octave_layers / sigma: FeatureOptions.SiftDetector.NumOctaveLayers / Sigma. */
+int fm3d_describe_keypoints_sift_oct(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
+                                     const int32_t* octaves, int n, int n_octave_layers, double sigma, float* descriptors);
 /* The base image alone (createInitialImage): base is w x h f32, rows w floats apart, device memory. */
 int fm3d_sift_base_image_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* base);
 

@@ -634,3 +634,54 @@ def test_adapters_shard_the_matching_over_the_gpus_of_the_process(tmp_path, nccl
         assert p.returncode == 0, p.stdout + p.stderr
         outs.append(open(out, "rb").read())
     assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 1000
+
+
+@pytest.mark.gpu
+def test_main_cpp_from_the_frames_alone_with_sift_and_sift(tmp_path):
+    """DetectorType SIFT + ExtractorType SIFT (descriptorsmatcher.cpp:243-256, :304-314) with the knobs of a SiftDetector
+    block: compareWithNNDR detects with cv::SIFT's scale-space detector (K14), describes every keypoint on its own pyramid
+    layer (K11) and matches on the GPU; the rest of main.cpp's pipeline runs on what it found.  Keypoints against the
+    oracle restatement of cv::SIFT::detect (itself pinned to cv2), descriptors against cv2.SIFT.compute where cv2 is here,
+    matches against the matcher oracle on the descriptors the adapter produced."""
+    from oracle import sift_detect_np as sd
+    from test_sift_detect import matched_fraction
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    tmp = str(tmp_path)
+    opts = """FeatureOptions:
+   DetectorType: SIFT
+   DetectorMode: STATIC
+   SiftDetector:
+      NumFeatures: 1500
+      NumOctaveLayers: 3
+      ContrastThreshold: 0.04
+      EdgeThreshold: 10
+      Sigma: 1.6
+   ExtractorType: SIFT
+"""
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+    descs = []
+    for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
+        want = sd.detect_sift(img, nfeatures=1500)
+        got = np.column_stack([k[:, :5], k[:, 5]]) if k.shape[1] > 5 else None
+        assert 1400 <= len(k) <= 1600 and abs(len(k) - len(want)) <= 15
+        if got is not None:
+            assert matched_fraction(want, got) >= 0.98
+        else:           # the driver writes x, y, size, angle, response
+            hit = sum(np.abs(k[:, :2] - a[:2]).max(1).min() < 0.01 for a in want[::7])
+            assert hit >= 0.98 * len(want[::7])
+        assert d.shape == (len(k), 128) and (d >= 0).all() and (d <= 255).all() and (np.linalg.norm(d, axis=1) > 300).all()
+        descs.append(d)
+    o_idx, o_dist = orc.knn2_f32(descs[0], descs[1])
+    oq, ot, od = orc.nndr_filter(o_idx, o_dist, 0.55)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    assert len(oq) >= 30 and len(res["normals"]) == int((res["status"] == 0).sum()) and len(res["normals"]) >= 5
+    print(f"SIFT+SIFT from the frames: {len(res['detected'][0][0])} / {len(res['detected'][1][0])} keypoints, {len(oq)} NNDR matches, "
+          f"{len(res['normals'])} refined normals")

@@ -263,6 +263,39 @@ def orb_keypoints():
     np.savez_compressed(os.path.join(OUT, "orb_keypoints.npz"), **out)
 
 
+def sift_detect_test_images():
+    """Frames for the SIFT detector fixtures: band-limited noise, a rendered synthetic frame, an odd-sized resample of it."""
+    import cv2
+    rng = np.random.default_rng(7400)
+    b = cv2.GaussianBlur(rng.integers(0, 256, (120, 160)).astype(np.float32), (0, 0), 2.0)
+    frame = synth.make_stereo_case(320, 240, 8, 99, pixels_ray=8, n_distractors=10)["scene"].img1
+    return {"blobs": ((b - b.min()) / (b.max() - b.min()) * 255).astype(np.uint8), "frame": frame,
+            "odd": cv2.resize(frame, (211, 137), interpolation=cv2.INTER_AREA)}
+
+
+SIFT_DETECT_PARAMS = {"default": dict(), "best50": dict(nfeatures=50),
+                      "knobs": dict(nOctaveLayers=4, contrastThreshold=0.03, edgeThreshold=8.0, sigma=1.4)}
+
+
+def sift_detect():
+    """K14 fixtures: cv2.SIFT_create(...).detect (what cv::SIFT(NumFeatures, NumOctaveLayers, ContrastThreshold, EdgeThreshold,
+    Sigma) of descriptorsmatcher.cpp:243-256 runs) on the frames above: rows (x, y, size, angle, response) and the packed octave,
+    in cv2's output order (KeyPointsFilter::removeDuplicatedSorted; retainBest leaves its own order: compare as a set)."""
+    import cv2
+    out = {}
+    for name, img in sift_detect_test_images().items():
+        out[f"img_{name}"] = img
+        for pname, kw in SIFT_DETECT_PARAMS.items():
+            kps = cv2.SIFT_create(**kw).detect(img, None)
+            out[f"kp_{name}_{pname}"] = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in kps], np.float32).reshape(-1, 5)
+            out[f"oct_{name}_{pname}"] = np.array([k.octave for k in kps], np.int32)
+            if pname != "best50":       # and what descriptor_extractor_->compute returns for them (K11 on the pyramid layers)
+                kps2, desc = cv2.SIFT_create(**kw).compute(img, kps)
+                assert len(kps2) == len(kps)
+                out[f"desc_{name}_{pname}"] = desc.astype(np.uint8)
+    np.savez_compressed(os.path.join(OUT, "sift_detect.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "--orb-only" in sys.argv:
@@ -273,6 +306,8 @@ if __name__ == "__main__":
         sift_keypoints()
     elif "--fast-only" in sys.argv:
         fast_keypoints()
+    elif "--sift-detect-only" in sys.argv:
+        sift_detect()
     else:
         if "--sift-only" not in sys.argv:
             primitives()
@@ -282,5 +317,6 @@ if __name__ == "__main__":
         sift_keypoints()
         brisk_keypoints()
         orb_keypoints()
+        sift_detect()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
