@@ -259,6 +259,37 @@ def frontend_sweep(ctx, stream):
                           "descriptors_per_s": n / ((ms_all - ms_base) * 1e-3) if ms_all > ms_base else None}), flush=True)
 
 
+def sift_detect_sweep(ctx, stream):
+    """K14 alone: cv::SIFT's detector (fm3d_detect_sift, host buffers in and out: the upload of the frame, the pyramids, the
+    extrema / refinement kernels, the download and the host-side sort are all inside the time) and the descriptors of its
+    keypoints on the pyramid layers, on rendered frames of 720p and 4K; cv2.SIFT on this box's host cores beside it."""
+    import importlib
+    synth = importlib.import_module("3dfeaturematcher_b200.synth")
+    for W, H in ((1280, 720), (3840, 2160)):
+        img = synth.make_stereo_case(W, H, 20, 1001, pixels_ray=32)["scene"].img1
+        ctx.detect_sift(img)
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter(); K = ctx.detect_sift(img); t.append(time.perf_counter() - t0)
+        ms_det = 1e3 * min(t)
+        kps, oct_ = K[:, :4].astype(np.float32), K[:, 5].astype(np.int32)
+        ctx.describe_keypoints_sift_oct(img, kps, oct_)
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter(); ctx.describe_keypoints_sift_oct(img, kps, oct_); t.append(time.perf_counter() - t0)
+        ms_desc = 1e3 * min(t)
+        out = {"case": "sift_detect_and_describe", "W": W, "H": H, "keypoints": int(len(K)), "ms_detect_host_to_host": ms_det,
+               "ms_describe_host_to_host": ms_desc, "pyramid_mb": (2 * W) * (2 * H) * 4 * (6 + 5) * 4 / 3 / 1e6}
+        try:
+            import cv2
+            s = cv2.SIFT_create()
+            t0 = time.perf_counter(); kp = s.detect(img, None); t1 = time.perf_counter(); s.compute(img, kp); t2 = time.perf_counter()
+            out.update({"cv2_keypoints": len(kp), "cv2_ms_detect": 1e3 * (t1 - t0), "cv2_ms_compute": 1e3 * (t2 - t1), "cv2_threads": cv2.getNumThreads()})
+        except ImportError:
+            pass
+        print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = api.Context(0)
@@ -273,6 +304,8 @@ if __name__ == "__main__":
         describe_sweep(ctx, stream)
     if which in ("all", "frontend"):
         frontend_sweep(ctx, stream)
+    if which in ("all", "sift_detect"):
+        sift_detect_sweep(ctx, stream)
     if which in ("c3",):
         c3_pipeline(ctx, stream)
     ctx.close()
