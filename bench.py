@@ -656,6 +656,18 @@ def run_gpu_arm(args):
     orb_kept = [int(d_okept[a, :n_kp[a]].sum().item()) for a in range(2)]
     kdesc_rows_nonzero = [int((d_kdesc[a, :n_kp[a]] != 0).any(1).sum().item()) for a in range(2)]
     del d_kdesc, d_bdesc, d_odesc, d_patches
+    # DetectorType SIFT + ExtractorType SIFT (K14 + K11 on the pyramid layers): host buffers in and out, wall clock (rank 0)
+    sift_front = None
+    if rank == 0:
+        h1 = case["scene"].img1
+        ctx.detect_sift(h1)
+        t0 = time.perf_counter()
+        ksift = ctx.detect_sift(h1)
+        t1 = time.perf_counter()
+        dsift = ctx.describe_keypoints_sift_oct(h1, ksift[:, :4].astype(np.float32), ksift[:, 5].astype(np.int32))
+        t2 = time.perf_counter()
+        sift_front = {"keypoints_frame1": int(len(ksift)), "ms_detect_frame1_host_to_host": 1e3 * (t1 - t0),
+                      "ms_describe_frame1_host_to_host": 1e3 * (t2 - t1), "descriptor_rows_nonzero": int((dsift != 0).any(1).sum())}
 
     # ---- the north-star configuration in the same run, at the same N: BASELINE configs[2], ONE 4K pair with 20 000 query
     # keypoints in total sharded over the ranks (strong scaling), pixelsRay 64, pyramids 3
@@ -834,7 +846,8 @@ def run_gpu_arm(args):
                 "brisk_descriptors_per_s": sum(n_kp) / (before_ms[2] * 1e-3) if before_ms[2] > 0 else None,
                 "detect_hbm_gbs": 2 * W * H / (before_ms[0] * 1e-3) / 1e9 if before_ms[0] > 0 else None,
                 "descriptors_per_s": sum(n_kp) / (before_ms[1] * 1e-3) if before_ms[1] > 0 else None,
-                "descriptor_rows_nonzero": kdesc_rows_nonzero},
+                "descriptor_rows_nonzero": kdesc_rows_nonzero,
+                "sift_detector": sift_front},
             "wall_s_device_arm": wall_dev, "gpu": info["name"],
         }
         emit(out)
