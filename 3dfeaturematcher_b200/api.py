@@ -470,14 +470,16 @@ class Context:
         h, w = img.shape
         n = C.c_int(0)
         args = (int(nfeatures), int(n_octave_layers), C.c_double(contrast_threshold), C.c_double(edge_threshold), C.c_double(sigma))
-        self._ck(self.lib.fm3d_detect_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], *args, 0, None, None, None, None, None, C.byref(n)))
-        m = n.value
-        xy = np.empty((max(m, 1), 2), np.float32)
-        size, angle, resp = (np.empty(max(m, 1), np.float32) for _ in range(3))
-        octave = np.empty(max(m, 1), np.int32)
-        if m > 0:
+        m = max(4096, (w * h) // 32)            # one call in the usual case; again with the real count if a frame has more
+        for _ in range(2):
+            xy = np.empty((m, 2), np.float32)
+            size, angle, resp = (np.empty(m, np.float32) for _ in range(3))
+            octave = np.empty(m, np.int32)
             self._ck(self.lib.fm3d_detect_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], *args, m, _ptr(xy, _fp), _ptr(size, _fp),
                                                _ptr(angle, _fp), _ptr(resp, _fp), _ptr(octave, C.POINTER(C.c_int32)), C.byref(n)))
+            if n.value <= m:
+                break
+            m = n.value
         got = min(n.value, m)
         return np.column_stack([xy[:got].astype(np.float64), size[:got], angle[:got], resp[:got], octave[:got].astype(np.float64)])
 

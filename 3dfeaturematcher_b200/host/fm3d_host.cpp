@@ -299,17 +299,21 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
     int n = 0;
     if (detector_type_ == "SIFT") {
         // cv::SIFT::detect, then cv::SIFT::compute on its keypoints (every descriptor from the keypoint's own pyramid layer)
-        check(ctx, fm3d_detect_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, 0,
-                                    nullptr, nullptr, nullptr, nullptr, nullptr, &n), "detect (SIFT, count)");
+        // one detection in the usual case (room for a keypoint per 32 pixels); again with the real count if the frame has more
+        int cap = std::max(4096, (w * h) / 32);
+        std::vector<float> xy, size, angle, resp, k4;
+        std::vector<int32_t> oct;
         kpts.clear();
         desc = cv::Mat();
+        for (int attempt = 0; attempt < 2; attempt++) {
+            xy.resize((size_t)2 * cap); size.resize(cap); angle.resize(cap); resp.resize(cap); oct.resize(cap);
+            check(ctx, fm3d_detect_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, cap,
+                                        xy.data(), size.data(), angle.data(), resp.data(), oct.data(), &n), "detect (SIFT)");
+            if (n <= cap) break;
+            cap = n;
+        }
         if (n == 0) return;
-        std::vector<float> xy((size_t)2 * n), size(n), angle(n), resp(n), k4((size_t)4 * n);
-        std::vector<int32_t> oct(n);
-        int m = 0;
-        check(ctx, fm3d_detect_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, n,
-                                    xy.data(), size.data(), angle.data(), resp.data(), oct.data(), &m), "detect (SIFT)");
-        n = std::min(n, m);
+        k4.resize((size_t)4 * n);
         kpts.reserve(n);
         for (int i = 0; i < n; i++) {
             cv::KeyPoint kp(xy[2 * i], xy[2 * i + 1], size[i]);
