@@ -251,6 +251,14 @@ DescriptorsMatcher::DescriptorsMatcher(cv::FileStorage& fs, cv::Mat& frame_a, cv
         if ((detector_type_ == "SIFT" || extractorType == "SIFT") && (sift_layers_ < 1 || sift_layers_ > 5 || !(sift_sigma_ > 0)))
             throw std::runtime_error("fm3d: FeatureOptions.SiftDetector needs 1 <= NumOctaveLayers <= 5 and Sigma > 0");
     }
+    if (!fs["FeatureOptions"]["OrbDetector"].empty()) {
+        const cv::FileNode od = fs["FeatureOptions"]["OrbDetector"];
+        if (!od["NumFeatures"].empty()) orb_nfeatures_ = (int)od["NumFeatures"];
+        if (!od["ScaleFactor"].empty()) orb_scale_ = (double)(float)(double)od["ScaleFactor"];       // cv::ORB takes a float
+        if (!od["NumLevels"].empty()) orb_levels_ = (int)od["NumLevels"];
+        if (detector_type_ == "ORB" && (orb_nfeatures_ < 0 || !(orb_scale_ > 1.0) || orb_levels_ < 1 || orb_levels_ > 16))
+            throw std::runtime_error("fm3d: FeatureOptions.OrbDetector needs NumFeatures >= 0, ScaleFactor > 1 and 1 <= NumLevels <= 16");
+    }
     host_ctx();
 }
 
@@ -278,13 +286,14 @@ void DescriptorsMatcher::features(std::vector<cv::KeyPoint>& ka, std::vector<cv:
     // DetectorType SIFT (STATIC) with ExtractorType SIFT: cv::SIFT's scale-space detector and its descriptors on the pyramid
     // layers (K14 + K11).
     if ((detector_type_ == "FAST" && (detector_mode_ == "STATIC" || detector_mode_ == "ADAPTIVE") && (extractor_type_ == "SIFT" || extractor_type_ == "BRISK" || extractor_type_ == "ORB")) ||
-        (detector_type_ == "SIFT" && detector_mode_ == "STATIC" && extractor_type_ == "SIFT")) {
+        (detector_type_ == "SIFT" && detector_mode_ == "STATIC" && extractor_type_ == "SIFT") ||
+        (detector_type_ == "ORB" && detector_mode_ == "STATIC" && extractor_type_ == "ORB")) {
         detectAndDescribe(image_a_, ka, da);
         detectAndDescribe(image_b_, kb, db);
         return;
     }
     throw std::runtime_error("fm3d: DescriptorsMatcher detects and describes on the GPU for DetectorType FAST (STATIC or ADAPTIVE) + "
-                             "ExtractorType SIFT, BRISK or ORB and for DetectorType SIFT (STATIC) + ExtractorType SIFT only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
+                             "ExtractorType SIFT, BRISK or ORB, for DetectorType SIFT (STATIC) + ExtractorType SIFT and for DetectorType ORB (STATIC) + ExtractorType ORB only (settings: " + detector_type_ + " / " + detector_mode_ + " / " + extractor_type_ +
                              "); inject the features of other detectors with setFeatures");
 }
 
@@ -324,6 +333,33 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
         desc = cv::Mat::zeros(cv::Size(128, n), CV_32F);
         check(ctx, fm3d_describe_keypoints_sift_oct(ctx, px, w, h, stride, k4.data(), oct.data(), n, sift_layers_, sift_sigma_, desc.ptr<float>()),
               "compute (SIFT on the pyramid)");
+        return;
+    }
+    if (detector_type_ == "ORB") {
+        // cv::ORB::detect, then cv::ORB::compute on its keypoints: one pyramid, FAST + Harris ranking + intensity-centroid angles per
+        // level, rBRIEF rows at the level positions (K15); the keypoint set and the rows of cv::ORB::detectAndCompute
+        int cap = std::max(64, 2 * orb_nfeatures_ + 64);
+        std::vector<float> xy, size, angle, resp;
+        std::vector<int32_t> oct;
+        std::vector<uint8_t> rows;
+        kpts.clear();
+        desc = cv::Mat();
+        for (int attempt = 0; attempt < 2; attempt++) {
+            xy.resize((size_t)2 * cap); size.resize(cap); angle.resize(cap); resp.resize(cap); oct.resize(cap); rows.resize((size_t)32 * cap);
+            check(ctx, fm3d_detect_orb(ctx, px, w, h, stride, orb_nfeatures_, orb_scale_, orb_levels_, 20, cap, xy.data(), size.data(), angle.data(),
+                                       resp.data(), oct.data(), rows.data(), &n), "detect + compute (ORB)");
+            if (n <= cap) break;
+            cap = n;
+        }
+        if (n == 0) return;
+        kpts.reserve(n);
+        desc = cv::Mat::zeros(cv::Size(32, n), CV_8U);
+        for (int i = 0; i < n; i++) {
+            cv::KeyPoint kp(xy[2 * i], xy[2 * i + 1], size[i]);
+            kp.angle = angle[i]; kp.response = resp[i]; kp.octave = oct[i];
+            kpts.push_back(kp);
+            memcpy(desc.ptr<uint8_t>(i), rows.data() + (size_t)32 * i, 32);
+        }
         return;
     }
     int threshold = fast_threshold_, nonmax = fast_nonmax_;

@@ -51,5 +51,8 @@ private:
     // FeatureOptions.SiftDetector (descriptorsmatcher.cpp:246-251, :306-311); cv::SIFT's defaults where the file is silent
     int sift_nfeatures_ = 0, sift_layers_ = 3;
     double sift_contrast_ = 0.04, sift_edge_ = 10.0, sift_sigma_ = 1.6;
+    // FeatureOptions.OrbDetector (descriptorsmatcher.cpp:273-281, :336-342); cv::ORB's defaults where the file is silent
+    int orb_nfeatures_ = 500, orb_levels_ = 8;
+    double orb_scale_ = 1.2;
 };
 #endif

@@ -468,6 +468,17 @@ int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
                      double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
                      float* angle, float* response, int32_t* octave, int* n);
 
+/* Replaces feature_detector_->detect followed by descriptor_extractor_->compute (DescriptorsMatcher/descriptorsmatcher.cpp:110-115,
+ * :91-96, :76-81) for DetectorType ORB + ExtractorType ORB (:273-279, :325-330: cv::ORB(OrbDetector.NumFeatures, ScaleFactor,
+ * NumLevels), the other arguments at cv::ORB's defaults; fast_threshold = 20 is its default): the INTER_LINEAR_EXACT pyramid,
+ * FAST + Harris ranking + intensity-centroid angles per level, rBRIEF rows on the blurred level images -- the keypoint SET and
+ * the rows of cv::ORB::detectAndCompute; the order is (level, y, x) (OpenCV's is whatever std::nth_element leaves).  Outputs
+ * (host, up to max_keypoints rows): xy in frame coordinates, size = 31 s^level, angle (degrees), response (Harris measure),
+ * octave = level, descriptors (32 bytes per keypoint; may be NULL).  *n = keypoints found. */
+int fm3d_detect_orb(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, double scale_factor, int nlevels,
+                    int fast_threshold, int max_keypoints, float* xy, float* size, float* angle, float* response, int32_t* octave,
+                    uint8_t* descriptors, int* n);
+
 /* ---------------------------------------------------------- keypoint description ---- */
 
 /* Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of

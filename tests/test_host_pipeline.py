@@ -685,3 +685,52 @@ def test_main_cpp_from_the_frames_alone_with_sift_and_sift(tmp_path):
     assert len(oq) >= 30 and len(res["normals"]) == int((res["status"] == 0).sum()) and len(res["normals"]) >= 5
     print(f"SIFT+SIFT from the frames: {len(res['detected'][0][0])} / {len(res['detected'][1][0])} keypoints, {len(oq)} NNDR matches, "
           f"{len(res['normals'])} refined normals")
+
+
+@pytest.mark.gpu
+def test_main_cpp_from_the_frames_alone_with_orb_and_orb(tmp_path):
+    """DetectorType ORB + ExtractorType ORB (descriptorsmatcher.cpp:273-281, :336-342) with an OrbDetector block: compareWithNNDR
+    runs cv::ORB's own detector and descriptors on the GPU (K15) and the Hamming matcher (:64-67); the rest of main.cpp's
+    pipeline runs on what it found.  Keypoints and rows against the oracle restatement of cv::ORB::detectAndCompute (itself
+    identical to cv2 keypoint for keypoint), matches against the matcher oracle on the rows the adapter produced."""
+    from oracle import orb_detect_np as od
+    exe = build_pipeline_main()
+    r, pyramids, eps_m, cmpp = 32, 2, 0.05, 0.25
+    case = stereo_case(640, 480, 60, 1000, r)
+    tmp = str(tmp_path)
+    opts = """FeatureOptions:
+   DetectorType: ORB
+   DetectorMode: STATIC
+   OrbDetector:
+      NumFeatures: 3000
+      ScaleFactor: 1.2
+      NumLevels: 8
+   ExtractorType: ORB
+"""
+    _write_inputs(tmp, case, r, pyramids, eps_m, cmpp, feature_options=opts)
+    with open(os.path.join(tmp, "settings.yml")) as f:
+        yml = f.read().replace("epsilon: 0.55", "epsilon: 0.8")
+    with open(os.path.join(tmp, "settings.yml"), "w") as f:
+        f.write(yml)
+    env = dict(os.environ, FM3D_PENALTY="1", FM3D_NO_PATCH_FILES="1")
+    p = subprocess.run([exe, "-s", os.path.join(tmp, "settings.yml"), "-", os.path.join(tmp, "result.bin")],
+                       capture_output=True, text=True, env=env, cwd=tmp, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = _read_result(os.path.join(tmp, "result.bin"))
+    descs = []
+    for (k, d), img in zip(res["detected"], (case["scene"].img1, case["scene"].img2)):
+        K, D = od.detect_and_describe_orb(img, nfeatures=3000)
+        assert len(k) == len(K) and len(k) >= 2500
+        np.testing.assert_array_equal(k[:, :3].astype(np.float32), K[:, :3].astype(np.float32))
+        assert np.abs(k[:, 3] - K[:, 3]).max() < 1e-3
+        np.testing.assert_allclose(k[:, 4], K[:, 4], rtol=1e-6)
+        bits = np.unpackbits(d.astype(np.uint8) ^ D, axis=1).sum(1)
+        assert d.shape == (len(k), 32) and np.mean(bits == 0) >= 0.995 and bits.max() <= 2
+        descs.append(np.ascontiguousarray(d.astype(np.uint8)))
+    o_idx, o_dist = orc.knn2_hamming(descs[0], descs[1])
+    oq, ot, od_ = orc.nndr_filter(o_idx, o_dist, 0.8)
+    np.testing.assert_array_equal(res["matches"]["q"], oq)
+    np.testing.assert_array_equal(res["matches"]["t"], ot)
+    assert len(res["normals"]) == int((res["status"] == 0).sum())
+    print(f"ORB+ORB from the frames: {len(res['detected'][0][0])} / {len(res['detected'][1][0])} keypoints, {len(oq)} NNDR matches, "
+          f"{len(res['normals'])} refined normals")

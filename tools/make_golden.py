@@ -296,6 +296,32 @@ def sift_detect():
     np.savez_compressed(os.path.join(OUT, "sift_detect.npz"), **out)
 
 
+ORB_DETECT_PARAMS = {"default": dict(), "knobs": dict(nfeatures=1500, scaleFactor=1.3, nlevels=5)}
+
+
+def orb_detect():
+    """K15 fixtures: cv2.ORB_create(nfeatures, scaleFactor, nlevels).detectAndCompute (what cv::ORB(NumFeatures, ScaleFactor,
+    NumLevels) of descriptorsmatcher.cpp:273-279 / :325-330 runs as detector and extractor) on two frames: rows (x, y, size,
+    angle, response), the octave and the 32-byte descriptors, sorted by (octave, y, x) -- OpenCV's own order is whatever
+    std::nth_element leaves."""
+    import cv2
+    rng = np.random.default_rng(7500)
+    b = cv2.GaussianBlur(rng.integers(0, 256, (240, 320)).astype(np.float32), (0, 0), 1.5)
+    imgs = {"blobs": ((b - b.min()) / (b.max() - b.min()) * 255).astype(np.uint8),
+            "frame": synth.make_stereo_case(320, 240, 8, 99, pixels_ray=8, n_distractors=10)["scene"].img1}
+    out = {}
+    for name, img in imgs.items():
+        out[f"img_{name}"] = img
+        for pname, kw in ORB_DETECT_PARAMS.items():
+            kps, desc = cv2.ORB_create(**kw).detectAndCompute(img, None)
+            K = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float64).reshape(-1, 6)
+            order = np.lexsort((K[:, 0], K[:, 1], K[:, 5]))
+            out[f"kp_{name}_{pname}"] = K[order, :5].astype(np.float32)
+            out[f"oct_{name}_{pname}"] = K[order, 5].astype(np.int32)
+            out[f"desc_{name}_{pname}"] = desc[order]
+    np.savez_compressed(os.path.join(OUT, "orb_detect.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "--orb-only" in sys.argv:
@@ -308,6 +334,8 @@ if __name__ == "__main__":
         fast_keypoints()
     elif "--sift-detect-only" in sys.argv:
         sift_detect()
+    elif "--orb-detect-only" in sys.argv:
+        orb_detect()
     else:
         if "--sift-only" not in sys.argv:
             primitives()
@@ -318,5 +346,6 @@ if __name__ == "__main__":
         brisk_keypoints()
         orb_keypoints()
         sift_detect()
+        orb_detect()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
