@@ -1,7 +1,7 @@
 // fm3d_describe.cu -- K9: the descriptor of every rectified patch, one CTA per patch.
 //
 // Replaces DescriptorsMatcher::extractDescriptorsFromPatches
-// (DescriptorsMatcher/descriptorsmatcher.cpp:133-174) for ExtractorType SIFT (:246): ONE keypoint per
+// (DescriptorsMatcher/descriptorsmatcher.cpp:133-174) for ExtractorType SIFT (:302-314): ONE keypoint per
 // patch, at (floor(S/2), floor(S/2)), size = S, angle = -1, octave = 0, handed to
 // DescriptorExtractor::compute.  With a provided keypoint of octave 0 cv::SIFT builds a one-octave
 // pyramid without up-sampling (firstOctave = 0), so the descriptor is read from

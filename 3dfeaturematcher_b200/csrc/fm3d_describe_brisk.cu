@@ -2,7 +2,7 @@
 //
 // Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
 // DescriptorsMatcher::compareWithNNDR / compare / crosscompare
-// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType BRISK (:337-342:
+// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType BRISK (:343-349:
 // cv::BRISK(BriskDetector.Threshold, BriskDetector.Octaves): both knobs only steer BRISK's own detector, which the
 // reference never runs), the binary extractor that feeds the Hamming matcher (:64-67).  OpenCV is a third-party
 // dependency of the reference; the published algorithm (modules/features2d/src/brisk.cpp; Leutenegger et al. 2011) is

@@ -2,7 +2,7 @@
 //
 // Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
 // DescriptorsMatcher::compareWithNNDR / compare / crosscompare
-// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType SIFT (:246) and
+// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType SIFT (:302-314) and
 // keypoints of octave 0 (what cv::FastFeatureDetector produces, :215-222: size 7, angle -1).  With such
 // keypoints cv::SIFT::compute builds no scale space: every descriptor is read from
 //     base = GaussianBlur(float(gray), sigma = sqrt(1.6^2 - 0.5^2))            (createInitialImage)

@@ -2,7 +2,7 @@
 //
 // Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
 // DescriptorsMatcher::compareWithNNDR / compare / crosscompare
-// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType ORB (:325-330:
+// (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType ORB (:336-342:
 // cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels): the knobs steer ORB's own detector and pyramid, which a
 // provided keypoint of octave 0 -- what DetectorType FAST produces -- does not touch), the 32-byte binary rows the
 // north star's Hamming sweep is quoted on.  OpenCV is a third-party dependency of the reference; the published

@@ -2,7 +2,7 @@
 //
 // Replaces feature_detector_->detect + descriptor_extractor_->compute of DescriptorsMatcher::compareWithNNDR / compare /
 // crosscompare (DescriptorsMatcher/descriptorsmatcher.cpp:110-115, :91-96, :76-81) for DetectorType ORB + ExtractorType ORB
-// (:273-279, :325-330: cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels), everything else at cv::ORB's defaults).  The
+// (:273-279, :336-342: cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels), everything else at cv::ORB's defaults).  The
 // algorithm is OpenCV's (third party, unpinned in the reference; restated in oracle/orb_detect_np.py, which reproduces
 // cv2.ORB_create(...).detectAndCompute keypoint for keypoint):
 //   pyramid      level l = cv::resize(level l - 1, INTER_LINEAR_EXACT) to cvRound(w / s^l) x cvRound(h / s^l): 8.8 fixed-point

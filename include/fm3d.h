@@ -428,7 +428,7 @@ int fm3d_circular_neighborhoods(fm3d_ctx* ctx, const double* points, double* nor
 /* ---------------------------------------------------------- patch descriptors ---- */
 
 /* Replaces DescriptorsMatcher::extractDescriptorsFromPatches
- * (DescriptorsMatcher/descriptorsmatcher.cpp:133-174) for ExtractorType SIFT (:246): one keypoint
+ * (DescriptorsMatcher/descriptorsmatcher.cpp:133-174) for ExtractorType SIFT (:302-314): one keypoint
  * per patch at (floor(S/2), floor(S/2)) with size = S, angle = -1, octave = 0, response = 1,
  * described by cv::SIFT::compute (nOctaveLayers 3, sigma 1.6).  patches: n x S x S u8 as written by
  * fm3d_extract_patches; descriptors: n x 128 f32, integer-valued in [0, 255] (cv::SIFT's CV_32F
@@ -469,7 +469,7 @@ int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
                      float* angle, float* response, int32_t* octave, int* n);
 
 /* Replaces feature_detector_->detect followed by descriptor_extractor_->compute (DescriptorsMatcher/descriptorsmatcher.cpp:110-115,
- * :91-96, :76-81) for DetectorType ORB + ExtractorType ORB (:273-279, :325-330: cv::ORB(OrbDetector.NumFeatures, ScaleFactor,
+ * :91-96, :76-81) for DetectorType ORB + ExtractorType ORB (:273-279, :336-342: cv::ORB(OrbDetector.NumFeatures, ScaleFactor,
  * NumLevels), the other arguments at cv::ORB's defaults; fast_threshold = 20 is its default): the INTER_LINEAR_EXACT pyramid,
  * FAST + Harris ranking + intensity-centroid angles per level, rBRIEF rows on the blurred level images -- the keypoint SET and
  * the rows of cv::ORB::detectAndCompute; the order is (level, y, x) (OpenCV's is whatever std::nth_element leaves).  Outputs
@@ -483,7 +483,7 @@ int fm3d_detect_orb(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride,
 
 /* Replaces descriptor_extractor_->compute(frame, keypoints, descriptors) of
  * DescriptorsMatcher::compareWithNNDR / compare / crosscompare
- * (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType SIFT (:246,
+ * (DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) for ExtractorType SIFT (:302-314,
  * default octave layers 3 / sigma 1.6) and keypoints of octave 0 -- what DetectorType FAST produces
  * (:215-222: size 7, angle -1) -- for which cv::SIFT::compute reads every descriptor from
  * GaussianBlur(float(frame), sqrt(1.6^2 - 0.5^2)) without building a scale space.
@@ -507,7 +507,7 @@ int fm3d_describe_keypoints_sift_oct(fm3d_ctx* ctx, const uint8_t* img, int w, i
 /* The base image alone (createInitialImage): base is w x h f32, rows w floats apart, device memory. */
 int fm3d_sift_base_image_dev(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* base);
 
-/* The same call for ExtractorType BRISK (:337-342: cv::BRISK(BriskDetector.Threshold, BriskDetector.Octaves) -- both
+/* The same call for ExtractorType BRISK (:343-349: cv::BRISK(BriskDetector.Threshold, BriskDetector.Octaves) -- both
  * knobs only steer BRISK's own detector, which the reference does not run): the binary descriptors that the Hamming
  * matcher consumes (:64-67).
  *   kps                  n x 4 f32 as above
@@ -524,7 +524,7 @@ int fm3d_describe_keypoints_brisk_dev(fm3d_ctx* ctx, const uint8_t* img, int w, 
                                       const float* kps, int n, int compute_orientation, uint8_t* descriptors,
                                       uint8_t* kept, float* angles);
 
-/* The same call for ExtractorType ORB (:325-330: cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels); the knobs
+/* The same call for ExtractorType ORB (:336-342: cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels); the knobs
  * steer ORB's own detector and pyramid, which keypoints of octave 0 do not touch): 256-bit rBRIEF rows.
  *   kps            n x 4 f32 as above (octave 0; angle in degrees -- FAST's -1 is a rotation by -1 degree, as in cv::ORB)
  *   descriptors    n x 32 u8; kept n u8

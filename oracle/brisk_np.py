@@ -2,7 +2,7 @@
 
 Restates what descriptor_extractor_->compute(frame, keypoints, descriptors) computes in
 DescriptorsMatcher::compareWithNNDR / compare / crosscompare
-(DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) when ExtractorType is BRISK (:337-342:
+(DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) when ExtractorType is BRISK (:343-349:
 cv::BRISK(FeatureOptions.BriskDetector.Threshold, FeatureOptions.BriskDetector.Octaves); threshold and octaves
 only steer BRISK's own detector, which the reference does not use).  OpenCV is a third-party dependency of the
 reference (unpinned, 2.4.x era); the published algorithm restated here is cv::BRISK's descriptor stage

@@ -509,7 +509,7 @@ def project_groups(cam: Camera, img, group, image_id):
 
 
 # ---------------------------------------------------------------------------------------------
-# patch descriptors (DescriptorsMatcher/descriptorsmatcher.cpp:133-174, ExtractorType SIFT :246)
+# patch descriptors (DescriptorsMatcher/descriptorsmatcher.cpp:133-174, ExtractorType SIFT :302-314)
 def describe_patches_sift(patches):
     """extractDescriptorsFromPatches: one keypoint per patch at (floor(S/2), floor(S/2)), size = S,
     angle = -1, response = 1, octave = 0, class_id = 0 (:150-157), then

@@ -2,7 +2,7 @@
 
 Restates what feature_detector_->detect(frame, keypoints) followed by descriptor_extractor_->compute(frame, keypoints,
 descriptors) computes in DescriptorsMatcher::compareWithNNDR / compare / crosscompare (DescriptorsMatcher/
-descriptorsmatcher.cpp:110-115, :91-96, :76-81) when DetectorType and ExtractorType are ORB (:273-279, :325-330:
+descriptorsmatcher.cpp:110-115, :91-96, :76-81) when DetectorType and ExtractorType are ORB (:273-279, :336-342:
 cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels); the remaining arguments keep cv::ORB's defaults: edgeThreshold 31,
 firstLevel 0, WTA_K 2, HARRIS_SCORE, patchSize 31, fastThreshold 20).  OpenCV is a third-party dependency of the reference
 (unpinned, 2.4.x era); the published algorithm restated here is cv::ORB_Impl::detectAndCompute of the OpenCV 4.13 in this

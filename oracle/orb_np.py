@@ -2,7 +2,7 @@
 
 Restates what descriptor_extractor_->compute(frame, keypoints, descriptors) computes in
 DescriptorsMatcher::compareWithNNDR / compare / crosscompare
-(DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) when ExtractorType is ORB (:325-330:
+(DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) when ExtractorType is ORB (:336-342:
 cv::ORB(OrbDetector.NumFeatures, ScaleFactor, NumLevels); the three knobs steer ORB's own detector and pyramid, which a
 provided keypoint of octave 0 does not touch).  OpenCV is a third-party dependency of the reference (unpinned, 2.4.x
 era); the published algorithm restated here is cv::ORB's descriptor stage (Rublee et al., ICCV 2011;

@@ -2,7 +2,7 @@
 
 Restates what descriptor_extractor_->compute(frame, keypoints, descriptors) computes in
 DescriptorsMatcher::compareWithNNDR / compare / crosscompare
-(DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) when ExtractorType is SIFT (:246,
+(DescriptorsMatcher/descriptorsmatcher.cpp:114-115, :95-96, :80-81) when ExtractorType is SIFT (:302-314,
 cv::SIFT / cv::SiftDescriptorExtractor with the default 3 octave layers and sigma 1.6) and the keypoints
 come from a detector that leaves octave = 0 (FAST, :215-222: size 7, angle -1; also GFTT/Dense-like
 keypoints a caller injects).  OpenCV is a third-party dependency of the reference (unpinned, 2.4.x

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE -- CPU oracle for K9 (fm3d_describe_patches_sift), numpy only.
 
 Restates what DescriptorsMatcher::extractDescriptorsFromPatches
-(DescriptorsMatcher/descriptorsmatcher.cpp:133-174) computes when ExtractorType is SIFT (:246):
+(DescriptorsMatcher/descriptorsmatcher.cpp:133-174) computes when ExtractorType is SIFT (:302-314):
 cv::SIFT::compute on each patch with ONE provided keypoint at (floor(S/2), floor(S/2)), size S,
 angle -1, octave 0.  OpenCV is a third-party dependency of the reference (unpinned, 2.4.x era); the
 published algorithm restated here is cv::SIFT's (modules/features2d/src/sift.*, OpenCV 4.13 as

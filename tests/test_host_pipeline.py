@@ -357,7 +357,7 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_sift(tmp_path):
 
 @pytest.mark.gpu
 def test_main_cpp_from_the_frames_alone_with_fast_and_brisk(tmp_path):
-    """The same with ExtractorType BRISK (descriptorsmatcher.cpp:337-342; build/settings.yml carries its knobs): binary
+    """The same with ExtractorType BRISK (descriptorsmatcher.cpp:343-349; build/settings.yml carries its knobs): binary
     rows from K12, the Hamming matcher (:64-67), keypoints near the border erased as cv::BRISK::compute erases them."""
     from oracle import fast_np as fo
     from oracle import brisk_np as bn
@@ -414,7 +414,7 @@ def test_main_cpp_from_the_frames_alone_with_fast_and_brisk(tmp_path):
 
 @pytest.mark.gpu
 def test_main_cpp_from_the_frames_alone_with_fast_and_orb(tmp_path):
-    """The same with ExtractorType ORB (descriptorsmatcher.cpp:325-330): 32-byte rows from K13, the Hamming matcher,
+    """The same with ExtractorType ORB (descriptorsmatcher.cpp:336-342): 32-byte rows from K13, the Hamming matcher,
     keypoints within 31 pixels of the border erased as cv::ORB::compute erases them."""
     from oracle import fast_np as fo
     from oracle import orb_np as on

@@ -169,7 +169,7 @@ def test_fast_restatement_against_live_cv2():
 
 def test_sift_keypoint_restatement_against_live_cv2():
     """oracle/sift_kp_np.py against cv2.SIFT_create().compute on fresh images: FAST keypoints (size 7, angle -1,
-    what DetectorType FAST + ExtractorType SIFT of descriptorsmatcher.cpp:215-222, :246 hands to compute) and
+    what DetectorType FAST + ExtractorType SIFT of descriptorsmatcher.cpp:215-222, :302-314 hands to compute) and
     keypoints with arbitrary size / angle, including positions on the image border."""
     cv2 = pytest.importorskip("cv2")
     from oracle import sift_kp_np as sk
@@ -192,7 +192,7 @@ def test_sift_keypoint_restatement_against_live_cv2():
 
 def test_brisk_restatement_against_live_cv2():
     """oracle/brisk_np.py against cv2.BRISK_create().compute on a fresh image: FAST keypoints (what DetectorType FAST +
-    ExtractorType BRISK of descriptorsmatcher.cpp:215-222, :337-342 hands to compute) and sub-pixel keypoints of many
+    ExtractorType BRISK of descriptorsmatcher.cpp:215-222, :343-349 hands to compute) and sub-pixel keypoints of many
     sizes.  Survivors, bits and angles identical."""
     cv2 = pytest.importorskip("cv2")
     from oracle import brisk_np as bn

@@ -1,5 +1,5 @@
 """K15 -- cv::ORB's own detector + descriptors (DetectorType ORB + ExtractorType ORB, DescriptorsMatcher/descriptorsmatcher.cpp:273-279,
-:325-330, called at :110-115): the oracle restatement against the committed outputs of cv2.ORB_create(...).detectAndCompute, and
+:336-342, called at :110-115): the oracle restatement against the committed outputs of cv2.ORB_create(...).detectAndCompute, and
 the GPU path (fm3d_detect_orb) against the same golden vectors.
 
 Integer work up to the Harris measure and the angle (float formulas on integer sums): the keypoint SET (level, level position)

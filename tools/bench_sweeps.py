@@ -290,6 +290,28 @@ def sift_detect_sweep(ctx, stream):
         print(json.dumps(out), flush=True)
 
 
+def orb_detect_sweep(ctx, stream):
+    """K15 alone: cv::ORB's detector + descriptors (fm3d_detect_orb, host buffers in and out) on rendered frames of 720p and 4K;
+    cv2.ORB.detectAndCompute on this box's host cores beside it."""
+    import importlib
+    synth = importlib.import_module("3dfeaturematcher_b200.synth")
+    for W, H, nf in ((1280, 720, 5000), (3840, 2160, 20000)):
+        img = synth.make_stereo_case(W, H, 20, 1001, pixels_ray=32)["scene"].img1
+        ctx.detect_orb(img, nfeatures=nf)
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter(); K, D = ctx.detect_orb(img, nfeatures=nf); t.append(time.perf_counter() - t0)
+        out = {"case": "orb_detect_and_describe", "W": W, "H": H, "nfeatures": nf, "keypoints": int(len(K)), "ms_host_to_host": 1e3 * min(t)}
+        try:
+            import cv2
+            o = cv2.ORB_create(nfeatures=nf)
+            t0 = time.perf_counter(); kp, d = o.detectAndCompute(img, None); t1 = time.perf_counter()
+            out.update({"cv2_keypoints": len(kp), "cv2_ms": 1e3 * (t1 - t0), "cv2_threads": cv2.getNumThreads()})
+        except ImportError:
+            pass
+        print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = api.Context(0)
@@ -306,6 +328,8 @@ if __name__ == "__main__":
         frontend_sweep(ctx, stream)
     if which in ("all", "sift_detect"):
         sift_detect_sweep(ctx, stream)
+    if which in ("all", "orb_detect"):
+        orb_detect_sweep(ctx, stream)
     if which in ("c3",):
         c3_pipeline(ctx, stream)
     ctx.close()

@@ -190,7 +190,7 @@ def sift_keypoints():
 
 def brisk_keypoints():
     """K12 fixtures: cv2.BRISK_create(25, 0).compute (descriptor_extractor_->compute of descriptorsmatcher.cpp:114-115
-    with ExtractorType BRISK, :337-342, knobs of build/settings.yml) on the FAST keypoints (threshold 20, non-maximum
+    with ExtractorType BRISK, :343-349, knobs of build/settings.yml) on the FAST keypoints (threshold 20, non-maximum
     suppression, at most 400 per image) of the images of fast_keypoints.npz, and on keypoints with sub-pixel
     positions and sizes 3 ... 36 (scale indices 0 ... 30).  cv::BRISK removes keypoints near the border: `kept`
     holds the indices of the survivors, `d` / `a` their rows and angles."""
@@ -226,7 +226,7 @@ def brisk_keypoints():
 
 def orb_keypoints():
     """K13 fixtures: cv2.ORB_create().compute (descriptor_extractor_->compute of descriptorsmatcher.cpp:114-115 with
-    ExtractorType ORB, :325-330) on the FAST keypoints (threshold 20, non-maximum suppression, at most 500 per image) of
+    ExtractorType ORB, :336-342) on the FAST keypoints (threshold 20, non-maximum suppression, at most 500 per image) of
     the images of fast_keypoints.npz and on octave-0 keypoints with sub-pixel positions and arbitrary angles.  cv::ORB
     removes keypoints within 31 pixels of the border: `kept` holds the indices of the survivors (carried through
     KeyPoint::class_id), `d` their rows."""
@@ -301,7 +301,7 @@ ORB_DETECT_PARAMS = {"default": dict(), "knobs": dict(nfeatures=1500, scaleFacto
 
 def orb_detect():
     """K15 fixtures: cv2.ORB_create(nfeatures, scaleFactor, nlevels).detectAndCompute (what cv::ORB(NumFeatures, ScaleFactor,
-    NumLevels) of descriptorsmatcher.cpp:273-279 / :325-330 runs as detector and extractor) on two frames: rows (x, y, size,
+    NumLevels) of descriptorsmatcher.cpp:273-279 / :336-342 runs as detector and extractor) on two frames: rows (x, y, size,
     angle, response), the octave and the 32-byte descriptors, sorted by (octave, y, x) -- OpenCV's own order is whatever
     std::nth_element leaves."""
     import cv2
