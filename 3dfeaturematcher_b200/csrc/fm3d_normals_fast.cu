@@ -75,9 +75,6 @@ namespace {
 #ifndef FM3D_NORMALS_L2HINT
 #define FM3D_NORMALS_L2HINT 0
 #endif
-#ifndef FM3D_NORMALS_LDCG
-#define FM3D_NORMALS_LDCG 0
-#endif
 constexpr int FAST_NT = FM3D_NORMALS_NT;
 constexpr float FLOOR_MAGIC = 12582912.0f;          // 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x)
 constexpr unsigned FLOOR_MAGIC_BITS = 0x4B400000u;
@@ -347,19 +344,6 @@ __device__ __forceinline__ f2 ld_scratch(const f2* a, uint64_t pol) {
     return v;
 }
 #define LD_SCRATCH(ptr) ld_scratch((ptr), l2pol)
-#elif FM3D_NORMALS_LDCG
-// the scratch stream is read once per pass: cache it in L2 only (ld.global.cg)
-__device__ __forceinline__ ulonglong2 ld_cg(const ulonglong2* a) {
-    ulonglong2 v;
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(a));
-    return v;
-}
-__device__ __forceinline__ f2 ld_cg(const f2* a) {
-    f2 v;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(a));
-    return v;
-}
-#define LD_SCRATCH(ptr) ld_cg(ptr)
 #else
 #define LD_SCRATCH(ptr) (*(ptr))
 #endif
