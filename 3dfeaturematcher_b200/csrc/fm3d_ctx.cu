@@ -214,6 +214,9 @@ static int* fm3d_option_slot(fm3d_ctx* ctx, const char* key) {
     if (!strcmp(key, "geometry_f32")) return &ctx->opt_geometry_f32;
     if (!strcmp(key, "matcher_tensor")) return &ctx->opt_matcher_tensor;
     if (!strcmp(key, "matcher_sp_tile")) return &ctx->opt_matcher_sp_tile;
+    if (!strcmp(key, "matcher_splits")) return &ctx->opt_matcher_splits;
+    if (!strcmp(key, "matcher_persistent")) return &ctx->opt_matcher_persistent;
+    if (!strcmp(key, "matcher_min_tiles")) return &ctx->opt_matcher_min_tiles;
     if (!strcmp(key, "lm_patience")) return &ctx->opt_lm_patience;
     if (!strcmp(key, "normals_threads")) return &ctx->opt_normals_threads;
     if (!strcmp(key, "normals_tma")) return &ctx->opt_normals_tma;

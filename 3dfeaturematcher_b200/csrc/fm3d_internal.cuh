@@ -44,6 +44,9 @@ struct fm3d_ctx {
     // options
     int opt_geometry_f32 = 0;
     int opt_matcher_tensor = 1;
+    int opt_matcher_persistent = 1;  // integer tensor-core matcher: one persistent CTA per SM over equal ranges of the (query tile, train tile) sequence; 0 = one CTA per (query tile, train split)
+    int opt_matcher_min_tiles = 1;   // persistent matcher: fewest train tiles worth a CTA of its own (small problems use fewer CTAs)
+    int opt_matcher_splits = 0;      // tensor-core matchers, one CTA per item: train splits per query tile; 0 = round 1's rule (split only below 2 CTAs per SM)
     int opt_matcher_sp_tile = 128;   // real-valued tensor filter at dim > 80: 128 = two stages of 128 train rows (default, measured faster), 256 = one stage of 256
     int opt_lm_patience = 100;
     int opt_normals_threads = 512;

@@ -555,6 +555,198 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
     }
 }
 
+// The same contraction as a PERSISTENT kernel: one CTA per SM for the whole launch, balanced to one tile.
+// Why not more, smaller CTAs: a streaming top-2 starts cold -- until a row's running second-best is small, nearly every chunk
+// of 32 columns holds a value that beats it for one of the warp's 32 rows and takes the slow path; the expected number of such
+// columns is ~ 64 ln(n / 64) per warp over n columns, 13-25 us (15-28 tile times) however short the CTA's train range is.
+// Splitting the train set for balance therefore never paid (`matcher_splits`, profiles/r02y_match_splits_*.jsonl: 50 000 x
+// 50 000 with 1 / 2 / 3 / 4 / 6 splits 0.62 / 0.71 / 0.71 / 0.79 / 0.88 ms), and one CTA per query tile leaves the last wave
+// partly empty (157 query tiles on 148 SMs: two waves for 1.06 waves of work).  Here the (query tile, train tile) pairs are
+// laid out query-tile-major and cut into gridDim.x EQUAL contiguous ranges: a CTA contracts the tail of one query tile's train
+// sequence, whole query tiles, and the head of another ("pieces"), with ~ (query tiles / SMs) + 1 cold starts.  TMEM,
+// barriers and pipelines are set up once; the train-tile ring and the two accumulators run across piece boundaries (global
+// tile counter), the query tile is double-buffered and the next piece's is fetched while the current one is contracted.
+// The pieces of a query tile belong to consecutive CTAs and fill list slots 0, 1, ...; the CTA of the last piece marks the
+// slots above as empty.  Same arithmetic, same result bits.  (Measured and dropped: whole query tiles first, all CTAs walking
+// the train set in step, and ranges only for the remainder -- every SM asks L2 for the same train tile at the same moment:
+// 8.0 ms against 7.4 at 200 000 x 200 000, 1.95 against 1.91 at 100 000; inserting the hit columns from the registers,
+// one vote per group of four columns, instead of re-reading them from TMEM: 5-15 % slower at every size.)
+constexpr int TCP_SMEM = 2 * TC_A_BYTES + TC_STAGES * TC_B_BYTES + 256;
+
+// the CTA whose range [c * total / G, (c + 1) * total / G) holds flattened tile y
+__host__ __device__ inline int tcp_cta_of(long long y, long long total, int G) { return (int)(((y + 1) * G - 1) / total); }
+
+struct TcpPieces {                // the pieces of one CTA, in order; every role walks its own copy
+    int G, cta, nt_tiles;
+    long long total, T, T1;
+    __device__ TcpPieces(int q_tiles, int nt_tiles_) {
+        G = gridDim.x; cta = blockIdx.x; nt_tiles = nt_tiles_;
+        total = (long long)q_tiles * nt_tiles;             // the host launches G <= total CTAs: no range is empty
+        T = (long long)cta * total / G;
+        T1 = (long long)(cta + 1) * total / G;
+    }
+    __device__ bool next(int& qtile, int& tile_lo, int& ntiles, int& slot) {
+        if (T >= T1) return false;
+        qtile = (int)(T / nt_tiles);
+        tile_lo = (int)(T - (long long)qtile * nt_tiles);
+        const long long n = min((long long)(nt_tiles - tile_lo), T1 - T);
+        ntiles = (int)n;
+        slot = cta - tcp_cta_of((long long)qtile * nt_tiles, total, G);
+        T += n;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int q_tiles, int nt_tiles,
+                           int lists_per_half, Cand* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                                  // [2]
+    uint8_t* sB = smem + 2 * TC_A_BYTES;                 // [TC_STAGES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TC_A_BYTES + TC_STAGES * TC_B_BYTES);
+    uint64_t* a_full = bars + 0;                         // [2]
+    uint64_t* a_empty = bars + 2;                        // [2]
+    uint64_t* b_full = bars + 4;                         // [TC_STAGES]
+    uint64_t* b_empty = bars + 4 + TC_STAGES;
+    uint64_t* acc_full = bars + 4 + 2 * TC_STAGES;       // [2]
+    uint64_t* acc_empty = bars + 6 + 2 * TC_STAGES;      // [2]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 8 + 2 * TC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 2; a++) { mbar_init(&a_full[a], 1); mbar_init(&a_empty[a], 1); }
+        for (int st = 0; st < TC_STAGES; st++) { mbar_init(&b_full[st], 1); mbar_init(&b_empty[st], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 32 * TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        const uint32_t ncols = 512;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ===== producer: query tiles into the two A buffers (one piece ahead), train tiles through the ring
+        if (lane == 0) {
+            int ka = 0, gi = 0;                          // query tiles issued, train tiles issued
+            auto issue_a = [&](int qtile) {
+                const int ab = ka & 1;
+                mbar_wait(&a_empty[ab], (((uint32_t)(ka >> 1)) & 1u) ^ 1u);
+                mbar_expect_tx(&a_full[ab], TC_A_BYTES);
+                bulk_g2s(sA + (size_t)ab * TC_A_BYTES, qa + (size_t)qtile * TC_A_BYTES, TC_A_BYTES, &a_full[ab]);
+                ka++;
+            };
+            TcpPieces it_p(q_tiles, nt_tiles);
+            int qtile, tile_lo, ntiles, slot;
+            bool have = it_p.next(qtile, tile_lo, ntiles, slot);
+            if (have) issue_a(qtile);
+            while (have) {
+                int q_n, lo_n, n_n, slot_n;
+                const bool more = it_p.next(q_n, lo_n, n_n, slot_n);
+                // the next query tile goes out once train tile 2 of this piece may be issued: by then the MMAs of the previous
+                // piece have completed (its stages came back), so the A buffer it used is free and the wait returns at once
+                const int a_at = ntiles > 2 ? 2 : ntiles - 1;
+                for (int it = 0; it < ntiles; it++, gi++) {
+                    const int st = gi % TC_STAGES;
+                    const uint32_t ph = (uint32_t)(gi / TC_STAGES) & 1u;
+                    mbar_wait(&b_empty[st], ph ^ 1u);
+                    mbar_expect_tx(&b_full[st], TC_B_BYTES);
+                    bulk_g2s(sB + (size_t)st * TC_B_BYTES, tb + (size_t)(tile_lo + it) * TC_B_BYTES, TC_B_BYTES, &b_full[st]);
+                    if (it == a_at && more) issue_a(q_n);
+                }
+                have = more; qtile = q_n; tile_lo = lo_n; ntiles = n_n; slot = slot_n;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            int ka = 0, gi = 0;
+            TcpPieces it_p(q_tiles, nt_tiles);
+            int qtile, tile_lo, ntiles, slot;
+            for (; it_p.next(qtile, tile_lo, ntiles, slot); ka++) {
+                const int ab = ka & 1;
+                mbar_wait(&a_full[ab], ((uint32_t)(ka >> 1)) & 1u);
+                const uint32_t a_addr = s32(sA + (size_t)ab * TC_A_BYTES);
+                for (int it = 0; it < ntiles; it++, gi++) {
+                    const int st = gi % TC_STAGES, acc = gi & 1;
+                    mbar_wait(&b_full[st], (uint32_t)(gi / TC_STAGES) & 1u);
+                    mbar_wait(&acc_empty[acc], ((uint32_t)(gi >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t b_addr = s32(sB + (size_t)st * TC_B_BYTES);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+#pragma unroll
+                    for (int k = 0; k < TC_KCHUNKS / 2; k++)
+                        umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 256), umma_smem_desc(b_addr + k * 256), idesc, k > 0);
+                    umma_commit(&b_empty[st]);
+                    umma_commit(&acc_full[acc]);
+                }
+                umma_commit(&a_empty[ab]);               // the query tile buffer is free once these MMAs have read it
+            }
+        }
+    } else {
+        // ===== epilogue (as in match_tc_kernel), one partial list per piece
+        const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = lane_grp * 32 + lane;
+        int gi = 0;
+        TcpPieces it_p(q_tiles, nt_tiles);
+        int qtile, tile_lo, ntiles, slot;
+        while (it_p.next(qtile, tile_lo, ntiles, slot)) {
+            float m0 = INFINITY, m1 = INFINITY;
+            int i0 = 0x7fffffff, i1 = 0x7fffffff;
+            for (int it = 0; it < ntiles; it++, gi++) {
+                const int acc = gi & 1;
+                mbar_wait(&acc_full[acc], (uint32_t)(gi >> 1) & 1u);
+                tc_fence_after();
+                const int col_base = (tile_lo + it) * TC_N;
+                const uint32_t t0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * TC_N);
+                constexpr int CH = TC_N / 32 / TC_EPI_HALVES;
+                const int c_lo = half * CH;
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(t0 + (uint32_t)(c_lo * 32), va);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int c = c_lo; c < c_lo + CH; c += 2) {
+                    tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
+                    top2_chunk(va, t0 + (uint32_t)(c * 32), col_base + c * 32, m0, i0, m1, i1);
+                    tmem_ld_wait();
+                    if (c + 2 < c_lo + CH) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+                    top2_chunk(vb, t0 + (uint32_t)((c + 1) * 32), col_base + (c + 1) * 32, m0, i0, m1, i1);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[acc]);
+            }
+            const int qrow = qtile * TC_M + row;
+            if (qrow < nq) {
+                Cand* o = partial + ((size_t)(slot * TC_EPI_HALVES + half) * nq + qrow) * 2;
+                o[0].d = m0; o[0].idx = i0;
+                o[1].d = m1; o[1].idx = i1;
+                if (tile_lo + ntiles == nt_tiles) {      // last piece of the query tile: the list slots above stay empty
+                    for (int sl = slot + 1; sl < lists_per_half; sl++) {
+                        Cand* e = partial + ((size_t)(sl * TC_EPI_HALVES + half) * nq + qrow) * 2;
+                        e[0].d = INFINITY; e[0].idx = 0x7fffffff;
+                        e[1].d = INFINITY; e[1].idx = 0x7fffffff;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        const uint32_t ncols = 512;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Tensor-core path for REAL-VALUED float descriptors (SURF, RootSIFT, learned descriptors; dim <= 128):
@@ -919,6 +1111,18 @@ int pick_splits(int work_tiles, int nt_tiles, int sms, int* tiles_per_split) {
     return eff > 0 ? eff : 1;
 }
 
+// Train splits of the one-CTA-per-item tensor-core kernels: round 1's rule (split only below 2 CTAs per SM), or as many as
+// `forced` > 0 says (measurements: every split costs another cold start of the streaming top-2, see match_tc_persistent_kernel).
+int pick_splits_waves(int q_tiles, int nt_tiles, int sms, int forced, int* tiles_per_split) {
+    if (forced <= 0) return pick_splits(q_tiles, nt_tiles, sms / 2 + 1, tiles_per_split);
+    int best = forced > nt_tiles ? nt_tiles : forced;
+    if (best < 1) best = 1;
+    *tiles_per_split = (nt_tiles + best - 1) / best;
+    if (*tiles_per_split < 1) *tiles_per_split = 1;
+    const int eff = (nt_tiles + *tiles_per_split - 1) / *tiles_per_split;
+    return eff > 0 ? eff : 1;
+}
+
 // exact CUDA-core path (K1')
 int knn2_f32_generic(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, int32_t* idx, float* dist) {
     const int sms = ctx->prop.multiProcessorCount;
@@ -960,14 +1164,37 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         {
             const int q_tiles = nq_pad / TC_M, nt_tiles = nt_pad / TC_N;
             int tps = 1;
-            const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
+            // persistent CTAs over equal ranges of the flattened (query tile, train tile) sequence (default), or one CTA per
+            // (query tile, train split) with round 1's split rule (`matcher_persistent` = 0; `matcher_splits` forces the splits)
+            const bool persistent = ctx->opt_matcher_persistent != 0 && ctx->opt_matcher_splits == 0 &&
+                                    (size_t)TCP_SMEM <= ctx->prop.sharedMemPerBlockOptin;
             Cand* partial = nullptr;
-            if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)splits * TC_EPI_HALVES * nq, (void**)&partial)) return rc;
-            FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-            dim3 grid(q_tiles, splits);
-            match_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, partial);
+            int lists = 0;
+            if (persistent) {
+                // CTAs: every SM, or as many as get `matcher_min_tiles` tiles each
+                const long long total = (long long)q_tiles * nt_tiles;
+                const int min_tiles = ctx->opt_matcher_min_tiles > 0 ? ctx->opt_matcher_min_tiles : 1;
+                long long G = total / min_tiles;
+                G = G < 1 ? 1 : (G > sms ? sms : G);
+                int pieces = 1;                          // most CTAs a query tile's train sequence is cut over (the kernel's arithmetic)
+                for (int qt = 0; qt < q_tiles; qt++) {
+                    const int c0 = tcp_cta_of((long long)qt * nt_tiles, total, (int)G), c1 = tcp_cta_of((long long)(qt + 1) * nt_tiles - 1, total, (int)G);
+                    if (c1 - c0 + 1 > pieces) pieces = c1 - c0 + 1;
+                }
+                lists = pieces * TC_EPI_HALVES;
+                if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)lists * nq, (void**)&partial)) return rc;
+                FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
+                match_tc_persistent_kernel<<<(int)G, TC_THREADS, TCP_SMEM, ctx->stream>>>(ops, ops + ba, nq, q_tiles, nt_tiles, pieces, partial);
+            } else {
+                const int splits = pick_splits_waves(q_tiles, nt_tiles, sms, ctx->opt_matcher_splits != 0 ? ctx->opt_matcher_splits : -1, &tps);
+                lists = splits * TC_EPI_HALVES;
+                if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)lists * nq, (void**)&partial)) return rc;
+                FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+                dim3 grid(q_tiles, splits);
+                match_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, partial);
+            }
             FM3D_LAUNCH_CHECK(ctx);
-            finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, splits * TC_EPI_HALVES, nq, nt, idx, dist);
+            finalize_f32_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(partial, lists, nq, nt, idx, dist);
             FM3D_LAUNCH_CHECK(ctx);
             int h_flag = 0;
             if (int rc = fm3d_d2h(ctx, &h_flag, flag, sizeof(int))) return rc;
@@ -997,7 +1224,7 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         FM3D_LAUNCH_CHECK(ctx);
         const int q_tiles = nq_pad / SP_M, nt_tiles = nt_pad / SP_N;
         int tps = 1;
-        const int splits = pick_splits(q_tiles, nt_tiles, sms / 2 + 1, &tps);
+        const int splits = pick_splits_waves(q_tiles, nt_tiles, sms, ctx->opt_matcher_splits != 0 ? ctx->opt_matcher_splits : -1, &tps);
         Cand4* partial4 = nullptr;
         if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * SP_EPI_HALVES * nq, (void**)&partial4)) return rc;
         int32_t* flagged = nullptr;

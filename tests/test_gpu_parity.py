@@ -83,13 +83,45 @@ def _check_knn(idx, dist, o_idx, o_dist):
     np.testing.assert_array_equal(dist, o_dist)
 
 
-@pytest.mark.parametrize("nq,nt", [(300, 360), (1, 1), (5, 2), (1000, 1300), (129, 257), (2048, 4096)])
+@pytest.mark.parametrize("nq,nt", [(300, 360), (1, 1), (5, 2), (1000, 1300), (129, 257), (2048, 4096), (1000, 60_000), (19_072, 1_700)])
 def test_match_f32_integer_descriptors_tensor_path(ctx, nq, nt):
     q, t, _ = synth.make_float_descriptors(nq, max(nt - nq, 0), 7 + nq)
     t = t[:nt]
     ctx.set_option("matcher_tensor", 1)
     idx, dist = ctx.match_knn2_f32(q, t)
     o_idx, o_dist = orc.knn2_f32(q, t, threads=8)
+    _check_knn(idx, dist, o_idx, o_dist)
+
+
+_PERSISTENT_CASE = {}
+
+
+def _persistent_case():
+    if not _PERSISTENT_CASE:
+        q, t, _ = synth.make_float_descriptors(40_000, 0, 4711)     # 313 query tiles x 12 train tiles
+        t = t[:3_000]
+        _PERSISTENT_CASE["v"] = (q, t) + tuple(orc.knn2_f32(q, t, threads=8))
+    return _PERSISTENT_CASE["v"]
+
+
+@pytest.mark.parametrize("persistent,splits,min_tiles", [(1, 0, 1), (1, 0, 7), (1, 0, 40), (1, 0, 5000), (0, 0, 1), (0, 3, 1), (0, 12, 1)])
+def test_match_f32_tensor_path_persistent_pieces_and_splits(ctx, persistent, splits, min_tiles):
+    """The persistent tensor-core matcher cuts the (query tile, train tile) sequence into equal ranges: a CTA contracts the
+    tail of one query tile, whole query tiles and the head of another back to back (query tile double buffer, train ring and
+    accumulators running across the boundaries), the lists of a query tile come from consecutive CTAs.  313 query tiles x 12
+    train tiles on every SM (25 tiles per CTA), on 93 CTAs (`matcher_min_tiles` 40) and on a single one; bit-exact against
+    the oracle, and so is the one-CTA-per-(query tile, split) kernel with 1, 3 and 12 splits."""
+    q, t, o_idx, o_dist = _persistent_case()
+    ctx.set_option("matcher_tensor", 1)
+    ctx.set_option("matcher_persistent", persistent)
+    ctx.set_option("matcher_splits", splits)
+    ctx.set_option("matcher_min_tiles", min_tiles)
+    try:
+        idx, dist = ctx.match_knn2_f32(q, t)
+    finally:
+        ctx.set_option("matcher_persistent", 1)
+        ctx.set_option("matcher_splits", 0)
+        ctx.set_option("matcher_min_tiles", 1)
     _check_knn(idx, dist, o_idx, o_dist)
 
 

@@ -50,6 +50,42 @@ def match_sweep(ctx, stream, sizes):
                           "note": "POPC roofline 4.54e12/s measured with tools/micro/popc_rate.cu (16 lanes/clk/SM)"}), flush=True)
 
 
+def match_splits_sweep(ctx, stream):
+    """The integer tensor-core matcher: one CTA per (query tile, train split) with round 1's split rule (`matcher_persistent`
+    0; `matcher_splits` > 0 forces the splits) against the persistent kernel over equal tile ranges (`matcher_min_tiles` =
+    fewest tiles worth a CTA); results are checked to be identical for every choice."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1003)
+    small = ((0, 0, 2), (1, 0, 1), (1, 0, 2), (1, 0, 4), (0, 0, 2), (1, 0, 2))
+    big = ((1, 0, 2), (0, 0, 2), (1, 0, 2), (0, 0, 2), (1, 0, 2), (0, 0, 2))       # alternating: the later launches of a size run on a warmer chip
+    for nq, nt, cases in ((300, 360, small), (1000, 1200, small), (2000, 2400, small), (5000, 6000, small), (5000, 48000, small), (10000, 10000, small),
+                          (20000, 24000, small), (50000, 50000, big), (100000, 100000, big), (150000, 150000, big), (200000, 200000, big)):
+        with torch.cuda.stream(stream):
+            t = torch.randint(0, 256, (nt, 128), device=dev, generator=g).float()
+            q = (t[torch.randperm(nt, device=dev, generator=g)[:nq]] + torch.randint(-6, 7, (nq, 128), device=dev, generator=g).float()).clamp_(0, 255)
+            idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+            dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+        stream.synchronize()
+        ref = None
+        for pers, f, mt in cases:
+            ctx.set_option("matcher_persistent", pers)
+            ctx.set_option("matcher_splits", f)
+            ctx.set_option("matcher_min_tiles", mt)
+            idx.fill_(-7); stream.synchronize()
+            ms = timed(stream, lambda: ctx.match_knn2_f32_dev(q.data_ptr(), nq, t.data_ptr(), nt, 128, idx.data_ptr(), dist.data_ptr()), 5 if nq <= 50000 else 3)
+            got = (idx.cpu().numpy().copy(), dist.cpu().numpy().copy())
+            if ref is None:
+                ref = got
+            same = bool((got[0] == ref[0]).all() and (got[1] == ref[1]).all())
+            tf = 256.0 * nq * nt / (ms * 1e-3) / 1e12
+            print(json.dumps({"case": "match_f32_sift128_tcgen05_splits", "lib": os.environ.get("FM3D_LIB", "default"), "nq": nq, "nt": nt, "matcher_persistent": pers,
+                              "matcher_splits": f, "matcher_min_tiles": mt, "ms": ms,
+                              "tflops": tf, "frac_of_measured_bf16_peak": tf / PEAKS.get("bf16_tflops", 1590.0), "same_as_first": same}), flush=True)
+        ctx.set_option("matcher_splits", 0)
+        ctx.set_option("matcher_persistent", 1)
+        ctx.set_option("matcher_min_tiles", 1)
+
+
 def normals_stress(ctx, stream, n_feat):
     dev = torch.device("cuda", 0)
     for r in (32, 64, 128):
@@ -330,6 +366,8 @@ if __name__ == "__main__":
         sift_detect_sweep(ctx, stream)
     if which in ("all", "orb_detect"):
         orb_detect_sweep(ctx, stream)
+    if which in ("splits",):
+        match_splits_sweep(ctx, stream)
     if which in ("c3",):
         c3_pipeline(ctx, stream)
     ctx.close()

@@ -25,11 +25,15 @@ for pen in (1, 0):
         for k, v in {**base, **cfg}.items(): ctx.set_option(k, v)
         fn = lambda: ctx.optimize_normals_dev(xyz.data_ptr(), n, 64, 1e-10, pen, normals.data_ptr(), status.data_ptr(), nfev.data_ptr(), npen.data_ptr(), cost.data_ptr())
         fn(); stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream); fn(); fn(); e1.record(stream)
-        stream.synchronize()
-        ms = e0.elapsed_time(e1) / 2
+        times = []
+        for _ in range(int(os.environ.get("AB_REPS", "1"))):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream); fn(); fn(); e1.record(stream)
+            stream.synchronize()
+            times.append(e0.elapsed_time(e1) / 2)
+        ms = float(np.median(times))
+        if len(times) > 1: print(f"   [{os.environ.get('FM3D_LIB', 'default lib')}] launches (ms, pairs): min {min(times):.3f} median {ms:.3f} max {max(times):.3f}", flush=True)
         st = ctx.normals_stats() if cfg.get("normals_fast", 1) else {}
         nf = nfev.cpu().numpy(); nr = normals.cpu().numpy()
         gt = angle_deg(nr, case["normal"])
