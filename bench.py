@@ -47,8 +47,8 @@ FLOP_EXEC_VALUE = 58.0        # executed by normals_fast_kernel per pixel of a v
 FLOP_EXEC_JAC = 113.0         # ... of a value + analytic-Jacobian pass (67 packed ops per pixel pair)
 SEED = 1001
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of normals_fast_kernel on this workload (ncu --set full)
-NORMALS_TRAFFIC_BYTES = 0.7471e9
-NORMALS_TRAFFIC_SOURCE = "profiles/r02m_normals_pp_kernel_ncu_raw_selected.csv: 182 MB read + 565 MB written, the ray scratch leaving L2"
+NORMALS_TRAFFIC_BYTES = 0.7585e9
+NORMALS_TRAFFIC_SOURCE = "profiles/r02y_normals_pp_kernel_ncu_raw_selected.csv (the kernel as benched, 11.85 ms under ncu): 195 MB read + 564 MB written, the ray scratch leaving L2"
 
 
 def log(*a):
