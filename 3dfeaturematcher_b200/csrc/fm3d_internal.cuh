@@ -43,6 +43,7 @@ struct fm3d_ctx {
     std::string err;
     // options
     int opt_geometry_f32 = 0;
+    int matcher_expect_integer = 1;  // verdict of the last 128-d float matching call: 1 = launch the integer contraction without waiting for the operand check
     int opt_matcher_tensor = 1;
     int opt_matcher_persistent = 1;  // integer tensor-core matcher: one persistent CTA per SM over equal ranges of the (query tile, train tile) sequence; 0 = one CTA per (query tile, train split)
     int opt_matcher_min_tiles = 1;   // persistent matcher: fewest train tiles worth a CTA of its own (small problems use fewer CTAs)

@@ -773,6 +773,7 @@ struct SpLayout {
     int kchunks;        // 2 * half_chunks + 2
     int group_bytes;    // kchunks * 128 (8 rows)
     int a_bytes, b_bytes, stages, smem;
+    int a_bufs, smem_persistent;
 };
 inline SpLayout sp_layout(int dim, size_t smem_optin, int n_tile_option) {
     SpLayout L;
@@ -790,6 +791,10 @@ inline SpLayout sp_layout(int dim, size_t smem_optin, int n_tile_option) {
         L.stages = 2;
     }
     L.smem = L.a_bytes + L.stages * L.b_bytes + 256;
+    // persistent kernel: a second query-tile buffer where it fits (dim <= 80), else the query tile of a piece is fetched
+    // when the previous piece has been contracted
+    L.a_bufs = (size_t)2 * L.a_bytes + (size_t)L.stages * L.b_bytes + 256 <= smem_optin ? 2 : 1;
+    L.smem_persistent = L.a_bufs * L.a_bytes + L.stages * L.b_bytes + 256;
     return L;
 }
 
@@ -1035,6 +1040,168 @@ match_sp_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
     }
 }
 
+// match_sp_kernel as a persistent kernel over equal ranges of the (query tile, train tile) sequence: see
+// match_tc_persistent_kernel (the top-4 of the filter starts even colder than a top-2).  Two query-tile buffers where shared
+// memory allows (dim <= 80); with one (dim 128: 68 KB query tile + two 68 KB train stages) the query tile of a piece goes
+// out right after the piece's first train tile, as soon as the MMAs of the previous piece have read the buffer.
+template <int SP_N>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+match_sp_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int q_tiles, int nt_tiles,
+                           int lists_per_half, int ksteps, const SpLayout lay, Cand4* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int SP_A_BYTES = lay.a_bytes, SP_B_BYTES = lay.b_bytes, SP_STAGES = lay.stages, SP_GROUP_BYTES = lay.group_bytes;
+    const int NBUF = lay.a_bufs;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)NBUF * SP_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NBUF * SP_A_BYTES + (size_t)SP_STAGES * SP_B_BYTES);
+    uint64_t* a_full = bars + 0;            // [2]
+    uint64_t* a_empty = bars + 2;           // [2]
+    uint64_t* b_full = bars + 4;            // [2]
+    uint64_t* b_empty = bars + 6;           // [2]
+    uint64_t* acc_full = bars + 8;          // [2]
+    uint64_t* acc_empty = bars + 10;        // [2]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 2; a++) { mbar_init(&a_full[a], 1); mbar_init(&a_empty[a], 1); }
+        for (int st = 0; st < 2; st++) { mbar_init(&b_full[st], 1); mbar_init(&b_empty[st], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128 * SP_EPI_HALVES); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        const uint32_t ncols = 2 * SP_N;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ka = 0, gi = 0;
+            auto issue_a = [&](int qtile) {
+                const int ab = ka % NBUF;
+                mbar_wait(&a_empty[ab], (((uint32_t)(ka / NBUF)) & 1u) ^ 1u);
+                mbar_expect_tx(&a_full[ab], SP_A_BYTES);
+                bulk_g2s(sA + (size_t)ab * SP_A_BYTES, qa + (size_t)qtile * SP_A_BYTES, SP_A_BYTES, &a_full[ab]);
+                ka++;
+            };
+            TcpPieces it_p(q_tiles, nt_tiles);
+            int qtile, tile_lo, ntiles, slot;
+            bool have = it_p.next(qtile, tile_lo, ntiles, slot);
+            if (have && NBUF == 2) issue_a(qtile);
+            while (have) {
+                int q_n, lo_n, n_n, slot_n;
+                const bool more = it_p.next(q_n, lo_n, n_n, slot_n);
+                const int a_at = ntiles > 2 ? 2 : ntiles - 1;
+                for (int it = 0; it < ntiles; it++, gi++) {
+                    const int st = gi % SP_STAGES;
+                    const uint32_t ph = (uint32_t)(gi / SP_STAGES) & 1u;
+                    mbar_wait(&b_empty[st], ph ^ 1u);
+                    mbar_expect_tx(&b_full[st], SP_B_BYTES);
+                    bulk_g2s(sB + (size_t)st * SP_B_BYTES, tb + (size_t)(tile_lo + it) * SP_B_BYTES, SP_B_BYTES, &b_full[st]);
+                    if (NBUF == 2) { if (it == a_at && more) issue_a(q_n); }
+                    else if (it == 0) issue_a(qtile);
+                }
+                have = more; qtile = q_n; tile_lo = lo_n; ntiles = n_n; slot = slot_n;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SP_N >> 3) << 17) | ((uint32_t)(SP_M >> 4) << 24);
+            const uint32_t ex_off = (uint32_t)(2 * lay.half_chunks) * 128u, lo_off = (uint32_t)lay.half_chunks * 128u;
+            int ka = 0, gi = 0;
+            TcpPieces it_p(q_tiles, nt_tiles);
+            int qtile, tile_lo, ntiles, slot;
+            for (; it_p.next(qtile, tile_lo, ntiles, slot); ka++) {
+                const int ab = ka % NBUF;
+                mbar_wait(&a_full[ab], ((uint32_t)(ka / NBUF)) & 1u);
+                const uint32_t a_addr = s32(sA + (size_t)ab * SP_A_BYTES);
+                for (int it = 0; it < ntiles; it++, gi++) {
+                    const int st = gi % SP_STAGES, acc = gi & 1;
+                    mbar_wait(&b_full[st], (uint32_t)(gi / SP_STAGES) & 1u);
+                    mbar_wait(&acc_empty[acc], ((uint32_t)(gi >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t b_addr = s32(sB + (size_t)st * SP_B_BYTES);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SP_N);
+                    umma_bf16(d_tmem, umma_smem_desc_g(a_addr + ex_off, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + ex_off, SP_GROUP_BYTES), idesc, 0);
+#pragma unroll 2
+                    for (int k = 0; k < ksteps; k++) {
+                        const uint32_t hi = k * 256, lo = lo_off + k * 256;
+                        umma_bf16(d_tmem, umma_smem_desc_g(a_addr + hi, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + hi, SP_GROUP_BYTES), idesc, 1);
+                        umma_bf16(d_tmem, umma_smem_desc_g(a_addr + hi, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + lo, SP_GROUP_BYTES), idesc, 1);
+                        umma_bf16(d_tmem, umma_smem_desc_g(a_addr + lo, SP_GROUP_BYTES), umma_smem_desc_g(b_addr + hi, SP_GROUP_BYTES), idesc, 1);
+                    }
+                    umma_commit(&b_empty[st]);
+                    umma_commit(&acc_full[acc]);
+                }
+                umma_commit(&a_empty[ab]);
+            }
+        }
+    } else {
+        const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = lane_grp * 32 + lane;
+        int gi = 0;
+        TcpPieces it_p(q_tiles, nt_tiles);
+        int qtile, tile_lo, ntiles, slot;
+        while (it_p.next(qtile, tile_lo, ntiles, slot)) {
+            float m[SP_TOPK];
+            int ix[SP_TOPK];
+#pragma unroll
+            for (int k = 0; k < SP_TOPK; k++) { m[k] = INFINITY; ix[k] = 0x7fffffff; }
+            for (int it = 0; it < ntiles; it++, gi++) {
+                const int acc = gi & 1;
+                mbar_wait(&acc_full[acc], (uint32_t)(gi >> 1) & 1u);
+                tc_fence_after();
+                const int col_base = (tile_lo + it) * SP_N;
+                const uint32_t t0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * SP_N);
+                constexpr int CH = SP_N / 32 / SP_EPI_HALVES;
+                const int c_lo = half * CH;
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(t0 + (uint32_t)(c_lo * 32), va);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int c = c_lo; c < c_lo + CH; c += 2) {
+                    tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
+                    top4_chunk(va, t0 + (uint32_t)(c * 32), col_base + c * 32, m, ix);
+                    tmem_ld_wait();
+                    if (c + 2 < c_lo + CH) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+                    top4_chunk(vb, t0 + (uint32_t)((c + 1) * 32), col_base + (c + 1) * 32, m, ix);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[acc]);
+            }
+            const int qrow = qtile * SP_M + row;
+            if (qrow < nq) {
+                Cand4* o = partial + (size_t)(slot * SP_EPI_HALVES + half) * nq + qrow;
+#pragma unroll
+                for (int k = 0; k < SP_TOPK; k++) { o->d[k] = m[k]; o->idx[k] = ix[k]; }
+                if (tile_lo + ntiles == nt_tiles) {      // last piece of the query tile: the list slots above stay empty
+                    for (int sl = slot + 1; sl < lists_per_half; sl++) {
+                        Cand4* e = partial + (size_t)(sl * SP_EPI_HALVES + half) * nq + qrow;
+#pragma unroll
+                        for (int k = 0; k < SP_TOPK; k++) { e->d[k] = INFINITY; e->idx[k] = 0x7fffffff; }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        const uint32_t ncols = 2 * SP_N;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+
 // Exact decision for one query per thread: re-evaluate its candidates with match_f32_kernel's arithmetic, keep
 // the two smallest by (d, index), and prove that no other train descriptor can beat the second (else: flag).
 __global__ void sp_refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim,
@@ -1111,6 +1278,30 @@ int pick_splits(int work_tiles, int nt_tiles, int sms, int* tiles_per_split) {
     return eff > 0 ? eff : 1;
 }
 
+// Persistent tensor-core matchers: the number of CTAs (every SM, or as many as get `min_tiles` tiles each) and the most CTAs a
+// query tile's train sequence is cut over (the kernels' arithmetic: TcpPieces).
+void tcp_plan(int q_tiles, int nt_tiles, int sms, int min_tiles, int* G_out, int* pieces_out) {
+    const long long total = (long long)q_tiles * nt_tiles;
+    long long G = total / (min_tiles > 0 ? min_tiles : 1);
+    G = G < 1 ? 1 : (G > sms ? sms : G);
+    int pieces = 1;
+    for (int qt = 0; qt < q_tiles; qt++) {
+        const int c0 = tcp_cta_of((long long)qt * nt_tiles, total, (int)G), c1 = tcp_cta_of((long long)(qt + 1) * nt_tiles - 1, total, (int)G);
+        if (c1 - c0 + 1 > pieces) pieces = c1 - c0 + 1;
+    }
+    *G_out = (int)G;
+    *pieces_out = pieces;
+}
+
+// The CTAs of the persistent kernels are at different places of the train set at any time, so the whole re-tiled train
+// operand has to stay in L2 (126 MB on B200, of which about half serves one die's SMs): real-valued 128-d descriptors at
+// 200 000 x 200 000 (109 MB) took 34 ms against 28 ms with one CTA per query tile (whose CTAs walk the train set more or less
+// together) -- 170 GB of train tiles through HBM; at 54 MB (100 000) and 58 MB (integer path, 200 000) the persistent kernels
+// are ahead.  `matcher_persistent` = 2 forces them.
+bool tcp_train_fits_l2(const fm3d_ctx* ctx, size_t train_operand_bytes) {
+    return ctx->opt_matcher_persistent == 2 || train_operand_bytes <= ((size_t)64 << 20);
+}
+
 // Train splits of the one-CTA-per-item tensor-core kernels: round 1's rule (split only below 2 CTAs per SM), or as many as
 // `forced` > 0 says (measurements: every split costs another cold start of the streaming top-2, see match_tc_persistent_kernel).
 int pick_splits_waves(int q_tiles, int nt_tiles, int sms, int forced, int* tiles_per_split) {
@@ -1160,33 +1351,35 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         // The contraction is launched WITHOUT waiting for the verdict of the two prep kernels ("every value is an integer in
         // [0, 255]"): the four kernels run back to back and the flag is read once, after them.  Integer descriptors (OpenCV
         // SIFT, the case this path exists for) never pay a mid-pipeline host round trip; for anything else the speculative
-        // result is simply overwritten by the exact paths below.
-        {
+        // result is overwritten by the exact paths below -- and the context remembers the verdict: after a call with
+        // real-valued 128-d descriptors (SURF-128, RootSIFT) the next one reads the flag BEFORE the contraction instead of
+        // wasting it (7.7 ms at 200 000 x 200 000 next to the 26 ms of the filter), until integer descriptors show up again.
+        bool contract = true;
+        if (!ctx->matcher_expect_integer) {
+            int h_flag = 0;
+            if (int rc = fm3d_d2h(ctx, &h_flag, flag, sizeof(int))) return rc;
+            FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            contract = h_flag == 0;
+            if (contract) ctx->matcher_expect_integer = 1;
+        }
+        if (contract) {
             const int q_tiles = nq_pad / TC_M, nt_tiles = nt_pad / TC_N;
             int tps = 1;
             // persistent CTAs over equal ranges of the flattened (query tile, train tile) sequence (default), or one CTA per
             // (query tile, train split) with round 1's split rule (`matcher_persistent` = 0; `matcher_splits` forces the splits)
-            const bool persistent = ctx->opt_matcher_persistent != 0 && ctx->opt_matcher_splits == 0 &&
+            const bool persistent = ctx->opt_matcher_persistent != 0 && ctx->opt_matcher_splits == 0 && tcp_train_fits_l2(ctx, bb) &&
                                     (size_t)TCP_SMEM <= ctx->prop.sharedMemPerBlockOptin;
             Cand* partial = nullptr;
             int lists = 0;
             if (persistent) {
-                // CTAs: every SM, or as many as get `matcher_min_tiles` tiles each
-                const long long total = (long long)q_tiles * nt_tiles;
-                const int min_tiles = ctx->opt_matcher_min_tiles > 0 ? ctx->opt_matcher_min_tiles : 1;
-                long long G = total / min_tiles;
-                G = G < 1 ? 1 : (G > sms ? sms : G);
-                int pieces = 1;                          // most CTAs a query tile's train sequence is cut over (the kernel's arithmetic)
-                for (int qt = 0; qt < q_tiles; qt++) {
-                    const int c0 = tcp_cta_of((long long)qt * nt_tiles, total, (int)G), c1 = tcp_cta_of((long long)(qt + 1) * nt_tiles - 1, total, (int)G);
-                    if (c1 - c0 + 1 > pieces) pieces = c1 - c0 + 1;
-                }
+                int G = 1, pieces = 1;
+                tcp_plan(q_tiles, nt_tiles, sms, ctx->opt_matcher_min_tiles, &G, &pieces);
                 lists = pieces * TC_EPI_HALVES;
                 if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)lists * nq, (void**)&partial)) return rc;
                 FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
-                match_tc_persistent_kernel<<<(int)G, TC_THREADS, TCP_SMEM, ctx->stream>>>(ops, ops + ba, nq, q_tiles, nt_tiles, pieces, partial);
+                match_tc_persistent_kernel<<<G, TC_THREADS, TCP_SMEM, ctx->stream>>>(ops, ops + ba, nq, q_tiles, nt_tiles, pieces, partial);
             } else {
-                const int splits = pick_splits_waves(q_tiles, nt_tiles, sms, ctx->opt_matcher_splits != 0 ? ctx->opt_matcher_splits : -1, &tps);
+                const int splits = pick_splits_waves(q_tiles, nt_tiles, sms, ctx->opt_matcher_splits, &tps);
                 lists = splits * TC_EPI_HALVES;
                 if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand) * 2 * (size_t)lists * nq, (void**)&partial)) return rc;
                 FM3D_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -1200,6 +1393,7 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
             if (int rc = fm3d_d2h(ctx, &h_flag, flag, sizeof(int))) return rc;
             FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (h_flag == 0) return FM3D_OK;
+            ctx->matcher_expect_integer = 0;
         }
     }
     // real-valued descriptors: bf16 hi/lo filter on the tensor cores + exact decision (see match_sp_kernel)
@@ -1224,21 +1418,38 @@ int knn2_f32_dev(fm3d_ctx* ctx, const float* q, int nq, const float* t, int nt, 
         FM3D_LAUNCH_CHECK(ctx);
         const int q_tiles = nq_pad / SP_M, nt_tiles = nt_pad / SP_N;
         int tps = 1;
-        const int splits = pick_splits_waves(q_tiles, nt_tiles, sms, ctx->opt_matcher_splits != 0 ? ctx->opt_matcher_splits : -1, &tps);
+        const bool persistent = ctx->opt_matcher_persistent != 0 && ctx->opt_matcher_splits == 0 && tcp_train_fits_l2(ctx, bb);
         Cand4* partial4 = nullptr;
-        if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)splits * SP_EPI_HALVES * nq, (void**)&partial4)) return rc;
         int32_t* flagged = nullptr;
         if (int rc = fm3d_scratch(ctx, 5, sizeof(int32_t) * (size_t)nq, (void**)&flagged)) return rc;
-        dim3 grid(q_tiles, splits);
-        if (SP_N == 256) {
-            FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
-            match_sp_kernel<256><<<grid, SP_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+        int lists = 0;
+        if (persistent) {
+            int G = 1, pieces = 1;
+            tcp_plan(q_tiles, nt_tiles, sms, ctx->opt_matcher_min_tiles, &G, &pieces);
+            lists = pieces * SP_EPI_HALVES;
+            if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)lists * nq, (void**)&partial4)) return rc;
+            if (SP_N == 256) {
+                FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_persistent_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem_persistent));
+                match_sp_persistent_kernel<256><<<G, SP_THREADS, lay.smem_persistent, ctx->stream>>>(ops, ops + ba, nq, q_tiles, nt_tiles, pieces, (dim + 15) / 16, lay, partial4);
+            } else {
+                FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_persistent_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem_persistent));
+                match_sp_persistent_kernel<128><<<G, SP_THREADS, lay.smem_persistent, ctx->stream>>>(ops, ops + ba, nq, q_tiles, nt_tiles, pieces, (dim + 15) / 16, lay, partial4);
+            }
         } else {
-            FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
-            match_sp_kernel<128><<<grid, SP_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+            const int splits = pick_splits_waves(q_tiles, nt_tiles, sms, ctx->opt_matcher_splits, &tps);
+            lists = splits * SP_EPI_HALVES;
+            if (int rc = fm3d_scratch(ctx, 4, sizeof(Cand4) * (size_t)lists * nq, (void**)&partial4)) return rc;
+            dim3 grid(q_tiles, splits);
+            if (SP_N == 256) {
+                FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
+                match_sp_kernel<256><<<grid, SP_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+            } else {
+                FM3D_CUDA(ctx, cudaFuncSetAttribute(match_sp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
+                match_sp_kernel<128><<<grid, SP_THREADS, lay.smem, ctx->stream>>>(ops, ops + ba, nq, nt_tiles, tps, (dim + 15) / 16, lay, partial4);
+            }
         }
         FM3D_LAUNCH_CHECK(ctx);
-        sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, splits * SP_EPI_HALVES, qnorm, flags + 1, idx, dist,
+        sp_refine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(q, nq, t, nt, dim, partial4, lists, qnorm, flags + 1, idx, dist,
                                                                     reinterpret_cast<int*>(flags + 2), flagged);
         FM3D_LAUNCH_CHECK(ctx);
         int n_flagged = 0;

@@ -209,6 +209,49 @@ def test_match_f32_real_valued_tensor_filter_is_exact(ctx):
     both(qn, t3)
 
 
+@pytest.mark.parametrize("dim", [64, 128, 36])
+def test_match_f32_real_valued_persistent_pieces(ctx, dim):
+    """The real-valued tensor filter as a persistent kernel: more query tiles than SMs (157 x 12 or 24 train tiles), every CTA
+    contracts the tail of one query tile and the head of another (two query-tile buffers at dim <= 80, one at 128), the
+    candidate lists of a query tile come from consecutive CTAs.  Bit-identical to the one-CTA-per-query-tile kernel, to the
+    exact CUDA-core path, and (a slice) to the oracle."""
+    rng = np.random.default_rng(17 + dim)
+    nq, nt = 20_000, 3_000
+    t = rng.normal(size=(nt, dim)).astype(np.float32)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    q = (t[rng.integers(0, nt, nq)] + 0.1 * rng.normal(size=(nq, dim))).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    got = {}
+    try:
+        for key, (tensor, pers, mt) in {"persistent": (1, 1, 1), "persistent_few_ctas": (1, 1, 40), "per_tile": (1, 0, 1), "exact": (0, 1, 1)}.items():
+            ctx.set_option("matcher_tensor", tensor)
+            ctx.set_option("matcher_persistent", pers)
+            ctx.set_option("matcher_min_tiles", mt)
+            got[key] = ctx.match_knn2_f32(q, t)
+    finally:
+        ctx.set_option("matcher_tensor", 1)
+        ctx.set_option("matcher_persistent", 1)
+        ctx.set_option("matcher_min_tiles", 1)
+    for key in ("persistent_few_ctas", "per_tile", "exact"):
+        _check_knn(got["persistent"][0], got["persistent"][1], got[key][0], got[key][1])
+    o_idx, o_dist = orc.knn2_f32(q[:300], t)
+    _check_knn(got["persistent"][0][:300], got["persistent"][1][:300], o_idx, o_dist)
+
+
+def test_match_f32_integer_and_real_valued_calls_alternate(ctx):
+    """The context remembers whether the last 128-d float call held integer descriptors (contraction launched without waiting
+    for the operand check) or real-valued ones (check first): every order of the two kinds returns the oracle's answer."""
+    rng = np.random.default_rng(23)
+    qi, ti, _ = synth.make_float_descriptors(2300, 100, 9)
+    tr = rng.uniform(0, 255, size=(2100, 128)).astype(np.float32)
+    qr = (tr[rng.integers(0, 2100, 2200)] + rng.normal(size=(2200, 128)) * 3).astype(np.float32)
+    oi = orc.knn2_f32(qi, ti, threads=8)
+    o_r = orc.knn2_f32(qr, tr, threads=8)
+    for kind in "irriiri":
+        idx, dist = ctx.match_knn2_f32(qi, ti) if kind == "i" else ctx.match_knn2_f32(qr, tr)
+        _check_knn(idx, dist, *(oi if kind == "i" else o_r))
+
+
 def test_match_f32_real_valued_tile_edges(ctx):
     """The tensor filter at the edges of its tiles: train counts around multiples of 128 / 256, 1-3 train descriptors,
     dimensions that are not multiples of 16, large magnitudes, quantised values with many exact ties, exact copies."""
