@@ -111,6 +111,12 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *                       fp32 decision for other float descriptors (dim <= 128, dim % 4 == 0, >= 2^22
  *                       pairs); results are identical either way.  0: always the exact CUDA-core path
  *   "matcher_sp_tile"   train rows per tile of that filter when dim > 80: 128 (default, two stages) or 256 (one stage)
+ *   "matcher_persistent" 1 (default): both tensor-core matchers run one persistent CTA per SM over equal ranges of the (query
+ *                       tile, train tile) sequence while the re-tiled train operand fits L2 (64 MB); 2: always; 0: one CTA per
+ *                       (query tile, train split).  Same result bits either way
+ *   "matcher_min_tiles" persistent matchers: fewest train tiles worth a CTA of its own (default 1)
+ *   "matcher_splits"    one-CTA-per-item kernels: train splits per query tile (0 = split only below two CTAs per SM); a value
+ *                       > 0 also selects those kernels
  *   "matcher_exact_fallback"  read-only: queries of the last filtered match that the exact path decided
  *   "lm_patience"       lm_control.patience / maxcall (default 100 -> 300 evaluations/level)
  *   "normals_threads"   threads per CTA of the normal optimiser (default 512)
