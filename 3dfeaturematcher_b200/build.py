@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libfm3d.so")
 SOURCES = ["fm3d_ctx.cu", "fm3d_triangulate.cu", "fm3d_pyramid.cu", "fm3d_normals.cu", "fm3d_normals_fast.cu",
            "fm3d_patches.cu", "fm3d_describe.cu", "fm3d_describe_kp.cu", "fm3d_describe_brisk.cu", "fm3d_describe_orb.cu", "fm3d_detect.cu", "fm3d_detect_sift.cu", "fm3d_detect_orb.cu", "fm3d_match.cu", "fm3d_probe.cu", "fm3d_comm.cu"]
-HEADERS = ["fm3d_internal.cuh", "fm3d_orb_pattern.h", "fm3d_lm2.h", "fm3d_normals_common.cuh", os.path.join("..", "..", "include", "fm3d.h")]
+HEADERS = ["fm3d_internal.cuh", "fm3d_orb_pattern.h", "fm3d_lm2.h", "fm3d_normals_common.cuh", "fm3d_match_pieces.h", os.path.join("..", "..", "include", "fm3d.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

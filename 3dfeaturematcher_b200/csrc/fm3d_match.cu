@@ -38,6 +38,7 @@
 #include <math.h>
 
 #include "fm3d_internal.cuh"
+#include "fm3d_match_pieces.h"
 
 namespace {
 
@@ -573,30 +574,6 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
 // one vote per group of four columns, instead of re-reading them from TMEM: 5-15 % slower at every size.)
 constexpr int TCP_SMEM = 2 * TC_A_BYTES + TC_STAGES * TC_B_BYTES + 256;
 
-// the CTA whose range [c * total / G, (c + 1) * total / G) holds flattened tile y
-__host__ __device__ inline int tcp_cta_of(long long y, long long total, int G) { return (int)(((y + 1) * G - 1) / total); }
-
-struct TcpPieces {                // the pieces of one CTA, in order; every role walks its own copy
-    int G, cta, nt_tiles;
-    long long total, T, T1;
-    __device__ TcpPieces(int q_tiles, int nt_tiles_) {
-        G = gridDim.x; cta = blockIdx.x; nt_tiles = nt_tiles_;
-        total = (long long)q_tiles * nt_tiles;             // the host launches G <= total CTAs: no range is empty
-        T = (long long)cta * total / G;
-        T1 = (long long)(cta + 1) * total / G;
-    }
-    __device__ bool next(int& qtile, int& tile_lo, int& ntiles, int& slot) {
-        if (T >= T1) return false;
-        qtile = (int)(T / nt_tiles);
-        tile_lo = (int)(T - (long long)qtile * nt_tiles);
-        const long long n = min((long long)(nt_tiles - tile_lo), T1 - T);
-        ntiles = (int)n;
-        slot = cta - tcp_cta_of((long long)qtile * nt_tiles, total, G);
-        T += n;
-        return true;
-    }
-};
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, int nq, int q_tiles, int nt_tiles,
                            int lists_per_half, Cand* __restrict__ partial) {
@@ -641,7 +618,7 @@ match_tc_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __rest
                 bulk_g2s(sA + (size_t)ab * TC_A_BYTES, qa + (size_t)qtile * TC_A_BYTES, TC_A_BYTES, &a_full[ab]);
                 ka++;
             };
-            TcpPieces it_p(q_tiles, nt_tiles);
+            TcpPieces it_p(q_tiles, nt_tiles, (int)gridDim.x, (int)blockIdx.x);
             int qtile, tile_lo, ntiles, slot;
             bool have = it_p.next(qtile, tile_lo, ntiles, slot);
             if (have) issue_a(qtile);
@@ -667,7 +644,7 @@ match_tc_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __rest
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             int ka = 0, gi = 0;
-            TcpPieces it_p(q_tiles, nt_tiles);
+            TcpPieces it_p(q_tiles, nt_tiles, (int)gridDim.x, (int)blockIdx.x);
             int qtile, tile_lo, ntiles, slot;
             for (; it_p.next(qtile, tile_lo, ntiles, slot); ka++) {
                 const int ab = ka & 1;
@@ -695,7 +672,7 @@ match_tc_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __rest
         const int half = (warp - 2) >> 2;
         const int row = lane_grp * 32 + lane;
         int gi = 0;
-        TcpPieces it_p(q_tiles, nt_tiles);
+        TcpPieces it_p(q_tiles, nt_tiles, (int)gridDim.x, (int)blockIdx.x);
         int qtile, tile_lo, ntiles, slot;
         while (it_p.next(qtile, tile_lo, ntiles, slot)) {
             float m0 = INFINITY, m1 = INFINITY;
@@ -1090,7 +1067,7 @@ match_sp_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __rest
                 bulk_g2s(sA + (size_t)ab * SP_A_BYTES, qa + (size_t)qtile * SP_A_BYTES, SP_A_BYTES, &a_full[ab]);
                 ka++;
             };
-            TcpPieces it_p(q_tiles, nt_tiles);
+            TcpPieces it_p(q_tiles, nt_tiles, (int)gridDim.x, (int)blockIdx.x);
             int qtile, tile_lo, ntiles, slot;
             bool have = it_p.next(qtile, tile_lo, ntiles, slot);
             if (have && NBUF == 2) issue_a(qtile);
@@ -1115,7 +1092,7 @@ match_sp_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __rest
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SP_N >> 3) << 17) | ((uint32_t)(SP_M >> 4) << 24);
             const uint32_t ex_off = (uint32_t)(2 * lay.half_chunks) * 128u, lo_off = (uint32_t)lay.half_chunks * 128u;
             int ka = 0, gi = 0;
-            TcpPieces it_p(q_tiles, nt_tiles);
+            TcpPieces it_p(q_tiles, nt_tiles, (int)gridDim.x, (int)blockIdx.x);
             int qtile, tile_lo, ntiles, slot;
             for (; it_p.next(qtile, tile_lo, ntiles, slot); ka++) {
                 const int ab = ka % NBUF;
@@ -1147,7 +1124,7 @@ match_sp_persistent_kernel(const uint8_t* __restrict__ qa, const uint8_t* __rest
         const int half = (warp - 2) >> 2;
         const int row = lane_grp * 32 + lane;
         int gi = 0;
-        TcpPieces it_p(q_tiles, nt_tiles);
+        TcpPieces it_p(q_tiles, nt_tiles, (int)gridDim.x, (int)blockIdx.x);
         int qtile, tile_lo, ntiles, slot;
         while (it_p.next(qtile, tile_lo, ntiles, slot)) {
             float m[SP_TOPK];
@@ -1276,21 +1253,6 @@ int pick_splits(int work_tiles, int nt_tiles, int sms, int* tiles_per_split) {
     if (*tiles_per_split < 1) *tiles_per_split = 1;
     const int eff = (nt_tiles + *tiles_per_split - 1) / *tiles_per_split;
     return eff > 0 ? eff : 1;
-}
-
-// Persistent tensor-core matchers: the number of CTAs (every SM, or as many as get `min_tiles` tiles each) and the most CTAs a
-// query tile's train sequence is cut over (the kernels' arithmetic: TcpPieces).
-void tcp_plan(int q_tiles, int nt_tiles, int sms, int min_tiles, int* G_out, int* pieces_out) {
-    const long long total = (long long)q_tiles * nt_tiles;
-    long long G = total / (min_tiles > 0 ? min_tiles : 1);
-    G = G < 1 ? 1 : (G > sms ? sms : G);
-    int pieces = 1;
-    for (int qt = 0; qt < q_tiles; qt++) {
-        const int c0 = tcp_cta_of((long long)qt * nt_tiles, total, (int)G), c1 = tcp_cta_of((long long)(qt + 1) * nt_tiles - 1, total, (int)G);
-        if (c1 - c0 + 1 > pieces) pieces = c1 - c0 + 1;
-    }
-    *G_out = (int)G;
-    *pieces_out = pieces;
 }
 
 // The CTAs of the persistent kernels are at different places of the train set at any time, so the whole re-tiled train
