@@ -557,12 +557,15 @@ match_tc_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict__ tb, 
 }
 
 // The same contraction as a PERSISTENT kernel: one CTA per SM for the whole launch, balanced to one tile.
-// Why not more, smaller CTAs: a streaming top-2 starts cold -- until a row's running second-best is small, nearly every chunk
-// of 32 columns holds a value that beats it for one of the warp's 32 rows and takes the slow path; the expected number of such
-// columns is ~ 64 ln(n / 64) per warp over n columns, 13-25 us (15-28 tile times) however short the CTA's train range is.
-// Splitting the train set for balance therefore never paid (`matcher_splits`, profiles/r02y_match_splits_*.jsonl: 50 000 x
-// 50 000 with 1 / 2 / 3 / 4 / 6 splits 0.62 / 0.71 / 0.71 / 0.79 / 0.88 ms), and one CTA per query tile leaves the last wave
-// partly empty (157 query tiles on 148 SMs: two waves for 1.06 waves of work).  Here the (query tile, train tile) pairs are
+// Why not more, smaller CTAs: every additional (query tile, train range) costs 13-25 us (15-28 tile times) however short
+// the range is -- measured with `matcher_splits` (profiles/r02y_match_splits_*.jsonl: 50 000 x 50 000 with 1 / 2 / 3 / 4 / 6
+// splits 0.62 / 0.71 / 0.71 / 0.79 / 0.88 ms, in this kernel and in match_tc_kernel alike: not CTA set-up).  The streaming
+// top-2 starts cold (until a row's running second-best is small, nearly every chunk of 32 columns holds a value that beats it
+// for one of the warp's 32 rows: ~ 64 ln(n / 64) slow-path columns per warp over n columns), and the first train tiles of a
+// range miss L2; which of the two it is was not settled -- inserting cold chunks from the registers instead of re-reading the
+// hit columns from TMEM was slower at every size (profiles/r02z_match_cold_list_insertion_dropped.jsonl).  Either way
+// splitting the train set for balance never paid, and one CTA per query tile leaves the last wave partly empty (157 query
+// tiles on 148 SMs: two waves for 1.06 waves of work).  Here the (query tile, train tile) pairs are
 // laid out query-tile-major and cut into gridDim.x EQUAL contiguous ranges: a CTA contracts the tail of one query tile's train
 // sequence, whole query tiles, and the head of another ("pieces"), with ~ (query tiles / SMs) + 1 cold starts.  TMEM,
 // barriers and pipelines are set up once; the train-tile ring and the two accumulators run across piece boundaries (global

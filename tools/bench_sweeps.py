@@ -387,6 +387,17 @@ if __name__ == "__main__":
             ctx.match_knn2_f32_dev(q.data_ptr(), n, t.data_ptr(), n, dim, idx.data_ptr(), dist.data_ptr())
         stream.synchronize()
         print(json.dumps({"n": n, "dim": dim, "queries_decided_by_exact_path": int(ctx.get_option("matcher_exact_fallback"))}))
+    if which in ("match_sizes",):           # the integer tensor matcher with its defaults over the sizes of the sweeps, one line each (A/B of library variants: FM3D_LIB)
+        dev = torch.device("cuda", 0)
+        g = torch.Generator(device=dev).manual_seed(1003)
+        for nq, nt in ((300, 360), (1000, 1200), (5000, 6000), (5000, 48000), (10000, 10000), (20000, 24000), (50000, 50000), (100000, 100000), (200000, 200000)):
+            t = torch.randint(0, 256, (nt, 128), device=dev, generator=g).float()
+            q = (t[torch.randperm(nt, device=dev, generator=g)[:nq]] + torch.randint(-6, 7, (nq, 128), device=dev, generator=g).float()).clamp_(0, 255)
+            idx = torch.empty((nq, 2), dtype=torch.int32, device=dev); dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
+            ms = min(timed(stream, lambda: ctx.match_knn2_f32_dev(q.data_ptr(), nq, t.data_ptr(), nt, 128, idx.data_ptr(), dist.data_ptr()), 5 if nq <= 50000 else 3) for _ in range(3))
+            print(json.dumps({"case": "match_f32_sift128_tcgen05", "lib": os.environ.get("FM3D_LIB", "default"), "nq": nq, "nt": nt, "ms": ms,
+                              "tflops": 256.0 * nq * nt / (ms * 1e-3) / 1e12, "checksum": [int(idx.long().sum().item()), float(dist.double().sum().item())]}), flush=True)
     if which in ("splits",):
         match_splits_sweep(ctx, stream)
     if which in ("c3",):
