@@ -38,7 +38,7 @@ SYMBOLS = [
     "fm3d_feature_frames_dev", "fm3d_patch_size", "fm3d_extract_patches",
     "fm3d_extract_patches_dev", "fm3d_project_groups", "fm3d_square_neighborhoods",
     "fm3d_describe_patches_sift", "fm3d_describe_patches_sift_dev",
-    "fm3d_detect_fast", "fm3d_detect_fast_dev", "fm3d_detect_sift", "fm3d_detect_orb",
+    "fm3d_detect_fast", "fm3d_detect_fast_dev", "fm3d_detect_sift", "fm3d_detect_and_describe_sift", "fm3d_detect_orb",
     "fm3d_describe_keypoints_sift", "fm3d_describe_keypoints_sift_dev", "fm3d_describe_keypoints_sift_oct", "fm3d_sift_base_image_dev",
     "fm3d_describe_keypoints_brisk", "fm3d_describe_keypoints_brisk_dev",
     "fm3d_describe_keypoints_orb", "fm3d_describe_keypoints_orb_dev",
@@ -482,6 +482,31 @@ class Context:
             m = n.value
         got = min(n.value, m)
         return np.column_stack([xy[:got].astype(np.float64), size[:got], angle[:got], resp[:got], octave[:got].astype(np.float64)])
+
+    def detect_and_describe_sift(self, img, nfeatures=0, n_octave_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma=1.6):
+        """feature_detector_->detect + descriptor_extractor_->compute for DetectorType SIFT + ExtractorType SIFT on one pyramid
+        (cv2.SIFT_create(...).detectAndCompute): (n x 6 f64 keypoint rows as detect_sift, n x 128 f32 descriptors)."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+            img = _arr(img, np.uint8)
+        h, w = img.shape
+        n = C.c_int(0)
+        args = (int(nfeatures), int(n_octave_layers), C.c_double(contrast_threshold), C.c_double(edge_threshold), C.c_double(sigma))
+        m = max(4096, (w * h) // 32)
+        for _ in range(2):
+            xy = np.empty((m, 2), np.float32)
+            size, angle, resp = (np.empty(m, np.float32) for _ in range(3))
+            octave = np.empty(m, np.int32)
+            desc = np.empty((m, 128), np.float32)       # rows beyond the keypoints found are never touched (nor their pages)
+            self._ck(self.lib.fm3d_detect_and_describe_sift(self._h, _ptr(img, _bp), w, h, img.strides[0], *args, m, _ptr(xy, _fp), _ptr(size, _fp),
+                                                            _ptr(angle, _fp), _ptr(resp, _fp), _ptr(octave, C.POINTER(C.c_int32)), C.byref(n),
+                                                            _ptr(desc, _fp)))
+            if n.value <= m:
+                break
+            m = n.value
+        got = min(n.value, m)
+        return (np.column_stack([xy[:got].astype(np.float64), size[:got], angle[:got], resp[:got], octave[:got].astype(np.float64)]),
+                desc[:got])
 
     def detect_orb(self, img, nfeatures=500, scale_factor=1.2, nlevels=8, fast_threshold=20):
         """feature_detector_->detect + descriptor_extractor_->compute for DetectorType ORB + ExtractorType ORB: H x W u8 ->

@@ -389,6 +389,39 @@ int fm3d_describe_keypoints_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h
     return FM3D_OK;
 }
 
+// cv::SIFT::compute on keypoints that carry an octave, on a pyramid that is already on the device (first octave P.first_octave):
+// every descriptor from the layer (octave - first octave)(nOctaveLayers + 3) + layer of its keypoint.  Scratch 0 holds the
+// keypoints, their layers and the descriptors (the pyramid lives in scratch 12).
+static int describe_on_pyramid(fm3d_ctx* ctx, const fm3d_sift_pyramid& P, int w, int h, const float* kps, const int32_t* octaves, int n,
+                               int n_octave_layers, float* descriptors) {
+    const int first = P.first_octave;
+    std::vector<KpLayer> layers(n);
+    for (int i = 0; i < n; i++) {
+        int o = octaves[i] & 255;
+        const int l = (octaves[i] >> 8) & 255;
+        o = o < 128 ? o : (-128 | o);
+        if (l > n_octave_layers + 2) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoint %d: layer %d of %d", i, l, n_octave_layers + 3);
+        const int oi = o - first;
+        if (oi < 0 || oi >= P.n_octaves) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoint %d: octave %d beyond the pyramid of this frame", i, o);
+        const size_t off = P.gauss_off[oi] + (size_t)l * P.w[oi] * P.h[oi];
+        if (off > (size_t)INT_MAX) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "SIFT pyramid larger than 2^31 floats");
+        layers[i] = KpLayer{(int)off, P.w[oi], P.h[oi], o >= 0 ? 1.f / (float)(1 << o) : (float)(1 << -o)};
+    }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t bk = sizeof(float) * 4 * (size_t)n, bl = sizeof(KpLayer) * (size_t)n, bd = sizeof(float) * 128 * (size_t)n;
+    char* d = nullptr;
+    if (int rc = fm3d_scratch(ctx, 0, al(bk) + al(bl) + al(bd), (void**)&d)) return rc;
+    if (int rc = fm3d_h2d(ctx, d, kps, bk)) return rc;
+    if (int rc = fm3d_h2d(ctx, d + al(bk), layers.data(), bl)) return rc;
+    float* d_desc = reinterpret_cast<float*>(d + al(bk) + al(bl));
+    describe_kp_kernel<<<(n + KP_PER_CTA - 1) / KP_PER_CTA, KP_NT, 0, ctx->stream>>>(
+        P.gauss, w, h, reinterpret_cast<const float*>(d), reinterpret_cast<const KpLayer*>(d + al(bk)), n, d_desc);
+    FM3D_LAUNCH_CHECK(ctx);
+    if (int rc = fm3d_d2h(ctx, descriptors, d_desc, bd)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // `layers` must outlive the copy
+    return FM3D_OK;
+}
+
 int fm3d_describe_keypoints_sift_oct(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, const float* kps,
                                      const int32_t* octaves, int n, int n_octave_layers, double sigma, float* descriptors) {
     if (!ctx) return FM3D_ERR_INVALID_ARG;
@@ -398,42 +431,36 @@ int fm3d_describe_keypoints_sift_oct(fm3d_ctx* ctx, const uint8_t* img, int w, i
     if (int rc = fm3d_bind(ctx)) return rc;
     // detectAndCompute(useProvidedKeypoints): the octave range of the keypoints decides the pyramid
     int first = 0, last = INT_MIN;
-    std::vector<int> oc(n), ly(n);
     for (int i = 0; i < n; i++) {
         int o = octaves[i] & 255;
-        const int l = (octaves[i] >> 8) & 255;
         o = o < 128 ? o : (-128 | o);
-        oc[i] = o; ly[i] = l;
         first = std::min(first, o); last = std::max(last, o);
-        if (l > n_octave_layers + 2) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoint %d: layer %d of %d", i, l, n_octave_layers + 3);
     }
     if (first < -1) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoints: first octave %d < -1", first);
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t bi = (size_t)w * h, bk = sizeof(float) * 4 * (size_t)n, bl = sizeof(KpLayer) * (size_t)n, bd = sizeof(float) * 128 * (size_t)n;
-    char* d = nullptr;
-    if (int rc = fm3d_scratch(ctx, 0, al(bi) + al(bk) + al(bl) + al(bd), (void**)&d)) return rc;
-    FM3D_CUDA(ctx, cudaMemcpy2DAsync(d, (size_t)w, img, (size_t)stride, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d_img = nullptr;
+    if (int rc = fm3d_scratch(ctx, 15, (size_t)w * h, (void**)&d_img)) return rc;
+    FM3D_CUDA(ctx, cudaMemcpy2DAsync(d_img, (size_t)w, img, (size_t)stride, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_copy++;
     fm3d_sift_pyramid P;
-    if (int rc = fm3d_sift_build_pyramid(ctx, reinterpret_cast<const uint8_t*>(d), w, h, w, first, last - first + 1, n_octave_layers, sigma,
-                                         false, &P)) return rc;
-    std::vector<KpLayer> layers(n);
-    for (int i = 0; i < n; i++) {
-        const int o = oc[i] - first;
-        if (o >= P.n_octaves) return fm3d_fail(ctx, FM3D_ERR_INVALID_ARG, "SIFT keypoint %d: octave %d beyond the pyramid of this frame", i, oc[i]);
-        const size_t off = P.gauss_off[o] + (size_t)ly[i] * P.w[o] * P.h[o];
-        if (off > (size_t)INT_MAX) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "SIFT pyramid larger than 2^31 floats");
-        layers[i] = KpLayer{(int)off, P.w[o], P.h[o], oc[i] >= 0 ? 1.f / (float)(1 << oc[i]) : (float)(1 << -oc[i])};
-    }
-    if (int rc = fm3d_h2d(ctx, d + al(bi), kps, bk)) return rc;
-    if (int rc = fm3d_h2d(ctx, d + al(bi) + al(bk), layers.data(), bl)) return rc;
-    float* d_desc = reinterpret_cast<float*>(d + al(bi) + al(bk) + al(bl));
-    describe_kp_kernel<<<(n + KP_PER_CTA - 1) / KP_PER_CTA, KP_NT, 0, ctx->stream>>>(
-        P.gauss, w, h, reinterpret_cast<const float*>(d + al(bi)), reinterpret_cast<const KpLayer*>(d + al(bi) + al(bk)), n, d_desc);
-    FM3D_LAUNCH_CHECK(ctx);
-    if (int rc = fm3d_d2h(ctx, descriptors, d_desc, bd)) return rc;
-    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // `layers` must outlive the copy
-    return FM3D_OK;
+    if (int rc = fm3d_sift_build_pyramid(ctx, d_img, w, h, w, first, last - first + 1, n_octave_layers, sigma, false, &P)) return rc;
+    return describe_on_pyramid(ctx, P, w, h, kps, octaves, n, n_octave_layers, descriptors);
+}
+
+int fm3d_detect_and_describe_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
+                                  double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
+                                  float* angle, float* response, int32_t* octave, int* n, float* descriptors) {
+    if (!ctx) return FM3D_ERR_INVALID_ARG;
+    FM3D_CHECK_ARG(ctx, max_keypoints == 0 || descriptors);
+    fm3d_sift_pyramid P;
+    if (int rc = fm3d_detect_sift_impl(ctx, img, w, h, stride, nfeatures, n_octave_layers, contrast_threshold, edge_threshold, sigma, max_keypoints,
+                                       xy, size, angle, response, octave, n, &P)) return rc;
+    const int m = std::min(*n, max_keypoints);
+    if (m <= 0 || *n > max_keypoints) return FM3D_OK;        // too little room: the caller comes back with the real count
+    // the keypoints in the layout of fm3d_describe_keypoints_sift_oct, described on the pyramid they were found on (the same
+    // images cv::SIFT::compute would build again: first octave -1, every octave)
+    std::vector<float> k4((size_t)4 * m);
+    for (int i = 0; i < m; i++) { k4[4 * i] = xy[2 * i]; k4[4 * i + 1] = xy[2 * i + 1]; k4[4 * i + 2] = size[i]; k4[4 * i + 3] = angle[i]; }
+    return describe_on_pyramid(ctx, P, w, h, k4.data(), octave, m, n_octave_layers, descriptors);
 }
 
 }  // extern "C"

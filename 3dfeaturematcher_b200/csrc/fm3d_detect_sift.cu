@@ -478,11 +478,12 @@ int fm3d_sift_build_pyramid(fm3d_ctx* ctx, const uint8_t* d_img, int w, int h, i
     return FM3D_OK;
 }
 
-extern "C" {
-
-int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
-                     double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
-                     float* angle, float* response, int32_t* octave, int* n) {
+// cv::SIFT::detect.  P_keep != nullptr: the pyramid the keypoints were found on (first octave -1, Gaussian images in scratch
+// 12) is described there and stays valid until the next call that builds one: fm3d_detect_and_describe_sift describes the
+// keypoints on it instead of building it a second time.
+int fm3d_detect_sift_impl(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
+                          double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
+                          float* angle, float* response, int32_t* octave, int* n, fm3d_sift_pyramid* P_keep) {
     if (!ctx) return FM3D_ERR_INVALID_ARG;
     FM3D_CHECK_ARG(ctx, img && n && w >= 2 && h >= 2 && stride >= w && n_octave_layers >= 1 && sigma > 0 && max_keypoints >= 0);
     FM3D_CHECK_ARG(ctx, max_keypoints == 0 || (xy && size && angle && response && octave));
@@ -493,6 +494,7 @@ int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
     ctx->n_copy++;
     fm3d_sift_pyramid P;
     if (int rc = fm3d_sift_build_pyramid(ctx, d_img, w, h, w, -1, 0, n_octave_layers, sigma, true, &P)) return rc;
+    if (P_keep) *P_keep = P;
 
     // candidate and keypoint lists (scratch 0): counters, candidates, keypoints
     const int cap_c = 1 << 20, cap_k = 1 << 20;
@@ -615,6 +617,15 @@ int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
         octave[i] = (kp[i].octave & ~255) | ((kp[i].octave - 1) & 255);
     }
     return FM3D_OK;
+}
+
+extern "C" {
+
+int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
+                     double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
+                     float* angle, float* response, int32_t* octave, int* n) {
+    return fm3d_detect_sift_impl(ctx, img, w, h, stride, nfeatures, n_octave_layers, contrast_threshold, edge_threshold, sigma, max_keypoints,
+                                 xy, size, angle, response, octave, n, nullptr);
 }
 
 }  // extern "C"

@@ -133,6 +133,9 @@ struct fm3d_sift_pyramid {
 };
 int fm3d_sift_build_pyramid(fm3d_ctx* ctx, const uint8_t* d_img, int w, int h, int stride, int first_octave, int n_octaves_wanted,
                             int n_octave_layers, double sigma, bool with_dog, fm3d_sift_pyramid* P);
+int fm3d_detect_sift_impl(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
+                          double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
+                          float* angle, float* response, int32_t* octave, int* n, fm3d_sift_pyramid* P_keep);
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

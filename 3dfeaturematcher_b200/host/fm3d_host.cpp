@@ -10,6 +10,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <memory>
 #include <vector>
 
 #include "../../include/fm3d.h"
@@ -310,29 +311,30 @@ void DescriptorsMatcher::detectAndDescribe(const cv::Mat& image, std::vector<cv:
         // cv::SIFT::detect, then cv::SIFT::compute on its keypoints (every descriptor from the keypoint's own pyramid layer)
         // one detection in the usual case (room for a keypoint per 32 pixels); again with the real count if the frame has more
         int cap = std::max(4096, (w * h) / 32);
-        std::vector<float> xy, size, angle, resp, k4;
+        // detector and extractor are both built from FeatureOptions.SiftDetector: one pyramid serves both (cv::SIFT::detectAndCompute)
+        std::vector<float> xy, size, angle, resp;
+        std::unique_ptr<float[]> rows;          // cap x 128, deliberately not value-initialised: only the rows found are written and read
         std::vector<int32_t> oct;
         kpts.clear();
         desc = cv::Mat();
         for (int attempt = 0; attempt < 2; attempt++) {
             xy.resize((size_t)2 * cap); size.resize(cap); angle.resize(cap); resp.resize(cap); oct.resize(cap);
-            check(ctx, fm3d_detect_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, cap,
-                                        xy.data(), size.data(), angle.data(), resp.data(), oct.data(), &n), "detect (SIFT)");
+            rows.reset(new float[(size_t)128 * cap]);
+            check(ctx, fm3d_detect_and_describe_sift(ctx, px, w, h, stride, sift_nfeatures_, sift_layers_, sift_contrast_, sift_edge_, sift_sigma_, cap,
+                                                     xy.data(), size.data(), angle.data(), resp.data(), oct.data(), &n, rows.get()),
+                  "detect + compute (SIFT on one pyramid)");
             if (n <= cap) break;
             cap = n;
         }
         if (n == 0) return;
-        k4.resize((size_t)4 * n);
         kpts.reserve(n);
         for (int i = 0; i < n; i++) {
             cv::KeyPoint kp(xy[2 * i], xy[2 * i + 1], size[i]);
             kp.angle = angle[i]; kp.response = resp[i]; kp.octave = oct[i];
             kpts.push_back(kp);
-            k4[4 * i] = kp.pt.x; k4[4 * i + 1] = kp.pt.y; k4[4 * i + 2] = kp.size; k4[4 * i + 3] = kp.angle;
         }
         desc = cv::Mat::zeros(cv::Size(128, n), CV_32F);
-        check(ctx, fm3d_describe_keypoints_sift_oct(ctx, px, w, h, stride, k4.data(), oct.data(), n, sift_layers_, sift_sigma_, desc.ptr<float>()),
-              "compute (SIFT on the pyramid)");
+        memcpy(desc.ptr<float>(), rows.get(), sizeof(float) * 128 * (size_t)n);
         return;
     }
     if (detector_type_ == "ORB") {

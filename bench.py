@@ -666,8 +666,14 @@ def run_gpu_arm(args):
         t1 = time.perf_counter()
         dsift = ctx.describe_keypoints_sift_oct(h1, ksift[:, :4].astype(np.float32), ksift[:, 5].astype(np.int32))
         t2 = time.perf_counter()
+        ctx.detect_and_describe_sift(h1)
+        t3 = time.perf_counter()
+        kboth, dboth = ctx.detect_and_describe_sift(h1)
+        t4 = time.perf_counter()
         sift_front = {"keypoints_frame1": int(len(ksift)), "ms_detect_frame1_host_to_host": 1e3 * (t1 - t0),
-                      "ms_describe_frame1_host_to_host": 1e3 * (t2 - t1), "descriptor_rows_nonzero": int((dsift != 0).any(1).sum())}
+                      "ms_describe_frame1_host_to_host": 1e3 * (t2 - t1), "descriptor_rows_nonzero": int((dsift != 0).any(1).sum()),
+                      "ms_detect_and_describe_on_one_pyramid_host_to_host": 1e3 * (t4 - t3),
+                      "one_pyramid_equals_two_calls": bool(np.array_equal(kboth, ksift) and np.array_equal(dboth, dsift))}
 
     # ---- the north-star configuration in the same run, at the same N: BASELINE configs[2], ONE 4K pair with 20 000 query
     # keypoints in total sharded over the ranks (strong scaling), pixelsRay 64, pyramids 3

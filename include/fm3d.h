@@ -474,6 +474,17 @@ int fm3d_detect_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride
                      double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
                      float* angle, float* response, int32_t* octave, int* n);
 
+/* Replaces feature_detector_->detect followed by descriptor_extractor_->compute on the same frame
+ * (DescriptorsMatcher/descriptorsmatcher.cpp:110-115, :91-96, :76-81) for DetectorType SIFT + ExtractorType SIFT with the same
+ * settings (:243-256, :302-314): fm3d_detect_sift, then the descriptors of its keypoints read from THE PYRAMID THEY WERE FOUND
+ * ON -- the images cv::SIFT::compute would build a second time (doubled frame, every octave) -- i.e. what
+ * cv::SIFT::detectAndCompute does.  Keypoints and descriptors are bit-identical to fm3d_detect_sift followed by
+ * fm3d_describe_keypoints_sift_oct.  descriptors: max_keypoints x 128 f32; when *n > max_keypoints nothing is described
+ * (call again with room for *n). */
+int fm3d_detect_and_describe_sift(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride, int nfeatures, int n_octave_layers,
+                                  double contrast_threshold, double edge_threshold, double sigma, int max_keypoints, float* xy, float* size,
+                                  float* angle, float* response, int32_t* octave, int* n, float* descriptors);
+
 /* Replaces feature_detector_->detect followed by descriptor_extractor_->compute (DescriptorsMatcher/descriptorsmatcher.cpp:110-115,
  * :91-96, :76-81) for DetectorType ORB + ExtractorType ORB (:273-279, :336-342: cv::ORB(OrbDetector.NumFeatures, ScaleFactor,
  * NumLevels), the other arguments at cv::ORB's defaults; fast_threshold = 20 is its default): the INTER_LINEAR_EXACT pyramid,

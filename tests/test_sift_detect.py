@@ -121,3 +121,24 @@ def test_gpu_sift_descriptors_of_sift_keypoints_against_cv2_golden_vectors(ctx):
             print(f"SIFT describe {name}/{pname}: {len(kp)} keypoints, values equal {np.mean(d == 0):.4f}, |diff| <= 1 {np.mean(d <= 1):.4f}, "
                   f"rows within 2: {rows_close:.4f}, max {d.max():.0f}")
             assert np.mean(d == 0) >= 0.95 and np.mean(d <= 1) >= 0.995 and rows_close >= 0.98
+
+
+@pytest.mark.gpu
+def test_gpu_sift_detect_and_describe_on_one_pyramid_equals_the_two_calls(ctx):
+    """fm3d_detect_and_describe_sift (cv::SIFT::detectAndCompute: the descriptors read from the pyramid the keypoints were found
+    on) returns, bit for bit, the keypoints of fm3d_detect_sift and the rows fm3d_describe_keypoints_sift_oct computes for them on
+    a pyramid of its own -- golden frames with three parameter sets (retainBest included) and a rendered 720p frame."""
+    synth = importlib.import_module("3dfeaturematcher_b200.synth")
+    g = np.load(os.path.join(GOLD, "sift_detect.npz"))
+    cases = [(g[f"img_{name}"], kw) for name in ("blobs", "frame", "odd") for kw in PARAMS.values()]
+    cases.append((synth.make_stereo_case(1280, 720, 20, 1001, pixels_ray=32)["scene"].img1, {}))
+    for img, kw in cases:
+        K = ctx.detect_sift(img, **kw)
+        K2, D2 = ctx.detect_and_describe_sift(img, **kw)
+        np.testing.assert_array_equal(K, K2)
+        assert D2.shape == (len(K), 128)
+        if len(K):
+            D = ctx.describe_keypoints_sift_oct(img, K[:, :4].astype(np.float32), K[:, 5].astype(np.int32),
+                                                n_octave_layers=kw.get("n_octave_layers", 3), sigma=kw.get("sigma", 1.6))
+            np.testing.assert_array_equal(D, D2)
+            assert (D2 != 0).any(1).all()
