@@ -112,6 +112,14 @@ __global__ void orb_angle_kernel(const uint8_t* __restrict__ img, int w, const i
     if (lane == 0) angle[k] = orb_fast_atan2_deg((float)m01, (float)m10);
 }
 
+// (x, y, 31, angle) rows for the descriptor stage from the level positions and the angles: KeyPoint::size of a level keypoint is
+// the patch size, the angle is the one orb_angle_kernel left
+__global__ void orb_k4_kernel(const int* __restrict__ xy, const float* __restrict__ angle, int n, float* __restrict__ k4) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    k4[4 * k] = (float)xy[2 * k]; k4[4 * k + 1] = (float)xy[2 * k + 1]; k4[4 * k + 2] = 31.f; k4[4 * k + 3] = angle[k];
+}
+
 inline int cv_round(double v) { return (int)std::nearbyint(v); }
 
 void resize_tables(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& a1) {
@@ -190,15 +198,26 @@ int fm3d_detect_orb(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride,
             ++v0;
         }
     }
-    // device buffers: pyramid (slot 12), resize tables + lists (slot 13)
+    // device buffers: pyramid (slot 12), resize tables + lists of every level (slot 13).  The levels are worked on TOGETHER, stage
+    // by stage, so that a frame costs four host round trips (corner counts, corners, Harris measures, angles + rows) instead of
+    // six per level: the two retainBest selections stay on the host (they keep everything that ties with the last kept response,
+    // as std::nth_element + std::partition do), everything between them runs level after level on the stream without a wait.
     uint8_t* pyr = nullptr;
     if (int rc = fm3d_scratch(ctx, 12, total, (void**)&pyr)) return rc;
     FM3D_CUDA(ctx, cudaMemcpy2DAsync(pyr, (size_t)w, img, (size_t)stride, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_copy++;
-    const int cap = std::max(4096, (w * h) / 16);            // FAST corners of one level
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t b_tab = al(sizeof(int) * 2 * (size_t)(w + h)), b_xy = al(sizeof(float) * 2 * (size_t)cap), b_r = al(sizeof(float) * (size_t)cap);
-    const size_t b_ixy = al(sizeof(int) * 2 * (size_t)cap), b_k4 = al(sizeof(float) * 4 * (size_t)cap), b_d = al((size_t)32 * cap), b_kept = al((size_t)cap);
+    int capl[ORB_MAX_LEVELS];                 // FAST corners a level has room for
+    size_t coff[ORB_MAX_LEVELS], cap_total = 0, tab_ints = 0, toff[ORB_MAX_LEVELS];
+    for (int l = 0; l < nlevels; l++) {
+        capl[l] = std::max(4096, (lw[l] * lh[l]) / 16);
+        coff[l] = cap_total;
+        cap_total += (size_t)capl[l];
+        toff[l] = tab_ints;
+        if (l > 0) tab_ints += 2 * (size_t)(lw[l] + lh[l]);
+    }
+    const size_t b_tab = al(sizeof(int) * std::max<size_t>(tab_ints, 1)), b_xy = al(sizeof(float) * 2 * cap_total), b_r = al(sizeof(float) * cap_total);
+    const size_t b_ixy = al(sizeof(int) * 2 * cap_total), b_k4 = al(sizeof(float) * 4 * cap_total), b_d = al((size_t)32 * cap_total), b_kept = al(cap_total);
     char* d = nullptr;
     if (int rc = fm3d_scratch(ctx, 13, b_tab + b_xy + 3 * b_r + b_ixy + b_k4 + b_d + b_kept + 256, (void**)&d)) return rc;
     int* d_tab = reinterpret_cast<int*>(d);
@@ -210,89 +229,128 @@ int fm3d_detect_orb(fm3d_ctx* ctx, const uint8_t* img, int w, int h, int stride,
     float* d_k4 = reinterpret_cast<float*>(d + b_tab + b_xy + 3 * b_r + b_ixy);
     uint8_t* d_desc = reinterpret_cast<uint8_t*>(d + b_tab + b_xy + 3 * b_r + b_ixy + b_k4);
     uint8_t* d_kept = d_desc + b_d;
-    int* d_n = reinterpret_cast<int*>(d_kept + b_kept);
+    int* d_n = reinterpret_cast<int*>(d_kept + b_kept);      // one corner count per level
 
     struct Kp { float x, y, size, angle, response; int octave, lx, ly; uint8_t desc[32]; };
     std::vector<Kp> out;
-    std::vector<int> tx, ta, ty, tb;
-    std::vector<float> hxy, hresp, hharris, hangle, hk4;
-    std::vector<int> hixy;
-    std::vector<uint8_t> hdesc;
+
+    // ---- stage A: the pyramid and the FAST corners of every level
+    std::vector<int> tab(tab_ints), tx, ta, ty, tb;
+    for (int l = 1; l < nlevels; l++) {
+        resize_tables(lw[l - 1], lw[l], tx, ta);
+        resize_tables(lh[l - 1], lh[l], ty, tb);
+        int* t = tab.data() + toff[l];
+        std::copy(tx.begin(), tx.end(), t); std::copy(ta.begin(), ta.end(), t + lw[l]);
+        std::copy(ty.begin(), ty.end(), t + 2 * lw[l]); std::copy(tb.begin(), tb.end(), t + 2 * lw[l] + lh[l]);
+    }
+    if (tab_ints) if (int rc = fm3d_h2d(ctx, d_tab, tab.data(), sizeof(int) * tab_ints)) return rc;      // `tab` lives until the first wait below
+    FM3D_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int) * ORB_MAX_LEVELS, ctx->stream));
+    ctx->n_copy++;
+    bool active[ORB_MAX_LEVELS];
     for (int l = 0; l < nlevels; l++) {
         uint8_t* lim = pyr + loff[l];
         if (l > 0) {
-            resize_tables(lw[l - 1], lw[l], tx, ta);
-            resize_tables(lh[l - 1], lh[l], ty, tb);
-            std::vector<int> tab;
-            tab.insert(tab.end(), tx.begin(), tx.end()); tab.insert(tab.end(), ta.begin(), ta.end());
-            tab.insert(tab.end(), ty.begin(), ty.end()); tab.insert(tab.end(), tb.begin(), tb.end());
-            if (int rc = fm3d_h2d(ctx, d_tab, tab.data(), sizeof(int) * tab.size())) return rc;
-            FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `tab` is a local
+            const int* t = d_tab + toff[l];
             const dim3 blk(32, 8);
             orb_resize_kernel<<<dim3((lw[l] + 31) / 32, (lh[l] + 7) / 8), blk, 0, ctx->stream>>>(
-                pyr + loff[l - 1], lw[l - 1], lh[l - 1], lw[l - 1], d_tab, d_tab + lw[l], d_tab + 2 * lw[l], d_tab + 2 * lw[l] + lh[l], lim, lw[l], lh[l]);
+                pyr + loff[l - 1], lw[l - 1], lh[l - 1], lw[l - 1], t, t + lw[l], t + 2 * lw[l], t + 2 * lw[l] + lh[l], lim, lw[l], lh[l]);
             FM3D_LAUNCH_CHECK(ctx);
         }
-        const int ww = lw[l], hh = lh[l];
-        if (npl[l] == 0 || ww <= 2 * edge || hh <= 2 * edge) continue;
-        if (int rc = fm3d_detect_fast_dev(ctx, lim, ww, hh, ww, fast_threshold, 1, cap, d_xy, d_resp, d_n)) return rc;
-        int nf = 0;
-        if (int rc = fm3d_d2h(ctx, &nf, d_n, sizeof(int))) return rc;
-        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (nf > cap) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "ORB: %d FAST corners on level %d exceed the buffer of %d", nf, l, cap);
-        if (nf == 0) continue;
-        hxy.resize(2 * (size_t)nf); hresp.resize(nf);
-        if (int rc = fm3d_d2h(ctx, hxy.data(), d_xy, sizeof(float) * 2 * (size_t)nf)) return rc;
-        if (int rc = fm3d_d2h(ctx, hresp.data(), d_resp, sizeof(float) * (size_t)nf)) return rc;
-        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        // runByImageBorder(edgeThreshold), retainBest(2 n_l) by FAST score
+        active[l] = !(npl[l] == 0 || lw[l] <= 2 * edge || lh[l] <= 2 * edge);
+        if (!active[l]) continue;
+        if (int rc = fm3d_detect_fast_dev(ctx, lim, lw[l], lh[l], lw[l], fast_threshold, 1, capl[l], d_xy + 2 * coff[l], d_resp + coff[l], d_n + l)) return rc;
+    }
+    int nf[ORB_MAX_LEVELS] = {0};
+    if (int rc = fm3d_d2h(ctx, nf, d_n, sizeof(int) * (size_t)nlevels)) return rc;
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<float> hxy[ORB_MAX_LEVELS], hresp[ORB_MAX_LEVELS];
+    for (int l = 0; l < nlevels; l++) {
+        if (!active[l] || nf[l] == 0) continue;
+        if (nf[l] > capl[l]) return fm3d_fail(ctx, FM3D_ERR_UNSUPPORTED, "ORB: %d FAST corners on level %d exceed the buffer of %d", nf[l], l, capl[l]);
+        hxy[l].resize(2 * (size_t)nf[l]); hresp[l].resize(nf[l]);
+        if (int rc = fm3d_d2h(ctx, hxy[l].data(), d_xy + 2 * coff[l], sizeof(float) * 2 * (size_t)nf[l])) return rc;
+        if (int rc = fm3d_d2h(ctx, hresp[l].data(), d_resp + coff[l], sizeof(float) * (size_t)nf[l])) return rc;
+    }
+    FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    // ---- stage B: runByImageBorder(edgeThreshold), retainBest(2 n_l) by FAST score; the Harris measure of the survivors
+    std::vector<int> hixy;                    // survivors of all levels, level after level
+    size_t moff[ORB_MAX_LEVELS + 1] = {0};
+    for (int l = 0; l < nlevels; l++) {
+        moff[l + 1] = moff[l];
+        if (!active[l] || nf[l] == 0) continue;
         std::vector<int> idx;
-        idx.reserve(nf);
-        for (int i = 0; i < nf; i++) {
-            const int x = (int)hxy[2 * i], y = (int)hxy[2 * i + 1];
-            if (x >= edge && x < ww - edge && y >= edge && y < hh - edge) idx.push_back(i);
+        idx.reserve(nf[l]);
+        for (int i = 0; i < nf[l]; i++) {
+            const int x = (int)hxy[l][2 * i], y = (int)hxy[l][2 * i + 1];
+            if (x >= edge && x < lw[l] - edge && y >= edge && y < lh[l] - edge) idx.push_back(i);
         }
-        retain_best(idx, hresp, 2 * npl[l]);
-        int m = (int)idx.size();
-        if (m == 0) continue;
-        hixy.resize(2 * (size_t)m);
-        for (int i = 0; i < m; i++) { hixy[2 * i] = (int)hxy[2 * idx[i]]; hixy[2 * i + 1] = (int)hxy[2 * idx[i] + 1]; }
-        if (int rc = fm3d_h2d(ctx, d_ixy, hixy.data(), sizeof(int) * 2 * (size_t)m)) return rc;
-        orb_harris_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(lim, ww, hh, d_ixy, m, d_harris);
-        FM3D_LAUNCH_CHECK(ctx);
-        hharris.resize(m);
-        if (int rc = fm3d_d2h(ctx, hharris.data(), d_harris, sizeof(float) * (size_t)m)) return rc;
+        retain_best(idx, hresp[l], 2 * npl[l]);
+        for (int i : idx) { hixy.push_back((int)hxy[l][2 * i]); hixy.push_back((int)hxy[l][2 * i + 1]); }
+        moff[l + 1] = moff[l] + idx.size();
+    }
+    const size_t m_all = moff[nlevels];
+    std::vector<float> hharris(m_all);
+    if (m_all) {
+        if (int rc = fm3d_h2d(ctx, d_ixy, hixy.data(), sizeof(int) * 2 * m_all)) return rc;
+        for (int l = 0; l < nlevels; l++) {
+            const int m = (int)(moff[l + 1] - moff[l]);
+            if (m == 0) continue;
+            orb_harris_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(pyr + loff[l], lw[l], lh[l], d_ixy + 2 * moff[l], m, d_harris + moff[l]);
+            FM3D_LAUNCH_CHECK(ctx);
+        }
+        if (int rc = fm3d_d2h(ctx, hharris.data(), d_harris, sizeof(float) * m_all)) return rc;
         FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+
+    // ---- stage C: retainBest(n_l) by the Harris measure; angles and rows of what is left
+    std::vector<int> kxy;                     // kept keypoints of all levels (level positions), level after level
+    std::vector<float> kresp;
+    size_t koff[ORB_MAX_LEVELS + 1] = {0};
+    for (int l = 0; l < nlevels; l++) {
+        koff[l + 1] = koff[l];
+        const int m = (int)(moff[l + 1] - moff[l]);
+        if (m == 0) continue;
+        std::vector<float> hl(hharris.begin() + moff[l], hharris.begin() + moff[l + 1]);
         std::vector<int> idx2(m);
         for (int i = 0; i < m; i++) idx2[i] = i;
-        retain_best(idx2, hharris, npl[l]);
-        const int m2 = (int)idx2.size();
-        if (m2 == 0) continue;
-        std::vector<int> kxy(2 * (size_t)m2);
-        for (int i = 0; i < m2; i++) { kxy[2 * i] = hixy[2 * idx2[i]]; kxy[2 * i + 1] = hixy[2 * idx2[i] + 1]; }
-        if (int rc = fm3d_h2d(ctx, d_ixy, kxy.data(), sizeof(int) * 2 * (size_t)m2)) return rc;
-        orb_angle_kernel<<<(m2 + 3) / 4, 128, 0, ctx->stream>>>(lim, ww, d_ixy, m2, um, d_angle);
-        FM3D_LAUNCH_CHECK(ctx);
-        hangle.resize(m2);
-        if (int rc = fm3d_d2h(ctx, hangle.data(), d_angle, sizeof(float) * (size_t)m2)) return rc;
-        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        hdesc.assign((size_t)32 * m2, 0);
-        if (descriptors) {
-            hk4.resize(4 * (size_t)m2);
-            for (int i = 0; i < m2; i++) {
-                hk4[4 * i] = (float)kxy[2 * i]; hk4[4 * i + 1] = (float)kxy[2 * i + 1]; hk4[4 * i + 2] = 31.f; hk4[4 * i + 3] = hangle[i];
-            }
-            if (int rc = fm3d_h2d(ctx, d_k4, hk4.data(), sizeof(float) * 4 * (size_t)m2)) return rc;
-            if (int rc = fm3d_describe_keypoints_orb_dev(ctx, lim, ww, hh, ww, d_k4, m2, d_desc, d_kept)) return rc;
-            if (int rc = fm3d_d2h(ctx, hdesc.data(), d_desc, (size_t)32 * m2)) return rc;
-            FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        retain_best(idx2, hl, npl[l]);
+        for (int i : idx2) { kxy.push_back(hixy[2 * (moff[l] + i)]); kxy.push_back(hixy[2 * (moff[l] + i) + 1]); kresp.push_back(hl[i]); }
+        koff[l + 1] = koff[l] + idx2.size();
+    }
+    const size_t k_all = koff[nlevels];
+    std::vector<float> hangle(k_all);
+    std::vector<uint8_t> hdesc((size_t)32 * k_all, 0);
+    if (k_all) {
+        if (int rc = fm3d_h2d(ctx, d_ixy, kxy.data(), sizeof(int) * 2 * k_all)) return rc;
+        for (int l = 0; l < nlevels; l++) {
+            const int m2 = (int)(koff[l + 1] - koff[l]);
+            if (m2 == 0) continue;
+            orb_angle_kernel<<<(m2 + 3) / 4, 128, 0, ctx->stream>>>(pyr + loff[l], lw[l], d_ixy + 2 * koff[l], m2, um, d_angle + koff[l]);
+            FM3D_LAUNCH_CHECK(ctx);
         }
-        for (int i = 0; i < m2; i++) {
+        if (descriptors) {
+            orb_k4_kernel<<<(unsigned)((k_all + 255) / 256), 256, 0, ctx->stream>>>(d_ixy, d_angle, (int)k_all, d_k4);
+            FM3D_LAUNCH_CHECK(ctx);
+            for (int l = 0; l < nlevels; l++) {
+                const int m2 = (int)(koff[l + 1] - koff[l]);
+                if (m2 == 0) continue;
+                if (int rc = fm3d_describe_keypoints_orb_dev(ctx, pyr + loff[l], lw[l], lh[l], lw[l], d_k4 + 4 * koff[l], m2, d_desc + 32 * koff[l],
+                                                             d_kept + koff[l])) return rc;
+            }
+            if (int rc = fm3d_d2h(ctx, hdesc.data(), d_desc, (size_t)32 * k_all)) return rc;
+        }
+        if (int rc = fm3d_d2h(ctx, hangle.data(), d_angle, sizeof(float) * k_all)) return rc;
+        FM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    out.reserve(k_all);
+    for (int l = 0; l < nlevels; l++) {
+        for (size_t i = koff[l]; i < koff[l + 1]; i++) {
             Kp k;
             k.lx = kxy[2 * i]; k.ly = kxy[2 * i + 1];
             k.x = (float)k.lx * sc[l]; k.y = (float)k.ly * sc[l];
             k.size = 31.f * sc[l];
-            k.angle = hangle[i]; k.response = hharris[idx2[i]]; k.octave = l;
+            k.angle = hangle[i]; k.response = kresp[i]; k.octave = l;
             memcpy(k.desc, &hdesc[(size_t)32 * i], 32);
             out.push_back(k);
         }
