@@ -54,8 +54,8 @@ struct fm3d_ctx {
     int opt_normals_tma = 1;
     int opt_normals_pingpong = 1;  // fast kernel, four-window layout, mode 0: two features per eight warps taking turns (normals_pp_kernel)
     int opt_normals_groups = 0;    // fast kernel: feature pipelines per CTA; 0 = automatic (2 when there are more features than SMs)
-    int opt_normals_memo = 1;      // fast kernel: trials whose fp32 coefficients equal the iterate's are not re-evaluated
-    int opt_normals_fuse = 1;      // fast kernel: Jacobian evaluated together with the first trial of an iteration
+    int opt_normals_memo = 2;      // fast kernel: 1 = trials whose fp32 coefficients equal the iterate's are not re-evaluated, 2 = nor are Jacobian requests (SSD)
+    int opt_normals_fuse = 3;      // fast kernel: Jacobian evaluated together with a trial: 1 = the first trial of an iteration, 2 = that, if the last one was accepted, 3 = every trial
     int opt_normals_sweep_batch = 4;  // fast kernel, dense sweep: candidates per pass (1: one pass per candidate)
     int opt_normals_fast = 1;      // 1: fm3d_normals_fast.cu (default), 0: the faithful fp64 kernel
     int opt_pyramid_fused = 1;     // K4: one fused launch per three pyramid levels (0: one pyrdown_kernel launch per level + copies)

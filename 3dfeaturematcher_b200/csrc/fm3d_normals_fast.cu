@@ -121,6 +121,9 @@ struct FastShared {
     float hbase[9];     // value coefficients (FastPass::h) of the current LM iterate ...
     double s0_base;     // ... and the residual sum the pass at the iterate returned
     int base_valid;
+    double jraw[6];     // SSD: the raw sums (residual sum, three moments of U, two U.d sums) of the last Jacobian pass evaluated ...
+    double jbase[6];    // ... and those of the pass at the iterate's coefficients, if one was evaluated (jbase_valid)
+    int jbase_valid;
     int cand;           // mode 2 (sweep): candidate being evaluated
     double sweep_c[2];  // mode 2: centre (phi, theta) of the candidate grid
     double best_cost;   // mode 2: running minimum
@@ -730,6 +733,13 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                                 }
                                 s[k] = v;
                             }
+                            // raw sums of this Jacobian pass: they depend on the pass's fp32 coefficients only (the sigma
+                            // coefficients are applied below, after the reduction), so a later Jacobian request at a point with
+                            // the same coefficients can be answered from them
+                            if (!ncc && P.kind == PASS_JAC && lane == 0) {
+    #pragma unroll
+                                for (int k = 0; k < 6; k++) S->jraw[k] = s[k];
+                            }
                             if (P.kind == PASS_JAC) jacobian_sums_from_moments(s, S->sg, ncc);
                             if (ncc) ncc_sums_to_normal_equations(s, S->ncc_su, S->ncc_suu, m, P.kind == PASS_JAC);
                         }
@@ -798,6 +808,11 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                                         first_trial = true;
                                         S->s0_base = s[0];      // sum and coefficients of the iterate
                                         take_base = 1;
+                                        if (!memo && !ncc) {    // ... and the raw Jacobian sums of the pass at them
+    #pragma unroll
+                                            for (int k = 0; k < 6; k++) S->jbase[k] = S->jraw[k];
+                                            S->jbase_valid = 1;
+                                        }
                                     } else {
                                         if (S->w[0] != 1.0) S->npenalty++;
                                         const int iter_before = lm.iter;
@@ -807,6 +822,13 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                                         if (!memo && accepted) {   // new iterate
                                             S->s0_base = s[0];
                                             take_base = 1;
+                                            if (where == AT_XT_FUSED && !ncc) {   // its Jacobian sums came with the trial
+    #pragma unroll
+                                                for (int k = 0; k < 6; k++) S->jbase[k] = S->jraw[k];
+                                                S->jbase_valid = 1;
+                                            } else {
+                                                S->jbase_valid = 0;
+                                            }
                                         }
                                         // accepted (x == xt now) and the Jacobian came with the trial
                                         if (cmd == FM3D_LM_CMD_JAC && where == AT_XT_FUSED) {
@@ -821,7 +843,10 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                                     } else if (cmd == FM3D_LM_CMD_TRIAL) {
                                         // first trial of an iteration: evaluate its Jacobian along with it;
                                         // re-trials after a rejection are value-only
-                                        const bool fuse = first_trial && (A.fuse_trials == 1 || (A.fuse_trials == 2 && S->fuse_hint));
+                                        // 3: re-trials too -- after a rejection lmfit shortens the step and the re-trial is usually
+                                        // accepted; its Jacobian then is the next iteration's (no separate Jacobian pass)
+                                        const bool fuse = (first_trial && (A.fuse_trials == 1 || (A.fuse_trials == 2 && S->fuse_hint))) ||
+                                                          A.fuse_trials == 3;
                                         S->trial_is_first = first_trial ? 1 : 0;
                                         S->where = fuse ? AT_XT_FUSED : AT_XT_PLAIN;
                                         next_kind = fuse ? PASS_JAC : PASS_VALUE; next_phi = lm.xt[0]; next_theta = lm.xt[1];
@@ -845,14 +870,24 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                             publish_pass(PP, S, cam, next_phi, next_theta, next_kind, A.penalty_mode, S->lm.eps, lane);
                             __syncwarp();
                             if (PP->kind == PASS_STOP) break;       // NaN normal
-                            // would this pass return the iterate's sum?  (trial points only)
-                            bool same = S->where != AT_X_JAC && S->base_valid != 0 && A.memo_trials;
+                            // would this pass return what the pass at the iterate's coefficients returned?  Trial points: its residual
+                            // sum.  Jacobian requests (normals_memo = 2, SSD): after an accepted trial that was itself answered from
+                            // memory the new iterate has the old coefficients -- the same pass, the same raw sums; only the sigma
+                            // coefficients and the penalty weights (both from the exact point, both applied here) differ.
+                            const bool at_jac = S->where == AT_X_JAC;
+                            bool same = S->base_valid != 0 && A.memo_trials && (!at_jac || (A.memo_trials >= 2 && !ncc && S->jbase_valid != 0));
                             if (lane < 9) same = same && (PP->h[lane] == S->hbase[lane]);
                             same = __all_sync(0xffffffffu, same);
                             if (!same) break;                       // run the pass
                             memo = true;
-                            s[0] = S->s0_base;
-                            if (lane == 0) { S->where = AT_XT_PLAIN; }
+                            if (at_jac) {
+    #pragma unroll
+                                for (int k = 0; k < 6; k++) s[k] = S->jbase[k];
+                                jacobian_sums_from_moments(s, S->sg, false);
+                            } else {
+                                s[0] = S->s0_base;
+                                if (lane == 0) { S->where = AT_XT_PLAIN; }
+                            }
                             __syncwarp();
                         }
                         if (lane == 0) {
@@ -1182,7 +1217,7 @@ __device__ FM3D_SETUP_INLINE unsigned level_setup(const NormalsArgs& A, GroupCtl
                 PP->slow = 0;
                 fm3d_lm2_init(&S->lm, phi, theta, A.eps_lmmin, A.patience);
                 S->where = AT_X_JAC;
-                S->base_valid = 0;
+                S->base_valid = 0; S->jbase_valid = 0;
                 S->fuse_hint = 1;
             }
             publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
@@ -1199,7 +1234,7 @@ __device__ FM3D_SETUP_INLINE unsigned level_setup(const NormalsArgs& A, GroupCtl
                 S->lm.nfev = 0;
                 S->lm.eps = 1e-5;
                 S->where = AT_XT_PLAIN;
-                S->base_valid = 0;
+                S->base_valid = 0; S->jbase_valid = 0;
                 S->cand = 0;
                 S->sweep_c[0] = phi; S->sweep_c[1] = theta;
                 S->best_cost = __longlong_as_double(0x7ff0000000000000LL);

@@ -125,9 +125,12 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *                       fm3d_evaluate_normals through the fast kernel
  *   "normals_cost"      fm3d_cost_mode: 0 (default) the reference's SSD, 1 NCC (fast kernel only: with
  *                       normals_fast = 0, and in fm3d_sweep_normals, NCC returns FM3D_ERR_UNSUPPORTED)
- *   "normals_fuse"      fast kernel: evaluate the first trial of an LM iteration with its Jacobian (1)
- *   "normals_memo"      fast kernel: do not re-evaluate trial points whose fp32 coefficients equal
- *                       the iterate's (1)
+ *   "normals_fuse"      fast kernel: evaluate the Jacobian together with a trial point, so that an accepted trial opens the
+ *                       next LM iteration without another pass: 3 (default) every trial, 1 the first trial of an iteration
+ *                       only, 2 that one if the previous first trial was accepted, 0 never.  Same iterates either way
+ *   "normals_memo"      fast kernel: answer from memory what a pass would return bit for bit -- 1: trial points whose fp32
+ *                       coefficients equal the iterate's; 2 (default): also Jacobian requests at such points (SSD cost);
+ *                       0: evaluate everything
  *   "normals_groups"    fast kernel: independent feature pipelines per CTA: 1, 2, or 0 (default:
  *                       2 when there are more features than SMs and the layout fits)
  *   "normals_sweep_batch"  fast kernel, fm3d_sweep_normals: 4 (default) evaluates four candidate normals per

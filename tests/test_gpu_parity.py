@@ -662,8 +662,9 @@ def test_optimize_normals_large_disc_r128(ctx):
 
 
 def test_fast_kernel_schedule_options_do_not_change_results(ctx):
-    """Fusing the first trial with its Jacobian and answering coefficient-identical trials without a
-    pass are exact: same evaluations counted, bit-identical normals."""
+    """Evaluating the Jacobian together with a trial (every trial by default; the first of an iteration only; adaptively; never)
+    and answering coefficient-identical trial points and Jacobian requests from memory (both by default; trials only; nothing)
+    are exact: same evaluations counted, bit-identical normals, and every weaker setting costs passes."""
     case = stereo_case(640, 480, 40, 1001, 32)
     setup_ctx(ctx, case, 2)
     xyz = case["X"]
@@ -671,18 +672,20 @@ def test_fast_kernel_schedule_options_do_not_change_results(ctx):
     try:
         base = ctx.optimize_normals(xyz, 32, 1e-10, 1)
         st0 = ctx.normals_stats()
-        for key in ("normals_fuse", "normals_memo"):
-            ctx.set_option(key, 0)
-            try:
-                alt = ctx.optimize_normals(xyz, 32, 1e-10, 1)
-                st = ctx.normals_stats()
-            finally:
-                ctx.set_option(key, 1)
-            np.testing.assert_array_equal(alt["nfev"], base["nfev"])
-            np.testing.assert_array_equal(alt["normals"], base["normals"])
-            np.testing.assert_array_equal(alt["status"], base["status"])
-            passes = lambda s_: s_["passes_value"] + s_["passes_jacobian"] + s_["passes_fused"]
-            assert passes(st) > passes(st0)          # the option did save passes
+        passes = lambda s_: s_["passes_value"] + s_["passes_jacobian"] + s_["passes_fused"]
+        for key, values, default in (("normals_fuse", (0, 1, 2), 3), ("normals_memo", (0, 1), 2)):
+            for v in values:
+                ctx.set_option(key, v)
+                try:
+                    alt = ctx.optimize_normals(xyz, 32, 1e-10, 1)
+                    st = ctx.normals_stats()
+                finally:
+                    ctx.set_option(key, default)
+                np.testing.assert_array_equal(alt["nfev"], base["nfev"])
+                np.testing.assert_array_equal(alt["normals"], base["normals"])
+                np.testing.assert_array_equal(alt["status"], base["status"])
+                print(key, v, "passes", passes(st), "default", passes(st0))
+                assert passes(st) > passes(st0)          # the default did save passes
     finally:
         ctx.set_option("normals_groups", 0)
     assert st0["trials_memoized"] > 0 and st0["fused_accepted"] > 0
