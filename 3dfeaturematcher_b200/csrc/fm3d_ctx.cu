@@ -227,6 +227,7 @@ static int* fm3d_option_slot(fm3d_ctx* ctx, const char* key) {
     if (!strcmp(key, "normals_memo")) return &ctx->opt_normals_memo;
     if (!strcmp(key, "normals_groups")) return &ctx->opt_normals_groups;
     if (!strcmp(key, "normals_pingpong")) return &ctx->opt_normals_pingpong;
+    if (!strcmp(key, "normals_level_sync")) return &ctx->opt_normals_level_sync;
     if (!strcmp(key, "normals_sweep_batch")) return &ctx->opt_normals_sweep_batch;
     if (!strcmp(key, "matcher_exact_fallback")) return &ctx->n_matcher_exact_fallback;   // read-out of the last float match
     return nullptr;

@@ -52,6 +52,7 @@ struct fm3d_ctx {
     int opt_lm_patience = 100;
     int opt_normals_threads = 512;
     int opt_normals_tma = 1;
+    int opt_normals_level_sync = 0; // two-slot kernel: the warps of a slot wait at the end of a level set-up until its LM warp has started the level (0: they go on)
     int opt_normals_pingpong = 1;  // fast kernel, four-window layout, mode 0: two features per eight warps taking turns (normals_pp_kernel)
     int opt_normals_groups = 0;    // fast kernel: feature pipelines per CTA; 0 = automatic (2 when there are more features than SMs)
     int opt_normals_memo = 2;      // fast kernel: 1 = trials whose fp32 coefficients equal the iterate's are not re-evaluated, 2 = nor are Jacobian requests (SSD)

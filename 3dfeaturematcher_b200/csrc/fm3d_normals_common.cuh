@@ -63,6 +63,7 @@ struct NormalsArgs {
     int win_tma[FM3D_MAX_LEVELS];       // fast kernel: level window loaded by one TMA tile
     int fuse_trials;                    // fast kernel: evaluate the Jacobian with the first trial
     int memo_trials;                    // fast kernel: answer coefficient-identical trials without a pass
+    int level_sync;                     // two-slot kernel: 1 = the shared warps wait for the LM warp's start of a level at the end of the level set-up
     int sweep_batch;                    // fast kernel, mode 2: > 1 evaluates the candidate grid in batches of SWEEP_B per pass
     int cost_mode;                      // fast kernel: FM3D_COST_SSD (the reference) / FM3D_COST_NCC
     int groups;                         // fast kernel: independent feature pipelines per CTA (1 or 2)

@@ -1072,7 +1072,7 @@ __device__ FM3D_SETUP_INLINE FeatureLocals feature_prologue(const NormalsArgs& A
 template <bool ncc>
 __device__ FM3D_SETUP_INLINE unsigned level_setup(const NormalsArgs& A, GroupCtl& G, uint8_t* win, float* i1, const int f, const int lvl,
                                                 const FeatureLocals& F, const int tid, const int NT, const int groups, const int g,
-                                                LevelConst& L_out) {
+                                                LevelConst& L_out, const bool final_sync = true) {
     const fm3d_cam& cam = A.cam;
     const int r = A.r;
     const double cu = F.cu, cv = F.cv;
@@ -1249,7 +1249,9 @@ __device__ FM3D_SETUP_INLINE unsigned level_setup(const NormalsArgs& A, GroupCtl
             publish_pass(PP, S, cam, phi, theta, PASS_VALUE, A.penalty_mode, 1e-5, lane);
         }
     }
-    gsync(groups, g, NT);
+    // two-slot kernel with normals_level_sync = 0: the shared warps do not wait for the LM warp's start of the level -- the next
+    // turn of the slot opens with the slot's barrier, after the LM warp has announced it (slot_ready)
+    if (final_sync) gsync(groups, g, NT);
 
     if (tid == 0) S->stats[15] += (unsigned long long)(clock64() - t_l0);   // level set-up: window + image-1 samples
     L_out = L;
@@ -1721,7 +1723,7 @@ normals_pp_kernel(const __grid_constant__ NormalsArgs A) {
                 const int lvl = G.lvl;
                 if (tid == 0) G.lvl_flags = 0u;
                 LevelConst L;
-                const unsigned lf = level_setup<ncc>(A, G, win, i1, f, lvl, F, tid, NT, 2, BAR, L);   // ends with the slot's barrier
+                const unsigned lf = level_setup<ncc>(A, G, win, i1, f, lvl, F, tid, NT, 2, BAR, L, A.level_sync != 0);
                 if (lf) atomicOr(&G.lvl_flags, lf);
                 if (tid == 0) { G.Lsave = L; G.kind = STEP_PASS; }
                 if (rank == 0) slot_ready(G, lane);
@@ -1829,6 +1831,7 @@ int run_normals_fast(fm3d_ctx* ctx, NormalsArgs& A) {
     A.use_tma = ctx->opt_normals_tma;
     A.fuse_trials = ctx->opt_normals_fuse;
     A.memo_trials = ctx->opt_normals_memo;
+    A.level_sync = ctx->opt_normals_level_sync;
     A.sweep_batch = ctx->opt_normals_sweep_batch;
     A.cost_mode = ctx->opt_normals_cost;
     if (A.cost_mode == FM3D_COST_NCC && A.mode == 2)

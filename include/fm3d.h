@@ -131,6 +131,8 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *   "normals_memo"      fast kernel: answer from memory what a pass would return bit for bit -- 1: trial points whose fp32
  *                       coefficients equal the iterate's; 2 (default): also Jacobian requests at such points (SSD cost);
  *                       0: evaluate everything
+ *   "normals_level_sync" two-slot kernel: 1 = the warps of a slot wait at the end of a level set-up until the slot's LM warp has
+ *                       started the level's LM; 0 (default) = they go on to the partner slot (same results)
  *   "normals_groups"    fast kernel: independent feature pipelines per CTA: 1, 2, or 0 (default:
  *                       2 when there are more features than SMs and the layout fits)
  *   "normals_sweep_batch"  fast kernel, fm3d_sweep_normals: 4 (default) evaluates four candidate normals per
