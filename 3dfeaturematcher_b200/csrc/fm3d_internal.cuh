@@ -55,7 +55,7 @@ struct fm3d_ctx {
     int opt_normals_level_sync = 0; // two-slot kernel: the warps of a slot wait at the end of a level set-up until its LM warp has started the level (0: they go on)
     int opt_normals_pingpong = 1;  // fast kernel, four-window layout, mode 0: two features per eight warps taking turns (normals_pp_kernel)
     int opt_normals_groups = 0;    // fast kernel: feature pipelines per CTA; 0 = automatic (2 when there are more features than SMs)
-    int opt_normals_memo = 2;      // fast kernel: 1 = trials whose fp32 coefficients equal the iterate's are not re-evaluated, 2 = nor are Jacobian requests (SSD)
+    int opt_normals_memo = 3;      // fast kernel: 1 = trials whose fp32 coefficients equal the iterate's are not re-evaluated, 2 = nor are Jacobian requests (SSD), 3 = nor requests at the coefficients of one of the level's last four Jacobian passes
     int opt_normals_fuse = 3;      // fast kernel: Jacobian evaluated together with a trial: 1 = the first trial of an iteration, 2 = that, if the last one was accepted, 3 = every trial
     int opt_normals_sweep_batch = 4;  // fast kernel, dense sweep: candidates per pass (1: one pass per candidate)
     int opt_normals_fast = 1;      // 1: fm3d_normals_fast.cu (default), 0: the faithful fp64 kernel

@@ -121,9 +121,15 @@ struct FastShared {
     float hbase[9];     // value coefficients (FastPass::h) of the current LM iterate ...
     double s0_base;     // ... and the residual sum the pass at the iterate returned
     int base_valid;
-    double jraw[6];     // SSD: the raw sums (residual sum, three moments of U, two U.d sums) of the last Jacobian pass evaluated ...
+    double jraw[6];     // SSD: the raw sums (residual sum, three moments of U, two U.d sums) of the last Jacobian result (a pass, or the table below) ...
     double jbase[6];    // ... and those of the pass at the iterate's coefficients, if one was evaluated (jbase_valid)
     int jbase_valid;
+    // normals_memo = 3: the last four Jacobian passes evaluated on this level, coefficients -> raw sums: in lmfit's tail the trial
+    // points fall on a handful of fp32 coefficient sets around the iterate, and a pass at one of them returns what it returned before
+    float th[4][9];
+    double ts[4][6];
+    int tvalid[4];
+    int tnext;
     int cand;           // mode 2 (sweep): candidate being evaluated
     double sweep_c[2];  // mode 2: centre (phi, theta) of the candidate grid
     double best_cost;   // mode 2: running minimum
@@ -744,6 +750,18 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                             if (ncc) ncc_sums_to_normal_equations(s, S->ncc_su, S->ncc_suu, m, P.kind == PASS_JAC);
                         }
                         any_flags = __reduce_or_sync(0xffffffffu, any_flags);
+                        if (!ncc && A.memo_trials >= 3 && A.mode == 0 && P.kind == PASS_JAC && any_flags == 0u) {
+                            const int e = S->tnext;         // a clean Jacobian pass: remember what it returned
+                            __syncwarp();
+                            if (lane < 9) S->th[e][lane] = PP->h[lane];     // (P.h[lane] would put the register copy of the pass on the stack)
+                            if (lane == 0) {
+    #pragma unroll
+                                for (int k = 0; k < 6; k++) S->ts[e][k] = S->jraw[k];
+                                S->tvalid[e] = 1;
+                                S->tnext = (e + 1) & 3;
+                            }
+                            __syncwarp();
+                        }
                         const long long t_r = clock64();
                         long long t_lm = 0;
                         // `memo`: the result in s[0] was not evaluated but taken from the base point: the
@@ -752,6 +770,7 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                         // in lmfit's tail (steps below 1e-8 rad, tolerances of 30 eps) this is what every
                         // trial does; those trials are answered here without a pass.
                         bool memo = false;
+                        bool from_table = false;    // memo, answered from the table of earlier passes (value and Jacobian sums of another point than the iterate)
                         bool slow_pass = P.slow != 0;
                         int pass_kind = P.kind;
                         for (;;) {
@@ -808,7 +827,7 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                                         first_trial = true;
                                         S->s0_base = s[0];      // sum and coefficients of the iterate
                                         take_base = 1;
-                                        if (!memo && !ncc) {    // ... and the raw Jacobian sums of the pass at them
+                                        if ((!memo || from_table) && !ncc) {    // ... and the raw Jacobian sums of the pass at them
     #pragma unroll
                                             for (int k = 0; k < 6; k++) S->jbase[k] = S->jraw[k];
                                             S->jbase_valid = 1;
@@ -819,7 +838,7 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                                         cmd = fm3d_lm2_after_trial(&lm, S->w[0] * S->w[0] * s[0]);
                                         const bool accepted = lm.iter != iter_before;
                                         if (S->trial_is_first) S->fuse_hint = accepted ? 1 : 0;
-                                        if (!memo && accepted) {   // new iterate
+                                        if ((!memo || from_table) && accepted) {   // new iterate
                                             S->s0_base = s[0];
                                             take_base = 1;
                                             if (where == AT_XT_FUSED && !ncc) {   // its Jacobian sums came with the trial
@@ -880,9 +899,26 @@ __device__ __forceinline__ void lm_advance(const NormalsArgs& A, GroupCtl& G, co
                             bool same = S->base_valid != 0 && A.memo_trials && (!at_jac || (A.memo_trials >= 2 && !ncc && S->jbase_valid != 0));
                             if (lane < 9) same = same && (PP->h[lane] == S->hbase[lane]);
                             same = __all_sync(0xffffffffu, same);
-                            if (!same) break;                       // run the pass
+                            int hit = -1;                           // normals_memo = 3: a pass at these coefficients evaluated earlier on this level?
+                            if (!same && A.memo_trials >= 3 && !ncc && PP->kind == PASS_JAC) {
+                                for (int e = 0; e < 4 && hit < 0; e++) {
+                                    bool eq = S->tvalid[e] != 0;
+                                    if (lane < 9) eq = eq && (PP->h[lane] == S->th[e][lane]);
+                                    if (__all_sync(0xffffffffu, eq)) hit = e;
+                                }
+                            }
+                            if (!same && hit < 0) break;            // run the pass
                             memo = true;
-                            if (at_jac) {
+                            from_table = !same;
+                            if (!same) {
+                                // value and Jacobian sums of the earlier pass; S->where stays (a fused trial, or the Jacobian at x)
+    #pragma unroll
+                                if (lane < 6) S->jraw[lane] = S->ts[hit][lane];    // they are "the raw sums of the last Jacobian result" now
+                                __syncwarp();
+    #pragma unroll
+                                for (int k = 0; k < 6; k++) s[k] = S->jraw[k];
+                                jacobian_sums_from_moments(s, S->sg, false);
+                            } else if (at_jac) {
     #pragma unroll
                                 for (int k = 0; k < 6; k++) s[k] = S->jbase[k];
                                 jacobian_sums_from_moments(s, S->sg, false);
@@ -1219,7 +1255,7 @@ __device__ FM3D_SETUP_INLINE unsigned level_setup(const NormalsArgs& A, GroupCtl
                 PP->slow = 0;
                 fm3d_lm2_init(&S->lm, phi, theta, A.eps_lmmin, A.patience);
                 S->where = AT_X_JAC;
-                S->base_valid = 0; S->jbase_valid = 0;
+                S->base_valid = 0; S->jbase_valid = 0; S->tnext = 0; S->tvalid[0] = S->tvalid[1] = S->tvalid[2] = S->tvalid[3] = 0;
                 S->fuse_hint = 1;
             }
             publish_pass(PP, S, cam, phi, theta, PASS_JAC, A.penalty_mode, sqrt(fmax(A.eps_lmmin, FM3D_DBL_EPS)), lane);
@@ -1236,7 +1272,7 @@ __device__ FM3D_SETUP_INLINE unsigned level_setup(const NormalsArgs& A, GroupCtl
                 S->lm.nfev = 0;
                 S->lm.eps = 1e-5;
                 S->where = AT_XT_PLAIN;
-                S->base_valid = 0; S->jbase_valid = 0;
+                S->base_valid = 0; S->jbase_valid = 0; S->tnext = 0; S->tvalid[0] = S->tvalid[1] = S->tvalid[2] = S->tvalid[3] = 0;
                 S->cand = 0;
                 S->sweep_c[0] = phi; S->sweep_c[1] = theta;
                 S->best_cost = __longlong_as_double(0x7ff0000000000000LL);

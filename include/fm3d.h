@@ -129,8 +129,9 @@ int fm3d_device_info(fm3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *                       next LM iteration without another pass: 3 (default) every trial, 1 the first trial of an iteration
  *                       only, 2 that one if the previous first trial was accepted, 0 never.  Same iterates either way
  *   "normals_memo"      fast kernel: answer from memory what a pass would return bit for bit -- 1: trial points whose fp32
- *                       coefficients equal the iterate's; 2 (default): also Jacobian requests at such points (SSD cost);
- *                       0: evaluate everything
+ *                       coefficients equal the iterate's; 2: also Jacobian requests at such points (SSD cost); 3 (default):
+ *                       also trial / Jacobian requests whose coefficients equal those of one of the last four Jacobian
+ *                       passes of the level; 0: evaluate everything
  *   "normals_level_sync" two-slot kernel: 1 = the warps of a slot wait at the end of a level set-up until the slot's LM warp has
  *                       started the level's LM; 0 (default) = they go on to the partner slot (same results)
  *   "normals_groups"    fast kernel: independent feature pipelines per CTA: 1, 2, or 0 (default:

@@ -13,7 +13,7 @@ ctx = api.Context(0)
 ctx.set_camera(cam.K, cam.dist, cam.z_min, cam.z_max); ctx.set_g12(cam.g12)
 ctx.set_images(case["scene"].img1, case["scene"].img2, pyr)
 xyz = np.ascontiguousarray(case["X"])
-base = dict(normals_fast=1, normals_pingpong=1, normals_memo=2, normals_fuse=3, normals_groups=0)
+base = dict(normals_fast=1, normals_pingpong=1, normals_memo=3, normals_fuse=3, normals_groups=0)
 ref = None
 cfgs = [dict(), dict(normals_pingpong=0), dict(normals_memo=0), dict(normals_fuse=0), dict(normals_fast=0)]
 if os.environ.get("FM3D_DIAG_SHORT"):

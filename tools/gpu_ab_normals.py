@@ -18,7 +18,7 @@ normals = torch.empty((n, 3), dtype=torch.float64, device=dev); status = torch.e
 nfev = torch.zeros((n, 4), dtype=torch.int32, device=dev); npen = torch.zeros(n, dtype=torch.int32, device=dev); cost = torch.empty(n, dtype=torch.float64, device=dev)
 configs = [json.loads(a) for a in sys.argv[2:]] or [dict(normals_groups=1), dict(normals_groups=4)]; sys.argv = sys.argv[:2]
 configs += [json.loads(a) for a in sys.argv[2:]]
-base = dict(normals_fast=1, normals_memo=2, normals_fuse=3, normals_threads=512, normals_groups=0)
+base = dict(normals_fast=1, normals_memo=3, normals_fuse=3, normals_threads=512, normals_groups=0)
 for pen in (1, 0):
     ref = None
     for cfg in configs:
