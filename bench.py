@@ -756,7 +756,8 @@ def run_gpu_arm(args):
             "traffic_algorithmic": n_inl * 44e3,
             "note": "compute-bound kernel; achieved = ALGORITHMIC flops of SURVEY 8(d) (64 flop x sum over features and levels of "
                     "nfev x m pixel evaluations, nfev = what lmfit evaluates with its forward-difference Jacobian: 1 per trial, "
-                    "2 per Jacobian) / CUDA-event time of the launch; peak = measured FFMA rate (tools/micro/ffma2_rate.cu: "
+                    "2 per Jacobian -- including the evaluations the kernel answers from memory because their fp32 coefficients equal those of a "
+                    "pass already evaluated: `trials_memoized`) / CUDA-event time of the launch; peak = measured FFMA rate (tools/micro/ffma2_rate.cu: "
                     "73.96 TFLOP/s = 99.3 % of SMs*128*2*f_max; MEASURED_PEAKS.json has no fp32 figure).  `executed` is what the "
                     "kernel itself issues: 58 flop per pixel of a value-only pass, 113 per pixel of a value + analytic-Jacobian "
                     "pass, counted by the kernel (rounds 1 and 2a reported that figure as `frac`, with 64 / 152).  HBM traffic is "
@@ -764,7 +765,7 @@ def run_gpu_arm(args):
             "achieved_executed": achieved_exec, "frac_executed": achieved_exec / fp32_peak,
             "pixel_evals_value": stats["pixel_evals_value"], "pixel_evals_jacobian": stats["pixel_evals_jacobian"],
             "passes": n_pass, "passes_fused": stats["passes_fused"], "fused_accepted": stats["fused_accepted"],
-            "passes_global_taps": stats["passes_slow"],
+            "passes_global_taps": stats["passes_slow"], "trials_memoized": stats.get("trials_memoized"),
             "reference_equivalent_pixel_evals": pixel_evals_ref,
             "reference_equivalent_tflops": achieved,
             "frac_reference_equivalent": achieved / fp32_peak,
